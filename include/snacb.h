@@ -1,0 +1,159 @@
+/* snacb -- B200-native SNAC 24 kHz decode for Orpheus/Canopy audio-token streams.  C ABI.
+ *
+ * This is the drop-in boundary for ONE path of Demon-Sheriff/tts-inference: token window ->
+ * SNAC codes -> VQ decode -> conv decoder -> int16 PCM.  The reference has no FFI of its own
+ * (it is pure Python calling the pip package `snac`); every entry point below names the
+ * reference code it replaces.  Plain pointers and sizes only, no torch / C++ types.
+ *
+ * Conventions
+ *   - all functions return 0 on success, a negative snacb_status otherwise; they never abort
+ *     and never throw; snacb_last_error(h) gives the text of the last failure on a handle;
+ *   - pointers are DEVICE pointers unless the name ends in `_host`;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - a handle is bound to one GPU and is not re-entrant: one caller at a time (the reference
+ *     serialises callers with a global asyncio.Lock, vllm_inference/modal_audio_stream.py:83).
+ */
+#ifndef SNACB_H_
+#define SNACB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SNACB_VERSION 100
+
+typedef struct snacb_handle_s* snacb_handle;
+typedef struct snacb_batcher_s* snacb_batcher;
+
+typedef enum {
+    SNACB_OK = 0,
+    SNACB_ERR_ARG = -1,      /* bad argument (null pointer, negative size, ...)            */
+    SNACB_ERR_CUDA = -2,     /* a CUDA call failed; see snacb_last_error                    */
+    SNACB_ERR_NO_GPU = -3,   /* no CUDA device / device is not sm_100                       */
+    SNACB_ERR_STATE = -4,    /* call not valid in the handle's current state                */
+    SNACB_ERR_NOMEM = -5
+} snacb_status;
+
+/* decode flags */
+#define SNACB_RAW_IDS        0x1   /* tokens are raw LLM ids; subtract 128266 on device
+                                      (modal_audio_stream.py:103,366).  Otherwise they are
+                                      already `id - 128266`, as convert_to_audio receives them */
+#define SNACB_EXTRACT_SLICE  0x2   /* keep samples [2048:4096] when more than 4096 were decoded
+                                      (modal_audio_stream.py:94-95,195-198)                    */
+#define SNACB_FP32           0x4   /* fp32 CUDA-core arithmetic end to end (config 1);
+                                      default is bf16 tensor-core contractions, fp32 accumulate */
+#define SNACB_KEEP_TAPS      0x8   /* debug: keep every stage's output for snacb_debug_tap     */
+#define SNACB_STREAM_FP32    0x10  /* bf16 path: keep the residual stream in fp32 between kernels */
+
+/* Folded fp32 weights of the decode half of snac_24khz, host pointers.  Weight-norm is already
+ * folded (w = g * v / ||v||, norm over dim 0: per OUTPUT channel for Conv1d, per INPUT channel for
+ * ConvTranspose1d); the reference recomputes that on every forward (snac WNConv1d), we fold once at
+ * load (init_snac, modal_audio_stream.py:106-129).  Layouts are the PyTorch ones. */
+typedef struct {
+    const float* alpha1;   /* [C]        ResidualUnit.block.0 Snake alpha            */
+    const float* dw_w;     /* [C][1][7]  ResidualUnit.block.1 depthwise conv weight  */
+    const float* dw_b;     /* [C]                                                     */
+    const float* alpha2;   /* [C]        ResidualUnit.block.2 Snake alpha            */
+    const float* pw_w;     /* [C][C][1]  ResidualUnit.block.3 1x1 conv weight         */
+    const float* pw_b;     /* [C]                                                     */
+} snacb_resunit_weights;
+
+typedef struct {
+    const float* alpha;    /* [Cin]           DecoderBlock.block.0 Snake alpha        */
+    const float* convt_w;  /* [Cin][Cout][2s] DecoderBlock.block.1 ConvTranspose1d    */
+    const float* convt_b;  /* [Cout]                                                  */
+    const float* noise_w;  /* [Cout][Cout][1] DecoderBlock.block.2 NoiseBlock.linear (no bias) */
+    snacb_resunit_weights res[3];   /* dilations 1, 3, 9                              */
+} snacb_block_weights;
+
+typedef struct {
+    const float* codebook[3];    /* [4096][8]     quantizer.quantizers.i.codebook.weight   */
+    const float* out_proj_w[3];  /* [768][8][1]   quantizer.quantizers.i.out_proj (folded) */
+    const float* out_proj_b[3];  /* [768]                                                   */
+    const float* stem_dw_w;      /* [768][1][7]   decoder.model.0                           */
+    const float* stem_dw_b;      /* [768]                                                   */
+    const float* stem_pw_w;      /* [1024][768][1] decoder.model.1                          */
+    const float* stem_pw_b;      /* [1024]                                                  */
+    snacb_block_weights block[4];/* decoder.model.2..5: 1024->512 s8, ->256 s8, ->128 s4, ->64 s2 */
+    const float* tail_alpha;     /* [64]          decoder.model.6                           */
+    const float* tail_w;         /* [1][64][7]    decoder.model.7                           */
+    const float* tail_b;         /* [1]                                                     */
+} snacb_weights;
+
+int snacb_version(void);
+
+/* Replaces init_snac() (modal_audio_stream.py:106-129) / load_models (tensorrt_tts/inference.py:152-165):
+ * uploads and packs the weights on GPU `device` (fp32 copies, bf16 K-major copies for the tensor-core
+ * path, ConvTranspose weights re-indexed per output phase).  Fails with SNACB_ERR_NO_GPU when there
+ * is no sm_100 device -- there is no CPU fallback. */
+int snacb_create(snacb_handle* out, const snacb_weights* w, int device);
+void snacb_destroy(snacb_handle h);
+const char* snacb_last_error(snacb_handle h);   /* h may be NULL: error of the last failed create */
+
+/* Token -> code redistribution only (modal_audio_stream.py:156-188; redistribute_codes,
+ * tensorrt_tts/inference.py:54-93).  tok is [B][ntok] int32, the first 7*(ntok/7) entries of each row
+ * are used; c0 [B][F], c1 [B][2F], c2 [B][4F] int32 with F = ntok/7.  Bit-exact. */
+int snacb_unpack(snacb_handle h, const int32_t* tok, int B, int ntok, int flags,
+                 int32_t* c0, int32_t* c1, int32_t* c2, void* stream);
+
+/* The whole helper, batched: convert_to_audio (modal_audio_stream.py:132-202) / decode_snac
+ * (tensorrt_tts/inference.py:96-112) for B independent token rows of `frames` frames each.
+ *   tok        [B][tok_stride] int32 (tok_stride >= 7*frames)
+ *   noise      NULL -> NoiseBlock noise from the built-in counter RNG keyed by (seed, stream, block, t);
+ *              else 4 device pointers, float [B][frames*4*{8,64,256,512}] (one scalar per (stream, t))
+ *   pcm        int16 [B][n] with n = 2048 if SNACB_EXTRACT_SLICE and frames*2048 > 4096, else frames*2048
+ *   wave       optional float [B][n], the tanh output before quantisation (parity checks)
+ * Asynchronous on `stream`; no host synchronisation inside. */
+int snacb_decode(snacb_handle h, const int32_t* tok, int B, int tok_stride, int frames, int flags,
+                 const float* const* noise, uint64_t seed, int16_t* pcm, float* wave, void* stream);
+
+/* Same with HOST buffers (pinned or pageable): copies the tokens in, decodes, copies the PCM out and
+ * synchronises -- the boundary the reference's helper has (torch.tensor(..., device=) in,
+ * .cpu().numpy().tobytes() out; modal_audio_stream.py:176-202). */
+int snacb_decode_host(snacb_handle h, const int32_t* tok_host, int B, int tok_stride, int frames, int flags,
+                      uint64_t seed, int16_t* pcm_host);
+
+/* Number of PCM samples per stream that snacb_decode writes for (frames, flags). */
+int snacb_samples_out(int frames, int flags);
+
+/* Workspace policy: streams are processed in groups sized so that one activation buffer stays under
+ * `bytes` (default 48 MiB: two of them sit in the 126 MB L2).  0 keeps the current value. */
+int snacb_set_group_bytes(snacb_handle h, size_t bytes);
+
+/* Counters since creation: kernels launched by this library, streams decoded. */
+int snacb_stats(snacb_handle h, uint64_t* kernel_launches, uint64_t* streams_decoded);
+
+/* Debug taps (SNACB_KEEP_TAPS): stage outputs of the LAST group decoded, converted to fp32,
+ * channel-last [rows][cols].  names: "stem_dw","stem","b{0..3}.convt","b{i}.noise","b{i}.res{0..2}". */
+int snacb_debug_tap_count(snacb_handle h);
+int snacb_debug_tap_info(snacb_handle h, int idx, char* name, int name_cap, int64_t* rows, int64_t* cols);
+int snacb_debug_tap_copy(snacb_handle h, int idx, float* dst_host, size_t dst_elems);
+
+/* ---------------------------------------------------------------------------------------------
+ * Batcher: the multi-stream replacement of stream_audio's per-stream buffer policy
+ * (modal_audio_stream.py:352-396), which decodes one stream at a time under a global lock.
+ * Many producers push token ids; flush() packs every ready window of every stream into ONE decode.
+ *   policy 0 (chunk)  : the shipped rule -- pop 28 codes, decode, emit all 8192 samples; at end of
+ *                       stream decode the remaining whole frames.
+ *   policy 1 (sliding): the rule the constants describe (modal_audio_stream.py:86-95) -- once 28 codes
+ *                       are buffered, every 7 new codes decode the last 28 and emit samples [2048:4096].
+ * --------------------------------------------------------------------------------------------- */
+int snacb_batcher_create(snacb_batcher* out, snacb_handle h, int policy, int flags, int max_windows);
+void snacb_batcher_destroy(snacb_batcher b);
+/* Append n raw token ids (flags & SNACB_RAW_IDS) or codes to a stream; thread-safe. */
+int snacb_batcher_push(snacb_batcher b, uint64_t stream_id, const int32_t* tokens_host, int n);
+/* Mark a stream finished: policy 0 queues its remaining whole frames. */
+int snacb_batcher_end(snacb_batcher b, uint64_t stream_id);
+/* Decode every ready window in one launch sequence.  Returns the number of chunks produced (>= 0)
+ * or a negative status.  Chunk i: stream ids[i], PCM at pcm_host + offsets[i], lengths[i] samples. */
+int snacb_batcher_flush(snacb_batcher b, uint64_t seed, int max_chunks, uint64_t* ids, int64_t* offsets,
+                        int32_t* lengths, int16_t* pcm_host, size_t pcm_capacity);
+int snacb_batcher_pending(snacb_batcher b);     /* windows ready to decode right now */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SNACB_H_ */

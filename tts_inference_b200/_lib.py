@@ -1,0 +1,104 @@
+"""ctypes binding of ``libsnacb.so`` (include/snacb.h).  No fallback: if the CUDA library is
+missing or cannot be loaded, importing callers get a RuntimeError."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Dict
+
+import numpy as np
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG, "libsnacb.so")
+
+RAW_IDS, EXTRACT_SLICE, FP32, KEEP_TAPS, STREAM_FP32 = 0x1, 0x2, 0x4, 0x8, 0x10
+
+_FP = C.POINTER(C.c_float)
+
+
+class ResUnitWeights(C.Structure):
+    _fields_ = [(n, _FP) for n in ("alpha1", "dw_w", "dw_b", "alpha2", "pw_w", "pw_b")]
+
+
+class BlockWeights(C.Structure):
+    _fields_ = [("alpha", _FP), ("convt_w", _FP), ("convt_b", _FP), ("noise_w", _FP), ("res", ResUnitWeights * 3)]
+
+
+class Weights(C.Structure):
+    _fields_ = [
+        ("codebook", _FP * 3), ("out_proj_w", _FP * 3), ("out_proj_b", _FP * 3),
+        ("stem_dw_w", _FP), ("stem_dw_b", _FP), ("stem_pw_w", _FP), ("stem_pw_b", _FP),
+        ("block", BlockWeights * 4),
+        ("tail_alpha", _FP), ("tail_w", _FP), ("tail_b", _FP),
+    ]
+
+
+EXPORTS = [
+    "snacb_version", "snacb_create", "snacb_destroy", "snacb_last_error", "snacb_unpack", "snacb_decode",
+    "snacb_decode_host", "snacb_samples_out", "snacb_set_group_bytes", "snacb_stats",
+    "snacb_debug_tap_count", "snacb_debug_tap_info", "snacb_debug_tap_copy",
+    "snacb_batcher_create", "snacb_batcher_destroy", "snacb_batcher_push", "snacb_batcher_end",
+    "snacb_batcher_flush", "snacb_batcher_pending",
+]
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -m tts_inference_b200.build` "
+            "(nvcc, sm_100a).  There is no CPU or PyTorch fallback for this path.")
+    lib = C.CDLL(LIB_PATH)
+    vp, i32p, i16p, u64 = C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64
+    lib.snacb_version.restype = C.c_int
+    lib.snacb_create.argtypes = [C.POINTER(vp), C.POINTER(Weights), C.c_int]
+    lib.snacb_destroy.argtypes = [vp]
+    lib.snacb_destroy.restype = None
+    lib.snacb_last_error.argtypes = [vp]
+    lib.snacb_last_error.restype = C.c_char_p
+    lib.snacb_unpack.argtypes = [vp, i32p, C.c_int, C.c_int, C.c_int, i32p, i32p, i32p, vp]
+    lib.snacb_decode.argtypes = [vp, i32p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp), u64, i16p, vp, vp]
+    lib.snacb_decode_host.argtypes = [vp, i32p, C.c_int, C.c_int, C.c_int, C.c_int, u64, i16p]
+    lib.snacb_samples_out.argtypes = [C.c_int, C.c_int]
+    lib.snacb_set_group_bytes.argtypes = [vp, C.c_size_t]
+    lib.snacb_stats.argtypes = [vp, C.POINTER(u64), C.POINTER(u64)]
+    lib.snacb_debug_tap_count.argtypes = [vp]
+    lib.snacb_debug_tap_info.argtypes = [vp, C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    lib.snacb_debug_tap_copy.argtypes = [vp, C.c_int, vp, C.c_size_t]
+    lib.snacb_batcher_create.argtypes = [C.POINTER(vp), vp, C.c_int, C.c_int, C.c_int]
+    lib.snacb_batcher_destroy.argtypes = [vp]
+    lib.snacb_batcher_destroy.restype = None
+    lib.snacb_batcher_push.argtypes = [vp, u64, vp, C.c_int]
+    lib.snacb_batcher_end.argtypes = [vp, u64]
+    lib.snacb_batcher_flush.argtypes = [vp, u64, C.c_int, vp, vp, vp, vp, C.c_size_t]
+    lib.snacb_batcher_pending.argtypes = [vp]
+    _lib = lib
+    return lib
+
+
+def make_weights(folded: Dict[str, np.ndarray]):
+    """``snacb_weights`` struct pointing into ``folded`` (returned alongside to keep it alive)."""
+    def p(k):
+        a = folded[k]
+        assert a.dtype == np.float32 and a.flags["C_CONTIGUOUS"], k
+        return a.ctypes.data_as(_FP)
+    w = Weights()
+    for i in range(3):
+        w.codebook[i] = p(f"codebook{i}")
+        w.out_proj_w[i] = p(f"out_proj_w{i}")
+        w.out_proj_b[i] = p(f"out_proj_b{i}")
+    w.stem_dw_w, w.stem_dw_b = p("stem_dw_w"), p("stem_dw_b")
+    w.stem_pw_w, w.stem_pw_b = p("stem_pw_w"), p("stem_pw_b")
+    for bi in range(4):
+        b = w.block[bi]
+        b.alpha, b.convt_w, b.convt_b, b.noise_w = p(f"b{bi}.alpha"), p(f"b{bi}.convt_w"), p(f"b{bi}.convt_b"), p(f"b{bi}.noise_w")
+        for ri in range(3):
+            r = b.res[ri]
+            for n in ("alpha1", "dw_w", "dw_b", "alpha2", "pw_w", "pw_b"):
+                setattr(r, n, p(f"b{bi}.r{ri}.{n}"))
+    w.tail_alpha, w.tail_w, w.tail_b = p("tail_alpha"), p("tail_w"), p("tail_b")
+    return w

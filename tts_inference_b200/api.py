@@ -1,0 +1,179 @@
+"""Batched Python front of libsnacb: device tensors in, device tensors out, no hidden sync.
+
+PyTorch is used only for device memory and streams; every FLOP of the path runs in the
+hand-written sm_100a kernels behind the C ABI (include/snacb.h).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Mapping, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+from .weights import fold_state_dict
+
+FRAME = 7
+WINDOW = 28
+
+
+class SnacbError(RuntimeError):
+    pass
+
+
+class SnacDecoder:
+    """One handle = one GPU.  Replaces the module-global ``snac_model`` the reference's helper
+    closes over (vllm_inference/modal_audio_stream.py:79-80,106-129)."""
+
+    def __init__(self, state_dict: Mapping[str, object], device: int = 0):
+        self._lib = _lib.load()
+        self._h = C.c_void_p()
+        self.device = int(device)
+        folded = fold_state_dict(state_dict)
+        w = _lib.make_weights(folded)
+        rc = self._lib.snacb_create(C.byref(self._h), C.byref(w), self.device)
+        if rc != 0:
+            msg = self._lib.snacb_last_error(None)
+            self._h = C.c_void_p()
+            raise SnacbError(f"snacb_create failed ({rc}): {msg.decode() if msg else ''}")
+
+    # ------------------------------------------------------------------ plumbing
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.snacb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            msg = self._lib.snacb_last_error(self._h)
+            raise SnacbError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
+
+    @staticmethod
+    def _stream_ptr():
+        import torch
+        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    @staticmethod
+    def _flags(raw_ids, extract_slice, precision, keep_taps=False, stream_fp32=False) -> int:
+        if precision not in ("bf16", "fp32"):
+            raise ValueError("precision must be 'bf16' or 'fp32'")
+        f = 0
+        f |= _lib.RAW_IDS if raw_ids else 0
+        f |= _lib.EXTRACT_SLICE if extract_slice else 0
+        f |= _lib.FP32 if precision == "fp32" else 0
+        f |= _lib.KEEP_TAPS if keep_taps else 0
+        f |= _lib.STREAM_FP32 if stream_fp32 else 0
+        return f
+
+    def samples_out(self, frames: int, extract_slice: bool) -> int:
+        return int(self._lib.snacb_samples_out(int(frames), _lib.EXTRACT_SLICE if extract_slice else 0))
+
+    def set_group_bytes(self, nbytes: int):
+        self._check(self._lib.snacb_set_group_bytes(self._h, int(nbytes)), "snacb_set_group_bytes")
+
+    def stats(self) -> Tuple[int, int]:
+        a, b = C.c_uint64(), C.c_uint64()
+        self._check(self._lib.snacb_stats(self._h, C.byref(a), C.byref(b)), "snacb_stats")
+        return int(a.value), int(b.value)
+
+    # ------------------------------------------------------------------ device API
+    def unpack(self, tokens, raw_ids: bool = False):
+        """tokens: cuda int32 [B, n] -> (c0 [B,F], c1 [B,2F], c2 [B,4F]) int32, F = n // 7."""
+        import torch
+        assert tokens.is_cuda and tokens.dtype == torch.int32 and tokens.dim() == 2 and tokens.is_contiguous()
+        B, n = tokens.shape
+        F_ = n // FRAME
+        c0 = torch.empty((B, F_), dtype=torch.int32, device=tokens.device)
+        c1 = torch.empty((B, 2 * F_), dtype=torch.int32, device=tokens.device)
+        c2 = torch.empty((B, 4 * F_), dtype=torch.int32, device=tokens.device)
+        rc = self._lib.snacb_unpack(self._h, tokens.data_ptr(), B, n, _lib.RAW_IDS if raw_ids else 0,
+                                    c0.data_ptr(), c1.data_ptr(), c2.data_ptr(), self._stream_ptr())
+        self._check(rc, "snacb_unpack")
+        return c0, c1, c2
+
+    def decode(self, tokens, *, raw_ids: bool = False, extract_slice: bool = False,
+               noise: Optional[Sequence] = None, seed: int = 0, precision: str = "bf16",
+               out=None, return_wave: bool = False, keep_taps: bool = False, stream_fp32: bool = False):
+        """tokens: cuda int32 [B, n>=7F] (trailing partial frame ignored, as the helper does).
+        Returns int16 [B, samples] (and the fp32 waveform when ``return_wave``)."""
+        import torch
+        assert tokens.is_cuda and tokens.dtype == torch.int32 and tokens.dim() == 2 and tokens.is_contiguous()
+        B, n = tokens.shape
+        frames = n // FRAME
+        flags = self._flags(raw_ids, extract_slice, precision, keep_taps, stream_fp32)
+        ns = self.samples_out(frames, extract_slice)
+        if out is None:
+            out = torch.empty((B, ns), dtype=torch.int16, device=tokens.device)
+        else:
+            assert out.is_cuda and out.dtype == torch.int16 and out.is_contiguous() and out.numel() == B * ns
+        wave = torch.empty((B, ns), dtype=torch.float32, device=tokens.device) if return_wave else None
+        nz_arr = None
+        keep = []
+        if noise is not None:
+            t0 = 4 * frames
+            lens = [t0 * 8, t0 * 64, t0 * 256, t0 * 512]
+            nz_arr = (C.c_void_p * 4)()
+            for i, t in enumerate(noise):
+                t = t.reshape(B, -1)
+                assert t.is_cuda and t.dtype == torch.float32 and t.shape[1] == lens[i], (t.shape, lens[i])
+                t = t.contiguous()
+                keep.append(t)
+                nz_arr[i] = t.data_ptr()
+        rc = self._lib.snacb_decode(self._h, tokens.data_ptr(), B, n, frames, flags, nz_arr, C.c_uint64(seed),
+                                    out.data_ptr(), wave.data_ptr() if wave is not None else None, self._stream_ptr())
+        self._check(rc, "snacb_decode")
+        return (out, wave) if return_wave else out
+
+    def decode_windows(self, tokens, **kw):
+        """[B, 28] sliding windows -> int16 [B, 2048] (samples [2048:4096] of each decode)."""
+        assert tokens.shape[1] == WINDOW
+        kw.setdefault("extract_slice", True)
+        return self.decode(tokens, **kw)
+
+    def decode_full(self, tokens, **kw):
+        """[B, 7F] whole utterances -> int16 [B, 2048 F]."""
+        kw["extract_slice"] = False
+        return self.decode(tokens, **kw)
+
+    # ------------------------------------------------------------------ host API (what the helper's caller sees)
+    def decode_host(self, tokens: np.ndarray, *, raw_ids: bool = False, extract_slice: bool = False,
+                    seed: int = 0, precision: str = "bf16", out: Optional[np.ndarray] = None) -> np.ndarray:
+        tokens = np.ascontiguousarray(tokens, dtype=np.int32)
+        assert tokens.ndim == 2
+        B, n = tokens.shape
+        frames = n // FRAME
+        ns = self.samples_out(frames, extract_slice)
+        if out is None:
+            out = np.empty((B, ns), dtype=np.int16)
+        assert out.dtype == np.int16 and out.flags["C_CONTIGUOUS"] and out.size == B * ns
+        rc = self._lib.snacb_decode_host(self._h, tokens.ctypes.data, B, n, frames,
+                                         self._flags(raw_ids, extract_slice, precision), C.c_uint64(seed),
+                                         out.ctypes.data)
+        self._check(rc, "snacb_decode_host")
+        return out
+
+    def decode_host_ptr(self, tok_ptr: int, B: int, n: int, pcm_ptr: int, *, raw_ids=False, extract_slice=False,
+                        seed: int = 0, precision: str = "bf16"):
+        """Same, raw host pointers (e.g. pinned torch tensors) -- used by the benchmark's e2e leg."""
+        rc = self._lib.snacb_decode_host(self._h, tok_ptr, B, n, n // FRAME,
+                                         self._flags(raw_ids, extract_slice, precision), C.c_uint64(seed), pcm_ptr)
+        self._check(rc, "snacb_decode_host")
+
+    # ------------------------------------------------------------------ debug taps
+    def taps(self) -> Dict[str, np.ndarray]:
+        out: Dict[str, np.ndarray] = {}
+        n = self._lib.snacb_debug_tap_count(self._h)
+        for i in range(max(n, 0)):
+            name = C.create_string_buffer(64)
+            rows, cols = C.c_int64(), C.c_int64()
+            self._check(self._lib.snacb_debug_tap_info(self._h, i, name, 64, C.byref(rows), C.byref(cols)), "tap_info")
+            a = np.empty((rows.value, cols.value), dtype=np.float32)
+            self._check(self._lib.snacb_debug_tap_copy(self._h, i, a.ctypes.data, a.size), "tap_copy")
+            out[name.value.decode()] = a
+        return out

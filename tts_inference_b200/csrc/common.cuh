@@ -1,0 +1,119 @@
+// Shared device helpers and the launch-side problem descriptors of the SNAC decode path.
+#pragma once
+#include <cstdint>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+namespace snacb {
+
+constexpr int kTokenAudioBase = 128266;   // reference: vllm_inference/modal_audio_stream.py:103
+constexpr int kFrame = 7;
+constexpr int kLatent = 768;
+constexpr int kDecDim = 1024;
+constexpr int kCodebook = 4096;
+constexpr int kCodeDim = 8;
+
+// Epilogue variants of the row-GEMMs (see DESIGN.md "kernels").
+enum Epi : int {
+    EPI_BIAS = 0,        // out = acc + bias[o]                          (ConvTranspose1d)
+    EPI_BIAS_SNAKE = 1,  // out = snake(acc + bias[o]; alpha[o])         (stem 1x1 -> block-0 input)
+    EPI_NOISE = 2,       // out = y[row][o] + noise[row] * acc           (NoiseBlock)
+    EPI_RES = 3,         // out = x[row][o] + acc + bias[o]              (ResidualUnit)
+    EPI_RES_SNAKE = 4,   // out = snake(x + acc + bias; alpha[o])        (last ResidualUnit of a block)
+};
+
+// A "row GEMM with taps":  out[(s, m*up + p), o] = epi( sum_tap sum_k A[(s, m + shift(p,tap)), k] * W[(p,o), tap*K + k] )
+// with A rows outside [0, Tin) of their stream reading as zero.  Plain 1x1 convs are ntaps=1, up=1.
+struct GemmArgs {
+    int S;          // streams (windows / utterances)
+    int Tin;        // A rows per stream
+    int K;          // channels in  (per tap)
+    int N;          // total output columns = up * Cout
+    int Cout;       // channels out (per phase)
+    int ntaps;      // 1 (1x1 conv) or 2 (ConvTranspose1d, k = 2*stride)
+    int up;         // output rows per input row (ConvTranspose stride), 1 for 1x1
+    int Tbox;       // rows of one stream per 128-row tile  (Tbox * Wbox == 128)
+    int Wbox;       // streams per tile
+    const float* bias;      // [Cout] or null
+    const float* alpha;     // [Cout] snake alpha (EPI_*_SNAKE)
+    const float* inv_alpha; // [Cout] 1 / (alpha + 1e-9)
+    const float* noise;     // [S][Tin] injected noise (EPI_NOISE) or null -> counter RNG
+    unsigned long long seed;
+    int noise_stage;        // decoder block index, keys the counter RNG
+    int stream_offset;      // global index of stream 0 of this chunk (counter RNG addressing)
+    const void* resid;      // residual / y tensor, [S*Tin*up][Cout], same dtype as out
+    void* out;              // [S*Tin*up][Cout]
+};
+
+struct ResUnitArgs {
+    int S, T, C, dil;
+    const void* x;           // [S*T][C] residual stream (XT)
+    void* out;               // [S*T][C]
+    const float* alpha1; const float* inv_alpha1;   // [C]
+    const float* dw_w;       // [7][C]
+    const float* dw_b;       // [C]
+    const float* alpha2; const float* inv_alpha2;   // [C]
+    const float* pw_b;       // [C]
+    const float* alpha_next; const float* inv_alpha_next;  // [C] (EPI_RES_SNAKE)
+};
+
+// ---------------------------------------------------------------- math
+// snake(x) = x + (alpha + 1e-9)^-1 * sin(alpha x)^2   (upstream snac layers.py; oracle/snac_ref.py)
+template <bool kFast>
+__device__ __forceinline__ float snake_f(float x, float alpha, float inv_alpha) {
+    float s = kFast ? __sinf(alpha * x) : sinf(alpha * x);
+    return fmaf(inv_alpha, s * s, x);
+}
+
+// int16 quantise of the reference helper: (x*32767).clamp(-32768,32767).to(int16) -- truncation
+// toward zero (vllm_inference/modal_audio_stream.py:201; numpy astype in tensorrt_tts/inference.py:110).
+__device__ __forceinline__ int16_t pcm16(float x) {
+    float v = fminf(fmaxf(x * 32767.0f, -32768.0f), 32767.0f);
+    return static_cast<int16_t>(__float2int_rz(v));
+}
+
+// Counter-based N(0,1): splitmix64(key + counter) -> Box-Muller.  Same construction as
+// oracle/synth_ckpt.py::rng_normal (key = splitmix64(seed*0x100000001B3 + stream)).
+__host__ __device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
+    x += 0x9E3779B97F4A7C15ull;
+    unsigned long long z = x;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__device__ __forceinline__ float counter_normal(unsigned long long key, unsigned long long ctr) {
+    unsigned long long b = splitmix64(key + ctr);
+    float u1 = (static_cast<float>(static_cast<unsigned>(b >> 32)) + 0.5f) * (1.0f / 4294967296.0f);
+    float u2 = (static_cast<float>(static_cast<unsigned>(b & 0xFFFFFFFFull)) + 0.5f) * (1.0f / 4294967296.0f);
+    u1 = fminf(u1, 0.99999994f);
+    return sqrtf(-2.0f * __logf(u1)) * __cosf(6.283185307179586f * u2);
+}
+
+// ---------------------------------------------------------------- typed load / store of 8 channels
+__device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
+    float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&v)[8]) {
+    uint4 raw = *reinterpret_cast<const uint4*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+}
+__device__ __forceinline__ void store8(float* p, const float (&v)[8]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&v)[8]) {
+    uint4 raw;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&raw);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    *reinterpret_cast<uint4*>(p) = raw;
+}
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
+__device__ __forceinline__ void from_f32(float& d, float v) { d = v; }
+__device__ __forceinline__ void from_f32(__nv_bfloat16& d, float v) { d = __float2bfloat16_rn(v); }
+
+}  // namespace snacb

@@ -1,0 +1,43 @@
+// Launch-side interface between the host pipeline (snacb.cu) and the kernel translation units.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "common.cuh"
+
+namespace snacb {
+
+struct VqStemWeights {
+    const float* codebook[3];  // [4096][8]
+    const float* out_w[3];     // [768][8]
+    const float* out_b[3];     // [768]
+    const float* dw_w;         // [7][768]  (tap-major so that channels are contiguous)
+    const float* dw_b;         // [768]
+};
+
+// ---- kernels_simt.cu
+void launch_unpack(const int32_t* tok, int B, int ntok, int F, int raw_ids, int32_t* c0, int32_t* c1, int32_t* c2,
+                   cudaStream_t st);
+template <typename OutT>
+void launch_vq_stem(const int32_t* c0, const int32_t* c1, const int32_t* c2, int S, int F, const VqStemWeights& w,
+                    OutT* out, cudaStream_t st);
+void launch_gemm_f32(int epi, const GemmArgs& a, const float* A, const float* W, cudaStream_t st);
+void launch_respre_f32(const ResUnitArgs& a, float* P, cudaStream_t st);
+template <typename InT>
+void launch_tail(const InT* a, int S, int T, int t_begin, int n_out, const float* w, float bias, int16_t* pcm,
+                 float* wave, cudaStream_t st);
+template <typename T>
+void launch_to_f32(const T* in, float* out, size_t n, cudaStream_t st);
+
+// ---- kernels_tc.cu  (tcgen05 / TMEM / TMA)
+// out dtype: 0 = bf16, 1 = fp32.  Returns cudaError_t of the launch.
+int gemm_tc_block_n(const GemmArgs& a);   // column-tile width the tensor-core GEMM will use for this problem
+cudaError_t launch_gemm_tc(int epi, int out_f32, const GemmArgs& a, const CUtensorMap& tmA, const CUtensorMap& tmW,
+                           int sm_count, cudaStream_t st);
+cudaError_t launch_resunit_tc(int epi, int x_f32, const ResUnitArgs& a, const CUtensorMap& tmW, cudaStream_t st);
+cudaError_t init_tc_kernels();            // opt-in shared memory sizes
+
+}  // namespace snacb

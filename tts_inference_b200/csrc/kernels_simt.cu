@@ -1,0 +1,355 @@
+// CUDA-core kernels of the SNAC decode path (sm_100a):
+//   * k_unpack        token ids -> three code levels (integer, bit-exact)
+//   * k_vq_stem       codebook gather + out_proj + repeat-interleave + level sum + stem depthwise k7
+//   * k_gemm_f32      fp32 row-GEMM with taps (1x1 convs, ConvTranspose1d, NoiseBlock) -- fp32 precision path
+//   * k_respre_f32    Snake -> depthwise dilated k7 -> Snake (fp32 precision path)
+//   * k_tail          final conv 64->1 k7 + tanh + slice + int16 quantise
+//   * k_to_f32        debug taps
+// Activations are channel-last: [stream][time][channel].
+#include "common.cuh"
+#include "kernels.h"
+
+namespace snacb {
+
+// ----------------------------------------------------------------------------------------------
+// Token -> code unpack.  Reference: vllm_inference/modal_audio_stream.py:165-188 (offsets, clamp),
+// tensorrt_tts/inference.py:54-93.  code = clamp(id - [128266] - 4096*(p mod 7), 0, 4095);
+// p=0 -> level 0; p=1,4 -> level 1; p=2,3,5,6 -> level 2.
+// ----------------------------------------------------------------------------------------------
+__global__ void k_unpack(const int32_t* __restrict__ tok, int B, int ntok, int F, int raw_ids,
+                         int32_t* __restrict__ c0, int32_t* __restrict__ c1, int32_t* __restrict__ c2) {
+    const int per = F * kFrame;
+    const long long total = static_cast<long long>(B) * per;
+    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int b = static_cast<int>(idx / per), r = static_cast<int>(idx % per);
+        const int f = r / kFrame, p = r % kFrame;
+        long long v = static_cast<long long>(tok[static_cast<size_t>(b) * ntok + r]) -
+                      (raw_ids ? kTokenAudioBase : 0) - 4096LL * p;
+        const int c = static_cast<int>(v < 0 ? 0 : (v > 4095 ? 4095 : v));
+        const size_t bf = static_cast<size_t>(b) * F + f;
+        switch (p) {
+            case 0: c0[bf] = c; break;
+            case 1: c1[2 * bf] = c; break;
+            case 4: c1[2 * bf + 1] = c; break;
+            case 2: c2[4 * bf] = c; break;
+            case 3: c2[4 * bf + 1] = c; break;
+            case 5: c2[4 * bf + 2] = c; break;
+            default: c2[4 * bf + 3] = c; break;
+        }
+    }
+}
+
+void launch_unpack(const int32_t* tok, int B, int ntok, int F, int raw_ids, int32_t* c0, int32_t* c1, int32_t* c2,
+                   cudaStream_t st) {
+    const long long total = static_cast<long long>(B) * F * kFrame;
+    if (total == 0) return;
+    const int threads = 256;
+    const int blocks = static_cast<int>((total + threads - 1) / threads > 148 * 8 ? 148 * 8 : (total + threads - 1) / threads);
+    k_unpack<<<blocks, threads, 0, st>>>(tok, B, ntok, F, raw_ids, c0, c1, c2);
+}
+
+// ----------------------------------------------------------------------------------------------
+// VQ decode + stem depthwise conv.  Reference: snac quantizer.from_codes (oracle/snac_ref.py
+// ResidualVectorQuantize.from_codes) followed by decoder.model.0 (depthwise k7, pad 3).
+// One CTA = 16 latent steps of one stream; z_q never leaves the SM.
+// ----------------------------------------------------------------------------------------------
+constexpr int kVqTile = 16;
+
+template <typename OutT>
+__global__ void __launch_bounds__(256)
+k_vq_stem(const int32_t* __restrict__ c0, const int32_t* __restrict__ c1, const int32_t* __restrict__ c2, int F,
+          VqStemWeights w, OutT* __restrict__ out) {
+    const int T0 = 4 * F;
+    const int s = blockIdx.y, t0 = blockIdx.x * kVqTile;
+    __shared__ float emb[3][kVqTile + 6][kCodeDim];
+    __shared__ int ok[kVqTile + 6];
+    for (int idx = threadIdx.x; idx < 3 * (kVqTile + 6); idx += blockDim.x) {
+        const int lv = idx / (kVqTile + 6), u = idx % (kVqTile + 6);
+        const int t = t0 - 3 + u;
+        const bool valid = (t >= 0 && t < T0);
+        if (lv == 0) ok[u] = valid;
+        float e[kCodeDim];
+#pragma unroll
+        for (int j = 0; j < kCodeDim; ++j) e[j] = 0.f;
+        if (valid) {
+            int code;
+            if (lv == 0) code = c0[static_cast<size_t>(s) * F + (t >> 2)];
+            else if (lv == 1) code = c1[static_cast<size_t>(s) * 2 * F + (t >> 1)];
+            else code = c2[static_cast<size_t>(s) * 4 * F + t];
+            const float* cb = w.codebook[lv] + static_cast<size_t>(code) * kCodeDim;
+#pragma unroll
+            for (int j = 0; j < kCodeDim; ++j) e[j] = cb[j];
+        }
+#pragma unroll
+        for (int j = 0; j < kCodeDim; ++j) emb[lv][u][j] = e[j];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < kLatent; c += blockDim.x) {
+        float wv[3][kCodeDim];
+        float bsum = 0.f;
+#pragma unroll
+        for (int lv = 0; lv < 3; ++lv) {
+            bsum += w.out_b[lv][c];
+#pragma unroll
+            for (int j = 0; j < kCodeDim; ++j) wv[lv][j] = w.out_w[lv][c * kCodeDim + j];
+        }
+        float z[kVqTile + 6];
+#pragma unroll
+        for (int u = 0; u < kVqTile + 6; ++u) {
+            float acc = 0.f;
+#pragma unroll
+            for (int lv = 0; lv < 3; ++lv) {
+                float a = w.out_b[lv][c];
+#pragma unroll
+                for (int j = 0; j < kCodeDim; ++j) a = fmaf(wv[lv][j], emb[lv][u][j], a);
+                acc += a;
+            }
+            z[u] = ok[u] ? acc : 0.f;
+        }
+        (void)bsum;
+        float dw[7];
+#pragma unroll
+        for (int j = 0; j < 7; ++j) dw[j] = w.dw_w[j * kLatent + c];
+        const float db = w.dw_b[c];
+#pragma unroll
+        for (int r = 0; r < kVqTile; ++r) {
+            const int t = t0 + r;
+            if (t < T0) {
+                float acc = db;
+#pragma unroll
+                for (int j = 0; j < 7; ++j) acc = fmaf(dw[j], z[r + j], acc);
+                from_f32(out[(static_cast<size_t>(s) * T0 + t) * kLatent + c], acc);
+            }
+        }
+    }
+}
+
+template <typename OutT>
+void launch_vq_stem(const int32_t* c0, const int32_t* c1, const int32_t* c2, int S, int F, const VqStemWeights& w,
+                    OutT* out, cudaStream_t st) {
+    dim3 grid((4 * F + kVqTile - 1) / kVqTile, S);
+    k_vq_stem<OutT><<<grid, 256, 0, st>>>(c0, c1, c2, F, w, out);
+}
+template void launch_vq_stem<float>(const int32_t*, const int32_t*, const int32_t*, int, int, const VqStemWeights&,
+                                    float*, cudaStream_t);
+template void launch_vq_stem<__nv_bfloat16>(const int32_t*, const int32_t*, const int32_t*, int, int,
+                                            const VqStemWeights&, __nv_bfloat16*, cudaStream_t);
+
+// ----------------------------------------------------------------------------------------------
+// fp32 row-GEMM with taps (CUDA cores).  64x64 tile, 16-deep K steps, 4x4 register micro-tile.
+// ----------------------------------------------------------------------------------------------
+template <int EPI>
+__global__ void __launch_bounds__(256)
+k_gemm_f32(GemmArgs a, const float* __restrict__ A, const float* __restrict__ W) {
+    constexpr int BM = 64, BN = 64, BK = 16;
+    __shared__ __align__(16) float As[BK][BM];
+    __shared__ __align__(16) float Ws[BK][BN];
+    const int tid = threadIdx.x;
+    const int n0 = blockIdx.x * BN;
+    const long long m0 = static_cast<long long>(blockIdx.y) * BM;
+    const long long M = static_cast<long long>(a.S) * a.Tin;
+    const int p = n0 / a.Cout;                         // output phase of this column tile
+    const int base_shift = (a.up > 1 && p >= a.up / 2) ? 1 : 0;
+    const int ldw = a.ntaps * a.K;
+
+    // loader mapping: one float4 of A and one of W per thread per K step
+    const int lrow = tid >> 2, lk = (tid & 3) * 4;
+    const long long ar = m0 + lrow;
+    const int as_ = static_cast<int>(ar / a.Tin), am = static_cast<int>(ar % a.Tin);
+    const float* wrow = W + static_cast<size_t>(n0 + lrow) * ldw;
+
+    const int ty = tid >> 4, tx = tid & 15;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    for (int tap = 0; tap < a.ntaps; ++tap) {
+        const int sm = am + base_shift - tap;
+        const bool avalid = (ar < M) && sm >= 0 && sm < a.Tin;
+        const float* arow = A + (static_cast<size_t>(as_) * a.Tin + (avalid ? sm : 0)) * a.K;
+        for (int k0 = 0; k0 < a.K; k0 += BK) {
+            float4 av = avalid ? *reinterpret_cast<const float4*>(arow + k0 + lk) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 wv = *reinterpret_cast<const float4*>(wrow + tap * a.K + k0 + lk);
+            __syncthreads();
+            As[lk + 0][lrow] = av.x; As[lk + 1][lrow] = av.y; As[lk + 2][lrow] = av.z; As[lk + 3][lrow] = av.w;
+            Ws[lk + 0][lrow] = wv.x; Ws[lk + 1][lrow] = wv.y; Ws[lk + 2][lrow] = wv.z; Ws[lk + 3][lrow] = wv.w;
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < BK; ++k) {
+                const float4 a4 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+                const float4 b4 = *reinterpret_cast<const float4*>(&Ws[k][tx * 4]);
+                const float av4[4] = {a4.x, a4.y, a4.z, a4.w};
+                const float bv4[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av4[i], bv4[j], acc[i][j]);
+            }
+        }
+    }
+
+    const int o0 = n0 - p * a.Cout + tx * 4;
+    float* out = static_cast<float*>(a.out);
+    const float* resid = static_cast<const float*>(a.resid);
+    unsigned long long key = 0;
+    if (EPI == EPI_NOISE && a.noise == nullptr)
+        key = splitmix64(a.seed * 0x100000001B3ull + static_cast<unsigned long long>(100 + a.noise_stage));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const long long r = m0 + ty * 4 + i;
+        if (r >= M) continue;
+        const int s = static_cast<int>(r / a.Tin), m = static_cast<int>(r % a.Tin);
+        const size_t orow = (static_cast<size_t>(s) * a.Tin + m) * a.up + p;
+        float v[4];
+        float nz = 0.f;
+        if (EPI == EPI_NOISE)
+            nz = a.noise ? a.noise[static_cast<size_t>(s) * a.Tin + m]
+                         : counter_normal(key, static_cast<unsigned long long>(a.stream_offset + s) * a.Tin + m);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int o = o0 + j;
+            float t = acc[i][j];
+            if (EPI == EPI_BIAS || EPI == EPI_BIAS_SNAKE) t += a.bias[o];
+            if (EPI == EPI_NOISE) t = resid[orow * a.Cout + o] + nz * t;
+            if (EPI == EPI_RES || EPI == EPI_RES_SNAKE) t = resid[orow * a.Cout + o] + (t + a.bias[o]);
+            if (EPI == EPI_BIAS_SNAKE || EPI == EPI_RES_SNAKE) t = snake_f<false>(t, a.alpha[o], a.inv_alpha[o]);
+            v[j] = t;
+        }
+        *reinterpret_cast<float4*>(out + orow * a.Cout + o0) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+}
+
+void launch_gemm_f32(int epi, const GemmArgs& a, const float* A, const float* W, cudaStream_t st) {
+    const long long M = static_cast<long long>(a.S) * a.Tin;
+    dim3 grid(a.N / 64, static_cast<unsigned>((M + 63) / 64));
+    switch (epi) {
+        case EPI_BIAS: k_gemm_f32<EPI_BIAS><<<grid, 256, 0, st>>>(a, A, W); break;
+        case EPI_BIAS_SNAKE: k_gemm_f32<EPI_BIAS_SNAKE><<<grid, 256, 0, st>>>(a, A, W); break;
+        case EPI_NOISE: k_gemm_f32<EPI_NOISE><<<grid, 256, 0, st>>>(a, A, W); break;
+        case EPI_RES: k_gemm_f32<EPI_RES><<<grid, 256, 0, st>>>(a, A, W); break;
+        default: k_gemm_f32<EPI_RES_SNAKE><<<grid, 256, 0, st>>>(a, A, W); break;
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// ResidualUnit front half, fp32 path:  P = snake2( dw_b + sum_j dw_w[j] * snake1(x[t + (j-3) d]) ).
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_respre_f32(ResUnitArgs a, float* __restrict__ P) {
+    const int c4n = a.C / 4;
+    const long long total = static_cast<long long>(a.S) * a.T * c4n;
+    const float* x = static_cast<const float*>(a.x);
+    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(idx % c4n) * 4;
+        const long long row = idx / c4n;
+        const int s = static_cast<int>(row / a.T), t = static_cast<int>(row % a.T);
+        const float4 al = *reinterpret_cast<const float4*>(a.alpha1 + c);
+        const float4 ia = *reinterpret_cast<const float4*>(a.inv_alpha1 + c);
+        float4 acc = *reinterpret_cast<const float4*>(a.dw_b + c);
+#pragma unroll
+        for (int j = 0; j < 7; ++j) {
+            const int tt = t + (j - 3) * a.dil;
+            if (tt < 0 || tt >= a.T) continue;
+            const float4 xv = *reinterpret_cast<const float4*>(x + (static_cast<size_t>(s) * a.T + tt) * a.C + c);
+            const float4 wv = *reinterpret_cast<const float4*>(a.dw_w + j * a.C + c);
+            acc.x = fmaf(wv.x, snake_f<false>(xv.x, al.x, ia.x), acc.x);
+            acc.y = fmaf(wv.y, snake_f<false>(xv.y, al.y, ia.y), acc.y);
+            acc.z = fmaf(wv.z, snake_f<false>(xv.z, al.z, ia.z), acc.z);
+            acc.w = fmaf(wv.w, snake_f<false>(xv.w, al.w, ia.w), acc.w);
+        }
+        const float4 a2 = *reinterpret_cast<const float4*>(a.alpha2 + c);
+        const float4 i2 = *reinterpret_cast<const float4*>(a.inv_alpha2 + c);
+        float4 o;
+        o.x = snake_f<false>(acc.x, a2.x, i2.x);
+        o.y = snake_f<false>(acc.y, a2.y, i2.y);
+        o.z = snake_f<false>(acc.z, a2.z, i2.z);
+        o.w = snake_f<false>(acc.w, a2.w, i2.w);
+        *reinterpret_cast<float4*>(P + row * a.C + c) = o;
+    }
+}
+
+void launch_respre_f32(const ResUnitArgs& a, float* P, cudaStream_t st) {
+    const long long total = static_cast<long long>(a.S) * a.T * (a.C / 4);
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148LL * 32) blocks = 148LL * 32;
+    k_respre_f32<<<static_cast<unsigned>(blocks), 256, 0, st>>>(a, P);
+}
+
+// ----------------------------------------------------------------------------------------------
+// Tail: conv 64->1 k7 pad 3 over the (already Snake'd) block-3 output, tanh, optional slice
+// [2048:4096] (vllm_inference/modal_audio_stream.py:94-95,195-198), int16 quantise (:201).
+// One warp = 32 consecutive samples; lane = channel pair; 7-row sliding window in registers.
+// ----------------------------------------------------------------------------------------------
+template <typename InT>
+__global__ void __launch_bounds__(128)
+k_tail(const InT* __restrict__ a, int T, int t_begin, int n_out, const float* __restrict__ w /*[7][64]*/, float bias,
+       int16_t* __restrict__ pcm, float* __restrict__ wave) {
+    const int s = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int base = t_begin + blockIdx.x * 128 + warp * 32;
+    if (base >= t_begin + n_out) return;
+    float w0[7], w1[7];
+#pragma unroll
+    for (int j = 0; j < 7; ++j) { w0[j] = w[j * 64 + 2 * lane]; w1[j] = w[j * 64 + 2 * lane + 1]; }
+    const InT* src = a + static_cast<size_t>(s) * T * 64 + 2 * lane;
+    auto load_row = [&](int t) -> float2 {
+        if (t < 0 || t >= T) return make_float2(0.f, 0.f);
+        const InT* p = src + static_cast<size_t>(t) * 64;
+        return make_float2(to_f32(p[0]), to_f32(p[1]));
+    };
+    float2 win[7];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) win[j + 1] = load_row(base - 3 + j);
+    float mine = 0.f;
+    for (int i = 0; i < 32; ++i) {
+#pragma unroll
+        for (int j = 0; j < 6; ++j) win[j] = win[j + 1];
+        win[6] = load_row(base + i + 3);
+        float part = 0.f;
+#pragma unroll
+        for (int j = 0; j < 7; ++j) part = fmaf(w0[j], win[j].x, fmaf(w1[j], win[j].y, part));
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
+        if (lane == i) mine = part;
+    }
+    const int t = base + lane;
+    if (t < t_begin + n_out && t < T) {
+        const float v = tanhf(mine + bias);
+        const size_t o = static_cast<size_t>(s) * n_out + (t - t_begin);
+        pcm[o] = pcm16(v);
+        if (wave) wave[o] = v;
+    }
+}
+
+template <typename InT>
+void launch_tail(const InT* a, int S, int T, int t_begin, int n_out, const float* w, float bias, int16_t* pcm,
+                 float* wave, cudaStream_t st) {
+    dim3 grid((n_out + 127) / 128, S);
+    k_tail<InT><<<grid, 128, 0, st>>>(a, T, t_begin, n_out, w, bias, pcm, wave);
+}
+template void launch_tail<float>(const float*, int, int, int, int, const float*, float, int16_t*, float*, cudaStream_t);
+template void launch_tail<__nv_bfloat16>(const __nv_bfloat16*, int, int, int, int, const float*, float, int16_t*,
+                                         float*, cudaStream_t);
+
+// ----------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void k_to_f32(const T* __restrict__ in, float* __restrict__ out, size_t n) {
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x)
+        out[i] = to_f32(in[i]);
+}
+template <typename T>
+void launch_to_f32(const T* in, float* out, size_t n, cudaStream_t st) {
+    if (n == 0) return;
+    size_t blocks = (n + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    k_to_f32<T><<<static_cast<unsigned>(blocks), 256, 0, st>>>(in, out, n);
+}
+template void launch_to_f32<float>(const float*, float*, size_t, cudaStream_t);
+template void launch_to_f32<__nv_bfloat16>(const __nv_bfloat16*, float*, size_t, cudaStream_t);
+
+}  // namespace snacb

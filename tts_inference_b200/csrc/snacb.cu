@@ -1,0 +1,631 @@
+// Host side of libsnacb: handle, weight packing, workspace, the per-group kernel pipeline and the
+// C ABI declared in include/snacb.h.
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <new>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "../../include/snacb.h"
+#include "kernels.h"
+
+using namespace snacb;
+
+namespace {
+
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+thread_local std::string g_create_error;
+
+struct ResW {
+    float *alpha1, *inv1, *dw_w, *dw_b, *alpha2, *inv2, *pw_f32, *pw_b;
+    __nv_bfloat16* pw_bf16;
+    CUtensorMap tm_pw;      // box (64, min(C,256)) for k_resunit_tc
+};
+struct BlockW {
+    int Cin, Cout, s;
+    float *alpha, *inv_alpha;           // Snake in front of the ConvTranspose (applied by the producer epilogue)
+    float *ct_f32, *ct_b;               // packed [s*Cout][2*Cin]
+    __nv_bfloat16* ct_bf16;
+    float* nz_f32;                      // [Cout][Cout]
+    __nv_bfloat16* nz_bf16;
+    ResW res[3];
+};
+struct Tap {
+    std::string name;
+    int64_t rows, cols;
+    float* dev;
+};
+struct TmapKey {
+    const void* p; int c, t, s, tb, wb;
+    bool operator<(const TmapKey& o) const {
+        return std::tie(p, c, t, s, tb, wb) < std::tie(o.p, o.c, o.t, o.s, o.tb, o.wb);
+    }
+};
+
+}  // namespace
+
+struct snacb_handle_s {
+    int device = 0;
+    int sm_count = 148;
+    std::string err;
+    cudaStream_t own_stream = nullptr;
+    PFN_tmapEncodeTiled encode = nullptr;
+
+    std::vector<void*> allocs;          // weight allocations
+    VqStemWeights vq{};
+    float *stem_pw_f32 = nullptr, *stem_pw_b = nullptr;
+    __nv_bfloat16* stem_pw_bf16 = nullptr;
+    BlockW blk[4]{};
+    float *tail_alpha = nullptr, *tail_inv = nullptr, *tail_w = nullptr;
+    float tail_b = 0.f;
+    std::map<std::pair<const void*, int>, CUtensorMap> wmaps;   // (weight ptr, box rows) -> map
+    std::map<TmapKey, CUtensorMap> amaps;
+
+    // workspace
+    size_t group_bytes = 48u << 20;
+    void* ws_buf[3] = {nullptr, nullptr, nullptr};
+    size_t ws_buf_bytes = 0;
+    void* ws_a0 = nullptr; size_t ws_a0_bytes = 0;
+    int32_t* ws_codes = nullptr; size_t ws_codes_elems = 0;
+    int32_t* st_tok = nullptr; size_t st_tok_elems = 0;       // decode_host staging
+    int16_t* st_pcm = nullptr; size_t st_pcm_elems = 0;
+
+    std::vector<Tap> taps;
+    uint64_t launches = 0, streams = 0;
+};
+
+namespace {
+
+int fail(snacb_handle h, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CK(h, call)                                                                                   \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess)                                                                        \
+            return fail(h, SNACB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+template <typename T>
+int dev_alloc(snacb_handle h, T** out, size_t n) {
+    void* p = nullptr;
+    CK(h, cudaMalloc(&p, n * sizeof(T)));
+    h->allocs.push_back(p);
+    *out = static_cast<T*>(p);
+    return 0;
+}
+int upload_f32(snacb_handle h, float** out, const std::vector<float>& v) {
+    int rc = dev_alloc(h, out, v.size());
+    if (rc) return rc;
+    CK(h, cudaMemcpy(*out, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice));
+    return 0;
+}
+int upload_bf16(snacb_handle h, __nv_bfloat16** out, const std::vector<float>& v) {
+    std::vector<__nv_bfloat16> b(v.size());
+    for (size_t i = 0; i < v.size(); ++i) b[i] = __float2bfloat16_rn(v[i]);
+    int rc = dev_alloc(h, out, v.size());
+    if (rc) return rc;
+    CK(h, cudaMemcpy(*out, b.data(), b.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
+    return 0;
+}
+std::vector<float> vec(const float* p, size_t n) { return std::vector<float>(p, p + n); }
+std::vector<float> inv_alpha(const float* a, size_t n) {
+    std::vector<float> r(n);
+    for (size_t i = 0; i < n; ++i) r[i] = 1.0f / (a[i] + 1e-9f);     // (alpha + 1e-9).reciprocal(), fp32
+    return r;
+}
+// [C][7] -> [7][C]
+std::vector<float> dw_transpose(const float* w, int C) {
+    std::vector<float> r(static_cast<size_t>(7) * C);
+    for (int c = 0; c < C; ++c)
+        for (int j = 0; j < 7; ++j) r[static_cast<size_t>(j) * C + c] = w[static_cast<size_t>(c) * 7 + j];
+    return r;
+}
+// ConvTranspose1d weight [Cin][Cout][2s] -> per-output-phase 2-tap GEMM weight [s*Cout][2*Cin]:
+//   Wp[p*Cout + o][tap*Cin + c] = W[c][o][((p + s/2) mod s) + tap*s]
+// (y[o, m*s+p] = sum_c x[c, m+sh-0] W[c,o,r] + x[c, m+sh-1] W[c,o,r+s], r = (p+s/2) mod s, sh = [p >= s/2])
+std::vector<float> pack_convt(const float* w, int Cin, int Cout, int s) {
+    std::vector<float> r(static_cast<size_t>(s) * Cout * 2 * Cin);
+    const int k = 2 * s;
+    for (int p = 0; p < s; ++p)
+        for (int o = 0; o < Cout; ++o)
+            for (int tap = 0; tap < 2; ++tap)
+                for (int c = 0; c < Cin; ++c)
+                    r[(static_cast<size_t>(p) * Cout + o) * (2 * Cin) + static_cast<size_t>(tap) * Cin + c] =
+                        w[(static_cast<size_t>(c) * Cout + o) * k + ((p + s / 2) % s) + tap * s];
+    return r;
+}
+
+int make_tmap_2d(snacb_handle h, CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, uint32_t box_rows) {
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstr[1] = {cols * 2};
+    cuuint32_t box[2] = {64, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = h->encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(h, SNACB_ERR_CUDA, "cuTensorMapEncodeTiled(2d %llu x %llu) failed: %d",
+                                       (unsigned long long)rows, (unsigned long long)cols, (int)r);
+    return 0;
+}
+int make_tmap_3d(snacb_handle h, CUtensorMap* m, const void* base, uint64_t C, uint64_t T, uint64_t S, uint32_t tbox,
+                 uint32_t wbox) {
+    cuuint64_t gdim[3] = {C, T, S};
+    cuuint64_t gstr[2] = {C * 2, T * C * 2};
+    cuuint32_t box[3] = {64, tbox, wbox};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = h->encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstr, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(h, SNACB_ERR_CUDA, "cuTensorMapEncodeTiled(3d C=%llu T=%llu S=%llu) failed: %d",
+                                       (unsigned long long)C, (unsigned long long)T, (unsigned long long)S, (int)r);
+    return 0;
+}
+int weight_map(snacb_handle h, const CUtensorMap** out, const __nv_bfloat16* w, int rows, int cols, int box_rows) {
+    auto key = std::make_pair(static_cast<const void*>(w), box_rows);
+    auto it = h->wmaps.find(key);
+    if (it == h->wmaps.end()) {
+        CUtensorMap m;
+        int rc = make_tmap_2d(h, &m, w, cols, rows, box_rows);
+        if (rc) return rc;
+        it = h->wmaps.emplace(key, m).first;
+    }
+    *out = &it->second;
+    return 0;
+}
+int act_map(snacb_handle h, const CUtensorMap** out, const void* base, int C, int T, int S, int tbox, int wbox) {
+    TmapKey key{base, C, T, S, tbox, wbox};
+    auto it = h->amaps.find(key);
+    if (it == h->amaps.end()) {
+        if (h->amaps.size() > 4096) h->amaps.clear();
+        CUtensorMap m;
+        int rc = make_tmap_3d(h, &m, base, C, T, S, tbox, wbox);
+        if (rc) return rc;
+        it = h->amaps.emplace(key, m).first;
+    }
+    *out = &it->second;
+    return 0;
+}
+
+void tile_boxes(int Tin, int* tbox, int* wbox) {
+    if (Tin < 128 && (Tin & (Tin - 1)) == 0) { *tbox = Tin; *wbox = 128 / Tin; }
+    else { *tbox = 128; *wbox = 1; }
+}
+
+int grow(snacb_handle h, void** p, size_t* cap, size_t need) {
+    if (need <= *cap) return 0;
+    if (*p) { CK(h, cudaFree(*p)); *p = nullptr; *cap = 0; h->amaps.clear(); }
+    CK(h, cudaMalloc(p, need));
+    *cap = need;
+    return 0;
+}
+
+template <typename T>
+int add_tap(snacb_handle h, const char* name, const T* src, int64_t rows, int64_t cols, cudaStream_t st) {
+    Tap t{name, rows, cols, nullptr};
+    CK(h, cudaMalloc(reinterpret_cast<void**>(&t.dev), static_cast<size_t>(rows) * cols * sizeof(float)));
+    launch_to_f32<T>(src, t.dev, static_cast<size_t>(rows) * cols, st);
+    CK(h, cudaGetLastError());
+    h->taps.push_back(t);
+    return 0;
+}
+void clear_taps(snacb_handle h) {
+    for (auto& t : h->taps) cudaFree(t.dev);
+    h->taps.clear();
+}
+
+// ------------------------------------------------------------------------------------------------
+// One group of S streams through the whole path.
+// ------------------------------------------------------------------------------------------------
+int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, int flags, const float* const* noise,
+              uint64_t seed, int stream_offset, int16_t* pcm, float* wave, cudaStream_t st) {
+    const bool f32 = (flags & SNACB_FP32) != 0;
+    const bool xf32 = f32 || (flags & SNACB_STREAM_FP32);      // residual stream dtype
+    const bool taps = (flags & SNACB_KEEP_TAPS) != 0;
+    const int T0 = 4 * F;
+    if (taps) clear_taps(h);
+
+    int32_t* c0 = h->ws_codes;
+    int32_t* c1 = c0 + static_cast<size_t>(S) * F;
+    int32_t* c2 = c1 + static_cast<size_t>(S) * 2 * F;
+    launch_unpack(tok, S, tok_stride, F, (flags & SNACB_RAW_IDS) ? 1 : 0, c0, c1, c2, st);
+    h->launches++;
+    if (f32) launch_vq_stem<float>(c0, c1, c2, S, F, h->vq, static_cast<float*>(h->ws_a0), st);
+    else launch_vq_stem<__nv_bfloat16>(c0, c1, c2, S, F, h->vq, static_cast<__nv_bfloat16*>(h->ws_a0), st);
+    h->launches++;
+    CK(h, cudaGetLastError());
+    if (taps) {
+        int rc = f32 ? add_tap(h, "stem_dw", static_cast<float*>(h->ws_a0), (int64_t)S * T0, kLatent, st)
+                     : add_tap(h, "stem_dw", static_cast<__nv_bfloat16*>(h->ws_a0), (int64_t)S * T0, kLatent, st);
+        if (rc) return rc;
+    }
+
+    void* cur = h->ws_buf[0];
+    void* oth = h->ws_buf[1];
+    float* P = static_cast<float*>(h->ws_buf[2]);
+
+    auto gemm = [&](int epi, bool out_f32, GemmArgs& a, const void* A, const float* Wf, const __nv_bfloat16* Wb,
+                    int Wrows, int Wcols) -> int {
+        tile_boxes(a.Tin, &a.Tbox, &a.Wbox);
+        a.seed = seed;
+        a.stream_offset = stream_offset;
+        h->launches++;
+        if (f32) {
+            launch_gemm_f32(epi, a, static_cast<const float*>(A), Wf, st);
+            CK(h, cudaGetLastError());
+            return 0;
+        }
+        const CUtensorMap *ma, *mw;
+        int rc = act_map(h, &ma, A, a.K, a.Tin, a.S, a.Tbox, a.Wbox);
+        if (rc) return rc;
+        rc = weight_map(h, &mw, Wb, Wrows, Wcols, gemm_tc_block_n(a));
+        if (rc) return rc;
+        CK(h, launch_gemm_tc(epi, out_f32 ? 1 : 0, a, *ma, *mw, h->sm_count, st));
+        return 0;
+    };
+    auto tap_any = [&](const char* name, const void* p, bool is_f32, int64_t rows, int64_t cols) -> int {
+        if (!taps) return 0;
+        return is_f32 ? add_tap(h, name, static_cast<const float*>(p), rows, cols, st)
+                      : add_tap(h, name, static_cast<const __nv_bfloat16*>(p), rows, cols, st);
+    };
+
+    // ---- stem 1x1 768 -> 1024, Snake of block 0 applied in the epilogue
+    {
+        GemmArgs a{};
+        a.S = S; a.Tin = T0; a.K = kLatent; a.N = kDecDim; a.Cout = kDecDim; a.ntaps = 1; a.up = 1;
+        a.bias = h->stem_pw_b; a.alpha = h->blk[0].alpha; a.inv_alpha = h->blk[0].inv_alpha;
+        a.out = cur;
+        int rc = gemm(EPI_BIAS_SNAKE, false, a, h->ws_a0, h->stem_pw_f32, h->stem_pw_bf16, kDecDim, kLatent);
+        if (rc) return rc;
+        rc = tap_any("stem", cur, f32, (int64_t)S * T0, kDecDim);
+        if (rc) return rc;
+    }
+
+    int Tin = T0;
+    char nm[32];
+    for (int bi = 0; bi < 4; ++bi) {
+        BlockW& b = h->blk[bi];
+        const int T = Tin * b.s;
+        // ---- ConvTranspose1d as a 2-tap GEMM per output phase: cur [S*Tin][Cin] -> oth [S*T][Cout]
+        {
+            GemmArgs a{};
+            a.S = S; a.Tin = Tin; a.K = b.Cin; a.N = b.s * b.Cout; a.Cout = b.Cout; a.ntaps = 2; a.up = b.s;
+            a.bias = b.ct_b; a.out = oth;
+            int rc = gemm(EPI_BIAS, false, a, cur, b.ct_f32, b.ct_bf16, b.s * b.Cout, 2 * b.Cin);
+            if (rc) return rc;
+            snprintf(nm, sizeof nm, "b%d.convt", bi);
+            rc = tap_any(nm, oth, f32, (int64_t)S * T, b.Cout);
+            if (rc) return rc;
+        }
+        // ---- NoiseBlock: oth -> cur   x = y + n * (Wn y)
+        {
+            GemmArgs a{};
+            a.S = S; a.Tin = T; a.K = b.Cout; a.N = b.Cout; a.Cout = b.Cout; a.ntaps = 1; a.up = 1;
+            a.noise = noise ? noise[bi] : nullptr; a.noise_stage = bi;
+            a.resid = oth; a.out = cur;
+            int rc = gemm(EPI_NOISE, xf32, a, oth, b.nz_f32, b.nz_bf16, b.Cout, b.Cout);
+            if (rc) return rc;
+            snprintf(nm, sizeof nm, "b%d.noise", bi);
+            rc = tap_any(nm, cur, xf32, (int64_t)S * T, b.Cout);
+            if (rc) return rc;
+        }
+        // ---- three ResidualUnits, dilations 1, 3, 9: cur -> oth -> cur -> oth
+        static const int dils[3] = {1, 3, 9};
+        for (int ri = 0; ri < 3; ++ri) {
+            ResW& r = b.res[ri];
+            const bool last = (ri == 2);
+            const float* an = last ? (bi < 3 ? h->blk[bi + 1].alpha : h->tail_alpha) : nullptr;
+            const float* ian = last ? (bi < 3 ? h->blk[bi + 1].inv_alpha : h->tail_inv) : nullptr;
+            ResUnitArgs ra{};
+            ra.S = S; ra.T = T; ra.C = b.Cout; ra.dil = dils[ri];
+            ra.x = cur; ra.out = oth;
+            ra.alpha1 = r.alpha1; ra.inv_alpha1 = r.inv1; ra.dw_w = r.dw_w; ra.dw_b = r.dw_b;
+            ra.alpha2 = r.alpha2; ra.inv_alpha2 = r.inv2; ra.pw_b = r.pw_b;
+            ra.alpha_next = an; ra.inv_alpha_next = ian;
+            if (f32) {
+                launch_respre_f32(ra, P, st);
+                GemmArgs a{};
+                a.S = S; a.Tin = T; a.K = b.Cout; a.N = b.Cout; a.Cout = b.Cout; a.ntaps = 1; a.up = 1;
+                a.bias = r.pw_b; a.alpha = an; a.inv_alpha = ian; a.resid = cur; a.out = oth;
+                tile_boxes(a.Tin, &a.Tbox, &a.Wbox);
+                launch_gemm_f32(last ? EPI_RES_SNAKE : EPI_RES, a, P, r.pw_f32, st);
+                h->launches += 2;
+                CK(h, cudaGetLastError());
+            } else {
+                CK(h, launch_resunit_tc(last ? EPI_RES_SNAKE : EPI_RES, xf32 ? 1 : 0, ra, r.tm_pw, st));
+                h->launches++;
+            }
+            snprintf(nm, sizeof nm, "b%d.res%d", bi, ri);
+            int rc = tap_any(nm, oth, last ? f32 : xf32, (int64_t)S * T, b.Cout);
+            if (rc) return rc;
+            void* t = cur; cur = oth; oth = t;
+        }
+        Tin = T;
+    }
+
+    // ---- tail
+    const int T = Tin;                                   // 2048 * F samples
+    const bool slice = (flags & SNACB_EXTRACT_SLICE) && T > 4096;
+    const int t_begin = slice ? 2048 : 0, n_out = slice ? 2048 : T;
+    if (f32) launch_tail<float>(static_cast<const float*>(cur), S, T, t_begin, n_out, h->tail_w, h->tail_b, pcm, wave, st);
+    else launch_tail<__nv_bfloat16>(static_cast<const __nv_bfloat16*>(cur), S, T, t_begin, n_out, h->tail_w, h->tail_b, pcm, wave, st);
+    h->launches++;
+    CK(h, cudaGetLastError());
+    h->streams += S;
+    return 0;
+}
+
+}  // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+int snacb_version(void) { return SNACB_VERSION; }
+
+int snacb_samples_out(int frames, int flags) {
+    const int T = 2048 * frames;
+    return ((flags & SNACB_EXTRACT_SLICE) && T > 4096) ? 2048 : T;
+}
+
+const char* snacb_last_error(snacb_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int snacb_create(snacb_handle* out, const snacb_weights* w, int device) {
+    if (!out || !w) return fail(nullptr, SNACB_ERR_ARG, "snacb_create: null argument");
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(nullptr, SNACB_ERR_NO_GPU, "snacb_create: no CUDA device (this library has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(nullptr, SNACB_ERR_ARG, "snacb_create: bad device %d", device);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major != 10)
+        return fail(nullptr, SNACB_ERR_NO_GPU, "snacb_create: device %d is sm_%d%d, this build is sm_100a only", device,
+                    prop.major, prop.minor);
+    snacb_handle h = new (std::nothrow) snacb_handle_s();
+    if (!h) return fail(nullptr, SNACB_ERR_NOMEM, "snacb_create: out of host memory");
+    h->device = device;
+    h->sm_count = prop.multiProcessorCount;
+    auto bail = [&](int rc) { g_create_error = h->err; snacb_destroy(h); return rc; };
+#define CKH(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+        fail(h, SNACB_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); return bail(SNACB_ERR_CUDA); } } while (0)
+#define RC(call) do { int rc_ = (call); if (rc_) return bail(rc_); } while (0)
+    CKH(cudaSetDevice(device));
+    CKH(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        CKH(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+        if (!fn || q != cudaDriverEntryPointSuccess) {
+            fail(h, SNACB_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+            return bail(SNACB_ERR_CUDA);
+        }
+        h->encode = reinterpret_cast<PFN_tmapEncodeTiled>(fn);
+    }
+    // ---- VQ + stem
+    for (int i = 0; i < 3; ++i) {
+        float* p;
+        RC(upload_f32(h, &p, vec(w->codebook[i], (size_t)kCodebook * kCodeDim))); h->vq.codebook[i] = p;
+        RC(upload_f32(h, &p, vec(w->out_proj_w[i], (size_t)kLatent * kCodeDim))); h->vq.out_w[i] = p;
+        RC(upload_f32(h, &p, vec(w->out_proj_b[i], kLatent))); h->vq.out_b[i] = p;
+    }
+    {
+        float* p;
+        RC(upload_f32(h, &p, dw_transpose(w->stem_dw_w, kLatent))); h->vq.dw_w = p;
+        RC(upload_f32(h, &p, vec(w->stem_dw_b, kLatent))); h->vq.dw_b = p;
+        auto pw = vec(w->stem_pw_w, (size_t)kDecDim * kLatent);
+        RC(upload_f32(h, &h->stem_pw_f32, pw));
+        RC(upload_bf16(h, &h->stem_pw_bf16, pw));
+        RC(upload_f32(h, &h->stem_pw_b, vec(w->stem_pw_b, kDecDim)));
+    }
+    // ---- decoder blocks
+    static const int strides[4] = {8, 8, 4, 2};
+    int cin = kDecDim;
+    for (int bi = 0; bi < 4; ++bi) {
+        const snacb_block_weights& s = w->block[bi];
+        BlockW& b = h->blk[bi];
+        b.Cin = cin; b.Cout = cin / 2; b.s = strides[bi];
+        RC(upload_f32(h, &b.alpha, vec(s.alpha, cin)));
+        RC(upload_f32(h, &b.inv_alpha, inv_alpha(s.alpha, cin)));
+        auto ct = pack_convt(s.convt_w, b.Cin, b.Cout, b.s);
+        RC(upload_f32(h, &b.ct_f32, ct));
+        RC(upload_bf16(h, &b.ct_bf16, ct));
+        RC(upload_f32(h, &b.ct_b, vec(s.convt_b, b.Cout)));
+        auto nz = vec(s.noise_w, (size_t)b.Cout * b.Cout);
+        RC(upload_f32(h, &b.nz_f32, nz));
+        RC(upload_bf16(h, &b.nz_bf16, nz));
+        for (int ri = 0; ri < 3; ++ri) {
+            const snacb_resunit_weights& rs = s.res[ri];
+            ResW& r = b.res[ri];
+            const int C = b.Cout;
+            RC(upload_f32(h, &r.alpha1, vec(rs.alpha1, C)));
+            RC(upload_f32(h, &r.inv1, inv_alpha(rs.alpha1, C)));
+            RC(upload_f32(h, &r.dw_w, dw_transpose(rs.dw_w, C)));
+            RC(upload_f32(h, &r.dw_b, vec(rs.dw_b, C)));
+            RC(upload_f32(h, &r.alpha2, vec(rs.alpha2, C)));
+            RC(upload_f32(h, &r.inv2, inv_alpha(rs.alpha2, C)));
+            auto pw = vec(rs.pw_w, (size_t)C * C);
+            RC(upload_f32(h, &r.pw_f32, pw));
+            RC(upload_bf16(h, &r.pw_bf16, pw));
+            RC(upload_f32(h, &r.pw_b, vec(rs.pw_b, C)));
+            RC(make_tmap_2d(h, &r.tm_pw, r.pw_bf16, C, C, C > 256 ? 256 : C));
+        }
+        cin = b.Cout;
+    }
+    RC(upload_f32(h, &h->tail_alpha, vec(w->tail_alpha, 64)));
+    RC(upload_f32(h, &h->tail_inv, inv_alpha(w->tail_alpha, 64)));
+    {
+        std::vector<float> tw(7 * 64);
+        for (int c = 0; c < 64; ++c)
+            for (int j = 0; j < 7; ++j) tw[j * 64 + c] = w->tail_w[c * 7 + j];
+        RC(upload_f32(h, &h->tail_w, tw));
+        h->tail_b = w->tail_b[0];
+    }
+    if (const char* e = getenv("SNACB_GROUP_MB")) {
+        long mb = atol(e);
+        if (mb > 0) h->group_bytes = static_cast<size_t>(mb) << 20;
+    }
+    CKH(cudaDeviceSynchronize());
+#undef CKH
+#undef RC
+    *out = h;
+    return SNACB_OK;
+}
+
+void snacb_destroy(snacb_handle h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    clear_taps(h);
+    for (void* p : h->allocs) cudaFree(p);
+    for (int i = 0; i < 3; ++i) if (h->ws_buf[i]) cudaFree(h->ws_buf[i]);
+    if (h->ws_a0) cudaFree(h->ws_a0);
+    if (h->ws_codes) cudaFree(h->ws_codes);
+    if (h->st_tok) cudaFree(h->st_tok);
+    if (h->st_pcm) cudaFree(h->st_pcm);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+}
+
+int snacb_set_group_bytes(snacb_handle h, size_t bytes) {
+    if (!h) return SNACB_ERR_ARG;
+    if (bytes) h->group_bytes = bytes;
+    return SNACB_OK;
+}
+
+int snacb_stats(snacb_handle h, uint64_t* kernel_launches, uint64_t* streams_decoded) {
+    if (!h) return SNACB_ERR_ARG;
+    if (kernel_launches) *kernel_launches = h->launches;
+    if (streams_decoded) *streams_decoded = h->streams;
+    return SNACB_OK;
+}
+
+int snacb_unpack(snacb_handle h, const int32_t* tok, int B, int ntok, int flags, int32_t* c0, int32_t* c1, int32_t* c2,
+                 void* stream) {
+    if (!h) return SNACB_ERR_ARG;
+    if (B < 0 || ntok < 0 || (B > 0 && (!tok || !c0 || !c1 || !c2))) return fail(h, SNACB_ERR_ARG, "snacb_unpack: bad argument");
+    const int F = ntok / kFrame;
+    if (B == 0 || F == 0) return SNACB_OK;
+    CK(h, cudaSetDevice(h->device));
+    launch_unpack(tok, B, ntok, F, (flags & SNACB_RAW_IDS) ? 1 : 0, c0, c1, c2, static_cast<cudaStream_t>(stream));
+    h->launches++;
+    CK(h, cudaGetLastError());
+    return SNACB_OK;
+}
+
+int snacb_decode(snacb_handle h, const int32_t* tok, int B, int tok_stride, int frames, int flags,
+                 const float* const* noise, uint64_t seed, int16_t* pcm, float* wave, void* stream) {
+    if (!h) return SNACB_ERR_ARG;
+    if (B < 0 || frames < 0 || tok_stride < frames * kFrame)
+        return fail(h, SNACB_ERR_ARG, "snacb_decode: bad sizes B=%d frames=%d tok_stride=%d", B, frames, tok_stride);
+    if (B == 0 || frames == 0) return SNACB_OK;
+    if (!tok || !pcm) return fail(h, SNACB_ERR_ARG, "snacb_decode: null tok/pcm");
+    if (frames > 16384) return fail(h, SNACB_ERR_ARG, "snacb_decode: frames=%d too large", frames);
+    CK(h, cudaSetDevice(h->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bool f32 = (flags & SNACB_FP32) != 0;
+    const bool xf32 = f32 || (flags & SNACB_STREAM_FP32);
+    const size_t per_stream_elems = static_cast<size_t>(131072) * frames;      // max T*C over the blocks
+    const size_t esz = xf32 ? 4 : 2;
+    size_t G = h->group_bytes / (per_stream_elems * esz);
+    if (G < 1) G = 1;
+    if (G > static_cast<size_t>(B)) G = B;
+    // workspace
+    {
+        const size_t need = G * per_stream_elems * esz;
+        if (need > h->ws_buf_bytes) {
+            h->amaps.clear();
+            for (int i = 0; i < 3; ++i) {
+                if (h->ws_buf[i]) { CK(h, cudaFree(h->ws_buf[i])); h->ws_buf[i] = nullptr; }
+            }
+            h->ws_buf_bytes = 0;
+            for (int i = 0; i < 3; ++i) CK(h, cudaMalloc(&h->ws_buf[i], need));
+            h->ws_buf_bytes = need;
+        }
+        int rc = grow(h, &h->ws_a0, &h->ws_a0_bytes, G * 4 * frames * kLatent * (f32 ? 4 : 2));
+        if (rc) return rc;
+        size_t cbytes = h->ws_codes_elems * sizeof(int32_t);
+        rc = grow(h, reinterpret_cast<void**>(&h->ws_codes), &cbytes, G * 7 * frames * sizeof(int32_t));
+        if (rc) return rc;
+        h->ws_codes_elems = cbytes / sizeof(int32_t);
+    }
+    const int n_out = snacb_samples_out(frames, flags);
+    const int T0 = 4 * frames;
+    const size_t nlen[4] = {(size_t)T0 * 8, (size_t)T0 * 64, (size_t)T0 * 256, (size_t)T0 * 512};
+    for (int g0 = 0; g0 < B; g0 += static_cast<int>(G)) {
+        const int S = (B - g0) < static_cast<int>(G) ? (B - g0) : static_cast<int>(G);
+        const float* nz[4];
+        if (noise) for (int i = 0; i < 4; ++i) nz[i] = noise[i] + static_cast<size_t>(g0) * nlen[i];
+        int rc = run_group(h, tok + static_cast<size_t>(g0) * tok_stride, S, tok_stride, frames, flags,
+                           noise ? nz : nullptr, seed, g0, pcm + static_cast<size_t>(g0) * n_out,
+                           wave ? wave + static_cast<size_t>(g0) * n_out : nullptr, st);
+        if (rc) return rc;
+    }
+    return SNACB_OK;
+}
+
+int snacb_decode_host(snacb_handle h, const int32_t* tok_host, int B, int tok_stride, int frames, int flags,
+                      uint64_t seed, int16_t* pcm_host) {
+    if (!h) return SNACB_ERR_ARG;
+    if (B < 0 || frames < 0 || tok_stride < frames * kFrame) return fail(h, SNACB_ERR_ARG, "snacb_decode_host: bad sizes");
+    if (B == 0 || frames == 0) return SNACB_OK;
+    if (!tok_host || !pcm_host) return fail(h, SNACB_ERR_ARG, "snacb_decode_host: null buffer");
+    CK(h, cudaSetDevice(h->device));
+    const size_t ntok = static_cast<size_t>(B) * tok_stride;
+    const size_t npcm = static_cast<size_t>(B) * snacb_samples_out(frames, flags);
+    size_t tb = h->st_tok_elems * sizeof(int32_t), pb = h->st_pcm_elems * sizeof(int16_t);
+    int rc = grow(h, reinterpret_cast<void**>(&h->st_tok), &tb, ntok * sizeof(int32_t));
+    if (rc) return rc;
+    h->st_tok_elems = tb / sizeof(int32_t);
+    rc = grow(h, reinterpret_cast<void**>(&h->st_pcm), &pb, npcm * sizeof(int16_t));
+    if (rc) return rc;
+    h->st_pcm_elems = pb / sizeof(int16_t);
+    cudaStream_t st = h->own_stream;
+    CK(h, cudaMemcpyAsync(h->st_tok, tok_host, ntok * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    rc = snacb_decode(h, h->st_tok, B, tok_stride, frames, flags, nullptr, seed, h->st_pcm, nullptr, st);
+    if (rc) return rc;
+    CK(h, cudaMemcpyAsync(pcm_host, h->st_pcm, npcm * sizeof(int16_t), cudaMemcpyDeviceToHost, st));
+    CK(h, cudaStreamSynchronize(st));
+    return SNACB_OK;
+}
+
+int snacb_debug_tap_count(snacb_handle h) { return h ? static_cast<int>(h->taps.size()) : SNACB_ERR_ARG; }
+
+int snacb_debug_tap_info(snacb_handle h, int idx, char* name, int name_cap, int64_t* rows, int64_t* cols) {
+    if (!h || idx < 0 || idx >= static_cast<int>(h->taps.size())) return SNACB_ERR_ARG;
+    const Tap& t = h->taps[idx];
+    if (name && name_cap > 0) { strncpy(name, t.name.c_str(), name_cap - 1); name[name_cap - 1] = 0; }
+    if (rows) *rows = t.rows;
+    if (cols) *cols = t.cols;
+    return SNACB_OK;
+}
+
+int snacb_debug_tap_copy(snacb_handle h, int idx, float* dst_host, size_t dst_elems) {
+    if (!h || idx < 0 || idx >= static_cast<int>(h->taps.size()) || !dst_host) return SNACB_ERR_ARG;
+    const Tap& t = h->taps[idx];
+    const size_t n = static_cast<size_t>(t.rows) * t.cols;
+    if (dst_elems < n) return fail(h, SNACB_ERR_ARG, "snacb_debug_tap_copy: buffer too small");
+    CK(h, cudaSetDevice(h->device));
+    CK(h, cudaDeviceSynchronize());
+    CK(h, cudaMemcpy(dst_host, t.dev, n * sizeof(float), cudaMemcpyDeviceToHost));
+    return SNACB_OK;
+}
+
+}  // extern "C"

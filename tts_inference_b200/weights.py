@@ -1,0 +1,100 @@
+"""Checkpoint -> folded fp32 weights for ``snacb_create`` (host-side load logic).
+
+The reference keeps weight-norm un-folded and recomputes ``w = g * v / ||v||`` inside every
+forward of the pip ``snac`` model it loads in ``init_snac`` (vllm_inference/modal_audio_stream.py:
+106-129).  Here the fold happens once at load.  Norm is over every dim but 0 (torch
+``weight_norm(dim=0)``): per OUTPUT channel for Conv1d ``[Cout, Cin/groups, k]``, per INPUT
+channel for ConvTranspose1d ``[Cin, Cout, k]``.  Both key styles are accepted:
+``*.weight_g`` / ``*.weight_v`` and ``*.parametrizations.weight.original0`` / ``original1``.
+"""
+from __future__ import annotations
+
+from typing import Dict, Mapping
+
+import numpy as np
+
+DECODER_RATES = (8, 8, 4, 2)
+
+
+def _np(x) -> np.ndarray:
+    if isinstance(x, np.ndarray):
+        return x
+    if hasattr(x, "detach"):
+        return x.detach().cpu().numpy()
+    return np.asarray(x)
+
+
+def fold_weight_norm(g, v) -> np.ndarray:
+    """w = g * v / ||v||, norm over all dims except 0; float64 arithmetic, float32 result."""
+    v64 = _np(v).astype(np.float64)
+    g64 = _np(g).astype(np.float64).reshape(v64.shape[0], *([1] * (v64.ndim - 1)))
+    norm = np.sqrt((v64.reshape(v64.shape[0], -1) ** 2).sum(axis=1)).reshape(g64.shape)
+    return np.ascontiguousarray((v64 * (g64 / norm)).astype(np.float32))
+
+
+def _weight(sd: Mapping[str, object], prefix: str) -> np.ndarray:
+    if prefix + ".weight_g" in sd:
+        return fold_weight_norm(sd[prefix + ".weight_g"], sd[prefix + ".weight_v"])
+    p = prefix + ".parametrizations.weight.original"
+    if p + "0" in sd:
+        return fold_weight_norm(sd[p + "0"], sd[p + "1"])
+    if prefix + ".weight" in sd:        # already folded checkpoint
+        return np.ascontiguousarray(_np(sd[prefix + ".weight"]).astype(np.float32))
+    raise KeyError(f"checkpoint has no weight for {prefix}")
+
+
+def _vec(sd, key) -> np.ndarray:
+    if key not in sd:
+        raise KeyError(f"checkpoint lacks {key}")
+    return np.ascontiguousarray(_np(sd[key]).astype(np.float32).reshape(-1))
+
+
+def fold_state_dict(sd: Mapping[str, object]) -> Dict[str, np.ndarray]:
+    """Flat dict of contiguous float32 arrays, keyed by the field names of ``snacb_weights``."""
+    out: Dict[str, np.ndarray] = {}
+    for i in range(3):
+        q = f"quantizer.quantizers.{i}"
+        out[f"codebook{i}"] = np.ascontiguousarray(_np(sd[q + ".codebook.weight"]).astype(np.float32))
+        out[f"out_proj_w{i}"] = _weight(sd, q + ".out_proj")
+        out[f"out_proj_b{i}"] = _vec(sd, q + ".out_proj.bias")
+        assert out[f"codebook{i}"].shape == (4096, 8) and out[f"out_proj_w{i}"].shape == (768, 8, 1)
+    out["stem_dw_w"] = _weight(sd, "decoder.model.0")
+    out["stem_dw_b"] = _vec(sd, "decoder.model.0.bias")
+    out["stem_pw_w"] = _weight(sd, "decoder.model.1")
+    out["stem_pw_b"] = _vec(sd, "decoder.model.1.bias")
+    assert out["stem_dw_w"].shape == (768, 1, 7) and out["stem_pw_w"].shape == (1024, 768, 1)
+    cin = 1024
+    for bi, s in enumerate(DECODER_RATES):
+        cout = cin // 2
+        p = f"decoder.model.{2 + bi}.block"
+        out[f"b{bi}.alpha"] = _vec(sd, p + ".0.alpha")
+        out[f"b{bi}.convt_w"] = _weight(sd, p + ".1")
+        out[f"b{bi}.convt_b"] = _vec(sd, p + ".1.bias")
+        out[f"b{bi}.noise_w"] = _weight(sd, p + ".2.linear")
+        assert out[f"b{bi}.convt_w"].shape == (cin, cout, 2 * s), out[f"b{bi}.convt_w"].shape
+        assert out[f"b{bi}.noise_w"].shape == (cout, cout, 1)
+        for ri in range(3):
+            q = f"{p}.{3 + ri}.block"
+            out[f"b{bi}.r{ri}.alpha1"] = _vec(sd, q + ".0.alpha")
+            out[f"b{bi}.r{ri}.dw_w"] = _weight(sd, q + ".1")
+            out[f"b{bi}.r{ri}.dw_b"] = _vec(sd, q + ".1.bias")
+            out[f"b{bi}.r{ri}.alpha2"] = _vec(sd, q + ".2.alpha")
+            out[f"b{bi}.r{ri}.pw_w"] = _weight(sd, q + ".3")
+            out[f"b{bi}.r{ri}.pw_b"] = _vec(sd, q + ".3.bias")
+            assert out[f"b{bi}.r{ri}.dw_w"].shape == (cout, 1, 7) and out[f"b{bi}.r{ri}.pw_w"].shape == (cout, cout, 1)
+        cin = cout
+    out["tail_alpha"] = _vec(sd, "decoder.model.6.alpha")
+    out["tail_w"] = _weight(sd, "decoder.model.7")
+    out["tail_b"] = _vec(sd, "decoder.model.7.bias")
+    assert out["tail_w"].shape == (1, 64, 7)
+    return out
+
+
+def load_checkpoint(path: str) -> Dict[str, np.ndarray]:
+    """Read ``pytorch_model.bin`` (or a directory holding it) of hubertsiuzdak/snac_24khz."""
+    import os
+    import torch
+    if os.path.isdir(path):
+        path = os.path.join(path, "pytorch_model.bin")
+    sd = torch.load(path, map_location="cpu", weights_only=True)
+    return {k: v.numpy() for k, v in sd.items()}
