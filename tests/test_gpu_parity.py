@@ -1,0 +1,208 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle on identical inputs.
+
+Bars (BASELINE.json north_star): unpacked codes bit-exact; fp32 waveform <= 1e-3 max-abs;
+bf16 path SNR >= 40 dB; int16 within +-1 LSB (fp32 path vs the quantised oracle waveform)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import glue_ref
+from tests._util import oracle_decode, pcm_of, snr_db
+from tts_inference_b200 import synth
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+FP32_TOL = 1e-3      # north_star: fp32 waveform within 1e-3 max-abs
+BF16_SNR_DB = 40.0   # north_star: bf16 path SNR >= 40 dB
+
+
+def _cuda(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+# ------------------------------------------------------------------------------------ integer kernel
+@pytest.mark.parametrize("B,ntok,raw,bad", [(1, 28, True, 0.0), (7, 28, True, 0.3), (3, 7, False, 0.2),
+                                            (5, 41, True, 0.1), (64, 3584, True, 0.01), (2, 6, True, 0.0)])
+def test_unpack_bit_exact(decoder, B, ntok, raw, bad):
+    F_ = max(1, (ntok + 6) // 7)
+    tok = synth.make_tokens(B, F_, seed=B * 100 + ntok, bad_frac=bad)[:, :ntok]
+    if not raw:
+        tok = (tok.astype(np.int64) - 128266).astype(np.int32)
+    c = decoder.unpack(_cuda(tok), raw_ids=raw)
+    if ntok < 7:
+        assert all(x.numel() == 0 for x in c)
+        return
+    codes = tok.astype(np.int64) - (128266 if raw else 0)
+    ref = glue_ref.unpack_np(codes)
+    for got, want in zip(c, ref):
+        assert np.array_equal(got.cpu().numpy(), want)
+    # and against the reference's scalar loop variants
+    for b in range(min(B, 3)):
+        l = glue_ref.unpack_trt(codes[b].tolist())
+        assert [x[b].cpu().tolist() for x in c] == [list(v) for v in l]
+
+
+def test_unpack_extreme_ids(decoder):
+    tok = np.array([[2 ** 31 - 1, -2 ** 31, 0, 128266, 128266 + 4095, 128266 + 4096, 128265]], dtype=np.int32)
+    c = decoder.unpack(_cuda(tok), raw_ids=True)
+    ref = glue_ref.unpack_np(tok.astype(np.int64) - 128266)
+    for got, want in zip(c, ref):
+        assert np.array_equal(got.cpu().numpy(), want)
+
+
+# ------------------------------------------------------------------------------------ fp32 path
+@pytest.mark.parametrize("B,F_", [(1, 4), (3, 4), (2, 1), (2, 5), (1, 9)])
+def test_fp32_waveform_parity(decoder, oracle_model, B, F_):
+    tokens = synth.make_tokens(B, F_, seed=11 + F_, bad_frac=0.02)
+    noises = synth.make_noises(B, 4 * F_, seed=5)
+    ref, _ = oracle_decode(oracle_model, tokens, noises)
+    pcm, wave = decoder.decode(_cuda(tokens), raw_ids=True, noise=[_cuda(n) for n in noises], precision="fp32",
+                               return_wave=True)
+    w = wave.cpu().numpy()
+    assert w.shape == ref.shape == (B, 2048 * F_)
+    assert np.abs(w - ref).max() <= FP32_TOL
+    d = np.abs(pcm.cpu().numpy().astype(np.int32) - pcm_of(ref).astype(np.int32))
+    assert d.max() <= 1, f"int16 differs by {d.max()} LSB"
+    assert np.array_equal(pcm.cpu().numpy(), pcm_of(w))           # quantiser itself is exact (truncation)
+
+
+def test_fp32_stage_taps(decoder, oracle_model):
+    tokens = synth.make_tokens(2, 4, seed=3)
+    noises = synth.make_noises(2, 16, seed=9)
+    _, rt = oracle_decode(oracle_model, tokens, noises, want_taps=True)
+    decoder.decode(_cuda(tokens), raw_ids=True, noise=[_cuda(n) for n in noises], precision="fp32", keep_taps=True)
+    taps = decoder.taps()
+    assert set(rt) <= set(taps)
+    for k, r in rt.items():
+        assert taps[k].shape == r.shape, k
+        assert np.abs(taps[k] - r).max() <= 2e-4 * max(1.0, np.abs(r).max()), k
+
+
+# ------------------------------------------------------------------------------------ bf16 tensor-core path
+@pytest.mark.parametrize("B,F_", [(1, 4), (5, 4), (2, 1), (2, 5), (1, 9), (40, 4)])
+def test_bf16_snr(decoder, oracle_model, B, F_):
+    tokens = synth.make_tokens(B, F_, seed=21 + F_, bad_frac=0.02)
+    noises = synth.make_noises(B, 4 * F_, seed=6)
+    ref, _ = oracle_decode(oracle_model, tokens, noises)
+    pcm, wave = decoder.decode(_cuda(tokens), raw_ids=True, noise=[_cuda(n) for n in noises], precision="bf16",
+                               return_wave=True)
+    w = wave.cpu().numpy()
+    assert np.isfinite(w).all()
+    assert snr_db(ref, w) >= BF16_SNR_DB
+    assert np.array_equal(pcm.cpu().numpy(), pcm_of(w))
+
+
+def test_bf16_stage_taps(decoder, oracle_model):
+    tokens = synth.make_tokens(2, 4, seed=4)
+    noises = synth.make_noises(2, 16, seed=8)
+    _, rt = oracle_decode(oracle_model, tokens, noises, want_taps=True)
+    decoder.decode(_cuda(tokens), raw_ids=True, noise=[_cuda(n) for n in noises], precision="bf16", keep_taps=True)
+    taps = decoder.taps()
+    for k, r in rt.items():
+        assert taps[k].shape == r.shape, k
+        assert snr_db(r, taps[k]) >= 38.0, (k, snr_db(r, taps[k]))
+
+
+# ------------------------------------------------------------------------------------ helper semantics
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_slice_semantics(decoder, prec):
+    tokens = synth.make_tokens(3, 4, seed=1)
+    full = decoder.decode(_cuda(tokens), raw_ids=True, seed=3, precision=prec)
+    sl = decoder.decode(_cuda(tokens), raw_ids=True, seed=3, precision=prec, extract_slice=True)
+    assert full.shape == (3, 8192) and sl.shape == (3, 2048)
+    assert torch.equal(sl, full[:, 2048:4096])                    # modal_audio_stream.py:195-196
+    two = synth.make_tokens(2, 2, seed=2)                          # 4096 samples: not > AUDIO_SLICE_END -> all kept
+    a = decoder.decode(_cuda(two), raw_ids=True, seed=3, precision=prec, extract_slice=True)
+    b = decoder.decode(_cuda(two), raw_ids=True, seed=3, precision=prec, extract_slice=False)
+    assert a.shape == (2, 4096) and torch.equal(a, b)
+
+
+def test_ragged_tail_is_dropped(decoder):
+    tokens = synth.make_tokens(2, 5, seed=8)
+    a = decoder.decode(_cuda(tokens[:, :31]), raw_ids=True, seed=1)     # 4 frames + 3 stray tokens
+    b = decoder.decode(_cuda(np.ascontiguousarray(tokens[:, :28])), raw_ids=True, seed=1)
+    assert a.shape == (2, 8192) and torch.equal(a, b)
+
+
+def test_builtin_noise_matches_counter_rng(decoder, oracle_model):
+    """noise=None uses the in-kernel counter RNG keyed by seed: same stream as synth.make_noises."""
+    tokens = synth.make_tokens(3, 4, seed=12)
+    ref, _ = oracle_decode(oracle_model, tokens, synth.make_noises(3, 16, seed=1234))
+    _, wave = decoder.decode(_cuda(tokens), raw_ids=True, seed=1234, precision="fp32", return_wave=True)
+    assert np.abs(wave.cpu().numpy() - ref).max() <= FP32_TOL
+    _, w2 = decoder.decode(_cuda(tokens), raw_ids=True, seed=1235, precision="fp32", return_wave=True)
+    assert not torch.equal(wave, w2)
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_grouping_and_batch_independence(decoder, prec):
+    """Streams are independent: a stream's PCM does not depend on batch size or group split."""
+    B = 37
+    tokens = synth.make_tokens(B, 4, seed=77)
+    noises = [_cuda(n) for n in synth.make_noises(B, 16, seed=2)]
+    decoder.set_group_bytes(48 << 20)
+    big = decoder.decode(_cuda(tokens), raw_ids=True, noise=noises, precision=prec)
+    decoder.set_group_bytes(5 * 131072 * 4 * 2)                     # forces groups of a few streams
+    small = decoder.decode(_cuda(tokens), raw_ids=True, noise=noises, precision=prec)
+    decoder.set_group_bytes(48 << 20)
+    assert torch.equal(big, small)
+    one = decoder.decode(_cuda(tokens[5:6]), raw_ids=True, noise=[n[5:6].contiguous() for n in noises], precision=prec)
+    assert torch.equal(one[0], big[5])
+
+
+def test_golden_vectors(decoder):
+    """Committed fixtures: bytes the REFERENCE's convert_to_audio returned with the oracle as SNAC."""
+    z = np.load(os.path.join(GOLD, "decode_golden.npz"))
+    tokens = z["tokens"]
+    noises = [_cuda(n) for n in synth.make_noises(tokens.shape[0], 16, seed=int(z["noise_seed"]))]
+    pcm, wave = decoder.decode(_cuda(tokens), raw_ids=True, noise=noises, precision="fp32", return_wave=True)
+    assert np.abs(wave.cpu().numpy() - z["wave"]).max() <= FP32_TOL
+    assert np.abs(pcm.cpu().numpy().astype(np.int32) - z["pcm_full"].astype(np.int32)).max() <= 1
+    sl = decoder.decode(_cuda(tokens), raw_ids=True, noise=noises, precision="fp32", extract_slice=True)
+    assert np.abs(sl.cpu().numpy().astype(np.int32) - z["pcm_slice"].astype(np.int32)).max() <= 1
+    tl = z["tokens_long"]
+    nl = [_cuda(n) for n in synth.make_noises(1, 36, seed=int(z["noise_seed_long"]))]
+    pl = decoder.decode(_cuda(tl), raw_ids=True, noise=nl, precision="fp32")
+    assert np.abs(pl.cpu().numpy()[0].astype(np.int32) - z["pcm_long"].astype(np.int32)).max() <= 1
+    pb, wb = decoder.decode(_cuda(tokens), raw_ids=True, noise=noises, precision="bf16", return_wave=True)
+    assert snr_db(z["wave"], wb.cpu().numpy()) >= BF16_SNR_DB
+
+
+def test_decode_host_equals_device(decoder):
+    tokens = synth.make_tokens(9, 4, seed=5)
+    a = decoder.decode_host(tokens, raw_ids=True, extract_slice=True, seed=4)
+    b = decoder.decode(_cuda(tokens), raw_ids=True, extract_slice=True, seed=4)
+    assert np.array_equal(a, b.cpu().numpy())
+
+
+def test_empty_and_bad_arguments(decoder):
+    from tts_inference_b200 import SnacbError
+    e = decoder.decode(torch.empty((0, 28), dtype=torch.int32, device="cuda"), raw_ids=True)
+    assert e.shape == (0, 8192)
+    assert decoder.decode_host(np.zeros((2, 6), dtype=np.int32)).shape == (2, 0)
+    with pytest.raises(SnacbError):
+        decoder._check(decoder._lib.snacb_decode(decoder._h, None, 1, 28, 4, 0, None, 0, None, None, None), "null")
+
+
+# ------------------------------------------------------------------------------------ full-size properties
+def test_full_size_batch_properties(decoder, oracle_model):
+    """BASELINE configs[1]/target size (B=1024 windows): determinism, and sampled windows equal their
+    stand-alone decode and meet the SNR bar against the oracle."""
+    B = 1024
+    tokens = synth.make_tokens(B, 4, seed=20241224)
+    tok = _cuda(tokens)
+    a = decoder.decode_windows(tok, raw_ids=True, seed=9)
+    b = decoder.decode_windows(tok, raw_ids=True, seed=9)
+    assert a.shape == (B, 2048) and torch.equal(a, b)
+    assert int((a != 0).sum()) > B * 1024
+    idx = [0, 511, 1023]
+    nz = synth.make_noises(B, 16, seed=9)
+    sub = [np.ascontiguousarray(n[idx]) for n in nz]
+    ref, _ = oracle_decode(oracle_model, tokens[idx], sub)
+    _, w = decoder.decode(_cuda(tokens[idx]), raw_ids=True, noise=[_cuda(n) for n in sub], return_wave=True)
+    assert snr_db(ref, w.cpu().numpy()) >= BF16_SNR_DB
+    _, wfull = decoder.decode(tok, raw_ids=True, seed=9, return_wave=True, extract_slice=True)
+    assert snr_db(ref[:, 2048:4096], wfull.cpu().numpy()[idx]) >= BF16_SNR_DB - 1.0

@@ -3,6 +3,7 @@
 // PTX ISA "tcgen05" chapter (same fields CUTLASS names in cute/arch/mma_sm100_desc.hpp).
 #pragma once
 #include <cstdint>
+#include <cstdio>
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -40,8 +41,21 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// Spin on try_wait.  A pipeline bug would otherwise hang the GPU until the host kills the process, so a
+// wait that lasts longer than ~2 s of SM clocks traps (the launch then fails with an error instead).
+#ifndef SNACB_WAIT_LIMIT_CYCLES
+#define SNACB_WAIT_LIMIT_CYCLES 4000000000ll
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    while (!mbar_try_wait(bar, parity)) { }
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > SNACB_WAIT_LIMIT_CYCLES) {
+            printf("snacb: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x,
+                   smem_u32(bar), parity);
+            __trap();
+        }
+    }
 }
 
 // generic-proxy smem writes -> visible to the async proxy (TMA / tcgen05 operand reads)
