@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""Benchmark of the SNAC-24 kHz decode hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B]
+
+One "step" = one pass of the hot path over one batch of synthetic token windows: B concurrent
+streams x one 28-token (4-frame) sliding window each -> unpack -> VQ -> decoder -> int16 slice
+[2048:4096].  N>1 runs under torchrun, one rank per GPU, streams sharded with NO data-path
+collective (weak scaling: B windows per GPU); NCCL is used only for the barrier and the
+max-over-ranks of the device time.  Rank 0 prints ONE JSON line.
+
+metric  : audio-sec decoded/sec = windows/s x 8192/24000 (every window is decoded in full: 16 latent
+          steps -> 8192 samples, of which the helper emits 2048; both figures are in the line)
+value   : tokens already in HBM, CUDA-event time of K steps (L2 flushed between steps)
+e2e     : same metric through the host-buffer C-ABI call (pinned host tokens -> H2D -> decode ->
+          D2H -> sync every step) -- the boundary the reference's convert_to_audio has
+roofline: dominant kernel class by share of step time, algorithmic FLOPs / CUDA-event duration vs
+          the measured sustained bf16 tensor peak (MEASURED_PEAKS.json)
+cpu_baseline / --impl reference: the oracle port of the reference's PyTorch SNAC decoder on the
+          host cores (the pip package `snac` is not installable here).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "audio-sec decoded/sec (SNAC 24kHz)"
+UNIT = "audio-s/s"
+FRAMES = 4
+WINDOW_SAMPLES = 2048 * FRAMES
+SR = 24000.0
+FLOP_PER_LATENT_STEP = 207.0e6          # 103.50 M MAC per latent step
+FLOP_PER_WINDOW = 16 * FLOP_PER_LATENT_STEP
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {"bf16_tflops_sustained": d.get("bf16_tflops_sustained", 1389.5), "hbm_gbs": d.get("hbm_gbs", 6552.6),
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+# ----------------------------------------------------------------------------------------------
+# per-stage algorithmic FLOPs for ONE group launch of S windows (F=4), used for the roofline
+# ----------------------------------------------------------------------------------------------
+def stage_flops(S: int) -> dict:
+    out = {}
+    t0 = 16
+    out["stem_pw"] = 2.0 * S * t0 * 768 * 1024
+    cin, t = 1024, t0
+    for bi, s in enumerate((8, 8, 4, 2)):
+        cout = cin // 2
+        tout = t * s
+        out[f"b{bi}.convt"] = 2.0 * S * tout * 2 * cin * cout          # 2 taps per output sample
+        out[f"b{bi}.noise"] = 2.0 * S * tout * cout * cout
+        for ri in range(3):
+            out[f"b{bi}.res{ri}"] = 2.0 * S * tout * (cout * cout + 7 * cout)
+        cin, t = cout, tout
+    out["tail"] = 2.0 * S * 8192 * 64 * 7
+    out["vq_stem"] = 2.0 * S * t0 * 768 * (24 + 7)
+    out["unpack"] = 0.0
+    return out
+
+
+class ClockSampler(threading.Thread):
+    """SM clock / throttle reasons during the timed region (pynvml)."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz, self._stop = index, [], set(), None, threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:  # noqa: BLE001
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40,
+                 "hw_power_brake": 0x80}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop.wait(0.05)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=1)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def cpu_port_rate(batch: int, reps: int, threads: int, state_dict=None):
+    """Oracle port of the reference decoder on the host cores: decoded audio-s/s, protocol of
+    tensorrt_tts/hindi_finetuned/benchmark.py:219-247 (tensor construction + clamp + decode + int16)."""
+    import torch
+    from oracle import glue_ref, synth_ckpt
+    from tts_inference_b200 import synth
+    torch.set_num_threads(threads)
+    model = synth_ckpt.make_model(0, state_dict=state_dict)
+    tokens = synth.make_tokens(batch, FRAMES)
+    codes = tokens.astype(np.int64) - 128266
+
+    def one():
+        lv = glue_ref.unpack_np(codes)
+        y = model.decode([torch.from_numpy(x.astype(np.int64)) for x in lv])
+        return glue_ref.pcm16_torch(y[:, :, 2048:4096])
+
+    one()
+    t = time.perf_counter()
+    for _ in range(reps):
+        one()
+    dt = (time.perf_counter() - t) / reps
+    return batch * WINDOW_SAMPLES / SR / dt, dt
+
+
+def run_reference(args, rank: int, world: int):
+    """--impl reference: the reference's own CPU implementation of the path = oracle port (the pip
+    package `snac` cannot be installed offline), all host threads, bounded sample per step."""
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    batch = 16
+    import torch
+    from oracle import glue_ref, synth_ckpt
+    from tts_inference_b200 import synth
+    torch.set_num_threads(threads)
+    model = synth_ckpt.make_model(0)
+    codes = synth.make_tokens(batch, FRAMES).astype(np.int64) - 128266
+
+    def step():
+        lv = glue_ref.unpack_np(codes)
+        y = model.decode([torch.from_numpy(x.astype(np.int64)) for x in lv])
+        return glue_ref.pcm16_torch(y[:, :, 2048:4096])
+
+    for _ in range(max(args.warmup, 1)):
+        step()
+    t = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t) / args.steps
+    v = batch * WINDOW_SAMPLES / SR / dt
+    sample = f"{batch} windows x 28 tokens per step (of the arm's {args.batch}), oracle port, torch {torch.__version__} CPU fp32"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args.batch), "sample_windows_per_step": batch},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(batch: int) -> str:
+    return (f"batched streaming decode: {batch} concurrent streams x one 28-token (4-frame) sliding window per step "
+            f"per GPU, slice [2048:4096] -> int16 (BASELINE configs[1] shape at the north_star batch)")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=1024)
+    ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-out", default=None, help="write the per-stage table here (json)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from tts_inference_b200 import SnacDecoder, synth
+
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    B = args.batch
+    sd = synth.make_state_dict(0)
+    dec = SnacDecoder(sd, device=local_rank)
+    # every rank decodes its own B streams (stream ids rank*B .. rank*B+B-1): weak scaling, no exchange
+    tokens = synth.make_tokens(B, FRAMES, seed=20241224 + rank)
+    tok_dev = torch.from_numpy(tokens).cuda()
+    pcm_dev = torch.empty((B, 2048), dtype=torch.int16, device="cuda")
+    tok_pin = torch.from_numpy(tokens).pin_memory()
+    pcm_pin = torch.empty((B, 2048), dtype=torch.int16).pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")     # > 126 MB L2
+
+    def step(i):
+        dec.decode(tok_dev, raw_ids=True, extract_slice=True, seed=i, precision=args.precision, out=pcm_dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+
+    # ------------------------------------------------------------------ timed region (device-resident inputs)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = dec.stats()[0]
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    t_wall = time.perf_counter()
+    for i in range(args.steps):
+        flush.zero_()                       # evict L2 between timed steps (not timed)
+        ev[i][0].record()
+        step(100 + i)
+        ev[i][1].record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall
+    launches = dec.stats()[0] - l0
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    clocks = sampler.stop()
+
+    # ------------------------------------------------------------------ e2e (host buffers, copies inside)
+    for i in range(2):
+        dec.decode_host_ptr(tok_pin.data_ptr(), B, 28, pcm_pin.data_ptr(), raw_ids=True, extract_slice=True,
+                            seed=i, precision=args.precision)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        dec.decode_host_ptr(tok_pin.data_ptr(), B, 28, pcm_pin.data_ptr(), raw_ids=True, extract_slice=True,
+                            seed=200 + i, precision=args.precision)
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    assert int((pcm_pin != 0).sum()) > B * 512, "e2e output looks empty"
+
+    # max over ranks
+    times = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = float(times[0]), float(times[1])
+
+    # ------------------------------------------------------------------ per-stage profile (separate pass)
+    prof = None
+    if rank == 0:
+        dec.profile(True)
+        nprof = min(args.steps, 5)
+        for i in range(nprof):
+            step(300 + i)
+        rep = dec.profile_report()
+        dec.profile(False)
+        tot = sum(ms for _, ms in rep.values())
+        groups = max(1, rep["tail"][0] // nprof)
+        S = -(-B // groups)
+        fl = stage_flops(S)
+        classes = {}
+        for name, (cnt, ms) in rep.items():
+            cls = name.split(".")[1].rstrip("012") if "." in name else name       # convt / noise / res / ...
+            c = classes.setdefault(cls, {"ms": 0.0, "launches": 0, "flop": 0.0})
+            c["ms"] += ms; c["launches"] += cnt; c["flop"] += fl.get(name, 0.0) * cnt
+        top = max(classes, key=lambda k: classes[k]["ms"])
+        prof = {"stages": {k: {"launches": c, "total_ms": ms, "share": ms / tot,
+                               "tflops": (fl.get(k, 0.0) * c / (ms * 1e-3) / 1e12) if ms > 0 else 0.0}
+                           for k, (c, ms) in rep.items()},
+                "classes": {k: {"share": v["ms"] / tot, "avg_launch_ms": v["ms"] / v["launches"],
+                                "tflops": v["flop"] / (v["ms"] * 1e-3) / 1e12} for k, v in classes.items()},
+                "top": top, "streams_per_launch": S, "steps": nprof}
+        if args.profile_out:
+            os.makedirs(os.path.dirname(os.path.abspath(args.profile_out)), exist_ok=True)
+            with open(args.profile_out, "w") as f:
+                json.dump(prof, f, indent=1)
+
+    if rank == 0:
+        peaks = measured_peaks()
+        windows = B * world * args.steps
+        value = windows * WINDOW_SAMPLES / SR / (dev_ms * 1e-3)
+        e2e = windows * WINDOW_SAMPLES / SR / (e2e_ms * 1e-3)
+        topc = prof["classes"][prof["top"]]
+        roof = {"bound": "tensor", "kernel": {"res": "k_resunit_tc", "convt": "k_gemm_tc(convT)", "noise": "k_gemm_tc(noise)"}.get(prof["top"], prof["top"]),
+                "achieved": topc["tflops"], "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                "frac": topc["tflops"] / peaks["bf16_tflops_sustained"], "traffic": None,
+                "share_of_step": topc["share"], "avg_launch_ms": topc["avg_launch_ms"], "peak_source": peaks["source"],
+                "whole_step": {"achieved": FLOP_PER_WINDOW * B * world * args.steps / (dev_ms * 1e-3) / 1e12 / world,
+                               "frac": FLOP_PER_WINDOW * B * args.steps / (dev_ms * 1e-3) / 1e12 / peaks["bf16_tflops_sustained"]}}
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            v, dt = cpu_port_rate(16, 8, threads, state_dict=sd)
+            cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                   "sample": f"8 x 16 windows (of {B}), oracle port of the reference PyTorch decoder, fp32, {dt * 1e3:.0f} ms per 16"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": {"fp16": "f16 operands, f32 accumulate", "bf16": "bf16 operands, f32 accumulate", "fp32": "f32"}[args.precision],
+            "data": "synthetic",
+            "config": {"workload": workload_name(B), "windows_per_gpu_per_step": B, "frames_per_window": FRAMES,
+                       "weights": "random-init snac_24khz decode architecture (seed 0)",
+                       "timing": "CUDA events per step, L2 flushed (256 MiB memset) between timed steps",
+                       "emitted_audio_s_per_s": value / 4.0, "windows_per_s": value * SR / WINDOW_SAMPLES,
+                       "wall_s_timed_region": t_wall},
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": B * 28 * 4, "d2h_bytes_per_step": B * 2048 * 2},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roof,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

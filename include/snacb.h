@@ -43,10 +43,12 @@ typedef enum {
                                       already `id - 128266`, as convert_to_audio receives them */
 #define SNACB_EXTRACT_SLICE  0x2   /* keep samples [2048:4096] when more than 4096 were decoded
                                       (modal_audio_stream.py:94-95,195-198)                    */
-#define SNACB_FP32           0x4   /* fp32 CUDA-core arithmetic end to end (config 1);
-                                      default is bf16 tensor-core contractions, fp32 accumulate */
+#define SNACB_FP32           0x4   /* fp32 CUDA-core arithmetic end to end (config 1).  Default: tensor-core
+                                      contractions (tcgen05, kind::f16) with fp16 operands, fp32 accumulate  */
 #define SNACB_KEEP_TAPS      0x8   /* debug: keep every stage's output for snacb_debug_tap     */
-#define SNACB_STREAM_FP32    0x10  /* bf16 path: keep the residual stream in fp32 between kernels */
+#define SNACB_STREAM_FP32    0x10  /* tensor-core path: keep the residual stream in fp32 between kernels  */
+#define SNACB_BF16           0x20  /* tensor-core path: bf16 operands / activations instead of fp16 (same
+                                      rate; 3 fewer mantissa bits -- see DESIGN.md "precision")              */
 
 /* Folded fp32 weights of the decode half of snac_24khz, host pointers.  Weight-norm is already
  * folded (w = g * v / ||v||, norm over dim 0: per OUTPUT channel for Conv1d, per INPUT channel for
@@ -125,6 +127,12 @@ int snacb_set_group_bytes(snacb_handle h, size_t bytes);
 
 /* Counters since creation: kernels launched by this library, streams decoded. */
 int snacb_stats(snacb_handle h, uint64_t* kernel_launches, uint64_t* streams_decoded);
+
+/* Per-launch CUDA-event timing of the pipeline stages (measurement aid; adds two event records per
+ * launch, so do not time a headline number with it on).  snacb_profile(h,1) starts a fresh recording,
+ * snacb_profile_report synchronises and writes one line per stage: "<name> <launches> <total_ms>". */
+int snacb_profile(snacb_handle h, int enable);
+int snacb_profile_report(snacb_handle h, char* buf, size_t cap);
 
 /* Debug taps (SNACB_KEEP_TAPS): stage outputs of the LAST group decoded, converted to fp32,
  * channel-last [rows][cols].  names: "stem_dw","stem","b{0..3}.convt","b{i}.noise","b{i}.res{0..2}". */

@@ -19,7 +19,7 @@ from tts_inference_b200 import SnacDecoder, synth  # noqa: E402
 def main():
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 3
     F_ = int(sys.argv[2]) if len(sys.argv) > 2 else 4
-    modes = sys.argv[3].split(",") if len(sys.argv) > 3 else ["fp32", "bf16", "bf16s"]
+    modes = sys.argv[3].split(",") if len(sys.argv) > 3 else ["fp32", "bf16", "bf16s", "fp16", "fp16s"]
     sd = synth.make_state_dict(0)
     model = synth_ckpt.make_model(0, state_dict=sd)
     tokens = synth.make_tokens(B, F_, bad_frac=0.02)
@@ -31,10 +31,10 @@ def main():
     tok = torch.from_numpy(tokens).cuda()
     nz = [torch.from_numpy(n).cuda() for n in noises]
     for mode in modes:
-        prec = "fp32" if mode == "fp32" else "bf16"
+        prec = mode.rstrip("s")
         try:
             pcm, wave = dec.decode(tok, raw_ids=True, noise=nz, precision=prec, return_wave=True, keep_taps=True,
-                                   stream_fp32=(mode == "bf16s"))
+                                   stream_fp32=mode.endswith("s"))
             torch.cuda.synchronize()
         except Exception as e:  # noqa: BLE001
             print(f"[{mode}] FAILED: {e}", flush=True)

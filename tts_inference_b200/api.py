@@ -61,12 +61,13 @@ class SnacDecoder:
 
     @staticmethod
     def _flags(raw_ids, extract_slice, precision, keep_taps=False, stream_fp32=False) -> int:
-        if precision not in ("bf16", "fp32"):
-            raise ValueError("precision must be 'bf16' or 'fp32'")
+        if precision not in ("fp16", "bf16", "fp32"):
+            raise ValueError("precision must be 'fp16', 'bf16' or 'fp32'")
         f = 0
         f |= _lib.RAW_IDS if raw_ids else 0
         f |= _lib.EXTRACT_SLICE if extract_slice else 0
         f |= _lib.FP32 if precision == "fp32" else 0
+        f |= _lib.BF16 if precision == "bf16" else 0
         f |= _lib.KEEP_TAPS if keep_taps else 0
         f |= _lib.STREAM_FP32 if stream_fp32 else 0
         return f
@@ -98,7 +99,7 @@ class SnacDecoder:
         return c0, c1, c2
 
     def decode(self, tokens, *, raw_ids: bool = False, extract_slice: bool = False,
-               noise: Optional[Sequence] = None, seed: int = 0, precision: str = "bf16",
+               noise: Optional[Sequence] = None, seed: int = 0, precision: str = "fp16",
                out=None, return_wave: bool = False, keep_taps: bool = False, stream_fp32: bool = False):
         """tokens: cuda int32 [B, n>=7F] (trailing partial frame ignored, as the helper does).
         Returns int16 [B, samples] (and the fp32 waveform when ``return_wave``)."""
@@ -143,7 +144,7 @@ class SnacDecoder:
 
     # ------------------------------------------------------------------ host API (what the helper's caller sees)
     def decode_host(self, tokens: np.ndarray, *, raw_ids: bool = False, extract_slice: bool = False,
-                    seed: int = 0, precision: str = "bf16", out: Optional[np.ndarray] = None) -> np.ndarray:
+                    seed: int = 0, precision: str = "fp16", out: Optional[np.ndarray] = None) -> np.ndarray:
         tokens = np.ascontiguousarray(tokens, dtype=np.int32)
         assert tokens.ndim == 2
         B, n = tokens.shape
@@ -159,11 +160,25 @@ class SnacDecoder:
         return out
 
     def decode_host_ptr(self, tok_ptr: int, B: int, n: int, pcm_ptr: int, *, raw_ids=False, extract_slice=False,
-                        seed: int = 0, precision: str = "bf16"):
+                        seed: int = 0, precision: str = "fp16"):
         """Same, raw host pointers (e.g. pinned torch tensors) -- used by the benchmark's e2e leg."""
         rc = self._lib.snacb_decode_host(self._h, tok_ptr, B, n, n // FRAME,
                                          self._flags(raw_ids, extract_slice, precision), C.c_uint64(seed), pcm_ptr)
         self._check(rc, "snacb_decode_host")
+
+    # ------------------------------------------------------------------ per-stage timing
+    def profile(self, enable: bool = True):
+        self._check(self._lib.snacb_profile(self._h, 1 if enable else 0), "snacb_profile")
+
+    def profile_report(self) -> Dict[str, Tuple[int, float]]:
+        """{stage: (launches, total_ms)} since profile(True); synchronises the device."""
+        buf = C.create_string_buffer(1 << 16)
+        self._check(self._lib.snacb_profile_report(self._h, buf, len(buf)), "snacb_profile_report")
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, cnt, ms = line.split()
+            out[name] = (int(cnt), float(ms))
+        return out
 
     # ------------------------------------------------------------------ debug taps
     def taps(self) -> Dict[str, np.ndarray]:

@@ -20,12 +20,13 @@ POLICY_SLIDING = 1   # constants' rule (modal_audio_stream.py:86-95): last 28 ev
 
 class WindowBatcher:
     def __init__(self, decoder: SnacDecoder, policy: int = POLICY_CHUNK, raw_ids: bool = True,
-                 max_windows: int = 1024, precision: str = "bf16"):
+                 max_windows: int = 1024, precision: str = "fp16"):
         self._lib = _lib.load()
         self._dec = decoder
         self._b = C.c_void_p()
         self.max_windows = int(max_windows)
-        flags = (_lib.RAW_IDS if raw_ids else 0) | (_lib.FP32 if precision == "fp32" else 0)
+        flags = (_lib.RAW_IDS if raw_ids else 0) | (_lib.FP32 if precision == "fp32" else 0) | \
+            (_lib.BF16 if precision == "bf16" else 0)
         rc = self._lib.snacb_batcher_create(C.byref(self._b), decoder._h, int(policy), flags, self.max_windows)
         if rc != 0:
             raise SnacbError(f"snacb_batcher_create failed ({rc})")

@@ -70,7 +70,7 @@ int snacb_batcher_create(snacb_batcher* out, snacb_handle h, int policy, int fla
     snacb_batcher b = new (std::nothrow) snacb_batcher_s();
     if (!b) return SNACB_ERR_NOMEM;
     b->h = h; b->policy = policy; b->max_windows = max_windows;
-    b->flags = flags & (SNACB_RAW_IDS | SNACB_FP32 | SNACB_STREAM_FP32);
+    b->flags = flags & (SNACB_RAW_IDS | SNACB_FP32 | SNACB_STREAM_FP32 | SNACB_BF16);
     if (policy == 1) b->flags |= SNACB_EXTRACT_SLICE;
     if (cudaMallocHost(reinterpret_cast<void**>(&b->pin_tok), static_cast<size_t>(max_windows) * kWindow * 4) != cudaSuccess ||
         cudaMallocHost(reinterpret_cast<void**>(&b->pin_pcm), static_cast<size_t>(max_windows) * 8192 * 2) != cudaSuccess) {

@@ -2,6 +2,7 @@
 #pragma once
 #include <cstdint>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 namespace snacb {
@@ -41,7 +42,7 @@ struct GemmArgs {
     unsigned long long seed;
     int noise_stage;        // decoder block index, keys the counter RNG
     int stream_offset;      // global index of stream 0 of this chunk (counter RNG addressing)
-    const void* resid;      // residual / y tensor, [S*Tin*up][Cout], same dtype as out
+    const void* resid;      // residual / y tensor, [S*Tin*up][Cout] (16-bit operand type on the tensor-core path)
     void* out;              // [S*Tin*up][Cout]
 };
 
@@ -111,7 +112,31 @@ __device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&v)[8]) {
     for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
     *reinterpret_cast<uint4*>(p) = raw;
 }
+__device__ __forceinline__ void load8(const __half* p, float (&v)[8]) {
+    uint4 raw = *reinterpret_cast<const uint4*>(p);
+    const __half2* h = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { float2 f = __half22float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+}
+__device__ __forceinline__ void store8(__half* p, const float (&v)[8]) {
+    uint4 raw;
+    __half2* h = reinterpret_cast<__half2*>(&raw);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+    *reinterpret_cast<uint4*>(p) = raw;
+}
+// two fp32 -> packed pair of the 16-bit operand type
+__device__ __forceinline__ uint32_t pack2(float a, float b, const __nv_bfloat16*) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ uint32_t pack2(float a, float b, const __half*) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
 __device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(__half v) { return __half2float(v); }
+__device__ __forceinline__ void from_f32(__half& d, float v) { d = __float2half_rn(v); }
 __device__ __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
 __device__ __forceinline__ void from_f32(float& d, float v) { d = v; }
 __device__ __forceinline__ void from_f32(__nv_bfloat16& d, float v) { d = __float2bfloat16_rn(v); }

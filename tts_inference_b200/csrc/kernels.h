@@ -4,6 +4,7 @@
 #include <cstdint>
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include "common.cuh"
@@ -35,9 +36,11 @@ void launch_to_f32(const T* in, float* out, size_t n, cudaStream_t st);
 // ---- kernels_tc.cu  (tcgen05 / TMEM / TMA)
 // out dtype: 0 = bf16, 1 = fp32.  Returns cudaError_t of the launch.
 int gemm_tc_block_n(const GemmArgs& a);   // column-tile width the tensor-core GEMM will use for this problem
-cudaError_t launch_gemm_tc(int epi, int out_f32, const GemmArgs& a, const CUtensorMap& tmA, const CUtensorMap& tmW,
-                           int sm_count, cudaStream_t st);
-cudaError_t launch_resunit_tc(int epi, int x_f32, const ResUnitArgs& a, const CUtensorMap& tmW, cudaStream_t st);
+// half_fp16: 16-bit operand / storage type, 0 = bf16, 1 = fp16 (same tensor-core rate, fp32 accumulate)
+cudaError_t launch_gemm_tc(int epi, int half_fp16, int out_f32, const GemmArgs& a, const CUtensorMap& tmA,
+                           const CUtensorMap& tmW, int sm_count, cudaStream_t st);
+cudaError_t launch_resunit_tc(int epi, int half_fp16, int x_f32, const ResUnitArgs& a, const CUtensorMap& tmW,
+                              cudaStream_t st);
 cudaError_t init_tc_kernels();            // opt-in shared memory sizes
 
 }  // namespace snacb

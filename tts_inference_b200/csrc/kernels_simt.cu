@@ -87,10 +87,8 @@ k_vq_stem(const int32_t* __restrict__ c0, const int32_t* __restrict__ c1, const 
     __syncthreads();
     for (int c = threadIdx.x; c < kLatent; c += blockDim.x) {
         float wv[3][kCodeDim];
-        float bsum = 0.f;
 #pragma unroll
         for (int lv = 0; lv < 3; ++lv) {
-            bsum += w.out_b[lv][c];
 #pragma unroll
             for (int j = 0; j < kCodeDim; ++j) wv[lv][j] = w.out_w[lv][c * kCodeDim + j];
         }
@@ -107,7 +105,6 @@ k_vq_stem(const int32_t* __restrict__ c0, const int32_t* __restrict__ c1, const 
             }
             z[u] = ok[u] ? acc : 0.f;
         }
-        (void)bsum;
         float dw[7];
 #pragma unroll
         for (int j = 0; j < 7; ++j) dw[j] = w.dw_w[j * kLatent + c];
@@ -135,6 +132,8 @@ template void launch_vq_stem<float>(const int32_t*, const int32_t*, const int32_
                                     float*, cudaStream_t);
 template void launch_vq_stem<__nv_bfloat16>(const int32_t*, const int32_t*, const int32_t*, int, int,
                                             const VqStemWeights&, __nv_bfloat16*, cudaStream_t);
+template void launch_vq_stem<__half>(const int32_t*, const int32_t*, const int32_t*, int, int, const VqStemWeights&,
+                                     __half*, cudaStream_t);
 
 // ----------------------------------------------------------------------------------------------
 // fp32 row-GEMM with taps (CUDA cores).  64x64 tile, 16-deep K steps, 4x4 register micro-tile.
@@ -334,6 +333,7 @@ void launch_tail(const InT* a, int S, int T, int t_begin, int n_out, const float
 template void launch_tail<float>(const float*, int, int, int, int, const float*, float, int16_t*, float*, cudaStream_t);
 template void launch_tail<__nv_bfloat16>(const __nv_bfloat16*, int, int, int, int, const float*, float, int16_t*,
                                          float*, cudaStream_t);
+template void launch_tail<__half>(const __half*, int, int, int, int, const float*, float, int16_t*, float*, cudaStream_t);
 
 // ----------------------------------------------------------------------------------------------
 template <typename T>
@@ -351,5 +351,6 @@ void launch_to_f32(const T* in, float* out, size_t n, cudaStream_t st) {
 }
 template void launch_to_f32<float>(const float*, float*, size_t, cudaStream_t);
 template void launch_to_f32<__nv_bfloat16>(const __nv_bfloat16*, float*, size_t, cudaStream_t);
+template void launch_to_f32<__half>(const __half*, float*, size_t, cudaStream_t);
 
 }  // namespace snacb

@@ -24,6 +24,10 @@ __device__ __forceinline__ uint8_t* align1024(uint8_t* p) {
     return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~static_cast<uintptr_t>(1023));
 }
 
+template <typename HT> struct HalfFmt;
+template <> struct HalfFmt<__half> { static constexpr uint32_t kFmt = 0; };
+template <> struct HalfFmt<__nv_bfloat16> { static constexpr uint32_t kFmt = 1; };
+
 template <typename T>
 __device__ __forceinline__ void load32(const T* p, float (&v)[32]) {
 #pragma unroll
@@ -58,7 +62,7 @@ struct GemmTcCfg {
     static constexpr int kTmemCols = 2 * BN;   // two accumulator stages
 };
 
-template <int BN, int EPI, typename OutT>
+template <int BN, int EPI, typename HT, typename OutT>
 __global__ void __launch_bounds__(192, 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const GemmArgs a,
           const int num_m_tiles, const int num_n_tiles) {
@@ -116,7 +120,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
-        constexpr uint32_t idesc = umma_idesc_bf16(kTileM, BN);
+        constexpr uint32_t idesc = umma_idesc_f16(kTileM, BN, HalfFmt<HT>::kFmt);
         int stage = 0; uint32_t phase = 0;
         int as = 0; uint32_t aphase = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -131,7 +135,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     const uint32_t sw = sa + kABytes;
 #pragma unroll
                     for (int k = 0; k < kChunkK / 16; ++k)
-                        mma_bf16_ss(d_tmem, umma_desc_sw128(sa + k * 32), umma_desc_sw128(sw + k * 32), idesc,
+                        mma_f16_ss(d_tmem, umma_desc_sw128(sa + k * 32), umma_desc_sw128(sw + k * 32), idesc,
                                     (kk > 0 || k > 0) ? 1u : 0u);
                     mma_commit(&empty[stage]);
                 }
@@ -185,7 +189,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     }
                     if (EPI == EPI_NOISE) {
                         float y[32];
-                        load32(static_cast<const __nv_bfloat16*>(a.resid) + orow * a.Cout + o, y);
+                        load32(static_cast<const HT*>(a.resid) + orow * a.Cout + o, y);
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = fmaf(nz, v[j], y[j]);
                     }
@@ -221,13 +225,13 @@ int gemm_tc_block_n(const GemmArgs& a) {
     return 64;
 }
 
-template <int BN, int EPI, typename OutT>
+template <int BN, int EPI, typename HT, typename OutT>
 static cudaError_t launch_gemm_tc_t(const GemmArgs& a, const CUtensorMap& tmA, const CUtensorMap& tmW, int sm_count,
                                     cudaStream_t st) {
     using Cfg = GemmTcCfg<BN>;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(k_gemm_tc<BN, EPI, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(k_gemm_tc<BN, EPI, HT, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              Cfg::kSmem);
         if (e != cudaSuccess) return e;
         attr_done = true;
@@ -239,29 +243,35 @@ static cudaError_t launch_gemm_tc_t(const GemmArgs& a, const CUtensorMap& tmA, c
     const int ctas_per_sm = (BN == 256) ? 1 : 2;
     int grid = total < sm_count * ctas_per_sm ? total : sm_count * ctas_per_sm;
     if (grid < 1) grid = 1;
-    k_gemm_tc<BN, EPI, OutT><<<grid, 192, Cfg::kSmem, st>>>(tmA, tmW, a, num_m, num_n);
+    k_gemm_tc<BN, EPI, HT, OutT><<<grid, 192, Cfg::kSmem, st>>>(tmA, tmW, a, num_m, num_n);
     return cudaGetLastError();
 }
 
-template <int EPI, typename OutT>
+template <int EPI, typename HT, typename OutT>
 static cudaError_t launch_gemm_tc_e(const GemmArgs& a, const CUtensorMap& tmA, const CUtensorMap& tmW, int sm_count,
                                     cudaStream_t st) {
     switch (gemm_tc_block_n(a)) {
-        case 256: return launch_gemm_tc_t<256, EPI, OutT>(a, tmA, tmW, sm_count, st);
-        case 128: return launch_gemm_tc_t<128, EPI, OutT>(a, tmA, tmW, sm_count, st);
-        default: return launch_gemm_tc_t<64, EPI, OutT>(a, tmA, tmW, sm_count, st);
+        case 256: return launch_gemm_tc_t<256, EPI, HT, OutT>(a, tmA, tmW, sm_count, st);
+        case 128: return launch_gemm_tc_t<128, EPI, HT, OutT>(a, tmA, tmW, sm_count, st);
+        default: return launch_gemm_tc_t<64, EPI, HT, OutT>(a, tmA, tmW, sm_count, st);
     }
 }
 
-cudaError_t launch_gemm_tc(int epi, int out_f32, const GemmArgs& a, const CUtensorMap& tmA, const CUtensorMap& tmW,
-                           int sm_count, cudaStream_t st) {
-    if (epi == EPI_BIAS) return launch_gemm_tc_e<EPI_BIAS, __nv_bfloat16>(a, tmA, tmW, sm_count, st);
-    if (epi == EPI_BIAS_SNAKE) return launch_gemm_tc_e<EPI_BIAS_SNAKE, __nv_bfloat16>(a, tmA, tmW, sm_count, st);
+template <typename HT>
+static cudaError_t launch_gemm_tc_h(int epi, int out_f32, const GemmArgs& a, const CUtensorMap& tmA,
+                                    const CUtensorMap& tmW, int sm_count, cudaStream_t st) {
+    if (epi == EPI_BIAS) return launch_gemm_tc_e<EPI_BIAS, HT, HT>(a, tmA, tmW, sm_count, st);
+    if (epi == EPI_BIAS_SNAKE) return launch_gemm_tc_e<EPI_BIAS_SNAKE, HT, HT>(a, tmA, tmW, sm_count, st);
     if (epi == EPI_NOISE) {
-        if (out_f32) return launch_gemm_tc_e<EPI_NOISE, float>(a, tmA, tmW, sm_count, st);
-        return launch_gemm_tc_e<EPI_NOISE, __nv_bfloat16>(a, tmA, tmW, sm_count, st);
+        if (out_f32) return launch_gemm_tc_e<EPI_NOISE, HT, float>(a, tmA, tmW, sm_count, st);
+        return launch_gemm_tc_e<EPI_NOISE, HT, HT>(a, tmA, tmW, sm_count, st);
     }
     return cudaErrorInvalidValue;
+}
+cudaError_t launch_gemm_tc(int epi, int half_fp16, int out_f32, const GemmArgs& a, const CUtensorMap& tmA,
+                           const CUtensorMap& tmW, int sm_count, cudaStream_t st) {
+    return half_fp16 ? launch_gemm_tc_h<__half>(epi, out_f32, a, tmA, tmW, sm_count, st)
+                     : launch_gemm_tc_h<__nv_bfloat16>(epi, out_f32, a, tmA, tmW, sm_count, st);
 }
 
 // =================================================================================================
@@ -281,7 +291,7 @@ struct ResTcCfg {
     }
 };
 
-template <int C, int EPI, typename XT, typename OutT>
+template <int C, int EPI, typename HT, typename XT, typename OutT>
 __global__ void __launch_bounds__(320, 1)
 k_resunit_tc(const __grid_constant__ CUtensorMap tmW, const ResUnitArgs a) {
     using Cfg = ResTcCfg<C>;
@@ -337,7 +347,7 @@ k_resunit_tc(const __grid_constant__ CUtensorMap tmW, const ResUnitArgs a) {
         }
     } else if (warp == 9) {
         // ------------------------------------------------------------------ MMA issuer
-        constexpr uint32_t idesc = umma_idesc_bf16(kTileM, Cfg::kMmaN);
+        constexpr uint32_t idesc = umma_idesc_f16(kTileM, Cfg::kMmaN, HalfFmt<HT>::kFmt);
         for (int kc = 0; kc < Cfg::kChunks; ++kc) {
             const int sa = kc % Cfg::kNSA, sw = kc % Cfg::kNSW;
             mbar_wait(&w_full[sw], (kc / Cfg::kNSW) & 1);
@@ -350,7 +360,7 @@ k_resunit_tc(const __grid_constant__ CUtensorMap tmW, const ResUnitArgs a) {
                 for (int k = 0; k < kChunkK / 16; ++k) {
 #pragma unroll
                     for (int nh = 0; nh < Cfg::kNHalf; ++nh)
-                        mma_bf16_ss(tmem_base + nh * 256, umma_desc_sw128(a_addr + k * 32),
+                        mma_f16_ss(tmem_base + nh * 256, umma_desc_sw128(a_addr + k * 32),
                                     umma_desc_sw128(w_addr + nh * (256 * 128) + k * 32), idesc,
                                     (kc > 0 || k > 0) ? 1u : 0u);
                 }
@@ -412,8 +422,8 @@ k_resunit_tc(const __grid_constant__ CUtensorMap tmW, const ResUnitArgs a) {
                     }
                     acc0 = snake_f<true>(acc0, a2.x, i2.x);
                     acc1 = snake_f<true>(acc1, a2.y, i2.y);
-                    *reinterpret_cast<__nv_bfloat162*>(dstA + sw128_offset(r, 2 * lane)) =
-                        __floats2bfloat162_rn(acc0, acc1);
+                    *reinterpret_cast<uint32_t*>(dstA + sw128_offset(r, 2 * lane)) =
+                        pack2(acc0, acc1, static_cast<const HT*>(nullptr));
                 }
             }
             fence_proxy_async_smem();
@@ -466,44 +476,51 @@ k_resunit_tc(const __grid_constant__ CUtensorMap tmW, const ResUnitArgs a) {
     if (warp == 9) tmem_dealloc(tmem_base, C);
 }
 
-template <int C, int EPI, typename XT, typename OutT>
+template <int C, int EPI, typename HT, typename XT, typename OutT>
 static cudaError_t launch_resunit_tc_t(const ResUnitArgs& a, const CUtensorMap& tmW, cudaStream_t st) {
     using Cfg = ResTcCfg<C>;
     static int attr_smem = 0;
     const int smem = Cfg::smem_bytes(a.dil);
     if (smem > attr_smem) {
-        cudaError_t e = cudaFuncSetAttribute(k_resunit_tc<C, EPI, XT, OutT>,
+        cudaError_t e = cudaFuncSetAttribute(k_resunit_tc<C, EPI, HT, XT, OutT>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::smem_bytes(9));
         if (e != cudaSuccess) return e;
         attr_smem = Cfg::smem_bytes(9);
     }
     const int tiles = a.S * ((a.T + kTileM - 1) / kTileM);
     if (tiles == 0) return cudaSuccess;
-    k_resunit_tc<C, EPI, XT, OutT><<<tiles, 320, smem, st>>>(tmW, a);
+    k_resunit_tc<C, EPI, HT, XT, OutT><<<tiles, 320, smem, st>>>(tmW, a);
     return cudaGetLastError();
 }
 
-template <int EPI, typename XT, typename OutT>
+template <int EPI, typename HT, typename XT, typename OutT>
 static cudaError_t launch_resunit_tc_c(const ResUnitArgs& a, const CUtensorMap& tmW, cudaStream_t st) {
     switch (a.C) {
-        case 512: return launch_resunit_tc_t<512, EPI, XT, OutT>(a, tmW, st);
-        case 256: return launch_resunit_tc_t<256, EPI, XT, OutT>(a, tmW, st);
-        case 128: return launch_resunit_tc_t<128, EPI, XT, OutT>(a, tmW, st);
-        case 64: return launch_resunit_tc_t<64, EPI, XT, OutT>(a, tmW, st);
+        case 512: return launch_resunit_tc_t<512, EPI, HT, XT, OutT>(a, tmW, st);
+        case 256: return launch_resunit_tc_t<256, EPI, HT, XT, OutT>(a, tmW, st);
+        case 128: return launch_resunit_tc_t<128, EPI, HT, XT, OutT>(a, tmW, st);
+        case 64: return launch_resunit_tc_t<64, EPI, HT, XT, OutT>(a, tmW, st);
         default: return cudaErrorInvalidValue;
     }
 }
 
-cudaError_t launch_resunit_tc(int epi, int x_f32, const ResUnitArgs& a, const CUtensorMap& tmW, cudaStream_t st) {
+template <typename HT>
+static cudaError_t launch_resunit_tc_h(int epi, int x_f32, const ResUnitArgs& a, const CUtensorMap& tmW,
+                                       cudaStream_t st) {
     if (epi == EPI_RES) {
-        if (x_f32) return launch_resunit_tc_c<EPI_RES, float, float>(a, tmW, st);
-        return launch_resunit_tc_c<EPI_RES, __nv_bfloat16, __nv_bfloat16>(a, tmW, st);
+        if (x_f32) return launch_resunit_tc_c<EPI_RES, HT, float, float>(a, tmW, st);
+        return launch_resunit_tc_c<EPI_RES, HT, HT, HT>(a, tmW, st);
     }
     if (epi == EPI_RES_SNAKE) {
-        if (x_f32) return launch_resunit_tc_c<EPI_RES_SNAKE, float, __nv_bfloat16>(a, tmW, st);
-        return launch_resunit_tc_c<EPI_RES_SNAKE, __nv_bfloat16, __nv_bfloat16>(a, tmW, st);
+        if (x_f32) return launch_resunit_tc_c<EPI_RES_SNAKE, HT, float, HT>(a, tmW, st);
+        return launch_resunit_tc_c<EPI_RES_SNAKE, HT, HT, HT>(a, tmW, st);
     }
     return cudaErrorInvalidValue;
+}
+cudaError_t launch_resunit_tc(int epi, int half_fp16, int x_f32, const ResUnitArgs& a, const CUtensorMap& tmW,
+                              cudaStream_t st) {
+    return half_fp16 ? launch_resunit_tc_h<__half>(epi, x_f32, a, tmW, st)
+                     : launch_resunit_tc_h<__nv_bfloat16>(epi, x_f32, a, tmW, st);
 }
 
 cudaError_t init_tc_kernels() { return cudaSuccess; }

@@ -12,6 +12,7 @@
 
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include "../../include/snacb.h"
@@ -29,16 +30,16 @@ thread_local std::string g_create_error;
 
 struct ResW {
     float *alpha1, *inv1, *dw_w, *dw_b, *alpha2, *inv2, *pw_f32, *pw_b;
-    __nv_bfloat16* pw_bf16;
-    CUtensorMap tm_pw;      // box (64, min(C,256)) for k_resunit_tc
+    void* pw_h[2];          // 16-bit copies: [0] bf16, [1] fp16
+    CUtensorMap tm_pw[2];   // box (64, min(C,256)) for k_resunit_tc
 };
 struct BlockW {
     int Cin, Cout, s;
     float *alpha, *inv_alpha;           // Snake in front of the ConvTranspose (applied by the producer epilogue)
     float *ct_f32, *ct_b;               // packed [s*Cout][2*Cin]
-    __nv_bfloat16* ct_bf16;
+    void* ct_h[2];
     float* nz_f32;                      // [Cout][Cout]
-    __nv_bfloat16* nz_bf16;
+    void* nz_h[2];
     ResW res[3];
 };
 struct Tap {
@@ -47,9 +48,9 @@ struct Tap {
     float* dev;
 };
 struct TmapKey {
-    const void* p; int c, t, s, tb, wb;
+    const void* p; int c, t, s, tb, wb, dt;
     bool operator<(const TmapKey& o) const {
-        return std::tie(p, c, t, s, tb, wb) < std::tie(o.p, o.c, o.t, o.s, o.tb, o.wb);
+        return std::tie(p, c, t, s, tb, wb, dt) < std::tie(o.p, o.c, o.t, o.s, o.tb, o.wb, o.dt);
     }
 };
 
@@ -65,7 +66,7 @@ struct snacb_handle_s {
     std::vector<void*> allocs;          // weight allocations
     VqStemWeights vq{};
     float *stem_pw_f32 = nullptr, *stem_pw_b = nullptr;
-    __nv_bfloat16* stem_pw_bf16 = nullptr;
+    void* stem_pw_h[2] = {nullptr, nullptr};
     BlockW blk[4]{};
     float *tail_alpha = nullptr, *tail_inv = nullptr, *tail_w = nullptr;
     float tail_b = 0.f;
@@ -83,6 +84,12 @@ struct snacb_handle_s {
 
     std::vector<Tap> taps;
     uint64_t launches = 0, streams = 0;
+
+    // optional per-launch CUDA-event timing (snacb_profile / snacb_profile_report)
+    struct ProfRec { int name_id; cudaEvent_t a, b; };
+    bool prof_on = false;
+    std::vector<std::string> prof_names;
+    std::vector<ProfRec> prof_recs;
 };
 
 namespace {
@@ -104,6 +111,22 @@ int fail(snacb_handle h, int code, const char* fmt, ...) {
             return fail(h, SNACB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
+void prof_begin(snacb_handle h, const char* name, cudaStream_t st) {
+    if (!h->prof_on) return;
+    int id = -1;
+    for (size_t i = 0; i < h->prof_names.size(); ++i) if (h->prof_names[i] == name) { id = static_cast<int>(i); break; }
+    if (id < 0) { id = static_cast<int>(h->prof_names.size()); h->prof_names.push_back(name); }
+    snacb_handle_s::ProfRec r{id, nullptr, nullptr};
+    cudaEventCreate(&r.a);
+    cudaEventCreate(&r.b);
+    cudaEventRecord(r.a, st);
+    h->prof_recs.push_back(r);
+}
+void prof_end(snacb_handle h, cudaStream_t st) {
+    if (!h->prof_on || h->prof_recs.empty()) return;
+    cudaEventRecord(h->prof_recs.back().b, st);
+}
+
 template <typename T>
 int dev_alloc(snacb_handle h, T** out, size_t n) {
     void* p = nullptr;
@@ -118,12 +141,19 @@ int upload_f32(snacb_handle h, float** out, const std::vector<float>& v) {
     CK(h, cudaMemcpy(*out, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice));
     return 0;
 }
-int upload_bf16(snacb_handle h, __nv_bfloat16** out, const std::vector<float>& v) {
+// both 16-bit copies of a weight matrix: out[0] bf16, out[1] fp16 (round to nearest even)
+int upload_h16(snacb_handle h, void** out, const std::vector<float>& v) {
     std::vector<__nv_bfloat16> b(v.size());
-    for (size_t i = 0; i < v.size(); ++i) b[i] = __float2bfloat16_rn(v[i]);
-    int rc = dev_alloc(h, out, v.size());
+    std::vector<__half> f(v.size());
+    for (size_t i = 0; i < v.size(); ++i) { b[i] = __float2bfloat16_rn(v[i]); f[i] = __float2half_rn(v[i]); }
+    __nv_bfloat16* db; __half* df;
+    int rc = dev_alloc(h, &db, v.size());
     if (rc) return rc;
-    CK(h, cudaMemcpy(*out, b.data(), b.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
+    rc = dev_alloc(h, &df, v.size());
+    if (rc) return rc;
+    CK(h, cudaMemcpy(db, b.data(), b.size() * 2, cudaMemcpyHostToDevice));
+    CK(h, cudaMemcpy(df, f.data(), f.size() * 2, cudaMemcpyHostToDevice));
+    out[0] = db; out[1] = df;
     return 0;
 }
 std::vector<float> vec(const float* p, size_t n) { return std::vector<float>(p, p + n); }
@@ -154,12 +184,13 @@ std::vector<float> pack_convt(const float* w, int Cin, int Cout, int s) {
     return r;
 }
 
-int make_tmap_2d(snacb_handle h, CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, uint32_t box_rows) {
+int make_tmap_2d(snacb_handle h, CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, uint32_t box_rows,
+                 int fp16) {
     cuuint64_t gdim[2] = {cols, rows};
     cuuint64_t gstr[1] = {cols * 2};
     cuuint32_t box[2] = {64, box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = h->encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+    CUresult r = h->encode(m, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(h, SNACB_ERR_CUDA, "cuTensorMapEncodeTiled(2d %llu x %llu) failed: %d",
@@ -167,37 +198,38 @@ int make_tmap_2d(snacb_handle h, CUtensorMap* m, const void* base, uint64_t cols
     return 0;
 }
 int make_tmap_3d(snacb_handle h, CUtensorMap* m, const void* base, uint64_t C, uint64_t T, uint64_t S, uint32_t tbox,
-                 uint32_t wbox) {
+                 uint32_t wbox, int fp16) {
     cuuint64_t gdim[3] = {C, T, S};
     cuuint64_t gstr[2] = {C * 2, T * C * 2};
     cuuint32_t box[3] = {64, tbox, wbox};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = h->encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstr, box, estr,
+    CUresult r = h->encode(m, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstr, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(h, SNACB_ERR_CUDA, "cuTensorMapEncodeTiled(3d C=%llu T=%llu S=%llu) failed: %d",
                                        (unsigned long long)C, (unsigned long long)T, (unsigned long long)S, (int)r);
     return 0;
 }
-int weight_map(snacb_handle h, const CUtensorMap** out, const __nv_bfloat16* w, int rows, int cols, int box_rows) {
-    auto key = std::make_pair(static_cast<const void*>(w), box_rows);
+int weight_map(snacb_handle h, const CUtensorMap** out, const void* w, int rows, int cols, int box_rows, int fp16) {
+    auto key = std::make_pair(w, box_rows);
     auto it = h->wmaps.find(key);
     if (it == h->wmaps.end()) {
         CUtensorMap m;
-        int rc = make_tmap_2d(h, &m, w, cols, rows, box_rows);
+        int rc = make_tmap_2d(h, &m, w, cols, rows, box_rows, fp16);
         if (rc) return rc;
         it = h->wmaps.emplace(key, m).first;
     }
     *out = &it->second;
     return 0;
 }
-int act_map(snacb_handle h, const CUtensorMap** out, const void* base, int C, int T, int S, int tbox, int wbox) {
-    TmapKey key{base, C, T, S, tbox, wbox};
+int act_map(snacb_handle h, const CUtensorMap** out, const void* base, int C, int T, int S, int tbox, int wbox,
+            int fp16) {
+    TmapKey key{base, C, T, S, tbox, wbox, fp16};
     auto it = h->amaps.find(key);
     if (it == h->amaps.end()) {
         if (h->amaps.size() > 4096) h->amaps.clear();
         CUtensorMap m;
-        int rc = make_tmap_3d(h, &m, base, C, T, S, tbox, wbox);
+        int rc = make_tmap_3d(h, &m, base, C, T, S, tbox, wbox, fp16);
         if (rc) return rc;
         it = h->amaps.emplace(key, m).first;
     }
@@ -239,22 +271,36 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
               uint64_t seed, int stream_offset, int16_t* pcm, float* wave, cudaStream_t st) {
     const bool f32 = (flags & SNACB_FP32) != 0;
     const bool xf32 = f32 || (flags & SNACB_STREAM_FP32);      // residual stream dtype
+    const int hk = (flags & SNACB_BF16) ? 0 : 1;               // 16-bit operand type: 0 bf16, 1 fp16
     const bool taps = (flags & SNACB_KEEP_TAPS) != 0;
     const int T0 = 4 * F;
     if (taps) clear_taps(h);
+    enum { DT_F32 = 0, DT_BF16 = 1, DT_F16 = 2 };
+    const int dt_h = f32 ? DT_F32 : (hk ? DT_F16 : DT_BF16);   // dtype of operand tensors
+    const int dt_x = xf32 ? DT_F32 : dt_h;                     // dtype of the residual stream
+    auto tap_any = [&](const char* name, const void* p, int dt, int64_t rows, int64_t cols) -> int {
+        if (!taps) return 0;
+        if (dt == DT_F32) return add_tap(h, name, static_cast<const float*>(p), rows, cols, st);
+        if (dt == DT_BF16) return add_tap(h, name, static_cast<const __nv_bfloat16*>(p), rows, cols, st);
+        return add_tap(h, name, static_cast<const __half*>(p), rows, cols, st);
+    };
 
     int32_t* c0 = h->ws_codes;
     int32_t* c1 = c0 + static_cast<size_t>(S) * F;
     int32_t* c2 = c1 + static_cast<size_t>(S) * 2 * F;
+    prof_begin(h, "unpack", st);
     launch_unpack(tok, S, tok_stride, F, (flags & SNACB_RAW_IDS) ? 1 : 0, c0, c1, c2, st);
+    prof_end(h, st);
     h->launches++;
+    prof_begin(h, "vq_stem", st);
     if (f32) launch_vq_stem<float>(c0, c1, c2, S, F, h->vq, static_cast<float*>(h->ws_a0), st);
+    else if (hk) launch_vq_stem<__half>(c0, c1, c2, S, F, h->vq, static_cast<__half*>(h->ws_a0), st);
     else launch_vq_stem<__nv_bfloat16>(c0, c1, c2, S, F, h->vq, static_cast<__nv_bfloat16*>(h->ws_a0), st);
+    prof_end(h, st);
     h->launches++;
     CK(h, cudaGetLastError());
-    if (taps) {
-        int rc = f32 ? add_tap(h, "stem_dw", static_cast<float*>(h->ws_a0), (int64_t)S * T0, kLatent, st)
-                     : add_tap(h, "stem_dw", static_cast<__nv_bfloat16*>(h->ws_a0), (int64_t)S * T0, kLatent, st);
+    {
+        int rc = tap_any("stem_dw", h->ws_a0, dt_h, (int64_t)S * T0, kLatent);
         if (rc) return rc;
     }
 
@@ -262,29 +308,29 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
     void* oth = h->ws_buf[1];
     float* P = static_cast<float*>(h->ws_buf[2]);
 
-    auto gemm = [&](int epi, bool out_f32, GemmArgs& a, const void* A, const float* Wf, const __nv_bfloat16* Wb,
-                    int Wrows, int Wcols) -> int {
+    auto gemm = [&](const char* pname, int epi, bool out_f32, GemmArgs& a, const void* A, const float* Wf,
+                    void* const* Wh, int Wrows, int Wcols) -> int {
         tile_boxes(a.Tin, &a.Tbox, &a.Wbox);
         a.seed = seed;
         a.stream_offset = stream_offset;
         h->launches++;
         if (f32) {
+            prof_begin(h, pname, st);
             launch_gemm_f32(epi, a, static_cast<const float*>(A), Wf, st);
+            prof_end(h, st);
             CK(h, cudaGetLastError());
             return 0;
         }
         const CUtensorMap *ma, *mw;
-        int rc = act_map(h, &ma, A, a.K, a.Tin, a.S, a.Tbox, a.Wbox);
+        int rc = act_map(h, &ma, A, a.K, a.Tin, a.S, a.Tbox, a.Wbox, hk);
         if (rc) return rc;
-        rc = weight_map(h, &mw, Wb, Wrows, Wcols, gemm_tc_block_n(a));
+        rc = weight_map(h, &mw, Wh[hk], Wrows, Wcols, gemm_tc_block_n(a), hk);
         if (rc) return rc;
-        CK(h, launch_gemm_tc(epi, out_f32 ? 1 : 0, a, *ma, *mw, h->sm_count, st));
+        prof_begin(h, pname, st);
+        cudaError_t le = launch_gemm_tc(epi, hk, out_f32 ? 1 : 0, a, *ma, *mw, h->sm_count, st);
+        prof_end(h, st);
+        CK(h, le);
         return 0;
-    };
-    auto tap_any = [&](const char* name, const void* p, bool is_f32, int64_t rows, int64_t cols) -> int {
-        if (!taps) return 0;
-        return is_f32 ? add_tap(h, name, static_cast<const float*>(p), rows, cols, st)
-                      : add_tap(h, name, static_cast<const __nv_bfloat16*>(p), rows, cols, st);
     };
 
     // ---- stem 1x1 768 -> 1024, Snake of block 0 applied in the epilogue
@@ -293,9 +339,9 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
         a.S = S; a.Tin = T0; a.K = kLatent; a.N = kDecDim; a.Cout = kDecDim; a.ntaps = 1; a.up = 1;
         a.bias = h->stem_pw_b; a.alpha = h->blk[0].alpha; a.inv_alpha = h->blk[0].inv_alpha;
         a.out = cur;
-        int rc = gemm(EPI_BIAS_SNAKE, false, a, h->ws_a0, h->stem_pw_f32, h->stem_pw_bf16, kDecDim, kLatent);
+        int rc = gemm("stem_pw", EPI_BIAS_SNAKE, false, a, h->ws_a0, h->stem_pw_f32, h->stem_pw_h, kDecDim, kLatent);
         if (rc) return rc;
-        rc = tap_any("stem", cur, f32, (int64_t)S * T0, kDecDim);
+        rc = tap_any("stem", cur, dt_h, (int64_t)S * T0, kDecDim);
         if (rc) return rc;
     }
 
@@ -309,10 +355,10 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
             GemmArgs a{};
             a.S = S; a.Tin = Tin; a.K = b.Cin; a.N = b.s * b.Cout; a.Cout = b.Cout; a.ntaps = 2; a.up = b.s;
             a.bias = b.ct_b; a.out = oth;
-            int rc = gemm(EPI_BIAS, false, a, cur, b.ct_f32, b.ct_bf16, b.s * b.Cout, 2 * b.Cin);
-            if (rc) return rc;
             snprintf(nm, sizeof nm, "b%d.convt", bi);
-            rc = tap_any(nm, oth, f32, (int64_t)S * T, b.Cout);
+            int rc = gemm(nm, EPI_BIAS, false, a, cur, b.ct_f32, b.ct_h, b.s * b.Cout, 2 * b.Cin);
+            if (rc) return rc;
+            rc = tap_any(nm, oth, dt_h, (int64_t)S * T, b.Cout);
             if (rc) return rc;
         }
         // ---- NoiseBlock: oth -> cur   x = y + n * (Wn y)
@@ -321,10 +367,10 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
             a.S = S; a.Tin = T; a.K = b.Cout; a.N = b.Cout; a.Cout = b.Cout; a.ntaps = 1; a.up = 1;
             a.noise = noise ? noise[bi] : nullptr; a.noise_stage = bi;
             a.resid = oth; a.out = cur;
-            int rc = gemm(EPI_NOISE, xf32, a, oth, b.nz_f32, b.nz_bf16, b.Cout, b.Cout);
-            if (rc) return rc;
             snprintf(nm, sizeof nm, "b%d.noise", bi);
-            rc = tap_any(nm, cur, xf32, (int64_t)S * T, b.Cout);
+            int rc = gemm(nm, EPI_NOISE, xf32, a, oth, b.nz_f32, b.nz_h, b.Cout, b.Cout);
+            if (rc) return rc;
+            rc = tap_any(nm, cur, dt_x, (int64_t)S * T, b.Cout);
             if (rc) return rc;
         }
         // ---- three ResidualUnits, dilations 1, 3, 9: cur -> oth -> cur -> oth
@@ -340,6 +386,8 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
             ra.alpha1 = r.alpha1; ra.inv_alpha1 = r.inv1; ra.dw_w = r.dw_w; ra.dw_b = r.dw_b;
             ra.alpha2 = r.alpha2; ra.inv_alpha2 = r.inv2; ra.pw_b = r.pw_b;
             ra.alpha_next = an; ra.inv_alpha_next = ian;
+            snprintf(nm, sizeof nm, "b%d.res%d", bi, ri);
+            prof_begin(h, nm, st);
             if (f32) {
                 launch_respre_f32(ra, P, st);
                 GemmArgs a{};
@@ -347,14 +395,16 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
                 a.bias = r.pw_b; a.alpha = an; a.inv_alpha = ian; a.resid = cur; a.out = oth;
                 tile_boxes(a.Tin, &a.Tbox, &a.Wbox);
                 launch_gemm_f32(last ? EPI_RES_SNAKE : EPI_RES, a, P, r.pw_f32, st);
+                prof_end(h, st);
                 h->launches += 2;
                 CK(h, cudaGetLastError());
             } else {
-                CK(h, launch_resunit_tc(last ? EPI_RES_SNAKE : EPI_RES, xf32 ? 1 : 0, ra, r.tm_pw, st));
+                cudaError_t le = launch_resunit_tc(last ? EPI_RES_SNAKE : EPI_RES, hk, xf32 ? 1 : 0, ra, r.tm_pw[hk], st);
+                prof_end(h, st);
+                CK(h, le);
                 h->launches++;
             }
-            snprintf(nm, sizeof nm, "b%d.res%d", bi, ri);
-            int rc = tap_any(nm, oth, last ? f32 : xf32, (int64_t)S * T, b.Cout);
+            int rc = tap_any(nm, oth, last ? dt_h : dt_x, (int64_t)S * T, b.Cout);
             if (rc) return rc;
             void* t = cur; cur = oth; oth = t;
         }
@@ -365,8 +415,11 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
     const int T = Tin;                                   // 2048 * F samples
     const bool slice = (flags & SNACB_EXTRACT_SLICE) && T > 4096;
     const int t_begin = slice ? 2048 : 0, n_out = slice ? 2048 : T;
+    prof_begin(h, "tail", st);
     if (f32) launch_tail<float>(static_cast<const float*>(cur), S, T, t_begin, n_out, h->tail_w, h->tail_b, pcm, wave, st);
+    else if (hk) launch_tail<__half>(static_cast<const __half*>(cur), S, T, t_begin, n_out, h->tail_w, h->tail_b, pcm, wave, st);
     else launch_tail<__nv_bfloat16>(static_cast<const __nv_bfloat16*>(cur), S, T, t_begin, n_out, h->tail_w, h->tail_b, pcm, wave, st);
+    prof_end(h, st);
     h->launches++;
     CK(h, cudaGetLastError());
     h->streams += S;
@@ -433,7 +486,7 @@ int snacb_create(snacb_handle* out, const snacb_weights* w, int device) {
         RC(upload_f32(h, &p, vec(w->stem_dw_b, kLatent))); h->vq.dw_b = p;
         auto pw = vec(w->stem_pw_w, (size_t)kDecDim * kLatent);
         RC(upload_f32(h, &h->stem_pw_f32, pw));
-        RC(upload_bf16(h, &h->stem_pw_bf16, pw));
+        RC(upload_h16(h, h->stem_pw_h, pw));
         RC(upload_f32(h, &h->stem_pw_b, vec(w->stem_pw_b, kDecDim)));
     }
     // ---- decoder blocks
@@ -447,11 +500,11 @@ int snacb_create(snacb_handle* out, const snacb_weights* w, int device) {
         RC(upload_f32(h, &b.inv_alpha, inv_alpha(s.alpha, cin)));
         auto ct = pack_convt(s.convt_w, b.Cin, b.Cout, b.s);
         RC(upload_f32(h, &b.ct_f32, ct));
-        RC(upload_bf16(h, &b.ct_bf16, ct));
+        RC(upload_h16(h, b.ct_h, ct));
         RC(upload_f32(h, &b.ct_b, vec(s.convt_b, b.Cout)));
         auto nz = vec(s.noise_w, (size_t)b.Cout * b.Cout);
         RC(upload_f32(h, &b.nz_f32, nz));
-        RC(upload_bf16(h, &b.nz_bf16, nz));
+        RC(upload_h16(h, b.nz_h, nz));
         for (int ri = 0; ri < 3; ++ri) {
             const snacb_resunit_weights& rs = s.res[ri];
             ResW& r = b.res[ri];
@@ -464,9 +517,9 @@ int snacb_create(snacb_handle* out, const snacb_weights* w, int device) {
             RC(upload_f32(h, &r.inv2, inv_alpha(rs.alpha2, C)));
             auto pw = vec(rs.pw_w, (size_t)C * C);
             RC(upload_f32(h, &r.pw_f32, pw));
-            RC(upload_bf16(h, &r.pw_bf16, pw));
+            RC(upload_h16(h, r.pw_h, pw));
             RC(upload_f32(h, &r.pw_b, vec(rs.pw_b, C)));
-            RC(make_tmap_2d(h, &r.tm_pw, r.pw_bf16, C, C, C > 256 ? 256 : C));
+            for (int k = 0; k < 2; ++k) RC(make_tmap_2d(h, &r.tm_pw[k], r.pw_h[k], C, C, C > 256 ? 256 : C, k));
         }
         cin = b.Cout;
     }
@@ -494,6 +547,7 @@ void snacb_destroy(snacb_handle h) {
     if (!h) return;
     cudaSetDevice(h->device);
     clear_taps(h);
+    for (auto& r : h->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (void* p : h->allocs) cudaFree(p);
     for (int i = 0; i < 3; ++i) if (h->ws_buf[i]) cudaFree(h->ws_buf[i]);
     if (h->ws_a0) cudaFree(h->ws_a0);
@@ -603,6 +657,36 @@ int snacb_decode_host(snacb_handle h, const int32_t* tok_host, int B, int tok_st
     if (rc) return rc;
     CK(h, cudaMemcpyAsync(pcm_host, h->st_pcm, npcm * sizeof(int16_t), cudaMemcpyDeviceToHost, st));
     CK(h, cudaStreamSynchronize(st));
+    return SNACB_OK;
+}
+
+int snacb_profile(snacb_handle h, int enable) {
+    if (!h) return SNACB_ERR_ARG;
+    for (auto& r : h->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    h->prof_recs.clear();
+    h->prof_names.clear();
+    h->prof_on = enable != 0;
+    return SNACB_OK;
+}
+
+int snacb_profile_report(snacb_handle h, char* buf, size_t cap) {
+    if (!h || !buf || cap == 0) return SNACB_ERR_ARG;
+    CK(h, cudaSetDevice(h->device));
+    CK(h, cudaDeviceSynchronize());
+    std::vector<double> tot(h->prof_names.size(), 0.0);
+    std::vector<long> cnt(h->prof_names.size(), 0);
+    for (auto& r : h->prof_recs) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) { tot[r.name_id] += ms; cnt[r.name_id]++; }
+    }
+    std::string out;
+    char line[128];
+    for (size_t i = 0; i < h->prof_names.size(); ++i) {
+        snprintf(line, sizeof line, "%s %ld %.6f\n", h->prof_names[i].c_str(), cnt[i], tot[i]);
+        out += line;
+    }
+    if (out.size() + 1 > cap) return fail(h, SNACB_ERR_ARG, "snacb_profile_report: buffer too small");
+    memcpy(buf, out.c_str(), out.size() + 1);
     return SNACB_OK;
 }
 
