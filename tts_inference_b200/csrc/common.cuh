@@ -141,4 +141,25 @@ __device__ __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162flo
 __device__ __forceinline__ void from_f32(float& d, float v) { d = v; }
 __device__ __forceinline__ void from_f32(__nv_bfloat16& d, float v) { d = __float2bfloat16_rn(v); }
 
+template <typename T>
+__device__ __forceinline__ void load32(const T* p, float (&v)[32]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float t[8];
+        load8(p + 8 * i, t);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[8 * i + j] = t[j];
+    }
+}
+template <typename T>
+__device__ __forceinline__ void store32(T* p, const float (&v)[32]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float t[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t[j] = v[8 * i + j];
+        store8(p + 8 * i, t);
+    }
+}
+
 }  // namespace snacb

@@ -43,4 +43,9 @@ cudaError_t launch_resunit_tc(int epi, int half_fp16, int x_f32, const ResUnitAr
                               cudaStream_t st);
 cudaError_t init_tc_kernels();            // opt-in shared memory sizes
 
+// ---- kernels_res2.cu  (persistent pipelined ResidualUnit, 16-bit activations)
+void resunit2_geometry(int C, int dil, int* tile_m, int* box_rows);   // x tensor-map box = (64, box_rows, 1), no swizzle
+cudaError_t launch_resunit2(int half_fp16, const ResUnitArgs& a, const CUtensorMap& tmX, const CUtensorMap& tmW,
+                            int sm_count, cudaStream_t st);
+
 }  // namespace snacb

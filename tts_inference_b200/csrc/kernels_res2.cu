@@ -1,0 +1,406 @@
+// k_resunit2: persistent, software-pipelined ResidualUnit kernel for sm_100a (16-bit activations).
+//
+//   out = x + W * snake2( dw_b + sum_j dw_w[j] * snake1(x[t + (j-3) d]) ) + b     (+ next Snake)
+//
+// One CTA per SM loops over 256-row (C<=256) or 128-row (C=512) time tiles of one stream each:
+//   * warp 16 (producer): TMA loads of the x tile + dilation halo, one 64-channel chunk per stage
+//     (stream edges = TMA out-of-bounds zero fill, which is exactly the conv's zero padding because
+//     snake(0) = 0), and of the 1x1 weights (resident for C<=128, streamed per chunk otherwise);
+//   * warps 0-15 (compute): lane = channel pair, each warp owns 16 (or 8) output rows taken in
+//     dilation-class order so that the 7-tap window slides in registers: Snake1 is evaluated once per
+//     input row, the depthwise conv and Snake2 run in fp32, the result is packed to the 16-bit operand
+//     type straight into the 128B-swizzled K-major A tile;
+//   * warp 17 (MMA): tcgen05.mma per chunk into TMEM accumulators (two stages when they fit), so the
+//     tensor work of tile i overlaps the CUDA-core prologue of tile i+1;
+//   * the compute warps then drain TMEM (tcgen05.ld), add bias + residual (+ the next layer's Snake)
+//     and store the 16-bit result.
+#include "common.cuh"
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace snacb {
+using namespace ptx;
+
+namespace {
+
+template <typename HT> struct HalfFmt2;
+template <> struct HalfFmt2<__half> { static constexpr uint32_t kFmt = 0; };
+template <> struct HalfFmt2<__nv_bfloat16> { static constexpr uint32_t kFmt = 1; };
+
+__device__ __forceinline__ float2 unpack2(uint32_t v, const __half*) {
+    return __half22float2(*reinterpret_cast<const __half2*>(&v));
+}
+__device__ __forceinline__ float2 unpack2(uint32_t v, const __nv_bfloat16*) {
+    return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v));
+}
+
+constexpr int kComputeWarps = 16;
+constexpr int kThreads = (kComputeWarps + 2) * 32;
+
+template <int C, int DIL>
+struct Res2Cfg {
+    static constexpr int kTileM = (C == 512) ? 128 : 256;
+    static constexpr int kAccs = kTileM / 128;                       // 128-row accumulators per tile
+    static constexpr int kChunks = C / 64;
+    static constexpr bool kWRes = (C <= 128);                        // 1x1 weights resident in smem
+    static constexpr int kRows = kTileM + 6 * DIL;                   // x rows per tile incl. halo (even)
+    static constexpr int kHalfRows = kRows / 2;                      // TMA box rows (<= 256)
+    static constexpr int kXsBytes = ((kRows * 128 + 1023) / 1024) * 1024;
+    static constexpr int kNXS = (C <= 128) ? 3 : 2;                  // x chunk stages
+    static constexpr int kABytes = kTileM * 128;                     // A operand stage (one 64-ch chunk)
+    static constexpr int kNSA = 2;
+    static constexpr int kWChunkBytes = C * 128;                     // [C (n)][64 (k)] 16-bit
+    static constexpr int kNSW = kWRes ? kChunks : 2;
+    static constexpr int kAccCols = kAccs * C;                       // TMEM columns of one accumulator stage
+    static constexpr int kAccStages = (2 * kAccCols <= 512) ? 2 : 1;
+    static constexpr int kTmemCols = kAccStages * kAccCols;          // 128 / 256 / 512 (power of two)
+    static constexpr int kNHalf = C > 256 ? 2 : 1;
+    static constexpr int kMmaN = C > 256 ? 256 : C;
+    static constexpr int kRowsPerWarp = kTileM / kComputeWarps;      // 16 or 8
+    static constexpr bool kParamsSmem = (C <= 256);
+    static constexpr int kPrmBytes = kParamsSmem ? (C / 2) * 96 : 0; // 24 floats per channel pair
+    static constexpr int kEpiBytes = 3 * C * 4;                      // bias, alpha_next, inv_alpha_next
+    static constexpr int kMapBytes = kTileM * 2;                     // class-order row map (uint16)
+    static constexpr int kBarBytes = 256;
+    static constexpr int kOffA = 0;
+    static constexpr int kOffW = kOffA + kNSA * kABytes;
+    static constexpr int kOffXs = kOffW + kNSW * kWChunkBytes;
+    static constexpr int kOffPrm = kOffXs + kNXS * kXsBytes;
+    static constexpr int kOffEpi = kOffPrm + kPrmBytes;
+    static constexpr int kOffMap = kOffEpi + kEpiBytes;
+    static constexpr int kOffBar = ((kOffMap + kMapBytes + 15) / 16) * 16;
+    static constexpr int kSmem = kOffBar + kBarBytes + 1024;
+    static_assert(kRows % 2 == 0 && kHalfRows <= 256, "TMA box");
+    static_assert(kSmem <= 232448, "shared memory budget");
+};
+
+// One Snake'd input row (2 channels) from the x stage.
+template <typename HT>
+__device__ __forceinline__ float2 snake_row(const uint8_t* xs, int xrow, int lane, float2 al, float2 ia) {
+    const uint32_t raw = *reinterpret_cast<const uint32_t*>(xs + xrow * 128 + lane * 4);
+    float2 v = unpack2(raw, static_cast<const HT*>(nullptr));
+    v.x = snake_f<true>(v.x, al.x, ia.x);
+    v.y = snake_f<true>(v.y, al.y, ia.y);
+    return v;
+}
+
+template <int C, int DIL, int EPI, typename HT>
+__global__ void __launch_bounds__(kThreads, 1)
+k_resunit2(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const ResUnitArgs a,
+           const int num_tiles) {
+    using Cfg = Res2Cfg<C, DIL>;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // keep pointer provenance (no integer round trip) so that the compiler emits LDS/STS
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* sA = smem + Cfg::kOffA;
+    uint8_t* sW = smem + Cfg::kOffW;
+    uint8_t* sX = smem + Cfg::kOffXs;
+    float* sPrm = reinterpret_cast<float*>(smem + Cfg::kOffPrm);
+    float* sEpi = reinterpret_cast<float*>(smem + Cfg::kOffEpi);
+    uint16_t* sMap = reinterpret_cast<uint16_t*>(smem + Cfg::kOffMap);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kOffBar);
+    uint64_t* x_full = bars;              // [3]
+    uint64_t* x_empty = bars + 3;         // [3]
+    uint64_t* a_full = bars + 6;          // [2]
+    uint64_t* a_empty = bars + 8;         // [2]
+    uint64_t* w_full = bars + 10;         // [2]
+    uint64_t* w_empty = bars + 12;        // [2]
+    uint64_t* acc_full = bars + 14;       // [2]
+    uint64_t* acc_empty = bars + 16;      // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int tiles_t = (a.T + Cfg::kTileM - 1) / Cfg::kTileM;
+
+    if (tid == 0) {
+        prefetch_tmap(&tmX);
+        prefetch_tmap(&tmW);
+        for (int i = 0; i < 3; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1);
+            mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1);
+            mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kComputeWarps);
+        }
+        fence_barrier_init();
+    }
+    if (warp == kComputeWarps + 1) { tmem_alloc(tmem_slot, Cfg::kTmemCols); tmem_relinquish(); }
+    // parameters -> shared memory (compute threads)
+    if (tid < kComputeWarps * 32) {
+        if (Cfg::kParamsSmem) {
+            for (int p = tid; p < C / 2; p += kComputeWarps * 32) {
+                float* d = sPrm + p * 24;
+                const int ch = 2 * p;
+                d[0] = a.alpha1[ch]; d[1] = a.alpha1[ch + 1];
+                d[2] = a.inv_alpha1[ch]; d[3] = a.inv_alpha1[ch + 1];
+#pragma unroll
+                for (int j = 0; j < 7; ++j) { d[4 + 2 * j] = a.dw_w[j * C + ch]; d[5 + 2 * j] = a.dw_w[j * C + ch + 1]; }
+                d[18] = a.dw_b[ch]; d[19] = a.dw_b[ch + 1];
+                d[20] = a.alpha2[ch]; d[21] = a.alpha2[ch + 1];
+                d[22] = a.inv_alpha2[ch]; d[23] = a.inv_alpha2[ch + 1];
+            }
+        }
+        for (int c = tid; c < C; c += kComputeWarps * 32) {
+            sEpi[c] = a.pw_b[c];
+            sEpi[C + c] = (EPI == EPI_RES_SNAKE) ? a.alpha_next[c] : 0.f;
+            sEpi[2 * C + c] = (EPI == EPI_RES_SNAKE) ? a.inv_alpha_next[c] : 0.f;
+        }
+        // rows of the tile in dilation-class order: class c = rows c, c+DIL, c+2 DIL, ...
+        for (int q = tid; q < Cfg::kTileM; q += kComputeWarps * 32) {
+            int rem = q, row = 0;
+            for (int c = 0; c < DIL; ++c) {
+                const int n = (Cfg::kTileM - c + DIL - 1) / DIL;
+                if (rem < n) { row = c + rem * DIL; break; }
+                rem -= n;
+            }
+            sMap[q] = static_cast<uint16_t>(row);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int my_tiles = (num_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+
+    if (warp == kComputeWarps) {
+        // ============================================================ producer (TMA)
+        if (lane == 0) {
+            if (Cfg::kWRes) {
+                mbar_expect_tx(&w_full[0], Cfg::kChunks * Cfg::kWChunkBytes);
+                for (int kc = 0; kc < Cfg::kChunks; ++kc)
+                    tma_load_2d(sW + kc * Cfg::kWChunkBytes, &tmW, kc * 64, 0, &w_full[0]);
+            }
+            int g = 0;
+            for (int n = 0; n < my_tiles; ++n) {
+                const int tile = blockIdx.x + n * gridDim.x;
+                const int s = tile / tiles_t, t0 = (tile % tiles_t) * Cfg::kTileM;
+                for (int kc = 0; kc < Cfg::kChunks; ++kc, ++g) {
+                    if (!Cfg::kWRes) {
+                        const int sw = g % 2;
+                        if (g >= 2) mbar_wait(&w_empty[sw], ((g / 2) - 1) & 1);
+                        mbar_expect_tx(&w_full[sw], Cfg::kWChunkBytes);
+#pragma unroll
+                        for (int nh = 0; nh < Cfg::kNHalf; ++nh)
+                            tma_load_2d(sW + sw * Cfg::kWChunkBytes + nh * (256 * 128), &tmW, kc * 64, nh * 256, &w_full[sw]);
+                    }
+                    const int sx = g % Cfg::kNXS;
+                    if (g >= Cfg::kNXS) mbar_wait(&x_empty[sx], ((g / Cfg::kNXS) - 1) & 1);
+                    mbar_expect_tx(&x_full[sx], Cfg::kRows * 128);
+                    uint8_t* dst = sX + sx * Cfg::kXsBytes;
+                    tma_load_3d(dst, &tmX, kc * 64, t0 - 3 * DIL, s, &x_full[sx]);
+                    tma_load_3d(dst + Cfg::kHalfRows * 128, &tmX, kc * 64, t0 - 3 * DIL + Cfg::kHalfRows, s, &x_full[sx]);
+                }
+            }
+        }
+    } else if (warp == kComputeWarps + 1) {
+        // ============================================================ MMA issuer
+        constexpr uint32_t idesc = umma_idesc_f16(128, Cfg::kMmaN, HalfFmt2<HT>::kFmt);
+        if (Cfg::kWRes) { mbar_wait(&w_full[0], 0); }
+        int g = 0;
+        for (int n = 0; n < my_tiles; ++n) {
+            const int as = n % Cfg::kAccStages;
+            mbar_wait(&acc_empty[as], ((n / Cfg::kAccStages) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t d_base = tmem_base + as * Cfg::kAccCols;
+            for (int kc = 0; kc < Cfg::kChunks; ++kc, ++g) {
+                const int sa = g % 2;
+                if (!Cfg::kWRes) mbar_wait(&w_full[g % 2], (g / 2) & 1);
+                mbar_wait(&a_full[sa], (g / 2) & 1);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t a_addr = smem_u32(sA + sa * Cfg::kABytes);
+                    const uint32_t w_addr = smem_u32(sW + (Cfg::kWRes ? kc : (g % 2)) * Cfg::kWChunkBytes);
+#pragma unroll
+                    for (int ac = 0; ac < Cfg::kAccs; ++ac) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+#pragma unroll
+                            for (int nh = 0; nh < Cfg::kNHalf; ++nh)
+                                mma_f16_ss(d_base + ac * C + nh * 256, umma_desc_sw128(a_addr + ac * 16384 + k * 32),
+                                           umma_desc_sw128(w_addr + nh * (256 * 128) + k * 32), idesc,
+                                           (kc > 0 || k > 0) ? 1u : 0u);
+                        }
+                    }
+                    mma_commit(&a_empty[sa]);
+                    if (!Cfg::kWRes) mma_commit(&w_empty[g % 2]);
+                    if (kc == Cfg::kChunks - 1) mma_commit(&acc_full[as]);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ============================================================ 16 compute warps
+        const HT* x = static_cast<const HT*>(a.x);
+        HT* out = static_cast<HT*>(a.out);
+
+        auto epilogue = [&](int n) {
+            const int tile = blockIdx.x + n * gridDim.x;
+            const int s = tile / tiles_t, t0 = (tile % tiles_t) * Cfg::kTileM;
+            const int as = n % Cfg::kAccStages;
+            const int q = warp & 3, rest = warp >> 2;
+            const int ac = (Cfg::kAccs == 2) ? (rest & 1) : 0;
+            constexpr int kColGroups = (Cfg::kAccs == 2) ? 2 : 4;
+            const int cg = (Cfg::kAccs == 2) ? (rest >> 1) : rest;
+            constexpr int kColsPerWarp = C / kColGroups;
+            const int row = ac * 128 + q * 32 + lane;
+            const int t = t0 + row;
+            const bool valid = t < a.T;
+            const size_t grow = static_cast<size_t>(s) * a.T + t;
+            mbar_wait(&acc_full[as], (n / Cfg::kAccStages) & 1);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * Cfg::kAccCols + ac * C;
+#pragma unroll 1
+            for (int cc = 0; cc < kColsPerWarp / 32; ++cc) {
+                const int col = cg * kColsPerWarp + cc * 32;
+                float xr[32];
+                if (valid) load32(x + grow * C + col, xr);
+                uint32_t raw[32];
+                tmem_ld32(taddr + col, raw);
+                tmem_ld_wait();
+                if (valid) {
+                    float v[32];
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 b = *reinterpret_cast<const float4*>(sEpi + col + j);
+                        v[j] = xr[j] + (__uint_as_float(raw[j]) + b.x);
+                        v[j + 1] = xr[j + 1] + (__uint_as_float(raw[j + 1]) + b.y);
+                        v[j + 2] = xr[j + 2] + (__uint_as_float(raw[j + 2]) + b.z);
+                        v[j + 3] = xr[j + 3] + (__uint_as_float(raw[j + 3]) + b.w);
+                    }
+                    if (EPI == EPI_RES_SNAKE) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 al = *reinterpret_cast<const float4*>(sEpi + C + col + j);
+                            const float4 ia = *reinterpret_cast<const float4*>(sEpi + 2 * C + col + j);
+                            v[j] = snake_f<true>(v[j], al.x, ia.x);
+                            v[j + 1] = snake_f<true>(v[j + 1], al.y, ia.y);
+                            v[j + 2] = snake_f<true>(v[j + 2], al.z, ia.z);
+                            v[j + 3] = snake_f<true>(v[j + 3], al.w, ia.w);
+                        }
+                    }
+                    store32(out + grow * C + col, v);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[as]);
+        };
+
+        int g = 0;
+        const int q0 = warp * Cfg::kRowsPerWarp;
+        for (int n = 0; n < my_tiles; ++n) {
+            for (int kc = 0; kc < Cfg::kChunks; ++kc, ++g) {
+                // ---- per-lane parameters of channels (kc*64 + 2*lane, +1)
+                float2 al1, ia1, w[7], bd, al2, ia2;
+                if (Cfg::kParamsSmem) {
+                    const float4* p4 = reinterpret_cast<const float4*>(sPrm + (kc * 32 + lane) * 24);
+                    const float4 p0 = p4[0], p1 = p4[1], p2 = p4[2], p3 = p4[3], p5 = p4[4], p6 = p4[5];
+                    al1 = make_float2(p0.x, p0.y); ia1 = make_float2(p0.z, p0.w);
+                    w[0] = make_float2(p1.x, p1.y); w[1] = make_float2(p1.z, p1.w);
+                    w[2] = make_float2(p2.x, p2.y); w[3] = make_float2(p2.z, p2.w);
+                    w[4] = make_float2(p3.x, p3.y); w[5] = make_float2(p3.z, p3.w);
+                    w[6] = make_float2(p5.x, p5.y); bd = make_float2(p5.z, p5.w);
+                    al2 = make_float2(p6.x, p6.y); ia2 = make_float2(p6.z, p6.w);
+                } else {
+                    const int ch = kc * 64 + 2 * lane;
+                    al1 = *reinterpret_cast<const float2*>(a.alpha1 + ch);
+                    ia1 = *reinterpret_cast<const float2*>(a.inv_alpha1 + ch);
+#pragma unroll
+                    for (int j = 0; j < 7; ++j) w[j] = *reinterpret_cast<const float2*>(a.dw_w + j * C + ch);
+                    bd = *reinterpret_cast<const float2*>(a.dw_b + ch);
+                    al2 = *reinterpret_cast<const float2*>(a.alpha2 + ch);
+                    ia2 = *reinterpret_cast<const float2*>(a.inv_alpha2 + ch);
+                }
+                const int sx = g % Cfg::kNXS, sa = g % 2;
+                mbar_wait(&x_full[sx], (g / Cfg::kNXS) & 1);
+                if (g >= 2) mbar_wait(&a_empty[sa], ((g / 2) - 1) & 1);
+                const uint8_t* xs = sX + sx * Cfg::kXsBytes;
+                uint8_t* dstA = sA + sa * Cfg::kABytes;
+
+                // ---- sliding 7-tap window over this warp's rows (dilation-class order)
+                float2 win[7];
+                int prev = -1000;
+#pragma unroll
+                for (int i = 0; i < Cfg::kRowsPerWarp; ++i) {
+                    const int r = sMap[q0 + i];
+                    if (r != prev + DIL) {                      // (re)start: rows r-3d .. r+2d  (x stage row = r + j d)
+#pragma unroll
+                        for (int j = 0; j < 6; ++j) win[j + 1] = snake_row<HT>(xs, r + j * DIL, lane, al1, ia1);
+                    }
+                    prev = r;
+#pragma unroll
+                    for (int j = 0; j < 6; ++j) win[j] = win[j + 1];
+                    win[6] = snake_row<HT>(xs, r + 6 * DIL, lane, al1, ia1);
+                    float ax = bd.x, ay = bd.y;
+#pragma unroll
+                    for (int j = 0; j < 7; ++j) { ax = fmaf(w[j].x, win[j].x, ax); ay = fmaf(w[j].y, win[j].y, ay); }
+                    ax = snake_f<true>(ax, al2.x, ia2.x);
+                    ay = snake_f<true>(ay, al2.y, ia2.y);
+                    *reinterpret_cast<uint32_t*>(dstA + (r >> 7) * 16384 + sw128_offset(r & 127, 2 * lane)) =
+                        pack2(ax, ay, static_cast<const HT*>(nullptr));
+                }
+                fence_proxy_async_smem();
+                asm volatile("bar.sync 1, %0;" ::"n"(kComputeWarps * 32) : "memory");
+                if (tid == 0) { mbar_arrive(&a_full[sa]); mbar_arrive(&x_empty[sx]); }
+            }
+            if (Cfg::kAccStages == 1) epilogue(n);
+            else if (n > 0) epilogue(n - 1);
+        }
+        if (Cfg::kAccStages == 2 && my_tiles > 0) epilogue(my_tiles - 1);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kComputeWarps + 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
+template <int C, int DIL, int EPI, typename HT>
+cudaError_t launch_t(const ResUnitArgs& a, const CUtensorMap& tmX, const CUtensorMap& tmW, int sm_count, cudaStream_t st) {
+    using Cfg = Res2Cfg<C, DIL>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(k_resunit2<C, DIL, EPI, HT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    const int tiles = a.S * ((a.T + Cfg::kTileM - 1) / Cfg::kTileM);
+    if (tiles == 0) return cudaSuccess;
+    const int grid = tiles < sm_count ? tiles : sm_count;
+    k_resunit2<C, DIL, EPI, HT><<<grid, kThreads, Cfg::kSmem, st>>>(tmX, tmW, a, tiles);
+    return cudaGetLastError();
+}
+
+template <int C, typename HT>
+cudaError_t launch_c(const ResUnitArgs& a, const CUtensorMap& tmX, const CUtensorMap& tmW, int sm_count, cudaStream_t st) {
+    if (a.dil == 1) return launch_t<C, 1, EPI_RES, HT>(a, tmX, tmW, sm_count, st);
+    if (a.dil == 3) return launch_t<C, 3, EPI_RES, HT>(a, tmX, tmW, sm_count, st);
+    if (a.dil == 9) return launch_t<C, 9, EPI_RES_SNAKE, HT>(a, tmX, tmW, sm_count, st);
+    return cudaErrorInvalidValue;
+}
+
+template <typename HT>
+cudaError_t launch_h(const ResUnitArgs& a, const CUtensorMap& tmX, const CUtensorMap& tmW, int sm_count, cudaStream_t st) {
+    switch (a.C) {
+        case 512: return launch_c<512, HT>(a, tmX, tmW, sm_count, st);
+        case 256: return launch_c<256, HT>(a, tmX, tmW, sm_count, st);
+        case 128: return launch_c<128, HT>(a, tmX, tmW, sm_count, st);
+        case 64: return launch_c<64, HT>(a, tmX, tmW, sm_count, st);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+}  // namespace
+
+void resunit2_geometry(int C, int dil, int* tile_m, int* box_rows) {
+    const int tm = (C == 512) ? 128 : 256;
+    *tile_m = tm;
+    *box_rows = (tm + 6 * dil) / 2;
+}
+
+// dil 1 and 3 use the plain residual epilogue, dil 9 (last unit of a block) applies the next Snake.
+cudaError_t launch_resunit2(int half_fp16, const ResUnitArgs& a, const CUtensorMap& tmX, const CUtensorMap& tmW,
+                            int sm_count, cudaStream_t st) {
+    return half_fp16 ? launch_h<__half>(a, tmX, tmW, sm_count, st) : launch_h<__nv_bfloat16>(a, tmX, tmW, sm_count, st);
+}
+
+}  // namespace snacb

@@ -28,27 +28,6 @@ template <typename HT> struct HalfFmt;
 template <> struct HalfFmt<__half> { static constexpr uint32_t kFmt = 0; };
 template <> struct HalfFmt<__nv_bfloat16> { static constexpr uint32_t kFmt = 1; };
 
-template <typename T>
-__device__ __forceinline__ void load32(const T* p, float (&v)[32]) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        float t[8];
-        load8(p + 8 * i, t);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[8 * i + j] = t[j];
-    }
-}
-template <typename T>
-__device__ __forceinline__ void store32(T* p, const float (&v)[32]) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        float t[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) t[j] = v[8 * i + j];
-        store8(p + 8 * i, t);
-    }
-}
-
 // =================================================================================================
 // k_gemm_tc
 // =================================================================================================
@@ -292,7 +271,7 @@ struct ResTcCfg {
 };
 
 template <int C, int EPI, typename HT, typename XT, typename OutT>
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(320, (C <= 128) ? 2 : 1)
 k_resunit_tc(const __grid_constant__ CUtensorMap tmW, const ResUnitArgs a) {
     using Cfg = ResTcCfg<C>;
     extern __shared__ uint8_t smem_raw[];
@@ -380,6 +359,7 @@ k_resunit_tc(const __grid_constant__ CUtensorMap tmW, const ResUnitArgs a) {
                 float al[8], ia[8];
                 load8(a.alpha1 + c0 + 8 * g, al);
                 load8(a.inv_alpha1 + c0 + 8 * g, ia);
+#pragma unroll 3
                 for (int r = rr; r < R; r += 32) {
                     const int t = t0 - 3 * a.dil + r;
                     float v[8];

@@ -48,9 +48,9 @@ struct Tap {
     float* dev;
 };
 struct TmapKey {
-    const void* p; int c, t, s, tb, wb, dt;
+    const void* p; int c, t, s, tb, wb, dt, sw;
     bool operator<(const TmapKey& o) const {
-        return std::tie(p, c, t, s, tb, wb, dt) < std::tie(o.p, o.c, o.t, o.s, o.tb, o.wb, o.dt);
+        return std::tie(p, c, t, s, tb, wb, dt, sw) < std::tie(o.p, o.c, o.t, o.s, o.tb, o.wb, o.dt, o.sw);
     }
 };
 
@@ -84,6 +84,7 @@ struct snacb_handle_s {
 
     std::vector<Tap> taps;
     uint64_t launches = 0, streams = 0;
+    bool res_v1 = false;                // SNACB_RES_V1=1: use the non-persistent ResidualUnit kernel
 
     // optional per-launch CUDA-event timing (snacb_profile / snacb_profile_report)
     struct ProfRec { int name_id; cudaEvent_t a, b; };
@@ -198,13 +199,14 @@ int make_tmap_2d(snacb_handle h, CUtensorMap* m, const void* base, uint64_t cols
     return 0;
 }
 int make_tmap_3d(snacb_handle h, CUtensorMap* m, const void* base, uint64_t C, uint64_t T, uint64_t S, uint32_t tbox,
-                 uint32_t wbox, int fp16) {
+                 uint32_t wbox, int fp16, int swizzle = 1) {
     cuuint64_t gdim[3] = {C, T, S};
     cuuint64_t gstr[2] = {C * 2, T * C * 2};
     cuuint32_t box[3] = {64, tbox, wbox};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = h->encode(m, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstr, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(h, SNACB_ERR_CUDA, "cuTensorMapEncodeTiled(3d C=%llu T=%llu S=%llu) failed: %d",
                                        (unsigned long long)C, (unsigned long long)T, (unsigned long long)S, (int)r);
@@ -223,13 +225,13 @@ int weight_map(snacb_handle h, const CUtensorMap** out, const void* w, int rows,
     return 0;
 }
 int act_map(snacb_handle h, const CUtensorMap** out, const void* base, int C, int T, int S, int tbox, int wbox,
-            int fp16) {
-    TmapKey key{base, C, T, S, tbox, wbox, fp16};
+            int fp16, int swizzle = 1) {
+    TmapKey key{base, C, T, S, tbox, wbox, fp16, swizzle};
     auto it = h->amaps.find(key);
     if (it == h->amaps.end()) {
         if (h->amaps.size() > 4096) h->amaps.clear();
         CUtensorMap m;
-        int rc = make_tmap_3d(h, &m, base, C, T, S, tbox, wbox, fp16);
+        int rc = make_tmap_3d(h, &m, base, C, T, S, tbox, wbox, fp16, swizzle);
         if (rc) return rc;
         it = h->amaps.emplace(key, m).first;
     }
@@ -398,6 +400,16 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
                 prof_end(h, st);
                 h->launches += 2;
                 CK(h, cudaGetLastError());
+            } else if (!xf32 && !h->res_v1) {
+                int tile_m, box_rows;
+                resunit2_geometry(ra.C, ra.dil, &tile_m, &box_rows);
+                const CUtensorMap* mx;
+                int rc2 = act_map(h, &mx, cur, ra.C, T, S, box_rows, 1, hk, 0);
+                if (rc2) return rc2;
+                cudaError_t le = launch_resunit2(hk, ra, *mx, r.tm_pw[hk], h->sm_count, st);
+                prof_end(h, st);
+                CK(h, le);
+                h->launches++;
             } else {
                 cudaError_t le = launch_resunit_tc(last ? EPI_RES_SNAKE : EPI_RES, hk, xf32 ? 1 : 0, ra, r.tm_pw[hk], st);
                 prof_end(h, st);
@@ -532,6 +544,7 @@ int snacb_create(snacb_handle* out, const snacb_weights* w, int device) {
         RC(upload_f32(h, &h->tail_w, tw));
         h->tail_b = w->tail_b[0];
     }
+    if (const char* e = getenv("SNACB_RES_V1")) h->res_v1 = atoi(e) != 0;
     if (const char* e = getenv("SNACB_GROUP_MB")) {
         long mb = atol(e);
         if (mb > 0) h->group_bytes = static_cast<size_t>(mb) << 20;
@@ -574,9 +587,10 @@ int snacb_stats(snacb_handle h, uint64_t* kernel_launches, uint64_t* streams_dec
 int snacb_unpack(snacb_handle h, const int32_t* tok, int B, int ntok, int flags, int32_t* c0, int32_t* c1, int32_t* c2,
                  void* stream) {
     if (!h) return SNACB_ERR_ARG;
-    if (B < 0 || ntok < 0 || (B > 0 && (!tok || !c0 || !c1 || !c2))) return fail(h, SNACB_ERR_ARG, "snacb_unpack: bad argument");
+    if (B < 0 || ntok < 0) return fail(h, SNACB_ERR_ARG, "snacb_unpack: negative size");
     const int F = ntok / kFrame;
-    if (B == 0 || F == 0) return SNACB_OK;
+    if (B == 0 || F == 0) return SNACB_OK;             // fewer than 7 codes: nothing to do (helper returns None)
+    if (!tok || !c0 || !c1 || !c2) return fail(h, SNACB_ERR_ARG, "snacb_unpack: null pointer");
     CK(h, cudaSetDevice(h->device));
     launch_unpack(tok, B, ntok, F, (flags & SNACB_RAW_IDS) ? 1 : 0, c0, c1, c2, static_cast<cudaStream_t>(stream));
     h->launches++;
