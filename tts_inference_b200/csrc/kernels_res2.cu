@@ -3,17 +3,17 @@
 //   out = x + W * snake2( dw_b + sum_j dw_w[j] * snake1(x[t + (j-3) d]) ) + b     (+ next Snake)
 //
 // One CTA per SM loops over 256-row (C<=256) or 128-row (C=512) time tiles of one stream each:
-//   * warp 16 (producer): TMA loads of the x tile + dilation halo, one 64-channel chunk per stage
+//   * warp 18 (producer): TMA loads of the x tile + dilation halo, one 64-channel chunk per stage
 //     (stream edges = TMA out-of-bounds zero fill, which is exactly the conv's zero padding because
 //     snake(0) = 0), and of the 1x1 weights (resident for C<=128, streamed per chunk otherwise);
-//   * warps 0-15 (compute): lane = channel pair, each warp owns 16 (or 8) output rows taken in
-//     dilation-class order so that the 7-tap window slides in registers: Snake1 is evaluated once per
+//   * warps 0-17 (compute): lane = channel pair, each warp owns one segment of 16 (or 8) output rows of one
+//     dilation class (rows r, r+d, r+2d, ...) so that the 7-tap window slides in registers: Snake1 is evaluated once per
 //     input row, the depthwise conv and Snake2 run in fp32, the result is packed to the 16-bit operand
 //     type straight into the 128B-swizzled K-major A tile;
-//   * warp 17 (MMA): tcgen05.mma per chunk into TMEM accumulators (two stages when they fit), so the
+//   * warp 19 (MMA): tcgen05.mma per chunk into TMEM accumulators (two stages when they fit), so the
 //     tensor work of tile i overlaps the CUDA-core prologue of tile i+1;
-//   * the compute warps then drain TMEM (tcgen05.ld), add bias + residual (+ the next layer's Snake)
-//     and store the 16-bit result.
+//   * warps 20-23 (epilogue, one per TMEM lane quadrant) drain TMEM (tcgen05.ld), add bias + residual
+//     (+ the next layer's Snake) and store the 16-bit result, concurrently with the next tile's prologue.
 #include "common.cuh"
 #include "kernels.h"
 #include "ptx.cuh"
@@ -34,8 +34,9 @@ __device__ __forceinline__ float2 unpack2(uint32_t v, const __nv_bfloat16*) {
     return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v));
 }
 
-constexpr int kComputeWarps = 16;
-constexpr int kThreads = (kComputeWarps + 2) * 32;
+constexpr int kComputeWarps = 18;     // prologue: 18 segments cover a tile for every dilation (see seg table)
+constexpr int kEpiWarps = 8;          // epilogue: two warps per TMEM lane quadrant (warps 20..27, warp%4 = quadrant)
+constexpr int kLockstepEpiWarps = 16; // C >= 256: the first 16 prologue warps drain TMEM themselves (4 quadrants x 4 column groups)
 
 template <int C, int DIL>
 struct Res2Cfg {
@@ -56,11 +57,13 @@ struct Res2Cfg {
     static constexpr int kTmemCols = kAccStages * kAccCols;          // 128 / 256 / 512 (power of two)
     static constexpr int kNHalf = C > 256 ? 2 : 1;
     static constexpr int kMmaN = C > 256 ? 256 : C;
-    static constexpr int kRowsPerWarp = kTileM / kComputeWarps;      // 16 or 8
+    static constexpr int kSegLen = kTileM / 16;                      // rows per prologue segment: 16 or 8
+    static constexpr bool kSplitEpi = (C <= 128);                    // dedicated epilogue warps (else prologue warps do it)
+    static constexpr int kThreads = (kComputeWarps + 2 + (kSplitEpi ? kEpiWarps : 0)) * 32;
     static constexpr bool kParamsSmem = (C <= 256);
     static constexpr int kPrmBytes = kParamsSmem ? (C / 2) * 96 : 0; // 24 floats per channel pair
     static constexpr int kEpiBytes = 3 * C * 4;                      // bias, alpha_next, inv_alpha_next
-    static constexpr int kMapBytes = kTileM * 2;                     // class-order row map (uint16)
+    static constexpr int kMapBytes = 128;                            // segment table (int per compute warp)
     static constexpr int kBarBytes = 256;
     static constexpr int kOffA = 0;
     static constexpr int kOffW = kOffA + kNSA * kABytes;
@@ -76,8 +79,8 @@ struct Res2Cfg {
 
 // One Snake'd input row (2 channels) from the x stage.
 template <typename HT>
-__device__ __forceinline__ float2 snake_row(const uint8_t* xs, int xrow, int lane, float2 al, float2 ia) {
-    const uint32_t raw = *reinterpret_cast<const uint32_t*>(xs + xrow * 128 + lane * 4);
+__device__ __forceinline__ float2 snake_row(const uint8_t* xlane, int xrow, float2 al, float2 ia) {
+    const uint32_t raw = *reinterpret_cast<const uint32_t*>(xlane + xrow * 128);
     float2 v = unpack2(raw, static_cast<const HT*>(nullptr));
     v.x = snake_f<true>(v.x, al.x, ia.x);
     v.y = snake_f<true>(v.y, al.y, ia.y);
@@ -85,7 +88,7 @@ __device__ __forceinline__ float2 snake_row(const uint8_t* xs, int xrow, int lan
 }
 
 template <int C, int DIL, int EPI, typename HT>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__((Res2Cfg<C, DIL>::kThreads), 1)
 k_resunit2(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const ResUnitArgs a,
            const int num_tiles) {
     using Cfg = Res2Cfg<C, DIL>;
@@ -97,7 +100,7 @@ k_resunit2(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
     uint8_t* sX = smem + Cfg::kOffXs;
     float* sPrm = reinterpret_cast<float*>(smem + Cfg::kOffPrm);
     float* sEpi = reinterpret_cast<float*>(smem + Cfg::kOffEpi);
-    uint16_t* sMap = reinterpret_cast<uint16_t*>(smem + Cfg::kOffMap);
+    int* sSeg = reinterpret_cast<int*>(smem + Cfg::kOffMap);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kOffBar);
     uint64_t* x_full = bars;              // [3]
     uint64_t* x_empty = bars + 3;         // [3]
@@ -120,7 +123,7 @@ k_resunit2(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
         for (int i = 0; i < 2; ++i) {
             mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1);
             mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1);
-            mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kComputeWarps);
+            mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], Cfg::kSplitEpi ? kEpiWarps : kLockstepEpiWarps);
         }
         fence_barrier_init();
     }
@@ -145,15 +148,21 @@ k_resunit2(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
             sEpi[C + c] = (EPI == EPI_RES_SNAKE) ? a.alpha_next[c] : 0.f;
             sEpi[2 * C + c] = (EPI == EPI_RES_SNAKE) ? a.inv_alpha_next[c] : 0.f;
         }
-        // rows of the tile in dilation-class order: class c = rows c, c+DIL, c+2 DIL, ...
-        for (int q = tid; q < Cfg::kTileM; q += kComputeWarps * 32) {
-            int rem = q, row = 0;
+        // Prologue segments: the rows of a tile split by dilation class (c, c+DIL, c+2 DIL, ...), each class cut
+        // into runs of kSegLen rows (the last run of a class is shifted back so that it ends with the class:
+        // a few rows are then computed twice with identical results).  <= 18 segments for DIL in {1,3,9}.
+        if (tid == 0) {
+            int nseg = 0;
             for (int c = 0; c < DIL; ++c) {
                 const int n = (Cfg::kTileM - c + DIL - 1) / DIL;
-                if (rem < n) { row = c + rem * DIL; break; }
-                rem -= n;
+                const int k = (n + Cfg::kSegLen - 1) / Cfg::kSegLen;
+                for (int j = 0; j < k; ++j) {
+                    int start = j * Cfg::kSegLen;
+                    if (start > n - Cfg::kSegLen) start = n - Cfg::kSegLen;
+                    if (nseg < kComputeWarps) sSeg[nseg++] = c + start * DIL;
+                }
             }
-            sMap[q] = static_cast<uint16_t>(row);
+            for (; nseg < kComputeWarps; ++nseg) sSeg[nseg] = -1;
         }
     }
     tc_fence_before();
@@ -229,12 +238,82 @@ k_resunit2(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
                 __syncwarp();
             }
         }
-    } else {
-        // ============================================================ 16 compute warps
+    } else if (Cfg::kSplitEpi && warp >= kComputeWarps + 2) {
+        // ============================================================ 8 epilogue warps (concurrent with the prologue)
         const HT* x = static_cast<const HT*>(a.x);
         HT* out = static_cast<HT*>(a.out);
-
+        const int q = warp & 3;
+        const int eh = (warp - (kComputeWarps + 2)) >> 2;       // which half of the 32-column pieces this warp takes
+        constexpr int kIters = Cfg::kAccs * (C / 32);          // 32-column pieces per tile and quadrant
+        for (int n = 0; n < my_tiles; ++n) {
+            const int tile = blockIdx.x + n * gridDim.x;
+            const int s = tile / tiles_t, t0 = (tile % tiles_t) * Cfg::kTileM;
+            const int as = n % Cfg::kAccStages;
+            const size_t srow = static_cast<size_t>(s) * a.T;
+            // residual of the first piece is fetched before waiting for the accumulator
+            uint4 xr[4], xn[4];
+            auto fetch = [&](int it, uint4 (&dst)[4]) {
+                const int ac = it / (C / 32), col = (it % (C / 32)) * 32;
+                const int t = t0 + ac * 128 + q * 32 + lane;
+                if (t < a.T) {
+                    const uint4* p = reinterpret_cast<const uint4*>(x + (srow + t) * C + col);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) dst[j] = p[j];
+                }
+            };
+            fetch(eh, xr);
+            mbar_wait(&acc_full[as], (n / Cfg::kAccStages) & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int it = eh; it < kIters; it += 2) {
+                const int ac = it / (C / 32), col = (it % (C / 32)) * 32;
+                const int t = t0 + ac * 128 + q * 32 + lane;
+                const bool valid = t < a.T;
+                uint32_t raw[32];
+                tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * Cfg::kAccCols + ac * C + col, raw);
+                if (it + 2 < kIters) fetch(it + 2, xn);
+                tmem_ld_wait();
+                if (valid) {
+                    uint4 o[4];
+                    const uint32_t* xw = reinterpret_cast<const uint32_t*>(xr);
+                    uint32_t* ow = reinterpret_cast<uint32_t*>(o);
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 b = *reinterpret_cast<const float4*>(sEpi + col + j);
+                        const float2 x0 = unpack2(xw[j / 2], static_cast<const HT*>(nullptr));
+                        const float2 x1 = unpack2(xw[j / 2 + 1], static_cast<const HT*>(nullptr));
+                        float v0 = x0.x + (__uint_as_float(raw[j]) + b.x);
+                        float v1 = x0.y + (__uint_as_float(raw[j + 1]) + b.y);
+                        float v2 = x1.x + (__uint_as_float(raw[j + 2]) + b.z);
+                        float v3 = x1.y + (__uint_as_float(raw[j + 3]) + b.w);
+                        if (EPI == EPI_RES_SNAKE) {
+                            const float4 al = *reinterpret_cast<const float4*>(sEpi + C + col + j);
+                            const float4 ia = *reinterpret_cast<const float4*>(sEpi + 2 * C + col + j);
+                            v0 = snake_f<true>(v0, al.x, ia.x);
+                            v1 = snake_f<true>(v1, al.y, ia.y);
+                            v2 = snake_f<true>(v2, al.z, ia.z);
+                            v3 = snake_f<true>(v3, al.w, ia.w);
+                        }
+                        ow[j / 2] = pack2(v0, v1, static_cast<const HT*>(nullptr));
+                        ow[j / 2 + 1] = pack2(v2, v3, static_cast<const HT*>(nullptr));
+                    }
+                    uint4* dst = reinterpret_cast<uint4*>(out + (srow + t) * C + col);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) dst[j] = o[j];
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) xr[j] = xn[j];
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[as]);
+        }
+    } else {
+        // ============================================================ 18 prologue warps
+        // lock-step epilogue (C >= 256): warp = (TMEM quadrant, accumulator / column group)
         auto epilogue = [&](int n) {
+            const HT* x = static_cast<const HT*>(a.x);
+            HT* out = static_cast<HT*>(a.out);
             const int tile = blockIdx.x + n * gridDim.x;
             const int s = tile / tiles_t, t0 = (tile % tiles_t) * Cfg::kTileM;
             const int as = n % Cfg::kAccStages;
@@ -243,8 +322,7 @@ k_resunit2(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
             constexpr int kColGroups = (Cfg::kAccs == 2) ? 2 : 4;
             const int cg = (Cfg::kAccs == 2) ? (rest >> 1) : rest;
             constexpr int kColsPerWarp = C / kColGroups;
-            const int row = ac * 128 + q * 32 + lane;
-            const int t = t0 + row;
+            const int t = t0 + ac * 128 + q * 32 + lane;
             const bool valid = t < a.T;
             const size_t grow = static_cast<size_t>(s) * a.T + t;
             mbar_wait(&acc_full[as], (n / Cfg::kAccStages) & 1);
@@ -288,7 +366,7 @@ k_resunit2(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
         };
 
         int g = 0;
-        const int q0 = warp * Cfg::kRowsPerWarp;
+        const int seg_base = sSeg[warp];
         for (int n = 0; n < my_tiles; ++n) {
             for (int kc = 0; kc < Cfg::kChunks; ++kc, ++g) {
                 // ---- per-lane parameters of channels (kc*64 + 2*lane, +1)
@@ -318,36 +396,38 @@ k_resunit2(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
                 const uint8_t* xs = sX + sx * Cfg::kXsBytes;
                 uint8_t* dstA = sA + sa * Cfg::kABytes;
 
-                // ---- sliding 7-tap window over this warp's rows (dilation-class order)
-                float2 win[7];
-                int prev = -1000;
+                // ---- this warp's segment: kSegLen output rows seg_base + i*DIL; the 7-tap window of Snake1'd rows
+                //      slides in registers (static structure: one base register + immediate offsets)
+                if (seg_base >= 0) {
+                    const uint8_t* xrow = xs + seg_base * 128 + lane * 4;      // x stage row of tap 0 of output 0
+                    float2 win[7];
 #pragma unroll
-                for (int i = 0; i < Cfg::kRowsPerWarp; ++i) {
-                    const int r = sMap[q0 + i];
-                    if (r != prev + DIL) {                      // (re)start: rows r-3d .. r+2d  (x stage row = r + j d)
+                    for (int j = 0; j < 6; ++j) win[j + 1] = snake_row<HT>(xrow, j * DIL, al1, ia1);
 #pragma unroll
-                        for (int j = 0; j < 6; ++j) win[j + 1] = snake_row<HT>(xs, r + j * DIL, lane, al1, ia1);
+                    for (int i = 0; i < Cfg::kSegLen; ++i) {
+#pragma unroll
+                        for (int j = 0; j < 6; ++j) win[j] = win[j + 1];
+                        win[6] = snake_row<HT>(xrow, (i + 6) * DIL, al1, ia1);
+                        float ax = bd.x, ay = bd.y;
+#pragma unroll
+                        for (int j = 0; j < 7; ++j) { ax = fmaf(w[j].x, win[j].x, ax); ay = fmaf(w[j].y, win[j].y, ay); }
+                        ax = snake_f<true>(ax, al2.x, ia2.x);
+                        ay = snake_f<true>(ay, al2.y, ia2.y);
+                        const int r = seg_base + i * DIL;
+                        *reinterpret_cast<uint32_t*>(dstA + (r >> 7) * 16384 + sw128_offset(r & 127, 2 * lane)) =
+                            pack2(ax, ay, static_cast<const HT*>(nullptr));
                     }
-                    prev = r;
-#pragma unroll
-                    for (int j = 0; j < 6; ++j) win[j] = win[j + 1];
-                    win[6] = snake_row<HT>(xs, r + 6 * DIL, lane, al1, ia1);
-                    float ax = bd.x, ay = bd.y;
-#pragma unroll
-                    for (int j = 0; j < 7; ++j) { ax = fmaf(w[j].x, win[j].x, ax); ay = fmaf(w[j].y, win[j].y, ay); }
-                    ax = snake_f<true>(ax, al2.x, ia2.x);
-                    ay = snake_f<true>(ay, al2.y, ia2.y);
-                    *reinterpret_cast<uint32_t*>(dstA + (r >> 7) * 16384 + sw128_offset(r & 127, 2 * lane)) =
-                        pack2(ax, ay, static_cast<const HT*>(nullptr));
                 }
                 fence_proxy_async_smem();
                 asm volatile("bar.sync 1, %0;" ::"n"(kComputeWarps * 32) : "memory");
                 if (tid == 0) { mbar_arrive(&a_full[sa]); mbar_arrive(&x_empty[sx]); }
             }
-            if (Cfg::kAccStages == 1) epilogue(n);
-            else if (n > 0) epilogue(n - 1);
+            if (!Cfg::kSplitEpi && warp < kLockstepEpiWarps) {
+                if (Cfg::kAccStages == 1) epilogue(n);
+                else if (n > 0) epilogue(n - 1);
+            }
         }
-        if (Cfg::kAccStages == 2 && my_tiles > 0) epilogue(my_tiles - 1);
+        if (!Cfg::kSplitEpi && Cfg::kAccStages == 2 && my_tiles > 0 && warp < kLockstepEpiWarps) epilogue(my_tiles - 1);
     }
     tc_fence_before();
     __syncthreads();
@@ -366,7 +446,7 @@ cudaError_t launch_t(const ResUnitArgs& a, const CUtensorMap& tmX, const CUtenso
     const int tiles = a.S * ((a.T + Cfg::kTileM - 1) / Cfg::kTileM);
     if (tiles == 0) return cudaSuccess;
     const int grid = tiles < sm_count ? tiles : sm_count;
-    k_resunit2<C, DIL, EPI, HT><<<grid, kThreads, Cfg::kSmem, st>>>(tmX, tmW, a, tiles);
+    k_resunit2<C, DIL, EPI, HT><<<grid, Cfg::kThreads, Cfg::kSmem, st>>>(tmX, tmW, a, tiles);
     return cudaGetLastError();
 }
 

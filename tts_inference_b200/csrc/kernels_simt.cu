@@ -85,7 +85,8 @@ k_vq_stem(const int32_t* __restrict__ c0, const int32_t* __restrict__ c1, const 
         for (int j = 0; j < kCodeDim; ++j) emb[lv][u][j] = e[j];
     }
     __syncthreads();
-    for (int c = threadIdx.x; c < kLatent; c += blockDim.x) {
+    {
+        const int c = blockIdx.z * blockDim.x + threadIdx.x;      // grid.z = 768 / 256 channel groups
         float wv[3][kCodeDim];
 #pragma unroll
         for (int lv = 0; lv < 3; ++lv) {
@@ -125,7 +126,7 @@ k_vq_stem(const int32_t* __restrict__ c0, const int32_t* __restrict__ c1, const 
 template <typename OutT>
 void launch_vq_stem(const int32_t* c0, const int32_t* c1, const int32_t* c2, int S, int F, const VqStemWeights& w,
                     OutT* out, cudaStream_t st) {
-    dim3 grid((4 * F + kVqTile - 1) / kVqTile, S);
+    dim3 grid((4 * F + kVqTile - 1) / kVqTile, S, kLatent / 256);
     k_vq_stem<OutT><<<grid, 256, 0, st>>>(c0, c1, c2, F, w, out);
 }
 template void launch_vq_stem<float>(const int32_t*, const int32_t*, const int32_t*, int, int, const VqStemWeights&,
