@@ -190,6 +190,7 @@ def main():
     ap.add_argument("--batch", type=int, default=1024)
     ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-latency", action="store_true")
     ap.add_argument("--profile-out", default=None, help="write the per-stage table here (json)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -265,11 +266,10 @@ def main():
     barrier()
     assert int((pcm_pin != 0).sum()) > B * 512, "e2e output looks empty"
 
-    # max over ranks
-    times = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms = float(times[0]), float(times[1])
+    # max over ranks (tts_inference_b200.dist: all_reduce MAX, identity at N=1)
+    from tts_inference_b200.dist import max_over_ranks
+    dev_ms = max_over_ranks(dev_ms, device="cuda")
+    e2e_ms = max_over_ranks(e2e_s * 1e3, device="cuda")
 
     # ------------------------------------------------------------------ per-stage profile (separate pass)
     prof = None
@@ -300,6 +300,12 @@ def main():
             os.makedirs(os.path.dirname(os.path.abspath(args.profile_out)), exist_ok=True)
             with open(args.profile_out, "w") as f:
                 json.dump(prof, f, indent=1)
+
+    # ------------------------------------------------------------------ latency mode (B=1 window), rank 0
+    latency = None
+    if rank == 0 and not args.no_latency:
+        from tts_inference_b200.bench_util import measure_latency
+        latency = measure_latency(200, args.precision, dec)
 
     if rank == 0:
         peaks = measured_peaks()
@@ -334,6 +340,7 @@ def main():
             "clocks": clocks,
             "roofline": roof,
             "cpu_baseline": cpu,
+            "latency_b1_window_ms": latency,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

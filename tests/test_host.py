@@ -1,0 +1,115 @@
+"""CPU tests of the host side: C-ABI surface, loud failure without a GPU, sharding over ranks (gloo)."""
+import os
+import re
+import socket
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from tts_inference_b200 import _lib
+    lib = _lib.load()
+    hdr = open(os.path.join(ROOT, "include", "snacb.h")).read()
+    declared = sorted(set(re.findall(r"\b(snacb_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(lib, name), f"libsnacb.so does not export {name}"
+    assert sorted(_lib.EXPORTS) == declared
+    assert lib.snacb_version() == 100
+    assert lib.snacb_samples_out(4, 0) == 8192 and lib.snacb_samples_out(4, _lib.EXTRACT_SLICE) == 2048
+    assert lib.snacb_samples_out(2, _lib.EXTRACT_SLICE) == 4096        # not > AUDIO_SLICE_END: all samples kept
+
+
+def test_no_cpu_fallback(state_dict):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from tts_inference_b200 import SnacDecoder, SnacbError, compat
+    with pytest.raises(SnacbError, match="no CUDA device"):
+        SnacDecoder(state_dict)
+    with pytest.raises(RuntimeError):
+        compat.convert_to_audio(list(range(28)))       # init_snac() never succeeded
+
+
+def test_product_does_not_import_oracle():
+    import subprocess
+    import sys
+    code = "import sys; import tts_inference_b200, tts_inference_b200.compat, tts_inference_b200.batcher, " \
+           "tts_inference_b200.synth, tts_inference_b200.dist; " \
+           "assert not any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules), 'oracle imported'"
+    subprocess.run([sys.executable, "-c", code], check=True, cwd=ROOT)
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "tts_inference_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
+
+
+def test_weights_struct_layout(state_dict):
+    from tts_inference_b200 import _lib, weights
+    folded = weights.fold_state_dict(state_dict)
+    w = _lib.make_weights(folded)
+    import ctypes as C
+    assert C.sizeof(_lib.Weights) == 8 * (9 + 4 + 4 * (4 + 3 * 6) + 3)
+    assert np.ctypeslib.as_array(w.block[3].res[2].pw_b, shape=(64,))[5] == folded["b3.r2.pw_b"][5]
+
+
+def test_shard_range_partitions():
+    from tts_inference_b200.dist import shard_range, stream_owner
+    for n in (0, 1, 7, 4096, 4099):
+        for world in (1, 2, 3, 8):
+            cover = []
+            for r in range(world):
+                s, c = shard_range(n, r, world)
+                cover += list(range(s, s + c))
+            assert cover == list(range(n))
+            sizes = [shard_range(n, r, world)[1] for r in range(world)]
+            assert max(sizes) - min(sizes) <= 1
+    assert [stream_owner(i, 8) for i in (0, 7, 8, 4095)] == [0, 7, 0, 7]
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    from tts_inference_b200 import synth
+    from tts_inference_b200.dist import max_over_ranks, shard_range, sum_over_ranks
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    tokens = synth.make_tokens(37, 4, seed=5)
+    s, c = shard_range(tokens.shape[0], rank, world)
+    mine = tokens[s:s + c]
+    checksum = float(mine.astype(np.int64).sum())
+    dist.barrier()
+    t = max_over_ranks(10.0 + rank)             # stands in for the per-rank device time
+    total = sum_over_ranks(float(c))
+    csum = sum_over_ranks(checksum)
+    q.put((rank, c, t, total, csum))
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharding_gloo():
+    """N>1 path of bench.py on CPU: shard, barrier, max-over-ranks timing, whole-job count."""
+    import torch.multiprocessing as mp
+    from tts_inference_b200 import synth
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert [r[1] for r in res] == [19, 18]
+    assert all(r[2] == 11.0 for r in res)                       # max over ranks
+    assert all(r[3] == 37.0 for r in res)                       # every stream decoded exactly once
+    assert all(r[4] == float(synth.make_tokens(37, 4, seed=5).astype(np.int64).sum()) for r in res)
