@@ -66,6 +66,27 @@ __device__ __forceinline__ float snake_f(float x, float alpha, float inv_alpha) 
     return fmaf(inv_alpha, s * s, x);
 }
 
+// Packed fp32x2 arithmetic (sm_100: FFMA2 / FMUL2 on 64-bit register pairs) -- halves the issue slots of the
+// channel-pair math in the ResidualUnit prologue.
+__device__ __forceinline__ unsigned long long f2_as_u64(float2 v) { return *reinterpret_cast<unsigned long long*>(&v); }
+__device__ __forceinline__ float2 u64_as_f2(unsigned long long v) { return *reinterpret_cast<float2*>(&v); }
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(f2_as_u64(a)), "l"(f2_as_u64(b)), "l"(f2_as_u64(c)));
+    return u64_as_f2(r);
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_as_u64(a)), "l"(f2_as_u64(b)));
+    return u64_as_f2(r);
+}
+// snake on a channel pair (fast sin): x + inv_alpha * sin(alpha x)^2
+__device__ __forceinline__ float2 snake_pair(float2 x, float2 alpha, float2 inv_alpha) {
+    const float2 t = fmul2(alpha, x);
+    const float2 s = make_float2(__sinf(t.x), __sinf(t.y));
+    return ffma2(inv_alpha, fmul2(s, s), x);
+}
+
 // int16 quantise of the reference helper: (x*32767).clamp(-32768,32767).to(int16) -- truncation
 // toward zero (vllm_inference/modal_audio_stream.py:201; numpy astype in tensorrt_tts/inference.py:110).
 __device__ __forceinline__ int16_t pcm16(float x) {

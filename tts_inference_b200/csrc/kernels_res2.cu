@@ -77,16 +77,6 @@ struct Res2Cfg {
     static_assert(kSmem <= 232448, "shared memory budget");
 };
 
-// One Snake'd input row (2 channels) from the x stage.
-template <typename HT>
-__device__ __forceinline__ float2 snake_row(const uint8_t* xlane, int xrow, float2 al, float2 ia) {
-    const uint32_t raw = *reinterpret_cast<const uint32_t*>(xlane + xrow * 128);
-    float2 v = unpack2(raw, static_cast<const HT*>(nullptr));
-    v.x = snake_f<true>(v.x, al.x, ia.x);
-    v.y = snake_f<true>(v.y, al.y, ia.y);
-    return v;
-}
-
 template <int C, int DIL, int EPI, typename HT>
 __global__ void __launch_bounds__((Res2Cfg<C, DIL>::kThreads), 1)
 k_resunit2(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const ResUnitArgs a,
@@ -119,9 +109,9 @@ k_resunit2(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
     if (tid == 0) {
         prefetch_tmap(&tmX);
         prefetch_tmap(&tmW);
-        for (int i = 0; i < 3; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); }
+        for (int i = 0; i < 3; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], kComputeWarps); }
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1);
+            mbar_init(&a_full[i], kComputeWarps); mbar_init(&a_empty[i], 1);
             mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1);
             mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], Cfg::kSplitEpi ? kEpiWarps : kLockstepEpiWarps);
         }
@@ -399,28 +389,36 @@ k_resunit2(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
                 // ---- this warp's segment: kSegLen output rows seg_base + i*DIL; the 7-tap window of Snake1'd rows
                 //      slides in registers (static structure: one base register + immediate offsets)
                 if (seg_base >= 0) {
-                    const uint8_t* xrow = xs + seg_base * 128 + lane * 4;      // x stage row of tap 0 of output 0
+                    const uint32_t xaddr = smem_u32(xs + seg_base * 128 + lane * 4);   // x stage row of tap 0 of output 0
+                    // all kSegLen+6 input rows of the segment are fetched up front (packed 16-bit pairs, one
+                    // register each) so that their shared-memory latency is paid once, not per row
+                    uint32_t xr[Cfg::kSegLen + 6];
+#pragma unroll
+                    for (int j = 0; j < Cfg::kSegLen + 6; ++j)
+                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(xr[j]) : "r"(xaddr + j * DIL * 128));
                     float2 win[7];
 #pragma unroll
-                    for (int j = 0; j < 6; ++j) win[j + 1] = snake_row<HT>(xrow, j * DIL, al1, ia1);
+                    for (int j = 0; j < 6; ++j)
+                        win[j + 1] = snake_pair(unpack2(xr[j], static_cast<const HT*>(nullptr)), al1, ia1);
 #pragma unroll
                     for (int i = 0; i < Cfg::kSegLen; ++i) {
 #pragma unroll
                         for (int j = 0; j < 6; ++j) win[j] = win[j + 1];
-                        win[6] = snake_row<HT>(xrow, (i + 6) * DIL, al1, ia1);
-                        float ax = bd.x, ay = bd.y;
+                        win[6] = snake_pair(unpack2(xr[i + 6], static_cast<const HT*>(nullptr)), al1, ia1);
+                        float2 acc = bd;
 #pragma unroll
-                        for (int j = 0; j < 7; ++j) { ax = fmaf(w[j].x, win[j].x, ax); ay = fmaf(w[j].y, win[j].y, ay); }
-                        ax = snake_f<true>(ax, al2.x, ia2.x);
-                        ay = snake_f<true>(ay, al2.y, ia2.y);
+                        for (int j = 0; j < 7; ++j) acc = ffma2(w[j], win[j], acc);
+                        acc = snake_pair(acc, al2, ia2);
                         const int r = seg_base + i * DIL;
                         *reinterpret_cast<uint32_t*>(dstA + (r >> 7) * 16384 + sw128_offset(r & 127, 2 * lane)) =
-                            pack2(ax, ay, static_cast<const HT*>(nullptr));
+                            pack2(acc.x, acc.y, static_cast<const HT*>(nullptr));
                     }
                 }
+                // per-warp hand-off (no CTA-wide barrier): make this warp's generic-proxy writes visible to the
+                // tensor core, then one lane arrives for the warp on the A-stage and x-stage barriers
                 fence_proxy_async_smem();
-                asm volatile("bar.sync 1, %0;" ::"n"(kComputeWarps * 32) : "memory");
-                if (tid == 0) { mbar_arrive(&a_full[sa]); mbar_arrive(&x_empty[sx]); }
+                __syncwarp();
+                if (lane == 0) { mbar_arrive(&a_full[sa]); mbar_arrive(&x_empty[sx]); }
             }
             if (!Cfg::kSplitEpi && warp < kLockstepEpiWarps) {
                 if (Cfg::kAccStages == 1) epilogue(n);

@@ -74,7 +74,7 @@ struct snacb_handle_s {
     std::map<TmapKey, CUtensorMap> amaps;
 
     // workspace
-    size_t group_bytes = 48u << 20;
+    size_t group_bytes = static_cast<size_t>(1) << 30;   // per activation buffer; launches are per group
     void* ws_buf[3] = {nullptr, nullptr, nullptr};
     size_t ws_buf_bytes = 0;
     void* ws_a0 = nullptr; size_t ws_a0_bytes = 0;
