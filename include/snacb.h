@@ -49,6 +49,8 @@ typedef enum {
 #define SNACB_STREAM_FP32    0x10  /* tensor-core path: keep the residual stream in fp32 between kernels  */
 #define SNACB_BF16           0x20  /* tensor-core path: bf16 operands / activations instead of fp16 (same
                                       rate; 3 fewer mantissa bits -- see DESIGN.md "precision")              */
+#define SNACB_UNFUSED        0x40  /* tensor-core path: one kernel per layer instead of the fused
+                                      NoiseBlock + ResidualUnit chain (A/B checks, per-stage taps)          */
 
 /* Folded fp32 weights of the decode half of snac_24khz, host pointers.  Weight-norm is already
  * folded (w = g * v / ||v||, norm over dim 0: per OUTPUT channel for Conv1d, per INPUT channel for
@@ -141,6 +143,12 @@ int snacb_profile_report(snacb_handle h, char* buf, size_t cap);
 int snacb_debug_tap_count(snacb_handle h);
 int snacb_debug_tap_info(snacb_handle h, int idx, char* name, int name_cap, int64_t* rows, int64_t* cols);
 int snacb_debug_tap_copy(snacb_handle h, int idx, float* dst_host, size_t dst_elems);
+
+/* Host-side schedule of the fused NoiseBlock + ResidualUnit chain kernel (C = 64 or 128 channels): for each
+ * of the 3 ResidualUnits (dilation 1, 3, 9) and each of the 16 warps, up to 2 spans {first_row, octets, chunk};
+ * a span covers rows first_row + k*dilation, k < 8*octets, of one 64-channel chunk.  out: int16[3][16][2][3].
+ * Returns the tile height in rows (incl. the 40-row halo either side) or SNACB_ERR_ARG.  No GPU needed. */
+int snacb_debug_chain_spans(int C, int16_t* out, int cap);
 
 /* ---------------------------------------------------------------------------------------------
  * Batcher: the multi-stream replacement of stream_audio's per-stream buffer policy

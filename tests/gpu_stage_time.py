@@ -13,4 +13,4 @@ for i in range(10):
     dec.decode(tok, raw_ids=True, extract_slice=True, seed=i)
 rep = dec.profile_report()
 tot = sum(ms for _, ms in rep.values())
-print("DBG", os.environ.get("SNACB_DBG", "0"), " ".join(f"{k}={ms / c * 1e3:.1f}" for k, (c, ms) in rep.items() if "res" in k), f"total={tot / 10 * 1e3:.0f}us")
+print(" ".join(f"{k}={ms / c * 1e3:.1f}" for k, (c, ms) in rep.items()), f"total={tot / 10 * 1e3:.0f}us")

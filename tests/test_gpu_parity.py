@@ -116,11 +116,29 @@ def test_tensorcore_stage_taps(decoder, oracle_model):
     tokens = synth.make_tokens(2, 4, seed=4)
     noises = synth.make_noises(2, 16, seed=8)
     _, rt = oracle_decode(oracle_model, tokens, noises, want_taps=True)
-    decoder.decode(_cuda(tokens), raw_ids=True, noise=[_cuda(n) for n in noises], precision="fp16", keep_taps=True)
+    decoder.decode(_cuda(tokens), raw_ids=True, noise=[_cuda(n) for n in noises], precision="fp16", keep_taps=True,
+                   unfused=True)
     taps = decoder.taps()
     for k, r in rt.items():
         assert taps[k].shape == r.shape, k
         assert snr_db(r, taps[k]) >= 45.0, (k, snr_db(r, taps[k]))
+
+
+@pytest.mark.parametrize("B,F_", [(2, 4), (3, 1), (1, 7)])
+def test_fused_chain_block_outputs(decoder, oracle_model, B, F_):
+    """The fused NoiseBlock + ResidualUnit chain (blocks 2 and 3): block outputs against the oracle's, and the
+    waveform against the per-layer kernels on the same inputs."""
+    tokens = synth.make_tokens(B, F_, seed=40 + F_, bad_frac=0.02)
+    noises = synth.make_noises(B, 4 * F_, seed=8)
+    nz = [_cuda(n) for n in noises]
+    _, rt = oracle_decode(oracle_model, tokens, noises, want_taps=True)
+    _, wf = decoder.decode(_cuda(tokens), raw_ids=True, noise=nz, precision="fp16", keep_taps=True, return_wave=True)
+    taps = decoder.taps()
+    for k in ("b0.res2", "b1.res2", "b2.res2", "b3.res2"):
+        assert taps[k].shape == rt[k].shape, k
+        assert snr_db(rt[k], taps[k]) >= 45.0, (k, snr_db(rt[k], taps[k]))
+    _, wu = decoder.decode(_cuda(tokens), raw_ids=True, noise=nz, precision="fp16", unfused=True, return_wave=True)
+    assert snr_db(wu.cpu().numpy(), wf.cpu().numpy()) >= 45.0
 
 
 # ------------------------------------------------------------------------------------ helper semantics

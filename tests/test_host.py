@@ -113,3 +113,54 @@ def test_two_rank_sharding_gloo():
     assert all(r[2] == 11.0 for r in res)                       # max over ranks
     assert all(r[3] == 37.0 for r in res)                       # every stream decoded exactly once
     assert all(r[4] == float(synth.make_tokens(37, 4, seed=5).astype(np.int64).sum()) for r in res)
+
+
+@pytest.mark.parametrize("C", [64, 128])
+def test_chain_span_schedule(C):
+    """Schedule of the fused chain kernel's in-place prologue (host logic, no GPU): emulate the kernel's protocol
+    on integers -- every warp first fetches the 3 rows before/after its spans, then all warps rewrite their rows
+    in place in arbitrary order -- and check that every row whose result is needed at that layer is produced from
+    the layer's ORIGINAL inputs (no read-after-overwrite hazard), for dilations 1, 3, 9."""
+    import ctypes as Ct
+    from tts_inference_b200 import _lib
+    lib = _lib.load()
+    buf = (Ct.c_int16 * (3 * 16 * 2 * 3))()
+    rows = lib.snacb_debug_chain_spans(C, buf, len(buf))
+    assert rows == (1024 if C == 64 else 512)
+    sp = np.frombuffer(buf, dtype=np.int16).reshape(3, 16, 2, 3)
+    need_lo = {1: 4, 3: 13, 9: 40}          # first row whose result is consumed downstream, per dilation
+    rng = np.random.default_rng(0)
+    for l, d in enumerate((1, 3, 9)):
+        for kc in range(C // 64):
+            x = rng.integers(1, 1 << 30, size=rows).astype(np.int64)       # layer input (one value per row)
+            f = lambda r, src: int(sum((j + 2) * (src[r + (j - 3) * d] if 0 <= r + (j - 3) * d < rows else 0)
+                                       for j in range(7)))                 # stands in for the 7-tap op
+            want = {r: f(r, x) for r in range(rows)}
+            work = x.copy()
+            spans = [(w, k, *sp[l, w, k]) for w in range(16) for k in range(2) if sp[l, w, k, 1] > 0 and sp[l, w, k, 2] == kc]
+            pre = {}
+            for (w, k, r0, noct, _) in spans:                               # phase 1: pre-reads
+                assert r0 % 8 == 0
+                head = [work[r0 - (3 - j) * d] if r0 - (3 - j) * d >= 0 else 0 for j in range(3)]
+                tail = [work[r0 + (8 * noct + j) * d] if r0 + (8 * noct + j) * d < rows else 0 for j in range(3)]
+                pre[(w, k)] = (head, tail)
+            written = set()
+            for (w, k, r0, noct, _) in sorted(spans, key=lambda s_: rng.random()):   # phase 2, any warp order
+                head, tail = pre[(w, k)]
+                n = 8 * noct
+                get = lambda i: (head[i + 3] if i < 0 else tail[i - n] if i >= n else
+                                 (work[r0 + i * d] if 0 <= r0 + i * d < rows else 0))
+                win = [get(i) for i in range(-3, 3)]
+                for q in range(noct):
+                    raw = [get(8 * q + kk + 3) for kk in range(8)]          # the octet's 8 loads come first
+                    for kk in range(8):
+                        win = win[-6:] + [raw[kk]]
+                        r = r0 + (8 * q + kk) * d
+                        if 0 <= r < rows:
+                            assert r not in written
+                            written.add(r)
+                            work[r] = sum((j + 2) * win[j] for j in range(7))
+            for r in range(need_lo[d], rows - need_lo[d]):
+                assert r in written and work[r] == want[r], (C, d, kc, r)
+    per_warp = sp[:, :, :, 1].sum(axis=2)
+    assert per_warp.max() - per_warp.min() <= 1                             # balanced to one octet

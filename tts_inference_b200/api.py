@@ -60,7 +60,7 @@ class SnacDecoder:
         return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
     @staticmethod
-    def _flags(raw_ids, extract_slice, precision, keep_taps=False, stream_fp32=False) -> int:
+    def _flags(raw_ids, extract_slice, precision, keep_taps=False, stream_fp32=False, unfused=False) -> int:
         if precision not in ("fp16", "bf16", "fp32"):
             raise ValueError("precision must be 'fp16', 'bf16' or 'fp32'")
         f = 0
@@ -70,6 +70,7 @@ class SnacDecoder:
         f |= _lib.BF16 if precision == "bf16" else 0
         f |= _lib.KEEP_TAPS if keep_taps else 0
         f |= _lib.STREAM_FP32 if stream_fp32 else 0
+        f |= _lib.UNFUSED if unfused else 0
         return f
 
     def samples_out(self, frames: int, extract_slice: bool) -> int:
@@ -100,14 +101,15 @@ class SnacDecoder:
 
     def decode(self, tokens, *, raw_ids: bool = False, extract_slice: bool = False,
                noise: Optional[Sequence] = None, seed: int = 0, precision: str = "fp16",
-               out=None, return_wave: bool = False, keep_taps: bool = False, stream_fp32: bool = False):
+               out=None, return_wave: bool = False, keep_taps: bool = False, stream_fp32: bool = False,
+               unfused: bool = False):
         """tokens: cuda int32 [B, n>=7F] (trailing partial frame ignored, as the helper does).
         Returns int16 [B, samples] (and the fp32 waveform when ``return_wave``)."""
         import torch
         assert tokens.is_cuda and tokens.dtype == torch.int32 and tokens.dim() == 2 and tokens.is_contiguous()
         B, n = tokens.shape
         frames = n // FRAME
-        flags = self._flags(raw_ids, extract_slice, precision, keep_taps, stream_fp32)
+        flags = self._flags(raw_ids, extract_slice, precision, keep_taps, stream_fp32, unfused)
         ns = self.samples_out(frames, extract_slice)
         if out is None:
             out = torch.empty((B, ns), dtype=torch.int16, device=tokens.device)

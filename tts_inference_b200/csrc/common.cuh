@@ -58,6 +58,28 @@ struct ResUnitArgs {
     const float* alpha_next; const float* inv_alpha_next;  // [C] (EPI_RES_SNAKE)
 };
 
+// Fused NoiseBlock + 3 ResidualUnits of one DecoderBlock (kernels_chain.cu).
+constexpr int kChainWarps = 16;
+constexpr int kChainHalo = 40;
+struct ChainSpan { short r_first, n_oct, kc, pad; };   // a warp's run of 8-step octets along one dilation class
+struct ChainLayer {
+    const float *alpha1, *inv1;   // [C]
+    const float* dw_w;            // [7][C]
+    const float* dw_b;            // [C]
+    const float *alpha2, *inv2;   // [C]
+};
+struct ChainArgs {
+    int S, T, C;
+    void* out;                    // [S*T][C] 16-bit, Snake of the next layer applied
+    ChainLayer res[3];
+    const float* bias_cum;        // [3][C]: b_0, b_0+b_1, b_0+b_1+b_2 (1x1 biases, added when TMEM is read)
+    const float *alpha_next, *inv_next;   // [C]
+    const float* noise;           // [S][T] injected noise or null -> counter RNG
+    unsigned long long seed;
+    int noise_stage, stream_offset;
+    ChainSpan spans[3][kChainWarps][2];
+};
+
 // ---------------------------------------------------------------- math
 // snake(x) = x + (alpha + 1e-9)^-1 * sin(alpha x)^2   (upstream snac layers.py; oracle/snac_ref.py)
 template <bool kFast>

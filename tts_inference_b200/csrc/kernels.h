@@ -48,4 +48,12 @@ void resunit2_geometry(int C, int dil, int* tile_m, int* box_rows);   // x tenso
 cudaError_t launch_resunit2(int half_fp16, const ResUnitArgs& a, const CUtensorMap& tmX, const CUtensorMap& tmW,
                             int sm_count, cudaStream_t st);
 
+// ---- kernels_chain.cu  (NoiseBlock + 3 ResidualUnits fused, residual stream in TMEM)
+bool chain_supported(int C);
+int chain_tile_rows(int C);           // y tensor-map box = (64, 128, 1), 128B swizzle
+void chain_build_spans(int C, ChainSpan (*spans)[kChainWarps][2]);
+// tmW: noise 1x1, res d=1, d=3, d=9 weight maps, box (64, C)
+cudaError_t launch_chain(int half_fp16, const ChainArgs& a, const CUtensorMap& tmY, const CUtensorMap* tmW,
+                         int sm_count, cudaStream_t st);
+
 }  // namespace snacb

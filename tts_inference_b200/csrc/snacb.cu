@@ -41,6 +41,9 @@ struct BlockW {
     float* nz_f32;                      // [Cout][Cout]
     void* nz_h[2];
     ResW res[3];
+    float* bias_cum;                    // [3][Cout] running sums of the ResidualUnit 1x1 biases (fused chain)
+    bool chain;                         // the fused NoiseBlock + ResidualUnit chain covers this block
+    ChainSpan spans[3][kChainWarps][2];
 };
 struct Tap {
     std::string name;
@@ -85,6 +88,7 @@ struct snacb_handle_s {
     std::vector<Tap> taps;
     uint64_t launches = 0, streams = 0;
     bool res_v1 = false;                // SNACB_RES_V1=1: use the non-persistent ResidualUnit kernel
+    bool no_chain = false;              // SNACB_NO_CHAIN=1: per-layer kernels instead of the fused chain
 
     // optional per-launch CUDA-event timing (snacb_profile / snacb_profile_report)
     struct ProfRec { int name_id; cudaEvent_t a, b; };
@@ -363,6 +367,38 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
             rc = tap_any(nm, oth, dt_h, (int64_t)S * T, b.Cout);
             if (rc) return rc;
         }
+        // ---- fused NoiseBlock + 3 ResidualUnits + next Snake: oth -> cur, one kernel
+        const bool unfused = (flags & SNACB_UNFUSED) != 0 || h->no_chain;
+        if (!f32 && !xf32 && !unfused && b.chain) {
+            ChainArgs ca{};
+            ca.S = S; ca.T = T; ca.C = b.Cout; ca.out = cur;
+            for (int ri = 0; ri < 3; ++ri) {
+                const ResW& r = b.res[ri];
+                ca.res[ri] = ChainLayer{r.alpha1, r.inv1, r.dw_w, r.dw_b, r.alpha2, r.inv2};
+            }
+            ca.bias_cum = b.bias_cum;
+            ca.alpha_next = bi < 3 ? h->blk[bi + 1].alpha : h->tail_alpha;
+            ca.inv_next = bi < 3 ? h->blk[bi + 1].inv_alpha : h->tail_inv;
+            ca.noise = noise ? noise[bi] : nullptr; ca.seed = seed; ca.noise_stage = bi; ca.stream_offset = stream_offset;
+            memcpy(ca.spans, b.spans, sizeof ca.spans);
+            const CUtensorMap *my, *mn;
+            int rc = act_map(h, &my, oth, b.Cout, T, S, 128, 1, hk, 1);
+            if (rc) return rc;
+            rc = weight_map(h, &mn, b.nz_h[hk], b.Cout, b.Cout, b.Cout, hk);
+            if (rc) return rc;
+            const CUtensorMap wm[4] = {*mn, b.res[0].tm_pw[hk], b.res[1].tm_pw[hk], b.res[2].tm_pw[hk]};
+            snprintf(nm, sizeof nm, "b%d.chain", bi);
+            prof_begin(h, nm, st);
+            cudaError_t le = launch_chain(hk, ca, *my, wm, h->sm_count, st);
+            prof_end(h, st);
+            CK(h, le);
+            h->launches++;
+            snprintf(nm, sizeof nm, "b%d.res2", bi);
+            rc = tap_any(nm, cur, dt_h, (int64_t)S * T, b.Cout);
+            if (rc) return rc;
+            Tin = T;
+            continue;
+        }
         // ---- NoiseBlock: oth -> cur   x = y + n * (Wn y)
         {
             GemmArgs a{};
@@ -533,6 +569,16 @@ int snacb_create(snacb_handle* out, const snacb_weights* w, int device) {
             RC(upload_f32(h, &r.pw_b, vec(rs.pw_b, C)));
             for (int k = 0; k < 2; ++k) RC(make_tmap_2d(h, &r.tm_pw[k], r.pw_h[k], C, C, C > 256 ? 256 : C, k));
         }
+        {
+            std::vector<float> bc(static_cast<size_t>(3) * b.Cout);
+            for (int c = 0; c < b.Cout; ++c) {
+                float acc = 0.f;
+                for (int ri = 0; ri < 3; ++ri) { acc += s.res[ri].pw_b[c]; bc[static_cast<size_t>(ri) * b.Cout + c] = acc; }
+            }
+            RC(upload_f32(h, &b.bias_cum, bc));
+            b.chain = chain_supported(b.Cout);
+            if (b.chain) chain_build_spans(b.Cout, b.spans);
+        }
         cin = b.Cout;
     }
     RC(upload_f32(h, &h->tail_alpha, vec(w->tail_alpha, 64)));
@@ -545,6 +591,7 @@ int snacb_create(snacb_handle* out, const snacb_weights* w, int device) {
         h->tail_b = w->tail_b[0];
     }
     if (const char* e = getenv("SNACB_RES_V1")) h->res_v1 = atoi(e) != 0;
+    if (const char* e = getenv("SNACB_NO_CHAIN")) h->no_chain = atoi(e) != 0;
     if (const char* e = getenv("SNACB_GROUP_MB")) {
         long mb = atol(e);
         if (mb > 0) h->group_bytes = static_cast<size_t>(mb) << 20;
@@ -702,6 +749,19 @@ int snacb_profile_report(snacb_handle h, char* buf, size_t cap) {
     if (out.size() + 1 > cap) return fail(h, SNACB_ERR_ARG, "snacb_profile_report: buffer too small");
     memcpy(buf, out.c_str(), out.size() + 1);
     return SNACB_OK;
+}
+
+int snacb_debug_chain_spans(int C, int16_t* out, int cap) {
+    if (!out || !chain_supported(C) || cap < 3 * kChainWarps * 2 * 3) return SNACB_ERR_ARG;
+    ChainSpan sp[3][kChainWarps][2];
+    chain_build_spans(C, sp);
+    for (int l = 0; l < 3; ++l)
+        for (int w = 0; w < kChainWarps; ++w)
+            for (int k = 0; k < 2; ++k) {
+                int16_t* o = out + ((l * kChainWarps + w) * 2 + k) * 3;
+                o[0] = sp[l][w][k].r_first; o[1] = sp[l][w][k].n_oct; o[2] = sp[l][w][k].kc;
+            }
+    return chain_tile_rows(C);
 }
 
 int snacb_debug_tap_count(snacb_handle h) { return h ? static_cast<int>(h->taps.size()) : SNACB_ERR_ARG; }
