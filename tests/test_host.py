@@ -124,10 +124,12 @@ def test_chain_span_schedule(C):
     import ctypes as Ct
     from tts_inference_b200 import _lib
     lib = _lib.load()
-    buf = (Ct.c_int16 * (3 * 16 * 2 * 3))()
-    rows = lib.snacb_debug_chain_spans(C, buf, len(buf))
-    assert rows == (1024 if C == 64 else 512)
-    sp = np.frombuffer(buf, dtype=np.int16).reshape(3, 16, 2, 3)
+    buf = (Ct.c_int16 * (3 * 16 * 3 * 3))()
+    rc = lib.snacb_debug_chain_spans(C, buf, len(buf))
+    rows, nw = rc & 0xFFFF, rc >> 16
+    assert rows % 128 == 0 and 256 <= rows <= 1024 and nw in (8, 16)
+    sp = np.frombuffer(buf, dtype=np.int16).reshape(3, 16, 3, 3)
+    assert (sp[:, nw:, :, 1] == 0).all()
     need_lo = {1: 4, 3: 13, 9: 40}          # first row whose result is consumed downstream, per dilation
     rng = np.random.default_rng(0)
     for l, d in enumerate((1, 3, 9)):
@@ -137,7 +139,7 @@ def test_chain_span_schedule(C):
                                        for j in range(7)))                 # stands in for the 7-tap op
             want = {r: f(r, x) for r in range(rows)}
             work = x.copy()
-            spans = [(w, k, *sp[l, w, k]) for w in range(16) for k in range(2) if sp[l, w, k, 1] > 0 and sp[l, w, k, 2] == kc]
+            spans = [(w, k, *sp[l, w, k]) for w in range(16) for k in range(3) if sp[l, w, k, 1] > 0 and sp[l, w, k, 2] == kc]
             pre = {}
             for (w, k, r0, noct, _) in spans:                               # phase 1: pre-reads
                 assert r0 % 8 == 0
@@ -162,5 +164,5 @@ def test_chain_span_schedule(C):
                             work[r] = sum((j + 2) * win[j] for j in range(7))
             for r in range(need_lo[d], rows - need_lo[d]):
                 assert r in written and work[r] == want[r], (C, d, kc, r)
-    per_warp = sp[:, :, :, 1].sum(axis=2)
+    per_warp = sp[:, :nw, :, 1].sum(axis=2)
     assert per_warp.max() - per_warp.min() <= 1                             # balanced to one octet

@@ -59,7 +59,8 @@ struct ResUnitArgs {
 };
 
 // Fused NoiseBlock + 3 ResidualUnits of one DecoderBlock (kernels_chain.cu).
-constexpr int kChainWarps = 16;
+constexpr int kChainWarps = 16;        // at most; a launch configuration may use 8
+constexpr int kChainSpans = 3;         // spans per warp and layer, at most
 constexpr int kChainHalo = 40;
 struct ChainSpan { short r_first, n_oct, kc, pad; };   // a warp's run of 8-step octets along one dilation class
 struct ChainLayer {
@@ -77,7 +78,9 @@ struct ChainArgs {
     const float* noise;           // [S][T] injected noise or null -> counter RNG
     unsigned long long seed;
     int noise_stage, stream_offset;
-    ChainSpan spans[3][kChainWarps][2];
+    ChainSpan spans[3][kChainWarps][kChainSpans];
+    int* tile_counter;            // zeroed before the launch: tiles beyond the first gridDim.x are claimed dynamically
+    unsigned long long* prof;     // debug: 20 per-phase clock64 sums of CTA 0 / thread 0 (SNACB_CHAIN_PROF=1), else null
 };
 
 // ---------------------------------------------------------------- math

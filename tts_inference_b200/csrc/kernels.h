@@ -50,10 +50,11 @@ cudaError_t launch_resunit2(int half_fp16, const ResUnitArgs& a, const CUtensorM
 
 // ---- kernels_chain.cu  (NoiseBlock + 3 ResidualUnits fused, residual stream in TMEM)
 bool chain_supported(int C);
-int chain_tile_rows(int C);           // y tensor-map box = (64, 128, 1), 128B swizzle
-void chain_build_spans(int C, ChainSpan (*spans)[kChainWarps][2]);
-// tmW: noise 1x1, res d=1, d=3, d=9 weight maps, box (64, C)
-cudaError_t launch_chain(int half_fp16, const ChainArgs& a, const CUtensorMap& tmY, const CUtensorMap* tmW,
-                         int sm_count, cudaStream_t st);
+int chain_tile_rows(int C);           // rows of a tile incl. the halo (y tensor-map box = (64, 128, 1), 128B swizzle)
+int chain_warps(int C);               // warps per CTA of the launch configuration used for C channels
+void chain_build_spans(int C, ChainSpan (*spans)[kChainWarps][kChainSpans]);
+// tm[7]: y load map box (64,128,1); out store maps box (64,128-kChainHalo,1) and (64,128,1); noise 1x1, res d=1,
+// d=3, d=9 weight maps box (64, C); all 128B-swizzled
+cudaError_t launch_chain(int half_fp16, const ChainArgs& a, const CUtensorMap* tm, int sm_count, cudaStream_t st);
 
 }  // namespace snacb

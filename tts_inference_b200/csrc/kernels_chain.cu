@@ -6,17 +6,21 @@
 //   x_{l+1} = x_l + W_l snake2(dw_d(snake1(x_l))) + b_l      d = 1, 3, 9  (ResidualUnit)
 //   out = snake_next(x_4)
 //
-//   * the fp32 residual stream lives in TENSOR MEMORY: tcgen05.mma accumulates every layer's 1x1
-//     conv directly on top of it (accumulate = 1); it is seeded with y by an MMA against a 64x64 identity;
+//   * the fp32 residual stream lives in TENSOR MEMORY: the NoiseBlock epilogue writes x1 there (tcgen05.st)
+//     and tcgen05.mma then accumulates every ResidualUnit's 1x1 conv directly on top of it;
 //   * a single 16-bit copy of the tile lives in shared memory (128B-swizzled K-major, the UMMA A-operand
 //     layout, filled by TMA).  Each layer rewrites it IN PLACE: the prologue turns x_l into the operand
 //     snake2(dw(snake1(x_l))) with a 7-tap window sliding in registers along one dilation class (taps of row r
 //     are r + j*d, so a class only ever reads its own rows; the 3 rows either side of a warp's span are
-//     fetched before a CTA barrier), the MMAs consume it, and the epilogue writes x_{l+1} = TMEM + bias
-//     back as 16-bit for the next prologue;
+//     fetched before a CTA barrier), the MMAs consume it block by block, and the epilogue of each 128-row block
+//     (started as soon as that block's MMAs commit) writes x_{l+1} = TMEM + bias back as 16-bit;
+//   * fp16 operands: the prologue runs the Snake tails and the depthwise conv in packed half2 (HFMA2) -- the
+//     FMA pipe, not MUFU, bounds the fp32 formulation; bf16 keeps fp32 math;
 //   * a tile carries a 40-row halo either side (3*(1+3+9) = 39 rows of receptive field); halo results are
 //     garbage by construction and never stored.  Rows outside [0, T) are forced to zero after every layer
 //     (the convs' zero padding);
+//   * the last epilogue leaves snake_next(x_4) in the tile copy and TMA stores stream it out block by block while
+//     the next tile's TMA loads refill the blocks behind them;
 //   * HBM traffic: the ConvTranspose output is read once (+ halo), the block output written once.
 #include <cstdio>
 #include <cstdlib>
@@ -33,8 +37,8 @@ using namespace ptx;
 namespace {
 
 template <typename HT> struct HalfFmtC;
-template <> struct HalfFmtC<__half> { static constexpr uint32_t kFmt = 0; static constexpr uint16_t kOne = 0x3C00; };
-template <> struct HalfFmtC<__nv_bfloat16> { static constexpr uint32_t kFmt = 1; static constexpr uint16_t kOne = 0x3F80; };
+template <> struct HalfFmtC<__half> { static constexpr uint32_t kFmt = 0; };
+template <> struct HalfFmtC<__nv_bfloat16> { static constexpr uint32_t kFmt = 1; };
 
 __device__ __forceinline__ float2 unpack2c(uint32_t v, const __half*) {
     return __half22float2(*reinterpret_cast<const __half2*>(&v));
@@ -42,9 +46,9 @@ __device__ __forceinline__ float2 unpack2c(uint32_t v, const __half*) {
 __device__ __forceinline__ float2 unpack2c(uint32_t v, const __nv_bfloat16*) {
     return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v));
 }
+__device__ __forceinline__ __half2 as_h2(uint32_t v) { return *reinterpret_cast<const __half2*>(&v); }
+__device__ __forceinline__ uint32_t as_u32(__half2 v) { return *reinterpret_cast<const uint32_t*>(&v); }
 
-constexpr int kWarps = kChainWarps;          // 16 symmetric warps: prologue, epilogue; thread 0 also issues TMA / MMA
-constexpr int kThreads = kWarps * 32;
 constexpr int kHalo = kChainHalo;            // 40 >= 39, multiple of 8
 
 template <int C, int NB>
@@ -57,76 +61,199 @@ struct ChainCfg {
     static constexpr bool kWRes = (C == 64);                // all four 1x1 weights resident
     static constexpr int kWLayer = C * C * 2;               // one layer's weights [kCH][C rows][128 B]
     static constexpr int kWBytes = kWRes ? 4 * kWLayer : 2 * kWLayer;
-    static constexpr int kIBytes = 8192;                    // 64 x 64 identity
-    static constexpr int kPrmBytes = 3 * (C / 2) * 96;      // per layer and channel pair: 24 floats
+    static constexpr int kPrmBytes = 3 * (C / 2) * 96;      // per layer and channel pair: 24 words
     static constexpr int kEpiBytes = 5 * C * 4;             // bias_cum[3][C], alpha_next[C], inv_next[C]
+    static constexpr int kNzBytes = kRows * 4;              // noise value of every tile row
     static constexpr int kOffX = 0;
     static constexpr int kOffW = kOffX + kXBytes;
-    static constexpr int kOffI = kOffW + kWBytes;
-    static constexpr int kOffPrm = kOffI + kIBytes;
+    static constexpr int kOffPrm = kOffW + kWBytes;
     static constexpr int kOffEpi = kOffPrm + kPrmBytes;
-    static constexpr int kOffBar = kOffEpi + kEpiBytes;
-    static constexpr int kSmem = kOffBar + 128 + 1024;
+    static constexpr int kOffNz = kOffEpi + kEpiBytes;
+    static constexpr int kOffBar = kOffNz + kNzBytes;
+    static constexpr int kSmem = kOffBar + 256 + 1024;
     static constexpr int kTmemCols = NB * C;
+    static_assert(NB >= 2 && NB <= 8, "blocks per tile");
     static_assert(kTmemCols == 512 || kTmemCols == 256 || kTmemCols == 128, "TMEM columns");
     static_assert(kSmem <= 232448, "shared memory budget");
     static_assert(kWBytes >= 16384, "tail pre-reads may run up to 90 rows past the tile");
-    static_assert(kRows % kThreads == 0 || kThreads % kRows == 0, "noise row mapping");
 };
+
+// ---------------------------------------------------------------------------------------------------------
+// One span of the in-place prologue: rows r_oct + k*D, k < 8*nq, of one 64-channel chunk (lane = channel pair).
+// h0..h2 / t0..t2: the three rows before / after the span (fetched before the barrier, other warps rewrite them).
+// ---------------------------------------------------------------------------------------------------------
+template <int D, int ROWS>
+__device__ __forceinline__ void span_half(uint8_t* plane, int r_oct, const int nq, const uint32_t h0, const uint32_t h1,
+                                          const uint32_t h2, const uint32_t t0, const uint32_t t1, const uint32_t t2,
+                                          const uint32_t (&swz)[8], const uint32_t* prm) {
+    const uint4 q0 = *reinterpret_cast<const uint4*>(prm), q1 = *reinterpret_cast<const uint4*>(prm + 4);
+    const uint4 q2 = *reinterpret_cast<const uint4*>(prm + 8), q3 = *reinterpret_cast<const uint4*>(prm + 12);
+    const float2 al1 = make_float2(__uint_as_float(q0.x), __uint_as_float(q0.y));
+    const float2 al2 = make_float2(__uint_as_float(q0.z), __uint_as_float(q0.w));
+    const __half2 ia1 = as_h2(q1.x), ia2 = as_h2(q1.y), bd = as_h2(q1.z);
+    const __half2 w[7] = {as_h2(q1.w), as_h2(q2.x), as_h2(q2.y), as_h2(q2.z), as_h2(q2.w), as_h2(q3.x), as_h2(q3.y)};
+    auto snake1 = [&](uint32_t raw) -> __half2 {
+        const __half2 xh = as_h2(raw);
+        const float2 t = fmul2(al1, __half22float2(xh));
+        const __half2 sh = __floats2half2_rn(__sinf(t.x), __sinf(t.y));
+        return __hfma2(ia1, __hmul2(sh, sh), xh);
+    };
+    __half2 win[7];
+    win[1] = snake1(h0); win[2] = snake1(h1); win[3] = snake1(h2);
+    uint8_t* ob = plane + r_oct * 128;             // r_oct = 0 (mod 8): (row & 7) of step k is (k*D) & 7
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        uint32_t raw = 0u;                         // class starts may lie up to 24 rows above the tile
+        if (r_oct + j * D >= 0) raw = *reinterpret_cast<const uint32_t*>(ob + j * D * 128 + swz[(j * D) & 7]);
+        win[4 + j] = snake1(raw);
+    }
+#pragma unroll 1
+    for (int qo = 0; qo < nq; ++qo) {
+        uint32_t raw[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            raw[k] = *reinterpret_cast<const uint32_t*>(ob + (k + 3) * D * 128 + swz[((k + 3) * D) & 7]);
+        if (qo == nq - 1) { raw[5] = t0; raw[6] = t1; raw[7] = t2; }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+#pragma unroll
+            for (int j = 0; j < 6; ++j) win[j] = win[j + 1];
+            win[6] = snake1(raw[k]);
+            __half2 acc = bd;
+#pragma unroll
+            for (int j = 0; j < 7; ++j) acc = __hfma2(w[j], win[j], acc);
+            const float2 t = fmul2(al2, __half22float2(acc));
+            const __half2 sh = __floats2half2_rn(__sinf(t.x), __sinf(t.y));
+            const __half2 o = __hfma2(ia2, __hmul2(sh, sh), acc);
+            const int r = r_oct + k * D;
+            if (static_cast<unsigned>(r) < static_cast<unsigned>(ROWS))
+                *reinterpret_cast<uint32_t*>(ob + k * D * 128 + swz[(k * D) & 7]) = as_u32(o);
+        }
+        r_oct += 8 * D;
+        ob += 8 * D * 128;
+    }
+}
+
+// same span, fp32 math (bf16 operands: an 8-bit mantissa cannot carry the depthwise accumulation)
+template <int D, int ROWS, typename HT>
+__device__ __forceinline__ void span_f32(uint8_t* plane, int r_oct, const int nq, const uint32_t h0, const uint32_t h1,
+                                         const uint32_t h2, const uint32_t t0, const uint32_t t1, const uint32_t t2,
+                                         const uint32_t (&swz)[8], const uint32_t* prm) {
+    const float4* p4 = reinterpret_cast<const float4*>(prm);
+    const float4 q0 = p4[0], q1 = p4[1], q2 = p4[2], q3 = p4[3], q4 = p4[4], q5 = p4[5];
+    const float2 al1 = make_float2(q0.x, q0.y), ia1 = make_float2(q0.z, q0.w);
+    const float2 w[7] = {make_float2(q1.x, q1.y), make_float2(q1.z, q1.w), make_float2(q2.x, q2.y), make_float2(q2.z, q2.w),
+                         make_float2(q3.x, q3.y), make_float2(q3.z, q3.w), make_float2(q4.x, q4.y)};
+    const float2 bd = make_float2(q4.z, q4.w);
+    const float2 al2 = make_float2(q5.x, q5.y), ia2 = make_float2(q5.z, q5.w);
+    const HT* tag = nullptr;
+    float2 win[7];
+    win[1] = snake_pair(unpack2c(h0, tag), al1, ia1);
+    win[2] = snake_pair(unpack2c(h1, tag), al1, ia1);
+    win[3] = snake_pair(unpack2c(h2, tag), al1, ia1);
+    uint8_t* ob = plane + r_oct * 128;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        uint32_t raw = 0u;
+        if (r_oct + j * D >= 0) raw = *reinterpret_cast<const uint32_t*>(ob + j * D * 128 + swz[(j * D) & 7]);
+        win[4 + j] = snake_pair(unpack2c(raw, tag), al1, ia1);
+    }
+#pragma unroll 1
+    for (int qo = 0; qo < nq; ++qo) {
+        uint32_t raw[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            raw[k] = *reinterpret_cast<const uint32_t*>(ob + (k + 3) * D * 128 + swz[((k + 3) * D) & 7]);
+        if (qo == nq - 1) { raw[5] = t0; raw[6] = t1; raw[7] = t2; }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+#pragma unroll
+            for (int j = 0; j < 6; ++j) win[j] = win[j + 1];
+            win[6] = snake_pair(unpack2c(raw[k], tag), al1, ia1);
+            float2 acc = bd;
+#pragma unroll
+            for (int j = 0; j < 7; ++j) acc = ffma2(w[j], win[j], acc);
+            acc = snake_pair(acc, al2, ia2);
+            const int r = r_oct + k * D;
+            if (static_cast<unsigned>(r) < static_cast<unsigned>(ROWS))
+                *reinterpret_cast<uint32_t*>(ob + k * D * 128 + swz[(k * D) & 7]) = pack2(acc.x, acc.y, tag);
+        }
+        r_oct += 8 * D;
+        ob += 8 * D * 128;
+    }
+}
+
+enum { EPI_C_NOISE = 0, EPI_C_MID = 1, EPI_C_FINAL = 2 };
 
 }  // namespace
 
-template <int C, int NB, typename HT>
-__global__ void __launch_bounds__(kThreads, 1)
-k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmWn,
+// NW symmetric warps (prologue + epilogue); thread 0 also issues TMA / MMA.  16 warps: one CTA per SM; 8 warps: two.
+template <int C, int NB, int NW, typename HT>
+__global__ void __launch_bounds__(NW * 32) __maxnreg__(NW == 8 ? 112 : 128)
+k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmOe,
+        const __grid_constant__ CUtensorMap tmOm, const __grid_constant__ CUtensorMap tmWn,
         const __grid_constant__ CUtensorMap tmW0, const __grid_constant__ CUtensorMap tmW1,
         const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ ChainArgs a, const int num_tiles) {
     using Cfg = ChainCfg<C, NB>;
     constexpr int CH = Cfg::kCH;
+    constexpr int kThreads = NW * 32;
+    constexpr bool kHalfMath = std::is_same<HT, __half>::value;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* sX = smem + Cfg::kOffX;
     uint8_t* sW = smem + Cfg::kOffW;
-    uint8_t* sI = smem + Cfg::kOffI;
-    float* sPrm = reinterpret_cast<float*>(smem + Cfg::kOffPrm);
+    uint32_t* sPrm = reinterpret_cast<uint32_t*>(smem + Cfg::kOffPrm);
     float* sEpi = reinterpret_cast<float*>(smem + Cfg::kOffEpi);
+    float* sNz = reinterpret_cast<float*>(smem + Cfg::kOffNz);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kOffBar);
     uint64_t* ld_bar = bars;          // tile landed (TMA)
-    uint64_t* mma_bar = bars + 1;     // all MMAs of a layer complete
-    uint64_t* w_bar = bars + 2;       // [2] weight buffers landed
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+    uint64_t* w_bar = bars + 1;       // [2] weight buffers landed
+    uint64_t* mma_bar = bars + 3;     // [NB] the layer's MMAs of one 128-row block complete
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 + NB);
+    volatile int* s_next = reinterpret_cast<volatile int*>(tmem_slot + 2);   // [2] next tile of this CTA, by tile parity
 
+    const long long t_kernel0 = clock64();
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const int tiles_t = (a.T + Cfg::kROut - 1) / Cfg::kROut;
-    const int my_tiles = (num_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
     const CUtensorMap* wmaps[4] = {&tmWn, &tmW0, &tmW1, &tmW2};
 
     // ------------------------------------------------------------------ one-time setup
     if (tid == 0) {
-        prefetch_tmap(&tmY); prefetch_tmap(&tmWn); prefetch_tmap(&tmW0); prefetch_tmap(&tmW1); prefetch_tmap(&tmW2);
-        mbar_init(ld_bar, 1); mbar_init(mma_bar, 1); mbar_init(&w_bar[0], 1); mbar_init(&w_bar[1], 1);
+        prefetch_tmap(&tmY); prefetch_tmap(&tmOe); prefetch_tmap(&tmOm);
+        prefetch_tmap(&tmWn); prefetch_tmap(&tmW0); prefetch_tmap(&tmW1); prefetch_tmap(&tmW2);
+        mbar_init(ld_bar, 1); mbar_init(&w_bar[0], 1); mbar_init(&w_bar[1], 1);
+        for (int b = 0; b < NB; ++b) mbar_init(&mma_bar[b], 1);
         fence_barrier_init();
     }
     if (warp == 1) { tmem_alloc(tmem_slot, Cfg::kTmemCols); tmem_relinquish(); }
-    for (int i = tid; i < 3 * (C / 2); i += kThreads) {            // per-layer prologue parameters, 24 floats per channel pair
+    for (int i = tid; i < 3 * (C / 2); i += kThreads) {            // per-layer prologue parameters of one channel pair
         const int l = i / (C / 2), ch = 2 * (i % (C / 2));
         const ChainLayer& L = a.res[l];
-        float* d = sPrm + i * 24;
-        d[0] = L.alpha1[ch]; d[1] = L.alpha1[ch + 1];
-        d[2] = L.inv1[ch]; d[3] = L.inv1[ch + 1];
+        uint32_t* d = sPrm + i * 24;
+        if (kHalfMath) {
+            // words: alpha1 (2 x f32), alpha2 (2 x f32), then half2: inv1, inv2, dw bias, dw taps 0..6
+            d[0] = __float_as_uint(L.alpha1[ch]); d[1] = __float_as_uint(L.alpha1[ch + 1]);
+            d[2] = __float_as_uint(L.alpha2[ch]); d[3] = __float_as_uint(L.alpha2[ch + 1]);
+            d[4] = as_u32(__floats2half2_rn(L.inv1[ch], L.inv1[ch + 1]));
+            d[5] = as_u32(__floats2half2_rn(L.inv2[ch], L.inv2[ch + 1]));
+            d[6] = as_u32(__floats2half2_rn(L.dw_b[ch], L.dw_b[ch + 1]));
 #pragma unroll
-        for (int j = 0; j < 7; ++j) { d[4 + 2 * j] = L.dw_w[j * C + ch]; d[5 + 2 * j] = L.dw_w[j * C + ch + 1]; }
-        d[18] = L.dw_b[ch]; d[19] = L.dw_b[ch + 1];
-        d[20] = L.alpha2[ch]; d[21] = L.alpha2[ch + 1];
-        d[22] = L.inv2[ch]; d[23] = L.inv2[ch + 1];
+            for (int j = 0; j < 7; ++j) d[7 + j] = as_u32(__floats2half2_rn(L.dw_w[j * C + ch], L.dw_w[j * C + ch + 1]));
+        } else {
+            d[0] = __float_as_uint(L.alpha1[ch]); d[1] = __float_as_uint(L.alpha1[ch + 1]);
+            d[2] = __float_as_uint(L.inv1[ch]); d[3] = __float_as_uint(L.inv1[ch + 1]);
+#pragma unroll
+            for (int j = 0; j < 7; ++j) {
+                d[4 + 2 * j] = __float_as_uint(L.dw_w[j * C + ch]); d[5 + 2 * j] = __float_as_uint(L.dw_w[j * C + ch + 1]);
+            }
+            d[18] = __float_as_uint(L.dw_b[ch]); d[19] = __float_as_uint(L.dw_b[ch + 1]);
+            d[20] = __float_as_uint(L.alpha2[ch]); d[21] = __float_as_uint(L.alpha2[ch + 1]);
+            d[22] = __float_as_uint(L.inv2[ch]); d[23] = __float_as_uint(L.inv2[ch + 1]);
+        }
     }
     for (int c = tid; c < 3 * C; c += kThreads) sEpi[c] = a.bias_cum[c];
     for (int c = tid; c < C; c += kThreads) { sEpi[3 * C + c] = a.alpha_next[c]; sEpi[4 * C + c] = a.inv_next[c]; }
-    for (int i = tid; i < Cfg::kIBytes / 4; i += kThreads) reinterpret_cast<uint32_t*>(sI)[i] = 0u;
-    __syncthreads();
-    if (tid < 64) *reinterpret_cast<uint16_t*>(sI + sw128_offset(tid, tid)) = HalfFmtC<HT>::kOne;
-    fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -140,17 +267,17 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
 #pragma unroll
         for (int kc = 0; kc < CH; ++kc) tma_load_2d(dst + kc * (C * 128), wmaps[l], kc * 64, 0, bar);
     };
-    auto load_tile = [&](int n) {             // thread 0
-        const int tile = blockIdx.x + n * gridDim.x;
-        const int s = tile / tiles_t, t_start = (tile % tiles_t) * Cfg::kROut - kHalo;
-        mbar_expect_tx(ld_bar, Cfg::kXBytes);
+    auto tile_coords = [&](int tile, int& s, int& t_start) {
+        s = tile / tiles_t;
+        t_start = (tile % tiles_t) * Cfg::kROut - kHalo;
+    };
+    auto load_block = [&](int s, int t_start, int b) {      // thread 0; ld_bar's expect_tx covers the whole tile
 #pragma unroll
         for (int kc = 0; kc < CH; ++kc)
-#pragma unroll
-            for (int b = 0; b < NB; ++b)
-                tma_load_3d(sX + kc * Cfg::kPlane + b * 16384, &tmY, kc * 64, t_start + b * 128, s, ld_bar);
+            tma_load_3d(sX + kc * Cfg::kPlane + b * 16384, &tmY, kc * 64, t_start + b * 128, s, ld_bar);
     };
-    if (tid == 0 && my_tiles > 0) {
+    int tile = blockIdx.x;
+    if (tid == 0 && tile < num_tiles) {
         if (Cfg::kWRes) {
             mbar_expect_tx(&w_bar[0], 4 * Cfg::kWLayer);
             for (int l = 0; l < 4; ++l) load_w(l, 0);
@@ -158,11 +285,13 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
             load_w(0, 0);
             load_w(1, 1);
         }
-        load_tile(0);
+        int s, t_start;
+        tile_coords(tile, s, t_start);
+        mbar_expect_tx(ld_bar, Cfg::kXBytes);
+        for (int b = 0; b < NB; ++b) load_block(s, t_start, b);
     }
 
     uint32_t mma_par = 0;
-    constexpr uint32_t idescI = umma_idesc_f16(128, 64, HalfFmtC<HT>::kFmt);
     constexpr uint32_t idescW = umma_idesc_f16(128, C, HalfFmtC<HT>::kFmt);
 
     // swizzled byte offset of this lane's channel pair inside a 128-byte row, for each (row & 7)
@@ -171,7 +300,7 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
     for (int j = 0; j < 8; ++j) swz[j] = ((((lane >> 2) ^ j) & 7) << 4) + ((lane & 3) << 2);
     const uint32_t sx_addr = smem_u32(sX);
 
-    // issue one layer's 1x1 conv for the whole tile (thread 0): TMEM[blk] += A[blk] * W^T
+    // issue one layer's 1x1 conv for the whole tile (thread 0): TMEM[blk] (+)= A[blk] * W^T, one commit per block
     auto issue_layer = [&](int l, int n) {
         const int buf = l & 1;
         if (Cfg::kWRes) { if (n == 0 && l == 0) mbar_wait(&w_bar[0], 0); }
@@ -179,152 +308,140 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
         tc_fence_after();
         const uint32_t w_addr = smem_u32(sW + (Cfg::kWRes ? l : buf) * Cfg::kWLayer);
 #pragma unroll
-        for (int b = 0; b < NB; ++b)
+        for (int b = 0; b < NB; ++b) {
 #pragma unroll
             for (int kc = 0; kc < CH; ++kc)
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
                     mma_f16_ss(tmem_base + b * C, umma_desc_sw128(sx_addr + kc * Cfg::kPlane + b * 16384 + k * 32),
-                               umma_desc_sw128(w_addr + kc * (C * 128) + k * 32), idescW, 1u);
-        mma_commit(mma_bar);
+                               umma_desc_sw128(w_addr + kc * (C * 128) + k * 32), idescW,
+                               (l > 0 || kc > 0 || k > 0) ? 1u : 0u);
+            mma_commit(&mma_bar[b]);
+        }
     };
-    // after layer l's MMAs completed: its weight buffer is free -> prefetch the layer two ahead (thread 0)
-    auto prefetch_w = [&](int l, int n) {
+    // after ALL of layer l's MMAs completed: its weight buffer is free -> prefetch the layer two ahead (thread 0)
+    auto prefetch_w = [&](int l, bool has_next) {
         if (Cfg::kWRes) return;
         const int l2 = (l + 2) & 3;
-        if (l + 2 < 4 || n + 1 < my_tiles) load_w(l2, l & 1);
+        if (l + 2 < 4 || has_next) load_w(l2, l & 1);
     };
 
-    // epilogue: TMEM (+ cumulative bias) -> 16-bit tile copy (kFinal = false) or Snake -> global (kFinal = true)
-    auto epilogue = [&](const float* bias, bool has_bias, bool final_layer, int s, int t_start) {
+    // epilogue of one layer; each 128-row block is drained as soon as its MMAs have committed
+    //   NOISE: x1 = y + n[t] * TMEM  -> TMEM (fp32 residual stream) and the 16-bit tile copy
+    //   MID:   tile copy = TMEM + cumulative bias          FINAL: tile copy = snake_next(TMEM + cumulative bias)
+    auto epilogue = [&](auto mode_tag, const float* bias, int t_start) {
+        constexpr int MODE = decltype(mode_tag)::value;
         const int q = warp & 3, g = warp >> 2;
         constexpr int kPieces = NB * (C / 32);
-        HT* out = static_cast<HT*>(a.out);
+        const HT* tag = nullptr;
 #pragma unroll 1
-        for (int it = g; it < kPieces; it += 4) {
+        for (int it = g; it < kPieces; it += NW / 4) {
             const int blk = it / (C / 32), cg = it % (C / 32);
+            mbar_wait(&mma_bar[blk], mma_par);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + blk * C + cg * 32;
             uint32_t raw[32];
-            tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + blk * C + cg * 32, raw);
-            tmem_ld_wait();
+            tmem_ld32(taddr, raw);
             const int i = blk * 128 + q * 32 + lane;
             const int t = t_start + i;
             const bool valid = static_cast<unsigned>(t) < static_cast<unsigned>(a.T);
+            uint8_t* row = sX + (cg >> 1) * Cfg::kPlane + i * 128;
+            uint4 yv[4];
+            float nz = 0.f;
+            if (MODE == EPI_C_NOISE) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) yv[c] = *reinterpret_cast<const uint4*>(row + ((((cg & 1) * 4 + c) ^ (i & 7)) << 4));
+                nz = sNz[i];
+            }
+            tmem_ld_wait();
             uint32_t o[16];
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
-                float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (has_bias) b = *reinterpret_cast<const float4*>(bias + cg * 32 + j);
-                float v0 = __uint_as_float(raw[j]) + b.x, v1 = __uint_as_float(raw[j + 1]) + b.y;
-                float v2 = __uint_as_float(raw[j + 2]) + b.z, v3 = __uint_as_float(raw[j + 3]) + b.w;
-                if (final_layer) {
+                float v0 = __uint_as_float(raw[j]), v1 = __uint_as_float(raw[j + 1]);
+                float v2 = __uint_as_float(raw[j + 2]), v3 = __uint_as_float(raw[j + 3]);
+                if (MODE == EPI_C_NOISE) {
+                    const uint32_t* yw = reinterpret_cast<const uint32_t*>(yv);
+                    const float2 y0 = unpack2c(yw[j / 2], tag), y1 = unpack2c(yw[j / 2 + 1], tag);
+                    v0 = fmaf(nz, v0, y0.x); v1 = fmaf(nz, v1, y0.y); v2 = fmaf(nz, v2, y1.x); v3 = fmaf(nz, v3, y1.y);
+                    raw[j] = __float_as_uint(v0); raw[j + 1] = __float_as_uint(v1);
+                    raw[j + 2] = __float_as_uint(v2); raw[j + 3] = __float_as_uint(v3);
+                } else {
+                    const float4 b = *reinterpret_cast<const float4*>(bias + cg * 32 + j);
+                    v0 += b.x; v1 += b.y; v2 += b.z; v3 += b.w;
+                }
+                if (MODE == EPI_C_FINAL) {
                     const float4 al = *reinterpret_cast<const float4*>(sEpi + 3 * C + cg * 32 + j);
                     const float4 ia = *reinterpret_cast<const float4*>(sEpi + 4 * C + cg * 32 + j);
                     v0 = snake_f<true>(v0, al.x, ia.x); v1 = snake_f<true>(v1, al.y, ia.y);
                     v2 = snake_f<true>(v2, al.z, ia.z); v3 = snake_f<true>(v3, al.w, ia.w);
                 }
-                o[j / 2] = pack2(v0, v1, static_cast<const HT*>(nullptr));
-                o[j / 2 + 1] = pack2(v2, v3, static_cast<const HT*>(nullptr));
+                o[j / 2] = pack2(v0, v1, tag);
+                o[j / 2 + 1] = pack2(v2, v3, tag);
             }
-            if (final_layer) {
-                if (valid && i >= kHalo && i < Cfg::kRows - kHalo) {
-                    uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<size_t>(s) * a.T + t) * C + cg * 32);
+            if (MODE == EPI_C_NOISE) tmem_st32(taddr, raw);
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) dst[c] = make_uint4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
-                }
-            } else {
-                uint8_t* row = sX + (cg >> 1) * Cfg::kPlane + i * 128;
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const int chunk = ((cg & 1) * 4 + c) ^ (i & 7);
-                    *reinterpret_cast<uint4*>(row + chunk * 16) =
-                        valid ? make_uint4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]) : make_uint4(0u, 0u, 0u, 0u);
-                }
+            for (int c = 0; c < 4; ++c) {
+                const int chunk = ((cg & 1) * 4 + c) ^ (i & 7);
+                *reinterpret_cast<uint4*>(row + chunk * 16) =
+                    (valid || MODE == EPI_C_FINAL) ? make_uint4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3])
+                                                   : make_uint4(0u, 0u, 0u, 0u);
             }
+        }
+        if (MODE == EPI_C_NOISE) tmem_st_wait();
+    };
+
+    long long t_last = clock64();
+    auto tick = [&](int slot) {
+        if (a.prof != nullptr && tid == 0 && blockIdx.x == 0) {
+            const long long t = clock64();
+            a.prof[slot] += static_cast<unsigned long long>(t - t_last);
+            t_last = t;
         }
     };
 
-    for (int n = 0; n < my_tiles; ++n) {
-        const int tile = blockIdx.x + n * gridDim.x;
-        const int s = tile / tiles_t, t_start = (tile % tiles_t) * Cfg::kROut - kHalo;
+    for (int n = 0; tile < num_tiles; ++n) {
+        int s, t_start;
+        tile_coords(tile, s, t_start);
+        // claim the tile after this one (persistent CTAs, dynamic order: tiles cost the same but SMs do not run alike)
+        if (tid == 0) s_next[n & 1] = static_cast<int>(gridDim.x) + atomicAdd(a.tile_counter, 1);
 
-        // ---------------------------------------------------------------- tile landed -> TMEM = y (identity MMA)
-        mbar_wait(ld_bar, n & 1);
-        tc_fence_after();
-        if (tid == 0) {
-            const uint32_t i_addr = smem_u32(sI);
-#pragma unroll
-            for (int b = 0; b < NB; ++b)
-#pragma unroll
-                for (int kc = 0; kc < CH; ++kc)
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        mma_f16_ss(tmem_base + b * C + kc * 64,
-                                   umma_desc_sw128(sx_addr + kc * Cfg::kPlane + b * 16384 + k * 32),
-                                   umma_desc_sw128(i_addr + k * 32), idescI, k > 0 ? 1u : 0u);
-            mma_commit(mma_bar);
-        }
-        // noise values of this thread's rows (overlaps the identity MMA)
-        constexpr int kRowsPerThread = (Cfg::kRows + kThreads - 1) / kThreads;
-        float nzv[kRowsPerThread];
+        // ---------------------------------------------------------------- noise values (overlaps the tile load)
         {
             unsigned long long key = 0;
             if (a.noise == nullptr)
                 key = splitmix64(a.seed * 0x100000001B3ull + static_cast<unsigned long long>(100 + a.noise_stage));
-#pragma unroll
-            for (int r = 0; r < kRowsPerThread; ++r) {
-                const int i = tid + r * kThreads;
+            for (int i = tid; i < Cfg::kRows; i += kThreads) {
                 const int t = t_start + i;
                 float v = 0.f;
-                if (i < Cfg::kRows && static_cast<unsigned>(t) < static_cast<unsigned>(a.T))
+                if (static_cast<unsigned>(t) < static_cast<unsigned>(a.T))
                     v = a.noise ? a.noise[static_cast<size_t>(s) * a.T + t]
                                 : counter_normal(key, static_cast<unsigned long long>(a.stream_offset + s) * a.T + t);
-                nzv[r] = v;
+                sNz[i] = v;
             }
         }
-        mbar_wait(mma_bar, mma_par); mma_par ^= 1u;
-        // ---------------------------------------------------------------- NoiseBlock: operand = n[t] * y, in place
-#pragma unroll
-        for (int r = 0; r < kRowsPerThread; ++r) {
-            const int i = tid + r * kThreads;
-            if (i < Cfg::kRows) {
-                const float nz = nzv[r];
-#pragma unroll
-                for (int kc = 0; kc < CH; ++kc) {
-                    uint8_t* row = sX + kc * Cfg::kPlane + i * 128;
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        uint4* p = reinterpret_cast<uint4*>(row + ((c ^ (i & 7)) << 4));
-                        uint4 v = *p;
-                        uint32_t* w = reinterpret_cast<uint32_t*>(&v);
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const float2 f = unpack2c(w[e], static_cast<const HT*>(nullptr));
-                            w[e] = pack2(f.x * nz, f.y * nz, static_cast<const HT*>(nullptr));
-                        }
-                        *p = v;
-                    }
-                }
-            }
-        }
-        fence_proxy_async_smem();
+        mbar_wait(ld_bar, n & 1);
         __syncthreads();
+        const int next_tile = s_next[n & 1];
+        const bool has_next = next_tile < num_tiles;
+        tick(0);
+        // ---------------------------------------------------------------- NoiseBlock: TMEM = Wn y, then x1 = y + n TMEM
         if (tid == 0) issue_layer(0, n);
-        mbar_wait(mma_bar, mma_par); mma_par ^= 1u;
-        tc_fence_after();
-        if (tid == 0) prefetch_w(0, n);
-        epilogue(nullptr, false, false, s, t_start);
+        epilogue(std::integral_constant<int, EPI_C_NOISE>{}, nullptr, t_start);
+        if (tid == 0) { mbar_wait(&mma_bar[NB - 1], mma_par); prefetch_w(0, has_next); }
+        mma_par ^= 1u;
         tc_fence_before();
         __syncthreads();
+        tick(1);
 
         // ---------------------------------------------------------------- three ResidualUnits
 #pragma unroll 1
         for (int l = 0; l < 3; ++l) {
             const int d = (l == 0) ? 1 : (l == 1 ? 3 : 9);
             // ---- spans of this warp: pre-read the 3 rows before and after each span (owned by other warps)
-            uint32_t hd[2][3], tl[2][3];
-            int r_first[2], n_oct[2], kcs[2];
+            uint32_t hd[kChainSpans][3], tl[kChainSpans][3];
+            int r_first[kChainSpans], n_oct[kChainSpans], kcs[kChainSpans];
 #pragma unroll
-            for (int sp = 0; sp < 2; ++sp) {
+            for (int sp = 0; sp < kChainSpans; ++sp) {
                 const ChainSpan spn = a.spans[l][warp][sp];
                 r_first[sp] = spn.r_first; n_oct[sp] = spn.n_oct; kcs[sp] = spn.kc;
                 const uint8_t* plane = sX + spn.kc * Cfg::kPlane;
@@ -341,82 +458,84 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
                 }
             }
             __syncthreads();
+            tick(2 + 4 * l);
 #pragma unroll 1
-            for (int sp = 0; sp < 2; ++sp) {
-                const int nq = sp ? n_oct[1] : n_oct[0];
+            for (int sp = 0; sp < kChainSpans; ++sp) {
+                const int nq = sp == 0 ? n_oct[0] : (sp == 1 ? n_oct[1] : n_oct[2]);
                 if (nq == 0) continue;
-                const int kc = sp ? kcs[1] : kcs[0];
-                int r_oct = sp ? r_first[1] : r_first[0];
-                const uint32_t h0 = sp ? hd[1][0] : hd[0][0], h1 = sp ? hd[1][1] : hd[0][1], h2 = sp ? hd[1][2] : hd[0][2];
-                const uint32_t t0 = sp ? tl[1][0] : tl[0][0], t1 = sp ? tl[1][1] : tl[0][1], t2 = sp ? tl[1][2] : tl[0][2];
-                // per-lane parameters of channels (kc*64 + 2*lane, +1)
-                const float4* p4 = reinterpret_cast<const float4*>(sPrm + ((l * (C / 2)) + kc * 32 + lane) * 24);
-                const float4 q0 = p4[0], q1 = p4[1], q2 = p4[2], q3 = p4[3], q4 = p4[4], q5 = p4[5];
-                const float2 al1 = make_float2(q0.x, q0.y), ia1 = make_float2(q0.z, q0.w);
-                float2 w[7];
-                w[0] = make_float2(q1.x, q1.y); w[1] = make_float2(q1.z, q1.w);
-                w[2] = make_float2(q2.x, q2.y); w[3] = make_float2(q2.z, q2.w);
-                w[4] = make_float2(q3.x, q3.y); w[5] = make_float2(q3.z, q3.w);
-                w[6] = make_float2(q4.x, q4.y);
-                const float2 bd = make_float2(q4.z, q4.w);
-                const float2 al2 = make_float2(q5.x, q5.y), ia2 = make_float2(q5.z, q5.w);
-
+                const int kc = sp == 0 ? kcs[0] : (sp == 1 ? kcs[1] : kcs[2]);
+                const int r0 = sp == 0 ? r_first[0] : (sp == 1 ? r_first[1] : r_first[2]);
+                uint32_t hh[3], tt[3];
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    hh[j] = sp == 0 ? hd[0][j] : (sp == 1 ? hd[1][j] : hd[2][j]);
+                    tt[j] = sp == 0 ? tl[0][j] : (sp == 1 ? tl[1][j] : tl[2][j]);
+                }
+                const uint32_t* prm = sPrm + ((l * (C / 2)) + kc * 32 + lane) * 24;
                 uint8_t* plane = sX + kc * Cfg::kPlane;
-                auto run = [&](auto dtag) {
-                    constexpr int D = decltype(dtag)::value;
-                    float2 win[7];
-                    win[1] = snake_pair(unpack2c(h0, static_cast<const HT*>(nullptr)), al1, ia1);
-                    win[2] = snake_pair(unpack2c(h1, static_cast<const HT*>(nullptr)), al1, ia1);
-                    win[3] = snake_pair(unpack2c(h2, static_cast<const HT*>(nullptr)), al1, ia1);
-                    uint8_t* ob = plane + r_oct * 128;             // r_oct = 0 (mod 8): (row & 7) of step k is (k*D) & 7
-#pragma unroll
-                    for (int j = 0; j < 3; ++j) {
-                        uint32_t raw = 0u;               // class starts may lie up to 24 rows above the tile
-                        if (r_oct + j * D >= 0) raw = *reinterpret_cast<const uint32_t*>(ob + j * D * 128 + swz[(j * D) & 7]);
-                        win[4 + j] = snake_pair(unpack2c(raw, static_cast<const HT*>(nullptr)), al1, ia1);
-                    }
-#pragma unroll 1
-                    for (int qo = 0; qo < nq; ++qo) {
-                        uint32_t raw[8];
-#pragma unroll
-                        for (int k = 0; k < 8; ++k)
-                            raw[k] = *reinterpret_cast<const uint32_t*>(ob + (k + 3) * D * 128 + swz[((k + 3) * D) & 7]);
-                        if (qo == nq - 1) { raw[5] = t0; raw[6] = t1; raw[7] = t2; }
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) {
-#pragma unroll
-                            for (int j = 0; j < 6; ++j) win[j] = win[j + 1];
-                            win[6] = snake_pair(unpack2c(raw[k], static_cast<const HT*>(nullptr)), al1, ia1);
-                            float2 acc = bd;
-#pragma unroll
-                            for (int j = 0; j < 7; ++j) acc = ffma2(w[j], win[j], acc);
-                            acc = snake_pair(acc, al2, ia2);
-                            const int r = r_oct + k * D;
-                            if (static_cast<unsigned>(r) < static_cast<unsigned>(Cfg::kRows))
-                                *reinterpret_cast<uint32_t*>(ob + k * D * 128 + swz[(k * D) & 7]) =
-                                    pack2(acc.x, acc.y, static_cast<const HT*>(nullptr));
-                        }
-                        r_oct += 8 * D;
-                        ob += 8 * D * 128;
-                    }
-                };
-                if (d == 1) run(std::integral_constant<int, 1>{});
-                else if (d == 3) run(std::integral_constant<int, 3>{});
-                else run(std::integral_constant<int, 9>{});
+                if (kHalfMath) {
+                    if (d == 1) span_half<1, Cfg::kRows>(plane, r0, nq, hh[0], hh[1], hh[2], tt[0], tt[1], tt[2], swz, prm);
+                    else if (d == 3) span_half<3, Cfg::kRows>(plane, r0, nq, hh[0], hh[1], hh[2], tt[0], tt[1], tt[2], swz, prm);
+                    else span_half<9, Cfg::kRows>(plane, r0, nq, hh[0], hh[1], hh[2], tt[0], tt[1], tt[2], swz, prm);
+                } else {
+                    if (d == 1) span_f32<1, Cfg::kRows, HT>(plane, r0, nq, hh[0], hh[1], hh[2], tt[0], tt[1], tt[2], swz, prm);
+                    else if (d == 3) span_f32<3, Cfg::kRows, HT>(plane, r0, nq, hh[0], hh[1], hh[2], tt[0], tt[1], tt[2], swz, prm);
+                    else span_f32<9, Cfg::kRows, HT>(plane, r0, nq, hh[0], hh[1], hh[2], tt[0], tt[1], tt[2], swz, prm);
+                }
             }
+            tick(3 + 4 * l);
             fence_proxy_async_smem();
             __syncthreads();
+            tick(4 + 4 * l);
             if (tid == 0) issue_layer(l + 1, n);
-            mbar_wait(mma_bar, mma_par); mma_par ^= 1u;
-            tc_fence_after();
-            if (tid == 0) {
-                prefetch_w(l + 1, n);
-                if (l == 2 && n + 1 < my_tiles) load_tile(n + 1);    // the tile copy is dead: overlap the next load
-            }
-            epilogue(sEpi + l * C, true, l == 2, s, t_start);
+            if (l < 2) epilogue(std::integral_constant<int, EPI_C_MID>{}, sEpi + l * C, t_start);
+            else epilogue(std::integral_constant<int, EPI_C_FINAL>{}, sEpi + l * C, t_start);
+            if (tid == 0) { mbar_wait(&mma_bar[NB - 1], mma_par); prefetch_w(l + 1, has_next); }
+            mma_par ^= 1u;
+            if (l == 2) fence_proxy_async_smem();          // the tile copy is the source of the TMA stores below
             tc_fence_before();
             __syncthreads();
+            tick(5 + 4 * l);
         }
+
+        // ---------------------------------------------------------------- stream the tile out, refill behind it
+        if (tid == 0) {
+            const int t_out = t_start + kHalo;
+#pragma unroll
+            for (int b = 0; b < NB; ++b) {
+#pragma unroll
+                for (int kc = 0; kc < CH; ++kc) {
+                    const uint8_t* src = sX + kc * Cfg::kPlane + b * 16384;
+                    if (b == 0) tma_store_3d(&tmOe, src + kHalo * 128, kc * 64, t_out, s);
+                    else if (b == NB - 1) tma_store_3d(&tmOe, src, kc * 64, t_start + b * 128, s);
+                    else tma_store_3d(&tmOm, src, kc * 64, t_start + b * 128, s);
+                }
+                bulk_commit_group();
+            }
+            if (has_next) {
+                int s2, t2;
+                tile_coords(next_tile, s2, t2);
+                mbar_expect_tx(ld_bar, Cfg::kXBytes);
+                // block b may be refilled once the store of block b has read it (groups complete in order)
+                if (NB > 7) { bulk_wait_group_read<7>(); load_block(s2, t2, NB - 8); }
+                if (NB > 6) { bulk_wait_group_read<6>(); load_block(s2, t2, NB - 7); }
+                if (NB > 5) { bulk_wait_group_read<5>(); load_block(s2, t2, NB - 6); }
+                if (NB > 4) { bulk_wait_group_read<4>(); load_block(s2, t2, NB - 5); }
+                if (NB > 3) { bulk_wait_group_read<3>(); load_block(s2, t2, NB - 4); }
+                if (NB > 2) { bulk_wait_group_read<2>(); load_block(s2, t2, NB - 3); }
+                bulk_wait_group_read<1>(); load_block(s2, t2, NB - 2);
+                bulk_wait_group_read<0>(); load_block(s2, t2, NB - 1);
+            }
+        }
+        tick(14);
+        tile = next_tile;
+    }
+    if (tid == 0) bulk_wait_group<0>();
+    if (a.prof != nullptr && tid == 0) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        a.prof[20 + 2 * blockIdx.x] = static_cast<unsigned long long>(clock64() - t_kernel0);
+        a.prof[21 + 2 * blockIdx.x] = smid;
     }
     tc_fence_before();
     __syncthreads();
@@ -425,33 +544,51 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
 
 namespace {
 
-template <int C, int NB, typename HT>
-cudaError_t launch_chain_t(const ChainArgs& a, const CUtensorMap& tmY, const CUtensorMap* tmW, int sm_count,
-                           cudaStream_t st) {
+template <int C, int NB, int NW, typename HT>
+cudaError_t launch_chain_t(const ChainArgs& a, const CUtensorMap* tm, int sm_count, cudaStream_t st) {
     using Cfg = ChainCfg<C, NB>;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(k_chain<C, NB, HT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
+        cudaError_t e = cudaFuncSetAttribute(k_chain<C, NB, NW, HT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(k_chain<C, NB, NW, HT>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                 cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
     const int tiles = a.S * ((a.T + Cfg::kROut - 1) / Cfg::kROut);
     if (tiles == 0) return cudaSuccess;
-    const int grid = tiles < sm_count ? tiles : sm_count;
-    k_chain<C, NB, HT><<<grid, kThreads, Cfg::kSmem, st>>>(tmY, tmW[0], tmW[1], tmW[2], tmW[3], a, tiles);
+    const int slots = sm_count * (NW == 8 ? 2 : 1);
+    const int grid = tiles < slots ? tiles : slots;
+    if (a.prof != nullptr) {
+        int occ = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_chain<C, NB, NW, HT>, NW * 32, Cfg::kSmem);
+        cudaFuncAttributes fa;
+        cudaFuncGetAttributes(&fa, k_chain<C, NB, NW, HT>);
+        int occ_nosmem = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_nosmem, k_chain<C, NB, NW, HT>, NW * 32, 0);
+        fprintf(stderr, "k_chain<%d,%d,%d>: grid %d, smem %d (+%zu static), regs %d, occupancy %d CTA/SM (%d without smem)\n", C, NB, NW,
+                grid, Cfg::kSmem, fa.sharedSizeBytes, fa.numRegs, occ, occ_nosmem);
+    }
+    k_chain<C, NB, NW, HT><<<grid, NW * 32, Cfg::kSmem, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], tm[6], a, tiles);
     return cudaGetLastError();
 }
+
+// launch configurations: C = 64: 512-row tiles, 8 warps, two CTAs per SM (one CTA's barrier / MMA / TMA waits are
+// the other's issue slots); C = 128: 512-row tiles, 16 warps, one CTA per SM (shared memory bound)
+constexpr int kNB64 = 4, kNW64 = 8, kNB128 = 4, kNW128 = 16;
 
 }  // namespace
 
 bool chain_supported(int C) { return C == 64 || C == 128; }
-int chain_tile_rows(int C) { return C == 64 ? 1024 : 512; }
+int chain_tile_rows(int C) { return (C == 64 ? kNB64 : kNB128) * 128; }
+int chain_warps(int C) { return C == 64 ? kNW64 : kNW128; }
 
 // Spans of the in-place prologue (see the header comment): for dilation d the rows of a tile split into d classes
 // r = r0 + k d.  Class starts are multiples of 8 (so that the swizzle phase of step k is static) no larger than the
 // first row whose result is needed at that layer; negative starts skip their first few steps.
-void chain_build_spans(int C, ChainSpan (*spans)[kChainWarps][2]) {
-    const int rows = chain_tile_rows(C), ch = C / 64;
+void chain_build_spans(int C, ChainSpan (*spans)[kChainWarps][kChainSpans]) {
+    const int rows = chain_tile_rows(C), ch = C / 64, nw = chain_warps(C);
     static const int dil[3] = {1, 3, 9};
     for (int l = 0; l < 3; ++l) {
         const int d = dil[l];
@@ -467,15 +604,15 @@ void chain_build_spans(int C, ChainSpan (*spans)[kChainWarps][2]) {
         int total = 0;
         for (auto& c : cls) total += c.noct;
         for (int w = 0; w < kChainWarps; ++w) {
-            const int lo = static_cast<int>(static_cast<long long>(w) * total / kChainWarps);
-            const int hi = static_cast<int>(static_cast<long long>(w + 1) * total / kChainWarps);
+            for (int k = 0; k < kChainSpans; ++k) spans[l][w][k] = ChainSpan{0, 0, 0, 0};
+            if (w >= nw) continue;
+            const int lo = static_cast<int>(static_cast<long long>(w) * total / nw);
+            const int hi = static_cast<int>(static_cast<long long>(w + 1) * total / nw);
             int nsp = 0, base = 0;
-            spans[l][w][0] = ChainSpan{0, 0, 0, 0};
-            spans[l][w][1] = ChainSpan{0, 0, 0, 0};
             for (auto& c : cls) {
                 const int a0 = lo > base ? lo : base, a1 = hi < base + c.noct ? hi : base + c.noct;
                 if (a1 > a0) {
-                    if (nsp >= 2) { fprintf(stderr, "snacb: chain span table overflow\n"); abort(); }
+                    if (nsp >= kChainSpans) { fprintf(stderr, "snacb: chain span table overflow\n"); abort(); }
                     spans[l][w][nsp++] = ChainSpan{static_cast<short>(c.r0 + 8 * d * (a0 - base)),
                                                    static_cast<short>(a1 - a0), static_cast<short>(c.kc), 0};
                 }
@@ -485,14 +622,15 @@ void chain_build_spans(int C, ChainSpan (*spans)[kChainWarps][2]) {
     }
 }
 
-cudaError_t launch_chain(int half_fp16, const ChainArgs& a, const CUtensorMap& tmY, const CUtensorMap* tmW,
-                         int sm_count, cudaStream_t st) {
+// tm: [0] y load map, box (64, 128, 1); [1] out store map, box (64, 88, 1); [2] out store map, box (64, 128, 1);
+//     [3..6] noise 1x1, res d=1, d=3, d=9 weight maps, box (64, C); all 128B-swizzled
+cudaError_t launch_chain(int half_fp16, const ChainArgs& a, const CUtensorMap* tm, int sm_count, cudaStream_t st) {
     if (a.C == 64)
-        return half_fp16 ? launch_chain_t<64, 8, __half>(a, tmY, tmW, sm_count, st)
-                         : launch_chain_t<64, 8, __nv_bfloat16>(a, tmY, tmW, sm_count, st);
+        return half_fp16 ? launch_chain_t<64, kNB64, kNW64, __half>(a, tm, sm_count, st)
+                         : launch_chain_t<64, kNB64, kNW64, __nv_bfloat16>(a, tm, sm_count, st);
     if (a.C == 128)
-        return half_fp16 ? launch_chain_t<128, 4, __half>(a, tmY, tmW, sm_count, st)
-                         : launch_chain_t<128, 4, __nv_bfloat16>(a, tmY, tmW, sm_count, st);
+        return half_fp16 ? launch_chain_t<128, kNB128, kNW128, __half>(a, tm, sm_count, st)
+                         : launch_chain_t<128, kNB128, kNW128, __nv_bfloat16>(a, tm, sm_count, st);
     return cudaErrorInvalidValue;
 }
 

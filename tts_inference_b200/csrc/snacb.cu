@@ -43,7 +43,7 @@ struct BlockW {
     ResW res[3];
     float* bias_cum;                    // [3][Cout] running sums of the ResidualUnit 1x1 biases (fused chain)
     bool chain;                         // the fused NoiseBlock + ResidualUnit chain covers this block
-    ChainSpan spans[3][kChainWarps][2];
+    ChainSpan spans[3][kChainWarps][kChainSpans];
 };
 struct Tap {
     std::string name;
@@ -82,6 +82,7 @@ struct snacb_handle_s {
     size_t ws_buf_bytes = 0;
     void* ws_a0 = nullptr; size_t ws_a0_bytes = 0;
     int32_t* ws_codes = nullptr; size_t ws_codes_elems = 0;
+    int* tile_counter = nullptr;                              // dynamic tile scheduler of the chain kernel
     int32_t* st_tok = nullptr; size_t st_tok_elems = 0;       // decode_host staging
     int16_t* st_pcm = nullptr; size_t st_pcm_elems = 0;
 
@@ -381,17 +382,63 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
             ca.inv_next = bi < 3 ? h->blk[bi + 1].inv_alpha : h->tail_inv;
             ca.noise = noise ? noise[bi] : nullptr; ca.seed = seed; ca.noise_stage = bi; ca.stream_offset = stream_offset;
             memcpy(ca.spans, b.spans, sizeof ca.spans);
-            const CUtensorMap *my, *mn;
+            ca.tile_counter = h->tile_counter;
+            CK(h, cudaMemsetAsync(h->tile_counter, 0, sizeof(int), st));
+            const CUtensorMap *my, *moe, *mom, *mn;
             int rc = act_map(h, &my, oth, b.Cout, T, S, 128, 1, hk, 1);
+            if (rc) return rc;
+            rc = act_map(h, &moe, cur, b.Cout, T, S, 128 - kChainHalo, 1, hk, 1);
+            if (rc) return rc;
+            rc = act_map(h, &mom, cur, b.Cout, T, S, 128, 1, hk, 1);
             if (rc) return rc;
             rc = weight_map(h, &mn, b.nz_h[hk], b.Cout, b.Cout, b.Cout, hk);
             if (rc) return rc;
-            const CUtensorMap wm[4] = {*mn, b.res[0].tm_pw[hk], b.res[1].tm_pw[hk], b.res[2].tm_pw[hk]};
+            const CUtensorMap tm[7] = {*my, *moe, *mom, *mn, b.res[0].tm_pw[hk], b.res[1].tm_pw[hk], b.res[2].tm_pw[hk]};
             snprintf(nm, sizeof nm, "b%d.chain", bi);
             prof_begin(h, nm, st);
-            cudaError_t le = launch_chain(hk, ca, *my, wm, h->sm_count, st);
+            static const bool chain_prof = getenv("SNACB_CHAIN_PROF") && atoi(getenv("SNACB_CHAIN_PROF")) != 0;
+            if (chain_prof) {
+                CK(h, cudaMalloc(reinterpret_cast<void**>(&ca.prof), 1024 * sizeof(unsigned long long)));
+                CK(h, cudaMemsetAsync(ca.prof, 0, 1024 * sizeof(unsigned long long), st));
+            }
+            cudaError_t le = launch_chain(hk, ca, tm, h->sm_count, st);
             prof_end(h, st);
             CK(h, le);
+            if (chain_prof) {
+                unsigned long long pv[1024];
+                CK(h, cudaStreamSynchronize(st));
+                CK(h, cudaMemcpy(pv, ca.prof, sizeof pv, cudaMemcpyDeviceToHost));
+                CK(h, cudaFree(ca.prof));
+                const int rows = chain_tile_rows(b.Cout) - 2 * kChainHalo;
+                const int tiles = S * ((T + rows - 1) / rows);
+                const int slots = h->sm_count * (chain_warps(b.Cout) == 8 ? 2 : 1);
+                const int mine = (tiles + slots - 1) / slots;
+                fprintf(stderr, "chain b%d C=%d: CTA0 cycles per tile (%d tiles): nz+ld %llu noise %llu |", bi, b.Cout, mine,
+                        pv[0] / mine, pv[1] / mine);
+                for (int l = 0; l < 3; ++l)
+                    fprintf(stderr, " L%d: pre %llu pro %llu sync %llu mma+epi %llu |", l, pv[2 + 4 * l] / mine,
+                            pv[3 + 4 * l] / mine, pv[4 + 4 * l] / mine, pv[5 + 4 * l] / mine);
+                fprintf(stderr, " store/load issue %llu\n", pv[14] / mine);
+                {
+                    const int grid = tiles < slots ? tiles : slots;
+                    unsigned long long mn = ~0ull, mx = 0, sum = 0;
+                    int per_sm[256] = {0};
+                    for (int c = 0; c < grid && c < 500; ++c) {
+                        const unsigned long long v = pv[20 + 2 * c];
+                        mn = v < mn ? v : mn; mx = v > mx ? v : mx; sum += v;
+                        per_sm[pv[21 + 2 * c] & 255]++;
+                    }
+                    int sm1 = 0, sm2 = 0, sm3 = 0;
+                    for (int i = 0; i < 256; ++i) { sm1 += per_sm[i] == 1; sm2 += per_sm[i] == 2; sm3 += per_sm[i] > 2; }
+                    if (getenv("SNACB_CHAIN_PROF") && atoi(getenv("SNACB_CHAIN_PROF")) > 1) {
+                        for (int c = 0; c < grid && c < 500; ++c)
+                            fprintf(stderr, "%d:%llu:%llu ", c, pv[21 + 2 * c], pv[20 + 2 * c] / 1000);
+                        fprintf(stderr, "\n");
+                    }
+                    fprintf(stderr, "   CTA lifetimes (cycles): min %llu avg %llu max %llu; SMs with 1/2/>2 CTAs: %d/%d/%d\n", mn,
+                            sum / (grid < 500 ? grid : 500), mx, sm1, sm2, sm3);
+                }
+            }
             h->launches++;
             snprintf(nm, sizeof nm, "b%d.res2", bi);
             rc = tap_any(nm, cur, dt_h, (int64_t)S * T, b.Cout);
@@ -596,6 +643,7 @@ int snacb_create(snacb_handle* out, const snacb_weights* w, int device) {
         long mb = atol(e);
         if (mb > 0) h->group_bytes = static_cast<size_t>(mb) << 20;
     }
+    RC(dev_alloc(h, &h->tile_counter, 1));
     CKH(cudaDeviceSynchronize());
 #undef CKH
 #undef RC
@@ -752,16 +800,16 @@ int snacb_profile_report(snacb_handle h, char* buf, size_t cap) {
 }
 
 int snacb_debug_chain_spans(int C, int16_t* out, int cap) {
-    if (!out || !chain_supported(C) || cap < 3 * kChainWarps * 2 * 3) return SNACB_ERR_ARG;
-    ChainSpan sp[3][kChainWarps][2];
+    if (!out || !chain_supported(C) || cap < 3 * kChainWarps * kChainSpans * 3) return SNACB_ERR_ARG;
+    ChainSpan sp[3][kChainWarps][kChainSpans];
     chain_build_spans(C, sp);
     for (int l = 0; l < 3; ++l)
         for (int w = 0; w < kChainWarps; ++w)
-            for (int k = 0; k < 2; ++k) {
-                int16_t* o = out + ((l * kChainWarps + w) * 2 + k) * 3;
+            for (int k = 0; k < kChainSpans; ++k) {
+                int16_t* o = out + ((l * kChainWarps + w) * kChainSpans + k) * 3;
                 o[0] = sp[l][w][k].r_first; o[1] = sp[l][w][k].n_oct; o[2] = sp[l][w][k].kc;
             }
-    return chain_tile_rows(C);
+    return chain_tile_rows(C) | (chain_warps(C) << 16);
 }
 
 int snacb_debug_tap_count(snacb_handle h) { return h ? static_cast<int>(h->taps.size()) : SNACB_ERR_ARG; }
