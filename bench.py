@@ -68,6 +68,8 @@ def stage_flops(S: int) -> dict:
         out[f"b{bi}.noise"] = 2.0 * S * tout * cout * cout
         for ri in range(3):
             out[f"b{bi}.res{ri}"] = 2.0 * S * tout * (cout * cout + 7 * cout)
+        # fused NoiseBlock + 3 ResidualUnits (k_chain): same algorithmic work in one launch
+        out[f"b{bi}.chain"] = out[f"b{bi}.noise"] + 3 * out[f"b{bi}.res0"]
         cin, t = cout, tout
     out["tail"] = 2.0 * S * 8192 * 64 * 7
     out["vq_stem"] = 2.0 * S * t0 * 768 * (24 + 7)
@@ -313,9 +315,15 @@ def main():
         value = windows * WINDOW_SAMPLES / SR / (dev_ms * 1e-3)
         e2e = windows * WINDOW_SAMPLES / SR / (e2e_ms * 1e-3)
         topc = prof["classes"][prof["top"]]
-        roof = {"bound": "tensor", "kernel": {"res": "k_resunit_tc", "convt": "k_gemm_tc(convT)", "noise": "k_gemm_tc(noise)"}.get(prof["top"], prof["top"]),
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")     # dram bytes per launch from the committed ncu capture
+        if os.path.exists(tp):
+            with open(tp) as f:
+                traffic = json.load(f).get(prof["top"], {}).get(str(B))
+        roof = {"bound": "tensor", "kernel": {"res": "k_resunit2", "convt": "k_gemm_tc(convT)", "noise": "k_gemm_tc(noise)",
+                                              "chain": "k_chain (NoiseBlock + 3 ResidualUnits fused)"}.get(prof["top"], prof["top"]),
                 "achieved": topc["tflops"], "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                "frac": topc["tflops"] / peaks["bf16_tflops_sustained"], "traffic": None,
+                "frac": topc["tflops"] / peaks["bf16_tflops_sustained"], "traffic": traffic,
                 "share_of_step": topc["share"], "avg_launch_ms": topc["avg_launch_ms"], "peak_source": peaks["source"],
                 "whole_step": {"achieved": FLOP_PER_WINDOW * B * world * args.steps / (dev_ms * 1e-3) / 1e12 / world,
                                "frac": FLOP_PER_WINDOW * B * args.steps / (dev_ms * 1e-3) / 1e12 / peaks["bf16_tflops_sustained"]}}

@@ -33,6 +33,8 @@ struct GemmArgs {
     int Cout;       // channels out (per phase)
     int ntaps;      // 1 (1x1 conv) or 2 (ConvTranspose1d, k = 2*stride)
     int up;         // output rows per input row (ConvTranspose stride), 1 for 1x1
+    int t_lo, t_n;  // A rows [t_lo, t_lo + t_n) of every stream are processed (t_n = 0: all of [0, Tin)); dead-sample
+                    // trimming for the sliced output -- rows outside are neither read nor written
     int Tbox;       // rows of one stream per 128-row tile  (Tbox * Wbox == 128)
     int Wbox;       // streams per tile
     const float* bias;      // [Cout] or null
@@ -48,6 +50,7 @@ struct GemmArgs {
 
 struct ResUnitArgs {
     int S, T, C, dil;
+    int t_lo, t_n;           // output rows [t_lo, t_lo + t_n) of every stream (t_n = 0: all)
     const void* x;           // [S*T][C] residual stream (XT)
     void* out;               // [S*T][C]
     const float* alpha1; const float* inv_alpha1;   // [C]
@@ -71,6 +74,7 @@ struct ChainLayer {
 };
 struct ChainArgs {
     int S, T, C;
+    int t_lo, t_n;                // output rows [t_lo, t_lo + t_n) of every stream (t_n = 0: all)
     void* out;                    // [S*T][C] 16-bit, Snake of the next layer applied
     ChainLayer res[3];
     const float* bias_cum;        // [3][C]: b_0, b_0+b_1, b_0+b_1+b_2 (1x1 biases, added when TMEM is read)

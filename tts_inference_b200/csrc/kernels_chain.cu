@@ -215,7 +215,7 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
     const long long t_kernel0 = clock64();
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
-    const int tiles_t = (a.T + Cfg::kROut - 1) / Cfg::kROut;
+    const int tiles_t = ((a.t_n > 0 ? a.t_n : a.T) + Cfg::kROut - 1) / Cfg::kROut;
     const CUtensorMap* wmaps[4] = {&tmWn, &tmW0, &tmW1, &tmW2};
 
     // ------------------------------------------------------------------ one-time setup
@@ -269,7 +269,7 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
     };
     auto tile_coords = [&](int tile, int& s, int& t_start) {
         s = tile / tiles_t;
-        t_start = (tile % tiles_t) * Cfg::kROut - kHalo;
+        t_start = (a.t_n > 0 ? a.t_lo : 0) + (tile % tiles_t) * Cfg::kROut - kHalo;
     };
     auto load_block = [&](int s, int t_start, int b) {      // thread 0; ld_bar's expect_tx covers the whole tile
 #pragma unroll
@@ -556,7 +556,7 @@ cudaError_t launch_chain_t(const ChainArgs& a, const CUtensorMap* tm, int sm_cou
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
-    const int tiles = a.S * ((a.T + Cfg::kROut - 1) / Cfg::kROut);
+    const int tiles = a.S * (((a.t_n > 0 ? a.t_n : a.T) + Cfg::kROut - 1) / Cfg::kROut);
     if (tiles == 0) return cudaSuccess;
     const int slots = sm_count * (NW == 8 ? 2 : 1);
     const int grid = tiles < slots ? tiles : slots;

@@ -104,7 +104,8 @@ k_resunit2(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
-    const int tiles_t = (a.T + Cfg::kTileM - 1) / Cfg::kTileM;
+    const int t_lo = a.t_n > 0 ? a.t_lo : 0;
+    const int tiles_t = ((a.t_n > 0 ? a.t_n : a.T) + Cfg::kTileM - 1) / Cfg::kTileM;
 
     if (tid == 0) {
         prefetch_tmap(&tmX);
@@ -173,7 +174,7 @@ k_resunit2(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
             int g = 0;
             for (int n = 0; n < my_tiles; ++n) {
                 const int tile = blockIdx.x + n * gridDim.x;
-                const int s = tile / tiles_t, t0 = (tile % tiles_t) * Cfg::kTileM;
+                const int s = tile / tiles_t, t0 = t_lo + (tile % tiles_t) * Cfg::kTileM;
                 for (int kc = 0; kc < Cfg::kChunks; ++kc, ++g) {
                     if (!Cfg::kWRes) {
                         const int sw = g % 2;
@@ -237,7 +238,7 @@ k_resunit2(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
         constexpr int kIters = Cfg::kAccs * (C / 32);          // 32-column pieces per tile and quadrant
         for (int n = 0; n < my_tiles; ++n) {
             const int tile = blockIdx.x + n * gridDim.x;
-            const int s = tile / tiles_t, t0 = (tile % tiles_t) * Cfg::kTileM;
+            const int s = tile / tiles_t, t0 = t_lo + (tile % tiles_t) * Cfg::kTileM;
             const int as = n % Cfg::kAccStages;
             const size_t srow = static_cast<size_t>(s) * a.T;
             // residual of the first piece is fetched before waiting for the accumulator
@@ -305,7 +306,7 @@ k_resunit2(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
             const HT* x = static_cast<const HT*>(a.x);
             HT* out = static_cast<HT*>(a.out);
             const int tile = blockIdx.x + n * gridDim.x;
-            const int s = tile / tiles_t, t0 = (tile % tiles_t) * Cfg::kTileM;
+            const int s = tile / tiles_t, t0 = t_lo + (tile % tiles_t) * Cfg::kTileM;
             const int as = n % Cfg::kAccStages;
             const int q = warp & 3, rest = warp >> 2;
             const int ac = (Cfg::kAccs == 2) ? (rest & 1) : 0;
@@ -441,7 +442,7 @@ cudaError_t launch_t(const ResUnitArgs& a, const CUtensorMap& tmX, const CUtenso
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
-    const int tiles = a.S * ((a.T + Cfg::kTileM - 1) / Cfg::kTileM);
+    const int tiles = a.S * (((a.t_n > 0 ? a.t_n : a.T) + Cfg::kTileM - 1) / Cfg::kTileM);
     if (tiles == 0) return cudaSuccess;
     const int grid = tiles < sm_count ? tiles : sm_count;
     k_resunit2<C, DIL, EPI, HT><<<grid, Cfg::kThreads, Cfg::kSmem, st>>>(tmX, tmW, a, tiles);

@@ -72,7 +72,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     const uint32_t tmem_base = *tmem_slot;
 
     const int total_tiles = num_m_tiles * num_n_tiles;
-    const int tiles_t = (a.Tin + a.Tbox - 1) / a.Tbox;
+    const int t_lo = a.t_n > 0 ? a.t_lo : 0, t_n = a.t_n > 0 ? a.t_n : a.Tin;
+    const int tiles_t = (t_n + a.Tbox - 1) / a.Tbox;
     const int kchunks = a.K / kChunkK;
     const int nk = a.ntaps * kchunks;
 
@@ -82,7 +83,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             int stage = 0; uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int mt = tile / num_n_tiles, nt = tile % num_n_tiles;
-                const int s0 = (mt / tiles_t) * a.Wbox, t0 = (mt % tiles_t) * a.Tbox;
+                const int s0 = (mt / tiles_t) * a.Wbox, t0 = t_lo + (mt % tiles_t) * a.Tbox;
                 const int n0 = nt * BN;
                 const int p = n0 / a.Cout;
                 const int base_shift = (a.up > 1 && p >= a.up / 2) ? 1 : 0;
@@ -137,8 +138,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int mt = tile / num_n_tiles, nt = tile % num_n_tiles;
             const int s = (mt / tiles_t) * a.Wbox + r / a.Tbox;
-            const int m = (mt % tiles_t) * a.Tbox + r % a.Tbox;
-            const bool valid = (s < a.S) && (m < a.Tin);
+            const int m = t_lo + (mt % tiles_t) * a.Tbox + r % a.Tbox;
+            const bool valid = (s < a.S) && (m < a.Tin) && (m < t_lo + t_n);
             const int n0 = nt * BN;
             float nz = 0.f;
             if (EPI == EPI_NOISE && valid)
@@ -215,7 +216,7 @@ static cudaError_t launch_gemm_tc_t(const GemmArgs& a, const CUtensorMap& tmA, c
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
-    const int tiles_t = (a.Tin + a.Tbox - 1) / a.Tbox;
+    const int tiles_t = ((a.t_n > 0 ? a.t_n : a.Tin) + a.Tbox - 1) / a.Tbox;
     const int num_m = ((a.S + a.Wbox - 1) / a.Wbox) * tiles_t;
     const int num_n = a.N / BN;
     const int total = num_m * num_n;

@@ -90,6 +90,7 @@ struct snacb_handle_s {
     uint64_t launches = 0, streams = 0;
     bool res_v1 = false;                // SNACB_RES_V1=1: use the non-persistent ResidualUnit kernel
     bool no_chain = false;              // SNACB_NO_CHAIN=1: per-layer kernels instead of the fused chain
+    bool no_trim = false;               // SNACB_NO_TRIM=1: sliced output still decodes every sample of the window
 
     // optional per-launch CUDA-event timing (snacb_profile / snacb_profile_report)
     struct ProfRec { int name_id; cudaEvent_t a, b; };
@@ -318,6 +319,7 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
     auto gemm = [&](const char* pname, int epi, bool out_f32, GemmArgs& a, const void* A, const float* Wf,
                     void* const* Wh, int Wrows, int Wcols) -> int {
         tile_boxes(a.Tin, &a.Tbox, &a.Wbox);
+        if (a.Wbox != 1) a.t_n = 0;
         a.seed = seed;
         a.stream_offset = stream_offset;
         h->launches++;
@@ -352,6 +354,39 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
         if (rc) return rc;
     }
 
+    // ---- dead-sample trimming (sliced output): only the rows of each stage inside the receptive field of samples
+    //      [2048, 4096) are computed.  Backward range propagation; block 0 and the stem are always computed in full.
+    struct Rng { int lo, hi; };
+    Rng ct_in[4], post[4];                 // ConvTranspose input rows; rows the post-ConvTranspose layers process
+    bool trimmed[4] = {false, false, false, false};
+    {
+        const int Tfin = 2048 * F;
+        const bool want = (flags & SNACB_EXTRACT_SLICE) && Tfin > 4096 && !f32 && !xf32 && !taps && !h->no_trim;
+        int Tb[4], tt = T0;
+        for (int bi = 0; bi < 4; ++bi) { tt *= h->blk[bi].s; Tb[bi] = tt; }
+        auto clip = [](Rng r, int T) { return Rng{r.lo < 0 ? 0 : r.lo, r.hi > T ? T : r.hi}; };
+        Rng need = clip(Rng{2048 - 3, 4096 + 3}, Tb[3]);            // tail conv k7
+        for (int bi = 3; bi >= 0; --bi) {
+            const BlockW& b = h->blk[bi];
+            const int Tinb = bi ? Tb[bi - 1] : T0;
+            if (!want || bi == 0) { post[bi] = Rng{0, Tb[bi]}; ct_in[bi] = Rng{0, Tinb}; continue; }
+            trimmed[bi] = true;
+            Rng y;                                                  // ConvTranspose output rows that must be valid
+            const bool unfused = (flags & SNACB_UNFUSED) != 0 || h->no_chain;
+            if (b.chain && !unfused) {
+                const int rows = chain_tile_rows(b.Cout) - 2 * kChainHalo;
+                const int n = (need.hi - need.lo + rows - 1) / rows;
+                post[bi] = Rng{need.lo, need.lo + n * rows};
+                y = clip(Rng{post[bi].lo - kChainHalo, post[bi].hi + kChainHalo}, Tb[bi]);
+            } else {
+                post[bi] = clip(Rng{need.lo - 39, need.hi + 39}, Tb[bi]);   // 3 * (1 + 3 + 9) rows of receptive field
+                y = post[bi];
+            }
+            ct_in[bi] = clip(Rng{y.lo / b.s - 1, (y.hi - 1) / b.s + 2}, Tinb);
+            need = ct_in[bi];
+        }
+    }
+
     int Tin = T0;
     char nm[32];
     for (int bi = 0; bi < 4; ++bi) {
@@ -361,6 +396,7 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
         {
             GemmArgs a{};
             a.S = S; a.Tin = Tin; a.K = b.Cin; a.N = b.s * b.Cout; a.Cout = b.Cout; a.ntaps = 2; a.up = b.s;
+            if (trimmed[bi]) { a.t_lo = ct_in[bi].lo; a.t_n = ct_in[bi].hi - ct_in[bi].lo; }
             a.bias = b.ct_b; a.out = oth;
             snprintf(nm, sizeof nm, "b%d.convt", bi);
             int rc = gemm(nm, EPI_BIAS, false, a, cur, b.ct_f32, b.ct_h, b.s * b.Cout, 2 * b.Cin);
@@ -373,6 +409,7 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
         if (!f32 && !xf32 && !unfused && b.chain) {
             ChainArgs ca{};
             ca.S = S; ca.T = T; ca.C = b.Cout; ca.out = cur;
+            if (trimmed[bi]) { ca.t_lo = post[bi].lo; ca.t_n = post[bi].hi - post[bi].lo; }
             for (int ri = 0; ri < 3; ++ri) {
                 const ResW& r = b.res[ri];
                 ca.res[ri] = ChainLayer{r.alpha1, r.inv1, r.dw_w, r.dw_b, r.alpha2, r.inv2};
@@ -450,6 +487,7 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
         {
             GemmArgs a{};
             a.S = S; a.Tin = T; a.K = b.Cout; a.N = b.Cout; a.Cout = b.Cout; a.ntaps = 1; a.up = 1;
+            if (trimmed[bi]) { a.t_lo = post[bi].lo; a.t_n = post[bi].hi - post[bi].lo; }
             a.noise = noise ? noise[bi] : nullptr; a.noise_stage = bi;
             a.resid = oth; a.out = cur;
             snprintf(nm, sizeof nm, "b%d.noise", bi);
@@ -467,6 +505,7 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
             const float* ian = last ? (bi < 3 ? h->blk[bi + 1].inv_alpha : h->tail_inv) : nullptr;
             ResUnitArgs ra{};
             ra.S = S; ra.T = T; ra.C = b.Cout; ra.dil = dils[ri];
+            if (trimmed[bi]) { ra.t_lo = post[bi].lo; ra.t_n = post[bi].hi - post[bi].lo; }
             ra.x = cur; ra.out = oth;
             ra.alpha1 = r.alpha1; ra.inv_alpha1 = r.inv1; ra.dw_w = r.dw_w; ra.dw_b = r.dw_b;
             ra.alpha2 = r.alpha2; ra.inv_alpha2 = r.inv2; ra.pw_b = r.pw_b;
@@ -639,6 +678,7 @@ int snacb_create(snacb_handle* out, const snacb_weights* w, int device) {
     }
     if (const char* e = getenv("SNACB_RES_V1")) h->res_v1 = atoi(e) != 0;
     if (const char* e = getenv("SNACB_NO_CHAIN")) h->no_chain = atoi(e) != 0;
+    if (const char* e = getenv("SNACB_NO_TRIM")) h->no_trim = atoi(e) != 0;
     if (const char* e = getenv("SNACB_GROUP_MB")) {
         long mb = atol(e);
         if (mb > 0) h->group_bytes = static_cast<size_t>(mb) << 20;
