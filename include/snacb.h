@@ -144,9 +144,9 @@ int snacb_debug_tap_count(snacb_handle h);
 int snacb_debug_tap_info(snacb_handle h, int idx, char* name, int name_cap, int64_t* rows, int64_t* cols);
 int snacb_debug_tap_copy(snacb_handle h, int idx, float* dst_host, size_t dst_elems);
 
-/* Host-side schedule of the fused NoiseBlock + ResidualUnit chain kernel (C = 64 or 128 channels): for each
- * of the 3 ResidualUnits (dilation 1, 3, 9) and each of up to 16 warps, up to 3 spans {first_row, octets, chunk};
- * a span covers rows first_row + k*dilation, k < 8*octets, of one 64-channel chunk.  out: int16[3][16][3][3].
+/* Host-side schedule of the fused NoiseBlock + ResidualUnit chain kernel (C = 64, 128 or 256 channels): for each
+ * of the 3 ResidualUnits (dilation 1, 3, 9) and each of up to 16 warps, up to 4 spans {first_row, octets, chunk};
+ * a span covers rows first_row + k*dilation, k < 8*octets, of one 64-channel chunk.  out: int16[3][16][4][3].
  * Returns (tile height in rows incl. the 40-row halo either side) | (warps per CTA << 16), or SNACB_ERR_ARG.
  * No GPU needed. */
 int snacb_debug_chain_spans(int C, int16_t* out, int cap);

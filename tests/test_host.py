@@ -115,7 +115,7 @@ def test_two_rank_sharding_gloo():
     assert all(r[4] == float(synth.make_tokens(37, 4, seed=5).astype(np.int64).sum()) for r in res)
 
 
-@pytest.mark.parametrize("C", [64, 128])
+@pytest.mark.parametrize("C", [64, 128, 256])
 def test_chain_span_schedule(C):
     """Schedule of the fused chain kernel's in-place prologue (host logic, no GPU): emulate the kernel's protocol
     on integers -- every warp first fetches the 3 rows before/after its spans, then all warps rewrite their rows
@@ -124,11 +124,11 @@ def test_chain_span_schedule(C):
     import ctypes as Ct
     from tts_inference_b200 import _lib
     lib = _lib.load()
-    buf = (Ct.c_int16 * (3 * 16 * 3 * 3))()
+    buf = (Ct.c_int16 * (3 * 16 * 4 * 3))()
     rc = lib.snacb_debug_chain_spans(C, buf, len(buf))
     rows, nw = rc & 0xFFFF, rc >> 16
     assert rows % 128 == 0 and 256 <= rows <= 1024 and nw in (8, 16)
-    sp = np.frombuffer(buf, dtype=np.int16).reshape(3, 16, 3, 3)
+    sp = np.frombuffer(buf, dtype=np.int16).reshape(3, 16, 4, 3)
     assert (sp[:, nw:, :, 1] == 0).all()
     need_lo = {1: 4, 3: 13, 9: 40}          # first row whose result is consumed downstream, per dilation
     rng = np.random.default_rng(0)
@@ -139,7 +139,7 @@ def test_chain_span_schedule(C):
                                        for j in range(7)))                 # stands in for the 7-tap op
             want = {r: f(r, x) for r in range(rows)}
             work = x.copy()
-            spans = [(w, k, *sp[l, w, k]) for w in range(16) for k in range(3) if sp[l, w, k, 1] > 0 and sp[l, w, k, 2] == kc]
+            spans = [(w, k, *sp[l, w, k]) for w in range(16) for k in range(4) if sp[l, w, k, 1] > 0 and sp[l, w, k, 2] == kc]
             pre = {}
             for (w, k, r0, noct, _) in spans:                               # phase 1: pre-reads
                 assert r0 % 8 == 0

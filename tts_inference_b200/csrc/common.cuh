@@ -63,7 +63,7 @@ struct ResUnitArgs {
 
 // Fused NoiseBlock + 3 ResidualUnits of one DecoderBlock (kernels_chain.cu).
 constexpr int kChainWarps = 16;        // at most; a launch configuration may use 8
-constexpr int kChainSpans = 3;         // spans per warp and layer, at most
+constexpr int kChainSpans = 4;         // spans per warp and layer, at most
 constexpr int kChainHalo = 40;
 struct ChainSpan { short r_first, n_oct, kc, pad; };   // a warp's run of 8-step octets along one dilation class
 struct ChainLayer {

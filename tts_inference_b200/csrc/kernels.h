@@ -49,7 +49,7 @@ cudaError_t launch_resunit2(int half_fp16, const ResUnitArgs& a, const CUtensorM
                             int sm_count, cudaStream_t st);
 
 // ---- kernels_chain.cu  (NoiseBlock + 3 ResidualUnits fused, residual stream in TMEM)
-bool chain_supported(int C);
+bool chain_supported(int C, int half_fp16);
 int chain_tile_rows(int C);           // rows of a tile incl. the halo (y tensor-map box = (64, 128, 1), 128B swizzle)
 int chain_warps(int C);               // warps per CTA of the launch configuration used for C channels
 void chain_build_spans(int C, ChainSpan (*spans)[kChainWarps][kChainSpans]);

@@ -51,7 +51,7 @@ __device__ __forceinline__ uint32_t as_u32(__half2 v) { return *reinterpret_cast
 
 constexpr int kHalo = kChainHalo;            // 40 >= 39, multiple of 8
 
-template <int C, int NB>
+template <int C, int NB, bool HALF = true>
 struct ChainCfg {
     static constexpr int kCH = C / 64;                      // 64-channel K chunks
     static constexpr int kRows = NB * 128;                  // tile rows incl. halo
@@ -59,9 +59,12 @@ struct ChainCfg {
     static constexpr int kPlane = NB * 16384;               // one chunk plane of the tile [NB][128 rows][128 B]
     static constexpr int kXBytes = kCH * kPlane;
     static constexpr bool kWRes = (C == 64);                // all four 1x1 weights resident
+    static constexpr bool kWChunked = (C == 256);           // weights streamed one 64-channel K chunk at a time
     static constexpr int kWLayer = C * C * 2;               // one layer's weights [kCH][C rows][128 B]
-    static constexpr int kWBytes = kWRes ? 4 * kWLayer : 2 * kWLayer;
-    static constexpr int kPrmBytes = 3 * (C / 2) * 96;      // per layer and channel pair: 24 words
+    static constexpr int kWChunk = C * 128;                 // one K chunk of them
+    static constexpr int kWBytes = kWRes ? 4 * kWLayer : (kWChunked ? 2 * kWChunk : 2 * kWLayer);
+    static constexpr int kPrmWords = HALF ? 16 : 24;        // per layer and channel pair
+    static constexpr int kPrmBytes = 3 * (C / 2) * kPrmWords * 4;
     static constexpr int kEpiBytes = 5 * C * 4;             // bias_cum[3][C], alpha_next[C], inv_next[C]
     static constexpr int kNzBytes = kRows * 4;              // noise value of every tile row
     static constexpr int kOffX = 0;
@@ -194,10 +197,10 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
         const __grid_constant__ CUtensorMap tmOm, const __grid_constant__ CUtensorMap tmWn,
         const __grid_constant__ CUtensorMap tmW0, const __grid_constant__ CUtensorMap tmW1,
         const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ ChainArgs a, const int num_tiles) {
-    using Cfg = ChainCfg<C, NB>;
+    constexpr bool kHalfMath = std::is_same<HT, __half>::value;
+    using Cfg = ChainCfg<C, NB, kHalfMath>;
     constexpr int CH = Cfg::kCH;
     constexpr int kThreads = NW * 32;
-    constexpr bool kHalfMath = std::is_same<HT, __half>::value;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* sX = smem + Cfg::kOffX;
@@ -209,7 +212,8 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
     uint64_t* ld_bar = bars;          // tile landed (TMA)
     uint64_t* w_bar = bars + 1;       // [2] weight buffers landed
     uint64_t* mma_bar = bars + 3;     // [NB] the layer's MMAs of one 128-row block complete
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 + NB);
+    uint64_t* wfree_bar = bars + 3 + NB;   // [2] chunked weights: the MMAs reading a buffer have retired
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5 + NB);
     volatile int* s_next = reinterpret_cast<volatile int*>(tmem_slot + 2);   // [2] next tile of this CTA, by tile parity
 
     const long long t_kernel0 = clock64();
@@ -224,13 +228,14 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
         prefetch_tmap(&tmWn); prefetch_tmap(&tmW0); prefetch_tmap(&tmW1); prefetch_tmap(&tmW2);
         mbar_init(ld_bar, 1); mbar_init(&w_bar[0], 1); mbar_init(&w_bar[1], 1);
         for (int b = 0; b < NB; ++b) mbar_init(&mma_bar[b], 1);
+        mbar_init(&wfree_bar[0], 1); mbar_init(&wfree_bar[1], 1);
         fence_barrier_init();
     }
     if (warp == 1) { tmem_alloc(tmem_slot, Cfg::kTmemCols); tmem_relinquish(); }
     for (int i = tid; i < 3 * (C / 2); i += kThreads) {            // per-layer prologue parameters of one channel pair
         const int l = i / (C / 2), ch = 2 * (i % (C / 2));
         const ChainLayer& L = a.res[l];
-        uint32_t* d = sPrm + i * 24;
+        uint32_t* d = sPrm + i * Cfg::kPrmWords;
         if (kHalfMath) {
             // words: alpha1 (2 x f32), alpha2 (2 x f32), then half2: inv1, inv2, dw bias, dw taps 0..6
             d[0] = __float_as_uint(L.alpha1[ch]); d[1] = __float_as_uint(L.alpha1[ch + 1]);
@@ -267,6 +272,12 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
 #pragma unroll
         for (int kc = 0; kc < CH; ++kc) tma_load_2d(dst + kc * (C * 128), wmaps[l], kc * 64, 0, bar);
     };
+    // chunked weights (C = 256): chunk G of the CTA's running sequence = layer (G / CH) % 4, K chunk G % CH, buffer G & 1
+    auto load_wc = [&](int G) {               // thread 0
+        const int buf = G & 1;
+        mbar_expect_tx(&w_bar[buf], Cfg::kWChunk);
+        tma_load_2d(sW + buf * Cfg::kWChunk, wmaps[(G / CH) & 3], (G % CH) * 64, 0, &w_bar[buf]);
+    };
     auto tile_coords = [&](int tile, int& s, int& t_start) {
         s = tile / tiles_t;
         t_start = (a.t_n > 0 ? a.t_lo : 0) + (tile % tiles_t) * Cfg::kROut - kHalo;
@@ -281,6 +292,9 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
         if (Cfg::kWRes) {
             mbar_expect_tx(&w_bar[0], 4 * Cfg::kWLayer);
             for (int l = 0; l < 4; ++l) load_w(l, 0);
+        } else if (Cfg::kWChunked) {
+            load_wc(0);
+            load_wc(1);
         } else {
             load_w(0, 0);
             load_w(1, 1);
@@ -301,7 +315,36 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
     const uint32_t sx_addr = smem_u32(sX);
 
     // issue one layer's 1x1 conv for the whole tile (thread 0): TMEM[blk] (+)= A[blk] * W^T, one commit per block
-    auto issue_layer = [&](int l, int n) {
+    auto issue_layer = [&](int l, int n, bool has_next) {
+        if (Cfg::kWChunked) {
+            // K chunk by K chunk through two weight buffers; a buffer is refilled (two chunks ahead) as soon as the
+            // MMAs reading it have retired.  All blocks complete with the last chunk.
+            const int gbase = (n * 4 + l) * CH;
+#pragma unroll
+            for (int kc = 0; kc < CH; ++kc) {
+                const int G = gbase + kc, buf = G & 1;
+                mbar_wait(&w_bar[buf], (G >> 1) & 1);
+                tc_fence_after();
+                const uint32_t w_addr = smem_u32(sW + buf * Cfg::kWChunk);
+#pragma unroll
+                for (int b = 0; b < NB; ++b)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        mma_f16_ss(tmem_base + b * C, umma_desc_sw128(sx_addr + kc * Cfg::kPlane + b * 16384 + k * 32),
+                                   umma_desc_sw128(w_addr + k * 32), idescW, (l > 0 || kc > 0 || k > 0) ? 1u : 0u);
+                mma_commit(&wfree_bar[buf]);
+                if (kc & 1) {
+                    const bool more = (kc + 1 < CH) || (l < 3) || has_next;
+                    if (more) {
+                        mbar_wait(&wfree_bar[0], ((G - 1) >> 1) & 1); load_wc(G + 1);
+                        mbar_wait(&wfree_bar[1], (G >> 1) & 1); load_wc(G + 2);
+                    }
+                }
+            }
+#pragma unroll
+            for (int b = 0; b < NB; ++b) mma_commit(&mma_bar[b]);
+            return;
+        }
         const int buf = l & 1;
         if (Cfg::kWRes) { if (n == 0 && l == 0) mbar_wait(&w_bar[0], 0); }
         else mbar_wait(&w_bar[buf], (2 * n + (l >> 1)) & 1);
@@ -321,7 +364,7 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
     };
     // after ALL of layer l's MMAs completed: its weight buffer is free -> prefetch the layer two ahead (thread 0)
     auto prefetch_w = [&](int l, bool has_next) {
-        if (Cfg::kWRes) return;
+        if (Cfg::kWRes || Cfg::kWChunked) return;
         const int l2 = (l + 2) & 3;
         if (l + 2 < 4 || has_next) load_w(l2, l & 1);
     };
@@ -425,7 +468,7 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
         const bool has_next = next_tile < num_tiles;
         tick(0);
         // ---------------------------------------------------------------- NoiseBlock: TMEM = Wn y, then x1 = y + n TMEM
-        if (tid == 0) issue_layer(0, n);
+        if (tid == 0) issue_layer(0, n, has_next);
         epilogue(std::integral_constant<int, EPI_C_NOISE>{}, nullptr, t_start);
         if (tid == 0) { mbar_wait(&mma_bar[NB - 1], mma_par); prefetch_w(0, has_next); }
         mma_par ^= 1u;
@@ -461,17 +504,18 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
             tick(2 + 4 * l);
 #pragma unroll 1
             for (int sp = 0; sp < kChainSpans; ++sp) {
-                const int nq = sp == 0 ? n_oct[0] : (sp == 1 ? n_oct[1] : n_oct[2]);
+                static_assert(kChainSpans == 4, "span select");
+                const int nq = sp == 0 ? n_oct[0] : (sp == 1 ? n_oct[1] : (sp == 2 ? n_oct[2] : n_oct[3]));
                 if (nq == 0) continue;
-                const int kc = sp == 0 ? kcs[0] : (sp == 1 ? kcs[1] : kcs[2]);
-                const int r0 = sp == 0 ? r_first[0] : (sp == 1 ? r_first[1] : r_first[2]);
+                const int kc = sp == 0 ? kcs[0] : (sp == 1 ? kcs[1] : (sp == 2 ? kcs[2] : kcs[3]));
+                const int r0 = sp == 0 ? r_first[0] : (sp == 1 ? r_first[1] : (sp == 2 ? r_first[2] : r_first[3]));
                 uint32_t hh[3], tt[3];
 #pragma unroll
                 for (int j = 0; j < 3; ++j) {
-                    hh[j] = sp == 0 ? hd[0][j] : (sp == 1 ? hd[1][j] : hd[2][j]);
-                    tt[j] = sp == 0 ? tl[0][j] : (sp == 1 ? tl[1][j] : tl[2][j]);
+                    hh[j] = sp == 0 ? hd[0][j] : (sp == 1 ? hd[1][j] : (sp == 2 ? hd[2][j] : hd[3][j]));
+                    tt[j] = sp == 0 ? tl[0][j] : (sp == 1 ? tl[1][j] : (sp == 2 ? tl[2][j] : tl[3][j]));
                 }
-                const uint32_t* prm = sPrm + ((l * (C / 2)) + kc * 32 + lane) * 24;
+                const uint32_t* prm = sPrm + ((l * (C / 2)) + kc * 32 + lane) * Cfg::kPrmWords;
                 uint8_t* plane = sX + kc * Cfg::kPlane;
                 if (kHalfMath) {
                     if (d == 1) span_half<1, Cfg::kRows>(plane, r0, nq, hh[0], hh[1], hh[2], tt[0], tt[1], tt[2], swz, prm);
@@ -487,7 +531,7 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
             fence_proxy_async_smem();
             __syncthreads();
             tick(4 + 4 * l);
-            if (tid == 0) issue_layer(l + 1, n);
+            if (tid == 0) issue_layer(l + 1, n, has_next);
             if (l < 2) epilogue(std::integral_constant<int, EPI_C_MID>{}, sEpi + l * C, t_start);
             else epilogue(std::integral_constant<int, EPI_C_FINAL>{}, sEpi + l * C, t_start);
             if (tid == 0) { mbar_wait(&mma_bar[NB - 1], mma_par); prefetch_w(l + 1, has_next); }
@@ -546,7 +590,7 @@ namespace {
 
 template <int C, int NB, int NW, typename HT>
 cudaError_t launch_chain_t(const ChainArgs& a, const CUtensorMap* tm, int sm_count, cudaStream_t st) {
-    using Cfg = ChainCfg<C, NB>;
+    using Cfg = ChainCfg<C, NB, std::is_same<HT, __half>::value>;
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(k_chain<C, NB, NW, HT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
@@ -576,13 +620,15 @@ cudaError_t launch_chain_t(const ChainArgs& a, const CUtensorMap* tm, int sm_cou
 
 // launch configurations: C = 64: 512-row tiles, 8 warps, two CTAs per SM (one CTA's barrier / MMA / TMA waits are
 // the other's issue slots); C = 128: 512-row tiles, 16 warps, one CTA per SM (shared memory bound)
-constexpr int kNB64 = 4, kNW64 = 8, kNB128 = 4, kNW128 = 16;
+// C = 256 (fp16 only: the fp32-math parameters of the bf16 variant do not fit): 256-row tiles (TMEM: 2 x 256 columns),
+// 16 warps, weights streamed per K chunk
+constexpr int kNB64 = 4, kNW64 = 8, kNB128 = 4, kNW128 = 16, kNB256 = 2, kNW256 = 16;
 
 }  // namespace
 
-bool chain_supported(int C) { return C == 64 || C == 128; }
-int chain_tile_rows(int C) { return (C == 64 ? kNB64 : kNB128) * 128; }
-int chain_warps(int C) { return C == 64 ? kNW64 : kNW128; }
+bool chain_supported(int C, int half_fp16) { return C == 64 || C == 128 || (C == 256 && half_fp16); }
+int chain_tile_rows(int C) { return (C == 64 ? kNB64 : (C == 128 ? kNB128 : kNB256)) * 128; }
+int chain_warps(int C) { return C == 64 ? kNW64 : (C == 128 ? kNW128 : kNW256); }
 
 // Spans of the in-place prologue (see the header comment): for dilation d the rows of a tile split into d classes
 // r = r0 + k d.  Class starts are multiples of 8 (so that the swizzle phase of step k is static) no larger than the
@@ -631,6 +677,7 @@ cudaError_t launch_chain(int half_fp16, const ChainArgs& a, const CUtensorMap* t
     if (a.C == 128)
         return half_fp16 ? launch_chain_t<128, kNB128, kNW128, __half>(a, tm, sm_count, st)
                          : launch_chain_t<128, kNB128, kNW128, __nv_bfloat16>(a, tm, sm_count, st);
+    if (a.C == 256 && half_fp16) return launch_chain_t<256, kNB256, kNW256, __half>(a, tm, sm_count, st);
     return cudaErrorInvalidValue;
 }
 

@@ -284,52 +284,63 @@ void launch_respre_f32(const ResUnitArgs& a, float* P, cudaStream_t st) {
 // [2048:4096] (vllm_inference/modal_audio_stream.py:94-95,195-198), int16 quantise (:201).
 // One warp = 32 consecutive samples; lane = channel pair; 7-row sliding window in registers.
 // ----------------------------------------------------------------------------------------------
+// One warp = 32 consecutive output samples of one stream; lane = channel pair while the 7-tap window slides down
+// the rows (each input row is loaded once, 128 B per warp), every lane keeping its 2-channel partial sum of all 32
+// samples in registers; one recursive-halving exchange (31 shuffles) then leaves sample `lane` summed in lane `lane`.
 template <typename InT>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 k_tail(const InT* __restrict__ a, int T, int t_begin, int n_out, const float* __restrict__ w /*[7][64]*/, float bias,
        int16_t* __restrict__ pcm, float* __restrict__ wave) {
     const int s = blockIdx.y;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int base = t_begin + blockIdx.x * 128 + warp * 32;
+    const int base = t_begin + blockIdx.x * 256 + warp * 32;
     if (base >= t_begin + n_out) return;
-    float w0[7], w1[7];
+    float2 wj[7];
 #pragma unroll
-    for (int j = 0; j < 7; ++j) { w0[j] = w[j * 64 + 2 * lane]; w1[j] = w[j * 64 + 2 * lane + 1]; }
+    for (int j = 0; j < 7; ++j) wj[j] = make_float2(w[j * 64 + 2 * lane], w[j * 64 + 2 * lane + 1]);
     const InT* src = a + static_cast<size_t>(s) * T * 64 + 2 * lane;
     auto load_row = [&](int t) -> float2 {
         if (t < 0 || t >= T) return make_float2(0.f, 0.f);
         const InT* p = src + static_cast<size_t>(t) * 64;
         return make_float2(to_f32(p[0]), to_f32(p[1]));
     };
-    float2 win[7];
+    float2 rows[38];                       // the 32 + 6 input rows of this warp's samples, issued back to back
 #pragma unroll
-    for (int j = 0; j < 6; ++j) win[j + 1] = load_row(base - 3 + j);
-    float mine = 0.f;
+    for (int i = 0; i < 38; ++i) rows[i] = load_row(base - 3 + i);
+    float v[32];
+#pragma unroll
     for (int i = 0; i < 32; ++i) {
+        float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int j = 0; j < 6; ++j) win[j] = win[j + 1];
-        win[6] = load_row(base + i + 3);
-        float part = 0.f;
+        for (int j = 0; j < 7; ++j) acc = ffma2(wj[j], rows[i + j], acc);
+        v[i] = acc.x + acc.y;
+    }
+    // transpose-reduce: after the step with offset o, a lane keeps the half of its values whose sample index has
+    // bit o equal to the lane's bit o, summed with the partner's copy
 #pragma unroll
-        for (int j = 0; j < 7; ++j) part = fmaf(w0[j], win[j].x, fmaf(w1[j], win[j].y, part));
+    for (int o = 16; o > 0; o >>= 1) {
+        const bool up = (lane & o) != 0;
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
-        if (lane == i) mine = part;
+        for (int i = 0; i < o; ++i) {
+            const float send = up ? v[i] : v[i + o];
+            const float keep = up ? v[i + o] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
     }
     const int t = base + lane;
     if (t < t_begin + n_out && t < T) {
-        const float v = tanhf(mine + bias);
+        const float r = tanhf(v[0] + bias);
         const size_t o = static_cast<size_t>(s) * n_out + (t - t_begin);
-        pcm[o] = pcm16(v);
-        if (wave) wave[o] = v;
+        pcm[o] = pcm16(r);
+        if (wave) wave[o] = r;
     }
 }
 
 template <typename InT>
 void launch_tail(const InT* a, int S, int T, int t_begin, int n_out, const float* w, float bias, int16_t* pcm,
                  float* wave, cudaStream_t st) {
-    dim3 grid((n_out + 127) / 128, S);
-    k_tail<InT><<<grid, 128, 0, st>>>(a, T, t_begin, n_out, w, bias, pcm, wave);
+    dim3 grid((n_out + 255) / 256, S);
+    k_tail<InT><<<grid, 256, 0, st>>>(a, T, t_begin, n_out, w, bias, pcm, wave);
 }
 template void launch_tail<float>(const float*, int, int, int, int, const float*, float, int16_t*, float*, cudaStream_t);
 template void launch_tail<__nv_bfloat16>(const __nv_bfloat16*, int, int, int, int, const float*, float, int16_t*,

@@ -42,7 +42,7 @@ struct BlockW {
     void* nz_h[2];
     ResW res[3];
     float* bias_cum;                    // [3][Cout] running sums of the ResidualUnit 1x1 biases (fused chain)
-    bool chain;                         // the fused NoiseBlock + ResidualUnit chain covers this block
+    bool chain[2];                      // the fused NoiseBlock + ResidualUnit chain covers this block ([0] bf16, [1] fp16)
     ChainSpan spans[3][kChainWarps][kChainSpans];
 };
 struct Tap {
@@ -373,7 +373,7 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
             trimmed[bi] = true;
             Rng y;                                                  // ConvTranspose output rows that must be valid
             const bool unfused = (flags & SNACB_UNFUSED) != 0 || h->no_chain;
-            if (b.chain && !unfused) {
+            if (b.chain[hk] && !unfused) {
                 const int rows = chain_tile_rows(b.Cout) - 2 * kChainHalo;
                 const int n = (need.hi - need.lo + rows - 1) / rows;
                 post[bi] = Rng{need.lo, need.lo + n * rows};
@@ -406,7 +406,7 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
         }
         // ---- fused NoiseBlock + 3 ResidualUnits + next Snake: oth -> cur, one kernel
         const bool unfused = (flags & SNACB_UNFUSED) != 0 || h->no_chain;
-        if (!f32 && !xf32 && !unfused && b.chain) {
+        if (!f32 && !xf32 && !unfused && b.chain[hk]) {
             ChainArgs ca{};
             ca.S = S; ca.T = T; ca.C = b.Cout; ca.out = cur;
             if (trimmed[bi]) { ca.t_lo = post[bi].lo; ca.t_n = post[bi].hi - post[bi].lo; }
@@ -662,8 +662,9 @@ int snacb_create(snacb_handle* out, const snacb_weights* w, int device) {
                 for (int ri = 0; ri < 3; ++ri) { acc += s.res[ri].pw_b[c]; bc[static_cast<size_t>(ri) * b.Cout + c] = acc; }
             }
             RC(upload_f32(h, &b.bias_cum, bc));
-            b.chain = chain_supported(b.Cout);
-            if (b.chain) chain_build_spans(b.Cout, b.spans);
+            b.chain[0] = chain_supported(b.Cout, 0);
+            b.chain[1] = chain_supported(b.Cout, 1);
+            if (b.chain[1]) chain_build_spans(b.Cout, b.spans);
         }
         cin = b.Cout;
     }
@@ -840,7 +841,7 @@ int snacb_profile_report(snacb_handle h, char* buf, size_t cap) {
 }
 
 int snacb_debug_chain_spans(int C, int16_t* out, int cap) {
-    if (!out || !chain_supported(C) || cap < 3 * kChainWarps * kChainSpans * 3) return SNACB_ERR_ARG;
+    if (!out || !chain_supported(C, 1) || cap < 3 * kChainWarps * kChainSpans * 3) return SNACB_ERR_ARG;
     ChainSpan sp[3][kChainWarps][kChainSpans];
     chain_build_spans(C, sp);
     for (int l = 0; l < 3; ++l)
