@@ -270,13 +270,13 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
         uint64_t* bar = &w_bar[Cfg::kWRes ? 0 : buf];
         if (!Cfg::kWRes) mbar_expect_tx(bar, Cfg::kWLayer);
 #pragma unroll
-        for (int kc = 0; kc < CH; ++kc) tma_load_2d(dst + kc * (C * 128), wmaps[l], kc * 64, 0, bar);
+        for (int kc = 0; kc < CH; ++kc) tma_load_2d_hint(dst + kc * (C * 128), wmaps[l], kc * 64, 0, bar, kL2EvictLast);
     };
     // chunked weights (C = 256): chunk G of the CTA's running sequence = layer (G / CH) % 4, K chunk G % CH, buffer G & 1
     auto load_wc = [&](int G) {               // thread 0
         const int buf = G & 1;
         mbar_expect_tx(&w_bar[buf], Cfg::kWChunk);
-        tma_load_2d(sW + buf * Cfg::kWChunk, wmaps[(G / CH) & 3], (G % CH) * 64, 0, &w_bar[buf]);
+        tma_load_2d_hint(sW + buf * Cfg::kWChunk, wmaps[(G / CH) & 3], (G % CH) * 64, 0, &w_bar[buf], kL2EvictLast);
     };
     auto tile_coords = [&](int tile, int& s, int& t_start) {
         s = tile / tiles_t;
@@ -285,7 +285,7 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
     auto load_block = [&](int s, int t_start, int b) {      // thread 0; ld_bar's expect_tx covers the whole tile
 #pragma unroll
         for (int kc = 0; kc < CH; ++kc)
-            tma_load_3d(sX + kc * Cfg::kPlane + b * 16384, &tmY, kc * 64, t_start + b * 128, s, ld_bar);
+            tma_load_3d_hint(sX + kc * Cfg::kPlane + b * 16384, &tmY, kc * 64, t_start + b * 128, s, ld_bar, kL2EvictFirst);
     };
     int tile = blockIdx.x;
     if (tid == 0 && tile < num_tiles) {

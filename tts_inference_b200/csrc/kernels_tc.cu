@@ -93,7 +93,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     uint8_t* sa = smem + stage * Cfg::kStageBytes;
                     mbar_expect_tx(&full[stage], Cfg::kStageBytes);
                     tma_load_3d(sa, &tmA, kc * kChunkK, t0 + base_shift - tap, s0, &full[stage]);
-                    tma_load_2d(sa + kABytes, &tmW, tap * a.K + kc * kChunkK, n0, &full[stage]);
+                    tma_load_2d_hint(sa + kABytes, &tmW, tap * a.K + kc * kChunkK, n0, &full[stage], kL2EvictLast);
                     if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
                 }
             }
