@@ -69,10 +69,12 @@ def test_fp32_waveform_parity(decoder, oracle_model, B, F_):
                                return_wave=True)
     w = wave.cpu().numpy()
     assert w.shape == ref.shape == (B, 2048 * F_)
-    assert np.abs(w - ref).max() <= FP32_TOL
+    err = np.abs(w - ref)
+    assert np.isfinite(w).all(), f"{(~np.isfinite(w)).sum()} non-finite samples, first at {np.argwhere(~np.isfinite(w))[:3]}"
+    assert err.max() <= FP32_TOL, f"max-abs {err.max():.3e} at {np.unravel_index(err.argmax(), err.shape)}, {(err > FP32_TOL).sum()} samples over"
     d = np.abs(pcm.cpu().numpy().astype(np.int32) - pcm_of(ref).astype(np.int32))
     assert d.max() <= 1, f"int16 differs by {d.max()} LSB"
-    assert np.array_equal(pcm.cpu().numpy(), pcm_of(w))           # quantiser itself is exact (truncation)
+    assert np.array_equal(pcm.cpu().numpy(), pcm_of(w)), "quantiser"   # quantiser itself is exact (truncation)
 
 
 def test_fp32_stage_taps(decoder, oracle_model):

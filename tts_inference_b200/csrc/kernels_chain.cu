@@ -63,9 +63,9 @@ struct ChainCfg {
     static constexpr int kWLayer = C * C * 2;               // one layer's weights [kCH][C rows][128 B]
     static constexpr int kWChunk = C * 128;                 // one K chunk of them
     static constexpr int kWBytes = kWRes ? 4 * kWLayer : (kWChunked ? 2 * kWChunk : 2 * kWLayer);
-    static constexpr int kPrmWords = HALF ? 16 : 24;        // per layer and channel pair
+    static constexpr int kPrmWords = HALF ? 8 : 24;         // per layer and channel pair
     static constexpr int kPrmBytes = 3 * (C / 2) * kPrmWords * 4;
-    static constexpr int kEpiBytes = 5 * C * 4;             // bias_cum[3][C], alpha_next[C], inv_next[C]
+    static constexpr int kEpiBytes = 8 * C * 4;             // epilogue vectors, see kEpi* below
     static constexpr int kNzBytes = kRows * 4;              // noise value of every tile row
     static constexpr int kOffX = 0;
     static constexpr int kOffW = kOffX + kXBytes;
@@ -85,30 +85,30 @@ struct ChainCfg {
 // One span of the in-place prologue: rows r_oct + k*D, k < 8*nq, of one 64-channel chunk (lane = channel pair).
 // h0..h2 / t0..t2: the three rows before / after the span (fetched before the barrier, other warps rewrite them).
 // ---------------------------------------------------------------------------------------------------------
+// fp16 formulation without a single alpha multiply: the tile copy holds x'' = alpha1 * x, so that
+//   snake1(x) = (x'' + sin^2 x'') / alpha1          (inv_alpha * alpha = 1)
+// the depthwise taps carry alpha2 / alpha1 and its bias alpha2, so that the conv emits a'' = alpha2 * a directly, and
+//   snake2(a) = (a'' + sin^2 a'') / alpha2          with 1 / alpha2 folded into the 1x1 weights' K columns (host).
 template <int D, int ROWS>
 __device__ __forceinline__ void span_half(uint8_t* plane, int r_oct, const int nq, const uint32_t h0, const uint32_t h1,
                                           const uint32_t h2, const uint32_t t0, const uint32_t t1, const uint32_t t2,
                                           const uint32_t (&swz)[8], const uint32_t* prm) {
     const uint4 q0 = *reinterpret_cast<const uint4*>(prm), q1 = *reinterpret_cast<const uint4*>(prm + 4);
-    const uint4 q2 = *reinterpret_cast<const uint4*>(prm + 8), q3 = *reinterpret_cast<const uint4*>(prm + 12);
-    const float2 al1 = make_float2(__uint_as_float(q0.x), __uint_as_float(q0.y));
-    const float2 al2 = make_float2(__uint_as_float(q0.z), __uint_as_float(q0.w));
-    const __half2 ia1 = as_h2(q1.x), ia2 = as_h2(q1.y), bd = as_h2(q1.z);
-    const __half2 w[7] = {as_h2(q1.w), as_h2(q2.x), as_h2(q2.y), as_h2(q2.z), as_h2(q2.w), as_h2(q3.x), as_h2(q3.y)};
-    auto snake1 = [&](uint32_t raw) -> __half2 {
-        const __half2 xh = as_h2(raw);
-        const float2 t = fmul2(al1, __half22float2(xh));
+    const __half2 bd = as_h2(q0.x);
+    const __half2 w[7] = {as_h2(q0.y), as_h2(q0.z), as_h2(q0.w), as_h2(q1.x), as_h2(q1.y), as_h2(q1.z), as_h2(q1.w)};
+    auto snake = [&](__half2 xh) -> __half2 {      // xh + sin^2(xh)
+        const float2 t = __half22float2(xh);
         const __half2 sh = __floats2half2_rn(__sinf(t.x), __sinf(t.y));
-        return __hfma2(ia1, __hmul2(sh, sh), xh);
+        return __hfma2(sh, sh, xh);
     };
     __half2 win[7];
-    win[1] = snake1(h0); win[2] = snake1(h1); win[3] = snake1(h2);
+    win[1] = snake(as_h2(h0)); win[2] = snake(as_h2(h1)); win[3] = snake(as_h2(h2));
     uint8_t* ob = plane + r_oct * 128;             // r_oct = 0 (mod 8): (row & 7) of step k is (k*D) & 7
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
         uint32_t raw = 0u;                         // class starts may lie up to 24 rows above the tile
         if (r_oct + j * D >= 0) raw = *reinterpret_cast<const uint32_t*>(ob + j * D * 128 + swz[(j * D) & 7]);
-        win[4 + j] = snake1(raw);
+        win[4 + j] = snake(as_h2(raw));
     }
 #pragma unroll 1
     for (int qo = 0; qo < nq; ++qo) {
@@ -121,13 +121,11 @@ __device__ __forceinline__ void span_half(uint8_t* plane, int r_oct, const int n
         for (int k = 0; k < 8; ++k) {
 #pragma unroll
             for (int j = 0; j < 6; ++j) win[j] = win[j + 1];
-            win[6] = snake1(raw[k]);
+            win[6] = snake(as_h2(raw[k]));
             __half2 acc = bd;
 #pragma unroll
             for (int j = 0; j < 7; ++j) acc = __hfma2(w[j], win[j], acc);
-            const float2 t = fmul2(al2, __half22float2(acc));
-            const __half2 sh = __floats2half2_rn(__sinf(t.x), __sinf(t.y));
-            const __half2 o = __hfma2(ia2, __hmul2(sh, sh), acc);
+            const __half2 o = snake(acc);
             const int r = r_oct + k * D;
             if (static_cast<unsigned>(r) < static_cast<unsigned>(ROWS))
                 *reinterpret_cast<uint32_t*>(ob + k * D * 128 + swz[(k * D) & 7]) = as_u32(o);
@@ -237,14 +235,12 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
         const ChainLayer& L = a.res[l];
         uint32_t* d = sPrm + i * Cfg::kPrmWords;
         if (kHalfMath) {
-            // words: alpha1 (2 x f32), alpha2 (2 x f32), then half2: inv1, inv2, dw bias, dw taps 0..6
-            d[0] = __float_as_uint(L.alpha1[ch]); d[1] = __float_as_uint(L.alpha1[ch + 1]);
-            d[2] = __float_as_uint(L.alpha2[ch]); d[3] = __float_as_uint(L.alpha2[ch + 1]);
-            d[4] = as_u32(__floats2half2_rn(L.inv1[ch], L.inv1[ch + 1]));
-            d[5] = as_u32(__floats2half2_rn(L.inv2[ch], L.inv2[ch + 1]));
-            d[6] = as_u32(__floats2half2_rn(L.dw_b[ch], L.dw_b[ch + 1]));
+            // half2 words: alpha2 * dw bias, then dw taps 0..6 times alpha2 / alpha1 (see span_half)
+            const float a1x = L.alpha1[ch], a1y = L.alpha1[ch + 1], a2x = L.alpha2[ch], a2y = L.alpha2[ch + 1];
+            d[0] = as_u32(__floats2half2_rn(L.dw_b[ch] * a2x, L.dw_b[ch + 1] * a2y));
 #pragma unroll
-            for (int j = 0; j < 7; ++j) d[7 + j] = as_u32(__floats2half2_rn(L.dw_w[j * C + ch], L.dw_w[j * C + ch + 1]));
+            for (int j = 0; j < 7; ++j)
+                d[1 + j] = as_u32(__floats2half2_rn(L.dw_w[j * C + ch] * (a2x / a1x), L.dw_w[j * C + ch + 1] * (a2y / a1y)));
         } else {
             d[0] = __float_as_uint(L.alpha1[ch]); d[1] = __float_as_uint(L.alpha1[ch + 1]);
             d[2] = __float_as_uint(L.inv1[ch]); d[3] = __float_as_uint(L.inv1[ch + 1]);
@@ -257,8 +253,18 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
             d[22] = __float_as_uint(L.inv2[ch]); d[23] = __float_as_uint(L.inv2[ch + 1]);
         }
     }
-    for (int c = tid; c < 3 * C; c += kThreads) sEpi[c] = a.bias_cum[c];
-    for (int c = tid; c < C; c += kThreads) { sEpi[3 * C + c] = a.alpha_next[c]; sEpi[4 * C + c] = a.inv_next[c]; }
+    // epilogue vectors: [0] scale of the NoiseBlock output, [1],[2] scale and scaled bias after unit d=1, [3],[4] after
+    // d=3, [5] bias after d=9, [6],[7] alpha / 1/alpha of the next Snake.  scale = alpha1 of the next unit's Snake in the
+    // fp16 formulation (the tile copy holds alpha1 * x), 1 otherwise.
+    for (int c = tid; c < C; c += kThreads) {
+        const float s0 = kHalfMath ? a.res[0].alpha1[c] : 1.f, s1 = kHalfMath ? a.res[1].alpha1[c] : 1.f;
+        const float s2 = kHalfMath ? a.res[2].alpha1[c] : 1.f;
+        sEpi[c] = s0;
+        sEpi[C + c] = s1; sEpi[2 * C + c] = a.bias_cum[c] * s1;
+        sEpi[3 * C + c] = s2; sEpi[4 * C + c] = a.bias_cum[C + c] * s2;
+        sEpi[5 * C + c] = a.bias_cum[2 * C + c];
+        sEpi[6 * C + c] = a.alpha_next[c]; sEpi[7 * C + c] = a.inv_next[c];
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -372,7 +378,7 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
     // epilogue of one layer; each 128-row block is drained as soon as its MMAs have committed
     //   NOISE: x1 = y + n[t] * TMEM  -> TMEM (fp32 residual stream) and the 16-bit tile copy
     //   MID:   tile copy = TMEM + cumulative bias          FINAL: tile copy = snake_next(TMEM + cumulative bias)
-    auto epilogue = [&](auto mode_tag, const float* bias, int t_start) {
+    auto epilogue = [&](auto mode_tag, const float* scale, const float* bias, int t_start) {
         constexpr int MODE = decltype(mode_tag)::value;
         const int q = warp & 3, g = warp >> 2;
         constexpr int kPieces = NB * (C / 32);
@@ -408,13 +414,21 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
                     v0 = fmaf(nz, v0, y0.x); v1 = fmaf(nz, v1, y0.y); v2 = fmaf(nz, v2, y1.x); v3 = fmaf(nz, v3, y1.y);
                     raw[j] = __float_as_uint(v0); raw[j + 1] = __float_as_uint(v1);
                     raw[j + 2] = __float_as_uint(v2); raw[j + 3] = __float_as_uint(v3);
+                    if (kHalfMath) {
+                        const float4 sc = *reinterpret_cast<const float4*>(scale + cg * 32 + j);
+                        v0 *= sc.x; v1 *= sc.y; v2 *= sc.z; v3 *= sc.w;
+                    }
+                } else if (MODE == EPI_C_MID && kHalfMath) {
+                    const float4 sc = *reinterpret_cast<const float4*>(scale + cg * 32 + j);
+                    const float4 b = *reinterpret_cast<const float4*>(bias + cg * 32 + j);
+                    v0 = fmaf(v0, sc.x, b.x); v1 = fmaf(v1, sc.y, b.y); v2 = fmaf(v2, sc.z, b.z); v3 = fmaf(v3, sc.w, b.w);
                 } else {
                     const float4 b = *reinterpret_cast<const float4*>(bias + cg * 32 + j);
                     v0 += b.x; v1 += b.y; v2 += b.z; v3 += b.w;
                 }
                 if (MODE == EPI_C_FINAL) {
-                    const float4 al = *reinterpret_cast<const float4*>(sEpi + 3 * C + cg * 32 + j);
-                    const float4 ia = *reinterpret_cast<const float4*>(sEpi + 4 * C + cg * 32 + j);
+                    const float4 al = *reinterpret_cast<const float4*>(sEpi + 6 * C + cg * 32 + j);
+                    const float4 ia = *reinterpret_cast<const float4*>(sEpi + 7 * C + cg * 32 + j);
                     v0 = snake_f<true>(v0, al.x, ia.x); v1 = snake_f<true>(v1, al.y, ia.y);
                     v2 = snake_f<true>(v2, al.z, ia.z); v3 = snake_f<true>(v3, al.w, ia.w);
                 }
@@ -469,7 +483,7 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
         tick(0);
         // ---------------------------------------------------------------- NoiseBlock: TMEM = Wn y, then x1 = y + n TMEM
         if (tid == 0) issue_layer(0, n, has_next);
-        epilogue(std::integral_constant<int, EPI_C_NOISE>{}, nullptr, t_start);
+        epilogue(std::integral_constant<int, EPI_C_NOISE>{}, sEpi, nullptr, t_start);
         if (tid == 0) { mbar_wait(&mma_bar[NB - 1], mma_par); prefetch_w(0, has_next); }
         mma_par ^= 1u;
         tc_fence_before();
@@ -532,8 +546,8 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
             __syncthreads();
             tick(4 + 4 * l);
             if (tid == 0) issue_layer(l + 1, n, has_next);
-            if (l < 2) epilogue(std::integral_constant<int, EPI_C_MID>{}, sEpi + l * C, t_start);
-            else epilogue(std::integral_constant<int, EPI_C_FINAL>{}, sEpi + l * C, t_start);
+            if (l < 2) epilogue(std::integral_constant<int, EPI_C_MID>{}, sEpi + (1 + 2 * l) * C, sEpi + (2 + 2 * l) * C, t_start);
+            else epilogue(std::integral_constant<int, EPI_C_FINAL>{}, nullptr, sEpi + 5 * C, t_start);
             if (tid == 0) { mbar_wait(&mma_bar[NB - 1], mma_par); prefetch_w(l + 1, has_next); }
             mma_par ^= 1u;
             if (l == 2) fence_proxy_async_smem();          // the tile copy is the source of the TMA stores below

@@ -32,6 +32,8 @@ struct ResW {
     float *alpha1, *inv1, *dw_w, *dw_b, *alpha2, *inv2, *pw_f32, *pw_b;
     void* pw_h[2];          // 16-bit copies: [0] bf16, [1] fp16
     CUtensorMap tm_pw[2];   // box (64, min(C,256)) for k_resunit_tc
+    void* pwc_h = nullptr;  // fp16 1x1 weights with 1/alpha2 folded into the K columns (fp16 chain kernel)
+    CUtensorMap tm_pwc;
 };
 struct BlockW {
     int Cin, Cout, s;
@@ -430,7 +432,8 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
             if (rc) return rc;
             rc = weight_map(h, &mn, b.nz_h[hk], b.Cout, b.Cout, b.Cout, hk);
             if (rc) return rc;
-            const CUtensorMap tm[7] = {*my, *moe, *mom, *mn, b.res[0].tm_pw[hk], b.res[1].tm_pw[hk], b.res[2].tm_pw[hk]};
+            const CUtensorMap tm[7] = {*my, *moe, *mom, *mn, hk ? b.res[0].tm_pwc : b.res[0].tm_pw[0],
+                                       hk ? b.res[1].tm_pwc : b.res[1].tm_pw[0], hk ? b.res[2].tm_pwc : b.res[2].tm_pw[0]};
             snprintf(nm, sizeof nm, "b%d.chain", bi);
             prof_begin(h, nm, st);
             static const bool chain_prof = getenv("SNACB_CHAIN_PROF") && atoi(getenv("SNACB_CHAIN_PROF")) != 0;
@@ -664,7 +667,23 @@ int snacb_create(snacb_handle* out, const snacb_weights* w, int device) {
             RC(upload_f32(h, &b.bias_cum, bc));
             b.chain[0] = chain_supported(b.Cout, 0);
             b.chain[1] = chain_supported(b.Cout, 1);
-            if (b.chain[1]) chain_build_spans(b.Cout, b.spans);
+            if (b.chain[1]) {
+                chain_build_spans(b.Cout, b.spans);
+                const int C = b.Cout;
+                for (int ri = 0; ri < 3; ++ri) {
+                    // snake2(a) = (a'' + sin^2 a'') / alpha2 with a'' = alpha2 a: the 1 / alpha2 goes into W's K columns
+                    std::vector<__half> wc(static_cast<size_t>(C) * C);
+                    for (int n = 0; n < C; ++n)
+                        for (int k = 0; k < C; ++k)
+                            wc[static_cast<size_t>(n) * C + k] =
+                                __float2half_rn(s.res[ri].pw_w[static_cast<size_t>(n) * C + k] / s.res[ri].alpha2[k]);
+                    __half* d;
+                    RC(dev_alloc(h, &d, wc.size()));
+                    CKH(cudaMemcpy(d, wc.data(), wc.size() * 2, cudaMemcpyHostToDevice));
+                    b.res[ri].pwc_h = d;
+                    RC(make_tmap_2d(h, &b.res[ri].tm_pwc, d, C, C, C, 1));
+                }
+            }
         }
         cin = b.Cout;
     }
