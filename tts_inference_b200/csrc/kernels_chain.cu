@@ -190,7 +190,7 @@ enum { EPI_C_NOISE = 0, EPI_C_MID = 1, EPI_C_FINAL = 2 };
 
 // NW symmetric warps (prologue + epilogue); thread 0 also issues TMA / MMA.  16 warps: one CTA per SM; 8 warps: two.
 template <int C, int NB, int NW, typename HT>
-__global__ void __launch_bounds__(NW * 32) __maxnreg__(NW == 8 ? 112 : 128)
+__global__ void __launch_bounds__(NW * 32) __maxnreg__(NW == 8 ? 128 : 128 + 0 * NW)
 k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmOe,
         const __grid_constant__ CUtensorMap tmOm, const __grid_constant__ CUtensorMap tmWn,
         const __grid_constant__ CUtensorMap tmW0, const __grid_constant__ CUtensorMap tmW1,
