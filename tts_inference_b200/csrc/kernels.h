@@ -48,6 +48,12 @@ void resunit2_geometry(int C, int dil, int* tile_m, int* box_rows);   // x tenso
 cudaError_t launch_resunit2(int half_fp16, const ResUnitArgs& a, const CUtensorMap& tmX, const CUtensorMap& tmW,
                             int sm_count, cudaStream_t st);
 
+// ---- kernels_convt.cu  (ConvTranspose1d with resident weights and row-shifted UMMA descriptors; block 3)
+bool convt_res_supported(int Cin, int Cout, int s);
+int convt_res_box_rows();             // activation tensor-map box = (64, box_rows, 1), 128B swizzle
+cudaError_t launch_convt_res(int half_fp16, const GemmArgs& a, const CUtensorMap& tmA, const CUtensorMap& tmW,
+                             const CUtensorMap& tmO, int sm_count, cudaStream_t st);   // tmO: output box (64, 128*s, 1)
+
 // ---- kernels_chain.cu  (NoiseBlock + 3 ResidualUnits fused, residual stream in TMEM)
 bool chain_supported(int C, int half_fp16);
 int chain_tile_rows(int C);           // rows of a tile incl. the halo (y tensor-map box = (64, 128, 1), 128B swizzle)

@@ -1,0 +1,230 @@
+// k_convt_res: ConvTranspose1d(k = 2s, stride s) for the layers whose whole weight matrix fits shared memory
+// (block 3: Cin 128 -> Cout 64, s = 2, 64 KB), hand-written for sm_100a.
+//
+//   y[m*s + p][o] = b[o] + sum_tap sum_c  x[m + sh(p) - tap][c] * Wp[p*Cout + o][tap*Cin + c],   sh(p) = [p >= s/2]
+//
+// The generic k_gemm_tc streams the weight tile and one row-shifted copy of the activation tile per (phase, tap)
+// through L2 for every 128-row tile and is L2-bandwidth-bound there (SM <-> L2 ~ 43 B/clk/SM against 190 B/clk/SM
+// asked).  Here:
+//   * the packed weights [s*Cout][2*Cin] are loaded ONCE per persistent CTA and stay resident;
+//   * one TMA load brings the 136 input rows m0-1 .. m0+134 of a tile; every (phase, tap) reads them through a
+//     ROW-SHIFTED UMMA descriptor (start address + delta*128 B; the swizzle is a function of the absolute smem
+//     address, see ptx.cuh) -- no second copy;
+//   * 32 tcgen05.mma (M=128, N=Cout, K=16) per tile into one of two TMEM accumulator stages [128 lanes x s*Cout];
+//   * epilogue: 8 warps drain TMEM (+ bias) into a swizzled [256 out rows][128 B] staging tile, one TMA store per
+//     tile writes it (direct 16-byte stores at a 256-byte stride were LSU-bound).
+// Stream edges are TMA out-of-bounds zero fill (x is already Snake'd, snake(0) = 0, so this is the conv's padding).
+#include "common.cuh"
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace snacb {
+using namespace ptx;
+
+namespace {
+
+template <typename HT> struct HalfFmtT;
+template <> struct HalfFmtT<__half> { static constexpr uint32_t kFmt = 0; };
+template <> struct HalfFmtT<__nv_bfloat16> { static constexpr uint32_t kFmt = 1; };
+
+template <int CIN, int COUT, int S>
+struct ConvtCfg {
+    static constexpr int kCH = CIN / 64;                 // K chunks per tap
+    static constexpr int kN = S * COUT;                  // accumulator columns
+    static constexpr int kBoxRows = 136;                 // 128 + halo, multiple of 8 (swizzle atom)
+    static constexpr int kAChunk = kBoxRows * 128;
+    static constexpr int kAStage = kCH * kAChunk;
+    static constexpr int kStages = 3;
+    static constexpr int kOutBytes = 128 * S * COUT * 2;  // output staging tile [128*S rows][COUT] 16-bit
+    static constexpr int kWChunk = kN * 128;             // [kN rows][64 k]
+    static constexpr int kWBytes = 2 * kCH * kWChunk;    // taps x chunks
+    static constexpr int kOffA = 0;
+    static constexpr int kOffW = kStages * kAStage;
+    static constexpr int kOffOut = kOffW + kWBytes;
+    static constexpr int kOffBias = kOffOut + kOutBytes;
+    static constexpr int kOffBar = kOffBias + COUT * 4;
+    static constexpr int kSmem = kOffBar + 128 + 1024;
+    static constexpr int kTmemCols = 2 * kN;
+    static constexpr int kEpiWarps = 8;
+    static constexpr int kThreads = 64 + kEpiWarps * 32;
+    static_assert(kN <= 256 && (kTmemCols & (kTmemCols - 1)) == 0, "accumulator width");
+    static_assert(kAChunk % 1024 == 0 && kOffOut % 1024 == 0 && kSmem <= 232448, "shared memory");
+    static_assert(COUT == 64, "one output row = one 128-byte swizzle row");
+    static_assert(S == 2, "tap shifts are written out for stride 2");
+};
+
+}  // namespace
+
+template <int CIN, int COUT, int S, typename HT>
+__global__ void __launch_bounds__((ConvtCfg<CIN, COUT, S>::kThreads), 1)
+k_convt_res(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+            const __grid_constant__ CUtensorMap tmO, const GemmArgs a, const int num_tiles) {
+    using Cfg = ConvtCfg<CIN, COUT, S>;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* sA = smem + Cfg::kOffA;
+    uint8_t* sW = smem + Cfg::kOffW;
+    uint8_t* sO = smem + Cfg::kOffOut;
+    float* sBias = reinterpret_cast<float*>(smem + Cfg::kOffBias);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kOffBar);
+    uint64_t* full = bars;                    // [kStages]
+    uint64_t* empty = bars + Cfg::kStages;    // [kStages]
+    uint64_t* tfull = bars + 2 * Cfg::kStages;   // [2]
+    uint64_t* tempty = tfull + 2;             // [2]
+    uint64_t* wbar = tempty + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int t_lo = a.t_n > 0 ? a.t_lo : 0, t_n = a.t_n > 0 ? a.t_n : a.Tin;
+    const int tiles_t = (t_n + 127) / 128;
+
+    if (threadIdx.x == 0) {
+        prefetch_tmap(&tmA);
+        prefetch_tmap(&tmW);
+        prefetch_tmap(&tmO);
+        for (int i = 0; i < Cfg::kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], Cfg::kEpiWarps); }
+        mbar_init(wbar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) { tmem_alloc(tmem_slot, Cfg::kTmemCols); tmem_relinquish(); }
+    for (int c = threadIdx.x; c < COUT; c += Cfg::kThreads) sBias[c] = a.bias[c];
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            mbar_expect_tx(wbar, Cfg::kWBytes);
+            for (int j = 0; j < 2 * Cfg::kCH; ++j)
+                tma_load_2d_hint(sW + j * Cfg::kWChunk, &tmW, j * 64, 0, wbar, kL2EvictLast);
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int s = tile / tiles_t, m0 = t_lo + (tile % tiles_t) * 128;
+                mbar_wait(&empty[stage], phase ^ 1u);
+                mbar_expect_tx(&full[stage], Cfg::kAStage);
+                for (int kc = 0; kc < Cfg::kCH; ++kc)
+                    tma_load_3d(sA + stage * Cfg::kAStage + kc * Cfg::kAChunk, &tmA, kc * 64, m0 - 1, s, &full[stage]);
+                if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        constexpr uint32_t idesc = umma_idesc_f16(128, COUT, HalfFmtT<HT>::kFmt);
+        mbar_wait(wbar, 0);
+        int stage = 0; uint32_t phase = 0;
+        int as = 0; uint32_t aphase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            mbar_wait(&tempty[as], aphase ^ 1u);
+            mbar_wait(&full[stage], phase);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t a_base = smem_u32(sA + stage * Cfg::kAStage);
+                const uint32_t w_base = smem_u32(sW);
+#pragma unroll
+                for (int p = 0; p < S; ++p) {
+                    const int sh = (p >= S / 2) ? 1 : 0;
+#pragma unroll
+                    for (int tap = 0; tap < 2; ++tap) {
+                        const uint32_t delta = 1 + sh - tap;           // tile row 0 is input row m0 - 1
+#pragma unroll
+                        for (int kc = 0; kc < Cfg::kCH; ++kc)
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                mma_f16_ss(tmem_base + as * Cfg::kN + p * COUT,
+                                           umma_desc_sw128(a_base + kc * Cfg::kAChunk + delta * 128 + k * 32),
+                                           umma_desc_sw128(w_base + (tap * Cfg::kCH + kc) * Cfg::kWChunk + p * COUT * 128 + k * 32),
+                                           idesc, (tap > 0 || kc > 0 || k > 0) ? 1u : 0u);
+                    }
+                }
+                mma_commit(&empty[stage]);
+                mma_commit(&tfull[as]);
+            }
+            __syncwarp();
+            if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
+            if (++as == 2) { as = 0; aphase ^= 1u; }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue: 2 warps per TMEM lane quadrant
+        const int q = warp & 3, half = (warp - 2) >> 2;      // half = output phase p (64 of the 128 accumulator columns)
+        const bool leader = (warp == 2 && lane == 0);
+        int as = 0; uint32_t aphase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int s = tile / tiles_t, m0 = t_lo + (tile % tiles_t) * 128;
+            mbar_wait(&tfull[as], aphase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * Cfg::kN + half * COUT;
+            uint32_t r0[32], r1[32];
+            tmem_ld32(taddr, r0);
+            tmem_ld32(taddr + 32, r1);
+            // the staging tile is free once the previous tile's TMA store has read it
+            if (leader) bulk_wait_group_read<0>();
+            asm volatile("bar.sync 1, %0;" ::"n"(Cfg::kEpiWarps * 32) : "memory");
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[as]);
+            const int orow = (q * 32 + lane) * S + half;                   // row of the 256-row output tile
+            uint8_t* dst = sO + orow * 128;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const uint32_t* r = (c < 4) ? r0 : r1;
+                uint32_t o[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int col = (c & 3) * 8 + 2 * e, ch = c * 8 + 2 * e;
+                    o[e] = pack2(__uint_as_float(r[col]) + sBias[ch], __uint_as_float(r[col + 1]) + sBias[ch + 1],
+                                 static_cast<const HT*>(nullptr));
+                }
+                *reinterpret_cast<uint4*>(dst + ((c ^ (orow & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+            }
+            fence_proxy_async_smem();
+            asm volatile("bar.sync 1, %0;" ::"n"(Cfg::kEpiWarps * 32) : "memory");
+            if (leader) {
+                tma_store_3d(&tmO, sO, 0, m0 * S, s);                      // rows beyond T are clipped by TMA
+                bulk_commit_group();
+            }
+            if (++as == 2) { as = 0; aphase ^= 1u; }
+        }
+        if (leader) bulk_wait_group<0>();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
+namespace {
+template <int CIN, int COUT, int S, typename HT>
+cudaError_t launch_t(const GemmArgs& a, const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmO, int sm_count,
+                     cudaStream_t st) {
+    using Cfg = ConvtCfg<CIN, COUT, S>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(k_convt_res<CIN, COUT, S, HT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    const int t_n = a.t_n > 0 ? a.t_n : a.Tin;
+    const int tiles = a.S * ((t_n + 127) / 128);
+    if (tiles == 0) return cudaSuccess;
+    const int grid = tiles < sm_count ? tiles : sm_count;
+    k_convt_res<CIN, COUT, S, HT><<<grid, Cfg::kThreads, Cfg::kSmem, st>>>(tmA, tmW, tmO, a, tiles);
+    return cudaGetLastError();
+}
+}  // namespace
+
+bool convt_res_supported(int Cin, int Cout, int s) { return Cin == 128 && Cout == 64 && s == 2; }
+int convt_res_box_rows() { return 136; }
+
+// tmA: activation map box (64, 136, 1); tmW: packed ConvTranspose weights [s*Cout][2*Cin], box (64, s*Cout);
+// tmO: output map box (64, 128*s, 1); all 128B-swizzled
+cudaError_t launch_convt_res(int half_fp16, const GemmArgs& a, const CUtensorMap& tmA, const CUtensorMap& tmW,
+                             const CUtensorMap& tmO, int sm_count, cudaStream_t st) {
+    if (!convt_res_supported(a.K, a.Cout, a.up)) return cudaErrorInvalidValue;
+    return half_fp16 ? launch_t<128, 64, 2, __half>(a, tmA, tmW, tmO, sm_count, st)
+                     : launch_t<128, 64, 2, __nv_bfloat16>(a, tmA, tmW, tmO, sm_count, st);
+}
+
+}  // namespace snacb

@@ -183,6 +183,10 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     d |= static_cast<uint64_t>(2) << 61;                 // SWIZZLE_128B
     return d;
 }
+// Row-shifted views: the 128B swizzle is applied to the ABSOLUTE shared-memory address, so a descriptor whose start
+// address is `rows * 128` bytes past a 1024-byte-aligned, TMA-written tile reads rows [rows, rows + M) of that tile
+// consistently -- with the matrix-base-offset field left at 0 (measured on B200: setting it to (addr >> 7) & 7 gives
+// wrong operands; kernels_convt.cu relies on the plain shifted start address for its +-1-row conv taps).
 // Instruction descriptor (kind::f16): D fp32 (1 at [4,6)), A format [7,10), B format [10,13)
 // (0 = fp16, 1 = bf16), both K-major, dense.  N>>3 at [17,23), M>>4 at [24,29).
 __host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N, uint32_t fmt) {

@@ -92,6 +92,7 @@ struct snacb_handle_s {
     uint64_t launches = 0, streams = 0;
     bool res_v1 = false;                // SNACB_RES_V1=1: use the non-persistent ResidualUnit kernel
     bool no_chain = false;              // SNACB_NO_CHAIN=1: per-layer kernels instead of the fused chain
+    bool no_convt_res = false;          // SNACB_NO_CONVT_RES=1: generic k_gemm_tc for every ConvTranspose
     bool no_trim = false;               // SNACB_NO_TRIM=1: sliced output still decodes every sample of the window
 
     // optional per-launch CUDA-event timing (snacb_profile / snacb_profile_report)
@@ -401,7 +402,25 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
             if (trimmed[bi]) { a.t_lo = ct_in[bi].lo; a.t_n = ct_in[bi].hi - ct_in[bi].lo; }
             a.bias = b.ct_b; a.out = oth;
             snprintf(nm, sizeof nm, "b%d.convt", bi);
-            int rc = gemm(nm, EPI_BIAS, false, a, cur, b.ct_f32, b.ct_h, b.s * b.Cout, 2 * b.Cin);
+            int rc = 0;
+            if (!f32 && !h->no_convt_res && convt_res_supported(b.Cin, b.Cout, b.s) && Tin >= 128) {
+                // weights resident in smem, one activation load per tile, row-shifted descriptors per tap
+                const CUtensorMap *ma, *mw, *mo;
+                rc = act_map(h, &ma, cur, b.Cin, Tin, S, convt_res_box_rows(), 1, hk);
+                if (rc) return rc;
+                rc = weight_map(h, &mw, b.ct_h[hk], b.s * b.Cout, 2 * b.Cin, b.s * b.Cout, hk);
+                if (rc) return rc;
+                rc = act_map(h, &mo, oth, b.Cout, T, S, 128 * b.s, 1, hk);
+                if (rc) return rc;
+                a.seed = seed; a.stream_offset = stream_offset; a.Tbox = 128; a.Wbox = 1;
+                prof_begin(h, nm, st);
+                cudaError_t le = launch_convt_res(hk, a, *ma, *mw, *mo, h->sm_count, st);
+                prof_end(h, st);
+                CK(h, le);
+                h->launches++;
+            } else {
+                rc = gemm(nm, EPI_BIAS, false, a, cur, b.ct_f32, b.ct_h, b.s * b.Cout, 2 * b.Cin);
+            }
             if (rc) return rc;
             rc = tap_any(nm, oth, dt_h, (int64_t)S * T, b.Cout);
             if (rc) return rc;
@@ -699,6 +718,7 @@ int snacb_create(snacb_handle* out, const snacb_weights* w, int device) {
     if (const char* e = getenv("SNACB_RES_V1")) h->res_v1 = atoi(e) != 0;
     if (const char* e = getenv("SNACB_NO_CHAIN")) h->no_chain = atoi(e) != 0;
     if (const char* e = getenv("SNACB_NO_TRIM")) h->no_trim = atoi(e) != 0;
+    if (const char* e = getenv("SNACB_NO_CONVT_RES")) h->no_convt_res = atoi(e) != 0;
     if (const char* e = getenv("SNACB_GROUP_MB")) {
         long mb = atol(e);
         if (mb > 0) h->group_bytes = static_cast<size_t>(mb) << 20;
