@@ -157,6 +157,21 @@ def test_slice_semantics(decoder, prec):
     assert a.shape == (2, 4096) and torch.equal(a, b)
 
 
+@pytest.mark.parametrize("F_,unfused", [(3, False), (6, False), (9, False), (6, True), (17, False)])
+def test_sliced_call_trims_dead_samples_bit_identically(decoder, F_, unfused):
+    """extract_slice=True computes only the receptive field of samples [2048, 4096) (dead-sample trimming, DESIGN.md
+    section 4.2): every utterance length and both kernel paths give exactly the slice of the full decode."""
+    tokens = synth.make_tokens(5, F_, seed=100 + F_, bad_frac=0.01)
+    noises = [_cuda(n) for n in synth.make_noises(5, 4 * F_, seed=3)]
+    full = decoder.decode(_cuda(tokens), raw_ids=True, noise=noises, unfused=unfused)
+    sl = decoder.decode(_cuda(tokens), raw_ids=True, noise=noises, extract_slice=True, unfused=unfused)
+    assert full.shape == (5, 2048 * F_) and sl.shape == (5, 2048)
+    assert torch.equal(sl, full[:, 2048:4096])
+    rng = decoder.decode(_cuda(tokens), raw_ids=True, seed=77, extract_slice=True, unfused=unfused)   # in-kernel noise
+    rng_full = decoder.decode(_cuda(tokens), raw_ids=True, seed=77, unfused=unfused)
+    assert torch.equal(rng, rng_full[:, 2048:4096])
+
+
 def test_ragged_tail_is_dropped(decoder):
     tokens = synth.make_tokens(2, 5, seed=8)
     a = decoder.decode(_cuda(tokens[:, :31]), raw_ids=True, seed=1)     # 4 frames + 3 stray tokens
