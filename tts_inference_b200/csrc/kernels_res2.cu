@@ -51,7 +51,9 @@ struct Res2Cfg {
     static constexpr int kABytes = kTileM * 128;                     // A operand stage (one 64-ch chunk)
     static constexpr int kNSA = 2;
     static constexpr int kWChunkBytes = C * 128;                     // [C (n)][64 (k)] 16-bit
-    static constexpr int kNSW = kWRes ? kChunks : 2;
+    static constexpr int kNHalfW = C > 256 ? 2 : 1;                  // streamed weights: one stage = one <=256-row N half
+    static constexpr int kWStageBytes = kWRes ? kWChunkBytes : (kWChunkBytes / kNHalfW);
+    static constexpr int kNSW = kWRes ? kChunks : (C > 256 ? 4 : 2); // C = 512: 4 x 32 KB ring (3 loads in flight)
     static constexpr int kAccCols = kAccs * C;                       // TMEM columns of one accumulator stage
     static constexpr int kAccStages = (2 * kAccCols <= 512) ? 2 : 1;
     static constexpr int kTmemCols = kAccStages * kAccCols;          // 128 / 256 / 512 (power of two)
@@ -67,7 +69,7 @@ struct Res2Cfg {
     static constexpr int kBarBytes = 256;
     static constexpr int kOffA = 0;
     static constexpr int kOffW = kOffA + kNSA * kABytes;
-    static constexpr int kOffXs = kOffW + kNSW * kWChunkBytes;
+    static constexpr int kOffXs = kOffW + kNSW * kWStageBytes;
     static constexpr int kOffPrm = kOffXs + kNXS * kXsBytes;
     static constexpr int kOffEpi = kOffPrm + kPrmBytes;
     static constexpr int kOffMap = kOffEpi + kEpiBytes;
@@ -96,11 +98,11 @@ k_resunit2(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
     uint64_t* x_empty = bars + 3;         // [3]
     uint64_t* a_full = bars + 6;          // [2]
     uint64_t* a_empty = bars + 8;         // [2]
-    uint64_t* w_full = bars + 10;         // [2]
-    uint64_t* w_empty = bars + 12;        // [2]
-    uint64_t* acc_full = bars + 14;       // [2]
-    uint64_t* acc_empty = bars + 16;      // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+    uint64_t* w_full = bars + 10;         // [4]
+    uint64_t* w_empty = bars + 14;        // [4]
+    uint64_t* acc_full = bars + 18;       // [2]
+    uint64_t* acc_empty = bars + 20;      // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -114,6 +116,7 @@ k_resunit2(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
         for (int i = 0; i < 2; ++i) {
             mbar_init(&a_full[i], kComputeWarps); mbar_init(&a_empty[i], 1);
             mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1);
+            mbar_init(&w_full[i + 2], 1); mbar_init(&w_empty[i + 2], 1);
             mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], Cfg::kSplitEpi ? kEpiWarps : kLockstepEpiWarps);
         }
         fence_barrier_init();
@@ -176,20 +179,21 @@ k_resunit2(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
                 const int tile = blockIdx.x + n * gridDim.x;
                 const int s = tile / tiles_t, t0 = t_lo + (tile % tiles_t) * Cfg::kTileM;
                 for (int kc = 0; kc < Cfg::kChunks; ++kc, ++g) {
-                    if (!Cfg::kWRes) {
-                        const int sw = g % 2;
-                        if (g >= 2) mbar_wait(&w_empty[sw], ((g / 2) - 1) & 1);
-                        mbar_expect_tx(&w_full[sw], Cfg::kWChunkBytes);
-#pragma unroll
-                        for (int nh = 0; nh < Cfg::kNHalf; ++nh)
-                            tma_load_2d(sW + sw * Cfg::kWChunkBytes + nh * (256 * 128), &tmW, kc * 64, nh * 256, &w_full[sw]);
-                    }
                     const int sx = g % Cfg::kNXS;
                     if (g >= Cfg::kNXS) mbar_wait(&x_empty[sx], ((g / Cfg::kNXS) - 1) & 1);
                     mbar_expect_tx(&x_full[sx], Cfg::kRows * 128);
                     uint8_t* dst = sX + sx * Cfg::kXsBytes;
                     tma_load_3d(dst, &tmX, kc * 64, t0 - 3 * DIL, s, &x_full[sx]);
                     tma_load_3d(dst + Cfg::kHalfRows * 128, &tmX, kc * 64, t0 - 3 * DIL + Cfg::kHalfRows, s, &x_full[sx]);
+                    if (!Cfg::kWRes) {
+#pragma unroll
+                        for (int nh = 0; nh < Cfg::kNHalfW; ++nh) {
+                            const int h = g * Cfg::kNHalfW + nh, sw = h % Cfg::kNSW;
+                            if (h >= Cfg::kNSW) mbar_wait(&w_empty[sw], ((h / Cfg::kNSW) - 1) & 1);
+                            mbar_expect_tx(&w_full[sw], Cfg::kWStageBytes);
+                            tma_load_2d(sW + sw * Cfg::kWStageBytes, &tmW, kc * 64, nh * 256, &w_full[sw]);
+                        }
+                    }
                 }
             }
         }
@@ -205,25 +209,29 @@ k_resunit2(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
             const uint32_t d_base = tmem_base + as * Cfg::kAccCols;
             for (int kc = 0; kc < Cfg::kChunks; ++kc, ++g) {
                 const int sa = g % 2;
-                if (!Cfg::kWRes) mbar_wait(&w_full[g % 2], (g / 2) & 1);
                 mbar_wait(&a_full[sa], (g / 2) & 1);
-                tc_fence_after();
-                if (lane == 0) {
-                    const uint32_t a_addr = smem_u32(sA + sa * Cfg::kABytes);
-                    const uint32_t w_addr = smem_u32(sW + (Cfg::kWRes ? kc : (g % 2)) * Cfg::kWChunkBytes);
+                const uint32_t a_addr = smem_u32(sA + sa * Cfg::kABytes);
 #pragma unroll
-                    for (int ac = 0; ac < Cfg::kAccs; ++ac) {
+                for (int nh = 0; nh < Cfg::kNHalf; ++nh) {
+                    // streamed weights: one ring stage per N half, released as soon as its MMAs retire
+                    const int h = g * Cfg::kNHalfW + nh, sw = h % Cfg::kNSW;
+                    if (!Cfg::kWRes) mbar_wait(&w_full[sw], (h / Cfg::kNSW) & 1);
+                    tc_fence_after();
+                    if (lane == 0) {
+                        const uint32_t w_addr = Cfg::kWRes ? smem_u32(sW + kc * Cfg::kWChunkBytes + nh * (256 * 128))
+                                                           : smem_u32(sW + sw * Cfg::kWStageBytes);
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
+                        for (int ac = 0; ac < Cfg::kAccs; ++ac)
 #pragma unroll
-                            for (int nh = 0; nh < Cfg::kNHalf; ++nh)
+                            for (int k = 0; k < 4; ++k)
                                 mma_f16_ss(d_base + ac * C + nh * 256, umma_desc_sw128(a_addr + ac * 16384 + k * 32),
-                                           umma_desc_sw128(w_addr + nh * (256 * 128) + k * 32), idesc,
-                                           (kc > 0 || k > 0) ? 1u : 0u);
-                        }
+                                           umma_desc_sw128(w_addr + k * 32), idesc, (kc > 0 || k > 0) ? 1u : 0u);
+                        if (!Cfg::kWRes) mma_commit(&w_empty[sw]);
                     }
+                    __syncwarp();
+                }
+                if (lane == 0) {
                     mma_commit(&a_empty[sa]);
-                    if (!Cfg::kWRes) mma_commit(&w_empty[g % 2]);
                     if (kc == Cfg::kChunks - 1) mma_commit(&acc_full[as]);
                 }
                 __syncwarp();
