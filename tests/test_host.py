@@ -162,7 +162,7 @@ def test_chain_span_schedule(C):
                             assert r not in written
                             written.add(r)
                             work[r] = sum((j + 2) * win[j] for j in range(7))
-            for r in range(need_lo[d], rows - need_lo[d]):
+            for r in range(need_lo[d], rows - need_lo[d]):     # the schedule may skip rows nobody consumes
                 assert r in written and work[r] == want[r], (C, d, kc, r)
     per_warp = sp[:, :nw, :, 1].sum(axis=2)
     assert per_warp.max() - per_warp.min() <= 1                             # balanced to one octet

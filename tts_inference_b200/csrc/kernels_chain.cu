@@ -386,6 +386,8 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
 #pragma unroll 1
         for (int it = g; it < kPieces; it += NW / 4) {
             const int blk = it / (C / 32), cg = it % (C / 32);
+            // the last epilogue only feeds the TMA stores: 32-row groups entirely inside the halo are skipped
+            if (MODE == EPI_C_FINAL && (blk * 128 + q * 32 + 32 <= kHalo || blk * 128 + q * 32 >= Cfg::kRows - kHalo)) continue;
             mbar_wait(&mma_bar[blk], mma_par);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + blk * C + cg * 32;
@@ -655,10 +657,13 @@ void chain_build_spans(int C, ChainSpan (*spans)[kChainWarps][kChainSpans]) {
         struct Cls { int kc, r0, noct; };
         std::vector<Cls> cls;
         const int top = (d == 1) ? 0 : (d == 3 ? 8 : 40);
+        // rows at or beyond `hi` are not needed downstream: the last unit feeds only the stored rows (< rows - halo),
+        // the unit before it additionally that unit's 27 rows of taps, the first one 9 more
+        const int hi = rows - kChainHalo + (l == 2 ? 0 : (l == 1 ? 27 : 36));
         for (int kc = 0; kc < ch; ++kc)
             for (int m = 0; m < d; ++m) {
                 const int r0 = top - 8 * m;
-                const int steps = (rows - r0 + d - 1) / d;
+                const int steps = (hi - r0 + d - 1) / d;
                 cls.push_back({kc, r0, (steps + 7) / 8});
             }
         int total = 0;
