@@ -284,6 +284,12 @@ void launch_respre_f32(const ResUnitArgs& a, float* P, cudaStream_t st) {
 // [2048:4096] (vllm_inference/modal_audio_stream.py:94-95,195-198), int16 quantise (:201).
 // One warp = 32 consecutive samples; lane = channel pair; 7-row sliding window in registers.
 // ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 load_pair(const float* p) { return *reinterpret_cast<const float2*>(p); }
+__device__ __forceinline__ float2 load_pair(const __half* p) { return __half22float2(*reinterpret_cast<const __half2*>(p)); }
+__device__ __forceinline__ float2 load_pair(const __nv_bfloat16* p) {
+    return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p));
+}
+
 // One warp = 32 consecutive output samples of one stream; lane = channel pair while the 7-tap window slides down
 // the rows (each input row is loaded once, 128 B per warp), every lane keeping its 2-channel partial sum of all 32
 // samples in registers; one recursive-halving exchange (31 shuffles) then leaves sample `lane` summed in lane `lane`.
@@ -299,10 +305,9 @@ k_tail(const InT* __restrict__ a, int T, int t_begin, int n_out, const float* __
 #pragma unroll
     for (int j = 0; j < 7; ++j) wj[j] = make_float2(w[j * 64 + 2 * lane], w[j * 64 + 2 * lane + 1]);
     const InT* src = a + static_cast<size_t>(s) * T * 64 + 2 * lane;
-    auto load_row = [&](int t) -> float2 {
+    auto load_row = [&](int t) -> float2 {     // one 4-byte (16-bit types) or 8-byte load per lane and row
         if (t < 0 || t >= T) return make_float2(0.f, 0.f);
-        const InT* p = src + static_cast<size_t>(t) * 64;
-        return make_float2(to_f32(p[0]), to_f32(p[1]));
+        return load_pair(src + static_cast<size_t>(t) * 64);
     };
     float2 rows[38];                       // the 32 + 6 input rows of this warp's samples, issued back to back
 #pragma unroll
