@@ -59,6 +59,7 @@ struct ResUnitArgs {
     const float* alpha2; const float* inv_alpha2;   // [C]
     const float* pw_b;       // [C]
     const float* alpha_next; const float* inv_alpha_next;  // [C] (EPI_RES_SNAKE)
+    unsigned long long* prof;   // debug: clock64 sums of CTA 0 (SNACB_RES_PROF=1), else null
 };
 
 // Fused NoiseBlock + 3 ResidualUnits of one DecoderBlock (kernels_chain.cu).
@@ -140,6 +141,22 @@ __device__ __forceinline__ float counter_normal(unsigned long long key, unsigned
     return sqrtf(-2.0f * __logf(u1)) * __cosf(6.283185307179586f * u2);
 }
 
+// 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256): a thread that owns a 64-byte row segment moves it in two
+// requests instead of four -- the row-per-thread epilogues are bound by L1 wavefronts (32 distinct lines per request)
+struct alignas(32) U32x8 { uint32_t v[8]; };
+__device__ __forceinline__ U32x8 ld_global_v8(const void* p) {
+    U32x8 r;
+    asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_global_v8(void* p, const U32x8& r) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"l"(p), "r"(r.v[0]), "r"(r.v[1]), "r"(r.v[2]), "r"(r.v[3]), "r"(r.v[4]), "r"(r.v[5]), "r"(r.v[6]), "r"(r.v[7])
+                 : "memory");
+}
+
 // ---------------------------------------------------------------- typed load / store of 8 channels
 __device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
     float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
@@ -191,6 +208,28 @@ __device__ __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162flo
 __device__ __forceinline__ void from_f32(float& d, float v) { d = v; }
 __device__ __forceinline__ void from_f32(__nv_bfloat16& d, float v) { d = __float2bfloat16_rn(v); }
 
+__device__ __forceinline__ void load32(const __half* p, float (&v)[32]) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const U32x8 r = ld_global_v8(p + 16 * h);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&r.v[i]));
+            v[16 * h + 2 * i] = f.x; v[16 * h + 2 * i + 1] = f.y;
+        }
+    }
+}
+__device__ __forceinline__ void load32(const __nv_bfloat16* p, float (&v)[32]) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const U32x8 r = ld_global_v8(p + 16 * h);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r.v[i]));
+            v[16 * h + 2 * i] = f.x; v[16 * h + 2 * i + 1] = f.y;
+        }
+    }
+}
 template <typename T>
 __device__ __forceinline__ void load32(const T* p, float (&v)[32]) {
 #pragma unroll
@@ -199,6 +238,25 @@ __device__ __forceinline__ void load32(const T* p, float (&v)[32]) {
         load8(p + 8 * i, t);
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[8 * i + j] = t[j];
+    }
+}
+__device__ __forceinline__ void store32(__half* p, const float (&v)[32]) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        U32x8 r;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r.v[i] = pack2(v[16 * h + 2 * i], v[16 * h + 2 * i + 1], static_cast<const __half*>(nullptr));
+        st_global_v8(p + 16 * h, r);
+    }
+}
+__device__ __forceinline__ void store32(__nv_bfloat16* p, const float (&v)[32]) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        U32x8 r;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            r.v[i] = pack2(v[16 * h + 2 * i], v[16 * h + 2 * i + 1], static_cast<const __nv_bfloat16*>(nullptr));
+        st_global_v8(p + 16 * h, r);
     }
 }
 template <typename T>

@@ -204,18 +204,24 @@ k_resunit2(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
         int g = 0;
         for (int n = 0; n < my_tiles; ++n) {
             const int as = n % Cfg::kAccStages;
+            long long tp2 = clock64();
             mbar_wait(&acc_empty[as], ((n / Cfg::kAccStages) & 1) ^ 1);
+            if (a.prof && blockIdx.x == 0 && lane == 0) a.prof[2] += clock64() - tp2;
             tc_fence_after();
             const uint32_t d_base = tmem_base + as * Cfg::kAccCols;
             for (int kc = 0; kc < Cfg::kChunks; ++kc, ++g) {
                 const int sa = g % 2;
+                long long tp0 = clock64();
                 mbar_wait(&a_full[sa], (g / 2) & 1);
+                if (a.prof && blockIdx.x == 0 && lane == 0) a.prof[0] += clock64() - tp0;
                 const uint32_t a_addr = smem_u32(sA + sa * Cfg::kABytes);
 #pragma unroll
                 for (int nh = 0; nh < Cfg::kNHalf; ++nh) {
                     // streamed weights: one ring stage per N half, released as soon as its MMAs retire
                     const int h = g * Cfg::kNHalfW + nh, sw = h % Cfg::kNSW;
+                    long long tp1 = clock64();
                     if (!Cfg::kWRes) mbar_wait(&w_full[sw], (h / Cfg::kNSW) & 1);
+                    if (a.prof && blockIdx.x == 0 && lane == 0) a.prof[1] += clock64() - tp1;
                     tc_fence_after();
                     if (lane == 0) {
                         const uint32_t w_addr = Cfg::kWRes ? smem_u32(sW + kc * Cfg::kWChunkBytes + nh * (256 * 128))
@@ -324,40 +330,55 @@ k_resunit2(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
             const int t = t0 + ac * 128 + q * 32 + lane;
             const bool valid = t < a.T;
             const size_t grow = static_cast<size_t>(s) * a.T + t;
+            // the residual of a 32-column piece is fetched one piece ahead (the first one before the accumulator is
+            // ready): its L2 latency is the long pole of this epilogue, not the arithmetic
+            U32x8 xa[2], xb[2];
+            auto fetch = [&](int cc, U32x8 (&dst)[2]) {
+                if (valid) {
+                    const HT* p = x + grow * C + cg * kColsPerWarp + cc * 32;
+                    dst[0] = ld_global_v8(p);
+                    dst[1] = ld_global_v8(p + 16);
+                }
+            };
+            fetch(0, xa);
             mbar_wait(&acc_full[as], (n / Cfg::kAccStages) & 1);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * Cfg::kAccCols + ac * C;
 #pragma unroll 1
             for (int cc = 0; cc < kColsPerWarp / 32; ++cc) {
                 const int col = cg * kColsPerWarp + cc * 32;
-                float xr[32];
-                if (valid) load32(x + grow * C + col, xr);
                 uint32_t raw[32];
                 tmem_ld32(taddr + col, raw);
+                if (cc + 1 < kColsPerWarp / 32) fetch(cc + 1, xb);
                 tmem_ld_wait();
                 if (valid) {
-                    float v[32];
+                    const uint32_t* xw = reinterpret_cast<const uint32_t*>(xa);
+                    U32x8 o[2];
+                    uint32_t* ow = reinterpret_cast<uint32_t*>(o);
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
                         const float4 b = *reinterpret_cast<const float4*>(sEpi + col + j);
-                        v[j] = xr[j] + (__uint_as_float(raw[j]) + b.x);
-                        v[j + 1] = xr[j + 1] + (__uint_as_float(raw[j + 1]) + b.y);
-                        v[j + 2] = xr[j + 2] + (__uint_as_float(raw[j + 2]) + b.z);
-                        v[j + 3] = xr[j + 3] + (__uint_as_float(raw[j + 3]) + b.w);
-                    }
-                    if (EPI == EPI_RES_SNAKE) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
+                        const float2 x0 = unpack2(xw[j / 2], static_cast<const HT*>(nullptr));
+                        const float2 x1 = unpack2(xw[j / 2 + 1], static_cast<const HT*>(nullptr));
+                        float v0 = x0.x + (__uint_as_float(raw[j]) + b.x);
+                        float v1 = x0.y + (__uint_as_float(raw[j + 1]) + b.y);
+                        float v2 = x1.x + (__uint_as_float(raw[j + 2]) + b.z);
+                        float v3 = x1.y + (__uint_as_float(raw[j + 3]) + b.w);
+                        if (EPI == EPI_RES_SNAKE) {
                             const float4 al = *reinterpret_cast<const float4*>(sEpi + C + col + j);
                             const float4 ia = *reinterpret_cast<const float4*>(sEpi + 2 * C + col + j);
-                            v[j] = snake_f<true>(v[j], al.x, ia.x);
-                            v[j + 1] = snake_f<true>(v[j + 1], al.y, ia.y);
-                            v[j + 2] = snake_f<true>(v[j + 2], al.z, ia.z);
-                            v[j + 3] = snake_f<true>(v[j + 3], al.w, ia.w);
+                            v0 = snake_f<true>(v0, al.x, ia.x);
+                            v1 = snake_f<true>(v1, al.y, ia.y);
+                            v2 = snake_f<true>(v2, al.z, ia.z);
+                            v3 = snake_f<true>(v3, al.w, ia.w);
                         }
+                        ow[j / 2] = pack2(v0, v1, static_cast<const HT*>(nullptr));
+                        ow[j / 2 + 1] = pack2(v2, v3, static_cast<const HT*>(nullptr));
                     }
-                    store32(out + grow * C + col, v);
+                    st_global_v8(out + grow * C + col, o[0]);
+                    st_global_v8(out + grow * C + col + 16, o[1]);
                 }
+                xa[0] = xb[0]; xa[1] = xb[1];
             }
             tc_fence_before();
             __syncwarp();
@@ -390,8 +411,12 @@ k_resunit2(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
                     ia2 = *reinterpret_cast<const float2*>(a.inv_alpha2 + ch);
                 }
                 const int sx = g % Cfg::kNXS, sa = g % 2;
+                const bool pr = a.prof && blockIdx.x == 0 && tid == 0;
+                long long tq = clock64();
                 mbar_wait(&x_full[sx], (g / Cfg::kNXS) & 1);
+                if (pr) { const long long t = clock64(); a.prof[3] += t - tq; tq = t; }
                 if (g >= 2) mbar_wait(&a_empty[sa], ((g / 2) - 1) & 1);
+                if (pr) { const long long t = clock64(); a.prof[4] += t - tq; tq = t; }
                 const uint8_t* xs = sX + sx * Cfg::kXsBytes;
                 uint8_t* dstA = sA + sa * Cfg::kABytes;
 
@@ -428,10 +453,13 @@ k_resunit2(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) { mbar_arrive(&a_full[sa]); mbar_arrive(&x_empty[sx]); }
+                if (pr) { const long long t = clock64(); a.prof[5] += t - tq; tq = t; }
             }
             if (!Cfg::kSplitEpi && warp < kLockstepEpiWarps) {
+                const long long te = clock64();
                 if (Cfg::kAccStages == 1) epilogue(n);
                 else if (n > 0) epilogue(n - 1);
+                if (a.prof && blockIdx.x == 0 && tid == 0) { a.prof[6] += clock64() - te; a.prof[7] += 1; }
             }
         }
         if (!Cfg::kSplitEpi && Cfg::kAccStages == 2 && my_tiles > 0 && warp < kLockstepEpiWarps) epilogue(my_tiles - 1);

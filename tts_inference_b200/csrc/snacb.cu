@@ -550,10 +550,25 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
                 const CUtensorMap* mx;
                 int rc2 = act_map(h, &mx, cur, ra.C, T, S, box_rows, 1, hk, 0);
                 if (rc2) return rc2;
+                static const bool res_prof = getenv("SNACB_RES_PROF") && atoi(getenv("SNACB_RES_PROF")) != 0;
+                if (res_prof) {
+                    CK(h, cudaMalloc(reinterpret_cast<void**>(&ra.prof), 16 * sizeof(unsigned long long)));
+                    CK(h, cudaMemsetAsync(ra.prof, 0, 16 * sizeof(unsigned long long), st));
+                }
                 cudaError_t le = launch_resunit2(hk, ra, *mx, r.tm_pw[hk], h->sm_count, st);
                 prof_end(h, st);
                 CK(h, le);
                 h->launches++;
+                if (res_prof) {
+                    unsigned long long pv[16];
+                    CK(h, cudaStreamSynchronize(st));
+                    CK(h, cudaMemcpy(pv, ra.prof, sizeof pv, cudaMemcpyDeviceToHost));
+                    CK(h, cudaFree(ra.prof));
+                    const unsigned long long nt = pv[7] ? pv[7] : 1;
+                    fprintf(stderr, "resunit2 b%d d=%d C=%d: CTA0 cycles per tile (%llu tiles): MMA warp waits a_full %llu w_full %llu acc_empty %llu | "
+                            "warp0 waits x_full %llu a_empty %llu, prologue %llu, epilogue %llu\n", bi, ra.dil, ra.C, nt, pv[0] / nt, pv[1] / nt,
+                            pv[2] / nt, pv[3] / nt, pv[4] / nt, pv[5] / nt, pv[6] / nt);
+                }
             } else {
                 cudaError_t le = launch_resunit_tc(last ? EPI_RES_SNAKE : EPI_RES, hk, xf32 ? 1 : 0, ra, r.tm_pw[hk], st);
                 prof_end(h, st);
