@@ -230,6 +230,14 @@ def test_decode_host_equals_device(decoder):
     assert np.array_equal(a, b.cpu().numpy())
 
 
+def test_decode_host_large_batch_equals_device(decoder):
+    """Host-buffer entry point on a batch that spans many tiles per kernel: same bytes as the device-buffer call."""
+    tokens = synth.make_tokens(520, 4, seed=15)
+    a = decoder.decode_host(tokens, raw_ids=True, seed=6)
+    b = decoder.decode(_cuda(tokens), raw_ids=True, seed=6)
+    assert a.shape == (520, 8192) and np.array_equal(a, b.cpu().numpy())
+
+
 def test_empty_and_bad_arguments(decoder):
     from tts_inference_b200 import SnacbError
     e = decoder.decode(torch.empty((0, 28), dtype=torch.int32, device="cuda"), raw_ids=True)
