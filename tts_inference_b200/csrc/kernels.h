@@ -54,6 +54,10 @@ int convt_res_box_rows();             // activation tensor-map box = (64, box_ro
 cudaError_t launch_convt_res(int half_fp16, const GemmArgs& a, const CUtensorMap& tmA, const CUtensorMap& tmW,
                              const CUtensorMap& tmO, int sm_count, cudaStream_t st);   // tmO: output box (64, 128*s, 1)
 
+bool convt_ph_supported(int Cin, int Cout, int s);   // block 2: one output phase's weights resident per CTA group
+cudaError_t launch_convt_ph(int half_fp16, const GemmArgs& a, const CUtensorMap& tmA, const CUtensorMap& tmW, int sm_count,
+                            cudaStream_t st);        // tmA box (64, 136, 1); tmW box (64, Cout)
+
 // ---- kernels_chain.cu  (NoiseBlock + 3 ResidualUnits fused, residual stream in TMEM)
 bool chain_supported(int C, int half_fp16);
 int chain_tile_rows(int C);           // rows of a tile incl. the halo (y tensor-map box = (64, 128, 1), 128B swizzle)

@@ -195,6 +195,159 @@ k_convt_res(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
 }
 
+// =================================================================================================
+// k_convt_ph: ConvTranspose1d whose weights do not fit shared memory as a whole (block 2: Cin 256 -> Cout 128, s = 4,
+// 512 KB) but whose slice for ONE output phase does (128 KB).  The persistent CTAs are split into s groups, one per
+// output phase p; a CTA keeps its phase's weights [Cout][2*Cin] resident and walks the 128-row input tiles of its
+// group, loading each tile's 136 input rows once (one 64-channel chunk per ring stage, both taps read it through
+// row-shifted descriptors).  L2 -> SM traffic per 128x128x512 tile: 68 KB (33 B/clk at the tensor rate) instead of the
+// 192 KB the generic kernel streams; the s groups read the same activations at about the same time (L2 hits).
+// =================================================================================================
+namespace {
+template <int CIN, int COUT, int S>
+struct ConvtPhCfg {
+    static constexpr int kCH = CIN / 64;
+    static constexpr int kBoxRows = 136;
+    static constexpr int kAChunk = kBoxRows * 128;
+    static constexpr int kRing = 5;                      // A chunk stages (more than one tile deep)
+    static constexpr int kWChunk = COUT * 128;           // [COUT rows][64 k]
+    static constexpr int kWBytes = 2 * kCH * kWChunk;    // taps x chunks of this phase
+    static constexpr int kOffA = 0;
+    static constexpr int kOffW = kRing * kAChunk;
+    static constexpr int kOffBias = kOffW + kWBytes;
+    static constexpr int kOffBar = kOffBias + COUT * 4;
+    static constexpr int kSmem = kOffBar + 128 + 1024;
+    static constexpr int kTmemCols = 2 * COUT;
+    static constexpr int kEpiWarps = 8;
+    static constexpr int kThreads = 64 + kEpiWarps * 32;
+    static_assert(COUT == 128 && (kOffW % 1024) == 0 && kSmem <= 232448, "configuration");
+};
+}  // namespace
+
+template <int CIN, int COUT, int S, typename HT>
+__global__ void __launch_bounds__((ConvtPhCfg<CIN, COUT, S>::kThreads), 1)
+k_convt_ph(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const GemmArgs a,
+           const int num_tiles) {
+    using Cfg = ConvtPhCfg<CIN, COUT, S>;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* sA = smem + Cfg::kOffA;
+    uint8_t* sW = smem + Cfg::kOffW;
+    float* sBias = reinterpret_cast<float*>(smem + Cfg::kOffBias);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kOffBar);
+    uint64_t* full = bars;                    // [kRing]
+    uint64_t* empty = bars + Cfg::kRing;      // [kRing]
+    uint64_t* tfull = bars + 2 * Cfg::kRing;  // [2]
+    uint64_t* tempty = tfull + 2;             // [2]
+    uint64_t* wbar = tempty + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int t_lo = a.t_n > 0 ? a.t_lo : 0, t_n = a.t_n > 0 ? a.t_n : a.Tin;
+    const int tiles_t = (t_n + 127) / 128;
+    const int p = blockIdx.x % S;                                   // output phase of this CTA
+    const int gi = blockIdx.x / S, gs = (static_cast<int>(gridDim.x) - p + S - 1) / S;   // index / size of its group
+    const int sh = (p >= S / 2) ? 1 : 0;
+
+    if (threadIdx.x == 0) {
+        prefetch_tmap(&tmA);
+        prefetch_tmap(&tmW);
+        for (int i = 0; i < Cfg::kRing; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], Cfg::kEpiWarps); }
+        mbar_init(wbar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) { tmem_alloc(tmem_slot, Cfg::kTmemCols); tmem_relinquish(); }
+    for (int c = threadIdx.x; c < COUT; c += Cfg::kThreads) sBias[c] = a.bias[c];
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            mbar_expect_tx(wbar, Cfg::kWBytes);
+            for (int j = 0; j < 2 * Cfg::kCH; ++j)
+                tma_load_2d_hint(sW + j * Cfg::kWChunk, &tmW, j * 64, p * COUT, wbar, kL2EvictLast);
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = gi; tile < num_tiles; tile += gs) {
+                const int s = tile / tiles_t, m0 = t_lo + (tile % tiles_t) * 128;
+                for (int kc = 0; kc < Cfg::kCH; ++kc) {
+                    mbar_wait(&empty[stage], phase ^ 1u);
+                    mbar_expect_tx(&full[stage], Cfg::kAChunk);
+                    tma_load_3d(sA + stage * Cfg::kAChunk, &tmA, kc * 64, m0 - 1, s, &full[stage]);
+                    if (++stage == Cfg::kRing) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        constexpr uint32_t idesc = umma_idesc_f16(128, COUT, HalfFmtT<HT>::kFmt);
+        mbar_wait(wbar, 0);
+        int stage = 0; uint32_t phase = 0;
+        int as = 0; uint32_t aphase = 0;
+        for (int tile = gi; tile < num_tiles; tile += gs) {
+            mbar_wait(&tempty[as], aphase ^ 1u);
+            for (int kc = 0; kc < Cfg::kCH; ++kc) {
+                mbar_wait(&full[stage], phase);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t a_base = smem_u32(sA + stage * Cfg::kAChunk);
+                    const uint32_t w_base = smem_u32(sW);
+#pragma unroll
+                    for (int tap = 0; tap < 2; ++tap) {
+                        const uint32_t delta = 1 + sh - tap;               // stage row 0 is input row m0 - 1
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            mma_f16_ss(tmem_base + as * COUT, umma_desc_sw128(a_base + delta * 128 + k * 32),
+                                       umma_desc_sw128(w_base + (tap * Cfg::kCH + kc) * Cfg::kWChunk + k * 32), idesc,
+                                       (kc > 0 || tap > 0 || k > 0) ? 1u : 0u);
+                    }
+                    mma_commit(&empty[stage]);
+                    if (kc == Cfg::kCH - 1) mma_commit(&tfull[as]);
+                }
+                __syncwarp();
+                if (++stage == Cfg::kRing) { stage = 0; phase ^= 1u; }
+            }
+            if (++as == 2) { as = 0; aphase ^= 1u; }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue: 2 warps per TMEM lane quadrant
+        const int q = warp & 3, half = (warp - 2) >> 2;      // half: which 64 of the phase's 128 channels
+        HT* out = static_cast<HT*>(a.out);
+        int as = 0; uint32_t aphase = 0;
+        for (int tile = gi; tile < num_tiles; tile += gs) {
+            const int s = tile / tiles_t, m = t_lo + (tile % tiles_t) * 128 + q * 32 + lane;
+            const bool valid = (m < a.Tin) && (m < t_lo + t_n);
+            mbar_wait(&tfull[as], aphase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * COUT + half * 64;
+            uint32_t r0[32], r1[32];
+            tmem_ld32(taddr, r0);
+            tmem_ld32(taddr + 32, r1);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[as]);
+            if (valid) {
+                HT* dst = out + (static_cast<size_t>(s) * a.Tin * S + static_cast<size_t>(m) * S + p) * COUT + half * 64;
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r0[j]) + sBias[half * 64 + j];
+                store32(dst, v);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r1[j]) + sBias[half * 64 + 32 + j];
+                store32(dst + 32, v);
+            }
+            if (++as == 2) { as = 0; aphase ^= 1u; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
 namespace {
 template <int CIN, int COUT, int S, typename HT>
 cudaError_t launch_t(const GemmArgs& a, const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmO, int sm_count,
@@ -214,6 +367,36 @@ cudaError_t launch_t(const GemmArgs& a, const CUtensorMap& tmA, const CUtensorMa
     return cudaGetLastError();
 }
 }  // namespace
+
+namespace {
+template <int CIN, int COUT, int S, typename HT>
+cudaError_t launch_ph_t(const GemmArgs& a, const CUtensorMap& tmA, const CUtensorMap& tmW, int sm_count, cudaStream_t st) {
+    using Cfg = ConvtPhCfg<CIN, COUT, S>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(k_convt_ph<CIN, COUT, S, HT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    const int t_n = a.t_n > 0 ? a.t_n : a.Tin;
+    const int tiles = a.S * ((t_n + 127) / 128);
+    if (tiles == 0) return cudaSuccess;
+    int per = sm_count / S;                           // CTAs per phase group
+    if (per > tiles) per = tiles;
+    if (per < 1) per = 1;
+    k_convt_ph<CIN, COUT, S, HT><<<per * S, Cfg::kThreads, Cfg::kSmem, st>>>(tmA, tmW, a, tiles);
+    return cudaGetLastError();
+}
+}  // namespace
+
+bool convt_ph_supported(int Cin, int Cout, int s) { return Cin == 256 && Cout == 128 && s == 4; }
+// tmA: activation map box (64, 136, 1); tmW: packed weights [s*Cout][2*Cin], box (64, Cout)
+cudaError_t launch_convt_ph(int half_fp16, const GemmArgs& a, const CUtensorMap& tmA, const CUtensorMap& tmW, int sm_count,
+                            cudaStream_t st) {
+    if (!convt_ph_supported(a.K, a.Cout, a.up)) return cudaErrorInvalidValue;
+    return half_fp16 ? launch_ph_t<256, 128, 4, __half>(a, tmA, tmW, sm_count, st)
+                     : launch_ph_t<256, 128, 4, __nv_bfloat16>(a, tmA, tmW, sm_count, st);
+}
 
 bool convt_res_supported(int Cin, int Cout, int s) { return Cin == 128 && Cout == 64 && s == 2; }
 int convt_res_box_rows() { return 136; }

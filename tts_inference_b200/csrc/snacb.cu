@@ -418,6 +418,19 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
                 prof_end(h, st);
                 CK(h, le);
                 h->launches++;
+            } else if (!f32 && !h->no_convt_res && convt_ph_supported(b.Cin, b.Cout, b.s) && Tin >= 128) {
+                // one output phase's weights resident per CTA group, one activation load per tile
+                const CUtensorMap *ma, *mw;
+                rc = act_map(h, &ma, cur, b.Cin, Tin, S, convt_res_box_rows(), 1, hk);
+                if (rc) return rc;
+                rc = weight_map(h, &mw, b.ct_h[hk], b.s * b.Cout, 2 * b.Cin, b.Cout, hk);
+                if (rc) return rc;
+                a.seed = seed; a.stream_offset = stream_offset; a.Tbox = 128; a.Wbox = 1;
+                prof_begin(h, nm, st);
+                cudaError_t le = launch_convt_ph(hk, a, *ma, *mw, h->sm_count, st);
+                prof_end(h, st);
+                CK(h, le);
+                h->launches++;
             } else {
                 rc = gemm(nm, EPI_BIAS, false, a, cur, b.ct_f32, b.ct_h, b.s * b.Cout, 2 * b.Cin);
             }
