@@ -72,7 +72,9 @@ struct ChainCfg {
     static constexpr int kOffPrm = kOffW + kWBytes;
     static constexpr int kOffEpi = kOffPrm + kPrmBytes;
     static constexpr int kOffNz = kOffEpi + kEpiBytes;
-    static constexpr int kOffBar = kOffNz + kNzBytes;
+    static constexpr int kSpanBytes = 3 * kChainWarps * kChainSpans * 8;   // the launch's span table (copied from the kernel parameters)
+    static constexpr int kOffSpan = kOffNz + kNzBytes;
+    static constexpr int kOffBar = kOffSpan + kSpanBytes;
     static constexpr int kSmem = kOffBar + 256 + 1024;
     static constexpr int kTmemCols = NB * C;
     static_assert(NB >= 2 && NB <= 8, "blocks per tile");
@@ -206,6 +208,7 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
     uint32_t* sPrm = reinterpret_cast<uint32_t*>(smem + Cfg::kOffPrm);
     float* sEpi = reinterpret_cast<float*>(smem + Cfg::kOffEpi);
     float* sNz = reinterpret_cast<float*>(smem + Cfg::kOffNz);
+    ChainSpan* sSpan = reinterpret_cast<ChainSpan*>(smem + Cfg::kOffSpan);   // [3][kChainWarps][kChainSpans]
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kOffBar);
     uint64_t* ld_bar = bars;          // tile landed (TMA)
     uint64_t* w_bar = bars + 1;       // [2] weight buffers landed
@@ -253,6 +256,10 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
             d[22] = __float_as_uint(L.inv2[ch]); d[23] = __float_as_uint(L.inv2[ch + 1]);
         }
     }
+    // the span table is indexed by (layer, warp) at run time: from shared memory, not from the constant bank (a dynamically
+    // indexed kernel parameter costs a constant-cache miss per layer: ~1 k cycles of the 'pre' phase, measured)
+    for (int i = tid; i < 3 * kChainWarps * kChainSpans; i += kThreads)
+        sSpan[i] = a.spans[i / (kChainWarps * kChainSpans)][(i / kChainSpans) % kChainWarps][i % kChainSpans];
     // epilogue vectors: [0] scale of the NoiseBlock output, [1],[2] scale and scaled bias after unit d=1, [3],[4] after
     // d=3, [5] bias after d=9, [6],[7] alpha / 1/alpha of the next Snake.  scale = alpha1 of the next unit's Snake in the
     // fp16 formulation (the tile copy holds alpha1 * x), 1 otherwise.
@@ -501,19 +508,20 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
             int r_first[kChainSpans], n_oct[kChainSpans], kcs[kChainSpans];
 #pragma unroll
             for (int sp = 0; sp < kChainSpans; ++sp) {
-                const ChainSpan spn = a.spans[l][warp][sp];
+                const ChainSpan spn = sSpan[(l * kChainWarps + warp) * kChainSpans + sp];
                 r_first[sp] = spn.r_first; n_oct[sp] = spn.n_oct; kcs[sp] = spn.kc;
-                const uint8_t* plane = sX + spn.kc * Cfg::kPlane;
 #pragma unroll
-                for (int j = 0; j < 3; ++j) {
-                    const int rh = spn.r_first - (3 - j) * d;
-                    const int rt = spn.r_first + (8 * spn.n_oct + j) * d;
-                    uint32_t vh = 0u, vt = 0u;
-                    if (spn.n_oct > 0) {
-                        if (rh >= 0) vh = *reinterpret_cast<const uint32_t*>(plane + rh * 128 + ((((lane >> 2) ^ rh) & 7) << 4) + ((lane & 3) << 2));
-                        vt = *reinterpret_cast<const uint32_t*>(plane + rt * 128 + ((((lane >> 2) ^ rt) & 7) << 4) + ((lane & 3) << 2));
+                for (int j = 0; j < 3; ++j) { hd[sp][j] = 0u; tl[sp][j] = 0u; }
+                if (spn.n_oct > 0) {                       // warp-uniform: unused span slots cost one branch
+                    const uint8_t* lane_base = sX + spn.kc * Cfg::kPlane + ((lane & 3) << 2);
+                    const int c16 = lane >> 2;
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+                        const int rh = spn.r_first - (3 - j) * d;
+                        const int rt = spn.r_first + (8 * spn.n_oct + j) * d;
+                        if (rh >= 0) hd[sp][j] = *reinterpret_cast<const uint32_t*>(lane_base + rh * 128 + (((c16 ^ rh) & 7) << 4));
+                        tl[sp][j] = *reinterpret_cast<const uint32_t*>(lane_base + rt * 128 + (((c16 ^ rt) & 7) << 4));
                     }
-                    hd[sp][j] = vh; tl[sp][j] = vt;
                 }
             }
             __syncthreads();
