@@ -151,6 +151,12 @@ int snacb_debug_tap_copy(snacb_handle h, int idx, float* dst_host, size_t dst_el
  * No GPU needed. */
 int snacb_debug_chain_spans(int C, int16_t* out, int cap);
 
+/* The same for the two-group chain kernel (C = 64 or 128, fp16 operands; kernels_chain2.cu): warps 0-7 own the rows
+ * above the middle of the tile, warps 8-15 the rows below it.  out: int16[3][16][4][4] = {first_row, octets, chunk,
+ * flags}; flags bit 0: the span ends its class at the group boundary and reads its three tail rows late, bit 1: the
+ * span starts its class at the boundary and takes its three head rows from the stash.  Returns the tile height. */
+int snacb_debug_chain2_spans(int C, int16_t* out, int cap);
+
 /* ---------------------------------------------------------------------------------------------
  * Batcher: the multi-stream replacement of stream_audio's per-stream buffer policy
  * (modal_audio_stream.py:352-396), which decodes one stream at a time under a global lock.

@@ -15,7 +15,7 @@ import torch
 
 from oracle import glue_ref
 from tests._util import oracle_decode, pcm_of, snr_db
-from tts_inference_b200 import synth
+from tts_inference_b200 import SnacDecoder, synth
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -141,6 +141,24 @@ def test_fused_chain_block_outputs(decoder, oracle_model, B, F_):
         assert snr_db(rt[k], taps[k]) >= 45.0, (k, snr_db(rt[k], taps[k]))
     _, wu = decoder.decode(_cuda(tokens), raw_ids=True, noise=nz, precision="fp16", unfused=True, return_wave=True)
     assert snr_db(wu.cpu().numpy(), wf.cpu().numpy()) >= 45.0
+
+
+@pytest.mark.parametrize("B,F_,sliced", [(3, 4, False), (37, 4, True), (2, 16, False)])
+def test_two_group_chain_kernel_is_bit_identical(decoder, B, F_, sliced):
+    """kernels_chain2.cu (two warp groups half a layer apart, opt-in through SNACB_CHAIN2=1) performs every element's
+    arithmetic in the order of kernels_chain.cu: PCM and waveform are equal bit for bit, injected and in-kernel noise."""
+    import os
+    tokens = synth.make_tokens(B, F_, seed=60 + F_, bad_frac=0.01)
+    nz = [_cuda(n) for n in synth.make_noises(B, 4 * F_, seed=9)]
+    os.environ["SNACB_CHAIN2"] = "1"
+    try:
+        two = SnacDecoder(synth.make_state_dict(0), device=0)        # the switch is read when the handle is created
+    finally:
+        del os.environ["SNACB_CHAIN2"]
+    for kw in (dict(noise=nz), dict(seed=5)):
+        p0, w0 = decoder.decode(_cuda(tokens), raw_ids=True, precision="fp16", extract_slice=sliced, return_wave=True, **kw)
+        p1, w1 = two.decode(_cuda(tokens), raw_ids=True, precision="fp16", extract_slice=sliced, return_wave=True, **kw)
+        assert torch.equal(p0, p1) and torch.equal(w0, w1)
 
 
 # ------------------------------------------------------------------------------------ helper semantics

@@ -166,3 +166,78 @@ def test_chain_span_schedule(C):
                 assert r in written and work[r] == want[r], (C, d, kc, r)
     per_warp = sp[:, :nw, :, 1].sum(axis=2)
     assert per_warp.max() - per_warp.min() <= 1                             # balanced to one octet
+
+
+@pytest.mark.parametrize("C", [64, 128])
+def test_chain2_span_schedule(C):
+    """Schedule of the two-group chain kernel (kernels_chain2.cu), emulated on integers in the kernel's order: group 0
+    stashes its last 27 rows, pre-reads its in-group neighbours, rewrites its half in place and reads the tails that
+    lie below the group boundary LATE (group 1 has not touched its rows yet); then group 1 pre-reads its in-group
+    neighbours, takes the heads above the boundary from the stash and rewrites its half.  Every row whose result is
+    consumed downstream must come out of the layer's ORIGINAL inputs, for dilations 1, 3, 9."""
+    import ctypes as Ct
+    from tts_inference_b200 import _lib
+    lib = _lib.load()
+    buf = (Ct.c_int16 * (3 * 16 * 4 * 4))()
+    rows = lib.snacb_debug_chain2_spans(C, buf, len(buf))
+    assert rows % 256 == 0 and 256 <= rows <= 1024
+    half = rows // 2
+    sp = np.frombuffer(buf, dtype=np.int16).reshape(3, 16, 4, 4)
+    need_lo = {1: 4, 3: 13, 9: 40}
+    rng = np.random.default_rng(1)
+    LATE, STASH = 1, 2
+    for l, d in enumerate((1, 3, 9)):
+        for kc in range(C // 64):
+            x = rng.integers(1, 1 << 30, size=rows + 128).astype(np.int64)   # reads may run past the tile (garbage)
+            f = lambda r: int(sum((j + 2) * (x[r + (j - 3) * d] if 0 <= r + (j - 3) * d < rows else 0) for j in range(7)))
+            work = x.copy()
+            written = set()
+            stash = {r: work[r] for r in range(half - 27, half)}
+            for g in (0, 1):
+                spans = [(w, k, *map(int, sp[l, w, k])) for w in range(8 * g, 8 * g + 8) for k in range(4)
+                         if sp[l, w, k, 1] > 0 and sp[l, w, k, 2] == kc]
+                pre = {}
+                for (w, k, r0, noct, _, fl) in spans:                       # pre-reads before the group barrier
+                    assert r0 + 3 * d >= -8                                 # 1 KB of slack above the tile
+                    hrows = [r0 - (3 - j) * d for j in range(3)]
+                    trows = [r0 + (8 * noct + j) * d for j in range(3)]
+                    if g == 0:
+                        assert not fl & STASH
+                        assert r0 + (8 * noct - 1) * d < half               # group 0 never writes below the boundary
+                        assert bool(fl & LATE) == (trows[0] >= half)
+                    else:
+                        assert not fl & LATE and r0 >= half
+                        assert bool(fl & STASH) == (hrows[2] < half)
+                        if fl & STASH:
+                            assert all(half - 27 <= r < half for r in hrows)
+                    head = [stash[r] if fl & STASH else (work[r] if r >= 0 else 0) for r in hrows]
+                    tail = None if fl & LATE else [work[r] for r in trows]
+                    if not fl & STASH:
+                        assert all(r not in written for r in hrows if r >= 0)
+                    if not fl & LATE:
+                        assert all(r not in written for r in trows)
+                    pre[(w, k)] = (head, tail)
+                for (w, k, r0, noct, _, fl) in sorted(spans, key=lambda s_: rng.random()):   # any warp order
+                    head, tail = pre[(w, k)]
+                    n = 8 * noct
+                    if fl & LATE:                                           # read at the last octet, other group's rows
+                        trows = [r0 + (n + j) * d for j in range(3)]
+                        assert all(half <= r and r not in written for r in trows)
+                        tail = [work[r] for r in trows]
+                    get = lambda i: (head[i + 3] if i < 0 else tail[i - n] if i >= n else
+                                     (work[r0 + i * d] if 0 <= r0 + i * d else 0))
+                    win = [get(i) for i in range(-3, 3)]
+                    for q in range(noct):
+                        raw = [get(8 * q + kk + 3) if 8 * q + kk + 3 < n + 3 else 0 for kk in range(8)]
+                        for kk in range(8):
+                            win = win[-6:] + [raw[kk]]
+                            r = r0 + (8 * q + kk) * d
+                            if 0 <= r < rows:
+                                assert r not in written and (r < half) == (g == 0)
+                                written.add(r)
+                                work[r] = sum((j + 2) * win[j] for j in range(7))
+            for r in range(need_lo[d], rows - need_lo[d]):
+                assert r in written and work[r] == f(r), (C, d, kc, r)
+        for g in (0, 1):
+            per_warp = sp[l, 8 * g:8 * g + 8, :, 1].sum(axis=1)
+            assert per_warp.max() - per_warp.min() <= 1

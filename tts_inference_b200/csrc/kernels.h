@@ -67,4 +67,10 @@ void chain_build_spans(int C, ChainSpan (*spans)[kChainWarps][kChainSpans]);
 // d=3, d=9 weight maps box (64, C); all 128B-swizzled
 cudaError_t launch_chain(int half_fp16, const ChainArgs& a, const CUtensorMap* tm, int sm_count, cudaStream_t st);
 
+// ---- kernels_chain2.cu  (the same chain with two warp groups half a layer apart; fp16 operands)
+bool chain2_supported(int C);
+int chain2_tile_rows(int C);
+void chain2_build_spans(int C, ChainSpan (*spans)[kChainWarps][kChainSpans]);   // ChainSpan::pad carries the span flags
+cudaError_t launch_chain2(const ChainArgs& a, const CUtensorMap* tm, int sm_count, cudaStream_t st);
+
 }  // namespace snacb

@@ -46,6 +46,8 @@ struct BlockW {
     float* bias_cum;                    // [3][Cout] running sums of the ResidualUnit 1x1 biases (fused chain)
     bool chain[2];                      // the fused NoiseBlock + ResidualUnit chain covers this block ([0] bf16, [1] fp16)
     ChainSpan spans[3][kChainWarps][kChainSpans];
+    bool chain2;                        // fp16 only: the two-group chain kernel (kernels_chain2.cu) covers this block
+    ChainSpan spans2[3][kChainWarps][kChainSpans];
 };
 struct Tap {
     std::string name;
@@ -91,6 +93,8 @@ struct snacb_handle_s {
     std::vector<Tap> taps;
     uint64_t launches = 0, streams = 0;
     bool res_v1 = false;                // SNACB_RES_V1=1: use the non-persistent ResidualUnit kernel
+    bool no_chain2 = true;              // SNACB_CHAIN2=1 opts into the two-group chain kernel (kernels_chain2.cu): bit-identical
+                                        // output, measured 5 % (C = 128) / 40 % (C = 64) slower than k_chain
     bool no_chain = false;              // SNACB_NO_CHAIN=1: per-layer kernels instead of the fused chain
     bool no_convt_res = false;          // SNACB_NO_CONVT_RES=1: generic k_gemm_tc for every ConvTranspose
     bool no_trim = false;               // SNACB_NO_TRIM=1: sliced output still decodes every sample of the window
@@ -377,7 +381,8 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
             Rng y;                                                  // ConvTranspose output rows that must be valid
             const bool unfused = (flags & SNACB_UNFUSED) != 0 || h->no_chain;
             if (b.chain[hk] && !unfused) {
-                const int rows = chain_tile_rows(b.Cout) - 2 * kChainHalo;
+                const bool two = hk && b.chain2 && !h->no_chain2;
+                const int rows = (two ? chain2_tile_rows(b.Cout) : chain_tile_rows(b.Cout)) - 2 * kChainHalo;
                 const int n = (need.hi - need.lo + rows - 1) / rows;
                 post[bi] = Rng{need.lo, need.lo + n * rows};
                 y = clip(Rng{post[bi].lo - kChainHalo, post[bi].hi + kChainHalo}, Tb[bi]);
@@ -452,7 +457,8 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
             ca.alpha_next = bi < 3 ? h->blk[bi + 1].alpha : h->tail_alpha;
             ca.inv_next = bi < 3 ? h->blk[bi + 1].inv_alpha : h->tail_inv;
             ca.noise = noise ? noise[bi] : nullptr; ca.seed = seed; ca.noise_stage = bi; ca.stream_offset = stream_offset;
-            memcpy(ca.spans, b.spans, sizeof ca.spans);
+            const bool two = hk && b.chain2 && !h->no_chain2;
+            memcpy(ca.spans, two ? b.spans2 : b.spans, sizeof ca.spans);
             ca.tile_counter = h->tile_counter;
             CK(h, cudaMemsetAsync(h->tile_counter, 0, sizeof(int), st));
             const CUtensorMap *my, *moe, *mom, *mn;
@@ -473,10 +479,28 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
                 CK(h, cudaMalloc(reinterpret_cast<void**>(&ca.prof), 1024 * sizeof(unsigned long long)));
                 CK(h, cudaMemsetAsync(ca.prof, 0, 1024 * sizeof(unsigned long long), st));
             }
-            cudaError_t le = launch_chain(hk, ca, tm, h->sm_count, st);
+            cudaError_t le = two ? launch_chain2(ca, tm, h->sm_count, st) : launch_chain(hk, ca, tm, h->sm_count, st);
             prof_end(h, st);
             CK(h, le);
-            if (chain_prof) {
+            if (chain_prof && two) {
+                unsigned long long pv[64];
+                CK(h, cudaStreamSynchronize(st));
+                CK(h, cudaMemcpy(pv, ca.prof, sizeof pv, cudaMemcpyDeviceToHost));
+                CK(h, cudaFree(ca.prof));
+                const int rows = chain2_tile_rows(b.Cout) - 2 * kChainHalo;
+                const int tiles = S * (((ca.t_n > 0 ? ca.t_n : T) + rows - 1) / rows);
+                const int mine = (tiles + h->sm_count - 1) / h->sm_count;
+                for (int g = 0; g < 2; ++g) {
+                    const unsigned long long* q = pv + 32 * g;
+                    fprintf(stderr, "chain2 b%d C=%d group %d: cycles per tile (~%d tiles): nz+ld %llu noise %llu |", bi, b.Cout, g, mine,
+                            q[0] / mine, q[1] / mine);
+                    for (int l = 0; l < 3; ++l)
+                        fprintf(stderr, " L%d: pre %llu tok %llu pro %llu sync %llu mma+epi %llu |", l, q[2 + 5 * l] / mine,
+                                q[3 + 5 * l] / mine, q[4 + 5 * l] / mine, q[5 + 5 * l] / mine, q[6 + 5 * l] / mine);
+                    fprintf(stderr, " store/load issue %llu\n", q[17] / mine);
+                }
+            }
+            if (chain_prof && !two) {
                 unsigned long long pv[1024];
                 CK(h, cudaStreamSynchronize(st));
                 CK(h, cudaMemcpy(pv, ca.prof, sizeof pv, cudaMemcpyDeviceToHost));
@@ -714,6 +738,8 @@ int snacb_create(snacb_handle* out, const snacb_weights* w, int device) {
             RC(upload_f32(h, &b.bias_cum, bc));
             b.chain[0] = chain_supported(b.Cout, 0);
             b.chain[1] = chain_supported(b.Cout, 1);
+            b.chain2 = b.chain[1] && chain2_supported(b.Cout);
+            if (b.chain2) chain2_build_spans(b.Cout, b.spans2);
             if (b.chain[1]) {
                 chain_build_spans(b.Cout, b.spans);
                 const int C = b.Cout;
@@ -745,6 +771,7 @@ int snacb_create(snacb_handle* out, const snacb_weights* w, int device) {
     }
     if (const char* e = getenv("SNACB_RES_V1")) h->res_v1 = atoi(e) != 0;
     if (const char* e = getenv("SNACB_NO_CHAIN")) h->no_chain = atoi(e) != 0;
+    if (const char* e = getenv("SNACB_CHAIN2")) h->no_chain2 = atoi(e) == 0;
     if (const char* e = getenv("SNACB_NO_TRIM")) h->no_trim = atoi(e) != 0;
     if (const char* e = getenv("SNACB_NO_CONVT_RES")) h->no_convt_res = atoi(e) != 0;
     if (const char* e = getenv("SNACB_GROUP_MB")) {
@@ -918,6 +945,19 @@ int snacb_debug_chain_spans(int C, int16_t* out, int cap) {
                 o[0] = sp[l][w][k].r_first; o[1] = sp[l][w][k].n_oct; o[2] = sp[l][w][k].kc;
             }
     return chain_tile_rows(C) | (chain_warps(C) << 16);
+}
+
+int snacb_debug_chain2_spans(int C, int16_t* out, int cap) {
+    if (!out || !chain2_supported(C) || cap < 3 * kChainWarps * kChainSpans * 4) return SNACB_ERR_ARG;
+    ChainSpan sp[3][kChainWarps][kChainSpans];
+    chain2_build_spans(C, sp);
+    for (int l = 0; l < 3; ++l)
+        for (int w = 0; w < kChainWarps; ++w)
+            for (int k = 0; k < kChainSpans; ++k) {
+                int16_t* o = out + ((l * kChainWarps + w) * kChainSpans + k) * 4;
+                o[0] = sp[l][w][k].r_first; o[1] = sp[l][w][k].n_oct; o[2] = sp[l][w][k].kc; o[3] = sp[l][w][k].pad;
+            }
+    return chain2_tile_rows(C);
 }
 
 int snacb_debug_tap_count(snacb_handle h) { return h ? static_cast<int>(h->taps.size()) : SNACB_ERR_ARG; }
