@@ -327,6 +327,13 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
                     void* const* Wh, int Wrows, int Wcols) -> int {
         tile_boxes(a.Tin, &a.Tbox, &a.Wbox);
         if (a.Wbox != 1) a.t_n = 0;
+        else if (!f32 && a.t_n > 0 && a.t_n <= 64) {
+            // the trimmed rows of a stream fill at most half a 128-row tile (block-1 ConvTranspose of the sliced call:
+            // 57 of 128 rows): pack the same row range of several streams into one tile
+            int tb = 8;
+            while (tb < a.t_n) tb <<= 1;
+            a.Tbox = tb; a.Wbox = 128 / tb;
+        }
         a.seed = seed;
         a.stream_offset = stream_offset;
         h->launches++;
