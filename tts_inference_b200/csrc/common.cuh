@@ -85,6 +85,7 @@ struct ChainArgs {
     int noise_stage, stream_offset;
     ChainSpan spans[3][kChainWarps][kChainSpans];
     int* tile_counter;            // zeroed before the launch: tiles beyond the first gridDim.x are claimed dynamically
+    int snake_poly;               // fp16 prologue: bit 0 / bit 1 = snake1 / snake2 as a half2 polynomial instead of MUFU.SIN
     unsigned long long* prof;     // debug: 20 per-phase clock64 sums of CTA 0 / thread 0 (SNACB_CHAIN_PROF=1), else null
 };
 

@@ -91,18 +91,38 @@ struct ChainCfg {
 //   snake1(x) = (x'' + sin^2 x'') / alpha1          (inv_alpha * alpha = 1)
 // the depthwise taps carry alpha2 / alpha1 and its bias alpha2, so that the conv emits a'' = alpha2 * a directly, and
 //   snake2(a) = (a'' + sin^2 a'') / alpha2          with 1 / alpha2 folded into the 1x1 weights' K columns (host).
-template <int D, int ROWS>
+//
+// POLY (bit 0: snake1, bit 1: snake2): sin^2 on the FMA pipe in packed half2 instead of two MUFU.SIN in fp32 --
+//   t = x / pi, r = t - rint(t) (magic-number rounding, exact for |t| < 512), sin^2(pi r) = s P(s), s = r^2 <= 1/4,
+// P a degree-3 minimax fit (2.3e-5 max error, below half an fp16 ulp of the result).  Eight HFMA2-class instructions per
+// channel pair, mostly with immediate operands, against 2 converts + 2 FMUL.RZ + 2 MUFU.SIN + pack + HFMA2: the same
+// issue slots, no XU time (the XU pipe, 8 cycles per MUFU warp instruction, bounds the MUFU formulation: DESIGN.md 6).
+__device__ __forceinline__ __half2 snake_h2_poly(__half2 xh) {
+    const __half2 kInvPi = __float2half2_rn(0.318309886f), kMagic = __float2half2_rn(1536.f);
+    const __half2 m = __hfma2(xh, kInvPi, kMagic);
+    const __half2 n = __hsub2(m, kMagic);
+    const __half2 r = __hfma2(xh, kInvPi, __hneg2(n));
+    const __half2 s = __hmin2(__hmul2(r, r), __float2half2_rn(0.25f));      // |x| >= 1608 (no phase left in fp16): stay finite
+    __half2 p = __hfma2(__float2half2_rn(-22.99092533f), s, __float2half2_rn(41.29496355f));
+    p = __hfma2(p, s, __float2half2_rn(-32.35387252f));
+    p = __hfma2(p, s, __float2half2_rn(9.86667475f));
+    return __hfma2(p, s, xh);
+}
+
+template <int D, int ROWS, int POLY>
 __device__ __forceinline__ void span_half(uint8_t* plane, int r_oct, const int nq, const uint32_t h0, const uint32_t h1,
                                           const uint32_t h2, const uint32_t t0, const uint32_t t1, const uint32_t t2,
                                           const uint32_t (&swz)[8], const uint32_t* prm) {
     const uint4 q0 = *reinterpret_cast<const uint4*>(prm), q1 = *reinterpret_cast<const uint4*>(prm + 4);
     const __half2 bd = as_h2(q0.x);
     const __half2 w[7] = {as_h2(q0.y), as_h2(q0.z), as_h2(q0.w), as_h2(q1.x), as_h2(q1.y), as_h2(q1.z), as_h2(q1.w)};
-    auto snake = [&](__half2 xh) -> __half2 {      // xh + sin^2(xh)
+    auto snake_mufu = [&](__half2 xh) -> __half2 {      // xh + sin^2(xh)
         const float2 t = __half22float2(xh);
         const __half2 sh = __floats2half2_rn(__sinf(t.x), __sinf(t.y));
         return __hfma2(sh, sh, xh);
     };
+    auto snake = [&](__half2 xh) -> __half2 { return (POLY & 1) ? snake_h2_poly(xh) : snake_mufu(xh); };
+    auto snake2 = [&](__half2 xh) -> __half2 { return (POLY & 2) ? snake_h2_poly(xh) : snake_mufu(xh); };
     __half2 win[7];
     win[1] = snake(as_h2(h0)); win[2] = snake(as_h2(h1)); win[3] = snake(as_h2(h2));
     uint8_t* ob = plane + r_oct * 128;             // r_oct = 0 (mod 8): (row & 7) of step k is (k*D) & 7
@@ -127,7 +147,7 @@ __device__ __forceinline__ void span_half(uint8_t* plane, int r_oct, const int n
             __half2 acc = bd;
 #pragma unroll
             for (int j = 0; j < 7; ++j) acc = __hfma2(w[j], win[j], acc);
-            const __half2 o = snake(acc);
+            const __half2 o = snake2(acc);
             const int r = r_oct + k * D;
             if (static_cast<unsigned>(r) < static_cast<unsigned>(ROWS))
                 *reinterpret_cast<uint32_t*>(ob + k * D * 128 + swz[(k * D) & 7]) = as_u32(o);
@@ -191,7 +211,7 @@ enum { EPI_C_NOISE = 0, EPI_C_MID = 1, EPI_C_FINAL = 2 };
 }  // namespace
 
 // NW symmetric warps (prologue + epilogue); thread 0 also issues TMA / MMA.  16 warps: one CTA per SM; 8 warps: two.
-template <int C, int NB, int NW, typename HT>
+template <int C, int NB, int NW, typename HT, int POLY>
 __global__ void __launch_bounds__(NW * 32) __maxnreg__(NW == 8 ? 128 : 128 + 0 * NW)
 k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmOe,
         const __grid_constant__ CUtensorMap tmOm, const __grid_constant__ CUtensorMap tmWn,
@@ -542,9 +562,9 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
                 const uint32_t* prm = sPrm + ((l * (C / 2)) + kc * 32 + lane) * Cfg::kPrmWords;
                 uint8_t* plane = sX + kc * Cfg::kPlane;
                 if (kHalfMath) {
-                    if (d == 1) span_half<1, Cfg::kRows>(plane, r0, nq, hh[0], hh[1], hh[2], tt[0], tt[1], tt[2], swz, prm);
-                    else if (d == 3) span_half<3, Cfg::kRows>(plane, r0, nq, hh[0], hh[1], hh[2], tt[0], tt[1], tt[2], swz, prm);
-                    else span_half<9, Cfg::kRows>(plane, r0, nq, hh[0], hh[1], hh[2], tt[0], tt[1], tt[2], swz, prm);
+                    if (d == 1) span_half<1, Cfg::kRows, POLY>(plane, r0, nq, hh[0], hh[1], hh[2], tt[0], tt[1], tt[2], swz, prm);
+                    else if (d == 3) span_half<3, Cfg::kRows, POLY>(plane, r0, nq, hh[0], hh[1], hh[2], tt[0], tt[1], tt[2], swz, prm);
+                    else span_half<9, Cfg::kRows, POLY>(plane, r0, nq, hh[0], hh[1], hh[2], tt[0], tt[1], tt[2], swz, prm);
                 } else {
                     if (d == 1) span_f32<1, Cfg::kRows, HT>(plane, r0, nq, hh[0], hh[1], hh[2], tt[0], tt[1], tt[2], swz, prm);
                     else if (d == 3) span_f32<3, Cfg::kRows, HT>(plane, r0, nq, hh[0], hh[1], hh[2], tt[0], tt[1], tt[2], swz, prm);
@@ -612,14 +632,14 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
 
 namespace {
 
-template <int C, int NB, int NW, typename HT>
+template <int C, int NB, int NW, typename HT, int POLY = 0>
 cudaError_t launch_chain_t(const ChainArgs& a, const CUtensorMap* tm, int sm_count, cudaStream_t st) {
     using Cfg = ChainCfg<C, NB, std::is_same<HT, __half>::value>;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(k_chain<C, NB, NW, HT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
+        cudaError_t e = cudaFuncSetAttribute(k_chain<C, NB, NW, HT, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(k_chain<C, NB, NW, HT>, cudaFuncAttributePreferredSharedMemoryCarveout,
+        e = cudaFuncSetAttribute(k_chain<C, NB, NW, HT, POLY>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                  cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return e;
         attr_done = true;
@@ -630,15 +650,15 @@ cudaError_t launch_chain_t(const ChainArgs& a, const CUtensorMap* tm, int sm_cou
     const int grid = tiles < slots ? tiles : slots;
     if (a.prof != nullptr) {
         int occ = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_chain<C, NB, NW, HT>, NW * 32, Cfg::kSmem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_chain<C, NB, NW, HT, POLY>, NW * 32, Cfg::kSmem);
         cudaFuncAttributes fa;
-        cudaFuncGetAttributes(&fa, k_chain<C, NB, NW, HT>);
+        cudaFuncGetAttributes(&fa, k_chain<C, NB, NW, HT, POLY>);
         int occ_nosmem = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_nosmem, k_chain<C, NB, NW, HT>, NW * 32, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_nosmem, k_chain<C, NB, NW, HT, POLY>, NW * 32, 0);
         fprintf(stderr, "k_chain<%d,%d,%d>: grid %d, smem %d (+%zu static), regs %d, occupancy %d CTA/SM (%d without smem)\n", C, NB, NW,
                 grid, Cfg::kSmem, fa.sharedSizeBytes, fa.numRegs, occ, occ_nosmem);
     }
-    k_chain<C, NB, NW, HT><<<grid, NW * 32, Cfg::kSmem, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], tm[6], a, tiles);
+    k_chain<C, NB, NW, HT, POLY><<<grid, NW * 32, Cfg::kSmem, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], tm[6], a, tiles);
     return cudaGetLastError();
 }
 
@@ -698,13 +718,21 @@ void chain_build_spans(int C, ChainSpan (*spans)[kChainWarps][kChainSpans]) {
 // tm: [0] y load map, box (64, 128, 1); [1] out store map, box (64, 88, 1); [2] out store map, box (64, 128, 1);
 //     [3..6] noise 1x1, res d=1, d=3, d=9 weight maps, box (64, C); all 128B-swizzled
 cudaError_t launch_chain(int half_fp16, const ChainArgs& a, const CUtensorMap* tm, int sm_count, cudaStream_t st) {
-    if (a.C == 64)
-        return half_fp16 ? launch_chain_t<64, kNB64, kNW64, __half>(a, tm, sm_count, st)
-                         : launch_chain_t<64, kNB64, kNW64, __nv_bfloat16>(a, tm, sm_count, st);
-    if (a.C == 128)
-        return half_fp16 ? launch_chain_t<128, kNB128, kNW128, __half>(a, tm, sm_count, st)
-                         : launch_chain_t<128, kNB128, kNW128, __nv_bfloat16>(a, tm, sm_count, st);
-    if (a.C == 256 && half_fp16) return launch_chain_t<256, kNB256, kNW256, __half>(a, tm, sm_count, st);
+    if (half_fp16) {
+        // a.snake_poly: 0 = both Snakes through MUFU.SIN, 2 = snake2 as a half2 polynomial, 3 = both (see span_half)
+#define SNACB_CHAIN_POLY(P)                                                                                      \
+        if (a.C == 64) return launch_chain_t<64, kNB64, kNW64, __half, P>(a, tm, sm_count, st);                   \
+        if (a.C == 128) return launch_chain_t<128, kNB128, kNW128, __half, P>(a, tm, sm_count, st);               \
+        if (a.C == 256) return launch_chain_t<256, kNB256, kNW256, __half, P>(a, tm, sm_count, st);               \
+        return cudaErrorInvalidValue;
+        if (a.snake_poly == 3) { SNACB_CHAIN_POLY(3) }
+        if (a.snake_poly == 2) { SNACB_CHAIN_POLY(2) }
+        if (a.snake_poly == 1) { SNACB_CHAIN_POLY(1) }
+        SNACB_CHAIN_POLY(0)
+#undef SNACB_CHAIN_POLY
+    }
+    if (a.C == 64) return launch_chain_t<64, kNB64, kNW64, __nv_bfloat16>(a, tm, sm_count, st);
+    if (a.C == 128) return launch_chain_t<128, kNB128, kNW128, __nv_bfloat16>(a, tm, sm_count, st);
     return cudaErrorInvalidValue;
 }
 

@@ -95,6 +95,7 @@ struct snacb_handle_s {
     bool res_v1 = false;                // SNACB_RES_V1=1: use the non-persistent ResidualUnit kernel
     bool no_chain2 = true;              // SNACB_CHAIN2=1 opts into the two-group chain kernel (kernels_chain2.cu): bit-identical
                                         // output, measured 5 % (C = 128) / 40 % (C = 64) slower than k_chain
+    int snake_poly = 0;                 // SNACB_SNAKE_POLY: fp16 chain prologue, bit 0 / 1 = snake1 / snake2 as a half2 polynomial
     bool no_chain = false;              // SNACB_NO_CHAIN=1: per-layer kernels instead of the fused chain
     bool no_convt_res = false;          // SNACB_NO_CONVT_RES=1: generic k_gemm_tc for every ConvTranspose
     bool no_trim = false;               // SNACB_NO_TRIM=1: sliced output still decodes every sample of the window
@@ -467,6 +468,7 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
             const bool two = hk && b.chain2 && !h->no_chain2;
             memcpy(ca.spans, two ? b.spans2 : b.spans, sizeof ca.spans);
             ca.tile_counter = h->tile_counter;
+            ca.snake_poly = h->snake_poly;
             CK(h, cudaMemsetAsync(h->tile_counter, 0, sizeof(int), st));
             const CUtensorMap *my, *moe, *mom, *mn;
             int rc = act_map(h, &my, oth, b.Cout, T, S, 128, 1, hk, 1);
@@ -778,6 +780,7 @@ int snacb_create(snacb_handle* out, const snacb_weights* w, int device) {
     }
     if (const char* e = getenv("SNACB_RES_V1")) h->res_v1 = atoi(e) != 0;
     if (const char* e = getenv("SNACB_NO_CHAIN")) h->no_chain = atoi(e) != 0;
+    if (const char* e = getenv("SNACB_SNAKE_POLY")) h->snake_poly = atoi(e) & 3;
     if (const char* e = getenv("SNACB_CHAIN2")) h->no_chain2 = atoi(e) == 0;
     if (const char* e = getenv("SNACB_NO_TRIM")) h->no_trim = atoi(e) != 0;
     if (const char* e = getenv("SNACB_NO_CONVT_RES")) h->no_convt_res = atoi(e) != 0;
