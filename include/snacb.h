@@ -27,6 +27,7 @@ extern "C" {
 
 typedef struct snacb_handle_s* snacb_handle;
 typedef struct snacb_batcher_s* snacb_batcher;
+typedef struct snacb_ingest_s* snacb_ingest;
 
 typedef enum {
     SNACB_OK = 0,
@@ -177,6 +178,52 @@ int snacb_batcher_end(snacb_batcher b, uint64_t stream_id);
 int snacb_batcher_flush(snacb_batcher b, uint64_t seed, int max_chunks, uint64_t* ids, int64_t* offsets,
                         int32_t* lengths, int16_t* pcm_host, size_t pcm_capacity);
 int snacb_batcher_pending(snacb_batcher b);     /* windows ready to decode right now */
+
+/* ---------------------------------------------------------------------------------------------
+ * Device-side token ingest: the LLM loop's sampled token ids go from a device
+ * tensor straight into ready decode windows -- no Python ints, no per-token host work.  Per stream it restates
+ *   generate_audio_tokens  (modal_audio_stream.py:313-333; same rule tensorrt_tts/inference.py:231-241):
+ *                          skip everything up to and including the first TOKEN_SOS (128257), stop at the first
+ *                          TOKEN_EOS (128258), pass every other id on;
+ *   stream_audio           (modal_audio_stream.py:352-396): whenever 28 ids are buffered pop them as one window;
+ *                          when the stream ends emit the remaining whole frames (1..3) and drop the rest.
+ * Stream slots are indices 0..max_streams-1; a slot is reusable after snacb_ingest_reset.  Ids stay RAW (decode the
+ * windows with SNACB_RAW_IDS).  Integer work, bit-exact against oracle/ingest_ref.py and the golden vectors
+ * produced by the reference's own two functions (tests/golden/make_golden_ingest.py).
+ * --------------------------------------------------------------------------------------------- */
+int snacb_ingest_create(snacb_ingest* out, int device, int max_streams);
+void snacb_ingest_destroy(snacb_ingest g);
+/* Forget streams [first, first + n): state back to "waiting for TOKEN_SOS", buffer emptied. */
+int snacb_ingest_reset(snacb_ingest g, int first, int n, void* stream);
+/* Rows of win_tok / win_stream that one step over S streams x n_tok tokens can fill. */
+int snacb_ingest_window_capacity(int S, int n_tok);
+/* One step of the LLM loop for streams 0..S-1.
+ *   tok          [S][n_tok] int32 token ids sampled this step (device)
+ *   n_valid      optional [S]: how many of a stream's n_tok ids are real (NULL: all)
+ *   finish       optional [S] bytes: the stream's generator ended without TOKEN_EOS (max_tokens) -> flush it
+ *   win_tok      [win_cap][28], win_stream [win_cap]: full windows in (stream, time) order
+ *   tail_tok     [S][21] zero padded, tail_stream [S], tail_frames [S]: end-of-stream remainders of 1..3 frames
+ *   counts       [2]: number of full windows, number of tails written by this step
+ * win_cap must be >= snacb_ingest_window_capacity(S, n_tok).  Asynchronous on `stream`. */
+int snacb_ingest_step(snacb_ingest g, const int32_t* tok, int S, int n_tok, const int32_t* n_valid,
+                      const uint8_t* finish, int32_t* win_tok, int32_t* win_stream, int win_cap, int32_t* tail_tok,
+                      int32_t* tail_stream, int32_t* tail_frames, int32_t* counts, void* stream);
+/* Debug / tests: copy per-stream state (0 waiting for SOS, 1 in speech, 2 ended) and buffered-id count to the host. */
+int snacb_ingest_state(snacb_ingest g, int32_t* state_host, int32_t* count_host, int n);
+
+/* ---------------------------------------------------------------------------------------------
+ * Egress formats, device to device, byte-exact against the Python stdlib calls
+ * the reference makes.
+ *   snacb_pcm_to_base64  n_chunks PCM chunks of `samples` int16 each -> n_chunks strings of
+ *                        snacb_base64_len(2*samples) ASCII bytes (RFC 4648, '=' padded, no terminator):
+ *                        base64.b64encode(audio_chunk) of the /ws/audio endpoint (modal_audio_stream.py:483-487)
+ *   snacb_pcm_to_wav     n PCM strings -> n records of 44 + 2*samples bytes: the RIFF/WAVE file that
+ *                        wave.open(..., "wb") writes for 1 channel, 2 bytes per sample, `sample_rate`
+ *                        (modal_audio_stream.py:561-566, 650-657)
+ * --------------------------------------------------------------------------------------------- */
+long long snacb_base64_len(long long bytes);
+int snacb_pcm_to_base64(const int16_t* pcm, long long n_chunks, long long samples, uint8_t* out, void* stream);
+int snacb_pcm_to_wav(const int16_t* pcm, long long n, long long samples, int sample_rate, uint8_t* out, void* stream);
 
 #ifdef __cplusplus
 }

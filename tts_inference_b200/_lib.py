@@ -39,6 +39,8 @@ EXPORTS = [
     "snacb_profile", "snacb_profile_report", "snacb_debug_tap_count", "snacb_debug_tap_info", "snacb_debug_tap_copy", "snacb_debug_chain_spans", "snacb_debug_chain2_spans",
     "snacb_batcher_create", "snacb_batcher_destroy", "snacb_batcher_push", "snacb_batcher_end",
     "snacb_batcher_flush", "snacb_batcher_pending",
+    "snacb_ingest_create", "snacb_ingest_destroy", "snacb_ingest_reset", "snacb_ingest_window_capacity",
+    "snacb_ingest_step", "snacb_ingest_state", "snacb_base64_len", "snacb_pcm_to_base64", "snacb_pcm_to_wav",
 ]
 
 _lib = None
@@ -80,6 +82,17 @@ def load() -> C.CDLL:
     lib.snacb_batcher_end.argtypes = [vp, u64]
     lib.snacb_batcher_flush.argtypes = [vp, u64, C.c_int, vp, vp, vp, vp, C.c_size_t]
     lib.snacb_batcher_pending.argtypes = [vp]
+    lib.snacb_ingest_create.argtypes = [C.POINTER(vp), C.c_int, C.c_int]
+    lib.snacb_ingest_destroy.argtypes = [vp]
+    lib.snacb_ingest_destroy.restype = None
+    lib.snacb_ingest_reset.argtypes = [vp, C.c_int, C.c_int, vp]
+    lib.snacb_ingest_window_capacity.argtypes = [C.c_int, C.c_int]
+    lib.snacb_ingest_step.argtypes = [vp, i32p, C.c_int, C.c_int, i32p, vp, i32p, i32p, C.c_int, i32p, i32p, i32p, i32p, vp]
+    lib.snacb_ingest_state.argtypes = [vp, vp, vp, C.c_int]
+    lib.snacb_base64_len.argtypes = [C.c_longlong]
+    lib.snacb_base64_len.restype = C.c_longlong
+    lib.snacb_pcm_to_base64.argtypes = [i16p, C.c_longlong, C.c_longlong, vp, vp]
+    lib.snacb_pcm_to_wav.argtypes = [i16p, C.c_longlong, C.c_longlong, C.c_int, vp, vp]
     _lib = lib
     return lib
 
