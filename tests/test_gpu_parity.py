@@ -223,6 +223,19 @@ def test_grouping_and_batch_independence(decoder, prec):
     assert torch.equal(one[0], big[5])
 
 
+@pytest.mark.parametrize("prec", ["fp16", "bf16"])
+@pytest.mark.parametrize("B,F_,sliced", [(40, 4, False), (301, 4, True), (3, 64, False), (5, 37, False)])
+def test_bulk_tail_kernel_is_bit_identical(decoder, monkeypatch, prec, B, F_, sliced):
+    """k_tail_bulk (persistent, cp.async.bulk ring; large batches) against k_tail (one load per lane and row)."""
+    tokens = _cuda(synth.make_tokens(B, F_, seed=11))
+    new = decoder.decode(tokens, raw_ids=True, seed=4, precision=prec, extract_slice=sliced, return_wave=True)
+    monkeypatch.setenv("SNACB_TAIL_V1", "1")
+    old = decoder.decode(tokens, raw_ids=True, seed=4, precision=prec, extract_slice=sliced, return_wave=True)
+    torch.cuda.synchronize()
+    assert torch.equal(new[0], old[0]) and torch.equal(new[1], old[1])
+    assert int((new[0] != 0).sum()) > new[0].numel() // 2
+
+
 def test_golden_vectors(decoder):
     """Committed fixtures: bytes the REFERENCE's convert_to_audio returned with the oracle as SNAC."""
     z = np.load(os.path.join(GOLD, "decode_golden.npz"))

@@ -6,8 +6,11 @@
 //   * k_tail          final conv 64->1 k7 + tanh + slice + int16 quantise
 //   * k_to_f32        debug taps
 // Activations are channel-last: [stream][time][channel].
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
+#include "ptx.cuh"
 
 namespace snacb {
 
@@ -293,31 +296,20 @@ __device__ __forceinline__ float2 load_pair(const __nv_bfloat16* p) {
 // One warp = 32 consecutive output samples of one stream; lane = channel pair while the 7-tap window slides down
 // the rows (each input row is loaded once, 128 B per warp), every lane keeping its 2-channel partial sum of all 32
 // samples in registers; one recursive-halving exchange (31 shuffles) then leaves sample `lane` summed in lane `lane`.
-template <typename InT>
-__global__ void __launch_bounds__(256)
-k_tail(const InT* __restrict__ a, int T, int t_begin, int n_out, const float* __restrict__ w /*[7][64]*/, float bias,
-       int16_t* __restrict__ pcm, float* __restrict__ wave) {
-    const int s = blockIdx.y;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int base = t_begin + blockIdx.x * 256 + warp * 32;
-    if (base >= t_begin + n_out) return;
-    float2 wj[7];
+// rows(i), i < 38: channel pair of this lane in input row base - 3 + i (zero outside the stream).  Returns sample
+// base + lane in lane `lane` (before bias / tanh).  The arithmetic (tap order, lane tree) is the same wherever the
+// rows come from, so every tail kernel below yields the same bits.
+template <typename RowFn>
+__device__ __forceinline__ float tail_chunk(const float2 (&wj)[7], int lane, RowFn rows) {
+    float2 r[38];
 #pragma unroll
-    for (int j = 0; j < 7; ++j) wj[j] = make_float2(w[j * 64 + 2 * lane], w[j * 64 + 2 * lane + 1]);
-    const InT* src = a + static_cast<size_t>(s) * T * 64 + 2 * lane;
-    auto load_row = [&](int t) -> float2 {     // one 4-byte (16-bit types) or 8-byte load per lane and row
-        if (t < 0 || t >= T) return make_float2(0.f, 0.f);
-        return load_pair(src + static_cast<size_t>(t) * 64);
-    };
-    float2 rows[38];                       // the 32 + 6 input rows of this warp's samples, issued back to back
-#pragma unroll
-    for (int i = 0; i < 38; ++i) rows[i] = load_row(base - 3 + i);
+    for (int i = 0; i < 38; ++i) r[i] = rows(i);
     float v[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
         float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int j = 0; j < 7; ++j) acc = ffma2(wj[j], rows[i + j], acc);
+        for (int j = 0; j < 7; ++j) acc = ffma2(wj[j], r[i + j], acc);
         v[i] = acc.x + acc.y;
     }
     // transpose-reduce: after the step with offset o, a lane keeps the half of its values whose sample index has
@@ -332,18 +324,125 @@ k_tail(const InT* __restrict__ a, int T, int t_begin, int n_out, const float* __
             v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
         }
     }
+    return v[0];
+}
+
+template <typename InT>
+__global__ void __launch_bounds__(256)
+k_tail(const InT* __restrict__ a, int T, int t_begin, int n_out, const float* __restrict__ w /*[7][64]*/, float bias,
+       int16_t* __restrict__ pcm, float* __restrict__ wave) {
+    const int s = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int base = t_begin + blockIdx.x * 256 + warp * 32;
+    if (base >= t_begin + n_out) return;
+    float2 wj[7];
+#pragma unroll
+    for (int j = 0; j < 7; ++j) wj[j] = make_float2(w[j * 64 + 2 * lane], w[j * 64 + 2 * lane + 1]);
+    const InT* src = a + static_cast<size_t>(s) * T * 64 + 2 * lane;
+    const float v = tail_chunk(wj, lane, [&](int i) -> float2 {     // one 4-byte (16-bit types) or 8-byte load per lane and row
+        const int t = base - 3 + i;
+        if (t < 0 || t >= T) return make_float2(0.f, 0.f);
+        return load_pair(src + static_cast<size_t>(t) * 64);
+    });
     const int t = base + lane;
     if (t < t_begin + n_out && t < T) {
-        const float r = tanhf(v[0] + bias);
+        const float r = tanhf(v + bias);
         const size_t o = static_cast<size_t>(s) * n_out + (t - t_begin);
         pcm[o] = pcm16(r);
         if (wave) wave[o] = r;
     }
 }
 
+// The same for large batches of 16-bit activations, shaped for HBM bandwidth: persistent CTAs, the 262 input rows
+// (33.5 KB, contiguous in the channel-last layout) of a 256-sample tile arrive by ONE bulk async copy (cp.async.bulk,
+// mbarrier completion) into a 3-deep shared-memory ring, so ~100 KB per CTA are in flight while the 8 warps compute
+// from shared memory (lane = channel pair: 128 contiguous bytes per row, conflict-free).
+constexpr int kTailTile = 256;
+constexpr int kTailRows = kTailTile + 6;
+constexpr int kTailStages = 3;
+constexpr int kTailStageBytes = kTailRows * 128;
+constexpr int kTailSmem = kTailStages * kTailStageBytes + 64 + 128;
+
+template <typename InT>
+__global__ void __launch_bounds__(256, 2)
+k_tail_bulk(const InT* __restrict__ a, int T, int t_begin, int n_out, const float* __restrict__ w, float bias,
+            int16_t* __restrict__ pcm, float* __restrict__ wave, int tiles_per_stream, int num_tiles) {
+    static_assert(sizeof(InT) == 2, "16-bit activations");
+    extern __shared__ __align__(128) uint8_t tail_smem[];
+    uint8_t* ring = tail_smem + ((128u - (ptx::smem_u32(tail_smem) & 127u)) & 127u);
+    uint64_t* full = reinterpret_cast<uint64_t*>(ring + kTailStages * kTailStageBytes);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kTailStages; ++i) ptx::mbar_init(&full[i], 1);
+        ptx::fence_barrier_init();
+    }
+    __syncthreads();
+    float2 wj[7];
+#pragma unroll
+    for (int j = 0; j < 7; ++j) wj[j] = make_float2(w[j * 64 + 2 * lane], w[j * 64 + 2 * lane + 1]);
+
+    auto issue = [&](int tile, int stage) {               // thread 0: rows [base - 3, base + 259) clipped to the stream
+        const int s = tile / tiles_per_stream, base = t_begin + (tile % tiles_per_stream) * kTailTile;
+        const int lo = max(base - 3, 0), hi = min(base + kTailTile + 3, T);
+        const uint32_t bytes = static_cast<uint32_t>(hi - lo) * 128u;
+        const InT* src = a + (static_cast<size_t>(s) * T + lo) * 64;
+        uint8_t* dst = ring + stage * kTailStageBytes + (lo - (base - 3)) * 128;
+        ptx::mbar_expect_tx(&full[stage], bytes);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(ptx::smem_u32(dst)), "l"(src), "r"(bytes), "r"(ptx::smem_u32(&full[stage])) : "memory");
+    };
+    if (threadIdx.x == 0)
+        for (int k = 0; k < kTailStages; ++k) {
+            const int tile = blockIdx.x + k * gridDim.x;
+            if (tile < num_tiles) issue(tile, k);
+        }
+    int k = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++k) {
+        const int stage = k % kTailStages;
+        const int s = tile / tiles_per_stream, tile_base = t_begin + (tile % tiles_per_stream) * kTailTile;
+        ptx::mbar_wait(&full[stage], (k / kTailStages) & 1);
+        const int base = tile_base + warp * 32;
+        if (base < t_begin + n_out) {
+            const uint8_t* rows = ring + stage * kTailStageBytes + (warp * 32) * 128 + lane * 4;
+            const float v = tail_chunk(wj, lane, [&](int i) -> float2 {
+                const int t = base - 3 + i;
+                if (t < 0 || t >= T) return make_float2(0.f, 0.f);
+                return load_pair(reinterpret_cast<const InT*>(rows + i * 128));
+            });
+            const int t = base + lane;
+            if (t < t_begin + n_out && t < T) {
+                const float r = tanhf(v + bias);
+                const size_t o = static_cast<size_t>(s) * n_out + (t - t_begin);
+                pcm[o] = pcm16(r);
+                if (wave) wave[o] = r;
+            }
+        }
+        __syncthreads();                                   // every warp is done with the stage: refill it
+        if (threadIdx.x == 0) {
+            const int nxt = tile + kTailStages * gridDim.x;
+            if (nxt < num_tiles) issue(nxt, stage);
+        }
+    }
+}
+
 template <typename InT>
 void launch_tail(const InT* a, int S, int T, int t_begin, int n_out, const float* w, float bias, int16_t* pcm,
                  float* wave, cudaStream_t st) {
+    if constexpr (sizeof(InT) == 2) {
+        const int tps = (n_out + kTailTile - 1) / kTailTile;
+        const long long tiles = static_cast<long long>(S) * tps;
+        const char* v1 = getenv("SNACB_TAIL_V1");          // A/B switch (tests): the per-warp-load kernel for every size
+        if (tiles >= 2 * 148 && tiles < (1LL << 31) && !(v1 && v1[0] == '1')) {
+            static bool attr_done = false;
+            if (!attr_done) {
+                cudaFuncSetAttribute(k_tail_bulk<InT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTailSmem);
+                attr_done = true;
+            }
+            k_tail_bulk<InT><<<2 * 148, 256, kTailSmem, st>>>(a, T, t_begin, n_out, w, bias, pcm, wave, tps,
+                                                               static_cast<int>(tiles));
+            return;
+        }
+    }
     dim3 grid((n_out + 255) / 256, S);
     k_tail<InT><<<grid, 256, 0, st>>>(a, T, t_begin, n_out, w, bias, pcm, wave);
 }
