@@ -264,17 +264,39 @@ def main():
     clocks = sampler.stop()
 
     # ------------------------------------------------------------------ e2e (host buffers, copies inside)
-    for i in range(2):
-        dec.decode_host_ptr(tok_pin.data_ptr(), B, 28, pcm_pin.data_ptr(), raw_ids=True, extract_slice=False,
-                            seed=i, precision=args.precision)
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        dec.decode_host_ptr(tok_pin.data_ptr(), B, 28, pcm_pin.data_ptr(), raw_ids=True, extract_slice=False,
-                            seed=200 + i, precision=args.precision)
-    e2e_s = time.perf_counter() - t0
-    barrier()
-    assert int((pcm_pin != 0).sum()) > B * 2048, "e2e output looks empty"
+    # every step copies ITS tokens host->device and ITS PCM device->host (pinned buffers); the serving-loop form of the
+    # call keeps one step in flight, so the copy-out of step i overlaps the decode of step i + 1
+    # (snacb_decode_host_submit / _wait, include/snacb.h).  The blocking call is timed beside it.
+    def e2e_loop(pins, sliced, seed0):
+        for i in range(2):
+            dec.decode_host_ptr(tok_pin.data_ptr(), B, 28, pins[0].data_ptr(), raw_ids=True, extract_slice=sliced,
+                                seed=i, precision=args.precision)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            dec.decode_host_ptr(tok_pin.data_ptr(), B, 28, pins[0].data_ptr(), raw_ids=True, extract_slice=sliced,
+                                seed=seed0 + i, precision=args.precision)
+        blocking_s = time.perf_counter() - t0
+        barrier()
+        for i in range(2):                                   # warm-up of the pipelined form (allocates its two staging slots)
+            dec.submit_host_ptr(tok_pin.data_ptr(), B, 28, pins[i & 1].data_ptr(), raw_ids=True, extract_slice=sliced,
+                                seed=i, precision=args.precision)
+        dec.wait_host(); dec.wait_host()
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            dec.submit_host_ptr(tok_pin.data_ptr(), B, 28, pins[i & 1].data_ptr(), raw_ids=True, extract_slice=sliced,
+                                seed=seed0 + 50 + i, precision=args.precision)
+            if i:
+                dec.wait_host()
+        dec.wait_host()
+        pipelined_s = time.perf_counter() - t0
+        barrier()
+        return blocking_s, pipelined_s
+
+    pcm_pin2 = torch.empty((B, WINDOW_SAMPLES), dtype=torch.int16).pin_memory()
+    e2e_blocking_s, e2e_s = e2e_loop((pcm_pin, pcm_pin2), False, 200)
+    assert int((pcm_pin != 0).sum()) > B * 2048 and int((pcm_pin2 != 0).sum()) > B * 2048, "e2e output looks empty"
 
     # ------------------------------------------------------------------ sliding-window call (sliced, trimmed)
     for i in range(3):
@@ -288,21 +310,14 @@ def main():
         ev_sl[i][1].record()
     barrier()
     sl_ms = sum(a.elapsed_time(b) for a, b in ev_sl)
-    for i in range(2):
-        dec.decode_host_ptr(tok_pin.data_ptr(), B, 28, pcm_pin_sl.data_ptr(), raw_ids=True, extract_slice=True,
-                            seed=i, precision=args.precision)
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        dec.decode_host_ptr(tok_pin.data_ptr(), B, 28, pcm_pin_sl.data_ptr(), raw_ids=True, extract_slice=True,
-                            seed=500 + i, precision=args.precision)
-    sl_e2e_s = time.perf_counter() - t0
-    barrier()
+    pcm_pin_sl2 = torch.empty((B, 2048), dtype=torch.int16).pin_memory()
+    _, sl_e2e_s = e2e_loop((pcm_pin_sl, pcm_pin_sl2), True, 500)
 
     # max over ranks (tts_inference_b200.dist: all_reduce MAX, identity at N=1)
     from tts_inference_b200.dist import max_over_ranks
     dev_ms = max_over_ranks(dev_ms, device="cuda")
     e2e_ms = max_over_ranks(e2e_s * 1e3, device="cuda")
+    e2e_blocking_s = max_over_ranks(e2e_blocking_s * 1e3, device="cuda") * 1e-3
     sl_ms = max_over_ranks(sl_ms, device="cuda")
     sl_e2e_ms = max_over_ranks(sl_e2e_s * 1e3, device="cuda")
 
@@ -379,7 +394,9 @@ def main():
                        "timing": "CUDA events per step, L2 flushed (256 MiB memset) between timed steps",
                        "windows_per_s": value * SR / WINDOW_SAMPLES,
                        "wall_s_timed_region": t_wall},
-            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": B * 28 * 4, "d2h_bytes_per_step": B * WINDOW_SAMPLES * 2},
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": B * 28 * 4, "d2h_bytes_per_step": B * WINDOW_SAMPLES * 2,
+                    "call": "snacb_decode_host_submit / _wait (one step in flight: copy-out of step i overlaps decode of step i+1)",
+                    "blocking_call_value": windows * WINDOW_SAMPLES / SR / max(e2e_blocking_s, 1e-9)},
             "sliding_window_mode": {
                 "what": "same windows through the extract_slice=True call: samples [2048:4096] out, only their receptive "
                         "field computed (bit-identical to the full decode's slice; tests/test_gpu_parity.py::test_slice_semantics)",

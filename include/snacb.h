@@ -121,6 +121,15 @@ int snacb_decode(snacb_handle h, const int32_t* tok, int B, int tok_stride, int 
 int snacb_decode_host(snacb_handle h, const int32_t* tok_host, int B, int tok_stride, int frames, int flags,
                       uint64_t seed, int16_t* pcm_host);
 
+/* The same boundary, pipelined for a serving loop: _submit queues copy-in + decode + copy-out and returns; _wait
+ * blocks until the OLDEST outstanding submit has its PCM in `pcm_host`.  At most two submits may be outstanding.
+ * Calling submit(step i+1) and then wait() (for step i) every step overlaps the device->host copy of step i (copy stream) with the
+ * decode of step i+1; each step still pays its own host<->device copies.  Use pinned host buffers (pageable ones make
+ * the copies synchronous), and a distinct `pcm_host` for the two steps in flight. */
+int snacb_decode_host_submit(snacb_handle h, const int32_t* tok_host, int B, int tok_stride, int frames, int flags,
+                             uint64_t seed, int16_t* pcm_host);
+int snacb_decode_host_wait(snacb_handle h);
+
 /* Number of PCM samples per stream that snacb_decode writes for (frames, flags). */
 int snacb_samples_out(int frames, int flags);
 

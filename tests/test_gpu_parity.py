@@ -15,7 +15,7 @@ import torch
 
 from oracle import glue_ref
 from tests._util import oracle_decode, pcm_of, snr_db
-from tts_inference_b200 import SnacDecoder, synth
+from tts_inference_b200 import SnacDecoder, SnacbError, synth
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -259,6 +259,27 @@ def test_decode_host_equals_device(decoder):
     a = decoder.decode_host(tokens, raw_ids=True, extract_slice=True, seed=4)
     b = decoder.decode(_cuda(tokens), raw_ids=True, extract_slice=True, seed=4)
     assert np.array_equal(a, b.cpu().numpy())
+
+
+def test_pipelined_host_boundary(decoder):
+    """snacb_decode_host_submit / _wait: same bytes as the blocking call, two steps in flight at most."""
+    steps = [synth.make_tokens(33, 4, seed=20 + i) for i in range(5)]
+    want = [decoder.decode_host(t, raw_ids=True, seed=9 + i) for i, t in enumerate(steps)]
+    toks = [torch.from_numpy(t).pin_memory() for t in steps]
+    outs = [torch.zeros((33, 8192), dtype=torch.int16).pin_memory() for _ in steps]
+    with pytest.raises(SnacbError):
+        decoder.wait_host()                                           # nothing outstanding
+    for i in range(len(steps)):
+        decoder.submit_host_ptr(toks[i].data_ptr(), 33, 28, outs[i].data_ptr(), raw_ids=True, seed=9 + i)
+        if i:
+            decoder.wait_host()
+            assert np.array_equal(outs[i - 1].numpy(), want[i - 1])
+    decoder.submit_host_ptr(toks[0].data_ptr(), 33, 28, outs[0].data_ptr(), raw_ids=True, seed=9)
+    with pytest.raises(SnacbError):                                   # a third submit needs a wait first
+        decoder.submit_host_ptr(toks[1].data_ptr(), 33, 28, outs[1].data_ptr(), raw_ids=True, seed=10)
+    decoder.wait_host()
+    decoder.wait_host()
+    assert np.array_equal(outs[-1].numpy(), want[-1]) and np.array_equal(outs[0].numpy(), want[0])
 
 
 def test_decode_host_large_batch_equals_device(decoder):

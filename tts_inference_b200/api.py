@@ -168,6 +168,17 @@ class SnacDecoder:
                                          self._flags(raw_ids, extract_slice, precision), C.c_uint64(seed), pcm_ptr)
         self._check(rc, "snacb_decode_host")
 
+    def submit_host_ptr(self, tok_ptr: int, B: int, n: int, pcm_ptr: int, *, raw_ids=False, extract_slice=False,
+                        seed: int = 0, precision: str = "fp16"):
+        """Pipelined host boundary: queue copy-in + decode + copy-out of one step and return (at most two outstanding).
+        ``wait_host()`` blocks until the oldest outstanding step's PCM is in its host buffer."""
+        rc = self._lib.snacb_decode_host_submit(self._h, tok_ptr, B, n, n // FRAME,
+                                                self._flags(raw_ids, extract_slice, precision), C.c_uint64(seed), pcm_ptr)
+        self._check(rc, "snacb_decode_host_submit")
+
+    def wait_host(self):
+        self._check(self._lib.snacb_decode_host_wait(self._h), "snacb_decode_host_wait")
+
     # ------------------------------------------------------------------ per-stage timing
     def profile(self, enable: bool = True):
         self._check(self._lib.snacb_profile(self._h, 1 if enable else 0), "snacb_profile")

@@ -89,6 +89,12 @@ struct snacb_handle_s {
     int* tile_counter = nullptr;                              // dynamic tile scheduler of the chain kernel
     int32_t* st_tok = nullptr; size_t st_tok_elems = 0;       // decode_host staging
     int16_t* st_pcm = nullptr; size_t st_pcm_elems = 0;
+    // pipelined host boundary (snacb_decode_host_submit / _wait): two staging slots, a copy stream, per-slot events
+    int32_t* pl_tok[2] = {nullptr, nullptr}; size_t pl_tok_bytes[2] = {0, 0};
+    int16_t* pl_pcm[2] = {nullptr, nullptr}; size_t pl_pcm_bytes[2] = {0, 0};
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t pl_done[2] = {nullptr, nullptr}, pl_copied[2] = {nullptr, nullptr};
+    uint64_t pl_submitted = 0, pl_waited = 0;
 
     std::vector<Tap> taps;
     uint64_t launches = 0, streams = 0;
@@ -807,6 +813,13 @@ void snacb_destroy(snacb_handle h) {
     if (h->ws_codes) cudaFree(h->ws_codes);
     if (h->st_tok) cudaFree(h->st_tok);
     if (h->st_pcm) cudaFree(h->st_pcm);
+    for (int i = 0; i < 2; ++i) {
+        if (h->pl_tok[i]) cudaFree(h->pl_tok[i]);
+        if (h->pl_pcm[i]) cudaFree(h->pl_pcm[i]);
+        if (h->pl_done[i]) cudaEventDestroy(h->pl_done[i]);
+        if (h->pl_copied[i]) cudaEventDestroy(h->pl_copied[i]);
+    }
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
 }
@@ -911,6 +924,50 @@ int snacb_decode_host(snacb_handle h, const int32_t* tok_host, int B, int tok_st
     if (rc) return rc;
     CK(h, cudaMemcpyAsync(pcm_host, h->st_pcm, npcm * sizeof(int16_t), cudaMemcpyDeviceToHost, st));
     CK(h, cudaStreamSynchronize(st));
+    return SNACB_OK;
+}
+
+// Pipelined form of the host boundary: submit() returns once the work is queued, wait() blocks until the OLDEST
+// outstanding submit has its PCM in the caller's buffer.  With one submit in flight while the previous one is being
+// waited on, the device->host copy of step i (copy stream) overlaps the decode of step i + 1 (compute stream).
+int snacb_decode_host_submit(snacb_handle h, const int32_t* tok_host, int B, int tok_stride, int frames, int flags,
+                             uint64_t seed, int16_t* pcm_host) {
+    if (!h) return SNACB_ERR_ARG;
+    if (B <= 0 || frames <= 0 || tok_stride < frames * kFrame) return fail(h, SNACB_ERR_ARG, "snacb_decode_host_submit: bad sizes");
+    if (!tok_host || !pcm_host) return fail(h, SNACB_ERR_ARG, "snacb_decode_host_submit: null buffer");
+    if (h->pl_submitted - h->pl_waited >= 2) return fail(h, SNACB_ERR_STATE, "snacb_decode_host_submit: two submits outstanding, call snacb_decode_host_wait");
+    CK(h, cudaSetDevice(h->device));
+    const int slot = static_cast<int>(h->pl_submitted & 1);
+    if (!h->copy_stream) CK(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    if (!h->pl_done[slot]) {
+        CK(h, cudaEventCreateWithFlags(&h->pl_done[slot], cudaEventDisableTiming));
+        CK(h, cudaEventCreateWithFlags(&h->pl_copied[slot], cudaEventDisableTiming));
+    }
+    const size_t tbytes = static_cast<size_t>(B) * tok_stride * sizeof(int32_t);
+    const size_t pbytes = static_cast<size_t>(B) * snacb_samples_out(frames, flags) * sizeof(int16_t);
+    int rc = grow(h, reinterpret_cast<void**>(&h->pl_tok[slot]), &h->pl_tok_bytes[slot], tbytes);
+    if (rc) return rc;
+    rc = grow(h, reinterpret_cast<void**>(&h->pl_pcm[slot]), &h->pl_pcm_bytes[slot], pbytes);
+    if (rc) return rc;
+    cudaStream_t st = h->own_stream;
+    CK(h, cudaMemcpyAsync(h->pl_tok[slot], tok_host, tbytes, cudaMemcpyHostToDevice, st));
+    rc = snacb_decode(h, h->pl_tok[slot], B, tok_stride, frames, flags, nullptr, seed, h->pl_pcm[slot], nullptr, st);
+    if (rc) return rc;
+    CK(h, cudaEventRecord(h->pl_done[slot], st));
+    CK(h, cudaStreamWaitEvent(h->copy_stream, h->pl_done[slot], 0));
+    CK(h, cudaMemcpyAsync(pcm_host, h->pl_pcm[slot], pbytes, cudaMemcpyDeviceToHost, h->copy_stream));
+    CK(h, cudaEventRecord(h->pl_copied[slot], h->copy_stream));
+    h->pl_submitted++;
+    return SNACB_OK;
+}
+
+int snacb_decode_host_wait(snacb_handle h) {
+    if (!h) return SNACB_ERR_ARG;
+    if (h->pl_waited == h->pl_submitted) return fail(h, SNACB_ERR_STATE, "snacb_decode_host_wait: nothing outstanding");
+    CK(h, cudaSetDevice(h->device));
+    const int slot = static_cast<int>(h->pl_waited & 1);
+    CK(h, cudaEventSynchronize(h->pl_copied[slot]));
+    h->pl_waited++;
     return SNACB_OK;
 }
 
