@@ -161,6 +161,10 @@ int snacb_debug_tap_copy(snacb_handle h, int idx, float* dst_host, size_t dst_el
  * No GPU needed. */
 int snacb_debug_chain_spans(int C, int16_t* out, int cap);
 
+/* The same for the halo-exchange variant of the chain kernel (C = 64 or 128; opt-in, SNACB_XCH=1): a tile has no halo,
+ * every row is owned; the 32 rows above and below the tile hold the neighbouring tiles' boundary rows (27 used). */
+int snacb_debug_chain_spans_x(int C, int16_t* out, int cap);
+
 /* The same for the two-group chain kernel (C = 64 or 128, fp16 operands; kernels_chain2.cu): warps 0-7 own the rows
  * above the middle of the tile, warps 8-15 the rows below it.  out: int16[3][16][4][4] = {first_row, octets, chunk,
  * flags}; flags bit 0: the span ends its class at the group boundary and reads its three tail rows late, bit 1: the

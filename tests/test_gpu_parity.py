@@ -236,6 +236,22 @@ def test_bulk_tail_kernel_is_bit_identical(decoder, monkeypatch, prec, B, F_, sl
     assert int((new[0] != 0).sum()) > new[0].numel() // 2
 
 
+def test_halo_exchange_chain_is_bit_identical(decoder, state_dict, monkeypatch):
+    """SNACB_XCH=1: chain tiles without a halo, neighbouring tiles (other CTAs) exchange their boundary rows through L2
+    with release / acquire flags -- same bits as the default kernel, which recomputes a 40-row halo."""
+    monkeypatch.setenv("SNACB_XCH", "1")
+    dx = SnacDecoder(state_dict, device=0)
+    monkeypatch.delenv("SNACB_XCH")
+    for B, F_ in ((1, 4), (37, 4), (3, 16), (300, 4)):
+        tokens = _cuda(synth.make_tokens(B, F_, seed=31 + B))
+        noises = [_cuda(n) for n in synth.make_noises(B, 4 * F_, seed=8)]
+        a = decoder.decode(tokens, raw_ids=True, noise=noises, return_wave=True)
+        b = dx.decode(tokens, raw_ids=True, noise=noises, return_wave=True)
+        torch.cuda.synchronize()
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]), (B, F_)
+    dx.close()
+
+
 def test_golden_vectors(decoder):
     """Committed fixtures: bytes the REFERENCE's convert_to_audio returned with the oracle as SNAC."""
     z = np.load(os.path.join(GOLD, "decode_golden.npz"))

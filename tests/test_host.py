@@ -169,6 +169,65 @@ def test_chain_span_schedule(C):
 
 
 @pytest.mark.parametrize("C", [64, 128])
+def test_chain_span_schedule_halo_exchange(C):
+    """The same emulation for the halo-exchange variant (SNACB_XCH=1): the tile owns every row, the 32 rows above and
+    below it hold the neighbouring tiles' boundary rows (only the nearest 3*d matter), nothing outside is readable.
+    Every row of the tile must come out of the layer's ORIGINAL inputs, neighbours included."""
+    import ctypes as Ct
+    from tts_inference_b200 import _lib
+    lib = _lib.load()
+    buf = (Ct.c_int16 * (3 * 16 * 4 * 3))()
+    rc = lib.snacb_debug_chain_spans_x(C, buf, len(buf))
+    rows, nw = rc & 0xFFFF, rc >> 16
+    assert rows == 512 and nw in (8, 16)
+    sp = np.frombuffer(buf, dtype=np.int16).reshape(3, 16, 4, 3)
+    PAD = 32
+    rng = np.random.default_rng(1)
+    for l, d in enumerate((1, 3, 9)):
+        for kc in range(C // 64):
+            ext = rng.integers(1, 1 << 30, size=rows + 2 * PAD).astype(np.int64)     # virtual rows -PAD .. rows+PAD-1
+            ext[:PAD - 3 * d] = -7777; ext[rows + PAD + 3 * d:] = -7777                # stale pad rows: must never matter
+            at = lambda r, src: int(src[r + PAD]) if -PAD <= r < rows + PAD else 0
+            want = {r: sum((j + 2) * at(r + (j - 3) * d, ext) for j in range(7)) for r in range(rows)}
+            work = ext.copy()
+            spans = [(w, k, *sp[l, w, k]) for w in range(16) for k in range(4) if sp[l, w, k, 1] > 0 and sp[l, w, k, 2] == kc]
+            pre = {}
+            for (w, k, r0, noct, _) in spans:                                          # phase 1: pre-reads (guard: >= -PAD)
+                assert r0 % 8 == 0 and r0 + 27 >= -PAD                                 # in-loop look-ahead stays inside the pad
+                head = [at(r0 - (3 - j) * d, work) if r0 - (3 - j) * d >= -PAD else 0 for j in range(3)]
+                tail = [int(work[min(r0 + (8 * noct + j) * d + PAD, rows + 2 * PAD - 1)]) for j in range(3)]   # unguarded over-read
+                pre[(w, k)] = (head, tail)
+            written = set()
+            for (w, k, r0, noct, _) in sorted(spans, key=lambda s_: rng.random()):
+                head, tail = pre[(w, k)]
+                n = 8 * noct
+
+                def get(i):
+                    if i < 0:
+                        return head[i + 3]
+                    if i >= n:
+                        return tail[i - n]
+                    r = r0 + i * d
+                    if i < 3:                                                           # window init: guarded reads
+                        return at(r, work) if r >= -PAD else 0
+                    return int(work[min(r + PAD, rows + 2 * PAD - 1)])                  # main loop: unguarded
+                win = [get(i) for i in range(-3, 3)]
+                for q in range(noct):
+                    raw = [get(8 * q + kk + 3) for kk in range(8)]
+                    for kk in range(8):
+                        win = win[-6:] + [raw[kk]]
+                        r = r0 + (8 * q + kk) * d
+                        if 0 <= r < rows:
+                            assert r not in written
+                            written.add(r)
+                            work[r + PAD] = sum((j + 2) * win[j] for j in range(7))
+            for r in range(rows):
+                assert r in written and int(work[r + PAD]) == want[r], (C, d, kc, r)
+    per_warp = sp[:, :nw, :, 1].sum(axis=2)
+    assert per_warp.max() - per_warp.min() <= 1
+
+
+@pytest.mark.parametrize("C", [64, 128])
 def test_chain2_span_schedule(C):
     """Schedule of the two-group chain kernel (kernels_chain2.cu), emulated on integers in the kernel's order: group 0
     stashes its last 27 rows, pre-reads its in-group neighbours, rewrites its half in place and reads the tails that

@@ -62,7 +62,11 @@ cudaError_t launch_convt_ph(int half_fp16, const GemmArgs& a, const CUtensorMap&
 bool chain_supported(int C, int half_fp16);
 int chain_tile_rows(int C);           // rows of a tile incl. the halo (y tensor-map box = (64, 128, 1), 128B swizzle)
 int chain_warps(int C);               // warps per CTA of the launch configuration used for C channels
-void chain_build_spans(int C, ChainSpan (*spans)[kChainWarps][kChainSpans]);
+void chain_build_spans(int C, ChainSpan (*spans)[kChainWarps][kChainSpans], bool xch = false);
+// halo exchange variant (fp16, C = 64 / 128, whole streams, T a multiple of the tile height): tiles carry no halo;
+// ChainArgs::xbuf (xslots * chain_xch_slot_bytes(C) bytes), xflags and xack (3 ints per tile each, zeroed) must be set
+bool chain_xch_supported(int C, int half_fp16);
+size_t chain_xch_slot_bytes(int C);
 // tm[7]: y load map box (64,128,1); out store maps box (64,128-kChainHalo,1) and (64,128,1); noise 1x1, res d=1,
 // d=3, d=9 weight maps box (64, C); all 128B-swizzled
 cudaError_t launch_chain(int half_fp16, const ChainArgs& a, const CUtensorMap* tm, int sm_count, cudaStream_t st);

@@ -51,13 +51,18 @@ __device__ __forceinline__ uint32_t as_u32(__half2 v) { return *reinterpret_cast
 
 constexpr int kHalo = kChainHalo;            // 40 >= 39, multiple of 8
 
-template <int C, int NB, bool HALF = true>
+constexpr int kXPad = 32;                    // XCH: rows of neighbour data kept above / below every chunk plane (>= 27 + 2)
+constexpr int kXRows = 27;                   // rows exchanged per side: 3 * dilation of the coming unit, at most 27
+
+template <int C, int NB, bool HALF = true, bool XCH = false>
 struct ChainCfg {
     static constexpr int kCH = C / 64;                      // 64-channel K chunks
     static constexpr int kRows = NB * 128;                  // tile rows incl. halo
-    static constexpr int kROut = kRows - 2 * kHalo;         // rows stored per tile
+    static constexpr int kROut = XCH ? kRows : kRows - 2 * kHalo;   // rows stored per tile
     static constexpr int kPlane = NB * 16384;               // one chunk plane of the tile [NB][128 rows][128 B]
-    static constexpr int kXBytes = kCH * kPlane;
+    static constexpr int kPadB = XCH ? kXPad * 128 : 0;     // XCH: neighbour rows in front of / behind each plane
+    static constexpr int kPlaneS = kPlane + 2 * kPadB;      // plane stride
+    static constexpr int kXBytes = kCH * kPlaneS;
     static constexpr bool kWRes = (C == 64);                // all four 1x1 weights resident
     static constexpr bool kWChunked = (C == 256);           // weights streamed one 64-channel K chunk at a time
     static constexpr int kWLayer = C * C * 2;               // one layer's weights [kCH][C rows][128 B]
@@ -72,10 +77,12 @@ struct ChainCfg {
     static constexpr int kOffPrm = kOffW + kWBytes;
     static constexpr int kOffEpi = kOffPrm + kPrmBytes;
     static constexpr int kOffNz = kOffEpi + kEpiBytes;
-    static constexpr int kSpanBytes = 3 * kChainWarps * kChainSpans * 8;   // the launch's span table (copied from the kernel parameters)
+    static constexpr int kSpanWarps = (C == 64) ? 8 : kChainWarps;          // warps of the launch configuration (kNW*)
+    static constexpr int kSpanBytes = 3 * kSpanWarps * kChainSpans * 8;    // the launch's span table (copied from the kernel parameters)
+    static constexpr int kBarBytes = XCH ? 128 : 256;
     static constexpr int kOffSpan = kOffNz + kNzBytes;
     static constexpr int kOffBar = kOffSpan + kSpanBytes;
-    static constexpr int kSmem = kOffBar + 256 + 1024;
+    static constexpr int kSmem = kOffBar + kBarBytes + 1024;
     static constexpr int kTmemCols = NB * C;
     static_assert(NB >= 2 && NB <= 8, "blocks per tile");
     static_assert(kTmemCols == 512 || kTmemCols == 256 || kTmemCols == 128, "TMEM columns");
@@ -109,7 +116,7 @@ __device__ __forceinline__ __half2 snake_h2_poly(__half2 xh) {
     return __hfma2(p, s, xh);
 }
 
-template <int D, int ROWS, int POLY>
+template <int D, int ROWS, int POLY, int PADR = 0>
 __device__ __forceinline__ void span_half(uint8_t* plane, int r_oct, const int nq, const uint32_t h0, const uint32_t h1,
                                           const uint32_t h2, const uint32_t t0, const uint32_t t1, const uint32_t t2,
                                           const uint32_t (&swz)[8], const uint32_t* prm) {
@@ -128,8 +135,8 @@ __device__ __forceinline__ void span_half(uint8_t* plane, int r_oct, const int n
     uint8_t* ob = plane + r_oct * 128;             // r_oct = 0 (mod 8): (row & 7) of step k is (k*D) & 7
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
-        uint32_t raw = 0u;                         // class starts may lie up to 24 rows above the tile
-        if (r_oct + j * D >= 0) raw = *reinterpret_cast<const uint32_t*>(ob + j * D * 128 + swz[(j * D) & 7]);
+        uint32_t raw = 0u;                         // class starts may lie above the tile (PADR rows of neighbour data there)
+        if (r_oct + j * D >= -PADR) raw = *reinterpret_cast<const uint32_t*>(ob + j * D * 128 + swz[(j * D) & 7]);
         win[4 + j] = snake(as_h2(raw));
     }
 #pragma unroll 1
@@ -208,27 +215,43 @@ __device__ __forceinline__ void span_f32(uint8_t* plane, int r_oct, const int nq
 
 enum { EPI_C_NOISE = 0, EPI_C_MID = 1, EPI_C_FINAL = 2 };
 
+// inter-CTA flags of the halo exchange (global memory, gpu scope).  A wait that outlasts ~1 s traps instead of hanging.
+__device__ __forceinline__ void flag_release(int* p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void flag_wait_ge(const int* p, int want) {
+    const long long t0 = clock64();
+    for (;;) {
+        int v;
+        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+        if (v >= want) return;
+        __nanosleep(20);
+        if (clock64() - t0 > (1ll << 31)) __trap();
+    }
+}
+
 }  // namespace
 
 // NW symmetric warps (prologue + epilogue); thread 0 also issues TMA / MMA.  16 warps: one CTA per SM; 8 warps: two.
-template <int C, int NB, int NW, typename HT, int POLY>
+template <int C, int NB, int NW, typename HT, int POLY, bool XCH = false>
 __global__ void __launch_bounds__(NW * 32) __maxnreg__(NW == 8 ? 128 : 128 + 0 * NW)
 k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmOe,
         const __grid_constant__ CUtensorMap tmOm, const __grid_constant__ CUtensorMap tmWn,
         const __grid_constant__ CUtensorMap tmW0, const __grid_constant__ CUtensorMap tmW1,
         const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ ChainArgs a, const int num_tiles) {
     constexpr bool kHalfMath = std::is_same<HT, __half>::value;
-    using Cfg = ChainCfg<C, NB, kHalfMath>;
+    static_assert(!XCH || (kHalfMath && C <= 128), "halo exchange: fp16 operands, C = 64 / 128");
+    using Cfg = ChainCfg<C, NB, kHalfMath, XCH>;
     constexpr int CH = Cfg::kCH;
     constexpr int kThreads = NW * 32;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint8_t* sX = smem + Cfg::kOffX;
+    uint8_t* sX = smem + Cfg::kOffX + Cfg::kPadB;       // row 0 of chunk plane 0
     uint8_t* sW = smem + Cfg::kOffW;
     uint32_t* sPrm = reinterpret_cast<uint32_t*>(smem + Cfg::kOffPrm);
     float* sEpi = reinterpret_cast<float*>(smem + Cfg::kOffEpi);
     float* sNz = reinterpret_cast<float*>(smem + Cfg::kOffNz);
-    ChainSpan* sSpan = reinterpret_cast<ChainSpan*>(smem + Cfg::kOffSpan);   // [3][kChainWarps][kChainSpans]
+    ChainSpan* sSpan = reinterpret_cast<ChainSpan*>(smem + Cfg::kOffSpan);   // [3][kSpanWarps][kChainSpans]
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kOffBar);
     uint64_t* ld_bar = bars;          // tile landed (TMA)
     uint64_t* w_bar = bars + 1;       // [2] weight buffers landed
@@ -278,8 +301,9 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
     }
     // the span table is indexed by (layer, warp) at run time: from shared memory, not from the constant bank (a dynamically
     // indexed kernel parameter costs a constant-cache miss per layer: ~1 k cycles of the 'pre' phase, measured)
-    for (int i = tid; i < 3 * kChainWarps * kChainSpans; i += kThreads)
-        sSpan[i] = a.spans[i / (kChainWarps * kChainSpans)][(i / kChainSpans) % kChainWarps][i % kChainSpans];
+    static_assert(NW <= Cfg::kSpanWarps, "span table");
+    for (int i = tid; i < 3 * Cfg::kSpanWarps * kChainSpans; i += kThreads)
+        sSpan[i] = a.spans[i / (Cfg::kSpanWarps * kChainSpans)][(i / kChainSpans) % Cfg::kSpanWarps][i % kChainSpans];
     // epilogue vectors: [0] scale of the NoiseBlock output, [1],[2] scale and scaled bias after unit d=1, [3],[4] after
     // d=3, [5] bias after d=9, [6],[7] alpha / 1/alpha of the next Snake.  scale = alpha1 of the next unit's Snake in the
     // fp16 formulation (the tile copy holds alpha1 * x), 1 otherwise.
@@ -313,12 +337,12 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
     };
     auto tile_coords = [&](int tile, int& s, int& t_start) {
         s = tile / tiles_t;
-        t_start = (a.t_n > 0 ? a.t_lo : 0) + (tile % tiles_t) * Cfg::kROut - kHalo;
+        t_start = (a.t_n > 0 ? a.t_lo : 0) + (tile % tiles_t) * Cfg::kROut - (XCH ? 0 : kHalo);
     };
     auto load_block = [&](int s, int t_start, int b) {      // thread 0; ld_bar's expect_tx covers the whole tile
 #pragma unroll
         for (int kc = 0; kc < CH; ++kc)
-            tma_load_3d_hint(sX + kc * Cfg::kPlane + b * 16384, &tmY, kc * 64, t_start + b * 128, s, ld_bar, kL2EvictFirst);
+            tma_load_3d_hint(sX + kc * Cfg::kPlaneS + b * 16384, &tmY, kc * 64, t_start + b * 128, s, ld_bar, kL2EvictFirst);
     };
     int tile = blockIdx.x;
     if (tid == 0 && tile < num_tiles) {
@@ -334,7 +358,7 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
         }
         int s, t_start;
         tile_coords(tile, s, t_start);
-        mbar_expect_tx(ld_bar, Cfg::kXBytes);
+        mbar_expect_tx(ld_bar, CH * Cfg::kPlane);
         for (int b = 0; b < NB; ++b) load_block(s, t_start, b);
     }
 
@@ -363,7 +387,7 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
                 for (int b = 0; b < NB; ++b)
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
-                        mma_f16_ss(tmem_base + b * C, umma_desc_sw128(sx_addr + kc * Cfg::kPlane + b * 16384 + k * 32),
+                        mma_f16_ss(tmem_base + b * C, umma_desc_sw128(sx_addr + kc * Cfg::kPlaneS + b * 16384 + k * 32),
                                    umma_desc_sw128(w_addr + k * 32), idescW, (l > 0 || kc > 0 || k > 0) ? 1u : 0u);
                 mma_commit(&wfree_bar[buf]);
                 if (kc & 1) {
@@ -389,7 +413,7 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
             for (int kc = 0; kc < CH; ++kc)
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                    mma_f16_ss(tmem_base + b * C, umma_desc_sw128(sx_addr + kc * Cfg::kPlane + b * 16384 + k * 32),
+                    mma_f16_ss(tmem_base + b * C, umma_desc_sw128(sx_addr + kc * Cfg::kPlaneS + b * 16384 + k * 32),
                                umma_desc_sw128(w_addr + kc * (C * 128) + k * 32), idescW,
                                (l > 0 || kc > 0 || k > 0) ? 1u : 0u);
             mma_commit(&mma_bar[b]);
@@ -414,7 +438,7 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
         for (int it = g; it < kPieces; it += NW / 4) {
             const int blk = it / (C / 32), cg = it % (C / 32);
             // the last epilogue only feeds the TMA stores: 32-row groups entirely inside the halo are skipped
-            if (MODE == EPI_C_FINAL && (blk * 128 + q * 32 + 32 <= kHalo || blk * 128 + q * 32 >= Cfg::kRows - kHalo)) continue;
+            if (!XCH && MODE == EPI_C_FINAL && (blk * 128 + q * 32 + 32 <= kHalo || blk * 128 + q * 32 >= Cfg::kRows - kHalo)) continue;
             mbar_wait(&mma_bar[blk], mma_par);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + blk * C + cg * 32;
@@ -423,7 +447,7 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
             const int i = blk * 128 + q * 32 + lane;
             const int t = t_start + i;
             const bool valid = static_cast<unsigned>(t) < static_cast<unsigned>(a.T);
-            uint8_t* row = sX + (cg >> 1) * Cfg::kPlane + i * 128;
+            uint8_t* row = sX + (cg >> 1) * Cfg::kPlaneS + i * 128;
             uint4 yv[4];
             float nz = 0.f;
             if (MODE == EPI_C_NOISE) {
@@ -489,7 +513,9 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
         int s, t_start;
         tile_coords(tile, s, t_start);
         // claim the tile after this one (persistent CTAs, dynamic order: tiles cost the same but SMs do not run alike)
-        if (tid == 0) s_next[n & 1] = static_cast<int>(gridDim.x) + atomicAdd(a.tile_counter, 1);
+        // (halo exchange: static round-robin instead, so that the CTAs holding neighbouring tiles run side by side)
+        if (tid == 0) s_next[n & 1] = XCH ? tile + static_cast<int>(gridDim.x)
+                                          : static_cast<int>(gridDim.x) + atomicAdd(a.tile_counter, 1);
 
         // ---------------------------------------------------------------- noise values (overlaps the tile load)
         {
@@ -504,6 +530,12 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
                                 : counter_normal(key, static_cast<unsigned long long>(a.stream_offset + s) * a.T + t);
                 sNz[i] = v;
             }
+        }
+        if (XCH && tid == 0 && tile >= a.xslots) {
+            // the exchange slot of this tile was last used by tile - xslots: both its neighbours must have taken their rows
+            const int old = tile - a.xslots, pos = old % tiles_t;
+            const int readers = (pos > 0) + (pos + 1 < tiles_t);
+            for (int l = 0; l < 3; ++l) flag_wait_ge(&a.xack[old * 3 + l], readers);
         }
         mbar_wait(ld_bar, n & 1);
         __syncthreads();
@@ -523,23 +555,66 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
 #pragma unroll 1
         for (int l = 0; l < 3; ++l) {
             const int d = (l == 0) ? 1 : (l == 1 ? 3 : 9);
+            if (XCH) {
+                // ---- halo exchange: instead of recomputing a 40-row halo, neighbouring tiles of a stream (held by other
+                // CTAs, running side by side) swap the 3*d boundary rows of the 16-bit tile copy this unit's depthwise
+                // conv reaches across, through an L2-resident buffer + release / acquire flags.  A raw byte copy keeps
+                // the 128B swizzle: source and destination rows are congruent mod 8.
+                const int nx = 3 * d, pos = tile % tiles_t;
+                const bool has_prev = pos > 0, has_nxt = pos + 1 < tiles_t;
+                constexpr int kSideB = CH * kXRows * 128;
+                auto xslot = [&](int t, int side) { return a.xbuf + ((static_cast<size_t>(t % a.xslots) * 3 + l) * 2 + side) * kSideB; };
+                const int chunks = CH * nx * 8;                         // 16-byte pieces per side
+                for (int i = tid; i < 2 * chunks; i += kThreads) {
+                    const int side = i >= chunks, j = side ? i - chunks : i;
+                    const int kc = j / (nx * 8), rem = j % (nx * 8);
+                    if (side ? !has_nxt : !has_prev) continue;          // nobody reads that side
+                    const uint8_t* src = sX + kc * Cfg::kPlaneS + (side ? (Cfg::kRows - nx) * 128 : 0) + rem * 16;
+                    *reinterpret_cast<uint4*>(xslot(tile, side) + kc * (kXRows * 128) + rem * 16) = *reinterpret_cast<const uint4*>(src);
+                }
+                __syncthreads();
+                if (tid == 0) {
+                    __threadfence();                                    // cumulative: the CTA's stores above, ordered by the barrier
+                    flag_release(&a.xflags[tile * 3 + l], 1);
+                    if (has_prev) flag_wait_ge(&a.xflags[(tile - 1) * 3 + l], 1);
+                }
+                if (tid == 32 && has_nxt) flag_wait_ge(&a.xflags[(tile + 1) * 3 + l], 1);
+                __syncthreads();
+                for (int i = tid; i < 2 * chunks; i += kThreads) {
+                    const int side = i >= chunks, j = side ? i - chunks : i;
+                    const int kc = j / (nx * 8), rem = j % (nx * 8);
+                    uint4 v = make_uint4(0u, 0u, 0u, 0u);               // stream edge: the conv's zero padding
+                    if (side == 0) {                                    // rows -nx .. -1 <- the previous tile's last rows
+                        if (has_prev) v = __ldcg(reinterpret_cast<const uint4*>(xslot(tile - 1, 1) + kc * (kXRows * 128) + rem * 16));
+                        *reinterpret_cast<uint4*>(sX + kc * Cfg::kPlaneS - nx * 128 + rem * 16) = v;
+                    } else {                                            // rows kRows .. kRows + nx - 1 <- the next tile's first rows
+                        if (has_nxt) v = __ldcg(reinterpret_cast<const uint4*>(xslot(tile + 1, 0) + kc * (kXRows * 128) + rem * 16));
+                        *reinterpret_cast<uint4*>(sX + kc * Cfg::kPlaneS + Cfg::kRows * 128 + rem * 16) = v;
+                    }
+                }
+                __syncthreads();
+                if (tid == 0) {
+                    if (has_prev) atomicAdd(&a.xack[(tile - 1) * 3 + l], 1);
+                    if (has_nxt) atomicAdd(&a.xack[(tile + 1) * 3 + l], 1);
+                }
+            }
             // ---- spans of this warp: pre-read the 3 rows before and after each span (owned by other warps)
             uint32_t hd[kChainSpans][3], tl[kChainSpans][3];
             int r_first[kChainSpans], n_oct[kChainSpans], kcs[kChainSpans];
 #pragma unroll
             for (int sp = 0; sp < kChainSpans; ++sp) {
-                const ChainSpan spn = sSpan[(l * kChainWarps + warp) * kChainSpans + sp];
+                const ChainSpan spn = sSpan[(l * Cfg::kSpanWarps + warp) * kChainSpans + sp];
                 r_first[sp] = spn.r_first; n_oct[sp] = spn.n_oct; kcs[sp] = spn.kc;
 #pragma unroll
                 for (int j = 0; j < 3; ++j) { hd[sp][j] = 0u; tl[sp][j] = 0u; }
                 if (spn.n_oct > 0) {                       // warp-uniform: unused span slots cost one branch
-                    const uint8_t* lane_base = sX + spn.kc * Cfg::kPlane + ((lane & 3) << 2);
+                    const uint8_t* lane_base = sX + spn.kc * Cfg::kPlaneS + ((lane & 3) << 2);
                     const int c16 = lane >> 2;
 #pragma unroll
                     for (int j = 0; j < 3; ++j) {
                         const int rh = spn.r_first - (3 - j) * d;
                         const int rt = spn.r_first + (8 * spn.n_oct + j) * d;
-                        if (rh >= 0) hd[sp][j] = *reinterpret_cast<const uint32_t*>(lane_base + rh * 128 + (((c16 ^ rh) & 7) << 4));
+                        if (rh >= -(XCH ? kXPad : 0)) hd[sp][j] = *reinterpret_cast<const uint32_t*>(lane_base + rh * 128 + (((c16 ^ rh) & 7) << 4));
                         tl[sp][j] = *reinterpret_cast<const uint32_t*>(lane_base + rt * 128 + (((c16 ^ rt) & 7) << 4));
                     }
                 }
@@ -560,11 +635,11 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
                     tt[j] = sp == 0 ? tl[0][j] : (sp == 1 ? tl[1][j] : (sp == 2 ? tl[2][j] : tl[3][j]));
                 }
                 const uint32_t* prm = sPrm + ((l * (C / 2)) + kc * 32 + lane) * Cfg::kPrmWords;
-                uint8_t* plane = sX + kc * Cfg::kPlane;
+                uint8_t* plane = sX + kc * Cfg::kPlaneS;
                 if (kHalfMath) {
-                    if (d == 1) span_half<1, Cfg::kRows, POLY>(plane, r0, nq, hh[0], hh[1], hh[2], tt[0], tt[1], tt[2], swz, prm);
-                    else if (d == 3) span_half<3, Cfg::kRows, POLY>(plane, r0, nq, hh[0], hh[1], hh[2], tt[0], tt[1], tt[2], swz, prm);
-                    else span_half<9, Cfg::kRows, POLY>(plane, r0, nq, hh[0], hh[1], hh[2], tt[0], tt[1], tt[2], swz, prm);
+                    if (d == 1) span_half<1, Cfg::kRows, POLY, XCH ? kXPad : 0>(plane, r0, nq, hh[0], hh[1], hh[2], tt[0], tt[1], tt[2], swz, prm);
+                    else if (d == 3) span_half<3, Cfg::kRows, POLY, XCH ? kXPad : 0>(plane, r0, nq, hh[0], hh[1], hh[2], tt[0], tt[1], tt[2], swz, prm);
+                    else span_half<9, Cfg::kRows, POLY, XCH ? kXPad : 0>(plane, r0, nq, hh[0], hh[1], hh[2], tt[0], tt[1], tt[2], swz, prm);
                 } else {
                     if (d == 1) span_f32<1, Cfg::kRows, HT>(plane, r0, nq, hh[0], hh[1], hh[2], tt[0], tt[1], tt[2], swz, prm);
                     else if (d == 3) span_f32<3, Cfg::kRows, HT>(plane, r0, nq, hh[0], hh[1], hh[2], tt[0], tt[1], tt[2], swz, prm);
@@ -593,8 +668,9 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
             for (int b = 0; b < NB; ++b) {
 #pragma unroll
                 for (int kc = 0; kc < CH; ++kc) {
-                    const uint8_t* src = sX + kc * Cfg::kPlane + b * 16384;
-                    if (b == 0) tma_store_3d(&tmOe, src + kHalo * 128, kc * 64, t_out, s);
+                    const uint8_t* src = sX + kc * Cfg::kPlaneS + b * 16384;
+                    if (XCH) tma_store_3d(&tmOm, src, kc * 64, t_start + b * 128, s);
+                    else if (b == 0) tma_store_3d(&tmOe, src + kHalo * 128, kc * 64, t_out, s);
                     else if (b == NB - 1) tma_store_3d(&tmOe, src, kc * 64, t_start + b * 128, s);
                     else tma_store_3d(&tmOm, src, kc * 64, t_start + b * 128, s);
                 }
@@ -603,7 +679,7 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
             if (has_next) {
                 int s2, t2;
                 tile_coords(next_tile, s2, t2);
-                mbar_expect_tx(ld_bar, Cfg::kXBytes);
+                mbar_expect_tx(ld_bar, CH * Cfg::kPlane);
                 // block b may be refilled once the store of block b has read it (groups complete in order)
                 if (NB > 7) { bulk_wait_group_read<7>(); load_block(s2, t2, NB - 8); }
                 if (NB > 6) { bulk_wait_group_read<6>(); load_block(s2, t2, NB - 7); }
@@ -632,33 +708,42 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
 
 namespace {
 
-template <int C, int NB, int NW, typename HT, int POLY = 0>
+template <int C, int NB, int NW, typename HT, int POLY = 0, bool XCH = false>
 cudaError_t launch_chain_t(const ChainArgs& a, const CUtensorMap* tm, int sm_count, cudaStream_t st) {
-    using Cfg = ChainCfg<C, NB, std::is_same<HT, __half>::value>;
+    using Cfg = ChainCfg<C, NB, std::is_same<HT, __half>::value, XCH>;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(k_chain<C, NB, NW, HT, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
+        cudaError_t e = cudaFuncSetAttribute(k_chain<C, NB, NW, HT, POLY, XCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(k_chain<C, NB, NW, HT, POLY>, cudaFuncAttributePreferredSharedMemoryCarveout,
+        e = cudaFuncSetAttribute(k_chain<C, NB, NW, HT, POLY, XCH>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                  cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
     const int tiles = a.S * (((a.t_n > 0 ? a.t_n : a.T) + Cfg::kROut - 1) / Cfg::kROut);
     if (tiles == 0) return cudaSuccess;
-    const int slots = sm_count * (NW == 8 ? 2 : 1);
+    int slots = sm_count * (NW == 8 ? 2 : 1);
+    if (XCH) {
+        // the CTAs wait for one another: every CTA of the grid must be resident, and the exchange slots must cover it
+        static int occ = -1;
+        if (occ < 0 && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_chain<C, NB, NW, HT, POLY, XCH>, NW * 32, Cfg::kSmem) != cudaSuccess) occ = 0;
+        if (occ * sm_count < slots) slots = occ * sm_count;
+        if (2 * slots > a.xslots) slots = a.xslots / 2;
+        if (slots <= 0 || a.xbuf == nullptr || a.xflags == nullptr || a.xack == nullptr || a.t_n > 0 || a.T % Cfg::kRows != 0)
+            return cudaErrorInvalidValue;
+    }
     const int grid = tiles < slots ? tiles : slots;
     if (a.prof != nullptr) {
         int occ = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_chain<C, NB, NW, HT, POLY>, NW * 32, Cfg::kSmem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_chain<C, NB, NW, HT, POLY, XCH>, NW * 32, Cfg::kSmem);
         cudaFuncAttributes fa;
-        cudaFuncGetAttributes(&fa, k_chain<C, NB, NW, HT, POLY>);
+        cudaFuncGetAttributes(&fa, k_chain<C, NB, NW, HT, POLY, XCH>);
         int occ_nosmem = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_nosmem, k_chain<C, NB, NW, HT, POLY>, NW * 32, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_nosmem, k_chain<C, NB, NW, HT, POLY, XCH>, NW * 32, 0);
         fprintf(stderr, "k_chain<%d,%d,%d>: grid %d, smem %d (+%zu static), regs %d, occupancy %d CTA/SM (%d without smem)\n", C, NB, NW,
                 grid, Cfg::kSmem, fa.sharedSizeBytes, fa.numRegs, occ, occ_nosmem);
     }
-    k_chain<C, NB, NW, HT, POLY><<<grid, NW * 32, Cfg::kSmem, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], tm[6], a, tiles);
+    k_chain<C, NB, NW, HT, POLY, XCH><<<grid, NW * 32, Cfg::kSmem, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], tm[6], a, tiles);
     return cudaGetLastError();
 }
 
@@ -671,23 +756,26 @@ constexpr int kNB64 = 4, kNW64 = 8, kNB128 = 4, kNW128 = 16, kNB256 = 2, kNW256 
 }  // namespace
 
 bool chain_supported(int C, int half_fp16) { return C == 64 || C == 128 || (C == 256 && half_fp16); }
+bool chain_xch_supported(int C, int half_fp16) { return half_fp16 && (C == 64 || C == 128); }
+size_t chain_xch_slot_bytes(int C) { return static_cast<size_t>(3) * 2 * (C / 64) * kXRows * 128; }
 int chain_tile_rows(int C) { return (C == 64 ? kNB64 : (C == 128 ? kNB128 : kNB256)) * 128; }
 int chain_warps(int C) { return C == 64 ? kNW64 : (C == 128 ? kNW128 : kNW256); }
 
 // Spans of the in-place prologue (see the header comment): for dilation d the rows of a tile split into d classes
 // r = r0 + k d.  Class starts are multiples of 8 (so that the swizzle phase of step k is static) no larger than the
 // first row whose result is needed at that layer; negative starts skip their first few steps.
-void chain_build_spans(int C, ChainSpan (*spans)[kChainWarps][kChainSpans]) {
+void chain_build_spans(int C, ChainSpan (*spans)[kChainWarps][kChainSpans], bool xch) {
     const int rows = chain_tile_rows(C), ch = C / 64, nw = chain_warps(C);
     static const int dil[3] = {1, 3, 9};
     for (int l = 0; l < 3; ++l) {
         const int d = dil[l];
         struct Cls { int kc, r0, noct; };
         std::vector<Cls> cls;
-        const int top = (d == 1) ? 0 : (d == 3 ? 8 : 40);
+        // halo exchange: every row of the tile is owned, classes start at the first multiple of 8 at or below their first row
+        const int top = xch ? (d == 9 ? 8 : 0) : ((d == 1) ? 0 : (d == 3 ? 8 : 40));
         // rows at or beyond `hi` are not needed downstream: the last unit feeds only the stored rows (< rows - halo),
         // the unit before it additionally that unit's 27 rows of taps, the first one 9 more
-        const int hi = rows - kChainHalo + (l == 2 ? 0 : (l == 1 ? 27 : 36));
+        const int hi = xch ? rows : rows - kChainHalo + (l == 2 ? 0 : (l == 1 ? 27 : 36));
         for (int kc = 0; kc < ch; ++kc)
             for (int m = 0; m < d; ++m) {
                 const int r0 = top - 8 * m;
@@ -719,15 +807,18 @@ void chain_build_spans(int C, ChainSpan (*spans)[kChainWarps][kChainSpans]) {
 //     [3..6] noise 1x1, res d=1, d=3, d=9 weight maps, box (64, C); all 128B-swizzled
 cudaError_t launch_chain(int half_fp16, const ChainArgs& a, const CUtensorMap* tm, int sm_count, cudaStream_t st) {
     if (half_fp16) {
-        // a.snake_poly: 0 = both Snakes through MUFU.SIN, 2 = snake2 as a half2 polynomial, 3 = both (see span_half)
+        if (a.xbuf != nullptr) {            // halo exchange between neighbouring tiles instead of a recomputed halo
+            if (a.C == 64) return launch_chain_t<64, kNB64, kNW64, __half, 0, true>(a, tm, sm_count, st);
+            if (a.C == 128) return launch_chain_t<128, kNB128, kNW128, __half, 0, true>(a, tm, sm_count, st);
+            return cudaErrorInvalidValue;
+        }
+        // a.snake_poly: 0 = both Snakes through MUFU.SIN, 2 = snake2 as a half2 polynomial (see span_half)
 #define SNACB_CHAIN_POLY(P)                                                                                      \
         if (a.C == 64) return launch_chain_t<64, kNB64, kNW64, __half, P>(a, tm, sm_count, st);                   \
         if (a.C == 128) return launch_chain_t<128, kNB128, kNW128, __half, P>(a, tm, sm_count, st);               \
         if (a.C == 256) return launch_chain_t<256, kNB256, kNW256, __half, P>(a, tm, sm_count, st);               \
         return cudaErrorInvalidValue;
-        if (a.snake_poly == 3) { SNACB_CHAIN_POLY(3) }
-        if (a.snake_poly == 2) { SNACB_CHAIN_POLY(2) }
-        if (a.snake_poly == 1) { SNACB_CHAIN_POLY(1) }
+        if (a.snake_poly & 2) { SNACB_CHAIN_POLY(2) }
         SNACB_CHAIN_POLY(0)
 #undef SNACB_CHAIN_POLY
     }

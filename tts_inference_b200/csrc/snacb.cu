@@ -48,6 +48,8 @@ struct BlockW {
     ChainSpan spans[3][kChainWarps][kChainSpans];
     bool chain2;                        // fp16 only: the two-group chain kernel (kernels_chain2.cu) covers this block
     ChainSpan spans2[3][kChainWarps][kChainSpans];
+    ChainSpan spans_x[3][kChainWarps][kChainSpans];   // halo-exchange variant of the chain kernel (no halo rows)
+    bool chain_x = false;
 };
 struct Tap {
     std::string name;
@@ -101,6 +103,10 @@ struct snacb_handle_s {
     bool res_v1 = false;                // SNACB_RES_V1=1: use the non-persistent ResidualUnit kernel
     bool no_chain2 = true;              // SNACB_CHAIN2=1 opts into the two-group chain kernel (kernels_chain2.cu): bit-identical
                                         // output, measured 5 % (C = 128) / 40 % (C = 64) slower than k_chain
+    bool no_xch = true;                 // SNACB_XCH=1 opts into the halo-exchange chain tiles (kernels_chain.cu, XCH): bit-identical
+                                        // output, measured slower than recomputing the halo
+    unsigned char* xbuf = nullptr; size_t xbuf_bytes = 0;     // halo exchange buffer and its flags (chain kernel, XCH)
+    int* xflags = nullptr; size_t xflags_bytes = 0;
     int snake_poly = 0;                 // SNACB_SNAKE_POLY: fp16 chain prologue, bit 0 / 1 = snake1 / snake2 as a half2 polynomial
     bool no_chain = false;              // SNACB_NO_CHAIN=1: per-layer kernels instead of the fused chain
     bool no_convt_res = false;          // SNACB_NO_CONVT_RES=1: generic k_gemm_tc for every ConvTranspose
@@ -472,7 +478,22 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
             ca.inv_next = bi < 3 ? h->blk[bi + 1].inv_alpha : h->tail_inv;
             ca.noise = noise ? noise[bi] : nullptr; ca.seed = seed; ca.noise_stage = bi; ca.stream_offset = stream_offset;
             const bool two = hk && b.chain2 && !h->no_chain2;
-            memcpy(ca.spans, two ? b.spans2 : b.spans, sizeof ca.spans);
+            static const bool chain_prof_x = getenv("SNACB_CHAIN_PROF") && atoi(getenv("SNACB_CHAIN_PROF")) != 0;
+            // whole streams, fp16: neighbouring tiles exchange their boundary rows instead of recomputing a halo
+            const int xrows = chain_tile_rows(b.Cout);
+            const bool xch = hk && b.chain_x && !two && !h->no_xch && !trimmed[bi] && !chain_prof_x && h->snake_poly == 0 &&
+                             T % xrows == 0;
+            if (xch) {
+                const int slots = 2 * 2 * h->sm_count;                 // >= 2 x the largest grid (two CTAs per SM)
+                const size_t tiles = static_cast<size_t>(S) * (T / xrows);
+                int rc = grow(h, reinterpret_cast<void**>(&h->xbuf), &h->xbuf_bytes, slots * chain_xch_slot_bytes(b.Cout));
+                if (rc) return rc;
+                rc = grow(h, reinterpret_cast<void**>(&h->xflags), &h->xflags_bytes, tiles * 6 * sizeof(int));
+                if (rc) return rc;
+                CK(h, cudaMemsetAsync(h->xflags, 0, tiles * 6 * sizeof(int), st));
+                ca.xbuf = h->xbuf; ca.xflags = h->xflags; ca.xack = h->xflags + tiles * 3; ca.xslots = slots;
+            }
+            memcpy(ca.spans, two ? b.spans2 : (xch ? b.spans_x : b.spans), sizeof ca.spans);
             ca.tile_counter = h->tile_counter;
             ca.snake_poly = h->snake_poly;
             CK(h, cudaMemsetAsync(h->tile_counter, 0, sizeof(int), st));
@@ -757,6 +778,8 @@ int snacb_create(snacb_handle* out, const snacb_weights* w, int device) {
             if (b.chain2) chain2_build_spans(b.Cout, b.spans2);
             if (b.chain[1]) {
                 chain_build_spans(b.Cout, b.spans);
+                b.chain_x = chain_xch_supported(b.Cout, 1);
+                if (b.chain_x) chain_build_spans(b.Cout, b.spans_x, true);
                 const int C = b.Cout;
                 for (int ri = 0; ri < 3; ++ri) {
                     // snake2(a) = (a'' + sin^2 a'') / alpha2 with a'' = alpha2 a: the 1 / alpha2 goes into W's K columns
@@ -787,6 +810,7 @@ int snacb_create(snacb_handle* out, const snacb_weights* w, int device) {
     if (const char* e = getenv("SNACB_RES_V1")) h->res_v1 = atoi(e) != 0;
     if (const char* e = getenv("SNACB_NO_CHAIN")) h->no_chain = atoi(e) != 0;
     if (const char* e = getenv("SNACB_SNAKE_POLY")) h->snake_poly = atoi(e) & 3;
+    if (const char* e = getenv("SNACB_XCH")) h->no_xch = atoi(e) == 0;
     if (const char* e = getenv("SNACB_CHAIN2")) h->no_chain2 = atoi(e) == 0;
     if (const char* e = getenv("SNACB_NO_TRIM")) h->no_trim = atoi(e) != 0;
     if (const char* e = getenv("SNACB_NO_CONVT_RES")) h->no_convt_res = atoi(e) != 0;
@@ -813,6 +837,8 @@ void snacb_destroy(snacb_handle h) {
     if (h->ws_codes) cudaFree(h->ws_codes);
     if (h->st_tok) cudaFree(h->st_tok);
     if (h->st_pcm) cudaFree(h->st_pcm);
+    if (h->xbuf) cudaFree(h->xbuf);
+    if (h->xflags) cudaFree(h->xflags);
     for (int i = 0; i < 2; ++i) {
         if (h->pl_tok[i]) cudaFree(h->pl_tok[i]);
         if (h->pl_pcm[i]) cudaFree(h->pl_pcm[i]);
@@ -1005,6 +1031,19 @@ int snacb_debug_chain_spans(int C, int16_t* out, int cap) {
     if (!out || !chain_supported(C, 1) || cap < 3 * kChainWarps * kChainSpans * 3) return SNACB_ERR_ARG;
     ChainSpan sp[3][kChainWarps][kChainSpans];
     chain_build_spans(C, sp);
+    for (int l = 0; l < 3; ++l)
+        for (int w = 0; w < kChainWarps; ++w)
+            for (int k = 0; k < kChainSpans; ++k) {
+                int16_t* o = out + ((l * kChainWarps + w) * kChainSpans + k) * 3;
+                o[0] = sp[l][w][k].r_first; o[1] = sp[l][w][k].n_oct; o[2] = sp[l][w][k].kc;
+            }
+    return chain_tile_rows(C) | (chain_warps(C) << 16);
+}
+
+int snacb_debug_chain_spans_x(int C, int16_t* out, int cap) {
+    if (!out || !chain_xch_supported(C, 1) || cap < 3 * kChainWarps * kChainSpans * 3) return SNACB_ERR_ARG;
+    ChainSpan sp[3][kChainWarps][kChainSpans];
+    chain_build_spans(C, sp, true);
     for (int l = 0; l < 3; ++l)
         for (int w = 0; w < kChainWarps; ++w)
             for (int k = 0; k < kChainSpans; ++k) {
