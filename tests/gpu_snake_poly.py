@@ -1,4 +1,5 @@
-"""Half2-polynomial Snake in the fp16 chain prologue (SNACB_SNAKE_POLY = 0 / 1 / 2 / 3, kernels_chain.cu::span_half)
+"""Half2-polynomial Snake in the fp16 chain prologue (SNACB_SNAKE_POLY = 0 / 2, kernels_chain.cu::span_half; the build
+measured in DESIGN.md section 6 also instantiated 1 = snake1 only and 3 = both)
 on a GPU box: SNR of each setting against the oracle (same tokens, same injected noise), then the chain kernels'
 times at B windows.
 
@@ -20,7 +21,7 @@ def main():
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
     sd = synth.make_state_dict(0)
     decs = {}
-    for p in (0, 1, 2, 3):
+    for p in (0, 2):
         os.environ["SNACB_SNAKE_POLY"] = str(p)
         decs[p] = SnacDecoder(sd)
     os.environ.pop("SNACB_SNAKE_POLY")
