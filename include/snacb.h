@@ -115,6 +115,14 @@ int snacb_unpack(snacb_handle h, const int32_t* tok, int B, int ntok, int flags,
 int snacb_decode(snacb_handle h, const int32_t* tok, int B, int tok_stride, int frames, int flags,
                  const float* const* noise, uint64_t seed, int16_t* pcm, float* wave, void* stream);
 
+/* snacb_decode with the built-in NoiseBlock noise of row i keyed by stream_keys[i] (device int32 [B], >= 0) instead of
+ * by the row's position in the batch: a stream then draws the same noise for the same time step whichever rows share
+ * its launch and however many frames are decoded -- what a policy that re-decodes growing prefixes of many streams
+ * needs (tts_inference_b200/policy.py).  NULL keys = snacb_decode. */
+int snacb_decode_keyed(snacb_handle h, const int32_t* tok, int B, int tok_stride, int frames, int flags,
+                       const float* const* noise, uint64_t seed, const int32_t* stream_keys, int16_t* pcm, float* wave,
+                       void* stream);
+
 /* Same with HOST buffers (pinned or pageable): copies the tokens in, decodes, copies the PCM out and
  * synchronises -- the boundary the reference's helper has (torch.tensor(..., device=) in,
  * .cpu().numpy().tobytes() out; modal_audio_stream.py:176-202). */

@@ -198,13 +198,25 @@ def test_ragged_tail_is_dropped(decoder):
 
 
 def test_builtin_noise_matches_counter_rng(decoder, oracle_model):
-    """noise=None uses the in-kernel counter RNG keyed by seed: same stream as synth.make_noises."""
+    """noise=None uses the in-kernel counter RNG keyed by (seed, block, stream, t): same values as synth.make_noises_rng."""
     tokens = synth.make_tokens(3, 4, seed=12)
-    ref, _ = oracle_decode(oracle_model, tokens, synth.make_noises(3, 16, seed=1234))
+    ref, _ = oracle_decode(oracle_model, tokens, synth.make_noises_rng(3, 16, seed=1234))
     _, wave = decoder.decode(_cuda(tokens), raw_ids=True, seed=1234, precision="fp32", return_wave=True)
     assert np.abs(wave.cpu().numpy() - ref).max() <= FP32_TOL
     _, w2 = decoder.decode(_cuda(tokens), raw_ids=True, seed=1235, precision="fp32", return_wave=True)
     assert not torch.equal(wave, w2)
+
+
+@pytest.mark.parametrize("prec", ["fp32", "fp16"])
+def test_builtin_noise_is_independent_of_decoded_length(decoder, prec):
+    """A longer decode of the same stream redraws the same noise for the shared time steps: samples whose receptive
+    field lies inside the shorter prefix come out bit-identical (what streaming policies that re-decode prefixes need)."""
+    tokens = synth.make_tokens(3, 12, seed=14)
+    long_ = decoder.decode(_cuda(tokens), raw_ids=True, seed=77, precision=prec)
+    short = decoder.decode(_cuda(np.ascontiguousarray(tokens[:, :7 * 8])), raw_ids=True, seed=77, precision=prec)
+    n = 2048 * (8 - 3)                                   # 3 frames of margin >> receptive field
+    assert torch.equal(long_[:, :n], short[:, :n])
+    assert not torch.equal(long_[:, 2048 * 7: 2048 * 8], short[:, 2048 * 7:])
 
 
 @pytest.mark.parametrize("prec", ["fp32", "fp16", "bf16"])
@@ -327,7 +339,7 @@ def test_full_size_batch_properties(decoder, oracle_model):
     assert a.shape == (B, 2048) and torch.equal(a, b)
     assert int((a != 0).sum()) > B * 1024
     idx = [0, 511, 1023]
-    nz = synth.make_noises(B, 16, seed=9)
+    nz = synth.make_noises_rng(B, 16, seed=9)
     sub = [np.ascontiguousarray(n[idx]) for n in nz]
     ref, _ = oracle_decode(oracle_model, tokens[idx], sub)
     _, w = decoder.decode(_cuda(tokens[idx]), raw_ids=True, noise=[_cuda(n) for n in sub], return_wave=True)

@@ -194,3 +194,77 @@ def test_io_bad_arguments():
     lib.snacb_ingest_destroy(g)
     assert lib.snacb_pcm_to_wav(None, 1, 4, 0, None, None) == -1
     assert lib.snacb_base64_len(5) == 8 and lib.snacb_ingest_window_capacity(10, 29) == 30
+
+
+# ------------------------------------------------------------------------------------------------ lookahead policy
+class _FakeDecoder:
+    """Stands in for SnacDecoder on the CPU: sample t of a row is frames * 1_000_000 + t, so a test can tell which
+    decode a sample came from."""
+    device = "cpu"
+
+    def decode(self, tok, **kw):
+        import torch
+        B, n = tok.shape
+        f = n // 7
+        return (torch.arange(2048 * f).unsqueeze(0).repeat(B, 1) + 0 * f).to(torch.int32) + 1_000_000 * f
+
+
+def test_lookahead_policy_bookkeeping(monkeypatch):
+    """PIPELINE_REPORT.md:497-505: decode all frames every `frames_per_chunk` new frames, emit only samples with
+    >= 5 frames of future context, never twice, flush at the end."""
+    import torch
+    from tts_inference_b200 import policy
+    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self, raising=False)
+    la = policy.LookaheadStreamingDecoder(_FakeDecoder(), lookahead_frames=5, frames_per_chunk=3)
+    got = {"a": [], "b": []}
+    total = {"a": 23, "b": 4}
+    for step in range(30):
+        for s in ("a", "b"):
+            if step < total[s]:
+                la.push(s, [128266 + step] * 7)
+            elif step == total[s]:
+                la.finish(s)
+        for s, pcm in la.step():
+            got[s].append(pcm)
+    for s in ("a", "b"):
+        cat = np.concatenate(got[s])
+        assert cat.size == 2048 * total[s]
+        assert (cat % 1_000_000 == np.arange(cat.size)).all()          # every sample exactly once, in order
+        frames_of = cat // 1_000_000                                   # which decode emitted it
+        t = np.arange(cat.size)
+        final = frames_of == total[s]
+        assert ((frames_of - 5) * 2048 > t)[~final].all()              # >= 5 frames of context unless it is the flush
+    assert policy.stable_samples(4, 5, False) == 0 and policy.stable_samples(4, 5, True) == 8192
+    assert not la._streams
+
+
+@pytest.mark.gpu
+def test_lookahead_policy_against_batch_decode(decoder):
+    """Streamed audio against the batch decode of the same tokens.  The built-in noise is keyed by (stream, t) and not by
+    the decoded length, and 5 frames of lookahead exceed the decoder's receptive field, so the streamed samples are
+    BIT-IDENTICAL to the batch decode (the reference, which redraws torch.randn per decode, accepts MSE < 1e-3 and
+    correlation > 0.998, PIPELINE_REPORT.md:513-519)."""
+    import torch
+    from tts_inference_b200 import policy, synth
+    lens = [24, 17, 24, 9]                          # streams of different lengths share (and leave) the batched decodes
+    tokens = synth.make_tokens(4, 24, seed=9)
+    la = policy.LookaheadStreamingDecoder(decoder, lookahead_frames=5, frames_per_chunk=4, seed=3)
+    got = [[] for _ in lens]
+    for f in range(max(lens) + 1):
+        for s, n in enumerate(lens):
+            if f < n:
+                la.push(s, tokens[s, 7 * f: 7 * f + 7].tolist())
+            elif f == n:
+                la.finish(s)
+        for s, pcm in la.step():
+            got[s].append(pcm)
+    keys = torch.arange(4, dtype=torch.int32).cuda()
+    for s, n in enumerate(lens):
+        ref = decoder.decode(torch.from_numpy(np.ascontiguousarray(tokens[s:s + 1, :7 * n])).cuda(), raw_ids=True, seed=3,
+                             stream_keys=keys[s:s + 1]).cpu().numpy()[0]
+        cat = np.concatenate(got[s])
+        assert cat.size == 2048 * n
+        mse = np.mean(((cat.astype(np.float64) - ref) / 32768.0) ** 2)
+        corr = np.corrcoef(cat.astype(np.float64), ref.astype(np.float64))[0, 1]
+        assert mse < 1e-3 and corr > 0.998, (mse, corr)        # the reference's thresholds
+        assert np.array_equal(cat, ref), s                       # and in fact bit-identical

@@ -102,9 +102,10 @@ class SnacDecoder:
     def decode(self, tokens, *, raw_ids: bool = False, extract_slice: bool = False,
                noise: Optional[Sequence] = None, seed: int = 0, precision: str = "fp16",
                out=None, return_wave: bool = False, keep_taps: bool = False, stream_fp32: bool = False,
-               unfused: bool = False):
+               unfused: bool = False, stream_keys=None):
         """tokens: cuda int32 [B, n>=7F] (trailing partial frame ignored, as the helper does).
-        Returns int16 [B, samples] (and the fp32 waveform when ``return_wave``)."""
+        Returns int16 [B, samples] (and the fp32 waveform when ``return_wave``).
+        ``stream_keys`` (cuda int32 [B], optional): key of each row's built-in noise instead of its position in the batch."""
         import torch
         assert tokens.is_cuda and tokens.dtype == torch.int32 and tokens.dim() == 2 and tokens.is_contiguous()
         B, n = tokens.shape
@@ -128,8 +129,13 @@ class SnacDecoder:
                 t = t.contiguous()
                 keep.append(t)
                 nz_arr[i] = t.data_ptr()
-        rc = self._lib.snacb_decode(self._h, tokens.data_ptr(), B, n, frames, flags, nz_arr, C.c_uint64(seed),
-                                    out.data_ptr(), wave.data_ptr() if wave is not None else None, self._stream_ptr())
+        keys = None
+        if stream_keys is not None:
+            assert stream_keys.is_cuda and stream_keys.dtype == torch.int32 and stream_keys.numel() == B
+            stream_keys = stream_keys.contiguous()
+            keys = stream_keys.data_ptr()
+        rc = self._lib.snacb_decode_keyed(self._h, tokens.data_ptr(), B, n, frames, flags, nz_arr, C.c_uint64(seed), keys,
+                                          out.data_ptr(), wave.data_ptr() if wave is not None else None, self._stream_ptr())
         self._check(rc, "snacb_decode")
         return (out, wave) if return_wave else out
 

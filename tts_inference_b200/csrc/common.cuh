@@ -44,6 +44,7 @@ struct GemmArgs {
     unsigned long long seed;
     int noise_stage;        // decoder block index, keys the counter RNG
     int stream_offset;      // global index of stream 0 of this chunk (counter RNG addressing)
+    const int* stream_keys; // optional [S]: counter RNG key of each stream instead of stream_offset + s
     const void* resid;      // residual / y tensor, [S*Tin*up][Cout] (16-bit operand type on the tensor-core path)
     void* out;              // [S*Tin*up][Cout]
 };
@@ -83,6 +84,7 @@ struct ChainArgs {
     const float* noise;           // [S][T] injected noise or null -> counter RNG
     unsigned long long seed;
     int noise_stage, stream_offset;
+    const int* stream_keys;       // optional [S]: counter RNG key of each stream instead of stream_offset + s
     ChainSpan spans[3][kChainWarps][kChainSpans];
     int* tile_counter;            // zeroed before the launch: tiles beyond the first gridDim.x are claimed dynamically
     unsigned char* xbuf;          // halo exchange (kernels_chain.cu, XCH): boundary rows [xslots][3 layers][2 sides][C/64][27][128 B], or null
@@ -136,6 +138,12 @@ __host__ __device__ __forceinline__ unsigned long long splitmix64(unsigned long 
     z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
     z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
     return z ^ (z >> 31);
+}
+// Counter of the NoiseBlock value of (stream, time step): independent of the decoded length, so that decoding a longer
+// prefix of a stream redraws the SAME noise for the samples it shares with the shorter one (streaming policies re-decode
+// prefixes: tts_inference_b200/policy.py) and of the batch split.  synth.make_noises_rng mirrors it.
+__host__ __device__ __forceinline__ unsigned long long noise_counter(long long stream, int t) {
+    return (static_cast<unsigned long long>(stream) << 32) | static_cast<unsigned int>(t);
 }
 __device__ __forceinline__ float counter_normal(unsigned long long key, unsigned long long ctr) {
     unsigned long long b = splitmix64(key + ctr);

@@ -435,7 +435,7 @@ k_chain2(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtens
                 float v = 0.f;
                 if (static_cast<unsigned>(t) < static_cast<unsigned>(a.T))
                     v = a.noise ? a.noise[static_cast<size_t>(s) * a.T + t]
-                                : counter_normal(key, static_cast<unsigned long long>(a.stream_offset + s) * a.T + t);
+                                : counter_normal(key, noise_counter(a.stream_keys ? a.stream_keys[s] : a.stream_offset + s, t));
                 sNz[i] = v;
             }
         }

@@ -296,7 +296,7 @@ void clear_taps(snacb_handle h) {
 // One group of S streams through the whole path.
 // ------------------------------------------------------------------------------------------------
 int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, int flags, const float* const* noise,
-              uint64_t seed, int stream_offset, int16_t* pcm, float* wave, cudaStream_t st) {
+              uint64_t seed, int stream_offset, const int32_t* stream_keys, int16_t* pcm, float* wave, cudaStream_t st) {
     const bool f32 = (flags & SNACB_FP32) != 0;
     const bool xf32 = f32 || (flags & SNACB_STREAM_FP32);      // residual stream dtype
     const int hk = (flags & SNACB_BF16) ? 0 : 1;               // 16-bit operand type: 0 bf16, 1 fp16
@@ -348,7 +348,7 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
             a.Tbox = tb; a.Wbox = 128 / tb;
         }
         a.seed = seed;
-        a.stream_offset = stream_offset;
+        a.stream_offset = stream_offset; a.stream_keys = stream_keys;
         h->launches++;
         if (f32) {
             prof_begin(h, pname, st);
@@ -437,7 +437,7 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
                 if (rc) return rc;
                 rc = act_map(h, &mo, oth, b.Cout, T, S, 128 * b.s, 1, hk);
                 if (rc) return rc;
-                a.seed = seed; a.stream_offset = stream_offset; a.Tbox = 128; a.Wbox = 1;
+                a.seed = seed; a.stream_offset = stream_offset; a.stream_keys = stream_keys; a.Tbox = 128; a.Wbox = 1;
                 prof_begin(h, nm, st);
                 cudaError_t le = launch_convt_res(hk, a, *ma, *mw, *mo, h->sm_count, st);
                 prof_end(h, st);
@@ -450,7 +450,7 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
                 if (rc) return rc;
                 rc = weight_map(h, &mw, b.ct_h[hk], b.s * b.Cout, 2 * b.Cin, b.Cout, hk);
                 if (rc) return rc;
-                a.seed = seed; a.stream_offset = stream_offset; a.Tbox = 128; a.Wbox = 1;
+                a.seed = seed; a.stream_offset = stream_offset; a.stream_keys = stream_keys; a.Tbox = 128; a.Wbox = 1;
                 prof_begin(h, nm, st);
                 cudaError_t le = launch_convt_ph(hk, a, *ma, *mw, h->sm_count, st);
                 prof_end(h, st);
@@ -476,7 +476,7 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
             ca.bias_cum = b.bias_cum;
             ca.alpha_next = bi < 3 ? h->blk[bi + 1].alpha : h->tail_alpha;
             ca.inv_next = bi < 3 ? h->blk[bi + 1].inv_alpha : h->tail_inv;
-            ca.noise = noise ? noise[bi] : nullptr; ca.seed = seed; ca.noise_stage = bi; ca.stream_offset = stream_offset;
+            ca.noise = noise ? noise[bi] : nullptr; ca.seed = seed; ca.noise_stage = bi; ca.stream_offset = stream_offset; ca.stream_keys = stream_keys;
             const bool two = hk && b.chain2 && !h->no_chain2;
             static const bool chain_prof_x = getenv("SNACB_CHAIN_PROF") && atoi(getenv("SNACB_CHAIN_PROF")) != 0;
             // whole streams, fp16: neighbouring tiles exchange their boundary rows instead of recomputing a halo
@@ -879,6 +879,12 @@ int snacb_unpack(snacb_handle h, const int32_t* tok, int B, int ntok, int flags,
 
 int snacb_decode(snacb_handle h, const int32_t* tok, int B, int tok_stride, int frames, int flags,
                  const float* const* noise, uint64_t seed, int16_t* pcm, float* wave, void* stream) {
+    return snacb_decode_keyed(h, tok, B, tok_stride, frames, flags, noise, seed, nullptr, pcm, wave, stream);
+}
+
+int snacb_decode_keyed(snacb_handle h, const int32_t* tok, int B, int tok_stride, int frames, int flags,
+                       const float* const* noise, uint64_t seed, const int32_t* stream_keys, int16_t* pcm, float* wave,
+                       void* stream) {
     if (!h) return SNACB_ERR_ARG;
     if (B < 0 || frames < 0 || tok_stride < frames * kFrame)
         return fail(h, SNACB_ERR_ARG, "snacb_decode: bad sizes B=%d frames=%d tok_stride=%d", B, frames, tok_stride);
@@ -921,7 +927,8 @@ int snacb_decode(snacb_handle h, const int32_t* tok, int B, int tok_stride, int 
         const float* nz[4];
         if (noise) for (int i = 0; i < 4; ++i) nz[i] = noise[i] + static_cast<size_t>(g0) * nlen[i];
         int rc = run_group(h, tok + static_cast<size_t>(g0) * tok_stride, S, tok_stride, frames, flags,
-                           noise ? nz : nullptr, seed, g0, pcm + static_cast<size_t>(g0) * n_out,
+                           noise ? nz : nullptr, seed, g0, stream_keys ? stream_keys + g0 : nullptr,
+                           pcm + static_cast<size_t>(g0) * n_out,
                            wave ? wave + static_cast<size_t>(g0) * n_out : nullptr, st);
         if (rc) return rc;
     }

@@ -1,0 +1,104 @@
+"""Streaming policies above the decode path, for many streams at once.
+
+``LookaheadStreamingDecoder`` follows the algorithm the reference documents for its recommended engine
+(tensorrt_tts/PIPELINE_REPORT.md:475-511; the class itself is not in the reference tree, so this layer is built from
+that description and has no reference code to be pinned against):
+
+  1. buffer ALL audio tokens of a stream;
+  2. whenever ``frames_per_chunk`` new complete frames have arrived, decode ALL frames from frame 0;
+  3. emit only samples that have at least ``lookahead_frames`` (5 = 10 240 samples, ~430 ms) of future context,
+     tracking ``samples_emitted`` so that nothing is emitted twice;
+  4. at end of stream decode once more and emit everything that is left.
+
+Differences by construction: every stream due for a decode in a step is decoded in ONE batched call per distinct length
+(the reference decodes one stream per call), and the NoiseBlock noise comes from the counter RNG keyed by
+(seed, block, row, t) -- independent of the decoded length -- so a re-decode of a longer prefix draws the SAME noise for
+the samples it shares with the shorter one.  Since 5 frames of lookahead exceed the decoder's receptive field, the
+streamed audio is then bit-identical to the batch decode of the whole utterance (tests/test_io.py), where the
+reference, redrawing torch.randn on every decode (PIPELINE_REPORT.md:481), reports correlation 0.9987.  Each stream's noise is keyed by
+its own ``noise_key`` (snacb_decode_keyed), not by its row in whatever batch it happens to be decoded with.
+The quadratic re-decode is the reference's; an incremental decoder that reuses per-stage state is DESIGN.md section 8 "next".
+"""
+from __future__ import annotations
+
+from typing import Dict, Hashable, Iterable, List, Tuple
+
+import numpy as np
+
+FRAME = 7
+SAMPLES_PER_FRAME = 2048
+
+
+def stable_samples(frames: int, lookahead_frames: int, final: bool) -> int:
+    """Samples of a ``frames``-frame decode that may be emitted (PIPELINE_REPORT.md:497-505)."""
+    return SAMPLES_PER_FRAME * (frames if final else max(0, frames - lookahead_frames))
+
+
+class _Stream:
+    __slots__ = ("ids", "decoded_frames", "emitted", "done", "key")
+
+    def __init__(self, key: int):
+        self.key = key
+        self.ids: List[int] = []
+        self.decoded_frames = 0
+        self.emitted = 0
+        self.done = False
+
+
+class LookaheadStreamingDecoder:
+    def __init__(self, decoder, lookahead_frames: int = 5, frames_per_chunk: int = 4, raw_ids: bool = True,
+                 precision: str = "fp16", seed: int = 0):
+        if lookahead_frames < 0 or frames_per_chunk < 1:
+            raise ValueError("lookahead_frames >= 0 and frames_per_chunk >= 1")
+        self._dec = decoder
+        self.lookahead_frames, self.frames_per_chunk = int(lookahead_frames), int(frames_per_chunk)
+        self.raw_ids, self.precision, self.seed = raw_ids, precision, int(seed)
+        self._streams: Dict[Hashable, _Stream] = {}
+        self._next_key = 0
+
+    def _get(self, stream: Hashable) -> _Stream:
+        st = self._streams.get(stream)
+        if st is None:
+            st = self._streams[stream] = _Stream(self._next_key)       # noise key: order of first appearance
+            self._next_key = (self._next_key + 1) & 0x7FFFFFFF
+        return st
+
+    # ------------------------------------------------------------------ producers
+    def push(self, stream: Hashable, ids: Iterable[int]) -> None:
+        st = self._get(stream)
+        if st.done:
+            raise ValueError(f"stream {stream!r} already finished")
+        st.ids.extend(int(i) for i in ids)
+
+    def finish(self, stream: Hashable) -> None:
+        self._get(stream).done = True
+
+    # ------------------------------------------------------------------ decode tick
+    def step(self) -> List[Tuple[Hashable, np.ndarray]]:
+        """Decode every stream that is due (``frames_per_chunk`` new frames, or finished) -- one batched call per
+        distinct length -- and return [(stream, new int16 samples)] for the streams that have something to emit.
+        Finished streams are forgotten once flushed."""
+        import torch
+        due: Dict[int, List[Hashable]] = {}
+        for key, st in self._streams.items():
+            frames = len(st.ids) // FRAME
+            if frames > 0 and (st.done or frames - st.decoded_frames >= self.frames_per_chunk) and \
+                    (frames != st.decoded_frames or st.done):
+                due.setdefault(frames, []).append(key)
+        out: List[Tuple[Hashable, np.ndarray]] = []
+        for frames, keys in sorted(due.items()):
+            tok = np.asarray([self._streams[k].ids[: frames * FRAME] for k in keys], dtype=np.int64)
+            tok = np.clip(tok, -(2 ** 31), 2 ** 31 - 1).astype(np.int32)
+            nkeys = torch.tensor([self._streams[k].key for k in keys], dtype=torch.int32).cuda(self._dec.device)
+            pcm = self._dec.decode(torch.from_numpy(tok).cuda(self._dec.device), raw_ids=self.raw_ids,
+                                   extract_slice=False, seed=self.seed, precision=self.precision, stream_keys=nkeys)
+            for row, k in enumerate(keys):
+                st = self._streams[k]
+                st.decoded_frames = frames
+                end = stable_samples(frames, self.lookahead_frames, st.done)
+                if end > st.emitted:
+                    out.append((k, pcm[row, st.emitted:end].cpu().numpy()))
+                    st.emitted = end
+        for key in [k for k, st in self._streams.items() if st.done]:
+            del self._streams[key]
+        return out

@@ -177,6 +177,16 @@ def noise_lengths(t0: int) -> List[int]:
     return out
 
 
+def make_noises_rng(batch: int, t0: int, seed: int, stream_offset: int = 0) -> List[np.ndarray]:
+    """The values the kernels' built-in counter RNG draws (csrc/common.cuh noise_counter): stream key
+    (seed, 100 + block), counter (stream << 32) | t -- independent of the decoded length and of the batch split."""
+    out = []
+    for i, t in enumerate(noise_lengths(t0)):
+        rows = [rng_normal(seed, 100 + i, t, offset=(stream_offset + s) << 32) for s in range(batch)]
+        out.append(np.stack(rows).reshape(batch, 1, t).astype(np.float32))
+    return out
+
+
 def make_noises(batch: int, t0: int, seed: int = 7) -> List[np.ndarray]:
     """Injected NoiseBlock tensors, float32 [B,1,T_i] for the four decoder blocks."""
     return [rng_normal(seed, 100 + i, batch * t).reshape(batch, 1, t).astype(np.float32)
