@@ -123,6 +123,15 @@ int snacb_decode_keyed(snacb_handle h, const int32_t* tok, int B, int tok_stride
                        const float* const* noise, uint64_t seed, const int32_t* stream_keys, int16_t* pcm, float* wave,
                        void* stream);
 
+/* snacb_decode_keyed that writes only samples [sample_lo, sample_hi) of every row (pcm / wave are [B][sample_hi -
+ * sample_lo]; SNACB_EXTRACT_SLICE is ignored) and, on the tensor-core path, computes only their receptive field in
+ * blocks 1-3 (the dead-sample trimming of the sliced call, for an arbitrary range).  Bit-identical to slicing the full
+ * decode.  A policy that re-decodes a growing prefix and emits only the new stable samples pays for those samples, not
+ * for the whole prefix (block 0 and the stem, ~10 % of a decode, are still computed in full). */
+int snacb_decode_range(snacb_handle h, const int32_t* tok, int B, int tok_stride, int frames, int flags,
+                       const float* const* noise, uint64_t seed, const int32_t* stream_keys, int sample_lo, int sample_hi,
+                       int16_t* pcm, float* wave, void* stream);
+
 /* Same with HOST buffers (pinned or pageable): copies the tokens in, decodes, copies the PCM out and
  * synchronises -- the boundary the reference's helper has (torch.tensor(..., device=) in,
  * .cpu().numpy().tobytes() out; modal_audio_stream.py:176-202). */

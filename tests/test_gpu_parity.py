@@ -190,6 +190,22 @@ def test_sliced_call_trims_dead_samples_bit_identically(decoder, F_, unfused):
     assert torch.equal(rng, rng_full[:, 2048:4096])
 
 
+@pytest.mark.parametrize("prec", ["fp16", "bf16", "fp32"])
+@pytest.mark.parametrize("B,F_,lo,hi", [(3, 4, 2048, 4096), (2, 4, 0, 100), (2, 4, 8000, 8192), (5, 12, 6144, 14336),
+                                        (1, 40, 61440, 71680), (4, 9, 0, 18432), (2, 1, 5, 2043), (37, 6, 4096, 8192)])
+def test_ranged_decode_equals_slice_of_full_decode(decoder, prec, B, F_, lo, hi):
+    """snacb_decode_range: samples [lo, hi) only, their receptive field only -- bit-identical to the full decode's slice."""
+    tokens = _cuda(synth.make_tokens(B, F_, seed=40 + F_))
+    keys = _cuda(np.arange(100, 100 + B, dtype=np.int32))
+    full = decoder.decode(tokens, raw_ids=True, seed=6, precision=prec, stream_keys=keys, return_wave=True)
+    part = decoder.decode(tokens, raw_ids=True, seed=6, precision=prec, stream_keys=keys, return_wave=True,
+                          sample_range=(lo, hi))
+    assert part[0].shape == (B, hi - lo)
+    assert torch.equal(part[0], full[0][:, lo:hi]) and torch.equal(part[1], full[1][:, lo:hi])
+    with pytest.raises(ValueError):
+        decoder.decode(tokens, raw_ids=True, sample_range=(0, 2048 * F_ + 1))
+
+
 def test_ragged_tail_is_dropped(decoder):
     tokens = synth.make_tokens(2, 5, seed=8)
     a = decoder.decode(_cuda(tokens[:, :31]), raw_ids=True, seed=1)     # 4 frames + 3 stray tokens

@@ -202,11 +202,12 @@ class _FakeDecoder:
     decode a sample came from."""
     device = "cpu"
 
-    def decode(self, tok, **kw):
+    def decode(self, tok, sample_range=None, **kw):
         import torch
         B, n = tok.shape
         f = n // 7
-        return (torch.arange(2048 * f).unsqueeze(0).repeat(B, 1) + 0 * f).to(torch.int32) + 1_000_000 * f
+        full = (torch.arange(2048 * f).unsqueeze(0).repeat(B, 1) + 0 * f).to(torch.int32) + 1_000_000 * f
+        return full if sample_range is None else full[:, sample_range[0]:sample_range[1]]
 
 
 def test_lookahead_policy_bookkeeping(monkeypatch):

@@ -34,7 +34,7 @@ class Weights(C.Structure):
 
 
 EXPORTS = [
-    "snacb_version", "snacb_create", "snacb_destroy", "snacb_last_error", "snacb_unpack", "snacb_decode", "snacb_decode_keyed",
+    "snacb_version", "snacb_create", "snacb_destroy", "snacb_last_error", "snacb_unpack", "snacb_decode", "snacb_decode_keyed", "snacb_decode_range",
     "snacb_decode_host", "snacb_decode_host_submit", "snacb_decode_host_wait", "snacb_samples_out", "snacb_set_group_bytes", "snacb_stats",
     "snacb_profile", "snacb_profile_report", "snacb_debug_tap_count", "snacb_debug_tap_info", "snacb_debug_tap_copy", "snacb_debug_chain_spans", "snacb_debug_chain_spans_x", "snacb_debug_chain2_spans",
     "snacb_batcher_create", "snacb_batcher_destroy", "snacb_batcher_push", "snacb_batcher_end",
@@ -65,6 +65,8 @@ def load() -> C.CDLL:
     lib.snacb_unpack.argtypes = [vp, i32p, C.c_int, C.c_int, C.c_int, i32p, i32p, i32p, vp]
     lib.snacb_decode.argtypes = [vp, i32p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp), u64, i16p, vp, vp]
     lib.snacb_decode_keyed.argtypes = [vp, i32p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp), u64, i32p, i16p, vp, vp]
+    lib.snacb_decode_range.argtypes = [vp, i32p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp), u64, i32p, C.c_int, C.c_int,
+                                       i16p, vp, vp]
     lib.snacb_decode_host.argtypes = [vp, i32p, C.c_int, C.c_int, C.c_int, C.c_int, u64, i16p]
     lib.snacb_decode_host_submit.argtypes = [vp, i32p, C.c_int, C.c_int, C.c_int, C.c_int, u64, i16p]
     lib.snacb_decode_host_wait.argtypes = [vp]

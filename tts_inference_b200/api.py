@@ -102,16 +102,23 @@ class SnacDecoder:
     def decode(self, tokens, *, raw_ids: bool = False, extract_slice: bool = False,
                noise: Optional[Sequence] = None, seed: int = 0, precision: str = "fp16",
                out=None, return_wave: bool = False, keep_taps: bool = False, stream_fp32: bool = False,
-               unfused: bool = False, stream_keys=None):
+               unfused: bool = False, stream_keys=None, sample_range: Optional[Tuple[int, int]] = None):
         """tokens: cuda int32 [B, n>=7F] (trailing partial frame ignored, as the helper does).
         Returns int16 [B, samples] (and the fp32 waveform when ``return_wave``).
-        ``stream_keys`` (cuda int32 [B], optional): key of each row's built-in noise instead of its position in the batch."""
+        ``stream_keys`` (cuda int32 [B], optional): key of each row's built-in noise instead of its position in the batch.
+        ``sample_range`` (lo, hi): write only samples [lo, hi) of every row and compute only their receptive field."""
         import torch
         assert tokens.is_cuda and tokens.dtype == torch.int32 and tokens.dim() == 2 and tokens.is_contiguous()
         B, n = tokens.shape
         frames = n // FRAME
         flags = self._flags(raw_ids, extract_slice, precision, keep_taps, stream_fp32, unfused)
         ns = self.samples_out(frames, extract_slice)
+        lo = hi = 0
+        if sample_range is not None:
+            lo, hi = int(sample_range[0]), int(sample_range[1])
+            if not 0 <= lo < hi <= 2048 * frames:
+                raise ValueError("sample_range outside the decoded samples")
+            ns = hi - lo
         if out is None:
             out = torch.empty((B, ns), dtype=torch.int16, device=tokens.device)
         else:
@@ -134,8 +141,9 @@ class SnacDecoder:
             assert stream_keys.is_cuda and stream_keys.dtype == torch.int32 and stream_keys.numel() == B
             stream_keys = stream_keys.contiguous()
             keys = stream_keys.data_ptr()
-        rc = self._lib.snacb_decode_keyed(self._h, tokens.data_ptr(), B, n, frames, flags, nz_arr, C.c_uint64(seed), keys,
-                                          out.data_ptr(), wave.data_ptr() if wave is not None else None, self._stream_ptr())
+        rc = self._lib.snacb_decode_range(self._h, tokens.data_ptr(), B, n, frames, flags, nz_arr, C.c_uint64(seed), keys,
+                                          lo, hi, out.data_ptr(), wave.data_ptr() if wave is not None else None,
+                                          self._stream_ptr())
         self._check(rc, "snacb_decode")
         return (out, wave) if return_wave else out
 

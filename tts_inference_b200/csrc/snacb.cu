@@ -296,7 +296,8 @@ void clear_taps(snacb_handle h) {
 // One group of S streams through the whole path.
 // ------------------------------------------------------------------------------------------------
 int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, int flags, const float* const* noise,
-              uint64_t seed, int stream_offset, const int32_t* stream_keys, int16_t* pcm, float* wave, cudaStream_t st) {
+              uint64_t seed, int stream_offset, const int32_t* stream_keys, int out_lo, int out_hi, int16_t* pcm,
+              float* wave, cudaStream_t st) {
     const bool f32 = (flags & SNACB_FP32) != 0;
     const bool xf32 = f32 || (flags & SNACB_STREAM_FP32);      // residual stream dtype
     const int hk = (flags & SNACB_BF16) ? 0 : 1;               // 16-bit operand type: 0 bf16, 1 fp16
@@ -388,11 +389,16 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
     bool trimmed[4] = {false, false, false, false};
     {
         const int Tfin = 2048 * F;
-        const bool want = (flags & SNACB_EXTRACT_SLICE) && Tfin > 4096 && !f32 && !xf32 && !taps && !h->no_trim;
+        // output samples [out_lo, out_hi): the caller's range (snacb_decode_range), the reference's slice, or everything
+        if (out_hi <= out_lo) {
+            const bool sl = (flags & SNACB_EXTRACT_SLICE) && Tfin > 4096;
+            out_lo = sl ? 2048 : 0; out_hi = sl ? 4096 : Tfin;
+        }
+        const bool want = (out_hi - out_lo < Tfin) && !f32 && !xf32 && !taps && !h->no_trim;
         int Tb[4], tt = T0;
         for (int bi = 0; bi < 4; ++bi) { tt *= h->blk[bi].s; Tb[bi] = tt; }
         auto clip = [](Rng r, int T) { return Rng{r.lo < 0 ? 0 : r.lo, r.hi > T ? T : r.hi}; };
-        Rng need = clip(Rng{2048 - 3, 4096 + 3}, Tb[3]);            // tail conv k7
+        Rng need = clip(Rng{out_lo - 3, out_hi + 3}, Tb[3]);        // tail conv k7
         for (int bi = 3; bi >= 0; --bi) {
             const BlockW& b = h->blk[bi];
             const int Tinb = bi ? Tb[bi - 1] : T0;
@@ -657,8 +663,7 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
 
     // ---- tail
     const int T = Tin;                                   // 2048 * F samples
-    const bool slice = (flags & SNACB_EXTRACT_SLICE) && T > 4096;
-    const int t_begin = slice ? 2048 : 0, n_out = slice ? 2048 : T;
+    const int t_begin = out_lo, n_out = out_hi - out_lo;
     prof_begin(h, "tail", st);
     if (f32) launch_tail<float>(static_cast<const float*>(cur), S, T, t_begin, n_out, h->tail_w, h->tail_b, pcm, wave, st);
     else if (hk) launch_tail<__half>(static_cast<const __half*>(cur), S, T, t_begin, n_out, h->tail_w, h->tail_b, pcm, wave, st);
@@ -885,7 +890,16 @@ int snacb_decode(snacb_handle h, const int32_t* tok, int B, int tok_stride, int 
 int snacb_decode_keyed(snacb_handle h, const int32_t* tok, int B, int tok_stride, int frames, int flags,
                        const float* const* noise, uint64_t seed, const int32_t* stream_keys, int16_t* pcm, float* wave,
                        void* stream) {
+    return snacb_decode_range(h, tok, B, tok_stride, frames, flags, noise, seed, stream_keys, 0, 0, pcm, wave, stream);
+}
+
+int snacb_decode_range(snacb_handle h, const int32_t* tok, int B, int tok_stride, int frames, int flags,
+                       const float* const* noise, uint64_t seed, const int32_t* stream_keys, int sample_lo, int sample_hi,
+                       int16_t* pcm, float* wave, void* stream) {
     if (!h) return SNACB_ERR_ARG;
+    const bool ranged = sample_lo != 0 || sample_hi != 0;
+    if (ranged && (sample_lo < 0 || sample_hi <= sample_lo || sample_hi > 2048LL * frames))
+        return fail(h, SNACB_ERR_ARG, "snacb_decode_range: bad sample range [%d, %d) for %d frames", sample_lo, sample_hi, frames);
     if (B < 0 || frames < 0 || tok_stride < frames * kFrame)
         return fail(h, SNACB_ERR_ARG, "snacb_decode: bad sizes B=%d frames=%d tok_stride=%d", B, frames, tok_stride);
     if (B == 0 || frames == 0) return SNACB_OK;
@@ -919,7 +933,7 @@ int snacb_decode_keyed(snacb_handle h, const int32_t* tok, int B, int tok_stride
         if (rc) return rc;
         h->ws_codes_elems = cbytes / sizeof(int32_t);
     }
-    const int n_out = snacb_samples_out(frames, flags);
+    const int n_out = ranged ? sample_hi - sample_lo : snacb_samples_out(frames, flags);
     const int T0 = 4 * frames;
     const size_t nlen[4] = {(size_t)T0 * 8, (size_t)T0 * 64, (size_t)T0 * 256, (size_t)T0 * 512};
     for (int g0 = 0; g0 < B; g0 += static_cast<int>(G)) {
@@ -928,7 +942,7 @@ int snacb_decode_keyed(snacb_handle h, const int32_t* tok, int B, int tok_stride
         if (noise) for (int i = 0; i < 4; ++i) nz[i] = noise[i] + static_cast<size_t>(g0) * nlen[i];
         int rc = run_group(h, tok + static_cast<size_t>(g0) * tok_stride, S, tok_stride, frames, flags,
                            noise ? nz : nullptr, seed, g0, stream_keys ? stream_keys + g0 : nullptr,
-                           pcm + static_cast<size_t>(g0) * n_out,
+                           ranged ? sample_lo : 0, ranged ? sample_hi : 0, pcm + static_cast<size_t>(g0) * n_out,
                            wave ? wave + static_cast<size_t>(g0) * n_out : nullptr, st);
         if (rc) return rc;
     }

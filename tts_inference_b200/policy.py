@@ -5,7 +5,9 @@
 that description and has no reference code to be pinned against):
 
   1. buffer ALL audio tokens of a stream;
-  2. whenever ``frames_per_chunk`` new complete frames have arrived, decode ALL frames from frame 0;
+  2. whenever ``frames_per_chunk`` new complete frames have arrived, decode ALL frames from frame 0 (here: hand all
+     frames to the decoder but let it compute only the receptive field of the samples about to be emitted,
+     ``snacb_decode_range`` -- same bits, a fraction of the work);
   3. emit only samples that have at least ``lookahead_frames`` (5 = 10 240 samples, ~430 ms) of future context,
      tracking ``samples_emitted`` so that nothing is emitted twice;
   4. at end of stream decode once more and emit everything that is left.
@@ -17,7 +19,8 @@ the samples it shares with the shorter one.  Since 5 frames of lookahead exceed 
 streamed audio is then bit-identical to the batch decode of the whole utterance (tests/test_io.py), where the
 reference, redrawing torch.randn on every decode (PIPELINE_REPORT.md:481), reports correlation 0.9987.  Each stream's noise is keyed by
 its own ``noise_key`` (snacb_decode_keyed), not by its row in whatever batch it happens to be decoded with.
-The quadratic re-decode is the reference's; an incremental decoder that reuses per-stage state is DESIGN.md section 8 "next".
+What is still linear in the prefix per step is block 0 and the stem (~10 % of a decode); reusing their state across steps
+is DESIGN.md section 8 "next".
 """
 from __future__ import annotations
 
@@ -79,26 +82,27 @@ class LookaheadStreamingDecoder:
         distinct length -- and return [(stream, new int16 samples)] for the streams that have something to emit.
         Finished streams are forgotten once flushed."""
         import torch
-        due: Dict[int, List[Hashable]] = {}
+        due: Dict[Tuple[int, int, int], List[Hashable]] = {}
         for key, st in self._streams.items():
             frames = len(st.ids) // FRAME
             if frames > 0 and (st.done or frames - st.decoded_frames >= self.frames_per_chunk) and \
                     (frames != st.decoded_frames or st.done):
-                due.setdefault(frames, []).append(key)
+                end = stable_samples(frames, self.lookahead_frames, st.done)
+                st.decoded_frames = frames
+                if end > st.emitted:
+                    due.setdefault((frames, st.emitted, end), []).append(key)
         out: List[Tuple[Hashable, np.ndarray]] = []
-        for frames, keys in sorted(due.items()):
+        for (frames, lo, hi), keys in sorted(due.items()):
             tok = np.asarray([self._streams[k].ids[: frames * FRAME] for k in keys], dtype=np.int64)
             tok = np.clip(tok, -(2 ** 31), 2 ** 31 - 1).astype(np.int32)
             nkeys = torch.tensor([self._streams[k].key for k in keys], dtype=torch.int32).cuda(self._dec.device)
+            # only the new stable samples [lo, hi) are computed (snacb_decode_range): the prefix is re-read, not re-decoded
             pcm = self._dec.decode(torch.from_numpy(tok).cuda(self._dec.device), raw_ids=self.raw_ids,
-                                   extract_slice=False, seed=self.seed, precision=self.precision, stream_keys=nkeys)
+                                   seed=self.seed, precision=self.precision, stream_keys=nkeys, sample_range=(lo, hi))
+            host = pcm.cpu().numpy()
             for row, k in enumerate(keys):
-                st = self._streams[k]
-                st.decoded_frames = frames
-                end = stable_samples(frames, self.lookahead_frames, st.done)
-                if end > st.emitted:
-                    out.append((k, pcm[row, st.emitted:end].cpu().numpy()))
-                    st.emitted = end
+                out.append((k, host[row]))
+                self._streams[k].emitted = hi
         for key in [k for k, st in self._streams.items() if st.done]:
             del self._streams[key]
         return out
