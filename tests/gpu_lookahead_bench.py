@@ -1,0 +1,70 @@
+"""Cost of the lookahead streaming policy (tts_inference_b200/policy.py; tensorrt_tts/PIPELINE_REPORT.md:475-511) for B
+streams of F frames, a decode every `chunk` new frames, 5 frames of lookahead -- CUDA-event time of all decode calls:
+  (a) the reference's algorithm: re-decode ALL frames every time;   (b) snacb_decode_range: new stable samples only;
+  (c) one batch decode of the finished utterances (lower bound).
+
+    python tests/gpu_lookahead_bench.py [B] [F] [chunk] > gpurun_out/lookahead_bench.json
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from tts_inference_b200 import SnacDecoder, policy, synth  # noqa: E402
+
+
+def main():
+    B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+    F = int(sys.argv[2]) if len(sys.argv) > 2 else 128
+    chunk = int(sys.argv[3]) if len(sys.argv) > 3 else 4
+    dec = SnacDecoder(synth.make_state_dict(0))
+    tok = torch.from_numpy(synth.make_tokens(B, F, seed=1)).cuda()
+    keys = torch.arange(B, dtype=torch.int32).cuda()
+    sched = []
+    emitted = 0
+    for f in list(range(chunk, F + 1, chunk)) + ([F] if F % chunk else []):
+        end = policy.stable_samples(f, 5, False)
+        if end > emitted:
+            sched.append((f, emitted, end)); emitted = end
+    sched.append((F, emitted, 2048 * F))
+
+    def run(mode):
+        ms = 0.0
+        outs = []
+        for (f, lo, hi) in sched:
+            t = tok[:, :7 * f].contiguous()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            if mode == "full":
+                o = dec.decode(t, raw_ids=True, seed=2, stream_keys=keys)[:, lo:hi]
+            else:
+                o = dec.decode(t, raw_ids=True, seed=2, stream_keys=keys, sample_range=(lo, hi))
+            b.record()
+            torch.cuda.synchronize()
+            ms += a.elapsed_time(b)
+            outs.append(o)
+        return ms, torch.cat(outs, dim=1)
+
+    run("range"); run("full")                                   # warm-up (workspace growth)
+    ms_full, pcm_full = run("full")
+    ms_range, pcm_range = run("range")
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dec.decode(tok, raw_ids=True, seed=2, stream_keys=keys)
+    a.record(); batch = dec.decode(tok, raw_ids=True, seed=2, stream_keys=keys); b.record()
+    torch.cuda.synchronize()
+    ms_batch = a.elapsed_time(b)
+    audio_s = B * F * 2048 / 24000.0
+    print(json.dumps({
+        "streams": B, "frames": F, "frames_per_chunk": chunk, "lookahead_frames": 5, "decode_calls": len(sched),
+        "redecode_all_ms": ms_full, "ranged_ms": ms_range, "one_batch_decode_ms": ms_batch,
+        "audio_s_per_s": {"redecode_all": audio_s / ms_full * 1e3, "ranged": audio_s / ms_range * 1e3,
+                          "one_batch_decode": audio_s / ms_batch * 1e3},
+        "streamed_equals_batch_decode": bool(torch.equal(pcm_range, batch) and torch.equal(pcm_full, batch)),
+    }, indent=1))
+
+
+if __name__ == "__main__":
+    main()
