@@ -192,7 +192,8 @@ def test_sliced_call_trims_dead_samples_bit_identically(decoder, F_, unfused):
 
 @pytest.mark.parametrize("prec", ["fp16", "bf16", "fp32"])
 @pytest.mark.parametrize("B,F_,lo,hi", [(3, 4, 2048, 4096), (2, 4, 0, 100), (2, 4, 8000, 8192), (5, 12, 6144, 14336),
-                                        (1, 40, 61440, 71680), (4, 9, 0, 18432), (2, 1, 5, 2043), (37, 6, 4096, 8192)])
+                                        (1, 40, 61440, 71680), (4, 9, 0, 18432), (2, 1, 5, 2043), (37, 6, 4096, 8192),
+                                        (2, 64, 100000, 104096), (3, 30, 0, 4096), (3, 30, 57344, 61440), (2, 100, 190000, 190001)])
 def test_ranged_decode_equals_slice_of_full_decode(decoder, prec, B, F_, lo, hi):
     """snacb_decode_range: samples [lo, hi) only, their receptive field only -- bit-identical to the full decode's slice."""
     tokens = _cuda(synth.make_tokens(B, F_, seed=40 + F_))

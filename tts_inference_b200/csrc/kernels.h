@@ -23,8 +23,8 @@ struct VqStemWeights {
 void launch_unpack(const int32_t* tok, int B, int ntok, int F, int raw_ids, int32_t* c0, int32_t* c1, int32_t* c2,
                    cudaStream_t st);
 template <typename OutT>
-void launch_vq_stem(const int32_t* c0, const int32_t* c1, const int32_t* c2, int S, int F, const VqStemWeights& w,
-                    OutT* out, cudaStream_t st);
+void launch_vq_stem(const int32_t* c0, const int32_t* c1, const int32_t* c2, int S, int F, int t_lo, int t_hi,
+                    const VqStemWeights& w, OutT* out, cudaStream_t st);   // latent steps [t_lo, t_hi) of every stream
 void launch_gemm_f32(int epi, const GemmArgs& a, const float* A, const float* W, cudaStream_t st);
 void launch_respre_f32(const ResUnitArgs& a, float* P, cudaStream_t st);
 template <typename InT>

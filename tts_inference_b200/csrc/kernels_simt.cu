@@ -62,9 +62,9 @@ constexpr int kVqTile = 16;
 template <typename OutT>
 __global__ void __launch_bounds__(256)
 k_vq_stem(const int32_t* __restrict__ c0, const int32_t* __restrict__ c1, const int32_t* __restrict__ c2, int F,
-          VqStemWeights w, OutT* __restrict__ out) {
+          int tile_lo, VqStemWeights w, OutT* __restrict__ out) {
     const int T0 = 4 * F;
-    const int s = blockIdx.y, t0 = blockIdx.x * kVqTile;
+    const int s = blockIdx.y, t0 = (tile_lo + blockIdx.x) * kVqTile;
     __shared__ float emb[3][kVqTile + 6][kCodeDim];
     __shared__ int ok[kVqTile + 6];
     for (int idx = threadIdx.x; idx < 3 * (kVqTile + 6); idx += blockDim.x) {
@@ -127,17 +127,20 @@ k_vq_stem(const int32_t* __restrict__ c0, const int32_t* __restrict__ c1, const 
 }
 
 template <typename OutT>
-void launch_vq_stem(const int32_t* c0, const int32_t* c1, const int32_t* c2, int S, int F, const VqStemWeights& w,
-                    OutT* out, cudaStream_t st) {
-    dim3 grid((4 * F + kVqTile - 1) / kVqTile, S, kLatent / 256);
-    k_vq_stem<OutT><<<grid, 256, 0, st>>>(c0, c1, c2, F, w, out);
+void launch_vq_stem(const int32_t* c0, const int32_t* c1, const int32_t* c2, int S, int F, int t_lo, int t_hi,
+                    const VqStemWeights& w, OutT* out, cudaStream_t st) {
+    // latent steps [t_lo, t_hi) of every stream, in whole 16-step tiles
+    const int tile_lo = t_lo / kVqTile, tile_hi = (t_hi + kVqTile - 1) / kVqTile;
+    if (tile_hi <= tile_lo) return;
+    dim3 grid(tile_hi - tile_lo, S, kLatent / 256);
+    k_vq_stem<OutT><<<grid, 256, 0, st>>>(c0, c1, c2, F, tile_lo, w, out);
 }
-template void launch_vq_stem<float>(const int32_t*, const int32_t*, const int32_t*, int, int, const VqStemWeights&,
-                                    float*, cudaStream_t);
-template void launch_vq_stem<__nv_bfloat16>(const int32_t*, const int32_t*, const int32_t*, int, int,
+template void launch_vq_stem<float>(const int32_t*, const int32_t*, const int32_t*, int, int, int, int,
+                                    const VqStemWeights&, float*, cudaStream_t);
+template void launch_vq_stem<__nv_bfloat16>(const int32_t*, const int32_t*, const int32_t*, int, int, int, int,
                                             const VqStemWeights&, __nv_bfloat16*, cudaStream_t);
-template void launch_vq_stem<__half>(const int32_t*, const int32_t*, const int32_t*, int, int, const VqStemWeights&,
-                                     __half*, cudaStream_t);
+template void launch_vq_stem<__half>(const int32_t*, const int32_t*, const int32_t*, int, int, int, int,
+                                     const VqStemWeights&, __half*, cudaStream_t);
 
 // ----------------------------------------------------------------------------------------------
 // fp32 row-GEMM with taps (CUDA cores).  64x64 tile, 16-deep K steps, 4x4 register micro-tile.

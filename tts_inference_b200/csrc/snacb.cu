@@ -321,10 +321,55 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
     launch_unpack(tok, S, tok_stride, F, (flags & SNACB_RAW_IDS) ? 1 : 0, c0, c1, c2, st);
     prof_end(h, st);
     h->launches++;
+    // ---- dead-sample trimming (sliced output): only the rows of each stage inside the receptive field of samples
+    //      [out_lo, out_hi) are computed.  Backward range propagation; the stem is always computed in full, block 0 unless
+    //      less than half of it is live.
+    struct Rng { int lo, hi; };
+    Rng ct_in[4], post[4];                 // ConvTranspose input rows; rows the post-ConvTranspose layers process
+    bool trimmed[4] = {false, false, false, false};
+    {
+        const int Tfin = 2048 * F;
+        // output samples [out_lo, out_hi): the caller's range (snacb_decode_range), the reference's slice, or everything
+        if (out_hi <= out_lo) {
+            const bool sl = (flags & SNACB_EXTRACT_SLICE) && Tfin > 4096;
+            out_lo = sl ? 2048 : 0; out_hi = sl ? 4096 : Tfin;
+        }
+        const bool want = (out_hi - out_lo < Tfin) && !f32 && !xf32 && !taps && !h->no_trim;
+        int Tb[4], tt = T0;
+        for (int bi = 0; bi < 4; ++bi) { tt *= h->blk[bi].s; Tb[bi] = tt; }
+        auto clip = [](Rng r, int T) { return Rng{r.lo < 0 ? 0 : r.lo, r.hi > T ? T : r.hi}; };
+        Rng need = clip(Rng{out_lo - 3, out_hi + 3}, Tb[3]);        // tail conv k7
+        for (int bi = 3; bi >= 0; --bi) {
+            const BlockW& b = h->blk[bi];
+            const int Tinb = bi ? Tb[bi - 1] : T0;
+            // block 0 (per-layer kernels, 128-row tiles) is trimmed only when less than half of it is needed: a short
+            // range of a long prefix (snacb_decode_range); for the 4-frame window's slice 111 of its 128 rows are live
+            const bool skip0 = bi == 0 && 2 * (need.hi - need.lo + 78) >= Tb[0];
+            if (!want || skip0) { post[bi] = Rng{0, Tb[bi]}; ct_in[bi] = Rng{0, Tinb}; continue; }
+            trimmed[bi] = true;
+            Rng y;                                                  // ConvTranspose output rows that must be valid
+            const bool unfused = (flags & SNACB_UNFUSED) != 0 || h->no_chain;
+            if (b.chain[hk] && !unfused) {
+                const bool two = hk && b.chain2 && !h->no_chain2;
+                const int rows = (two ? chain2_tile_rows(b.Cout) : chain_tile_rows(b.Cout)) - 2 * kChainHalo;
+                const int n = (need.hi - need.lo + rows - 1) / rows;
+                post[bi] = Rng{need.lo, need.lo + n * rows};
+                y = clip(Rng{post[bi].lo - kChainHalo, post[bi].hi + kChainHalo}, Tb[bi]);
+            } else {
+                post[bi] = clip(Rng{need.lo - 39, need.hi + 39}, Tb[bi]);   // 3 * (1 + 3 + 9) rows of receptive field
+                y = post[bi];
+            }
+            ct_in[bi] = clip(Rng{y.lo / b.s - 1, (y.hi - 1) / b.s + 2}, Tinb);
+            need = ct_in[bi];
+        }
+    }
+
     prof_begin(h, "vq_stem", st);
-    if (f32) launch_vq_stem<float>(c0, c1, c2, S, F, h->vq, static_cast<float*>(h->ws_a0), st);
-    else if (hk) launch_vq_stem<__half>(c0, c1, c2, S, F, h->vq, static_cast<__half*>(h->ws_a0), st);
-    else launch_vq_stem<__nv_bfloat16>(c0, c1, c2, S, F, h->vq, static_cast<__nv_bfloat16*>(h->ws_a0), st);
+    // latent steps the stem has to produce: the input rows of block 0's ConvTranspose (all of them unless block 0 is trimmed)
+    const int stem_lo = trimmed[0] ? ct_in[0].lo : 0, stem_hi = trimmed[0] ? ct_in[0].hi : T0;
+    if (f32) launch_vq_stem<float>(c0, c1, c2, S, F, stem_lo, stem_hi, h->vq, static_cast<float*>(h->ws_a0), st);
+    else if (hk) launch_vq_stem<__half>(c0, c1, c2, S, F, stem_lo, stem_hi, h->vq, static_cast<__half*>(h->ws_a0), st);
+    else launch_vq_stem<__nv_bfloat16>(c0, c1, c2, S, F, stem_lo, stem_hi, h->vq, static_cast<__nv_bfloat16*>(h->ws_a0), st);
     prof_end(h, st);
     h->launches++;
     CK(h, cudaGetLastError());
@@ -375,50 +420,12 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
         GemmArgs a{};
         a.S = S; a.Tin = T0; a.K = kLatent; a.N = kDecDim; a.Cout = kDecDim; a.ntaps = 1; a.up = 1;
         a.bias = h->stem_pw_b; a.alpha = h->blk[0].alpha; a.inv_alpha = h->blk[0].inv_alpha;
+        if (trimmed[0]) { a.t_lo = stem_lo; a.t_n = stem_hi - stem_lo; }
         a.out = cur;
         int rc = gemm("stem_pw", EPI_BIAS_SNAKE, false, a, h->ws_a0, h->stem_pw_f32, h->stem_pw_h, kDecDim, kLatent);
         if (rc) return rc;
         rc = tap_any("stem", cur, dt_h, (int64_t)S * T0, kDecDim);
         if (rc) return rc;
-    }
-
-    // ---- dead-sample trimming (sliced output): only the rows of each stage inside the receptive field of samples
-    //      [2048, 4096) are computed.  Backward range propagation; block 0 and the stem are always computed in full.
-    struct Rng { int lo, hi; };
-    Rng ct_in[4], post[4];                 // ConvTranspose input rows; rows the post-ConvTranspose layers process
-    bool trimmed[4] = {false, false, false, false};
-    {
-        const int Tfin = 2048 * F;
-        // output samples [out_lo, out_hi): the caller's range (snacb_decode_range), the reference's slice, or everything
-        if (out_hi <= out_lo) {
-            const bool sl = (flags & SNACB_EXTRACT_SLICE) && Tfin > 4096;
-            out_lo = sl ? 2048 : 0; out_hi = sl ? 4096 : Tfin;
-        }
-        const bool want = (out_hi - out_lo < Tfin) && !f32 && !xf32 && !taps && !h->no_trim;
-        int Tb[4], tt = T0;
-        for (int bi = 0; bi < 4; ++bi) { tt *= h->blk[bi].s; Tb[bi] = tt; }
-        auto clip = [](Rng r, int T) { return Rng{r.lo < 0 ? 0 : r.lo, r.hi > T ? T : r.hi}; };
-        Rng need = clip(Rng{out_lo - 3, out_hi + 3}, Tb[3]);        // tail conv k7
-        for (int bi = 3; bi >= 0; --bi) {
-            const BlockW& b = h->blk[bi];
-            const int Tinb = bi ? Tb[bi - 1] : T0;
-            if (!want || bi == 0) { post[bi] = Rng{0, Tb[bi]}; ct_in[bi] = Rng{0, Tinb}; continue; }
-            trimmed[bi] = true;
-            Rng y;                                                  // ConvTranspose output rows that must be valid
-            const bool unfused = (flags & SNACB_UNFUSED) != 0 || h->no_chain;
-            if (b.chain[hk] && !unfused) {
-                const bool two = hk && b.chain2 && !h->no_chain2;
-                const int rows = (two ? chain2_tile_rows(b.Cout) : chain_tile_rows(b.Cout)) - 2 * kChainHalo;
-                const int n = (need.hi - need.lo + rows - 1) / rows;
-                post[bi] = Rng{need.lo, need.lo + n * rows};
-                y = clip(Rng{post[bi].lo - kChainHalo, post[bi].hi + kChainHalo}, Tb[bi]);
-            } else {
-                post[bi] = clip(Rng{need.lo - 39, need.hi + 39}, Tb[bi]);   // 3 * (1 + 3 + 9) rows of receptive field
-                y = post[bi];
-            }
-            ct_in[bi] = clip(Rng{y.lo / b.s - 1, (y.hi - 1) / b.s + 2}, Tinb);
-            need = ct_in[bi];
-        }
     }
 
     int Tin = T0;
