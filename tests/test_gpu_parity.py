@@ -342,6 +342,15 @@ def test_empty_and_bad_arguments(decoder):
     assert decoder.decode_host(np.zeros((2, 6), dtype=np.int32)).shape == (2, 0)
     with pytest.raises(SnacbError):
         decoder._check(decoder._lib.snacb_decode(decoder._h, None, 1, 28, 4, 0, None, 0, None, None, None), "null")
+    tok = _cuda(synth.make_tokens(2, 4, seed=1))
+    out = torch.empty((2, 8192), dtype=torch.int16, device="cuda")
+    lib = decoder._lib
+    for lo, hi in ((-1, 10), (10, 10), (20, 10), (0, 8193)):        # bad sample ranges are refused, nothing is launched
+        assert lib.snacb_decode_range(decoder._h, tok.data_ptr(), 2, 28, 4, 1, None, 0, None, lo, hi, out.data_ptr(), None, None) == -1
+    assert lib.snacb_decode_range(decoder._h, tok.data_ptr(), 2, 28, 4, 1, None, 0, None, 0, 8192, out.data_ptr(), None, None) == 0
+    torch.cuda.synchronize()
+    assert torch.equal(out, decoder.decode(tok, raw_ids=True, seed=0))
+    assert lib.snacb_decode_host_submit(decoder._h, None, 2, 28, 4, 1, 0, None) == -1
 
 
 # ------------------------------------------------------------------------------------ full-size properties
