@@ -269,3 +269,26 @@ def test_lookahead_policy_against_batch_decode(decoder):
         corr = np.corrcoef(cat.astype(np.float64), ref.astype(np.float64))[0, 1]
         assert mse < 1e-3 and corr > 0.998, (mse, corr)        # the reference's thresholds
         assert np.array_equal(cat, ref), s                       # and in fact bit-identical
+
+
+@pytest.mark.gpu
+def test_device_ingest_flush_only_step_and_many_slots():
+    """A step that carries no ids at all (n_tok = 0) but finishes streams flushes their remainders; 5000 slots."""
+    import torch
+    from tts_inference_b200.ingest import DeviceIngest
+    S = 5000
+    ing = DeviceIngest(S)
+    ids = torch.full((S, 16), BASE + 3, dtype=torch.int32).cuda()
+    ids[:, 0] = SOS
+    wt, ws, tt, ts, tf = ing.step(ids)                                   # 15 ids buffered per stream, nothing ready
+    assert wt.shape[0] == 0 and tt.shape[0] == 0
+    fin = torch.zeros(S, dtype=torch.uint8).cuda()
+    fin[::2] = 1
+    wt, ws, tt, ts, tf = ing.step(torch.empty((S, 0), dtype=torch.int32).cuda(), finish=fin)
+    assert wt.shape[0] == 0 and tt.shape[0] == S // 2
+    assert ts.cpu().tolist() == list(range(0, S, 2)) and (tf == 2).all()
+    assert (tt[:, :14] == BASE + 3).all() and (tt[:, 14:] == 0).all()
+    st, cnt = ing.state()
+    assert (st[::2] == 2).all() and (st[1::2] == 1).all() and (cnt[1::2] == 15).all() and (cnt[::2] == 0).all()
+    wt, ws, tt, ts, tf = ing.step(ids[:, 1:14].contiguous())             # 13 more ids: the live streams complete a window
+    assert ws.cpu().tolist() == list(range(1, S, 2)) and tt.shape[0] == 0
