@@ -159,6 +159,14 @@ int snacb_set_group_bytes(snacb_handle h, size_t bytes);
 /* Counters since creation: kernels launched by this library, streams decoded. */
 int snacb_stats(snacb_handle h, uint64_t* kernel_launches, uint64_t* streams_decoded);
 
+/* Which formulation each DecoderBlock's fused chain kernel runs with fp16 operands, decided from the checkpoint when the
+ * handle is created: modes[0..3] = 0 per-layer kernels (block 0, C = 512), 1 general variant (Snake evaluated as
+ * x + (alpha + 1e-9)^-1 sin^2(alpha x) in fp32), 2 alpha-folded variant (alpha multiplied into neighbouring weights; only
+ * when every Snake alpha of the block has magnitude in [2^-8, 2^6] and the folded parameters fit fp16).  A checkpoint
+ * with alpha = 0, tiny, or huge values therefore still decodes correctly (alpha = 0 gives snake(x) = x as in the
+ * reference), on the slower general variant. */
+int snacb_chain_modes(snacb_handle h, int32_t* modes);
+
 /* Per-launch CUDA-event timing of the pipeline stages (measurement aid; adds two event records per
  * launch, so do not time a headline number with it on).  snacb_profile(h,1) starts a fresh recording,
  * snacb_profile_report synchronises and writes one line per stage: "<name> <launches> <total_ms>". */
@@ -178,16 +186,6 @@ int snacb_debug_tap_copy(snacb_handle h, int idx, float* dst_host, size_t dst_el
  * No GPU needed. */
 int snacb_debug_chain_spans(int C, int16_t* out, int cap);
 
-/* The same for the halo-exchange variant of the chain kernel (C = 64 or 128; opt-in, SNACB_XCH=1): a tile has no halo,
- * every row is owned; the 32 rows above and below the tile hold the neighbouring tiles' boundary rows (27 used). */
-int snacb_debug_chain_spans_x(int C, int16_t* out, int cap);
-
-/* The same for the two-group chain kernel (C = 64 or 128, fp16 operands; kernels_chain2.cu): warps 0-7 own the rows
- * above the middle of the tile, warps 8-15 the rows below it.  out: int16[3][16][4][4] = {first_row, octets, chunk,
- * flags}; flags bit 0: the span ends its class at the group boundary and reads its three tail rows late, bit 1: the
- * span starts its class at the boundary and takes its three head rows from the stash.  Returns the tile height. */
-int snacb_debug_chain2_spans(int C, int16_t* out, int cap);
-
 /* ---------------------------------------------------------------------------------------------
  * Batcher: the multi-stream replacement of stream_audio's per-stream buffer policy
  * (modal_audio_stream.py:352-396), which decodes one stream at a time under a global lock.
@@ -199,14 +197,29 @@ int snacb_debug_chain2_spans(int C, int16_t* out, int cap);
  * --------------------------------------------------------------------------------------------- */
 int snacb_batcher_create(snacb_batcher* out, snacb_handle h, int policy, int flags, int max_windows);
 void snacb_batcher_destroy(snacb_batcher b);
-/* Append n raw token ids (flags & SNACB_RAW_IDS) or codes to a stream; thread-safe. */
+/* Append n raw token ids (flags & SNACB_RAW_IDS) or codes to a stream.  THREAD-SAFE: any number of producer threads may
+ * push concurrently, also while a flush runs (streams are sharded over independently locked tables). */
 int snacb_batcher_push(snacb_batcher b, uint64_t stream_id, const int32_t* tokens_host, int n);
-/* Mark a stream finished: policy 0 queues its remaining whole frames. */
+/* Mark a stream finished: policy 0 queues its remaining whole frames.  The id stays known as ended -- a later push to it
+ * returns SNACB_ERR_STATE instead of silently starting a new stream -- until snacb_batcher_forget(id) releases it. */
 int snacb_batcher_end(snacb_batcher b, uint64_t stream_id);
-/* Decode every ready window in one launch sequence.  Returns the number of chunks produced (>= 0)
- * or a negative status.  Chunk i: stream ids[i], PCM at pcm_host + offsets[i], lengths[i] samples. */
+int snacb_batcher_forget(snacb_batcher b, uint64_t stream_id);
+/* Decode every ready window in one launch sequence per chunk length, STRAIGHT into pcm_host (use pinned memory: the
+ * copy-out is then an asynchronous DMA).  Returns the number of chunks produced (>= 0) or a negative status.  Chunk i:
+ * stream ids[i], PCM at pcm_host + offsets[i], lengths[i] samples; chunks of one stream appear in time order.  If the
+ * decode fails the windows go back to the head of their queues: nothing is lost, the call may be retried.
+ * The flush calls are SINGLE-CALLER (one flusher thread); producers keep pushing meanwhile.
+ *   snacb_batcher_flush         blocking: submit + wait
+ *   snacb_batcher_flush_submit  returns once copy-in + decode + copy-out are queued on the GPU (at most two outstanding);
+ *                               ids / offsets / lengths are final on return, the PCM is not
+ *   snacb_batcher_flush_wait    blocks until the OLDEST outstanding submit's PCM is in its pcm_host
+ * A serving loop that calls submit(tick i + 1) and then wait() (tick i) overlaps the copy-out of one tick with the
+ * decode of the next; give the two ticks in flight distinct pcm_host buffers. */
 int snacb_batcher_flush(snacb_batcher b, uint64_t seed, int max_chunks, uint64_t* ids, int64_t* offsets,
                         int32_t* lengths, int16_t* pcm_host, size_t pcm_capacity);
+int snacb_batcher_flush_submit(snacb_batcher b, uint64_t seed, int max_chunks, uint64_t* ids, int64_t* offsets,
+                               int32_t* lengths, int16_t* pcm_host, size_t pcm_capacity);
+int snacb_batcher_flush_wait(snacb_batcher b);
 int snacb_batcher_pending(snacb_batcher b);     /* windows ready to decode right now */
 
 /* ---------------------------------------------------------------------------------------------

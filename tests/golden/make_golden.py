@@ -80,6 +80,7 @@ def main():
 
     # ---------------- integer glue ----------------
     cases = []
+    glue_pcm = {}
     good = synth_ckpt.make_codes(1, 6)[0].tolist()
     bad = (synth_ckpt.make_tokens(1, 8, seed=5, bad_frac=0.2)[0].astype(np.int64) - 128266).tolist()
     code_lists = {
@@ -101,6 +102,7 @@ def main():
             rec["stream_levels"] = [c[0].tolist() for c in wrap.seen]
             rec["stream_pcm_sha256"] = hashlib.sha256(out).hexdigest()
             rec["stream_pcm_len"] = len(out)
+            glue_pcm[f"glue_pcm_{name}"] = np.frombuffer(out, dtype=np.int16).copy()   # the bytes themselves (+-1 LSB checks)
         else:
             rec["stream_returns_none"] = out is None
         if len(codes) >= 7:
@@ -140,7 +142,7 @@ def main():
         os.path.join(HERE, "decode_golden.npz"),
         tokens=tokens, noise_seed=np.int64(7), pcm_full=np.stack(pcm_full), pcm_slice=np.stack(pcm_slice),
         pcm_trt=np.stack(pcm_trt), wave=np.stack(wave).astype(np.float32),
-        tokens_long=tok2, noise_seed_long=np.int64(11), pcm_long=pcm_long, ckpt_seed=np.int64(0))
+        tokens_long=tok2, noise_seed_long=np.int64(11), pcm_long=pcm_long, ckpt_seed=np.int64(0), **glue_pcm)
     print("wrote glue_golden.json, decode_golden.npz",
           {k: v.shape for k, v in dict(pcm_full=np.stack(pcm_full), pcm_slice=np.stack(pcm_slice),
                                        pcm_long=pcm_long).items()})

@@ -35,6 +35,110 @@ def test_convert_to_audio_contract(compat_mod):
     assert len(compat_mod.convert_to_audio(huge)) == 2 * 8192
 
 
+def _with_hooks(compat, noise, precision):
+    class _H:
+        def __enter__(self_):
+            compat._test_noise, compat._test_precision = noise, precision
+        def __exit__(self_, *a):
+            compat._test_noise, compat._test_precision = None, None
+    return _H()
+
+
+def test_convert_to_audio_returns_the_reference_helpers_bytes(compat_mod):
+    """The bytes the REFERENCE's own convert_to_audio returned (tests/golden/make_golden.py executes it out of
+    /root/reference with the oracle as `snac`) against compat.convert_to_audio on the same codes and the same injected
+    NoiseBlock noise, fp32 arithmetic: every glue case (ragged, out-of-range, specials, maximum codes), +-1 LSB."""
+    z = np.load(os.path.join(GOLD, "decode_golden.npz"))
+    with open(os.path.join(GOLD, "glue_golden.json")) as f:
+        cases = json.load(f)["cases"]
+    n = 0
+    for c in cases:
+        if "stream_pcm_sha256" not in c:
+            assert compat_mod.convert_to_audio(c["codes"]) is None
+            continue
+        want = z["glue_pcm_" + c["name"]]
+        t0 = 4 * (len(c["codes"]) // 7)
+        noise = [torch.from_numpy(x).cuda() for x in synth.make_noises(1, t0)]
+        with _with_hooks(compat_mod, noise, "fp32"):
+            got = compat_mod.convert_to_audio(list(c["codes"]), False)
+        assert isinstance(got, bytes) and len(got) == c["stream_pcm_len"], c["name"]
+        d = np.abs(np.frombuffer(got, dtype=np.int16).astype(np.int32) - want.astype(np.int32))
+        assert d.max() <= 1, (c["name"], int(d.max()))
+        n += 1
+    assert n >= 9
+
+
+def test_compat_entry_points_against_decode_golden(compat_mod):
+    """decode_golden.npz through the reference's entry-point NAMES: convert_to_audio (full and sliced) and
+    redistribute_codes + decode_snac (pcm_trt), same noise, fp32: +-1 LSB; fp16 default path: SNR >= 40 dB."""
+    z = np.load(os.path.join(GOLD, "decode_golden.npz"))
+    tokens = z["tokens"]
+    noises = synth.make_noises(tokens.shape[0], 16, seed=int(z["noise_seed"]))
+    for b in range(tokens.shape[0]):
+        codes = (tokens[b].astype(np.int64) - 128266).tolist()
+        nb = [torch.from_numpy(np.ascontiguousarray(n[b:b + 1])).cuda() for n in noises]
+        with _with_hooks(compat_mod, nb, "fp32"):
+            full = np.frombuffer(compat_mod.convert_to_audio(codes, False), dtype=np.int16)
+            sl = np.frombuffer(compat_mod.convert_to_audio(codes, True), dtype=np.int16)
+            l0, l1, l2 = compat_mod.redistribute_codes(codes)
+            trt = np.frombuffer(compat_mod.decode_snac(l0, l1, l2, compat_mod.snac_model, "cuda"), dtype=np.int16)
+        for got, want in ((full, z["pcm_full"][b]), (sl, z["pcm_slice"][b]), (trt, z["pcm_trt"][b])):
+            assert got.shape == want.shape
+            assert np.abs(got.astype(np.int32) - want.astype(np.int32)).max() <= 1
+        with _with_hooks(compat_mod, nb, "fp16"):
+            h = np.frombuffer(compat_mod.convert_to_audio(codes, False), dtype=np.int16).astype(np.float64)
+        w = z["pcm_full"][b].astype(np.float64)
+        assert 10 * np.log10((w ** 2).sum() / ((w - h) ** 2).sum()) >= 40.0
+
+
+def test_init_snac_from_checkpoint_file_and_env(tmp_path, monkeypatch, state_dict, oracle_model):
+    """The real-checkpoint path: a pytorch_model.bin written with torch.save in BOTH weight-norm key styles is loaded by
+    init_snac(path), by init_snac(directory) and by the reference's argument-less init_snac() through SNACB_CKPT; the
+    decode equals the one from the in-memory state dict bit for bit, and the second load comes from the fold cache."""
+    from tests._util import oracle_decode
+    from tts_inference_b200 import compat, weights
+    monkeypatch.setenv("SNACB_CACHE_DIR", str(tmp_path / "cache"))
+    old_style = {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in state_dict.items()}
+    new_style = {}
+    for k, v in old_style.items():
+        k2 = k.replace(".weight_g", ".parametrizations.weight.original0").replace(".weight_v", ".parametrizations.weight.original1")
+        new_style[k2] = v
+    # keys a full snac_24khz checkpoint has and the decode path must ignore
+    new_style["encoder.block.0.weight"] = torch.zeros(3)
+    new_style["quantizer.quantizers.0.in_proj.bias"] = torch.zeros(8)
+    d_old, d_new = tmp_path / "old", tmp_path / "snac_24khz"
+    d_old.mkdir(); d_new.mkdir()
+    torch.save(old_style, d_old / "pytorch_model.bin")
+    torch.save(new_style, d_new / "pytorch_model.bin")
+    tokens = synth.make_tokens(2, 4, seed=77)
+    noises = synth.make_noises(2, 16, seed=4)
+    nz = [torch.from_numpy(n).cuda() for n in noises]
+    tok = torch.from_numpy(tokens).cuda()
+    keep = (compat.snac_model, compat.snac_device)
+    try:
+        ref_dec = compat.init_snac(state_dict, device=0)
+        want = ref_dec.decode(tok, raw_ids=True, noise=nz, precision="fp32", return_wave=True)
+        outs = []
+        outs.append(compat.init_snac(str(d_old / "pytorch_model.bin")))
+        outs.append(compat.init_snac(str(d_new)))                     # directory, new-style keys, extra keys
+        assert len(list((tmp_path / "cache").glob("folded-*.npz"))) == 2
+        outs.append(compat.init_snac(str(d_new)))                     # cache hit
+        monkeypatch.setenv("SNACB_CKPT", str(d_new))
+        outs.append(compat.init_snac())                               # the reference's call
+        for dec in outs:
+            got = dec.decode(tok, raw_ids=True, noise=nz, precision="fp32", return_wave=True)
+            assert torch.equal(got[0], want[0]) and torch.equal(got[1], want[1])
+        ref, _ = oracle_decode(oracle_model, tokens, noises)
+        assert np.abs(want[1].cpu().numpy() - ref).max() <= 1e-3
+        monkeypatch.delenv("SNACB_CKPT")
+        with pytest.raises(RuntimeError, match="no checkpoint"):
+            compat.init_snac()
+        with pytest.raises(FileNotFoundError):
+            compat.init_snac(str(tmp_path / "missing"))
+    finally:
+        compat.snac_model, compat.snac_device = keep
+
+
 def test_redistribute_codes_matches_reference_vectors(compat_mod):
     with open(os.path.join(GOLD, "glue_golden.json")) as f:
         cases = json.load(f)["cases"]

@@ -25,11 +25,13 @@ class SnacDecoder:
     """One handle = one GPU.  Replaces the module-global ``snac_model`` the reference's helper
     closes over (vllm_inference/modal_audio_stream.py:79-80,106-129)."""
 
-    def __init__(self, state_dict: Mapping[str, object], device: int = 0):
+    def __init__(self, state_dict: Mapping[str, object], device: int = 0, folded: bool = False):
+        """``state_dict``: the checkpoint's tensors under their upstream names (weight-norm folded here), or -- with
+        ``folded=True`` -- the output of ``weights.fold_state_dict`` / ``weights.load_folded``."""
         self._lib = _lib.load()
         self._h = C.c_void_p()
         self.device = int(device)
-        folded = fold_state_dict(state_dict)
+        folded = dict(state_dict) if folded else fold_state_dict(state_dict)
         w = _lib.make_weights(folded)
         rc = self._lib.snacb_create(C.byref(self._h), C.byref(w), self.device)
         if rc != 0:
@@ -54,10 +56,16 @@ class SnacDecoder:
             msg = self._lib.snacb_last_error(self._h)
             raise SnacbError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
 
-    @staticmethod
-    def _stream_ptr():
+    def _stream_ptr(self):
         import torch
-        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)      # the handle's GPU, not the current one
+
+    def chain_modes(self):
+        """Per DecoderBlock: 0 per-layer kernels, 1 general fused chain, 2 alpha-folded fused chain (fp16 operands);
+        decided from the checkpoint's Snake alphas at load (include/snacb.h snacb_chain_modes)."""
+        m = (C.c_int32 * 4)()
+        self._check(self._lib.snacb_chain_modes(self._h, m), "snacb_chain_modes")
+        return list(m)
 
     @staticmethod
     def _flags(raw_ids, extract_slice, precision, keep_taps=False, stream_fp32=False, unfused=False) -> int:

@@ -7,7 +7,7 @@ Replaces ``stream_audio``'s one-stream-at-a-time buffer policy
 from __future__ import annotations
 
 import ctypes as C
-from typing import List, Tuple
+from typing import List, Optional, Tuple
 
 import numpy as np
 
@@ -60,8 +60,12 @@ class WindowBatcher:
     def pending(self) -> int:
         return int(self._lib.snacb_batcher_pending(self._b))
 
-    def flush(self, seed: int = 0) -> List[Tuple[int, np.ndarray]]:
-        """Decode all ready windows; returns [(stream_id, int16 samples)] in queue order."""
+    def flush(self, seed: Optional[int] = None) -> List[Tuple[int, np.ndarray]]:
+        """Decode all ready windows; returns [(stream_id, int16 samples)] in queue order.
+        ``seed=None`` (default): fresh NoiseBlock noise on every flush, as the reference draws ``torch.randn`` per decode."""
+        if seed is None:
+            self._seed = getattr(self, "_seed", 0) + 1
+            seed = self._seed
         n = self._lib.snacb_batcher_flush(self._b, C.c_uint64(seed), self.max_windows, self._ids.ctypes.data,
                                           self._off.ctypes.data, self._len.ctypes.data, self._pcm.ctypes.data,
                                           self._pcm.size)

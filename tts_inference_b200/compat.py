@@ -5,7 +5,7 @@
 
 Reference                                            here
 ---------------------------------------------------  -------------------------------------------
-init_snac()            modal_audio_stream.py:106-129  init_snac(checkpoint=None, device=0)
+init_snac()            modal_audio_stream.py:106-129  init_snac(checkpoint=None, device=0)   [None -> $SNACB_CKPT, else raises]
 convert_to_audio()     modal_audio_stream.py:132-202  convert_to_audio(code_list, extract_slice=False)
 redistribute_codes()   tensorrt_tts/inference.py:54-93   redistribute_codes(codes)
 decode_snac()          tensorrt_tts/inference.py:96-112  decode_snac(l0, l1, l2, snac_model, device)
@@ -34,25 +34,50 @@ _noise_seed = itertools.count(1)      # the reference draws fresh torch.randn no
 _I32_MIN, _I32_MAX = -(2 ** 31), 2 ** 31 - 1
 
 
+# Test-only hooks (tests/test_gpu_api.py): the reference helper draws fresh torch.randn noise inside snac.decode and
+# runs fp32; to compare the bytes these entry points return with golden bytes of the reference's own functions, a test
+# pins the NoiseBlock noise (list of four cuda float32 tensors [1, 1, T_i]) and the arithmetic ("fp32").
+_test_noise = None
+_test_precision = None
+
+
 def init_snac(checkpoint=None, device: int = 0) -> SnacDecoder:
     """Load SNAC weights onto the GPU (weight-norm folded, tensor-core tiles packed).
 
-    ``checkpoint``: path of ``pytorch_model.bin`` / its directory, a state dict, or None for the
-    seeded synthetic checkpoint (no network in this environment; the reference downloads
-    ``hubertsiuzdak/snac_24khz`` here).  The reference's warm-up decode with (1,1),(1,2),(1,4)
-    codes (modal_audio_stream.py:120-127) is kept: it also sizes the workspace."""
+    The reference takes no argument and downloads ``hubertsiuzdak/snac_24khz``
+    (modal_audio_stream.py:113).  There is no network here, so the checkpoint is
+    ``checkpoint`` -- path of ``pytorch_model.bin`` / its directory, or a state dict -- or, for the
+    reference's argument-less call, the path in the environment variable ``SNACB_CKPT``.  With neither
+    this raises: weights are never made up.  (Benchmarks and tests that want random-init weights pass
+    ``synth.make_state_dict(seed)`` explicitly.)  The reference's warm-up decode
+    (modal_audio_stream.py:120-127) is kept: it also sizes the workspace."""
     global snac_model, snac_device
-    from . import synth, weights
+    import os
+    from . import weights
     if checkpoint is None:
-        sd = synth.make_state_dict(0)
-    elif isinstance(checkpoint, str):
-        sd = weights.load_checkpoint(checkpoint)
+        checkpoint = os.environ.get(weights.CKPT_ENV)
+        if not checkpoint:
+            raise RuntimeError(
+                "init_snac(): no checkpoint.  Pass the path of snac_24khz's pytorch_model.bin (or its directory, or a "
+                f"state dict), or set {weights.CKPT_ENV}; this build cannot download hubertsiuzdak/snac_24khz.")
+    if isinstance(checkpoint, (str, os.PathLike)):
+        model = SnacDecoder(weights.load_folded(os.fspath(checkpoint)), device=device, folded=True)
     else:
-        sd = checkpoint
-    snac_model = SnacDecoder(sd, device=device)
+        model = SnacDecoder(checkpoint, device=device)
+    snac_model = model
     snac_device = f"cuda:{device}"
     snac_model.decode_host(np.zeros((1, FRAME), dtype=np.int32))        # warm-up, one frame
     return snac_model
+
+
+def _decode_one(model: SnacDecoder, tok: np.ndarray, extract_slice: bool) -> np.ndarray:
+    if _test_noise is None and _test_precision is None:
+        return model.decode_host(tok, raw_ids=False, extract_slice=extract_slice, seed=next(_noise_seed))
+    import torch
+    t = torch.from_numpy(tok).to(f"cuda:{model.device}")
+    pcm = model.decode(t, raw_ids=False, extract_slice=extract_slice, noise=_test_noise, seed=next(_noise_seed),
+                       precision=_test_precision or "fp16")
+    return pcm.cpu().numpy()
 
 
 def _as_i32(codes) -> np.ndarray:
@@ -70,8 +95,7 @@ def convert_to_audio(code_list: list, extract_slice: bool = False) -> Optional[b
         return None
     num_frames = len(code_list) // FRAME
     tok = _as_i32(code_list[: num_frames * FRAME]).reshape(1, -1)
-    pcm = snac_model.decode_host(tok, raw_ids=False, extract_slice=extract_slice, seed=next(_noise_seed))
-    return pcm.tobytes()
+    return _decode_one(snac_model, tok, extract_slice).tobytes()
 
 
 def redistribute_codes(codes: List[int]) -> Tuple[List[int], List[int], List[int]]:
@@ -102,6 +126,4 @@ def decode_snac(layer0: List[int], layer1: List[int], layer2: List[int], snac_mo
     l2 = np.asarray(layer2, dtype=np.int64).reshape(F_, 4)
     flat = np.stack([l0, l1[:, 0], l2[:, 0], l2[:, 1], l1[:, 1], l2[:, 2], l2[:, 3]], axis=1)
     flat = np.clip(flat, 0, 4095) + np.asarray(POSITION_OFFSETS, dtype=np.int64)[None, :]
-    pcm = model.decode_host(flat.reshape(1, -1).astype(np.int32), raw_ids=False, extract_slice=False,
-                            seed=next(_noise_seed))
-    return pcm.tobytes()
+    return _decode_one(model, np.ascontiguousarray(flat.reshape(1, -1).astype(np.int32)), False).tobytes()

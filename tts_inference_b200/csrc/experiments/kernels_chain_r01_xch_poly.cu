@@ -9,32 +9,19 @@
 //   * the fp32 residual stream lives in TENSOR MEMORY: the NoiseBlock epilogue writes x1 there (tcgen05.st)
 //     and tcgen05.mma then accumulates every ResidualUnit's 1x1 conv directly on top of it;
 //   * a single 16-bit copy of the tile lives in shared memory (128B-swizzled K-major, the UMMA A-operand
-//     layout, filled by TMA).  Its content alternates between
-//         S1_l = snake1_l(x_l)        written by the EPILOGUE that drains TMEM after layer l-1's MMAs: the Snake in
-//                                     front of the depthwise conv is evaluated in fp32 on the fp32 residual, once per
-//                                     element, where the value is in registers anyway (round 2: it used to be
-//                                     re-derived from a 16-bit copy inside the prologue, which made the prologue the
-//                                     MUFU / FMA-pipe hot spot while both pipes idled through the epilogues), and
-//         A_l  = snake2_l(dw_l(S1_l)) written IN PLACE by the PROLOGUE: a 7-tap window slides in registers along one
-//                                     dilation class (taps of row r are r + j*d, so a class only ever reads its own
-//                                     rows; the 3 rows either side of a warp's span are fetched before a CTA barrier),
-//     the MMAs consume A_l block by block, and the epilogue of each 128-row block starts as soon as that block's MMAs
-//     have committed;
-//   * FOLD (fp16 operands, Snake alphas inside a safe range -- checked when the handle is created, snacb.cu): no alpha
-//     multiply is left in the prologue.  The epilogue emits S1'' = alpha1 * snake1(x) = x'' + sin^2 x'' with
-//     x'' = alpha1 * x (one FFMA on the accumulator), the depthwise taps carry alpha2 / alpha1, its bias alpha2, so the
-//     conv yields a'' = alpha2 * a and snake2 is a'' + sin^2 a'' with 1 / alpha2 folded into the 1x1 weights' K columns.
-//     Otherwise (alpha = 0, |alpha| tiny or huge, or bf16 operands) the general form x + (alpha + 1e-9)^-1 sin^2(alpha x)
-//     runs in fp32 -- for alpha = 0 that is exactly x, as in the reference;
+//     layout, filled by TMA).  Each layer rewrites it IN PLACE: the prologue turns x_l into the operand
+//     snake2(dw(snake1(x_l))) with a 7-tap window sliding in registers along one dilation class (taps of row r
+//     are r + j*d, so a class only ever reads its own rows; the 3 rows either side of a warp's span are
+//     fetched before a CTA barrier), the MMAs consume it block by block, and the epilogue of each 128-row block
+//     (started as soon as that block's MMAs commit) writes x_{l+1} = TMEM + bias back as 16-bit;
+//   * fp16 operands: the prologue runs the Snake tails and the depthwise conv in packed half2 (HFMA2) -- the
+//     FMA pipe, not MUFU, bounds the fp32 formulation; bf16 keeps fp32 math;
 //   * a tile carries a 40-row halo either side (3*(1+3+9) = 39 rows of receptive field); halo results are
 //     garbage by construction and never stored.  Rows outside [0, T) are forced to zero after every layer
 //     (the convs' zero padding);
 //   * the last epilogue leaves snake_next(x_4) in the tile copy and TMA stores stream it out block by block while
 //     the next tile's TMA loads refill the blocks behind them;
 //   * HBM traffic: the ConvTranspose output is read once (+ halo), the block output written once.
-//
-// Earlier variants of this kernel that were measured and dropped (halo exchange through L2, half2-polynomial Snake,
-// two warp groups half a layer apart) are kept, uncompiled, under csrc/experiments/ (DESIGN.md section 6).
 #include <cstdio>
 #include <cstdlib>
 #include <type_traits>
@@ -57,33 +44,33 @@ __device__ __forceinline__ float2 unpack2c(uint32_t v, const __half*) {
     return __half22float2(*reinterpret_cast<const __half2*>(&v));
 }
 __device__ __forceinline__ float2 unpack2c(uint32_t v, const __nv_bfloat16*) {
-    // bf16 -> fp32 is a shift: two ALU-pipe instructions, none on the FMA pipe
-    return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xFFFF0000u));
+    return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v));
 }
 __device__ __forceinline__ __half2 as_h2(uint32_t v) { return *reinterpret_cast<const __half2*>(&v); }
 __device__ __forceinline__ uint32_t as_u32(__half2 v) { return *reinterpret_cast<const uint32_t*>(&v); }
 
 constexpr int kHalo = kChainHalo;            // 40 >= 39, multiple of 8
 
-template <int C, int NB, bool HALF, bool FOLD>
+constexpr int kXPad = 32;                    // XCH: rows of neighbour data kept above / below every chunk plane (>= 27 + 2)
+constexpr int kXRows = 27;                   // rows exchanged per side: 3 * dilation of the coming unit, at most 27
+
+template <int C, int NB, bool HALF = true, bool XCH = false>
 struct ChainCfg {
     static constexpr int kCH = C / 64;                      // 64-channel K chunks
     static constexpr int kRows = NB * 128;                  // tile rows incl. halo
-    static constexpr int kROut = kRows - 2 * kHalo;         // rows stored per tile
+    static constexpr int kROut = XCH ? kRows : kRows - 2 * kHalo;   // rows stored per tile
     static constexpr int kPlane = NB * 16384;               // one chunk plane of the tile [NB][128 rows][128 B]
-    static constexpr int kXBytes = kCH * kPlane;
+    static constexpr int kPadB = XCH ? kXPad * 128 : 0;     // XCH: neighbour rows in front of / behind each plane
+    static constexpr int kPlaneS = kPlane + 2 * kPadB;      // plane stride
+    static constexpr int kXBytes = kCH * kPlaneS;
     static constexpr bool kWRes = (C == 64);                // all four 1x1 weights resident
     static constexpr bool kWChunked = (C == 256);           // weights streamed one 64-channel K chunk at a time
     static constexpr int kWLayer = C * C * 2;               // one layer's weights [kCH][C rows][128 B]
     static constexpr int kWChunk = C * 128;                 // one K chunk of them
     static constexpr int kWBytes = kWRes ? 4 * kWLayer : (kWChunked ? 2 * kWChunk : 2 * kWLayer);
-    // prologue parameters per layer and channel pair:
-    //   FOLD        8 words : half2 alpha2 * dw bias, 7 x half2 dw tap * alpha2 / alpha1
-    //   fp16        12 words: half2 dw bias, 7 x half2 dw tap, float2 alpha2, float2 1 / (alpha2 + 1e-9)
-    //   bf16        20 words: 7 x float2 dw tap, float2 dw bias, float2 alpha2, float2 1 / (alpha2 + 1e-9)
-    static constexpr int kPrmWords = FOLD ? 8 : (HALF ? 12 : 20);
+    static constexpr int kPrmWords = HALF ? 8 : 24;         // per layer and channel pair
     static constexpr int kPrmBytes = 3 * (C / 2) * kPrmWords * 4;
-    static constexpr int kEpiBytes = 12 * C * 4;            // epilogue vectors: 4 layer boundaries x 3, see the kernel
+    static constexpr int kEpiBytes = 8 * C * 4;             // epilogue vectors, see kEpi* below
     static constexpr int kNzBytes = kRows * 4;              // noise value of every tile row
     static constexpr int kOffX = 0;
     static constexpr int kOffW = kOffX + kXBytes;
@@ -92,12 +79,11 @@ struct ChainCfg {
     static constexpr int kOffNz = kOffEpi + kEpiBytes;
     static constexpr int kSpanWarps = (C == 64) ? 8 : kChainWarps;          // warps of the launch configuration (kNW*)
     static constexpr int kSpanBytes = 3 * kSpanWarps * kChainSpans * 8;    // the launch's span table (copied from the kernel parameters)
-    static constexpr int kBarBytes = 256;
+    static constexpr int kBarBytes = XCH ? 128 : 256;
     static constexpr int kOffSpan = kOffNz + kNzBytes;
     static constexpr int kOffBar = kOffSpan + kSpanBytes;
     static constexpr int kSmem = kOffBar + kBarBytes + 1024;
     static constexpr int kTmemCols = NB * C;
-    static_assert(!FOLD || HALF, "the alpha-folded formulation is fp16 only");
     static_assert(NB >= 2 && NB <= 8, "blocks per tile");
     static_assert(kTmemCols == 512 || kTmemCols == 256 || kTmemCols == 128, "TMEM columns");
     static_assert(kSmem <= 232448, "shared memory budget");
@@ -106,39 +92,52 @@ struct ChainCfg {
 
 // ---------------------------------------------------------------------------------------------------------
 // One span of the in-place prologue: rows r_oct + k*D, k < 8*nq, of one 64-channel chunk (lane = channel pair).
-// The tile copy holds S1 = snake1(x) (FOLD: alpha1 * snake1(x)); the span turns it into the 1x1 conv's operand.
 // h0..h2 / t0..t2: the three rows before / after the span (fetched before the barrier, other warps rewrite them).
 // ---------------------------------------------------------------------------------------------------------
-template <int D, int ROWS, bool FOLD>
+// fp16 formulation without a single alpha multiply: the tile copy holds x'' = alpha1 * x, so that
+//   snake1(x) = (x'' + sin^2 x'') / alpha1          (inv_alpha * alpha = 1)
+// the depthwise taps carry alpha2 / alpha1 and its bias alpha2, so that the conv emits a'' = alpha2 * a directly, and
+//   snake2(a) = (a'' + sin^2 a'') / alpha2          with 1 / alpha2 folded into the 1x1 weights' K columns (host).
+//
+// POLY (bit 0: snake1, bit 1: snake2): sin^2 on the FMA pipe in packed half2 instead of two MUFU.SIN in fp32 --
+//   t = x / pi, r = t - rint(t) (magic-number rounding, exact for |t| < 512), sin^2(pi r) = s P(s), s = r^2 <= 1/4,
+// P a degree-3 minimax fit (2.3e-5 max error, below half an fp16 ulp of the result).  Eight HFMA2-class instructions per
+// channel pair, mostly with immediate operands, against 2 converts + 2 FMUL.RZ + 2 MUFU.SIN + pack + HFMA2: the same
+// issue slots, no XU time (the XU pipe, 8 cycles per MUFU warp instruction, bounds the MUFU formulation: DESIGN.md 6).
+__device__ __forceinline__ __half2 snake_h2_poly(__half2 xh) {
+    const __half2 kInvPi = __float2half2_rn(0.318309886f), kMagic = __float2half2_rn(1536.f);
+    const __half2 m = __hfma2(xh, kInvPi, kMagic);
+    const __half2 n = __hsub2(m, kMagic);
+    const __half2 r = __hfma2(xh, kInvPi, __hneg2(n));
+    const __half2 s = __hmin2(__hmul2(r, r), __float2half2_rn(0.25f));      // |x| >= 1608 (no phase left in fp16): stay finite
+    __half2 p = __hfma2(__float2half2_rn(-22.99092533f), s, __float2half2_rn(41.29496355f));
+    p = __hfma2(p, s, __float2half2_rn(-32.35387252f));
+    p = __hfma2(p, s, __float2half2_rn(9.86667475f));
+    return __hfma2(p, s, xh);
+}
+
+template <int D, int ROWS, int POLY, int PADR = 0>
 __device__ __forceinline__ void span_half(uint8_t* plane, int r_oct, const int nq, const uint32_t h0, const uint32_t h1,
                                           const uint32_t h2, const uint32_t t0, const uint32_t t1, const uint32_t t2,
                                           const uint32_t (&swz)[8], const uint32_t* prm) {
     const uint4 q0 = *reinterpret_cast<const uint4*>(prm), q1 = *reinterpret_cast<const uint4*>(prm + 4);
     const __half2 bd = as_h2(q0.x);
     const __half2 w[7] = {as_h2(q0.y), as_h2(q0.z), as_h2(q0.w), as_h2(q1.x), as_h2(q1.y), as_h2(q1.z), as_h2(q1.w)};
-    float2 al2 = make_float2(0.f, 0.f), ia2 = make_float2(0.f, 0.f);
-    if (!FOLD) {
-        const uint4 q2 = *reinterpret_cast<const uint4*>(prm + 8);
-        al2 = make_float2(__uint_as_float(q2.x), __uint_as_float(q2.y));
-        ia2 = make_float2(__uint_as_float(q2.z), __uint_as_float(q2.w));
-    }
-    auto snake2 = [&](__half2 ah) -> uint32_t {
-        const float2 t = __half22float2(ah);
-        if (FOLD) {                                           // ah = alpha2 * a:  ah + sin^2 ah  (= alpha2 * snake2(a))
-            const __half2 sh = __floats2half2_rn(__sinf(t.x), __sinf(t.y));
-            return as_u32(__hfma2(sh, sh, ah));
-        }
-        const float2 o = snake_pair(t, al2, ia2);
-        return as_u32(__floats2half2_rn(o.x, o.y));
+    auto snake_mufu = [&](__half2 xh) -> __half2 {      // xh + sin^2(xh)
+        const float2 t = __half22float2(xh);
+        const __half2 sh = __floats2half2_rn(__sinf(t.x), __sinf(t.y));
+        return __hfma2(sh, sh, xh);
     };
+    auto snake = [&](__half2 xh) -> __half2 { return (POLY & 1) ? snake_h2_poly(xh) : snake_mufu(xh); };
+    auto snake2 = [&](__half2 xh) -> __half2 { return (POLY & 2) ? snake_h2_poly(xh) : snake_mufu(xh); };
     __half2 win[7];
-    win[1] = as_h2(h0); win[2] = as_h2(h1); win[3] = as_h2(h2);
+    win[1] = snake(as_h2(h0)); win[2] = snake(as_h2(h1)); win[3] = snake(as_h2(h2));
     uint8_t* ob = plane + r_oct * 128;             // r_oct = 0 (mod 8): (row & 7) of step k is (k*D) & 7
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
-        uint32_t raw = 0u;                         // class starts may lie above the tile
-        if (r_oct + j * D >= 0) raw = *reinterpret_cast<const uint32_t*>(ob + j * D * 128 + swz[(j * D) & 7]);
-        win[4 + j] = as_h2(raw);
+        uint32_t raw = 0u;                         // class starts may lie above the tile (PADR rows of neighbour data there)
+        if (r_oct + j * D >= -PADR) raw = *reinterpret_cast<const uint32_t*>(ob + j * D * 128 + swz[(j * D) & 7]);
+        win[4 + j] = snake(as_h2(raw));
     }
 #pragma unroll 1
     for (int qo = 0; qo < nq; ++qo) {
@@ -151,14 +150,14 @@ __device__ __forceinline__ void span_half(uint8_t* plane, int r_oct, const int n
         for (int k = 0; k < 8; ++k) {
 #pragma unroll
             for (int j = 0; j < 6; ++j) win[j] = win[j + 1];
-            win[6] = as_h2(raw[k]);
+            win[6] = snake(as_h2(raw[k]));
             __half2 acc = bd;
 #pragma unroll
             for (int j = 0; j < 7; ++j) acc = __hfma2(w[j], win[j], acc);
-            const uint32_t o = snake2(acc);
+            const __half2 o = snake2(acc);
             const int r = r_oct + k * D;
             if (static_cast<unsigned>(r) < static_cast<unsigned>(ROWS))
-                *reinterpret_cast<uint32_t*>(ob + k * D * 128 + swz[(k * D) & 7]) = o;
+                *reinterpret_cast<uint32_t*>(ob + k * D * 128 + swz[(k * D) & 7]) = as_u32(o);
         }
         r_oct += 8 * D;
         ob += 8 * D * 128;
@@ -166,25 +165,28 @@ __device__ __forceinline__ void span_half(uint8_t* plane, int r_oct, const int n
 }
 
 // same span, fp32 math (bf16 operands: an 8-bit mantissa cannot carry the depthwise accumulation)
-template <int D, int ROWS>
-__device__ __forceinline__ void span_bf16(uint8_t* plane, int r_oct, const int nq, const uint32_t h0, const uint32_t h1,
-                                          const uint32_t h2, const uint32_t t0, const uint32_t t1, const uint32_t t2,
-                                          const uint32_t (&swz)[8], const uint32_t* prm) {
+template <int D, int ROWS, typename HT>
+__device__ __forceinline__ void span_f32(uint8_t* plane, int r_oct, const int nq, const uint32_t h0, const uint32_t h1,
+                                         const uint32_t h2, const uint32_t t0, const uint32_t t1, const uint32_t t2,
+                                         const uint32_t (&swz)[8], const uint32_t* prm) {
     const float4* p4 = reinterpret_cast<const float4*>(prm);
-    const float4 q0 = p4[0], q1 = p4[1], q2 = p4[2], q3 = p4[3], q4 = p4[4];
-    const float2 w[7] = {make_float2(q0.x, q0.y), make_float2(q0.z, q0.w), make_float2(q1.x, q1.y), make_float2(q1.z, q1.w),
-                         make_float2(q2.x, q2.y), make_float2(q2.z, q2.w), make_float2(q3.x, q3.y)};
-    const float2 bd = make_float2(q3.z, q3.w);
-    const float2 al2 = make_float2(q4.x, q4.y), ia2 = make_float2(q4.z, q4.w);
-    const __nv_bfloat16* tag = nullptr;
+    const float4 q0 = p4[0], q1 = p4[1], q2 = p4[2], q3 = p4[3], q4 = p4[4], q5 = p4[5];
+    const float2 al1 = make_float2(q0.x, q0.y), ia1 = make_float2(q0.z, q0.w);
+    const float2 w[7] = {make_float2(q1.x, q1.y), make_float2(q1.z, q1.w), make_float2(q2.x, q2.y), make_float2(q2.z, q2.w),
+                         make_float2(q3.x, q3.y), make_float2(q3.z, q3.w), make_float2(q4.x, q4.y)};
+    const float2 bd = make_float2(q4.z, q4.w);
+    const float2 al2 = make_float2(q5.x, q5.y), ia2 = make_float2(q5.z, q5.w);
+    const HT* tag = nullptr;
     float2 win[7];
-    win[1] = unpack2c(h0, tag); win[2] = unpack2c(h1, tag); win[3] = unpack2c(h2, tag);
+    win[1] = snake_pair(unpack2c(h0, tag), al1, ia1);
+    win[2] = snake_pair(unpack2c(h1, tag), al1, ia1);
+    win[3] = snake_pair(unpack2c(h2, tag), al1, ia1);
     uint8_t* ob = plane + r_oct * 128;
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
         uint32_t raw = 0u;
         if (r_oct + j * D >= 0) raw = *reinterpret_cast<const uint32_t*>(ob + j * D * 128 + swz[(j * D) & 7]);
-        win[4 + j] = unpack2c(raw, tag);
+        win[4 + j] = snake_pair(unpack2c(raw, tag), al1, ia1);
     }
 #pragma unroll 1
     for (int qo = 0; qo < nq; ++qo) {
@@ -197,7 +199,7 @@ __device__ __forceinline__ void span_bf16(uint8_t* plane, int r_oct, const int n
         for (int k = 0; k < 8; ++k) {
 #pragma unroll
             for (int j = 0; j < 6; ++j) win[j] = win[j + 1];
-            win[6] = unpack2c(raw[k], tag);
+            win[6] = snake_pair(unpack2c(raw[k], tag), al1, ia1);
             float2 acc = bd;
 #pragma unroll
             for (int j = 0; j < 7; ++j) acc = ffma2(w[j], win[j], acc);
@@ -213,22 +215,38 @@ __device__ __forceinline__ void span_bf16(uint8_t* plane, int r_oct, const int n
 
 enum { EPI_C_NOISE = 0, EPI_C_MID = 1, EPI_C_FINAL = 2 };
 
+// inter-CTA flags of the halo exchange (global memory, gpu scope).  A wait that outlasts ~1 s traps instead of hanging.
+__device__ __forceinline__ void flag_release(int* p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void flag_wait_ge(const int* p, int want) {
+    const long long t0 = clock64();
+    for (;;) {
+        int v;
+        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+        if (v >= want) return;
+        __nanosleep(20);
+        if (clock64() - t0 > (1ll << 31)) __trap();
+    }
+}
+
 }  // namespace
 
 // NW symmetric warps (prologue + epilogue); thread 0 also issues TMA / MMA.  16 warps: one CTA per SM; 8 warps: two.
-template <int C, int NB, int NW, typename HT, bool FOLD>
-__global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 1)
+template <int C, int NB, int NW, typename HT, int POLY, bool XCH = false>
+__global__ void __launch_bounds__(NW * 32) __maxnreg__(NW == 8 ? 128 : 128 + 0 * NW)
 k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmOe,
         const __grid_constant__ CUtensorMap tmOm, const __grid_constant__ CUtensorMap tmWn,
         const __grid_constant__ CUtensorMap tmW0, const __grid_constant__ CUtensorMap tmW1,
         const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ ChainArgs a, const int num_tiles) {
     constexpr bool kHalfMath = std::is_same<HT, __half>::value;
-    using Cfg = ChainCfg<C, NB, kHalfMath, FOLD>;
+    static_assert(!XCH || (kHalfMath && C <= 128), "halo exchange: fp16 operands, C = 64 / 128");
+    using Cfg = ChainCfg<C, NB, kHalfMath, XCH>;
     constexpr int CH = Cfg::kCH;
     constexpr int kThreads = NW * 32;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint8_t* sX = smem + Cfg::kOffX;
+    uint8_t* sX = smem + Cfg::kOffX + Cfg::kPadB;       // row 0 of chunk plane 0
     uint8_t* sW = smem + Cfg::kOffW;
     uint32_t* sPrm = reinterpret_cast<uint32_t*>(smem + Cfg::kOffPrm);
     float* sEpi = reinterpret_cast<float*>(smem + Cfg::kOffEpi);
@@ -262,26 +280,23 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
         const int l = i / (C / 2), ch = 2 * (i % (C / 2));
         const ChainLayer& L = a.res[l];
         uint32_t* d = sPrm + i * Cfg::kPrmWords;
-        if (FOLD) {
+        if (kHalfMath) {
+            // half2 words: alpha2 * dw bias, then dw taps 0..6 times alpha2 / alpha1 (see span_half)
             const float a1x = L.alpha1[ch], a1y = L.alpha1[ch + 1], a2x = L.alpha2[ch], a2y = L.alpha2[ch + 1];
             d[0] = as_u32(__floats2half2_rn(L.dw_b[ch] * a2x, L.dw_b[ch + 1] * a2y));
 #pragma unroll
             for (int j = 0; j < 7; ++j)
                 d[1 + j] = as_u32(__floats2half2_rn(L.dw_w[j * C + ch] * (a2x / a1x), L.dw_w[j * C + ch + 1] * (a2y / a1y)));
-        } else if (kHalfMath) {
-            d[0] = as_u32(__floats2half2_rn(L.dw_b[ch], L.dw_b[ch + 1]));
-#pragma unroll
-            for (int j = 0; j < 7; ++j) d[1 + j] = as_u32(__floats2half2_rn(L.dw_w[j * C + ch], L.dw_w[j * C + ch + 1]));
-            d[8] = __float_as_uint(L.alpha2[ch]); d[9] = __float_as_uint(L.alpha2[ch + 1]);
-            d[10] = __float_as_uint(L.inv2[ch]); d[11] = __float_as_uint(L.inv2[ch + 1]);
         } else {
+            d[0] = __float_as_uint(L.alpha1[ch]); d[1] = __float_as_uint(L.alpha1[ch + 1]);
+            d[2] = __float_as_uint(L.inv1[ch]); d[3] = __float_as_uint(L.inv1[ch + 1]);
 #pragma unroll
             for (int j = 0; j < 7; ++j) {
-                d[2 * j] = __float_as_uint(L.dw_w[j * C + ch]); d[2 * j + 1] = __float_as_uint(L.dw_w[j * C + ch + 1]);
+                d[4 + 2 * j] = __float_as_uint(L.dw_w[j * C + ch]); d[5 + 2 * j] = __float_as_uint(L.dw_w[j * C + ch + 1]);
             }
-            d[14] = __float_as_uint(L.dw_b[ch]); d[15] = __float_as_uint(L.dw_b[ch + 1]);
-            d[16] = __float_as_uint(L.alpha2[ch]); d[17] = __float_as_uint(L.alpha2[ch + 1]);
-            d[18] = __float_as_uint(L.inv2[ch]); d[19] = __float_as_uint(L.inv2[ch + 1]);
+            d[18] = __float_as_uint(L.dw_b[ch]); d[19] = __float_as_uint(L.dw_b[ch + 1]);
+            d[20] = __float_as_uint(L.alpha2[ch]); d[21] = __float_as_uint(L.alpha2[ch + 1]);
+            d[22] = __float_as_uint(L.inv2[ch]); d[23] = __float_as_uint(L.inv2[ch + 1]);
         }
     }
     // the span table is indexed by (layer, warp) at run time: from shared memory, not from the constant bank (a dynamically
@@ -289,20 +304,17 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
     static_assert(NW <= Cfg::kSpanWarps, "span table");
     for (int i = tid; i < 3 * Cfg::kSpanWarps * kChainSpans; i += kThreads)
         sSpan[i] = a.spans[i / (Cfg::kSpanWarps * kChainSpans)][(i / kChainSpans) % Cfg::kSpanWarps][i % kChainSpans];
-    // epilogue vectors, three per layer boundary i (0: NoiseBlock -> unit d=1, 1: d=1 -> d=3, 2: d=3 -> d=9, 3: d=9 -> out):
-    //   [3i]     bias: sum of the 1x1 biases so far (0 for i = 0); FOLD, i < 3: that bias times alpha1 of the coming unit
-    //   [3i + 1] alpha of the Snake the epilogue applies (the coming unit's snake1, the next layer's Snake for i = 3)
-    //   [3i + 2] 1 / (alpha + 1e-9) of it (unused by FOLD for i < 3)
+    // epilogue vectors: [0] scale of the NoiseBlock output, [1],[2] scale and scaled bias after unit d=1, [3],[4] after
+    // d=3, [5] bias after d=9, [6],[7] alpha / 1/alpha of the next Snake.  scale = alpha1 of the next unit's Snake in the
+    // fp16 formulation (the tile copy holds alpha1 * x), 1 otherwise.
     for (int c = tid; c < C; c += kThreads) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float b = i == 0 ? 0.f : a.bias_cum[(i - 1) * C + c];
-            const float al = i < 3 ? a.res[i].alpha1[c] : a.alpha_next[c];
-            const float ia = i < 3 ? a.res[i].inv1[c] : a.inv_next[c];
-            sEpi[(3 * i) * C + c] = (FOLD && i < 3) ? b * al : b;
-            sEpi[(3 * i + 1) * C + c] = al;
-            sEpi[(3 * i + 2) * C + c] = ia;
-        }
+        const float s0 = kHalfMath ? a.res[0].alpha1[c] : 1.f, s1 = kHalfMath ? a.res[1].alpha1[c] : 1.f;
+        const float s2 = kHalfMath ? a.res[2].alpha1[c] : 1.f;
+        sEpi[c] = s0;
+        sEpi[C + c] = s1; sEpi[2 * C + c] = a.bias_cum[c] * s1;
+        sEpi[3 * C + c] = s2; sEpi[4 * C + c] = a.bias_cum[C + c] * s2;
+        sEpi[5 * C + c] = a.bias_cum[2 * C + c];
+        sEpi[6 * C + c] = a.alpha_next[c]; sEpi[7 * C + c] = a.inv_next[c];
     }
     tc_fence_before();
     __syncthreads();
@@ -325,12 +337,12 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
     };
     auto tile_coords = [&](int tile, int& s, int& t_start) {
         s = tile / tiles_t;
-        t_start = (a.t_n > 0 ? a.t_lo : 0) + (tile % tiles_t) * Cfg::kROut - kHalo;
+        t_start = (a.t_n > 0 ? a.t_lo : 0) + (tile % tiles_t) * Cfg::kROut - (XCH ? 0 : kHalo);
     };
     auto load_block = [&](int s, int t_start, int b) {      // thread 0; ld_bar's expect_tx covers the whole tile
 #pragma unroll
         for (int kc = 0; kc < CH; ++kc)
-            tma_load_3d_hint(sX + kc * Cfg::kPlane + b * 16384, &tmY, kc * 64, t_start + b * 128, s, ld_bar, kL2EvictFirst);
+            tma_load_3d_hint(sX + kc * Cfg::kPlaneS + b * 16384, &tmY, kc * 64, t_start + b * 128, s, ld_bar, kL2EvictFirst);
     };
     int tile = blockIdx.x;
     if (tid == 0 && tile < num_tiles) {
@@ -375,7 +387,7 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
                 for (int b = 0; b < NB; ++b)
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
-                        mma_f16_ss(tmem_base + b * C, umma_desc_sw128(sx_addr + kc * Cfg::kPlane + b * 16384 + k * 32),
+                        mma_f16_ss(tmem_base + b * C, umma_desc_sw128(sx_addr + kc * Cfg::kPlaneS + b * 16384 + k * 32),
                                    umma_desc_sw128(w_addr + k * 32), idescW, (l > 0 || kc > 0 || k > 0) ? 1u : 0u);
                 mma_commit(&wfree_bar[buf]);
                 if (kc & 1) {
@@ -401,7 +413,7 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
             for (int kc = 0; kc < CH; ++kc)
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                    mma_f16_ss(tmem_base + b * C, umma_desc_sw128(sx_addr + kc * Cfg::kPlane + b * 16384 + k * 32),
+                    mma_f16_ss(tmem_base + b * C, umma_desc_sw128(sx_addr + kc * Cfg::kPlaneS + b * 16384 + k * 32),
                                umma_desc_sw128(w_addr + kc * (C * 128) + k * 32), idescW,
                                (l > 0 || kc > 0 || k > 0) ? 1u : 0u);
             mma_commit(&mma_bar[b]);
@@ -414,16 +426,11 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
         if (l + 2 < 4 || has_next) load_w(l2, l & 1);
     };
 
-    // epilogue after layer boundary `bnd`; each 128-row block is drained as soon as its MMAs have committed
-    //   NOISE (bnd 0): x1 = y + n[t] * TMEM -> TMEM (fp32 residual stream); tile copy = snake1_0(x1)
-    //   MID (bnd 1, 2): tile copy = snake1_bnd(TMEM + cumulative bias)
-    //   FINAL (bnd 3):  tile copy = snake_next(TMEM + cumulative bias)
-    auto epilogue = [&](auto mode_tag, const int bnd, int t_start) {
+    // epilogue of one layer; each 128-row block is drained as soon as its MMAs have committed
+    //   NOISE: x1 = y + n[t] * TMEM  -> TMEM (fp32 residual stream) and the 16-bit tile copy
+    //   MID:   tile copy = TMEM + cumulative bias          FINAL: tile copy = snake_next(TMEM + cumulative bias)
+    auto epilogue = [&](auto mode_tag, const float* scale, const float* bias, int t_start) {
         constexpr int MODE = decltype(mode_tag)::value;
-        constexpr bool kFoldHere = FOLD && MODE != EPI_C_FINAL;
-        const float* vb = sEpi + (3 * bnd) * C;            // bias (FOLD: scaled bias)
-        const float* va = vb + C;                          // alpha (FOLD: the scale)
-        const float* vi = va + C;                          // 1 / (alpha + 1e-9)
         const int q = warp & 3, g = warp >> 2;
         constexpr int kPieces = NB * (C / 32);
         const HT* tag = nullptr;
@@ -431,7 +438,7 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
         for (int it = g; it < kPieces; it += NW / 4) {
             const int blk = it / (C / 32), cg = it % (C / 32);
             // the last epilogue only feeds the TMA stores: 32-row groups entirely inside the halo are skipped
-            if (MODE == EPI_C_FINAL && (blk * 128 + q * 32 + 32 <= kHalo || blk * 128 + q * 32 >= Cfg::kRows - kHalo)) continue;
+            if (!XCH && MODE == EPI_C_FINAL && (blk * 128 + q * 32 + 32 <= kHalo || blk * 128 + q * 32 >= Cfg::kRows - kHalo)) continue;
             mbar_wait(&mma_bar[blk], mma_par);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + blk * C + cg * 32;
@@ -440,7 +447,7 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
             const int i = blk * 128 + q * 32 + lane;
             const int t = t_start + i;
             const bool valid = static_cast<unsigned>(t) < static_cast<unsigned>(a.T);
-            uint8_t* row = sX + (cg >> 1) * Cfg::kPlane + i * 128;
+            uint8_t* row = sX + (cg >> 1) * Cfg::kPlaneS + i * 128;
             uint4 yv[4];
             float nz = 0.f;
             if (MODE == EPI_C_NOISE) {
@@ -460,23 +467,21 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
                     v0 = fmaf(nz, v0, y0.x); v1 = fmaf(nz, v1, y0.y); v2 = fmaf(nz, v2, y1.x); v3 = fmaf(nz, v3, y1.y);
                     raw[j] = __float_as_uint(v0); raw[j + 1] = __float_as_uint(v1);
                     raw[j + 2] = __float_as_uint(v2); raw[j + 3] = __float_as_uint(v3);
-                }
-                const float4 al = *reinterpret_cast<const float4*>(va + cg * 32 + j);
-                if (kFoldHere) {
-                    // x'' = alpha1 * (x + b);  S1'' = x'' + sin^2 x''
-                    if (MODE == EPI_C_NOISE) { v0 *= al.x; v1 *= al.y; v2 *= al.z; v3 *= al.w; }
-                    else {
-                        const float4 b = *reinterpret_cast<const float4*>(vb + cg * 32 + j);
-                        v0 = fmaf(v0, al.x, b.x); v1 = fmaf(v1, al.y, b.y); v2 = fmaf(v2, al.z, b.z); v3 = fmaf(v3, al.w, b.w);
+                    if (kHalfMath) {
+                        const float4 sc = *reinterpret_cast<const float4*>(scale + cg * 32 + j);
+                        v0 *= sc.x; v1 *= sc.y; v2 *= sc.z; v3 *= sc.w;
                     }
-                    const float s0 = __sinf(v0), s1 = __sinf(v1), s2 = __sinf(v2), s3 = __sinf(v3);
-                    v0 = fmaf(s0, s0, v0); v1 = fmaf(s1, s1, v1); v2 = fmaf(s2, s2, v2); v3 = fmaf(s3, s3, v3);
+                } else if (MODE == EPI_C_MID && kHalfMath) {
+                    const float4 sc = *reinterpret_cast<const float4*>(scale + cg * 32 + j);
+                    const float4 b = *reinterpret_cast<const float4*>(bias + cg * 32 + j);
+                    v0 = fmaf(v0, sc.x, b.x); v1 = fmaf(v1, sc.y, b.y); v2 = fmaf(v2, sc.z, b.z); v3 = fmaf(v3, sc.w, b.w);
                 } else {
-                    if (MODE != EPI_C_NOISE) {
-                        const float4 b = *reinterpret_cast<const float4*>(vb + cg * 32 + j);
-                        v0 += b.x; v1 += b.y; v2 += b.z; v3 += b.w;
-                    }
-                    const float4 ia = *reinterpret_cast<const float4*>(vi + cg * 32 + j);
+                    const float4 b = *reinterpret_cast<const float4*>(bias + cg * 32 + j);
+                    v0 += b.x; v1 += b.y; v2 += b.z; v3 += b.w;
+                }
+                if (MODE == EPI_C_FINAL) {
+                    const float4 al = *reinterpret_cast<const float4*>(sEpi + 6 * C + cg * 32 + j);
+                    const float4 ia = *reinterpret_cast<const float4*>(sEpi + 7 * C + cg * 32 + j);
                     v0 = snake_f<true>(v0, al.x, ia.x); v1 = snake_f<true>(v1, al.y, ia.y);
                     v2 = snake_f<true>(v2, al.z, ia.z); v3 = snake_f<true>(v3, al.w, ia.w);
                 }
@@ -508,7 +513,9 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
         int s, t_start;
         tile_coords(tile, s, t_start);
         // claim the tile after this one (persistent CTAs, dynamic order: tiles cost the same but SMs do not run alike)
-        if (tid == 0) s_next[n & 1] = static_cast<int>(gridDim.x) + atomicAdd(a.tile_counter, 1);
+        // (halo exchange: static round-robin instead, so that the CTAs holding neighbouring tiles run side by side)
+        if (tid == 0) s_next[n & 1] = XCH ? tile + static_cast<int>(gridDim.x)
+                                          : static_cast<int>(gridDim.x) + atomicAdd(a.tile_counter, 1);
 
         // ---------------------------------------------------------------- noise values (overlaps the tile load)
         {
@@ -524,6 +531,12 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
                 sNz[i] = v;
             }
         }
+        if (XCH && tid == 0 && tile >= a.xslots) {
+            // the exchange slot of this tile was last used by tile - xslots: both its neighbours must have taken their rows
+            const int old = tile - a.xslots, pos = old % tiles_t;
+            const int readers = (pos > 0) + (pos + 1 < tiles_t);
+            for (int l = 0; l < 3; ++l) flag_wait_ge(&a.xack[old * 3 + l], readers);
+        }
         mbar_wait(ld_bar, n & 1);
         __syncthreads();
         const int next_tile = s_next[n & 1];
@@ -531,7 +544,7 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
         tick(0);
         // ---------------------------------------------------------------- NoiseBlock: TMEM = Wn y, then x1 = y + n TMEM
         if (tid == 0) issue_layer(0, n, has_next);
-        epilogue(std::integral_constant<int, EPI_C_NOISE>{}, 0, t_start);
+        epilogue(std::integral_constant<int, EPI_C_NOISE>{}, sEpi, nullptr, t_start);
         if (tid == 0) { mbar_wait(&mma_bar[NB - 1], mma_par); prefetch_w(0, has_next); }
         mma_par ^= 1u;
         tc_fence_before();
@@ -542,6 +555,49 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
 #pragma unroll 1
         for (int l = 0; l < 3; ++l) {
             const int d = (l == 0) ? 1 : (l == 1 ? 3 : 9);
+            if (XCH) {
+                // ---- halo exchange: instead of recomputing a 40-row halo, neighbouring tiles of a stream (held by other
+                // CTAs, running side by side) swap the 3*d boundary rows of the 16-bit tile copy this unit's depthwise
+                // conv reaches across, through an L2-resident buffer + release / acquire flags.  A raw byte copy keeps
+                // the 128B swizzle: source and destination rows are congruent mod 8.
+                const int nx = 3 * d, pos = tile % tiles_t;
+                const bool has_prev = pos > 0, has_nxt = pos + 1 < tiles_t;
+                constexpr int kSideB = CH * kXRows * 128;
+                auto xslot = [&](int t, int side) { return a.xbuf + ((static_cast<size_t>(t % a.xslots) * 3 + l) * 2 + side) * kSideB; };
+                const int chunks = CH * nx * 8;                         // 16-byte pieces per side
+                for (int i = tid; i < 2 * chunks; i += kThreads) {
+                    const int side = i >= chunks, j = side ? i - chunks : i;
+                    const int kc = j / (nx * 8), rem = j % (nx * 8);
+                    if (side ? !has_nxt : !has_prev) continue;          // nobody reads that side
+                    const uint8_t* src = sX + kc * Cfg::kPlaneS + (side ? (Cfg::kRows - nx) * 128 : 0) + rem * 16;
+                    *reinterpret_cast<uint4*>(xslot(tile, side) + kc * (kXRows * 128) + rem * 16) = *reinterpret_cast<const uint4*>(src);
+                }
+                __syncthreads();
+                if (tid == 0) {
+                    __threadfence();                                    // cumulative: the CTA's stores above, ordered by the barrier
+                    flag_release(&a.xflags[tile * 3 + l], 1);
+                    if (has_prev) flag_wait_ge(&a.xflags[(tile - 1) * 3 + l], 1);
+                }
+                if (tid == 32 && has_nxt) flag_wait_ge(&a.xflags[(tile + 1) * 3 + l], 1);
+                __syncthreads();
+                for (int i = tid; i < 2 * chunks; i += kThreads) {
+                    const int side = i >= chunks, j = side ? i - chunks : i;
+                    const int kc = j / (nx * 8), rem = j % (nx * 8);
+                    uint4 v = make_uint4(0u, 0u, 0u, 0u);               // stream edge: the conv's zero padding
+                    if (side == 0) {                                    // rows -nx .. -1 <- the previous tile's last rows
+                        if (has_prev) v = __ldcg(reinterpret_cast<const uint4*>(xslot(tile - 1, 1) + kc * (kXRows * 128) + rem * 16));
+                        *reinterpret_cast<uint4*>(sX + kc * Cfg::kPlaneS - nx * 128 + rem * 16) = v;
+                    } else {                                            // rows kRows .. kRows + nx - 1 <- the next tile's first rows
+                        if (has_nxt) v = __ldcg(reinterpret_cast<const uint4*>(xslot(tile + 1, 0) + kc * (kXRows * 128) + rem * 16));
+                        *reinterpret_cast<uint4*>(sX + kc * Cfg::kPlaneS + Cfg::kRows * 128 + rem * 16) = v;
+                    }
+                }
+                __syncthreads();
+                if (tid == 0) {
+                    if (has_prev) atomicAdd(&a.xack[(tile - 1) * 3 + l], 1);
+                    if (has_nxt) atomicAdd(&a.xack[(tile + 1) * 3 + l], 1);
+                }
+            }
             // ---- spans of this warp: pre-read the 3 rows before and after each span (owned by other warps)
             uint32_t hd[kChainSpans][3], tl[kChainSpans][3];
             int r_first[kChainSpans], n_oct[kChainSpans], kcs[kChainSpans];
@@ -552,13 +608,13 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
 #pragma unroll
                 for (int j = 0; j < 3; ++j) { hd[sp][j] = 0u; tl[sp][j] = 0u; }
                 if (spn.n_oct > 0) {                       // warp-uniform: unused span slots cost one branch
-                    const uint8_t* lane_base = sX + spn.kc * Cfg::kPlane + ((lane & 3) << 2);
+                    const uint8_t* lane_base = sX + spn.kc * Cfg::kPlaneS + ((lane & 3) << 2);
                     const int c16 = lane >> 2;
 #pragma unroll
                     for (int j = 0; j < 3; ++j) {
                         const int rh = spn.r_first - (3 - j) * d;
                         const int rt = spn.r_first + (8 * spn.n_oct + j) * d;
-                        if (rh >= 0) hd[sp][j] = *reinterpret_cast<const uint32_t*>(lane_base + rh * 128 + (((c16 ^ rh) & 7) << 4));
+                        if (rh >= -(XCH ? kXPad : 0)) hd[sp][j] = *reinterpret_cast<const uint32_t*>(lane_base + rh * 128 + (((c16 ^ rh) & 7) << 4));
                         tl[sp][j] = *reinterpret_cast<const uint32_t*>(lane_base + rt * 128 + (((c16 ^ rt) & 7) << 4));
                     }
                 }
@@ -579,15 +635,15 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
                     tt[j] = sp == 0 ? tl[0][j] : (sp == 1 ? tl[1][j] : (sp == 2 ? tl[2][j] : tl[3][j]));
                 }
                 const uint32_t* prm = sPrm + ((l * (C / 2)) + kc * 32 + lane) * Cfg::kPrmWords;
-                uint8_t* plane = sX + kc * Cfg::kPlane;
+                uint8_t* plane = sX + kc * Cfg::kPlaneS;
                 if (kHalfMath) {
-                    if (d == 1) span_half<1, Cfg::kRows, FOLD>(plane, r0, nq, hh[0], hh[1], hh[2], tt[0], tt[1], tt[2], swz, prm);
-                    else if (d == 3) span_half<3, Cfg::kRows, FOLD>(plane, r0, nq, hh[0], hh[1], hh[2], tt[0], tt[1], tt[2], swz, prm);
-                    else span_half<9, Cfg::kRows, FOLD>(plane, r0, nq, hh[0], hh[1], hh[2], tt[0], tt[1], tt[2], swz, prm);
+                    if (d == 1) span_half<1, Cfg::kRows, POLY, XCH ? kXPad : 0>(plane, r0, nq, hh[0], hh[1], hh[2], tt[0], tt[1], tt[2], swz, prm);
+                    else if (d == 3) span_half<3, Cfg::kRows, POLY, XCH ? kXPad : 0>(plane, r0, nq, hh[0], hh[1], hh[2], tt[0], tt[1], tt[2], swz, prm);
+                    else span_half<9, Cfg::kRows, POLY, XCH ? kXPad : 0>(plane, r0, nq, hh[0], hh[1], hh[2], tt[0], tt[1], tt[2], swz, prm);
                 } else {
-                    if (d == 1) span_bf16<1, Cfg::kRows>(plane, r0, nq, hh[0], hh[1], hh[2], tt[0], tt[1], tt[2], swz, prm);
-                    else if (d == 3) span_bf16<3, Cfg::kRows>(plane, r0, nq, hh[0], hh[1], hh[2], tt[0], tt[1], tt[2], swz, prm);
-                    else span_bf16<9, Cfg::kRows>(plane, r0, nq, hh[0], hh[1], hh[2], tt[0], tt[1], tt[2], swz, prm);
+                    if (d == 1) span_f32<1, Cfg::kRows, HT>(plane, r0, nq, hh[0], hh[1], hh[2], tt[0], tt[1], tt[2], swz, prm);
+                    else if (d == 3) span_f32<3, Cfg::kRows, HT>(plane, r0, nq, hh[0], hh[1], hh[2], tt[0], tt[1], tt[2], swz, prm);
+                    else span_f32<9, Cfg::kRows, HT>(plane, r0, nq, hh[0], hh[1], hh[2], tt[0], tt[1], tt[2], swz, prm);
                 }
             }
             tick(3 + 4 * l);
@@ -595,8 +651,8 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
             __syncthreads();
             tick(4 + 4 * l);
             if (tid == 0) issue_layer(l + 1, n, has_next);
-            if (l < 2) epilogue(std::integral_constant<int, EPI_C_MID>{}, l + 1, t_start);
-            else epilogue(std::integral_constant<int, EPI_C_FINAL>{}, 3, t_start);
+            if (l < 2) epilogue(std::integral_constant<int, EPI_C_MID>{}, sEpi + (1 + 2 * l) * C, sEpi + (2 + 2 * l) * C, t_start);
+            else epilogue(std::integral_constant<int, EPI_C_FINAL>{}, nullptr, sEpi + 5 * C, t_start);
             if (tid == 0) { mbar_wait(&mma_bar[NB - 1], mma_par); prefetch_w(l + 1, has_next); }
             mma_par ^= 1u;
             if (l == 2) fence_proxy_async_smem();          // the tile copy is the source of the TMA stores below
@@ -612,8 +668,9 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
             for (int b = 0; b < NB; ++b) {
 #pragma unroll
                 for (int kc = 0; kc < CH; ++kc) {
-                    const uint8_t* src = sX + kc * Cfg::kPlane + b * 16384;
-                    if (b == 0) tma_store_3d(&tmOe, src + kHalo * 128, kc * 64, t_out, s);
+                    const uint8_t* src = sX + kc * Cfg::kPlaneS + b * 16384;
+                    if (XCH) tma_store_3d(&tmOm, src, kc * 64, t_start + b * 128, s);
+                    else if (b == 0) tma_store_3d(&tmOe, src + kHalo * 128, kc * 64, t_out, s);
                     else if (b == NB - 1) tma_store_3d(&tmOe, src, kc * 64, t_start + b * 128, s);
                     else tma_store_3d(&tmOm, src, kc * 64, t_start + b * 128, s);
                 }
@@ -651,24 +708,42 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
 
 namespace {
 
-template <int C, int NB, int NW, typename HT, bool FOLD>
+template <int C, int NB, int NW, typename HT, int POLY = 0, bool XCH = false>
 cudaError_t launch_chain_t(const ChainArgs& a, const CUtensorMap* tm, int sm_count, cudaStream_t st) {
-    using Cfg = ChainCfg<C, NB, std::is_same<HT, __half>::value, FOLD>;
-    static PerDeviceOnce once;
-    int dev_;
-    if (once.needed(&dev_)) {
-        cudaError_t e = cudaFuncSetAttribute(k_chain<C, NB, NW, HT, FOLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
+    using Cfg = ChainCfg<C, NB, std::is_same<HT, __half>::value, XCH>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(k_chain<C, NB, NW, HT, POLY, XCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(k_chain<C, NB, NW, HT, FOLD>, cudaFuncAttributePreferredSharedMemoryCarveout,
+        e = cudaFuncSetAttribute(k_chain<C, NB, NW, HT, POLY, XCH>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                  cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return e;
-        once.done(dev_);
+        attr_done = true;
     }
     const int tiles = a.S * (((a.t_n > 0 ? a.t_n : a.T) + Cfg::kROut - 1) / Cfg::kROut);
     if (tiles == 0) return cudaSuccess;
-    const int slots = sm_count * (NW == 8 ? 2 : 1);
+    int slots = sm_count * (NW == 8 ? 2 : 1);
+    if (XCH) {
+        // the CTAs wait for one another: every CTA of the grid must be resident, and the exchange slots must cover it
+        static int occ = -1;
+        if (occ < 0 && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_chain<C, NB, NW, HT, POLY, XCH>, NW * 32, Cfg::kSmem) != cudaSuccess) occ = 0;
+        if (occ * sm_count < slots) slots = occ * sm_count;
+        if (2 * slots > a.xslots) slots = a.xslots / 2;
+        if (slots <= 0 || a.xbuf == nullptr || a.xflags == nullptr || a.xack == nullptr || a.t_n > 0 || a.T % Cfg::kRows != 0)
+            return cudaErrorInvalidValue;
+    }
     const int grid = tiles < slots ? tiles : slots;
-    k_chain<C, NB, NW, HT, FOLD><<<grid, NW * 32, Cfg::kSmem, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], tm[6], a, tiles);
+    if (a.prof != nullptr) {
+        int occ = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_chain<C, NB, NW, HT, POLY, XCH>, NW * 32, Cfg::kSmem);
+        cudaFuncAttributes fa;
+        cudaFuncGetAttributes(&fa, k_chain<C, NB, NW, HT, POLY, XCH>);
+        int occ_nosmem = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_nosmem, k_chain<C, NB, NW, HT, POLY, XCH>, NW * 32, 0);
+        fprintf(stderr, "k_chain<%d,%d,%d>: grid %d, smem %d (+%zu static), regs %d, occupancy %d CTA/SM (%d without smem)\n", C, NB, NW,
+                grid, Cfg::kSmem, fa.sharedSizeBytes, fa.numRegs, occ, occ_nosmem);
+    }
+    k_chain<C, NB, NW, HT, POLY, XCH><<<grid, NW * 32, Cfg::kSmem, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], tm[6], a, tiles);
     return cudaGetLastError();
 }
 
@@ -681,23 +756,26 @@ constexpr int kNB64 = 4, kNW64 = 8, kNB128 = 4, kNW128 = 16, kNB256 = 2, kNW256 
 }  // namespace
 
 bool chain_supported(int C, int half_fp16) { return C == 64 || C == 128 || (C == 256 && half_fp16); }
+bool chain_xch_supported(int C, int half_fp16) { return half_fp16 && (C == 64 || C == 128); }
+size_t chain_xch_slot_bytes(int C) { return static_cast<size_t>(3) * 2 * (C / 64) * kXRows * 128; }
 int chain_tile_rows(int C) { return (C == 64 ? kNB64 : (C == 128 ? kNB128 : kNB256)) * 128; }
 int chain_warps(int C) { return C == 64 ? kNW64 : (C == 128 ? kNW128 : kNW256); }
 
 // Spans of the in-place prologue (see the header comment): for dilation d the rows of a tile split into d classes
 // r = r0 + k d.  Class starts are multiples of 8 (so that the swizzle phase of step k is static) no larger than the
 // first row whose result is needed at that layer; negative starts skip their first few steps.
-void chain_build_spans(int C, ChainSpan (*spans)[kChainWarps][kChainSpans]) {
+void chain_build_spans(int C, ChainSpan (*spans)[kChainWarps][kChainSpans], bool xch) {
     const int rows = chain_tile_rows(C), ch = C / 64, nw = chain_warps(C);
     static const int dil[3] = {1, 3, 9};
     for (int l = 0; l < 3; ++l) {
         const int d = dil[l];
         struct Cls { int kc, r0, noct; };
         std::vector<Cls> cls;
-        const int top = (d == 1) ? 0 : (d == 3 ? 8 : 40);
+        // halo exchange: every row of the tile is owned, classes start at the first multiple of 8 at or below their first row
+        const int top = xch ? (d == 9 ? 8 : 0) : ((d == 1) ? 0 : (d == 3 ? 8 : 40));
         // rows at or beyond `hi` are not needed downstream: the last unit feeds only the stored rows (< rows - halo),
         // the unit before it additionally that unit's 27 rows of taps, the first one 9 more
-        const int hi = rows - kChainHalo + (l == 2 ? 0 : (l == 1 ? 27 : 36));
+        const int hi = xch ? rows : rows - kChainHalo + (l == 2 ? 0 : (l == 1 ? 27 : 36));
         for (int kc = 0; kc < ch; ++kc)
             for (int m = 0; m < d; ++m) {
                 const int r0 = top - 8 * m;
@@ -726,24 +804,26 @@ void chain_build_spans(int C, ChainSpan (*spans)[kChainWarps][kChainSpans]) {
 }
 
 // tm: [0] y load map, box (64, 128, 1); [1] out store map, box (64, 88, 1); [2] out store map, box (64, 128, 1);
-//     [3..6] noise 1x1, res d=1, d=3, d=9 weight maps, box (64, C); all 128B-swizzled.
-// fold: the alpha-folded fp16 formulation (the d=1, 3, 9 weight maps then carry 1 / alpha2 in their K columns)
-cudaError_t launch_chain(int half_fp16, int fold, const ChainArgs& a, const CUtensorMap* tm, int sm_count, cudaStream_t st) {
+//     [3..6] noise 1x1, res d=1, d=3, d=9 weight maps, box (64, C); all 128B-swizzled
+cudaError_t launch_chain(int half_fp16, const ChainArgs& a, const CUtensorMap* tm, int sm_count, cudaStream_t st) {
     if (half_fp16) {
-        if (fold) {
-            if (a.C == 64) return launch_chain_t<64, kNB64, kNW64, __half, true>(a, tm, sm_count, st);
-            if (a.C == 128) return launch_chain_t<128, kNB128, kNW128, __half, true>(a, tm, sm_count, st);
-            if (a.C == 256) return launch_chain_t<256, kNB256, kNW256, __half, true>(a, tm, sm_count, st);
+        if (a.xbuf != nullptr) {            // halo exchange between neighbouring tiles instead of a recomputed halo
+            if (a.C == 64) return launch_chain_t<64, kNB64, kNW64, __half, 0, true>(a, tm, sm_count, st);
+            if (a.C == 128) return launch_chain_t<128, kNB128, kNW128, __half, 0, true>(a, tm, sm_count, st);
             return cudaErrorInvalidValue;
         }
-        if (a.C == 64) return launch_chain_t<64, kNB64, kNW64, __half, false>(a, tm, sm_count, st);
-        if (a.C == 128) return launch_chain_t<128, kNB128, kNW128, __half, false>(a, tm, sm_count, st);
-        if (a.C == 256) return launch_chain_t<256, kNB256, kNW256, __half, false>(a, tm, sm_count, st);
+        // a.snake_poly: 0 = both Snakes through MUFU.SIN, 2 = snake2 as a half2 polynomial (see span_half)
+#define SNACB_CHAIN_POLY(P)                                                                                      \
+        if (a.C == 64) return launch_chain_t<64, kNB64, kNW64, __half, P>(a, tm, sm_count, st);                   \
+        if (a.C == 128) return launch_chain_t<128, kNB128, kNW128, __half, P>(a, tm, sm_count, st);               \
+        if (a.C == 256) return launch_chain_t<256, kNB256, kNW256, __half, P>(a, tm, sm_count, st);               \
         return cudaErrorInvalidValue;
+        if (a.snake_poly & 2) { SNACB_CHAIN_POLY(2) }
+        SNACB_CHAIN_POLY(0)
+#undef SNACB_CHAIN_POLY
     }
-    if (fold) return cudaErrorInvalidValue;
-    if (a.C == 64) return launch_chain_t<64, kNB64, kNW64, __nv_bfloat16, false>(a, tm, sm_count, st);
-    if (a.C == 128) return launch_chain_t<128, kNB128, kNW128, __nv_bfloat16, false>(a, tm, sm_count, st);
+    if (a.C == 64) return launch_chain_t<64, kNB64, kNW64, __nv_bfloat16>(a, tm, sm_count, st);
+    if (a.C == 128) return launch_chain_t<128, kNB128, kNW128, __nv_bfloat16>(a, tm, sm_count, st);
     return cudaErrorInvalidValue;
 }
 

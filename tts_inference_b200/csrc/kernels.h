@@ -7,9 +7,26 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace snacb {
+
+// cudaFuncSetAttribute (opt-in dynamic shared memory, carveout) is per DEVICE: a process may hold handles on several GPUs
+// and use them from several threads, so every launcher keeps one atomic bit per device instead of a process-wide flag.
+// Setting an attribute twice is harmless; what must not happen is skipping it on the second device.
+struct PerDeviceOnce {
+    std::atomic<unsigned long long> mask{0};
+    // true when the calling thread's current device has not been configured through this object yet
+    bool needed(int* dev_out) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { *dev_out = -1; return true; }
+        *dev_out = dev;
+        return (mask.load(std::memory_order_acquire) & (1ull << dev)) == 0;
+    }
+    void done(int dev) { if (dev >= 0) mask.fetch_or(1ull << dev, std::memory_order_release); }
+};
 
 struct VqStemWeights {
     const float* codebook[3];  // [4096][8]
@@ -62,19 +79,10 @@ cudaError_t launch_convt_ph(int half_fp16, const GemmArgs& a, const CUtensorMap&
 bool chain_supported(int C, int half_fp16);
 int chain_tile_rows(int C);           // rows of a tile incl. the halo (y tensor-map box = (64, 128, 1), 128B swizzle)
 int chain_warps(int C);               // warps per CTA of the launch configuration used for C channels
-void chain_build_spans(int C, ChainSpan (*spans)[kChainWarps][kChainSpans], bool xch = false);
-// halo exchange variant (fp16, C = 64 / 128, whole streams, T a multiple of the tile height): tiles carry no halo;
-// ChainArgs::xbuf (xslots * chain_xch_slot_bytes(C) bytes), xflags and xack (3 ints per tile each, zeroed) must be set
-bool chain_xch_supported(int C, int half_fp16);
-size_t chain_xch_slot_bytes(int C);
+void chain_build_spans(int C, ChainSpan (*spans)[kChainWarps][kChainSpans]);
 // tm[7]: y load map box (64,128,1); out store maps box (64,128-kChainHalo,1) and (64,128,1); noise 1x1, res d=1,
-// d=3, d=9 weight maps box (64, C); all 128B-swizzled
-cudaError_t launch_chain(int half_fp16, const ChainArgs& a, const CUtensorMap* tm, int sm_count, cudaStream_t st);
-
-// ---- kernels_chain2.cu  (the same chain with two warp groups half a layer apart; fp16 operands)
-bool chain2_supported(int C);
-int chain2_tile_rows(int C);
-void chain2_build_spans(int C, ChainSpan (*spans)[kChainWarps][kChainSpans]);   // ChainSpan::pad carries the span flags
-cudaError_t launch_chain2(const ChainArgs& a, const CUtensorMap* tm, int sm_count, cudaStream_t st);
+// d=3, d=9 weight maps box (64, C); all 128B-swizzled.  fold = 1: the alpha-folded fp16 formulation (the three res
+// weight maps then point at the copies with 1 / alpha2 folded into their K columns); see chain_fold_safe in snacb.cu
+cudaError_t launch_chain(int half_fp16, int fold, const ChainArgs& a, const CUtensorMap* tm, int sm_count, cudaStream_t st);
 
 }  // namespace snacb

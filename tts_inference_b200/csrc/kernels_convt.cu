@@ -353,11 +353,12 @@ template <int CIN, int COUT, int S, typename HT>
 cudaError_t launch_t(const GemmArgs& a, const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmO, int sm_count,
                      cudaStream_t st) {
     using Cfg = ConvtCfg<CIN, COUT, S>;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static PerDeviceOnce once;
+    int dev_;
+    if (once.needed(&dev_)) {
         cudaError_t e = cudaFuncSetAttribute(k_convt_res<CIN, COUT, S, HT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
         if (e != cudaSuccess) return e;
-        attr_done = true;
+        once.done(dev_);
     }
     const int t_n = a.t_n > 0 ? a.t_n : a.Tin;
     const int tiles = a.S * ((t_n + 127) / 128);
@@ -372,11 +373,12 @@ namespace {
 template <int CIN, int COUT, int S, typename HT>
 cudaError_t launch_ph_t(const GemmArgs& a, const CUtensorMap& tmA, const CUtensorMap& tmW, int sm_count, cudaStream_t st) {
     using Cfg = ConvtPhCfg<CIN, COUT, S>;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static PerDeviceOnce once;
+    int dev_;
+    if (once.needed(&dev_)) {
         cudaError_t e = cudaFuncSetAttribute(k_convt_ph<CIN, COUT, S, HT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
         if (e != cudaSuccess) return e;
-        attr_done = true;
+        once.done(dev_);
     }
     const int t_n = a.t_n > 0 ? a.t_n : a.Tin;
     const int tiles = a.S * ((t_n + 127) / 128);

@@ -239,6 +239,7 @@ int snacb_ingest_create(snacb_ingest* out, int device, int max_streams) {
 
 void snacb_ingest_destroy(snacb_ingest g) {
     if (!g) return;
+    cudaSetDevice(g->device);
     cudaFree(g->state); cudaFree(g->count); cudaFree(g->buf);
     delete g;
 }
@@ -246,6 +247,7 @@ void snacb_ingest_destroy(snacb_ingest g) {
 int snacb_ingest_reset(snacb_ingest g, int first, int n, void* stream) {
     if (!g || first < 0 || n < 0 || first + n > g->max_streams) return SNACB_ERR_ARG;
     if (n == 0) return SNACB_OK;
+    if (cudaSetDevice(g->device) != cudaSuccess) return SNACB_ERR_CUDA;     // the caller's current device may be another GPU
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (cudaMemsetAsync(g->state + first, 0, static_cast<size_t>(n) * 4, st) != cudaSuccess ||
         cudaMemsetAsync(g->count + first, 0, static_cast<size_t>(n) * 4, st) != cudaSuccess)
@@ -268,6 +270,7 @@ int snacb_ingest_step(snacb_ingest g, const int32_t* tok, int S, int n_tok, cons
     const int need = snacb_ingest_window_capacity(S, n_tok);
     if (need < 0 || win_cap < need) return SNACB_ERR_ARG;
     const IngestOut o{win_tok, win_stream, tail_tok, tail_stream, tail_frames, counts};
+    if (cudaSetDevice(g->device) != cudaSuccess) return SNACB_ERR_CUDA;
     k_ingest<<<1, kIngestThreads, 0, static_cast<cudaStream_t>(stream)>>>(tok, S, n_tok, n_valid, finish, g->state,
                                                                           g->count, g->buf, o);
     return cudaGetLastError() == cudaSuccess ? SNACB_OK : SNACB_ERR_CUDA;
@@ -275,11 +278,20 @@ int snacb_ingest_step(snacb_ingest g, const int32_t* tok, int S, int n_tok, cons
 
 int snacb_ingest_state(snacb_ingest g, int32_t* state_host, int32_t* count_host, int n) {
     if (!g || n < 0 || n > g->max_streams) return SNACB_ERR_ARG;
+    if (cudaSetDevice(g->device) != cudaSuccess) return SNACB_ERR_CUDA;
     if (state_host && cudaMemcpy(state_host, g->state, static_cast<size_t>(n) * 4, cudaMemcpyDeviceToHost) != cudaSuccess)
         return SNACB_ERR_CUDA;
     if (count_host && cudaMemcpy(count_host, g->count, static_cast<size_t>(n) * 4, cudaMemcpyDeviceToHost) != cudaSuccess)
         return SNACB_ERR_CUDA;
     return SNACB_OK;
+}
+
+// The egress calls take no handle: launch on the GPU that owns the PCM buffer, whatever the caller's current device is.
+static bool use_device_of(const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+    if (at.type != cudaMemoryTypeDevice && at.type != cudaMemoryTypeManaged) return false;
+    return cudaSetDevice(at.device) == cudaSuccess;
 }
 
 long long snacb_base64_len(long long bytes) { return bytes < 0 ? SNACB_ERR_ARG : 4 * ((bytes + 2) / 3); }
@@ -288,6 +300,7 @@ int snacb_pcm_to_base64(const int16_t* pcm, long long n_chunks, long long sample
     if (n_chunks < 0 || samples < 0 || ((n_chunks > 0 && samples > 0) && (!pcm || !out))) return SNACB_ERR_ARG;
     const long long groups = n_chunks * ((2 * samples + 2) / 3);
     if (groups == 0) return SNACB_OK;
+    if (!use_device_of(pcm)) return SNACB_ERR_ARG;                 // pcm must be a device pointer
     const long long want = (groups + 255) / 256;
     const int blocks = static_cast<int>(want < 148LL * 32 ? want : 148LL * 32);    // grid-stride beyond 32 CTAs per SM
     k_base64<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const uint8_t*>(pcm), n_chunks,
@@ -300,6 +313,7 @@ int snacb_pcm_to_wav(const int16_t* pcm, long long n, long long samples, int sam
     if (2 * samples + 36 > 0xffffffffLL) return SNACB_ERR_ARG;
     const long long total = n * (22 + samples);
     if (total == 0) return SNACB_OK;
+    if (!use_device_of(out)) return SNACB_ERR_ARG;                 // out must be a device pointer
     const long long want = (total + 255) / 256;
     const int blocks = static_cast<int>(want < 148LL * 32 ? want : 148LL * 32);
     k_wav<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(pcm, n, samples, static_cast<uint32_t>(sample_rate), out);

@@ -472,11 +472,12 @@ k_resunit2(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
 template <int C, int DIL, int EPI, typename HT>
 cudaError_t launch_t(const ResUnitArgs& a, const CUtensorMap& tmX, const CUtensorMap& tmW, int sm_count, cudaStream_t st) {
     using Cfg = Res2Cfg<C, DIL>;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static PerDeviceOnce once;
+    int dev_;
+    if (once.needed(&dev_)) {
         cudaError_t e = cudaFuncSetAttribute(k_resunit2<C, DIL, EPI, HT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
         if (e != cudaSuccess) return e;
-        attr_done = true;
+        once.done(dev_);
     }
     const int tiles = a.S * (((a.t_n > 0 ? a.t_n : a.T) + Cfg::kTileM - 1) / Cfg::kTileM);
     if (tiles == 0) return cudaSuccess;

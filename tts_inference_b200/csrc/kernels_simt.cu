@@ -436,14 +436,19 @@ void launch_tail(const InT* a, int S, int T, int t_begin, int n_out, const float
         const long long tiles = static_cast<long long>(S) * tps;
         const char* v1 = getenv("SNACB_TAIL_V1");          // A/B switch (tests): the per-warp-load kernel for every size
         if (tiles >= 2 * 148 && tiles < (1LL << 31) && !(v1 && v1[0] == '1')) {
-            static bool attr_done = false;
-            if (!attr_done) {
-                cudaFuncSetAttribute(k_tail_bulk<InT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTailSmem);
-                attr_done = true;
+            static PerDeviceOnce once;
+            int dev;
+            bool ok = true;
+            if (once.needed(&dev)) {
+                ok = cudaFuncSetAttribute(k_tail_bulk<InT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTailSmem) == cudaSuccess;
+                if (ok) once.done(dev);
             }
-            k_tail_bulk<InT><<<2 * 148, 256, kTailSmem, st>>>(a, T, t_begin, n_out, w, bias, pcm, wave, tps,
-                                                               static_cast<int>(tiles));
-            return;
+            if (ok) {
+                k_tail_bulk<InT><<<2 * 148, 256, kTailSmem, st>>>(a, T, t_begin, n_out, w, bias, pcm, wave, tps,
+                                                                   static_cast<int>(tiles));
+                return;
+            }
+            (void)cudaGetLastError();       // the opt-in failed: fall through to the kernel that needs no dynamic shared memory
         }
     }
     dim3 grid((n_out + 255) / 256, S);

@@ -209,12 +209,13 @@ template <int BN, int EPI, typename HT, typename OutT>
 static cudaError_t launch_gemm_tc_t(const GemmArgs& a, const CUtensorMap& tmA, const CUtensorMap& tmW, int sm_count,
                                     cudaStream_t st) {
     using Cfg = GemmTcCfg<BN>;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static PerDeviceOnce once;
+    int dev_;
+    if (once.needed(&dev_)) {
         cudaError_t e = cudaFuncSetAttribute(k_gemm_tc<BN, EPI, HT, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              Cfg::kSmem);
         if (e != cudaSuccess) return e;
-        attr_done = true;
+        once.done(dev_);
     }
     const int tiles_t = ((a.t_n > 0 ? a.t_n : a.Tin) + a.Tbox - 1) / a.Tbox;
     const int num_m = ((a.S + a.Wbox - 1) / a.Wbox) * tiles_t;
@@ -460,13 +461,14 @@ k_resunit_tc(const __grid_constant__ CUtensorMap tmW, const ResUnitArgs a) {
 template <int C, int EPI, typename HT, typename XT, typename OutT>
 static cudaError_t launch_resunit_tc_t(const ResUnitArgs& a, const CUtensorMap& tmW, cudaStream_t st) {
     using Cfg = ResTcCfg<C>;
-    static int attr_smem = 0;
+    static PerDeviceOnce once;
     const int smem = Cfg::smem_bytes(a.dil);
-    if (smem > attr_smem) {
+    int dev_;
+    if (once.needed(&dev_)) {
         cudaError_t e = cudaFuncSetAttribute(k_resunit_tc<C, EPI, HT, XT, OutT>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::smem_bytes(9));
         if (e != cudaSuccess) return e;
-        attr_smem = Cfg::smem_bytes(9);
+        once.done(dev_);
     }
     const int tiles = a.S * ((a.T + kTileM - 1) / kTileM);
     if (tiles == 0) return cudaSuccess;

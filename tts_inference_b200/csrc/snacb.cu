@@ -1,5 +1,6 @@
 // Host side of libsnacb: handle, weight packing, workspace, the per-group kernel pipeline and the
 // C ABI declared in include/snacb.h.
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -22,6 +23,7 @@ using namespace snacb;
 
 namespace {
 
+constexpr size_t kMaxActMaps = 4096;
 typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                         const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                         CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -46,10 +48,8 @@ struct BlockW {
     float* bias_cum;                    // [3][Cout] running sums of the ResidualUnit 1x1 biases (fused chain)
     bool chain[2];                      // the fused NoiseBlock + ResidualUnit chain covers this block ([0] bf16, [1] fp16)
     ChainSpan spans[3][kChainWarps][kChainSpans];
-    bool chain2;                        // fp16 only: the two-group chain kernel (kernels_chain2.cu) covers this block
-    ChainSpan spans2[3][kChainWarps][kChainSpans];
-    ChainSpan spans_x[3][kChainWarps][kChainSpans];   // halo-exchange variant of the chain kernel (no halo rows)
-    bool chain_x = false;
+    bool fold = false;                  // fp16 chain: the alpha-folded formulation is numerically safe for this block's
+                                        // Snake alphas (chain_fold_safe); otherwise the general fp32-Snake variant runs
 };
 struct Tap {
     std::string name;
@@ -81,6 +81,7 @@ struct snacb_handle_s {
     float tail_b = 0.f;
     std::map<std::pair<const void*, int>, CUtensorMap> wmaps;   // (weight ptr, box rows) -> map
     std::map<TmapKey, CUtensorMap> amaps;
+    size_t max_act_maps = kMaxActMaps;  // SNACB_TMAP_CACHE=n shrinks the cache (tests: eviction inside a launch sequence)
 
     // workspace
     size_t group_bytes = static_cast<size_t>(1) << 30;   // per activation buffer; launches are per group
@@ -101,13 +102,8 @@ struct snacb_handle_s {
     std::vector<Tap> taps;
     uint64_t launches = 0, streams = 0;
     bool res_v1 = false;                // SNACB_RES_V1=1: use the non-persistent ResidualUnit kernel
-    bool no_chain2 = true;              // SNACB_CHAIN2=1 opts into the two-group chain kernel (kernels_chain2.cu): bit-identical
-                                        // output, measured 5 % (C = 128) / 40 % (C = 64) slower than k_chain
-    bool no_xch = true;                 // SNACB_XCH=1 opts into the halo-exchange chain tiles (kernels_chain.cu, XCH): bit-identical
-                                        // output, measured slower than recomputing the halo
-    unsigned char* xbuf = nullptr; size_t xbuf_bytes = 0;     // halo exchange buffer and its flags (chain kernel, XCH)
-    int* xflags = nullptr; size_t xflags_bytes = 0;
-    int snake_poly = 0;                 // SNACB_SNAKE_POLY: fp16 chain prologue, bit 0 / 1 = snake1 / snake2 as a half2 polynomial
+    bool no_fold = false;               // SNACB_NO_FOLD=1: general (fp32 Snake) chain variant even where the folded one is safe (A/B)
+    int chain_prof = 0;                 // SNACB_CHAIN_PROF=1|2: in-kernel clock64 phase timing of k_chain, printed per launch (debug)
     bool no_chain = false;              // SNACB_NO_CHAIN=1: per-layer kernels instead of the fused chain
     bool no_convt_res = false;          // SNACB_NO_CONVT_RES=1: generic k_gemm_tc for every ConvTranspose
     bool no_trim = false;               // SNACB_NO_TRIM=1: sliced output still decodes every sample of the window
@@ -250,18 +246,21 @@ int weight_map(snacb_handle h, const CUtensorMap** out, const void* w, int rows,
     *out = &it->second;
     return 0;
 }
-int act_map(snacb_handle h, const CUtensorMap** out, const void* base, int C, int T, int S, int tbox, int wbox,
+// Activation tensor maps are cached per (buffer, shape, box).  The map is returned BY VALUE: a launch sequence holds
+// several maps at once, and a cache that handed out pointers would leave them dangling whenever an insertion evicts
+// (the cache is bounded; a serving process with variable batch sizes / ranges sees thousands of distinct shapes).
+int act_map(snacb_handle h, CUtensorMap* out, const void* base, int C, int T, int S, int tbox, int wbox,
             int fp16, int swizzle = 1) {
     TmapKey key{base, C, T, S, tbox, wbox, fp16, swizzle};
     auto it = h->amaps.find(key);
     if (it == h->amaps.end()) {
-        if (h->amaps.size() > 4096) h->amaps.clear();
+        if (h->amaps.size() >= h->max_act_maps) h->amaps.clear();
         CUtensorMap m;
         int rc = make_tmap_3d(h, &m, base, C, T, S, tbox, wbox, fp16, swizzle);
         if (rc) return rc;
         it = h->amaps.emplace(key, m).first;
     }
-    *out = &it->second;
+    *out = it->second;
     return 0;
 }
 
@@ -290,6 +289,59 @@ int add_tap(snacb_handle h, const char* name, const T* src, int64_t rows, int64_
 void clear_taps(snacb_handle h) {
     for (auto& t : h->taps) cudaFree(t.dev);
     h->taps.clear();
+}
+
+// The fp16 chain kernel's alpha-folded formulation forms dw_w * alpha2 / alpha1, dw_b * alpha2 and pw_w / alpha2 in
+// half precision (kernels_chain.cu).  Trained Snake alphas may be ~0, negative or large; the fold is used only when every
+// alpha of the block's three ResidualUnits lies in [2^-8, 2^6] in magnitude and every folded parameter stays well inside
+// the fp16 range.  Otherwise the block runs the general variant, x + (alpha + 1e-9)^-1 sin^2(alpha x) in fp32, which for
+// alpha = 0 returns x exactly as the reference does (snac layers.py snake()).
+bool chain_fold_safe(const snacb_block_weights& s, int C) {
+    constexpr float kLo = 1.0f / 256.0f, kHi = 64.0f, kMaxH = 3.0e4f;
+    for (int ri = 0; ri < 3; ++ri) {
+        const snacb_resunit_weights& r = s.res[ri];
+        for (int c = 0; c < C; ++c) {
+            const float a1 = r.alpha1[c], a2 = r.alpha2[c];
+            if (!(fabsf(a1) >= kLo && fabsf(a1) <= kHi && fabsf(a2) >= kLo && fabsf(a2) <= kHi)) return false;   // also NaN
+            if (!(fabsf(r.dw_b[c] * a2) <= kMaxH)) return false;
+            for (int j = 0; j < 7; ++j)
+                if (!(fabsf(r.dw_w[static_cast<size_t>(c) * 7 + j] * (a2 / a1)) <= kMaxH)) return false;
+            for (int n = 0; n < C; ++n)
+                if (!(fabsf(r.pw_w[static_cast<size_t>(n) * C + c] / a2) <= kMaxH)) return false;
+        }
+    }
+    return true;
+}
+
+// SNACB_CHAIN_PROF (debug): per-phase clock64 sums of CTA 0 / thread 0 and per-CTA lifetimes of one k_chain launch
+int chain_prof_begin(snacb_handle h, ChainArgs* ca, cudaStream_t st) {
+    CK(h, cudaMalloc(reinterpret_cast<void**>(&ca->prof), 1024 * sizeof(unsigned long long)));
+    CK(h, cudaMemsetAsync(ca->prof, 0, 1024 * sizeof(unsigned long long), st));
+    return 0;
+}
+int chain_prof_report(snacb_handle h, const ChainArgs& ca, int bi, cudaStream_t st) {
+    unsigned long long pv[1024];
+    CK(h, cudaStreamSynchronize(st));
+    CK(h, cudaMemcpy(pv, ca.prof, sizeof pv, cudaMemcpyDeviceToHost));
+    CK(h, cudaFree(ca.prof));
+    const int rows = chain_tile_rows(ca.C) - 2 * kChainHalo;
+    const int tiles = ca.S * (((ca.t_n > 0 ? ca.t_n : ca.T) + rows - 1) / rows);
+    const int slots = h->sm_count * (chain_warps(ca.C) == 8 ? 2 : 1);
+    const int mine = (tiles + slots - 1) / slots;
+    fprintf(stderr, "chain b%d C=%d: CTA0 cycles per tile (~%d tiles per CTA): nz+ld %llu noise %llu |", bi, ca.C, mine,
+            pv[0] / mine, pv[1] / mine);
+    for (int l = 0; l < 3; ++l)
+        fprintf(stderr, " L%d: pre %llu pro %llu sync %llu mma+epi %llu |", l, pv[2 + 4 * l] / mine, pv[3 + 4 * l] / mine,
+                pv[4 + 4 * l] / mine, pv[5 + 4 * l] / mine);
+    fprintf(stderr, " store/load issue %llu\n", pv[14] / mine);
+    const int grid = tiles < slots ? tiles : slots;
+    unsigned long long mn = ~0ull, mx = 0, sum = 0;
+    for (int c = 0; c < grid && c < 500; ++c) {
+        const unsigned long long v = pv[20 + 2 * c];
+        mn = v < mn ? v : mn; mx = v > mx ? v : mx; sum += v;
+    }
+    fprintf(stderr, "   CTA lifetimes (cycles): min %llu avg %llu max %llu\n", mn, sum / (grid < 500 ? grid : 500), mx);
+    return 0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -350,8 +402,7 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
             Rng y;                                                  // ConvTranspose output rows that must be valid
             const bool unfused = (flags & SNACB_UNFUSED) != 0 || h->no_chain;
             if (b.chain[hk] && !unfused) {
-                const bool two = hk && b.chain2 && !h->no_chain2;
-                const int rows = (two ? chain2_tile_rows(b.Cout) : chain_tile_rows(b.Cout)) - 2 * kChainHalo;
+                const int rows = chain_tile_rows(b.Cout) - 2 * kChainHalo;
                 const int n = (need.hi - need.lo + rows - 1) / rows;
                 post[bi] = Rng{need.lo, need.lo + n * rows};
                 y = clip(Rng{post[bi].lo - kChainHalo, post[bi].hi + kChainHalo}, Tb[bi]);
@@ -403,13 +454,14 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
             CK(h, cudaGetLastError());
             return 0;
         }
-        const CUtensorMap *ma, *mw;
+        CUtensorMap ma;
+        const CUtensorMap* mw;
         int rc = act_map(h, &ma, A, a.K, a.Tin, a.S, a.Tbox, a.Wbox, hk);
         if (rc) return rc;
         rc = weight_map(h, &mw, Wh[hk], Wrows, Wcols, gemm_tc_block_n(a), hk);
         if (rc) return rc;
         prof_begin(h, pname, st);
-        cudaError_t le = launch_gemm_tc(epi, hk, out_f32 ? 1 : 0, a, *ma, *mw, h->sm_count, st);
+        cudaError_t le = launch_gemm_tc(epi, hk, out_f32 ? 1 : 0, a, ma, *mw, h->sm_count, st);
         prof_end(h, st);
         CK(h, le);
         return 0;
@@ -443,7 +495,8 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
             int rc = 0;
             if (!f32 && !h->no_convt_res && convt_res_supported(b.Cin, b.Cout, b.s) && Tin >= 128) {
                 // weights resident in smem, one activation load per tile, row-shifted descriptors per tap
-                const CUtensorMap *ma, *mw, *mo;
+                CUtensorMap ma, mo;
+                const CUtensorMap* mw;
                 rc = act_map(h, &ma, cur, b.Cin, Tin, S, convt_res_box_rows(), 1, hk);
                 if (rc) return rc;
                 rc = weight_map(h, &mw, b.ct_h[hk], b.s * b.Cout, 2 * b.Cin, b.s * b.Cout, hk);
@@ -452,20 +505,21 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
                 if (rc) return rc;
                 a.seed = seed; a.stream_offset = stream_offset; a.stream_keys = stream_keys; a.Tbox = 128; a.Wbox = 1;
                 prof_begin(h, nm, st);
-                cudaError_t le = launch_convt_res(hk, a, *ma, *mw, *mo, h->sm_count, st);
+                cudaError_t le = launch_convt_res(hk, a, ma, *mw, mo, h->sm_count, st);
                 prof_end(h, st);
                 CK(h, le);
                 h->launches++;
             } else if (!f32 && !h->no_convt_res && convt_ph_supported(b.Cin, b.Cout, b.s) && Tin >= 128) {
                 // one output phase's weights resident per CTA group, one activation load per tile
-                const CUtensorMap *ma, *mw;
+                CUtensorMap ma;
+                const CUtensorMap* mw;
                 rc = act_map(h, &ma, cur, b.Cin, Tin, S, convt_res_box_rows(), 1, hk);
                 if (rc) return rc;
                 rc = weight_map(h, &mw, b.ct_h[hk], b.s * b.Cout, 2 * b.Cin, b.Cout, hk);
                 if (rc) return rc;
                 a.seed = seed; a.stream_offset = stream_offset; a.stream_keys = stream_keys; a.Tbox = 128; a.Wbox = 1;
                 prof_begin(h, nm, st);
-                cudaError_t le = launch_convt_ph(hk, a, *ma, *mw, h->sm_count, st);
+                cudaError_t le = launch_convt_ph(hk, a, ma, *mw, h->sm_count, st);
                 prof_end(h, st);
                 CK(h, le);
                 h->launches++;
@@ -490,27 +544,12 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
             ca.alpha_next = bi < 3 ? h->blk[bi + 1].alpha : h->tail_alpha;
             ca.inv_next = bi < 3 ? h->blk[bi + 1].inv_alpha : h->tail_inv;
             ca.noise = noise ? noise[bi] : nullptr; ca.seed = seed; ca.noise_stage = bi; ca.stream_offset = stream_offset; ca.stream_keys = stream_keys;
-            const bool two = hk && b.chain2 && !h->no_chain2;
-            static const bool chain_prof_x = getenv("SNACB_CHAIN_PROF") && atoi(getenv("SNACB_CHAIN_PROF")) != 0;
-            // whole streams, fp16: neighbouring tiles exchange their boundary rows instead of recomputing a halo
-            const int xrows = chain_tile_rows(b.Cout);
-            const bool xch = hk && b.chain_x && !two && !h->no_xch && !trimmed[bi] && !chain_prof_x && h->snake_poly == 0 &&
-                             T % xrows == 0;
-            if (xch) {
-                const int slots = 2 * 2 * h->sm_count;                 // >= 2 x the largest grid (two CTAs per SM)
-                const size_t tiles = static_cast<size_t>(S) * (T / xrows);
-                int rc = grow(h, reinterpret_cast<void**>(&h->xbuf), &h->xbuf_bytes, slots * chain_xch_slot_bytes(b.Cout));
-                if (rc) return rc;
-                rc = grow(h, reinterpret_cast<void**>(&h->xflags), &h->xflags_bytes, tiles * 6 * sizeof(int));
-                if (rc) return rc;
-                CK(h, cudaMemsetAsync(h->xflags, 0, tiles * 6 * sizeof(int), st));
-                ca.xbuf = h->xbuf; ca.xflags = h->xflags; ca.xack = h->xflags + tiles * 3; ca.xslots = slots;
-            }
-            memcpy(ca.spans, two ? b.spans2 : (xch ? b.spans_x : b.spans), sizeof ca.spans);
+            memcpy(ca.spans, b.spans, sizeof ca.spans);
             ca.tile_counter = h->tile_counter;
-            ca.snake_poly = h->snake_poly;
             CK(h, cudaMemsetAsync(h->tile_counter, 0, sizeof(int), st));
-            const CUtensorMap *my, *moe, *mom, *mn;
+            const bool fold = hk && b.fold && !h->no_fold;
+            CUtensorMap my, moe, mom;
+            const CUtensorMap* mn;
             int rc = act_map(h, &my, oth, b.Cout, T, S, 128, 1, hk, 1);
             if (rc) return rc;
             rc = act_map(h, &moe, cur, b.Cout, T, S, 128 - kChainHalo, 1, hk, 1);
@@ -519,71 +558,15 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
             if (rc) return rc;
             rc = weight_map(h, &mn, b.nz_h[hk], b.Cout, b.Cout, b.Cout, hk);
             if (rc) return rc;
-            const CUtensorMap tm[7] = {*my, *moe, *mom, *mn, hk ? b.res[0].tm_pwc : b.res[0].tm_pw[0],
-                                       hk ? b.res[1].tm_pwc : b.res[1].tm_pw[0], hk ? b.res[2].tm_pwc : b.res[2].tm_pw[0]};
+            const CUtensorMap tm[7] = {my, moe, mom, *mn, fold ? b.res[0].tm_pwc : b.res[0].tm_pw[hk],
+                                       fold ? b.res[1].tm_pwc : b.res[1].tm_pw[hk], fold ? b.res[2].tm_pwc : b.res[2].tm_pw[hk]};
             snprintf(nm, sizeof nm, "b%d.chain", bi);
             prof_begin(h, nm, st);
-            static const bool chain_prof = getenv("SNACB_CHAIN_PROF") && atoi(getenv("SNACB_CHAIN_PROF")) != 0;
-            if (chain_prof) {
-                CK(h, cudaMalloc(reinterpret_cast<void**>(&ca.prof), 1024 * sizeof(unsigned long long)));
-                CK(h, cudaMemsetAsync(ca.prof, 0, 1024 * sizeof(unsigned long long), st));
-            }
-            cudaError_t le = two ? launch_chain2(ca, tm, h->sm_count, st) : launch_chain(hk, ca, tm, h->sm_count, st);
+            if (h->chain_prof) { rc = chain_prof_begin(h, &ca, st); if (rc) return rc; }
+            cudaError_t le = launch_chain(hk, fold ? 1 : 0, ca, tm, h->sm_count, st);
             prof_end(h, st);
             CK(h, le);
-            if (chain_prof && two) {
-                unsigned long long pv[64];
-                CK(h, cudaStreamSynchronize(st));
-                CK(h, cudaMemcpy(pv, ca.prof, sizeof pv, cudaMemcpyDeviceToHost));
-                CK(h, cudaFree(ca.prof));
-                const int rows = chain2_tile_rows(b.Cout) - 2 * kChainHalo;
-                const int tiles = S * (((ca.t_n > 0 ? ca.t_n : T) + rows - 1) / rows);
-                const int mine = (tiles + h->sm_count - 1) / h->sm_count;
-                for (int g = 0; g < 2; ++g) {
-                    const unsigned long long* q = pv + 32 * g;
-                    fprintf(stderr, "chain2 b%d C=%d group %d: cycles per tile (~%d tiles): nz+ld %llu noise %llu |", bi, b.Cout, g, mine,
-                            q[0] / mine, q[1] / mine);
-                    for (int l = 0; l < 3; ++l)
-                        fprintf(stderr, " L%d: pre %llu tok %llu pro %llu sync %llu mma+epi %llu |", l, q[2 + 5 * l] / mine,
-                                q[3 + 5 * l] / mine, q[4 + 5 * l] / mine, q[5 + 5 * l] / mine, q[6 + 5 * l] / mine);
-                    fprintf(stderr, " store/load issue %llu\n", q[17] / mine);
-                }
-            }
-            if (chain_prof && !two) {
-                unsigned long long pv[1024];
-                CK(h, cudaStreamSynchronize(st));
-                CK(h, cudaMemcpy(pv, ca.prof, sizeof pv, cudaMemcpyDeviceToHost));
-                CK(h, cudaFree(ca.prof));
-                const int rows = chain_tile_rows(b.Cout) - 2 * kChainHalo;
-                const int tiles = S * ((T + rows - 1) / rows);
-                const int slots = h->sm_count * (chain_warps(b.Cout) == 8 ? 2 : 1);
-                const int mine = (tiles + slots - 1) / slots;
-                fprintf(stderr, "chain b%d C=%d: CTA0 cycles per tile (%d tiles): nz+ld %llu noise %llu |", bi, b.Cout, mine,
-                        pv[0] / mine, pv[1] / mine);
-                for (int l = 0; l < 3; ++l)
-                    fprintf(stderr, " L%d: pre %llu pro %llu sync %llu mma+epi %llu |", l, pv[2 + 4 * l] / mine,
-                            pv[3 + 4 * l] / mine, pv[4 + 4 * l] / mine, pv[5 + 4 * l] / mine);
-                fprintf(stderr, " store/load issue %llu\n", pv[14] / mine);
-                {
-                    const int grid = tiles < slots ? tiles : slots;
-                    unsigned long long mn = ~0ull, mx = 0, sum = 0;
-                    int per_sm[256] = {0};
-                    for (int c = 0; c < grid && c < 500; ++c) {
-                        const unsigned long long v = pv[20 + 2 * c];
-                        mn = v < mn ? v : mn; mx = v > mx ? v : mx; sum += v;
-                        per_sm[pv[21 + 2 * c] & 255]++;
-                    }
-                    int sm1 = 0, sm2 = 0, sm3 = 0;
-                    for (int i = 0; i < 256; ++i) { sm1 += per_sm[i] == 1; sm2 += per_sm[i] == 2; sm3 += per_sm[i] > 2; }
-                    if (getenv("SNACB_CHAIN_PROF") && atoi(getenv("SNACB_CHAIN_PROF")) > 1) {
-                        for (int c = 0; c < grid && c < 500; ++c)
-                            fprintf(stderr, "%d:%llu:%llu ", c, pv[21 + 2 * c], pv[20 + 2 * c] / 1000);
-                        fprintf(stderr, "\n");
-                    }
-                    fprintf(stderr, "   CTA lifetimes (cycles): min %llu avg %llu max %llu; SMs with 1/2/>2 CTAs: %d/%d/%d\n", mn,
-                            sum / (grid < 500 ? grid : 500), mx, sm1, sm2, sm3);
-                }
-            }
+            if (h->chain_prof) { rc = chain_prof_report(h, ca, bi, st); if (rc) return rc; }
             h->launches++;
             snprintf(nm, sizeof nm, "b%d.res2", bi);
             rc = tap_any(nm, cur, dt_h, (int64_t)S * T, b.Cout);
@@ -633,28 +616,13 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
             } else if (!xf32 && !h->res_v1) {
                 int tile_m, box_rows;
                 resunit2_geometry(ra.C, ra.dil, &tile_m, &box_rows);
-                const CUtensorMap* mx;
+                CUtensorMap mx;
                 int rc2 = act_map(h, &mx, cur, ra.C, T, S, box_rows, 1, hk, 0);
                 if (rc2) return rc2;
-                static const bool res_prof = getenv("SNACB_RES_PROF") && atoi(getenv("SNACB_RES_PROF")) != 0;
-                if (res_prof) {
-                    CK(h, cudaMalloc(reinterpret_cast<void**>(&ra.prof), 16 * sizeof(unsigned long long)));
-                    CK(h, cudaMemsetAsync(ra.prof, 0, 16 * sizeof(unsigned long long), st));
-                }
-                cudaError_t le = launch_resunit2(hk, ra, *mx, r.tm_pw[hk], h->sm_count, st);
+                cudaError_t le = launch_resunit2(hk, ra, mx, r.tm_pw[hk], h->sm_count, st);
                 prof_end(h, st);
                 CK(h, le);
                 h->launches++;
-                if (res_prof) {
-                    unsigned long long pv[16];
-                    CK(h, cudaStreamSynchronize(st));
-                    CK(h, cudaMemcpy(pv, ra.prof, sizeof pv, cudaMemcpyDeviceToHost));
-                    CK(h, cudaFree(ra.prof));
-                    const unsigned long long nt = pv[7] ? pv[7] : 1;
-                    fprintf(stderr, "resunit2 b%d d=%d C=%d: CTA0 cycles per tile (%llu tiles): MMA warp waits a_full %llu w_full %llu acc_empty %llu | "
-                            "warp0 waits x_full %llu a_empty %llu, prologue %llu, epilogue %llu\n", bi, ra.dil, ra.C, nt, pv[0] / nt, pv[1] / nt,
-                            pv[2] / nt, pv[3] / nt, pv[4] / nt, pv[5] / nt, pv[6] / nt);
-                }
             } else {
                 cudaError_t le = launch_resunit_tc(last ? EPI_RES_SNAKE : EPI_RES, hk, xf32 ? 1 : 0, ra, r.tm_pw[hk], st);
                 prof_end(h, st);
@@ -786,12 +754,11 @@ int snacb_create(snacb_handle* out, const snacb_weights* w, int device) {
             RC(upload_f32(h, &b.bias_cum, bc));
             b.chain[0] = chain_supported(b.Cout, 0);
             b.chain[1] = chain_supported(b.Cout, 1);
-            b.chain2 = b.chain[1] && chain2_supported(b.Cout);
-            if (b.chain2) chain2_build_spans(b.Cout, b.spans2);
-            if (b.chain[1]) {
-                chain_build_spans(b.Cout, b.spans);
-                b.chain_x = chain_xch_supported(b.Cout, 1);
-                if (b.chain_x) chain_build_spans(b.Cout, b.spans_x, true);
+            if (b.chain[0] || b.chain[1]) chain_build_spans(b.Cout, b.spans);
+            // fp16 chain: the alpha-folded formulation (kernels_chain.cu) divides by the Snake alphas when it packs its
+            // parameters; it is used only where that is numerically safe for THIS checkpoint, else the general variant runs
+            b.fold = b.chain[1] && chain_fold_safe(s, b.Cout);
+            if (b.fold) {
                 const int C = b.Cout;
                 for (int ri = 0; ri < 3; ++ri) {
                     // snake2(a) = (a'' + sin^2 a'') / alpha2 with a'' = alpha2 a: the 1 / alpha2 goes into W's K columns
@@ -821,9 +788,9 @@ int snacb_create(snacb_handle* out, const snacb_weights* w, int device) {
     }
     if (const char* e = getenv("SNACB_RES_V1")) h->res_v1 = atoi(e) != 0;
     if (const char* e = getenv("SNACB_NO_CHAIN")) h->no_chain = atoi(e) != 0;
-    if (const char* e = getenv("SNACB_SNAKE_POLY")) h->snake_poly = atoi(e) & 3;
-    if (const char* e = getenv("SNACB_XCH")) h->no_xch = atoi(e) == 0;
-    if (const char* e = getenv("SNACB_CHAIN2")) h->no_chain2 = atoi(e) == 0;
+    if (const char* e = getenv("SNACB_NO_FOLD")) h->no_fold = atoi(e) != 0;
+    if (const char* e = getenv("SNACB_TMAP_CACHE")) { const long n = atol(e); if (n >= 1) h->max_act_maps = static_cast<size_t>(n); }
+    if (const char* e = getenv("SNACB_CHAIN_PROF")) h->chain_prof = atoi(e);
     if (const char* e = getenv("SNACB_NO_TRIM")) h->no_trim = atoi(e) != 0;
     if (const char* e = getenv("SNACB_NO_CONVT_RES")) h->no_convt_res = atoi(e) != 0;
     if (const char* e = getenv("SNACB_GROUP_MB")) {
@@ -849,8 +816,6 @@ void snacb_destroy(snacb_handle h) {
     if (h->ws_codes) cudaFree(h->ws_codes);
     if (h->st_tok) cudaFree(h->st_tok);
     if (h->st_pcm) cudaFree(h->st_pcm);
-    if (h->xbuf) cudaFree(h->xbuf);
-    if (h->xflags) cudaFree(h->xflags);
     for (int i = 0; i < 2; ++i) {
         if (h->pl_tok[i]) cudaFree(h->pl_tok[i]);
         if (h->pl_pcm[i]) cudaFree(h->pl_pcm[i]);
@@ -872,6 +837,15 @@ int snacb_stats(snacb_handle h, uint64_t* kernel_launches, uint64_t* streams_dec
     if (!h) return SNACB_ERR_ARG;
     if (kernel_launches) *kernel_launches = h->launches;
     if (streams_decoded) *streams_decoded = h->streams;
+    return SNACB_OK;
+}
+
+int snacb_chain_modes(snacb_handle h, int32_t* modes) {
+    if (!h || !modes) return SNACB_ERR_ARG;
+    for (int bi = 0; bi < 4; ++bi) {
+        const BlockW& b = h->blk[bi];
+        modes[bi] = !b.chain[1] ? 0 : ((b.fold && !h->no_fold) ? 2 : 1);
+    }
     return SNACB_OK;
 }
 
@@ -1066,32 +1040,6 @@ int snacb_debug_chain_spans(int C, int16_t* out, int cap) {
                 o[0] = sp[l][w][k].r_first; o[1] = sp[l][w][k].n_oct; o[2] = sp[l][w][k].kc;
             }
     return chain_tile_rows(C) | (chain_warps(C) << 16);
-}
-
-int snacb_debug_chain_spans_x(int C, int16_t* out, int cap) {
-    if (!out || !chain_xch_supported(C, 1) || cap < 3 * kChainWarps * kChainSpans * 3) return SNACB_ERR_ARG;
-    ChainSpan sp[3][kChainWarps][kChainSpans];
-    chain_build_spans(C, sp, true);
-    for (int l = 0; l < 3; ++l)
-        for (int w = 0; w < kChainWarps; ++w)
-            for (int k = 0; k < kChainSpans; ++k) {
-                int16_t* o = out + ((l * kChainWarps + w) * kChainSpans + k) * 3;
-                o[0] = sp[l][w][k].r_first; o[1] = sp[l][w][k].n_oct; o[2] = sp[l][w][k].kc;
-            }
-    return chain_tile_rows(C) | (chain_warps(C) << 16);
-}
-
-int snacb_debug_chain2_spans(int C, int16_t* out, int cap) {
-    if (!out || !chain2_supported(C) || cap < 3 * kChainWarps * kChainSpans * 4) return SNACB_ERR_ARG;
-    ChainSpan sp[3][kChainWarps][kChainSpans];
-    chain2_build_spans(C, sp);
-    for (int l = 0; l < 3; ++l)
-        for (int w = 0; w < kChainWarps; ++w)
-            for (int k = 0; k < kChainSpans; ++k) {
-                int16_t* o = out + ((l * kChainWarps + w) * kChainSpans + k) * 4;
-                o[0] = sp[l][w][k].r_first; o[1] = sp[l][w][k].n_oct; o[2] = sp[l][w][k].kc; o[3] = sp[l][w][k].pad;
-            }
-    return chain2_tile_rows(C);
 }
 
 int snacb_debug_tap_count(snacb_handle h) { return h ? static_cast<int>(h->taps.size()) : SNACB_ERR_ARG; }

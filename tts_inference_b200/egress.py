@@ -17,7 +17,7 @@ def _prep(pcm):
         raise ValueError("pcm must be an int16 CUDA tensor [n, samples]")
     if pcm.dim() == 1:
         pcm = pcm.unsqueeze(0)
-    return pcm.contiguous(), C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return pcm.contiguous(), C.c_void_p(torch.cuda.current_stream(pcm.device).cuda_stream)
 
 
 def pcm_to_base64(pcm, out=None):

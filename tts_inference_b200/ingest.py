@@ -76,7 +76,7 @@ class DeviceIngest:
             if not finish.is_cuda or finish.dtype not in (torch.uint8, torch.bool) or finish.numel() != S:
                 raise ValueError("finish must be a uint8 / bool CUDA tensor [S]")
             fp = finish.contiguous().data_ptr()
-        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        st = C.c_void_p(torch.cuda.current_stream(tokens.device).cuda_stream)
         rc = self._lib.snacb_ingest_step(self._g, tokens.data_ptr(), S, n, nv, fp, self._win_tok.data_ptr(),
                                          self._win_stream.data_ptr(), self._win_tok.shape[0], self._tail_tok.data_ptr(),
                                          self._tail_stream.data_ptr(), self._tail_frames.data_ptr(),
@@ -84,7 +84,7 @@ class DeviceIngest:
         if rc != 0:
             raise SnacbError(f"snacb_ingest_step failed ({rc})")
         self._counts_host.copy_(self._counts, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        torch.cuda.current_stream(tokens.device).synchronize()
         nw, nt = int(self._counts_host[0]), int(self._counts_host[1])
         return (self._win_tok[:nw], self._win_stream[:nw], self._tail_tok[:nt], self._tail_stream[:nt],
                 self._tail_frames[:nt])
@@ -98,12 +98,17 @@ class DeviceIngest:
             raise SnacbError(f"snacb_ingest_state failed ({rc})")
         return st, cnt
 
-    def step_decode(self, decoder: SnacDecoder, tokens, n_valid=None, finish=None, seed: int = 0,
+    def step_decode(self, decoder: SnacDecoder, tokens, n_valid=None, finish=None, seed: Optional[int] = None,
                     precision: str = "fp16") -> List[Tuple[int, "object"]]:
         """One LLM step end to end on the device: ingest, then ONE batched decode of every window that became ready
         (plus one small decode per remainder length at end of stream).  Returns [(stream, int16 PCM device tensor)]
-        in (stream, time) order -- what ``stream_audio`` yields, for all streams."""
+        in (stream, time) order -- what ``stream_audio`` yields, for all streams.
+        ``seed=None`` (default): every call draws fresh NoiseBlock noise, as the reference does with ``torch.randn`` on
+        every decode (a constant seed would repeat one noise sequence in every window of every step)."""
         import torch
+        if seed is None:
+            self._seed = getattr(self, "_seed", 0) + 1
+            seed = self._seed
         wt, ws, tt, ts, tf = self.step(tokens, n_valid, finish)
         out = []                                   # (stream, order within the stream, pcm)
         if wt.shape[0]:

@@ -110,11 +110,38 @@ def load_gains() -> Dict[str, float]:
     return {}
 
 
-def make_state_dict(seed: int = 0, gains: Optional[Dict[str, float]] = None) -> Dict[str, "np.ndarray"]:
+ALPHA_MODES = ("benign", "wild", "hard")
+
+
+def _alphas(seed: int, key: str, c: int, mode: str) -> np.ndarray:
+    """Snake alpha of one layer.  ``benign``: U(0.3, 3) (what the gains were calibrated on).  Trained alphas can be
+    ~0, negative or large, so the parity tests also run on
+      ``wild``: half of the channels from {-0.7, 12, 40} -- still inside the range where the fp16 chain kernel's
+                alpha-folded formulation is used (csrc/snacb.cu chain_fold_safe), and
+      ``hard``: half of the channels from {0, 1e-4, -1e-4, -0.7, 12, 40} -- forces the general (fp32 Snake) variant;
+                alpha = 0 must give snake(x) = x as in the reference."""
+    base = 0.3 + 2.7 * rng_uniform(seed, _sid(key), c)
+    if mode == "benign":
+        return base
+    pool = np.array([-0.7, 12.0, 40.0] if mode == "wild" else [0.0, 1e-4, -1e-4, -0.7, 12.0, 40.0])
+    pick = rng_uniform(seed, _sid(key + ".pick"), c) < 0.5
+    which = (rng_bits(seed, _sid(key + ".which"), c) % np.uint64(len(pool))).astype(np.int64)
+    return np.where(pick, pool[which], base)
+
+
+def make_state_dict(seed: int = 0, gains: Optional[Dict[str, float]] = None, alpha_mode: str = "benign",
+                    act_scale: float = 1.0) -> Dict[str, "np.ndarray"]:
     """Synthetic decode-path state dict as float32 numpy arrays, upstream key names
-    (old-style ``weight_g``/``weight_v``).  g = gain * ||v|| * U(0.5, 1.5) per norm channel."""
+    (old-style ``weight_g``/``weight_v``).  g = gain * ||v|| * U(0.5, 1.5) per norm channel.
+    ``act_scale``: activations of the whole decoder ``act_scale`` times larger (stem 1x1 gain up, tail conv gain down
+    by the same factor, so the tanh still is not saturated)."""
+    assert alpha_mode in ALPHA_MODES
     if gains is None:
         gains = load_gains()
+    if act_scale != 1.0:
+        gains = dict(gains)
+        gains["decoder.model.1"] = gains.get("decoder.model.1", 1.0) * act_scale
+        gains["decoder.model.7"] = gains.get("decoder.model.7", 1.0) / act_scale
     sd: Dict[str, np.ndarray] = {}
     for i in range(3):
         k = f"quantizer.quantizers.{i}.codebook.weight"
@@ -135,7 +162,7 @@ def make_state_dict(seed: int = 0, gains: Optional[Dict[str, float]] = None) -> 
             nb = shape[1] if kind == "convt" else shape[0]
             sd[prefix + ".bias"] = (0.1 * rng_normal(seed, _sid(prefix + ".b"), nb)).astype(np.float32)
     for k, c in _alpha_keys():
-        sd[k] = (0.3 + 2.7 * rng_uniform(seed, _sid(k), c)).reshape(1, c, 1).astype(np.float32)
+        sd[k] = _alphas(seed, k, c, alpha_mode).reshape(1, c, 1).astype(np.float32)
     return sd
 
 

@@ -90,11 +90,68 @@ def fold_state_dict(sd: Mapping[str, object]) -> Dict[str, np.ndarray]:
     return out
 
 
-def load_checkpoint(path: str) -> Dict[str, np.ndarray]:
-    """Read ``pytorch_model.bin`` (or a directory holding it) of hubertsiuzdak/snac_24khz."""
+CKPT_ENV = "SNACB_CKPT"            # path of pytorch_model.bin (or its directory) used when init_snac() gets no argument
+CACHE_ENV = "SNACB_CACHE_DIR"      # where folded weights are cached (default ~/.cache/snacb); "" disables the cache
+_FOLD_VERSION = 1                  # bump when fold_state_dict's output changes
+
+
+def resolve_checkpoint(path: str) -> str:
+    """``path`` may be the file or the directory ``SNAC.from_pretrained`` would have downloaded into
+    (``pytorch_model.bin`` next to ``config.json``)."""
     import os
-    import torch
     if os.path.isdir(path):
         path = os.path.join(path, "pytorch_model.bin")
-    sd = torch.load(path, map_location="cpu", weights_only=True)
-    return {k: v.numpy() for k, v in sd.items()}
+    if not os.path.isfile(path):
+        raise FileNotFoundError(f"SNAC checkpoint not found: {path}")
+    return path
+
+
+def load_checkpoint(path: str) -> Dict[str, np.ndarray]:
+    """Read ``pytorch_model.bin`` (or a directory holding it) of hubertsiuzdak/snac_24khz: the raw state dict
+    (weight-norm NOT folded), either key style."""
+    import torch
+    sd = torch.load(resolve_checkpoint(path), map_location="cpu", weights_only=True)
+    if isinstance(sd, dict) and "state_dict" in sd and "decoder.model.0.bias" not in sd:
+        sd = sd["state_dict"]
+    return {k: v.numpy() for k, v in sd.items() if hasattr(v, "numpy")}
+
+
+def _file_sha256(path: str) -> str:
+    import hashlib
+    h = hashlib.sha256()
+    with open(path, "rb") as f:
+        for chunk in iter(lambda: f.read(1 << 22), b""):
+            h.update(chunk)
+    return h.hexdigest()
+
+
+def load_folded(path: str, cache_dir: "str | None" = None) -> Dict[str, np.ndarray]:
+    """Checkpoint file -> folded fp32 arrays (``fold_state_dict``), through a cache keyed by the file's SHA-256:
+    the reference re-derives ``g * v / ||v||`` on every forward; here it is derived once per checkpoint CONTENT and
+    later loads of the same file skip torch.load and the fold.  A stale or unreadable cache entry
+    is ignored and rewritten."""
+    import os
+    path = resolve_checkpoint(path)
+    if cache_dir is None:
+        cache_dir = os.environ.get(CACHE_ENV, os.path.join(os.path.expanduser("~"), ".cache", "snacb"))
+    entry = None
+    if cache_dir:
+        entry = os.path.join(cache_dir, f"folded-v{_FOLD_VERSION}-{_file_sha256(path)[:32]}.npz")
+        if os.path.isfile(entry):
+            try:
+                with np.load(entry) as z:
+                    out = {k: np.ascontiguousarray(z[k], dtype=np.float32) for k in z.files}
+                if "tail_w" in out and "b3.r2.pw_w" in out:
+                    return out
+            except Exception:  # noqa: BLE001 -- corrupt entry: fall through and rebuild it
+                pass
+    out = fold_state_dict(load_checkpoint(path))
+    if entry:
+        try:
+            os.makedirs(cache_dir, exist_ok=True)
+            tmp = f"{entry}.{os.getpid()}.tmp.npz"
+            np.savez(tmp, **out)
+            os.replace(tmp, entry)
+        except OSError:
+            pass                     # read-only home etc.: the cache is an optimisation only
+    return out
