@@ -186,6 +186,11 @@ int snacb_debug_tap_copy(snacb_handle h, int idx, float* dst_host, size_t dst_el
  * No GPU needed. */
 int snacb_debug_chain_spans(int C, int16_t* out, int cap);
 
+/* The same for the warp-specialised, block-pipelined chain kernel (kernels_chain_ws.cu; C = 64 or 128, enabled with
+ * SNACB_CHAIN_WS=1): spans live inside ONE 128-row block and count QUADS (4 steps): {first_row (block-relative),
+ * quads, chunk} for each of the 8 prologue warps.  Returns (tile height in rows) | (prologue warps << 16). */
+int snacb_debug_chain_ws_spans(int C, int16_t* out, int cap);
+
 /* ---------------------------------------------------------------------------------------------
  * Batcher: the multi-stream replacement of stream_audio's per-stream buffer policy
  * (modal_audio_stream.py:352-396), which decodes one stream at a time under a global lock.
@@ -195,6 +200,7 @@ int snacb_debug_chain_spans(int C, int16_t* out, int cap);
  *   policy 1 (sliding): the rule the constants describe (modal_audio_stream.py:86-95) -- once 28 codes
  *                       are buffered, every 7 new codes decode the last 28 and emit samples [2048:4096].
  * --------------------------------------------------------------------------------------------- */
+/* h may be NULL: the batcher then only queues (push / end / take), flushing returns SNACB_ERR_STATE. */
 int snacb_batcher_create(snacb_batcher* out, snacb_handle h, int policy, int flags, int max_windows);
 void snacb_batcher_destroy(snacb_batcher b);
 /* Append n raw token ids (flags & SNACB_RAW_IDS) or codes to a stream.  THREAD-SAFE: any number of producer threads may
@@ -221,6 +227,9 @@ int snacb_batcher_flush_submit(snacb_batcher b, uint64_t seed, int max_chunks, u
                                int32_t* lengths, int16_t* pcm_host, size_t pcm_capacity);
 int snacb_batcher_flush_wait(snacb_batcher b);
 int snacb_batcher_pending(snacb_batcher b);     /* windows ready to decode right now */
+/* Pop up to max_windows ready windows WITHOUT decoding them (a caller that routes windows itself, e.g. into
+ * snacb_decode_keyed): ids[i], frames[i] (4, or 1..3 for an end-of-stream remainder), tok[i][28] zero padded. */
+int snacb_batcher_take(snacb_batcher b, int max_windows, uint64_t* ids, int32_t* frames, int32_t* tok);
 
 /* ---------------------------------------------------------------------------------------------
  * Device-side token ingest: the LLM loop's sampled token ids go from a device

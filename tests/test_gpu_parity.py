@@ -143,6 +143,55 @@ def test_fused_chain_block_outputs(decoder, oracle_model, B, F_):
     assert snr_db(wu.cpu().numpy(), wf.cpu().numpy()) >= 45.0
 
 
+# ------------------------------------------------------------------------------------ warp-specialised chain kernel
+@pytest.fixture(scope="module")
+def ws_decoder(state_dict):
+    """SNACB_CHAIN_WS=1: blocks 2 and 3 (C = 128 / 64) run kernels_chain_ws.cu (prologue / epilogue / IO warps pipelined
+    over the 128-row blocks of a tile) instead of the lock-step k_chain."""
+    import os
+    os.environ["SNACB_CHAIN_WS"] = "1"
+    try:
+        d = SnacDecoder(state_dict, device=0)          # the switch is read when the handle is created
+    finally:
+        del os.environ["SNACB_CHAIN_WS"]
+    yield d
+    d.close()
+
+
+@pytest.mark.parametrize("prec", ["fp16", "bf16"])
+@pytest.mark.parametrize("B,F_,sliced", [(1, 4, False), (3, 4, True), (37, 4, False), (2, 16, False), (300, 4, True), (5, 1, False),
+                                         (3, 33, False)])
+def test_ws_chain_is_bit_identical(decoder, ws_decoder, B, F_, sliced, prec):
+    """Every element goes through the same arithmetic in the same order as in k_chain: PCM and waveform are equal bit for
+    bit, injected and in-kernel noise, whole windows, the trimmed sliced call, long utterances, many tiles per CTA."""
+    tokens = _cuda(synth.make_tokens(B, F_, seed=60 + F_, bad_frac=0.01))
+    nz = [_cuda(n) for n in synth.make_noises(B, 4 * F_, seed=9)]
+    for kw in (dict(noise=nz), dict(seed=5)):
+        p0, w0 = decoder.decode(tokens, raw_ids=True, precision=prec, extract_slice=sliced, return_wave=True, **kw)
+        p1, w1 = ws_decoder.decode(tokens, raw_ids=True, precision=prec, extract_slice=sliced, return_wave=True, **kw)
+        torch.cuda.synchronize()
+        assert torch.equal(p0, p1) and torch.equal(w0, w1)
+
+
+def test_ws_chain_ranged_and_general_variant(ws_decoder, decoder, monkeypatch):
+    tokens = _cuda(synth.make_tokens(4, 9, seed=3))
+    full = ws_decoder.decode(tokens, raw_ids=True, seed=6, return_wave=True)
+    part = ws_decoder.decode(tokens, raw_ids=True, seed=6, return_wave=True, sample_range=(5000, 11000))
+    assert torch.equal(part[0], full[0][:, 5000:11000]) and torch.equal(part[1], full[1][:, 5000:11000])
+    assert torch.equal(full[0], decoder.decode(tokens, raw_ids=True, seed=6))
+    # the general (fp32 Snake) variant of both kernels on a checkpoint that forbids the alpha fold
+    sd = synth.make_state_dict(2, alpha_mode="hard")
+    a = SnacDecoder(sd, device=0)
+    monkeypatch.setenv("SNACB_CHAIN_WS", "1")
+    b = SnacDecoder(sd, device=0)
+    monkeypatch.delenv("SNACB_CHAIN_WS")
+    assert a.chain_modes() == [0, 1, 1, 1]
+    tok = _cuda(synth.make_tokens(6, 4, seed=8))
+    ra, rb = a.decode(tok, raw_ids=True, seed=2, return_wave=True), b.decode(tok, raw_ids=True, seed=2, return_wave=True)
+    assert torch.equal(ra[0], rb[0]) and torch.equal(ra[1], rb[1])
+    a.close(); b.close()
+
+
 # ------------------------------------------------------------------------------------ adversarial checkpoints
 ADVERSARIAL = [(1, "wild", 1.0), (2, "hard", 1.0), (3, "hard", 4.0), (4, "wild", 4.0), (5, "benign", 4.0)]
 

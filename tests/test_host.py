@@ -225,3 +225,272 @@ def test_chain_span_schedule(C):
                 assert r in written and work[r] == want[r], (C, d, kc, r)
     per_warp = sp[:, :nw, :, 1].sum(axis=2)
     assert per_warp.max() - per_warp.min() <= 1                             # balanced to one octet
+
+
+@pytest.mark.parametrize("policy", [0, 1])
+def test_batcher_queue_from_many_producer_threads(policy):
+    """The sharded batcher (csrc/batcher.cpp) without a decoder: 8 producer threads push 200 streams token by token /
+    in ragged pieces while a consumer takes ready windows concurrently; every stream's windows equal the oracle's
+    (stream_audio's 28-code chunks + end-of-stream remainder, modal_audio_stream.py:352-396; or the sliding 28/7
+    rule), in time order; a push after end is refused until the id is forgotten."""
+    import threading
+    from oracle import glue_ref
+    from tts_inference_b200 import SnacbError, synth
+    from tts_inference_b200.batcher import WindowBatcher
+    b = WindowBatcher(None, policy=policy, raw_ids=True, max_windows=4096)
+    streams = {1000 + 7 * i: synth.make_tokens(1, 12, seed=i)[0][: 84 - (i % 9)] for i in range(200)}
+    ids = list(streams)
+    got = {sid: [] for sid in ids}
+    done = threading.Event()
+
+    def producer(k):
+        rng = np.random.default_rng(k)
+        mine = ids[k::8]
+        pos = {s: 0 for s in mine}
+        live = list(mine)
+        while live:
+            s = live[int(rng.integers(len(live)))]
+            n = int(rng.integers(1, 4)) if k % 2 else 1
+            b.push(s, streams[s][pos[s]: pos[s] + n])
+            pos[s] += n
+            if pos[s] >= len(streams[s]):
+                b.end(s)
+                live.remove(s)
+
+    def consumer():
+        while True:
+            fin = done.is_set()
+            for sid, tok in b.take(257):
+                got[sid].append(tok.tolist())
+            if fin and b.pending() == 0:
+                return
+
+    th = [threading.Thread(target=producer, args=(k,)) for k in range(8)]
+    ct = threading.Thread(target=consumer)
+    ct.start()
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    done.set()
+    ct.join()
+    for sid, toks in streams.items():
+        want = glue_ref.stream_chunks(toks.tolist()) if policy == 0 else glue_ref.sliding_windows(toks.tolist())
+        assert got[sid] == want, sid
+    with pytest.raises(SnacbError):
+        b.push(ids[0], [1, 2, 3])                      # ended: refused, not a silent new stream
+    b.forget(ids[0])
+    b.push(ids[0], [1, 2, 3])                          # forgotten: the id is free again
+    with pytest.raises(SnacbError):
+        b.flush()                                      # no decoder attached
+    b.close()
+
+
+@pytest.mark.parametrize("C", [64, 128])
+def test_ws_chain_span_schedule(C):
+    """Data schedule of the warp-specialised chain kernel's prologue (kernels_chain_ws.cu), emulated on integers in the
+    kernel's order: blocks of a layer one after the other; per block every warp first fetches the 3 rows before / after
+    its spans (from the block, from the carry copy of the previous block's last 27 rows, or from the untouched next
+    block), the warps then copy the block's last rows to the carry buffer, and only then rewrite their rows in place in
+    arbitrary order.  Every row of the tile must come out of the layer's ORIGINAL values (no read-after-overwrite)."""
+    import ctypes as Ct
+    from tts_inference_b200 import _lib
+    lib = _lib.load()
+    buf = (Ct.c_int16 * (3 * 16 * 4 * 3))()
+    rc = lib.snacb_debug_chain_ws_spans(C, buf, len(buf))
+    rows, nw = rc & 0xFFFF, rc >> 16
+    assert rows % 128 == 0 and nw in (7, 8)
+    nb = rows // 128
+    sp = np.frombuffer(buf, dtype=np.int16).reshape(3, 16, 4, 3)
+    assert (sp[:, nw:, :, 1] == 0).all()
+    rng = np.random.default_rng(1)
+    for l, d in enumerate((1, 3, 9)):
+        quads = sp[l, :nw, :, 1].sum(axis=1)
+        assert quads.max() - quads.min() <= 1                               # balanced to one quad (4 steps)
+        for kc in range(C // 64):
+            x = rng.integers(1, 1 << 30, size=rows + 128).astype(np.int64)  # + rows past the tile (garbage the halo absorbs)
+            f = lambda r, src: int(sum((j + 2) * (src[r + (j - 3) * d] if r + (j - 3) * d >= 0 else 0) for j in range(7)))
+            want = {r: f(r, x) for r in range(rows)}
+            work = x.copy()
+            carry = {}
+            for b in range(nb):
+                base = 128 * b
+                spans = [(w, k, int(sp[l, w, k, 0]), int(sp[l, w, k, 1])) for w in range(nw) for k in range(4)
+                         if sp[l, w, k, 1] > 0 and sp[l, w, k, 2] == kc]
+                pre = {}
+                for (w, k, r0, nq) in spans:                                # phase 1: pre-reads
+                    head = []
+                    for j in range(3):
+                        rh = r0 - (3 - j) * d
+                        if rh >= 0:
+                            head.append(work[base + rh])
+                        elif b > 0:
+                            assert rh >= -27
+                            head.append(carry[(b - 1) & 1][27 + rh])
+                        else:
+                            head.append(0)
+                    tail = [work[base + r0 + (4 * nq + j) * d] for j in range(3)]
+                    pre[(w, k)] = (head, tail)
+                if b + 1 < nb:
+                    carry[b & 1] = work[base + 101: base + 128].copy()
+                written = set()
+                for (w, k, r0, nq) in sorted(spans, key=lambda s_: rng.random()):   # phase 2 (after the block barrier)
+                    head, tail = pre[(w, k)]
+                    mem = lambda i: work[base + r0 + i * d]                 # a load from the tile copy, whatever it holds now
+                    win = [0] + head + [mem(0), mem(1), mem(2)]
+                    noct = (nq + 1) // 2
+                    for o in range(noct):
+                        full = nq - 2 * o >= 2
+                        raw = [mem(8 * o + kk + 3) for kk in range(8)]      # the octet's 8 loads come first
+                        if o == noct - 1:
+                            if full:
+                                raw[5:8] = tail
+                            else:
+                                raw[1:4] = tail
+                        for kk in range(8 if full else 4):
+                            win = win[-6:] + [raw[kk]]
+                            r = r0 + (8 * o + kk) * d
+                            if r < 128:
+                                assert base + r not in written
+                                written.add(base + r)
+                                work[base + r] = sum((j + 2) * win[j] for j in range(7))
+                assert written == set(range(base, base + 128)), (C, d, kc, b)
+            for r in range(rows - 27):                                      # the last 3d rows see the garbage past the tile
+                assert work[r] == want[r], (C, d, kc, r)
+
+
+def test_ws_chain_protocol():
+    """The mbarrier protocol of kernels_chain_ws.cu under random timing: 7 prologue warps, 8 epilogue warps and the IO
+    thread as coroutines stepping in random order over several tiles.  mbarriers are modelled with their real semantics
+    (a waiter sees only the PARITY of the completed-phase count), so both failure modes of a mis-designed protocol show
+    up: a deadlock, or a wait that returns for the wrong phase (checked against the true phase counter).  Data
+    dependencies are checked on a shadow state: P(l, b) needs S1_l of blocks b and b+1, MMA needs the operand, E needs the
+    MMA, a TMA refill needs the store, the next tile's NoiseBlock MMA needs the refill and a drained accumulator."""
+    import random
+    NB, NP, NE = 4, 7, 8
+
+    class Bar:
+        def __init__(self, count):
+            self.count, self.pending, self.done = count, count, 0
+        def arrive(self):
+            self.pending -= 1
+            assert self.pending >= 0
+            if self.pending == 0:
+                self.pending, self.done = self.count, self.done + 1
+        def test(self, parity):                       # mbarrier.try_wait.parity
+            return (self.done & 1) != parity
+
+    for seed in range(40):
+        rnd = random.Random(seed)
+        n_tiles = rnd.choice([1, 2, 3, 5])
+        ld = [Bar(1) for _ in range(NB)]; mma = [Bar(1) for _ in range(NB)]; a_ = [Bar(NP) for _ in range(NB)]
+        s1 = [Bar(NE) for _ in range(NB)]; out = [Bar(NE) for _ in range(NB)]; tile_bar = Bar(1)
+        s_tile = [0, None]
+        # shadow state: what each block of the tile copy / TMEM holds
+        state = {"copy": [("y", 0)] * NB, "mma_issued": [(-1, -1)] * NB}
+        log = {"p": set(), "e": set(), "mma": set(), "store": set(), "load": {(0, b) for b in range(NB)}}
+        for b in range(NB):
+            ld[b].arrive()                            # first tile's loads land at some point: model as landed
+
+        def wait(bar, parity, want_done):
+            while not bar.test(parity):
+                yield
+            assert bar.done >= want_done, ("wait returned for an earlier phase", bar.done, want_done)
+            assert bar.done <= want_done + 1, ("waiter lags two phases: parity would alias", bar.done, want_done)
+
+        def p_warp(w):
+            n = 0
+            tile = 0
+            while tile < n_tiles:
+                for l in range(3):
+                    for b in range(NB):
+                        if b == 0:
+                            yield from wait(s1[0], (3 * n + l) & 1, 3 * n + l + 1)
+                        if b + 1 < NB:
+                            yield from wait(s1[b + 1], (3 * n + l) & 1, 3 * n + l + 1)
+                        assert (n, l, b) in log["e"] and (b + 1 == NB or (n, l, b + 1) in log["e"])
+                        yield                          # pre-read + carry copy, named barrier, compute
+                        log["p"].add((n, l + 1, b, w))
+                        a_[b].arrive()
+                yield from wait(tile_bar, n & 1, n + 1)
+                tile = s_tile[(n + 1) & 1]
+                n += 1
+
+        def e_warp(w):
+            n = 0
+            tile = 0
+            while tile < n_tiles:
+                for ph in range(4):
+                    for b in range(NB):
+                        yield from wait(mma[b], ph & 1, 4 * n + ph + 1)
+                        assert (n, ph, b) in log["mma"]
+                        yield
+                        if ph < 3:
+                            if w == 0:
+                                log["e"].add((n, ph, b))
+                            s1[b].arrive()
+                        else:
+                            if w == 0:
+                                log["e"].add((n, 3, b))
+                            out[b].arrive()
+                yield from wait(tile_bar, n & 1, n + 1)
+                tile = s_tile[(n + 1) & 1]
+                n += 1
+
+        def io():
+            mt = ml = mb = st = sb = 0
+            n_local, more, claimed = 1, True, False
+            next_free = 1
+            while mt < n_local or st < n_local:
+                if mt < n_local:
+                    if ml == 0:
+                        ready = ld[mb].test(mt & 1)
+                        if ready:
+                            assert ld[mb].done == mt + 1 and (mt, mb) in log["load"]
+                            assert mt == 0 or (mt - 1, 3, mb) in log["e"]           # accumulator drained
+                    else:
+                        ready = a_[mb].test((3 * mt + ml - 1) & 1)
+                        if ready:
+                            assert a_[mb].done == 3 * mt + ml
+                            assert all((mt, ml, mb, w) in log["p"] for w in range(NP))
+                    if ready:
+                        log["mma"].add((mt, ml, mb))
+                        mma[mb].arrive()               # tcgen05.commit, modelled as immediate
+                        if ml == 1 and mb == 0 and not claimed:
+                            nt = next_free if more else n_tiles
+                            next_free += 1
+                            more = nt < n_tiles
+                            s_tile[(mt + 1) & 1] = nt
+                            tile_bar.arrive()
+                            if more:
+                                n_local += 1
+                            claimed = True
+                        mb += 1
+                        if mb == NB:
+                            mb, ml = 0, ml + 1
+                            if ml == 4:
+                                ml, mt, claimed = 0, mt + 1, False
+                yield
+                if st < n_local and st <= mt and not (st == mt and ml < 3) and out[sb].test(st & 1):
+                    assert out[sb].done == st + 1 and (st, 3, sb) in log["e"]
+                    log["store"].add((st, sb))
+                    if st + 1 < n_local:
+                        log["load"].add((st + 1, sb))
+                        ld[sb].arrive()
+                    sb += 1
+                    if sb == NB:
+                        sb, st = 0, st + 1
+                yield
+
+        procs = [p_warp(w) for w in range(NP)] + [e_warp(w) for w in range(NE)] + [io()]
+        alive = list(range(len(procs)))
+        steps = 0
+        while alive:
+            i = rnd.choice(alive) if rnd.random() < 0.9 else alive[0]
+            try:
+                next(procs[i])
+            except StopIteration:
+                alive.remove(i)
+            steps += 1
+            assert steps < 2_000_000, f"deadlock (seed {seed}, {n_tiles} tiles)"
+        assert len(log["store"]) == n_tiles * NB

@@ -15,8 +15,8 @@ import sys
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libsnacb.so")
-SOURCES = ["snacb.cu", "kernels_simt.cu", "kernels_tc.cu", "kernels_res2.cu", "kernels_chain.cu", "kernels_convt.cu", "kernels_io.cu", "batcher.cpp"]
-HEADERS = ["common.cuh", "kernels.h", "ptx.cuh", os.path.join("..", "..", "include", "snacb.h")]
+SOURCES = ["snacb.cu", "kernels_simt.cu", "kernels_tc.cu", "kernels_res2.cu", "kernels_chain.cu", "kernels_chain_ws.cu", "kernels_convt.cu", "kernels_io.cu", "batcher.cpp"]
+HEADERS = ["common.cuh", "chain_span.cuh", "kernels.h", "ptx.cuh", os.path.join("..", "..", "include", "snacb.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
@@ -65,5 +65,23 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+BENCH_SRC = os.path.join(os.path.dirname(PKG), "tests", "native", "batcher_bench.cpp")
+BENCH_LIB = os.path.join(os.path.dirname(PKG), "tests", "native", "libbatcherbench.so")
+
+
+def build_test_helpers(force: bool = False) -> str:
+    """tests/native/libbatcherbench.so: the multi-threaded producer harness of tests/gpu_batcher_bench.py (g++, links
+    libsnacb.so by path; test infrastructure, not shipped)."""
+    if not os.path.exists(BENCH_SRC):
+        return ""
+    if not force and os.path.exists(BENCH_LIB) and os.path.getmtime(BENCH_LIB) >= max(os.path.getmtime(BENCH_SRC), os.path.getmtime(LIB)):
+        return BENCH_LIB
+    cmd = ["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-pthread", BENCH_SRC, "-o", BENCH_LIB,
+           "-L" + PKG, "-l:libsnacb.so", "-Wl,-rpath," + PKG, "-Wl,-rpath,$ORIGIN/../../tts_inference_b200"]
+    subprocess.run(cmd, check=True)
+    return BENCH_LIB
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    print(build_test_helpers(force="--force" in sys.argv))

@@ -103,13 +103,13 @@ static void queue_chunks(snacb_batcher b, Shard& sh, uint64_t id, StreamState& s
 extern "C" {
 
 int snacb_batcher_create(snacb_batcher* out, snacb_handle h, int policy, int flags, int max_windows) {
-    if (!out || !h || (policy != 0 && policy != 1) || max_windows <= 0) return SNACB_ERR_ARG;
+    if (!out || (policy != 0 && policy != 1) || max_windows <= 0) return SNACB_ERR_ARG;     // h may be NULL: queue only
     snacb_batcher b = new (std::nothrow) snacb_batcher_s();
     if (!b) return SNACB_ERR_NOMEM;
     b->h = h; b->policy = policy; b->max_windows = max_windows;
     b->flags = flags & (SNACB_RAW_IDS | SNACB_FP32 | SNACB_STREAM_FP32 | SNACB_BF16);
     if (policy == 1) b->flags |= SNACB_EXTRACT_SLICE;
-    for (int i = 0; i < 2; ++i)
+    for (int i = 0; h && i < 2; ++i)
         if (cudaMallocHost(reinterpret_cast<void**>(&b->pin_tok[i]), static_cast<size_t>(max_windows) * kWindow * 4) != cudaSuccess) {
             snacb_batcher_destroy(b);
             return SNACB_ERR_NOMEM;
@@ -185,9 +185,28 @@ int snacb_batcher_pending(snacb_batcher b) {
     return n > 0x7fffffffLL ? 0x7fffffff : static_cast<int>(n);
 }
 
+int snacb_batcher_take(snacb_batcher b, int max_windows, uint64_t* ids, int32_t* frames, int32_t* tok) {
+    if (!b || max_windows < 0 || !ids || !frames || !tok) return SNACB_ERR_ARG;
+    int n = 0;
+    for (int si = 0; si < kShards && n < max_windows; ++si) {
+        Shard& sh = b->shards[si];
+        std::lock_guard<std::mutex> lk(sh.mu);
+        while (!sh.ready.empty() && n < max_windows) {
+            const Item& it = sh.ready.front();
+            ids[n] = it.id; frames[n] = it.frames;
+            std::memcpy(tok + static_cast<size_t>(n) * kWindow, it.tok, kWindow * sizeof(int32_t));
+            sh.ready.pop_front();
+            ++n;
+        }
+    }
+    if (n) b->n_ready.fetch_sub(n, std::memory_order_relaxed);
+    return n;
+}
+
 int snacb_batcher_flush_submit(snacb_batcher b, uint64_t seed, int max_chunks, uint64_t* ids, int64_t* offsets,
                                int32_t* lengths, int16_t* pcm_host, size_t pcm_capacity) {
     if (!b || max_chunks < 0 || !ids || !offsets || !lengths || !pcm_host) return SNACB_ERR_ARG;
+    if (!b->h) return SNACB_ERR_STATE;                                  // a batcher created without a decoder only queues
     std::lock_guard<std::mutex> fl(b->flush_mu);
     if (b->inflight.size() >= 2) return SNACB_ERR_STATE;               // two flushes outstanding: wait first
     int outstanding = 0;

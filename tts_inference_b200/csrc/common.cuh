@@ -66,6 +66,7 @@ struct ResUnitArgs {
 // Fused NoiseBlock + 3 ResidualUnits of one DecoderBlock (kernels_chain.cu).
 constexpr int kChainWarps = 16;        // at most; a launch configuration may use 8
 constexpr int kChainSpans = 4;         // spans per warp and layer, at most
+constexpr int kChainWsP = 7;           // prologue warps of the warp-specialised chain kernel (kernels_chain_ws.cu)
 constexpr int kChainHalo = 40;
 struct ChainSpan { short r_first, n_oct, kc, pad; };   // a warp's run of 8-step octets along one dilation class
 struct ChainLayer {

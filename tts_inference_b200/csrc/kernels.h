@@ -85,4 +85,10 @@ void chain_build_spans(int C, ChainSpan (*spans)[kChainWarps][kChainSpans]);
 // weight maps then point at the copies with 1 / alpha2 folded into their K columns); see chain_fold_safe in snacb.cu
 cudaError_t launch_chain(int half_fp16, int fold, const ChainArgs& a, const CUtensorMap* tm, int sm_count, cudaStream_t st);
 
+// ---- kernels_chain_ws.cu  (the same chain, warp-specialised and pipelined over the 128-row blocks of a tile; C = 64 / 128)
+bool chain_ws_supported(int C, int half_fp16);
+int chain_ws_tile_rows(int C);
+void chain_ws_build_spans(int C, ChainSpan (*spans)[kChainWarps][kChainSpans]);   // ChainSpan::n_oct counts QUADS here
+cudaError_t launch_chain_ws(int half_fp16, int fold, const ChainArgs& a, const CUtensorMap* tm, int sm_count, cudaStream_t st);
+
 }  // namespace snacb

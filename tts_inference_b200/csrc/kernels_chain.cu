@@ -40,6 +40,7 @@
 #include <type_traits>
 #include <vector>
 
+#include "chain_span.cuh"
 #include "common.cuh"
 #include "kernels.h"
 #include "ptx.cuh"
@@ -122,50 +123,37 @@ __device__ __forceinline__ void span_half(uint8_t* plane, int r_oct, const int n
         al2 = make_float2(__uint_as_float(q2.x), __uint_as_float(q2.y));
         ia2 = make_float2(__uint_as_float(q2.z), __uint_as_float(q2.w));
     }
-    auto snake2 = [&](__half2 ah) -> uint32_t {
-        const float2 t = __half22float2(ah);
-        if (FOLD) {                                           // ah = alpha2 * a:  ah + sin^2 ah  (= alpha2 * snake2(a))
-            const __half2 sh = __floats2half2_rn(__sinf(t.x), __sinf(t.y));
-            return as_u32(__hfma2(sh, sh, ah));
-        }
-        const float2 o = snake_pair(t, al2, ia2);
-        return as_u32(__floats2half2_rn(o.x, o.y));
-    };
-    __half2 win[7];
-    win[1] = as_h2(h0); win[2] = as_h2(h1); win[3] = as_h2(h2);
+    uint32_t xs[14];                               // xs[i] = S1 of the class row (i - 3) steps from the octet's first row
+    xs[0] = h0; xs[1] = h1; xs[2] = h2;
     uint8_t* ob = plane + r_oct * 128;             // r_oct = 0 (mod 8): (row & 7) of step k is (k*D) & 7
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
         uint32_t raw = 0u;                         // class starts may lie above the tile
         if (r_oct + j * D >= 0) raw = *reinterpret_cast<const uint32_t*>(ob + j * D * 128 + swz[(j * D) & 7]);
-        win[4 + j] = as_h2(raw);
+        xs[3 + j] = raw;
     }
 #pragma unroll 1
     for (int qo = 0; qo < nq; ++qo) {
-        uint32_t raw[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k)
-            raw[k] = *reinterpret_cast<const uint32_t*>(ob + (k + 3) * D * 128 + swz[((k + 3) * D) & 7]);
-        if (qo == nq - 1) { raw[5] = t0; raw[6] = t1; raw[7] = t2; }
+            xs[6 + k] = *reinterpret_cast<const uint32_t*>(ob + (k + 3) * D * 128 + swz[((k + 3) * D) & 7]);
+        if (qo == nq - 1) { xs[11] = t0; xs[12] = t1; xs[13] = t2; }
+        uint32_t o[8];
+        dw_snake_half<8, FOLD>(xs, w, bd, al2, ia2, o);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-#pragma unroll
-            for (int j = 0; j < 6; ++j) win[j] = win[j + 1];
-            win[6] = as_h2(raw[k]);
-            __half2 acc = bd;
-#pragma unroll
-            for (int j = 0; j < 7; ++j) acc = __hfma2(w[j], win[j], acc);
-            const uint32_t o = snake2(acc);
             const int r = r_oct + k * D;
             if (static_cast<unsigned>(r) < static_cast<unsigned>(ROWS))
-                *reinterpret_cast<uint32_t*>(ob + k * D * 128 + swz[(k * D) & 7]) = o;
+                *reinterpret_cast<uint32_t*>(ob + k * D * 128 + swz[(k * D) & 7]) = o[k];
         }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) xs[i] = xs[8 + i];
         r_oct += 8 * D;
         ob += 8 * D * 128;
     }
 }
 
-// same span, fp32 math (bf16 operands: an 8-bit mantissa cannot carry the depthwise accumulation)
+// same span, fp32 math (bf16 operands)
 template <int D, int ROWS>
 __device__ __forceinline__ void span_bf16(uint8_t* plane, int r_oct, const int nq, const uint32_t h0, const uint32_t h1,
                                           const uint32_t h2, const uint32_t t0, const uint32_t t1, const uint32_t t2,
@@ -176,36 +164,31 @@ __device__ __forceinline__ void span_bf16(uint8_t* plane, int r_oct, const int n
                          make_float2(q2.x, q2.y), make_float2(q2.z, q2.w), make_float2(q3.x, q3.y)};
     const float2 bd = make_float2(q3.z, q3.w);
     const float2 al2 = make_float2(q4.x, q4.y), ia2 = make_float2(q4.z, q4.w);
-    const __nv_bfloat16* tag = nullptr;
-    float2 win[7];
-    win[1] = unpack2c(h0, tag); win[2] = unpack2c(h1, tag); win[3] = unpack2c(h2, tag);
+    uint32_t xs[14];
+    xs[0] = h0; xs[1] = h1; xs[2] = h2;
     uint8_t* ob = plane + r_oct * 128;
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
         uint32_t raw = 0u;
         if (r_oct + j * D >= 0) raw = *reinterpret_cast<const uint32_t*>(ob + j * D * 128 + swz[(j * D) & 7]);
-        win[4 + j] = unpack2c(raw, tag);
+        xs[3 + j] = raw;
     }
 #pragma unroll 1
     for (int qo = 0; qo < nq; ++qo) {
-        uint32_t raw[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k)
-            raw[k] = *reinterpret_cast<const uint32_t*>(ob + (k + 3) * D * 128 + swz[((k + 3) * D) & 7]);
-        if (qo == nq - 1) { raw[5] = t0; raw[6] = t1; raw[7] = t2; }
+            xs[6 + k] = *reinterpret_cast<const uint32_t*>(ob + (k + 3) * D * 128 + swz[((k + 3) * D) & 7]);
+        if (qo == nq - 1) { xs[11] = t0; xs[12] = t1; xs[13] = t2; }
+        uint32_t o[8];
+        dw_snake_bf16<8>(xs, w, bd, al2, ia2, o);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-#pragma unroll
-            for (int j = 0; j < 6; ++j) win[j] = win[j + 1];
-            win[6] = unpack2c(raw[k], tag);
-            float2 acc = bd;
-#pragma unroll
-            for (int j = 0; j < 7; ++j) acc = ffma2(w[j], win[j], acc);
-            acc = snake_pair(acc, al2, ia2);
             const int r = r_oct + k * D;
             if (static_cast<unsigned>(r) < static_cast<unsigned>(ROWS))
-                *reinterpret_cast<uint32_t*>(ob + k * D * 128 + swz[(k * D) & 7]) = pack2(acc.x, acc.y, tag);
+                *reinterpret_cast<uint32_t*>(ob + k * D * 128 + swz[(k * D) & 7]) = o[k];
         }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) xs[i] = xs[8 + i];
         r_oct += 8 * D;
         ob += 8 * D * 128;
     }

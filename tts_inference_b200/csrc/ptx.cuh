@@ -41,6 +41,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// Non-blocking test (try_wait may suspend the thread for a system-dependent time when the phase is not complete: an event
+// loop that polls several barriers must not sit in one of them while another becomes ready).
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 // Spin on try_wait.  A pipeline bug would otherwise hang the GPU until the host kills the process, so a
 // wait that lasts longer than ~2 s of SM clocks traps (the launch then fails with an error instead).
 #ifndef SNACB_WAIT_LIMIT_CYCLES

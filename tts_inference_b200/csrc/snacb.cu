@@ -48,6 +48,7 @@ struct BlockW {
     float* bias_cum;                    // [3][Cout] running sums of the ResidualUnit 1x1 biases (fused chain)
     bool chain[2];                      // the fused NoiseBlock + ResidualUnit chain covers this block ([0] bf16, [1] fp16)
     ChainSpan spans[3][kChainWarps][kChainSpans];
+    ChainSpan spans_ws[3][kChainWarps][kChainSpans];   // warp-specialised chain kernel (kernels_chain_ws.cu): quads inside a block
     bool fold = false;                  // fp16 chain: the alpha-folded formulation is numerically safe for this block's
                                         // Snake alphas (chain_fold_safe); otherwise the general fp32-Snake variant runs
 };
@@ -102,6 +103,7 @@ struct snacb_handle_s {
     std::vector<Tap> taps;
     uint64_t launches = 0, streams = 0;
     bool res_v1 = false;                // SNACB_RES_V1=1: use the non-persistent ResidualUnit kernel
+    bool chain_ws = false;              // SNACB_CHAIN_WS=1: warp-specialised, block-pipelined chain kernel where it applies
     bool no_fold = false;               // SNACB_NO_FOLD=1: general (fp32 Snake) chain variant even where the folded one is safe (A/B)
     int chain_prof = 0;                 // SNACB_CHAIN_PROF=1|2: in-kernel clock64 phase timing of k_chain, printed per launch (debug)
     bool no_chain = false;              // SNACB_NO_CHAIN=1: per-layer kernels instead of the fused chain
@@ -344,6 +346,23 @@ int chain_prof_report(snacb_handle h, const ChainArgs& ca, int bi, cudaStream_t 
     return 0;
 }
 
+int chain_ws_prof_report(snacb_handle h, const ChainArgs& ca, int bi, cudaStream_t st) {
+    unsigned long long pv[32];
+    CK(h, cudaStreamSynchronize(st));
+    CK(h, cudaMemcpy(pv, ca.prof, sizeof pv, cudaMemcpyDeviceToHost));
+    CK(h, cudaFree(ca.prof));
+    const int rows = chain_ws_tile_rows(ca.C) - 2 * kChainHalo;
+    const int tiles = ca.S * (((ca.t_n > 0 ? ca.t_n : ca.T) + rows - 1) / rows);
+    const int mine = (tiles + h->sm_count - 1) / h->sm_count;
+    fprintf(stderr, "chain_ws b%d C=%d: cycles per tile (~%d tiles per CTA) | P warp 0:", bi, ca.C, mine);
+    for (int l = 0; l < 3; ++l)
+        fprintf(stderr, " L%d wait-S1 %llu pre+bar %llu spans %llu |", l, pv[4 * l] / mine, pv[1 + 4 * l] / mine, pv[2 + 4 * l] / mine);
+    fprintf(stderr, " next-tile wait %llu || E warp 0:", pv[12] / mine);
+    for (int i = 0; i < 4; ++i) fprintf(stderr, " B%d wait-MMA %llu drain %llu |", i, pv[17 + 2 * i] / mine, pv[18 + 2 * i] / mine);
+    fprintf(stderr, " || IO idle polls %llu\n", pv[16] / mine);
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------------
 // One group of S streams through the whole path.
 // ------------------------------------------------------------------------------------------------
@@ -402,7 +421,8 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
             Rng y;                                                  // ConvTranspose output rows that must be valid
             const bool unfused = (flags & SNACB_UNFUSED) != 0 || h->no_chain;
             if (b.chain[hk] && !unfused) {
-                const int rows = chain_tile_rows(b.Cout) - 2 * kChainHalo;
+                const bool ws = h->chain_ws && chain_ws_supported(b.Cout, hk);
+                const int rows = (ws ? chain_ws_tile_rows(b.Cout) : chain_tile_rows(b.Cout)) - 2 * kChainHalo;
                 const int n = (need.hi - need.lo + rows - 1) / rows;
                 post[bi] = Rng{need.lo, need.lo + n * rows};
                 y = clip(Rng{post[bi].lo - kChainHalo, post[bi].hi + kChainHalo}, Tb[bi]);
@@ -544,7 +564,8 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
             ca.alpha_next = bi < 3 ? h->blk[bi + 1].alpha : h->tail_alpha;
             ca.inv_next = bi < 3 ? h->blk[bi + 1].inv_alpha : h->tail_inv;
             ca.noise = noise ? noise[bi] : nullptr; ca.seed = seed; ca.noise_stage = bi; ca.stream_offset = stream_offset; ca.stream_keys = stream_keys;
-            memcpy(ca.spans, b.spans, sizeof ca.spans);
+            const bool ws = h->chain_ws && chain_ws_supported(b.Cout, hk);
+            memcpy(ca.spans, ws ? b.spans_ws : b.spans, sizeof ca.spans);
             ca.tile_counter = h->tile_counter;
             CK(h, cudaMemsetAsync(h->tile_counter, 0, sizeof(int), st));
             const bool fold = hk && b.fold && !h->no_fold;
@@ -563,10 +584,11 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
             snprintf(nm, sizeof nm, "b%d.chain", bi);
             prof_begin(h, nm, st);
             if (h->chain_prof) { rc = chain_prof_begin(h, &ca, st); if (rc) return rc; }
-            cudaError_t le = launch_chain(hk, fold ? 1 : 0, ca, tm, h->sm_count, st);
+            cudaError_t le = ws ? launch_chain_ws(hk, fold ? 1 : 0, ca, tm, h->sm_count, st)
+                                : launch_chain(hk, fold ? 1 : 0, ca, tm, h->sm_count, st);
             prof_end(h, st);
             CK(h, le);
-            if (h->chain_prof) { rc = chain_prof_report(h, ca, bi, st); if (rc) return rc; }
+            if (h->chain_prof) { rc = ws ? chain_ws_prof_report(h, ca, bi, st) : chain_prof_report(h, ca, bi, st); if (rc) return rc; }
             h->launches++;
             snprintf(nm, sizeof nm, "b%d.res2", bi);
             rc = tap_any(nm, cur, dt_h, (int64_t)S * T, b.Cout);
@@ -755,6 +777,7 @@ int snacb_create(snacb_handle* out, const snacb_weights* w, int device) {
             b.chain[0] = chain_supported(b.Cout, 0);
             b.chain[1] = chain_supported(b.Cout, 1);
             if (b.chain[0] || b.chain[1]) chain_build_spans(b.Cout, b.spans);
+            if (chain_ws_supported(b.Cout, 1)) chain_ws_build_spans(b.Cout, b.spans_ws);
             // fp16 chain: the alpha-folded formulation (kernels_chain.cu) divides by the Snake alphas when it packs its
             // parameters; it is used only where that is numerically safe for THIS checkpoint, else the general variant runs
             b.fold = b.chain[1] && chain_fold_safe(s, b.Cout);
@@ -789,6 +812,7 @@ int snacb_create(snacb_handle* out, const snacb_weights* w, int device) {
     if (const char* e = getenv("SNACB_RES_V1")) h->res_v1 = atoi(e) != 0;
     if (const char* e = getenv("SNACB_NO_CHAIN")) h->no_chain = atoi(e) != 0;
     if (const char* e = getenv("SNACB_NO_FOLD")) h->no_fold = atoi(e) != 0;
+    if (const char* e = getenv("SNACB_CHAIN_WS")) h->chain_ws = atoi(e) != 0;
     if (const char* e = getenv("SNACB_TMAP_CACHE")) { const long n = atol(e); if (n >= 1) h->max_act_maps = static_cast<size_t>(n); }
     if (const char* e = getenv("SNACB_CHAIN_PROF")) h->chain_prof = atoi(e);
     if (const char* e = getenv("SNACB_NO_TRIM")) h->no_trim = atoi(e) != 0;
@@ -1040,6 +1064,19 @@ int snacb_debug_chain_spans(int C, int16_t* out, int cap) {
                 o[0] = sp[l][w][k].r_first; o[1] = sp[l][w][k].n_oct; o[2] = sp[l][w][k].kc;
             }
     return chain_tile_rows(C) | (chain_warps(C) << 16);
+}
+
+int snacb_debug_chain_ws_spans(int C, int16_t* out, int cap) {
+    if (!out || !chain_ws_supported(C, 1) || cap < 3 * kChainWarps * kChainSpans * 3) return SNACB_ERR_ARG;
+    ChainSpan sp[3][kChainWarps][kChainSpans];
+    chain_ws_build_spans(C, sp);
+    for (int l = 0; l < 3; ++l)
+        for (int w = 0; w < kChainWarps; ++w)
+            for (int k = 0; k < kChainSpans; ++k) {
+                int16_t* o = out + ((l * kChainWarps + w) * kChainSpans + k) * 3;
+                o[0] = sp[l][w][k].r_first; o[1] = sp[l][w][k].n_oct; o[2] = sp[l][w][k].kc;
+            }
+    return chain_ws_tile_rows(C) | (kChainWsP << 16);
 }
 
 int snacb_debug_tap_count(snacb_handle h) { return h ? static_cast<int>(h->taps.size()) : SNACB_ERR_ARG; }
