@@ -141,6 +141,88 @@ def cpu_port_rate(batch: int, reps: int, threads: int, state_dict=None):
     return batch * WINDOW_SAMPLES / SR / dt, dt
 
 
+def gpu_torch_baseline():
+    """The reference-equivalent PyTorch module (oracle restatement of snac.SNAC.decode: eager torch, cuDNN convs,
+    weight-norm recomputed per forward, TF32 defaults, cudnn.benchmark=True as init_snac sets it,
+    modal_audio_stream.py:116) on THIS GPU, protocol of tensorrt_tts/hindi_finetuned/benchmark.py:219-247: the timer
+    spans torch.tensor(list) -> clamp -> decode -> synchronize.  The closest stand-in for the reference's own GPU
+    numbers (the pip package / checkpoint cannot be installed here).  Reported beside the headline, never inside it."""
+    import torch
+    from oracle import glue_ref, synth_ckpt
+    from tts_inference_b200 import synth
+    torch.backends.cudnn.benchmark = True
+    model = synth_ckpt.make_model(0).cuda().eval()
+    out = {"what": "oracle restatement of the reference's PyTorch SNAC decoder, eager fp32/TF32 on this GPU, cudnn.benchmark, "
+                   "timer = tensor build + clamp + decode + sync (benchmark.py:219-247); 5 warm-up + 20 timed, median"}
+
+    def run(batch, frames):
+        codes = synth.make_tokens(batch, frames).astype(np.int64) - 128266
+        lv = [x.tolist() for x in glue_ref.unpack_np(codes)]
+
+        def once():
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            ct = [torch.tensor(l, dtype=torch.int32, device="cuda") for l in lv]
+            ct = [torch.clamp(c, 0, 4095) for c in ct]
+            with torch.inference_mode():
+                model.decode(ct)
+            torch.cuda.synchronize()
+            return time.perf_counter() - t0
+        for _ in range(5):
+            once()
+        ts = sorted(once() for _ in range(20))
+        med = ts[len(ts) // 2]
+        return {"ms": med * 1e3, "audio_s_per_s": batch * frames * 2048 / SR / med}
+    out["b1_window"] = run(1, 4)            # what convert_to_audio does per call: one stream, one 28-token window
+    out["b64_windows"] = run(64, 4)         # batching the reference never does, for scale
+    out["b1_utterance_512_frames"] = run(1, 512)
+    del model
+    torch.cuda.empty_cache()
+    return out
+
+
+def extra_configs(dec, args, world, max_over_ranks):
+    """BASELINE.json configs 1, 3 and 4 (config 2 is the headline, config 5 the latency block).  CUDA-event times, max over
+    ranks; every rank works on its own streams (no collective)."""
+    import torch
+    from tts_inference_b200 import synth
+    rank = int(os.environ.get("RANK", "0"))
+    res = {}
+
+    def timed(fn, reps, warm=2):
+        for i in range(warm):
+            fn(i)
+        torch.cuda.synchronize()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+        for i in range(reps):
+            ev[i][0].record(); fn(100 + i); ev[i][1].record()
+        torch.cuda.synchronize()
+        ts = sorted(a.elapsed_time(b) for a, b in ev)
+        return max_over_ranks(ts[len(ts) // 2], device="cuda")
+    # config 1: one 28-token window, batch 1, fp32 CUDA-core path
+    t1 = torch.from_numpy(synth.make_tokens(1, FRAMES, seed=20241224 + rank)).cuda()
+    o1 = torch.empty((1, WINDOW_SAMPLES), dtype=torch.int16, device="cuda")
+    ms = timed(lambda i: dec.decode(t1, raw_ids=True, seed=i, precision="fp32", out=o1), 30, 3)
+    res["config1_b1_window_fp32"] = {"ms": ms, "audio_s_per_s": WINDOW_SAMPLES / SR / (ms * 1e-3)}
+    # config 3: full utterances, 64 streams x F frames (512 frames = 43.7 s of audio per stream)
+    sweep = {}
+    for F in (16, 64, 512):
+        tk = torch.from_numpy(synth.make_tokens(64, F, seed=20241224 + rank)).cuda()
+        ok = torch.empty((64, 2048 * F), dtype=torch.int16, device="cuda")
+        ms = timed(lambda i: dec.decode(tk, raw_ids=True, seed=i, precision=args.precision, out=ok), 3 if F == 512 else 5, 1)
+        sweep[str(F)] = {"ms": ms, "audio_s_per_s": world * 64 * F * 2048 / SR / (ms * 1e-3)}
+        del tk, ok
+    res["config3_b64_full_utterance_frames"] = sweep
+    # config 4: Hindi-vocabulary streams (0.5 % out-of-range ids -> clamp), 512 streams per GPU, sliding-window call
+    tk = torch.from_numpy(synth.make_tokens(512, FRAMES, seed=77 + rank, bad_frac=0.005)).cuda()
+    ok = torch.empty((512, 2048), dtype=torch.int16, device="cuda")
+    ms = timed(lambda i: dec.decode(tk, raw_ids=True, seed=i, extract_slice=True, precision=args.precision, out=ok), 10, 3)
+    res["config4_hindi_vocab_512_streams_per_gpu"] = {
+        "streams": 512 * world, "ms": ms, "windows_per_s": world * 512 / (ms * 1e-3),
+        "emitted_audio_s_per_s": world * 512 * 2048 / SR / (ms * 1e-3), "bad_id_fraction": 0.005}
+    return res
+
+
 def run_reference(args, rank: int, world: int):
     """--impl reference: the reference's own CPU implementation of the path = oracle port (the pip
     package `snac` cannot be installed offline), all host threads, bounded sample per step."""
@@ -196,6 +278,7 @@ def main():
     ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-latency", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip BASELINE configs 1/3/4 and the PyTorch-on-GPU baseline")
     ap.add_argument("--profile-out", default=None, help="write the per-stage table here (json)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -321,6 +404,11 @@ def main():
     sl_ms = max_over_ranks(sl_ms, device="cuda")
     sl_e2e_ms = max_over_ranks(sl_e2e_s * 1e3, device="cuda")
 
+    # ------------------------------------------------------------------ BASELINE configs 1 / 3 / 4 (all ranks)
+    extra = None
+    if not args.no_extra:
+        extra = extra_configs(dec, args, world, max_over_ranks)
+
     # ------------------------------------------------------------------ per-stage profile (separate pass)
     prof = None
     if rank == 0:
@@ -410,6 +498,8 @@ def main():
             "roofline": roof,
             "cpu_baseline": cpu,
             "latency_b1_window_ms": latency,
+            "baseline_configs": extra,
+            "gpu_torch_baseline": gpu_torch_baseline() if (world == 1 and not args.no_extra) else None,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

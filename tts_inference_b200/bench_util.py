@@ -70,7 +70,9 @@ def measure_latency(iters=300, precision="fp16", dec=None):
         ts.append((time.perf_counter() - t) * 1e3)
     res["host_ms_e2e"] = {"p50": pct(ts, 50), "p99": pct(ts, 99)}
     res["precision"] = precision
-    res["launches_per_decode"] = 24
+    l0 = dec.stats()[0]
+    dec.decode(tok, raw_ids=True, extract_slice=True, seed=0, precision=precision, out=out)
+    res["launches_per_decode"] = dec.stats()[0] - l0          # counted, not assumed
     return res
 
 

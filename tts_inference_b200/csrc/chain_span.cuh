@@ -75,4 +75,105 @@ __device__ __forceinline__ void dw_snake_bf16(const uint32_t (&xs)[14], const fl
     }
 }
 
+// One span of the in-place prologue inside a 128-row block: rows r_first + k*D (block-relative), k < 4 * nquad, of one
+// 64-channel chunk; lane = channel pair.  `blk` = the block's first row in the chunk plane.  The span may start at any
+// row, so the 128B-swizzle phase of its steps is computed here (ph[k & 7]: 8*D rows further the phase repeats).
+// h0..h2 / t0..t2: the three rows before / after the span, fetched before the block's barrier.
+template <int D, bool FOLD>
+__device__ __forceinline__ void ws_span_half(uint8_t* blk, int r_first, const int nquad, const uint32_t h0, const uint32_t h1,
+                                             const uint32_t h2, const uint32_t t0, const uint32_t t1, const uint32_t t2,
+                                             const uint32_t lane_off, const uint32_t* prm) {
+    const uint4 q0 = *reinterpret_cast<const uint4*>(prm), q1 = *reinterpret_cast<const uint4*>(prm + 4);
+    const __half2 bd = cs_h2(q0.x);
+    const __half2 w[7] = {cs_h2(q0.y), cs_h2(q0.z), cs_h2(q0.w), cs_h2(q1.x), cs_h2(q1.y), cs_h2(q1.z), cs_h2(q1.w)};
+    float2 al2 = make_float2(0.f, 0.f), ia2 = make_float2(0.f, 0.f);
+    if (!FOLD) {
+        const uint4 q2 = *reinterpret_cast<const uint4*>(prm + 8);
+        al2 = make_float2(__uint_as_float(q2.x), __uint_as_float(q2.y));
+        ia2 = make_float2(__uint_as_float(q2.z), __uint_as_float(q2.w));
+    }
+    uint32_t ph[8];
+    const uint32_t p0s = static_cast<uint32_t>(r_first & 7) << 4;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ph[j] = ((p0s + static_cast<uint32_t>(((j * D) & 7) << 4)) & 0x70u) ^ lane_off;
+    uint32_t xs[14];                               // xs[i] = S1 of the class row (i - 3) steps from the octet's first row
+    xs[0] = h0; xs[1] = h1; xs[2] = h2;
+    uint8_t* ob = blk + r_first * 128;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) xs[3 + j] = *reinterpret_cast<const uint32_t*>(ob + j * D * 128 + ph[j]);
+    const int noct = (nquad + 1) >> 1;
+#pragma unroll 1
+    for (int qo = 0; qo < noct; ++qo) {
+        const bool full = nquad - 2 * qo >= 2;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            xs[6 + k] = *reinterpret_cast<const uint32_t*>(ob + (k + 3) * D * 128 + ph[(k + 3) & 7]);
+        if (qo == noct - 1) {
+            if (full) { xs[11] = t0; xs[12] = t1; xs[13] = t2; }
+            else { xs[7] = t0; xs[8] = t1; xs[9] = t2; }
+        }
+        uint32_t o[8];
+        if (full) dw_snake_half<8, FOLD>(xs, w, bd, al2, ia2, o);
+        else dw_snake_half<4, FOLD>(xs, w, bd, al2, ia2, o);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (k == 4 && !full) break;
+            if (r_first + k * D < 128)                      // the last quad of a class may run past the block
+                *reinterpret_cast<uint32_t*>(ob + k * D * 128 + ph[k]) = o[k];
+        }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) xs[i] = xs[8 + i];
+        r_first += 8 * D;
+        ob += 8 * D * 128;
+    }
+}
+
+// same span, fp32 math (bf16 operands)
+template <int D>
+__device__ __forceinline__ void ws_span_bf16(uint8_t* blk, int r_first, const int nquad, const uint32_t h0, const uint32_t h1,
+                                             const uint32_t h2, const uint32_t t0, const uint32_t t1, const uint32_t t2,
+                                             const uint32_t lane_off, const uint32_t* prm) {
+    const float4* p4 = reinterpret_cast<const float4*>(prm);
+    const float4 q0 = p4[0], q1 = p4[1], q2 = p4[2], q3 = p4[3], q4 = p4[4];
+    const float2 w[7] = {make_float2(q0.x, q0.y), make_float2(q0.z, q0.w), make_float2(q1.x, q1.y), make_float2(q1.z, q1.w),
+                         make_float2(q2.x, q2.y), make_float2(q2.z, q2.w), make_float2(q3.x, q3.y)};
+    const float2 bd = make_float2(q3.z, q3.w);
+    const float2 al2 = make_float2(q4.x, q4.y), ia2 = make_float2(q4.z, q4.w);
+    uint32_t ph[8];
+    const uint32_t p0s = static_cast<uint32_t>(r_first & 7) << 4;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ph[j] = ((p0s + static_cast<uint32_t>(((j * D) & 7) << 4)) & 0x70u) ^ lane_off;
+    uint32_t xs[14];
+    xs[0] = h0; xs[1] = h1; xs[2] = h2;
+    uint8_t* ob = blk + r_first * 128;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) xs[3 + j] = *reinterpret_cast<const uint32_t*>(ob + j * D * 128 + ph[j]);
+    const int noct = (nquad + 1) >> 1;
+#pragma unroll 1
+    for (int qo = 0; qo < noct; ++qo) {
+        const bool full = nquad - 2 * qo >= 2;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            xs[6 + k] = *reinterpret_cast<const uint32_t*>(ob + (k + 3) * D * 128 + ph[(k + 3) & 7]);
+        if (qo == noct - 1) {
+            if (full) { xs[11] = t0; xs[12] = t1; xs[13] = t2; }
+            else { xs[7] = t0; xs[8] = t1; xs[9] = t2; }
+        }
+        uint32_t o[8];
+        if (full) dw_snake_bf16<8>(xs, w, bd, al2, ia2, o);
+        else dw_snake_bf16<4>(xs, w, bd, al2, ia2, o);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (k == 4 && !full) break;
+            if (r_first + k * D < 128)
+                *reinterpret_cast<uint32_t*>(ob + k * D * 128 + ph[k]) = o[k];
+        }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) xs[i] = xs[8 + i];
+        r_first += 8 * D;
+        ob += 8 * D * 128;
+    }
+}
+
+
 }  // namespace snacb
