@@ -132,6 +132,46 @@ int snacb_decode_range(snacb_handle h, const int32_t* tok, int B, int tok_stride
                        const float* const* noise, uint64_t seed, const int32_t* stream_keys, int sample_lo, int sample_hi,
                        int16_t* pcm, float* wave, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Stateful streaming session: incremental decode of growing streams with per-stream,
+ * per-stage state kept in HBM, for the streaming policies the reference documents (re-decode of the whole prefix every
+ * N frames with lookahead, tensorrt_tts/PIPELINE_REPORT.md:475-511; sliding 28/7 windows,
+ * vllm_inference/modal_audio_stream.py:86-95, 352-396).  A step that adds k frames to a stream computes, in every
+ * stage, only the rows that became FINAL with them (their whole receptive field lies inside the known tokens) and emits
+ * the samples that became final: 4k latent steps of work, no recompute of the prefix, and -- the NoiseBlock noise being
+ * keyed by (seed, block, stream key, t) -- the concatenated output is BIT-IDENTICAL to one snacb_decode_keyed of the
+ * finished stream.  Non-final samples lag the newest token by the decoder's receptive field (2.3 frames = 4757 samples), not by a
+ * fixed 5-frame lookahead.
+ *   n_slots, max_frames   capacity: every slot can hold a stream of up to max_frames frames (rounded up to a multiple
+ *                         of 32); activations are kept for the whole stream, ~1.45 MB per frame per slot
+ *                         (snacb_session_bytes).  flags: SNACB_RAW_IDS, SNACB_BF16.
+ *   snacb_session_step    appends new_frames frames (new_tok [n][tok_stride] int32, device) to slots
+ *                         [slot0, slot0 + n), which must all hold the same number of frames, and writes each slot's newly
+ *                         final samples to pcm [n][pcm_stride] (device int16); *n_emitted = samples per slot (the same
+ *                         for all n; snacb_session_next_emit tells it in advance).  final != 0 ends the streams: everything
+ *                         up to 2048 * frames is emitted (the last receptive field sees the true end's zero padding and is
+ *                         decoded by one stateless ranged decode of the stored tokens) and the slots need
+ *                         snacb_session_reset before reuse.  stream_keys [n] (device) as in snacb_decode_keyed; NULL =
+ *                         the slot index.  Asynchronous on `stream`.
+ * --------------------------------------------------------------------------------------------- */
+typedef struct snacb_session_s* snacb_session;
+int snacb_session_create(snacb_handle h, int n_slots, int max_frames, int flags, snacb_session* out);
+void snacb_session_destroy(snacb_session s);
+int64_t snacb_session_bytes(snacb_session s);
+int snacb_session_max_frames(snacb_session s);
+int snacb_session_reset(snacb_session s, int slot0, int n);
+int snacb_session_frames(snacb_session s, int slot);
+int snacb_session_emitted(snacb_session s, int slot);
+int snacb_session_next_emit(snacb_session s, int slot, int new_frames, int final);
+int snacb_session_step(snacb_session s, int slot0, int n, const int32_t* new_tok, int tok_stride, int new_frames, int final,
+                       uint64_t seed, const int32_t* stream_keys, int16_t* pcm, int pcm_stride, int* n_emitted,
+                       void* stream);
+/* Host-side frontier table of a session (no GPU needed): the number of FINAL rows of every stage once `frames` frames are
+ * known, snac_24khz strides 8/8/4/2; bit bi of chain_mask = block bi runs the fused chain kernel.  out (>= 22 ints):
+ * stem, then per block {ConvTranspose out, NoiseBlock out, ResidualUnit 0/1/2 out} (the last three 0 for a chain block
+ * except res2 = the block output), then the emitted samples.  Returns the number of ints written. */
+int snacb_debug_session_frontier(int frames, int chain_mask, int32_t* out, int cap);
+
 /* Same with HOST buffers (pinned or pageable): copies the tokens in, decodes, copies the PCM out and
  * synchronises -- the boundary the reference's helper has (torch.tensor(..., device=) in,
  * .cpu().numpy().tobytes() out; modal_audio_stream.py:176-202). */

@@ -1,7 +1,8 @@
 """Cost of the lookahead streaming policy (tts_inference_b200/policy.py; tensorrt_tts/PIPELINE_REPORT.md:475-511) for B
 streams of F frames, a decode every `chunk` new frames, 5 frames of lookahead -- CUDA-event time of all decode calls:
   (a) the reference's algorithm: re-decode ALL frames every time;   (b) snacb_decode_range: new stable samples only;
-  (c) one batch decode of the finished utterances (lower bound).
+  (c) the stateful session (snacb_session_step): per-stage state in HBM, only newly final rows are computed;
+  (d) one batch decode of the finished utterances (lower bound).
 
     python tests/gpu_lookahead_bench.py [B] [F] [chunk] > gpurun_out/lookahead_bench.json
 """
@@ -48,7 +49,26 @@ def main():
             outs.append(o)
         return ms, torch.cat(outs, dim=1)
 
-    run("range"); run("full")                                   # warm-up (workspace growth)
+    sess = dec.open_session(B, F)
+
+    def run_stateful():
+        """the stateful session: every step appends `chunk` frames and emits what became final; no prefix is re-read"""
+        sess.reset()
+        ms, outs, f0 = 0.0, [], 0
+        steps = list(range(chunk, F + 1, chunk)) + ([F] if F % chunk else [])
+        for i, f in enumerate(steps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t = tok[:, 7 * f0:7 * f].contiguous()
+            a.record()
+            o = sess.step(0, t, final=(i == len(steps) - 1), seed=2, stream_keys=keys)
+            b.record()
+            torch.cuda.synchronize()
+            ms += a.elapsed_time(b)
+            outs.append(o); f0 = f
+        return ms, torch.cat(outs, dim=1), len(steps)
+
+    run("range"); run("full"); run_stateful()                   # warm-up (workspace growth)
+    ms_state, pcm_state, n_state = run_stateful()
     ms_full, pcm_full = run("full")
     ms_range, pcm_range = run("range")
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -59,10 +79,12 @@ def main():
     audio_s = B * F * 2048 / 24000.0
     print(json.dumps({
         "streams": B, "frames": F, "frames_per_chunk": chunk, "lookahead_frames": 5, "decode_calls": len(sched),
-        "redecode_all_ms": ms_full, "ranged_ms": ms_range, "one_batch_decode_ms": ms_batch,
+        "redecode_all_ms": ms_full, "ranged_ms": ms_range, "stateful_session_ms": ms_state, "one_batch_decode_ms": ms_batch,
+        "stateful_session_steps": n_state, "stateful_session_bytes": sess.nbytes,
         "audio_s_per_s": {"redecode_all": audio_s / ms_full * 1e3, "ranged": audio_s / ms_range * 1e3,
-                          "one_batch_decode": audio_s / ms_batch * 1e3},
-        "streamed_equals_batch_decode": bool(torch.equal(pcm_range, batch) and torch.equal(pcm_full, batch)),
+                          "stateful_session": audio_s / ms_state * 1e3, "one_batch_decode": audio_s / ms_batch * 1e3},
+        "streamed_equals_batch_decode": bool(torch.equal(pcm_range, batch) and torch.equal(pcm_full, batch)
+                                             and torch.equal(pcm_state, batch)),
     }, indent=1))
 
 

@@ -29,6 +29,23 @@ def run():
     return a.elapsed_time(b)
 
 
+sess = dec.open_session(B, F)
+steps = list(range(chunk, F + 1, chunk)) + ([F] if F % chunk else [])
+stoks = [tok[:, 7 * (f - chunk if f % chunk == 0 else f - f % chunk):7 * f].contiguous() for f in steps]
+
+
+def run_stateful():
+    sess.reset()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for i, t in enumerate(stoks):
+        sess.step(0, t, final=(i == len(stoks) - 1), seed=2, stream_keys=keys)
+    b.record(); torch.cuda.synchronize()
+    return a.elapsed_time(b)
+
+
+if len(sys.argv) > 4 and sys.argv[4] == "stateful":
+    run = run_stateful
 run(); run()
 ms = run()
 dec.profile(True)

@@ -228,3 +228,73 @@ def test_cuda_graph_replay_is_bit_identical(decoder):
     g.replay()
     torch.cuda.synchronize()
     assert torch.equal(out, ref)
+
+
+# ------------------------------------------------------------------ stateful streaming session
+@pytest.mark.parametrize("precision,chunks", [("fp16", [4] * 6), ("fp16", [1, 3, 7, 2, 5, 6]), ("fp16", [24]), ("bf16", [4, 8, 12])])
+def test_session_stream_is_bit_identical_to_batch_decode(decoder, precision, chunks):
+    """Frames appended step by step to a session: each stage computes only the rows that became final, and the
+    concatenated samples equal ONE keyed batch decode of the finished streams bit for bit."""
+    F = sum(chunks)
+    B = 3
+    tokens = synth.make_tokens(B, F, seed=31)
+    tok = torch.from_numpy(tokens).cuda()
+    keys = torch.tensor([5, 11, 2], dtype=torch.int32).cuda()
+    ref = decoder.decode(tok, raw_ids=True, seed=9, precision=precision, stream_keys=keys).cpu().numpy()
+    sess = decoder.open_session(B + 2, F, precision=precision)
+    assert sess.max_frames >= F and sess.nbytes > 0
+    got, f0 = [], 0
+    l0 = decoder.stats()[0]
+    for i, k in enumerate(chunks):
+        last = i == len(chunks) - 1
+        if last:                                           # end of stream as a separate, token-less step
+            got.append(sess.step(1, tok[:, 7 * f0: 7 * (f0 + k)], seed=9, stream_keys=keys).cpu().numpy())
+            got.append(sess.step(1, tok[:, :0], final=True, seed=9, stream_keys=keys).cpu().numpy())
+        else:
+            got.append(sess.step(1, tok[:, 7 * f0: 7 * (f0 + k)], seed=9, stream_keys=keys).cpu().numpy())
+        f0 += k
+        assert sess.frames(1) == f0 and sess.frames(0) == 0
+    cat = np.concatenate(got, axis=1)
+    assert cat.shape == ref.shape
+    assert np.array_equal(cat, ref)
+    assert sess.emitted(2) == 2048 * F
+    assert decoder.stats()[0] > l0
+    with pytest.raises(Exception):                         # finished slots need a reset
+        sess.step(1, tok[:, :7], seed=9)
+    sess.reset(1, B)
+    again = [sess.step(1, tok[:, :7 * F], final=True, seed=9, stream_keys=keys).cpu().numpy()]
+    assert np.array_equal(again[0], ref)
+    sess.close()
+
+
+def test_session_default_keys_are_slot_indices_and_steps_cost_new_rows_only(decoder):
+    """Without stream keys a slot's noise is keyed by its slot index whichever slots share its step; non-final steps emit
+    what snacb_session_next_emit announces (the receptive-field lag, 2.3 frames); slots at different positions are refused."""
+    F = 16
+    tokens = synth.make_tokens(4, F, seed=4)
+    tok = torch.from_numpy(tokens).cuda()
+    ref = decoder.decode(tok, raw_ids=True, seed=1, stream_keys=torch.arange(4, dtype=torch.int32).cuda()).cpu().numpy()
+    sess = decoder.open_session(4, F)
+    outs = {s: [] for s in range(4)}
+    # slots 0-1 run ahead of slots 2-3
+    outs01 = sess.step(0, tok[:2, :7 * 8], seed=1).cpu().numpy()
+    assert outs01.shape[1] == sess.emitted(0) and 2048 * 5.5 < outs01.shape[1] < 2048 * 6
+    for s in (0, 1):
+        outs[s].append(outs01[s])
+    with pytest.raises(Exception):
+        sess.step(0, tok[:, 7 * 8: 7 * 12], seed=1)                      # slots 0-1 hold 8 frames, slots 2-3 none
+    o = sess.step(2, tok[2:, :7 * 8], seed=1).cpu().numpy()
+    for s in (2, 3):
+        outs[s].append(o[s - 2])
+    n = sess.next_emit(0, 8, final=True)
+    o = sess.step(0, tok[:, 7 * 8:], final=True, seed=1).cpu().numpy()      # all four together from here
+    assert o.shape[1] == n
+    for s in range(4):
+        outs[s].append(o[s])
+        assert np.array_equal(np.concatenate(outs[s]), ref[s]), s
+    with pytest.raises(Exception):
+        small = decoder.open_session(1, 8)                                # holds 32 frames (rounded up)
+        for _ in range(3):
+            small.step(0, tok[:1], seed=1)                                 # 16 + 16 + 16 frames
+    with pytest.raises(ValueError):
+        decoder.open_session(1, 8, precision="fp32")

@@ -494,3 +494,56 @@ def test_ws_chain_protocol():
             steps += 1
             assert steps < 2_000_000, f"deadlock (seed {seed}, {n_tiles} tiles)"
         assert len(log["store"]) == n_tiles * NB
+
+
+@pytest.mark.parametrize("chain_mask", [0b1110, 0b1100, 0b0000])
+def test_session_frontier_table(chain_mask):
+    """snacb_session_step's frontier (rows of every stage that are final once F frames are known) against a brute-force
+    dependency walk over the decoder's layers: stem depthwise k7, ConvTranspose1d (k = 2s, stride s, padding s/2: output t
+    reads inputs floor((t + s/2) / s) and the one before), NoiseBlock 1x1, ResidualUnits with dilations 1/3/9 (k7),
+    tail conv k7.  Frontiers must be monotone in F and everything final with F frames must stay final with more."""
+    import ctypes as C
+    from tts_inference_b200 import _lib
+    lib = _lib.load()
+    strides = [8, 8, 4, 2]
+
+    def brute(F):
+        L = 4 * F
+
+        def first_invalid(pred, hi):
+            t = 0
+            while t < hi and pred(t):
+                t += 1
+            return t
+        rows = []
+        v = first_invalid(lambda t: t + 3 < L, L + 8)
+        rows.append(v)
+        for bi, s in enumerate(strides):
+            vin = v
+            # whole input rows m: both rows an output phase of m may read, m - 1 .. m + 1, must be final
+            y = first_invalid(lambda t: (t + s // 2) // s < vin and t // s + 1 < vin, (vin + 2) * s)
+            nz = y
+            r0 = first_invalid(lambda t: t + 3 < nz, nz + 1)
+            r1 = first_invalid(lambda t: t + 9 < r0, r0 + 1)
+            r2 = first_invalid(lambda t: t + 27 < r1, r1 + 1)
+            if chain_mask >> bi & 1:
+                rows += [y, 0, 0, 0, r2]
+            else:
+                rows += [y, nz, r0, r1, r2]
+            v = r2
+        rows.append(first_invalid(lambda t: t + 3 < v, v + 1))
+        return rows
+    prev = None
+    for F in list(range(0, 12)) + [31, 64]:
+        out = (C.c_int32 * 22)()
+        n = lib.snacb_debug_session_frontier(F, chain_mask, out, 22)
+        assert n == 22
+        got = list(out)
+        assert got == brute(F), (F, got, brute(F))
+        if prev is not None:
+            assert all(a <= b for a, b in zip(prev, got))
+        prev = got
+    # the emitted samples lag the newest token by the receptive field only (2.3 frames), not by a 5-frame lookahead
+    out = (C.c_int32 * 22)()
+    lib.snacb_debug_session_frontier(20, chain_mask, out, 22)
+    assert 2048 * 17.4 < out[21] < 2048 * 18

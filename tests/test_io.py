@@ -272,6 +272,36 @@ def test_lookahead_policy_against_batch_decode(decoder):
 
 
 @pytest.mark.gpu
+def test_stateful_policy_against_batch_decode(decoder):
+    """The same streams through the stateful session policy (per-slot, per-stage state in HBM, no re-decode of the
+    prefix): bit-identical to the batch decode, streams of different lengths joining and leaving shared steps, slots
+    reused by later streams."""
+    import torch
+    from tts_inference_b200 import policy, synth
+    lens = [24, 17, 24, 9, 13, 6]
+    starts = [0, 0, 0, 0, 12, 20]                   # the last two streams start later and reuse freed slots
+    tokens = synth.make_tokens(len(lens), 24, seed=9)
+    sd = policy.StatefulStreamingDecoder(decoder, max_streams=4, max_frames=32, frames_per_chunk=4, seed=3)
+    got = [[] for _ in lens]
+    for f in range(40):
+        for s, n in enumerate(lens):
+            g = f - starts[s]
+            if 0 <= g < n:
+                sd.push(s, tokens[s, 7 * g: 7 * g + 7].tolist())
+            elif g == n:
+                sd.finish(s)
+        for s, pcm in sd.step():
+            got[s].append(pcm)
+    for s, n in enumerate(lens):
+        key = torch.tensor([s], dtype=torch.int32).cuda()
+        ref = decoder.decode(torch.from_numpy(np.ascontiguousarray(tokens[s:s + 1, :7 * n])).cuda(), raw_ids=True, seed=3,
+                             stream_keys=key).cpu().numpy()[0]
+        cat = np.concatenate(got[s])
+        assert cat.size == 2048 * n, (s, cat.size)
+        assert np.array_equal(cat, ref), s
+
+
+@pytest.mark.gpu
 def test_device_ingest_flush_only_step_and_many_slots():
     """A step that carries no ids at all (n_tok = 0) but finishes streams flushes their remainders; 5000 slots."""
     import torch

@@ -5,6 +5,6 @@ behind a C ABI (include/snacb.h): token window -> SNAC codes -> VQ decode -> con
 int16 PCM.  ``compat`` mirrors the reference's helper names; ``api.SnacDecoder`` is the batched
 device-tensor interface; ``batcher.WindowBatcher`` packs many streams into one launch.
 """
-from .api import SnacDecoder, SnacbError  # noqa: F401
+from .api import SnacDecoder, SnacbError, StreamingSession  # noqa: F401
 
-__all__ = ["SnacDecoder", "SnacbError"]
+__all__ = ["SnacDecoder", "SnacbError", "StreamingSession"]

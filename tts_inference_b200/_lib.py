@@ -41,6 +41,9 @@ EXPORTS = [
     "snacb_batcher_flush", "snacb_batcher_pending", "snacb_batcher_forget", "snacb_batcher_flush_submit", "snacb_batcher_flush_wait", "snacb_batcher_take",
     "snacb_ingest_create", "snacb_ingest_destroy", "snacb_ingest_reset", "snacb_ingest_window_capacity",
     "snacb_ingest_step", "snacb_ingest_state", "snacb_base64_len", "snacb_pcm_to_base64", "snacb_pcm_to_wav",
+    "snacb_session_create", "snacb_session_destroy", "snacb_session_bytes", "snacb_session_max_frames", "snacb_session_reset",
+    "snacb_session_frames", "snacb_session_emitted", "snacb_session_next_emit", "snacb_session_step",
+    "snacb_debug_session_frontier",
 ]
 
 _lib = None
@@ -103,6 +106,19 @@ def load() -> C.CDLL:
     lib.snacb_base64_len.restype = C.c_longlong
     lib.snacb_pcm_to_base64.argtypes = [i16p, C.c_longlong, C.c_longlong, vp, vp]
     lib.snacb_pcm_to_wav.argtypes = [i16p, C.c_longlong, C.c_longlong, C.c_int, vp, vp]
+    lib.snacb_session_create.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
+    lib.snacb_session_destroy.argtypes = [vp]
+    lib.snacb_session_destroy.restype = None
+    lib.snacb_session_bytes.argtypes = [vp]
+    lib.snacb_session_bytes.restype = C.c_int64
+    lib.snacb_session_max_frames.argtypes = [vp]
+    lib.snacb_session_reset.argtypes = [vp, C.c_int, C.c_int]
+    lib.snacb_session_frames.argtypes = [vp, C.c_int]
+    lib.snacb_session_emitted.argtypes = [vp, C.c_int]
+    lib.snacb_session_next_emit.argtypes = [vp, C.c_int, C.c_int, C.c_int]
+    lib.snacb_session_step.argtypes = [vp, C.c_int, C.c_int, i32p, C.c_int, C.c_int, C.c_int, u64, i32p, i16p, C.c_int,
+                                       C.POINTER(C.c_int), vp]
+    lib.snacb_debug_session_frontier.argtypes = [C.c_int, C.c_int, i32p, C.c_int]
     _lib = lib
     return lib
 

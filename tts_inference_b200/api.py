@@ -201,6 +201,11 @@ class SnacDecoder:
     def wait_host(self):
         self._check(self._lib.snacb_decode_host_wait(self._h), "snacb_decode_host_wait")
 
+    # ------------------------------------------------------------------ stateful streaming
+    def open_session(self, n_slots: int, max_frames: int, *, raw_ids: bool = True, precision: str = "fp16") -> "StreamingSession":
+        """Incremental decode of growing streams with per-slot, per-stage state in HBM (include/snacb.h, snacb_session_*)."""
+        return StreamingSession(self, n_slots, max_frames, raw_ids=raw_ids, precision=precision)
+
     # ------------------------------------------------------------------ per-stage timing
     def profile(self, enable: bool = True):
         self._check(self._lib.snacb_profile(self._h, 1 if enable else 0), "snacb_profile")
@@ -226,4 +231,79 @@ class SnacDecoder:
             a = np.empty((rows.value, cols.value), dtype=np.float32)
             self._check(self._lib.snacb_debug_tap_copy(self._h, i, a.ctypes.data, a.size), "tap_copy")
             out[name.value.decode()] = a
+        return out
+
+
+class StreamingSession:
+    """``snacb_session``: slots 0..n_slots-1 each hold one growing stream; ``step`` appends frames to a contiguous range of
+    slots that are at the same position and returns the samples that became final -- no recompute of the prefix, and the
+    concatenation of all steps of a slot equals ``SnacDecoder.decode(..., stream_keys=key)`` of the finished stream bit for
+    bit (tests/test_gpu_api.py)."""
+
+    def __init__(self, decoder: SnacDecoder, n_slots: int, max_frames: int, *, raw_ids: bool = True, precision: str = "fp16"):
+        if precision not in ("fp16", "bf16"):
+            raise ValueError("a session runs the tensor-core path: precision 'fp16' or 'bf16'")
+        self._dec, self._lib = decoder, decoder._lib
+        self._s = C.c_void_p()
+        flags = (_lib.RAW_IDS if raw_ids else 0) | (_lib.BF16 if precision == "bf16" else 0)
+        rc = self._lib.snacb_session_create(decoder._h, int(n_slots), int(max_frames), flags, C.byref(self._s))
+        decoder._check(rc, "snacb_session_create")
+        self.n_slots = int(n_slots)
+        self.max_frames = int(self._lib.snacb_session_max_frames(self._s))
+
+    def close(self):
+        if getattr(self, "_s", None) is not None and self._s.value:
+            self._lib.snacb_session_destroy(self._s)
+            self._s = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def nbytes(self) -> int:
+        return int(self._lib.snacb_session_bytes(self._s))
+
+    def frames(self, slot: int) -> int:
+        return int(self._lib.snacb_session_frames(self._s, int(slot)))
+
+    def emitted(self, slot: int) -> int:
+        return int(self._lib.snacb_session_emitted(self._s, int(slot)))
+
+    def reset(self, slot0: int = 0, n: Optional[int] = None):
+        n = self.n_slots - slot0 if n is None else n
+        self._dec._check(self._lib.snacb_session_reset(self._s, int(slot0), int(n)), "snacb_session_reset")
+
+    def next_emit(self, slot: int, new_frames: int, final: bool = False) -> int:
+        r = int(self._lib.snacb_session_next_emit(self._s, int(slot), int(new_frames), 1 if final else 0))
+        if r < 0:
+            raise SnacbError(f"snacb_session_next_emit failed ({r})")
+        return r
+
+    def step(self, slot0: int, new_tokens, *, final: bool = False, seed: int = 0, stream_keys=None, out=None):
+        """new_tokens: cuda int32 [n, 7k] (k >= 0 new frames for slots slot0 .. slot0+n-1; k = 0 only with ``final``).
+        Returns int16 [n, m]: the m samples per slot that became final (m may be 0)."""
+        import torch
+        assert new_tokens.is_cuda and new_tokens.dtype == torch.int32 and new_tokens.dim() == 2
+        new_tokens = new_tokens.contiguous()
+        n, w = new_tokens.shape
+        k = w // FRAME
+        m = self.next_emit(slot0, k, final)
+        if out is None:
+            out = torch.empty((n, m), dtype=torch.int16, device=new_tokens.device)
+        else:
+            assert out.is_cuda and out.dtype == torch.int16 and out.is_contiguous() and out.shape == (n, m)
+        keys = None
+        if stream_keys is not None:
+            assert stream_keys.is_cuda and stream_keys.dtype == torch.int32 and stream_keys.numel() == n
+            stream_keys = stream_keys.contiguous()
+            keys = stream_keys.data_ptr()
+        got = C.c_int(0)
+        rc = self._lib.snacb_session_step(self._s, int(slot0), n, new_tokens.data_ptr() if w else None, w, k, 1 if final else 0,
+                                          C.c_uint64(seed), keys, out.data_ptr() if m else None, m, C.byref(got),
+                                          self._dec._stream_ptr())
+        self._dec._check(rc, "snacb_session_step")
+        assert got.value == m, (got.value, m)
         return out

@@ -366,9 +366,28 @@ int chain_ws_prof_report(snacb_handle h, const ChainArgs& ca, int bi, cudaStream
 // ------------------------------------------------------------------------------------------------
 // One group of S streams through the whole path.
 // ------------------------------------------------------------------------------------------------
+struct Rng { int lo, hi; };
+
+// A stateful streaming step (snacb_session_step): every stage writes to its OWN persistent buffer in absolute row
+// coordinates and processes only the rows that became computable since the previous step, [lo, hi) per stage; the rows
+// below lo are read back from the same buffers (they were final when written).  nullptr = the stateless decode.
+struct SessionPlan {
+    int32_t *c0, *c1, *c2;   // unpacked codes [S][Fmax], [S][2 Fmax], [S][4 Fmax]
+    void* a0;                // stem depthwise output [S][4 Fmax][768]
+    void* stem;              // stem 1x1 (+ Snake) output
+    void* ct[4];             // ConvTranspose outputs
+    void* nz[4];             // NoiseBlock outputs (blocks without the fused chain)
+    void* res[4][3];         // ResidualUnit outputs (blocks without the fused chain); [2] is the block output
+    void* out[4];            // block outputs (fused chain)
+    Rng stem_r;              // latent steps of the stem
+    Rng ct_in[4];            // ConvTranspose input rows
+    Rng post[4];             // fused chain: output rows
+    Rng nz_r[4], res_r[4][3];// per-layer rows of the blocks without the fused chain
+};
+
 int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, int flags, const float* const* noise,
               uint64_t seed, int stream_offset, const int32_t* stream_keys, int out_lo, int out_hi, int16_t* pcm,
-              float* wave, cudaStream_t st) {
+              float* wave, cudaStream_t st, const SessionPlan* plan = nullptr) {
     const bool f32 = (flags & SNACB_FP32) != 0;
     const bool xf32 = f32 || (flags & SNACB_STREAM_FP32);      // residual stream dtype
     const int hk = (flags & SNACB_BF16) ? 0 : 1;               // 16-bit operand type: 0 bf16, 1 fp16
@@ -385,9 +404,9 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
         return add_tap(h, name, static_cast<const __half*>(p), rows, cols, st);
     };
 
-    int32_t* c0 = h->ws_codes;
-    int32_t* c1 = c0 + static_cast<size_t>(S) * F;
-    int32_t* c2 = c1 + static_cast<size_t>(S) * 2 * F;
+    int32_t* c0 = plan ? plan->c0 : h->ws_codes;
+    int32_t* c1 = plan ? plan->c1 : c0 + static_cast<size_t>(S) * F;
+    int32_t* c2 = plan ? plan->c2 : c1 + static_cast<size_t>(S) * 2 * F;
     prof_begin(h, "unpack", st);
     launch_unpack(tok, S, tok_stride, F, (flags & SNACB_RAW_IDS) ? 1 : 0, c0, c1, c2, st);
     prof_end(h, st);
@@ -395,10 +414,11 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
     // ---- dead-sample trimming (sliced output): only the rows of each stage inside the receptive field of samples
     //      [out_lo, out_hi) are computed.  Backward range propagation; the stem is always computed in full, block 0 unless
     //      less than half of it is live.
-    struct Rng { int lo, hi; };
     Rng ct_in[4], post[4];                 // ConvTranspose input rows; rows the post-ConvTranspose layers process
     bool trimmed[4] = {false, false, false, false};
-    {
+    if (plan) {
+        for (int bi = 0; bi < 4; ++bi) { trimmed[bi] = true; ct_in[bi] = plan->ct_in[bi]; post[bi] = plan->post[bi]; }
+    } else {
         const int Tfin = 2048 * F;
         // output samples [out_lo, out_hi): the caller's range (snacb_decode_range), the reference's slice, or everything
         if (out_hi <= out_lo) {
@@ -437,21 +457,27 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
 
     prof_begin(h, "vq_stem", st);
     // latent steps the stem has to produce: the input rows of block 0's ConvTranspose (all of them unless block 0 is trimmed)
-    const int stem_lo = trimmed[0] ? ct_in[0].lo : 0, stem_hi = trimmed[0] ? ct_in[0].hi : T0;
-    if (f32) launch_vq_stem<float>(c0, c1, c2, S, F, stem_lo, stem_hi, h->vq, static_cast<float*>(h->ws_a0), st);
-    else if (hk) launch_vq_stem<__half>(c0, c1, c2, S, F, stem_lo, stem_hi, h->vq, static_cast<__half*>(h->ws_a0), st);
-    else launch_vq_stem<__nv_bfloat16>(c0, c1, c2, S, F, stem_lo, stem_hi, h->vq, static_cast<__nv_bfloat16*>(h->ws_a0), st);
+    const int stem_lo = plan ? plan->stem_r.lo : (trimmed[0] ? ct_in[0].lo : 0);
+    const int stem_hi = plan ? plan->stem_r.hi : (trimmed[0] ? ct_in[0].hi : T0);
+    void* const a0 = plan ? plan->a0 : h->ws_a0;
+    const bool stem_live = stem_hi > stem_lo;
+    if (!stem_live) {}
+    else if (f32) launch_vq_stem<float>(c0, c1, c2, S, F, stem_lo, stem_hi, h->vq, static_cast<float*>(a0), st);
+    else if (hk) launch_vq_stem<__half>(c0, c1, c2, S, F, stem_lo, stem_hi, h->vq, static_cast<__half*>(a0), st);
+    else launch_vq_stem<__nv_bfloat16>(c0, c1, c2, S, F, stem_lo, stem_hi, h->vq, static_cast<__nv_bfloat16*>(a0), st);
     prof_end(h, st);
-    h->launches++;
+    if (stem_live) h->launches++;
     CK(h, cudaGetLastError());
     {
-        int rc = tap_any("stem_dw", h->ws_a0, dt_h, (int64_t)S * T0, kLatent);
+        int rc = tap_any("stem_dw", a0, dt_h, (int64_t)S * T0, kLatent);
         if (rc) return rc;
     }
 
-    void* cur = h->ws_buf[0];
-    void* oth = h->ws_buf[1];
+    // stateless decode: two ping-pong activation buffers; session step: one persistent buffer per stage
+    auto other = [&](void* p) -> void* { return p == h->ws_buf[0] ? h->ws_buf[1] : h->ws_buf[0]; };
+    void* cur = plan ? plan->stem : h->ws_buf[0];
     float* P = static_cast<float*>(h->ws_buf[2]);
+    auto live = [](Rng r) { return r.hi > r.lo; };
 
     auto gemm = [&](const char* pname, int epi, bool out_f32, GemmArgs& a, const void* A, const float* Wf,
                     void* const* Wh, int Wrows, int Wcols) -> int {
@@ -494,7 +520,7 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
         a.bias = h->stem_pw_b; a.alpha = h->blk[0].alpha; a.inv_alpha = h->blk[0].inv_alpha;
         if (trimmed[0]) { a.t_lo = stem_lo; a.t_n = stem_hi - stem_lo; }
         a.out = cur;
-        int rc = gemm("stem_pw", EPI_BIAS_SNAKE, false, a, h->ws_a0, h->stem_pw_f32, h->stem_pw_h, kDecDim, kLatent);
+        int rc = stem_live ? gemm("stem_pw", EPI_BIAS_SNAKE, false, a, a0, h->stem_pw_f32, h->stem_pw_h, kDecDim, kLatent) : 0;
         if (rc) return rc;
         rc = tap_any("stem", cur, dt_h, (int64_t)S * T0, kDecDim);
         if (rc) return rc;
@@ -505,8 +531,9 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
     for (int bi = 0; bi < 4; ++bi) {
         BlockW& b = h->blk[bi];
         const int T = Tin * b.s;
+        void* const oth = plan ? plan->ct[bi] : other(cur);
         // ---- ConvTranspose1d as a 2-tap GEMM per output phase: cur [S*Tin][Cin] -> oth [S*T][Cout]
-        {
+        if (!plan || live(ct_in[bi])) {
             GemmArgs a{};
             a.S = S; a.Tin = Tin; a.K = b.Cin; a.N = b.s * b.Cout; a.Cout = b.Cout; a.ntaps = 2; a.up = b.s;
             if (trimmed[bi]) { a.t_lo = ct_in[bi].lo; a.t_n = ct_in[bi].hi - ct_in[bi].lo; }
@@ -553,8 +580,10 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
         // ---- fused NoiseBlock + 3 ResidualUnits + next Snake: oth -> cur, one kernel
         const bool unfused = (flags & SNACB_UNFUSED) != 0 || h->no_chain;
         if (!f32 && !xf32 && !unfused && b.chain[hk]) {
+            void* const ob = plan ? plan->out[bi] : cur;      // ping-pong: back into the ConvTranspose's input buffer
+            if (plan && !live(post[bi])) { cur = ob; Tin = T; continue; }
             ChainArgs ca{};
-            ca.S = S; ca.T = T; ca.C = b.Cout; ca.out = cur;
+            ca.S = S; ca.T = T; ca.C = b.Cout; ca.out = ob;
             if (trimmed[bi]) { ca.t_lo = post[bi].lo; ca.t_n = post[bi].hi - post[bi].lo; }
             for (int ri = 0; ri < 3; ++ri) {
                 const ResW& r = b.res[ri];
@@ -573,9 +602,9 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
             const CUtensorMap* mn;
             int rc = act_map(h, &my, oth, b.Cout, T, S, 128, 1, hk, 1);
             if (rc) return rc;
-            rc = act_map(h, &moe, cur, b.Cout, T, S, 128 - kChainHalo, 1, hk, 1);
+            rc = act_map(h, &moe, ob, b.Cout, T, S, 128 - kChainHalo, 1, hk, 1);
             if (rc) return rc;
-            rc = act_map(h, &mom, cur, b.Cout, T, S, 128, 1, hk, 1);
+            rc = act_map(h, &mom, ob, b.Cout, T, S, 128, 1, hk, 1);
             if (rc) return rc;
             rc = weight_map(h, &mn, b.nz_h[hk], b.Cout, b.Cout, b.Cout, hk);
             if (rc) return rc;
@@ -590,17 +619,20 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
             CK(h, le);
             if (h->chain_prof) { rc = ws ? chain_ws_prof_report(h, ca, bi, st) : chain_prof_report(h, ca, bi, st); if (rc) return rc; }
             h->launches++;
+            cur = ob;
             snprintf(nm, sizeof nm, "b%d.res2", bi);
             rc = tap_any(nm, cur, dt_h, (int64_t)S * T, b.Cout);
             if (rc) return rc;
             Tin = T;
             continue;
         }
-        // ---- NoiseBlock: oth -> cur   x = y + n * (Wn y)
-        {
+        // ---- NoiseBlock: oth -> cur   x = y + n * (Wn y)   (ping-pong: cur is the ConvTranspose's input buffer)
+        if (plan) cur = plan->nz[bi];
+        if (!plan || live(plan->nz_r[bi])) {
             GemmArgs a{};
             a.S = S; a.Tin = T; a.K = b.Cout; a.N = b.Cout; a.Cout = b.Cout; a.ntaps = 1; a.up = 1;
-            if (trimmed[bi]) { a.t_lo = post[bi].lo; a.t_n = post[bi].hi - post[bi].lo; }
+            if (plan) { a.t_lo = plan->nz_r[bi].lo; a.t_n = plan->nz_r[bi].hi - plan->nz_r[bi].lo; }
+            else if (trimmed[bi]) { a.t_lo = post[bi].lo; a.t_n = post[bi].hi - post[bi].lo; }
             a.noise = noise ? noise[bi] : nullptr; a.noise_stage = bi;
             a.resid = oth; a.out = cur;
             snprintf(nm, sizeof nm, "b%d.noise", bi);
@@ -616,10 +648,13 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
             const bool last = (ri == 2);
             const float* an = last ? (bi < 3 ? h->blk[bi + 1].alpha : h->tail_alpha) : nullptr;
             const float* ian = last ? (bi < 3 ? h->blk[bi + 1].inv_alpha : h->tail_inv) : nullptr;
+            void* const ro = plan ? plan->res[bi][ri] : other(cur);
+            if (plan && !live(plan->res_r[bi][ri])) { cur = ro; continue; }
             ResUnitArgs ra{};
             ra.S = S; ra.T = T; ra.C = b.Cout; ra.dil = dils[ri];
-            if (trimmed[bi]) { ra.t_lo = post[bi].lo; ra.t_n = post[bi].hi - post[bi].lo; }
-            ra.x = cur; ra.out = oth;
+            if (plan) { ra.t_lo = plan->res_r[bi][ri].lo; ra.t_n = plan->res_r[bi][ri].hi - plan->res_r[bi][ri].lo; }
+            else if (trimmed[bi]) { ra.t_lo = post[bi].lo; ra.t_n = post[bi].hi - post[bi].lo; }
+            ra.x = cur; ra.out = ro;
             ra.alpha1 = r.alpha1; ra.inv_alpha1 = r.inv1; ra.dw_w = r.dw_w; ra.dw_b = r.dw_b;
             ra.alpha2 = r.alpha2; ra.inv_alpha2 = r.inv2; ra.pw_b = r.pw_b;
             ra.alpha_next = an; ra.inv_alpha_next = ian;
@@ -629,7 +664,7 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
                 launch_respre_f32(ra, P, st);
                 GemmArgs a{};
                 a.S = S; a.Tin = T; a.K = b.Cout; a.N = b.Cout; a.Cout = b.Cout; a.ntaps = 1; a.up = 1;
-                a.bias = r.pw_b; a.alpha = an; a.inv_alpha = ian; a.resid = cur; a.out = oth;
+                a.bias = r.pw_b; a.alpha = an; a.inv_alpha = ian; a.resid = cur; a.out = ro;
                 tile_boxes(a.Tin, &a.Tbox, &a.Wbox);
                 launch_gemm_f32(last ? EPI_RES_SNAKE : EPI_RES, a, P, r.pw_f32, st);
                 prof_end(h, st);
@@ -651,9 +686,9 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
                 CK(h, le);
                 h->launches++;
             }
-            int rc = tap_any(nm, oth, last ? dt_h : dt_x, (int64_t)S * T, b.Cout);
+            int rc = tap_any(nm, ro, last ? dt_h : dt_x, (int64_t)S * T, b.Cout);
             if (rc) return rc;
-            void* t = cur; cur = oth; oth = t;
+            cur = ro;
         }
         Tin = T;
     }
@@ -661,6 +696,7 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
     // ---- tail
     const int T = Tin;                                   // 2048 * F samples
     const int t_begin = out_lo, n_out = out_hi - out_lo;
+    if (plan && n_out <= 0) { h->streams += S; return 0; }
     prof_begin(h, "tail", st);
     if (f32) launch_tail<float>(static_cast<const float*>(cur), S, T, t_begin, n_out, h->tail_w, h->tail_b, pcm, wave, st);
     else if (hk) launch_tail<__half>(static_cast<const __half*>(cur), S, T, t_begin, n_out, h->tail_w, h->tail_b, pcm, wave, st);
@@ -951,6 +987,283 @@ int snacb_decode_range(snacb_handle h, const int32_t* tok, int B, int tok_stride
                            wave ? wave + static_cast<size_t>(g0) * n_out : nullptr, st);
         if (rc) return rc;
     }
+    return SNACB_OK;
+}
+
+// =================================================================================================
+// Stateful streaming session: per-slot, per-stage activations persist in HBM, a step
+// with k new frames computes only the rows that became final with them.
+// =================================================================================================
+}  // extern "C"
+
+struct snacb_session_s {
+    snacb_handle h = nullptr;
+    int n_slots = 0, max_frames = 0, flags = 0;
+    std::vector<int> frames, emitted;         // per slot: frames ingested, samples emitted
+    std::vector<char> finished;
+    int32_t* tok = nullptr;                   // [n_slots][7 * max_frames]
+    int32_t* codes[3] = {nullptr, nullptr, nullptr};
+    int32_t* slot_keys = nullptr;             // [n_slots] = 0, 1, ...: the default NoiseBlock noise key of a slot
+    void* a0 = nullptr;
+    void* stem = nullptr;
+    void* ct[4] = {}; void* nz[4] = {}; void* res[4][3] = {}; void* out[4] = {};
+    std::vector<void*> allocs;
+    size_t bytes = 0;
+};
+
+namespace {
+
+// Rows of every stage that are FINAL once `F` frames of a stream are known (the stream may still grow): a row is final
+// when its whole receptive field lies inside the known latent steps.  Forward propagation through the decoder:
+//   stem depthwise k7:  latent step t needs z_q[t + 3]                          -> [0, 4F - 3)
+//   ConvTranspose (k = 2s, stride s, pad s/2): out row m*s + p reads input rows {m - 1, m} for p < s/2 and {m, m + 1}
+//                       for p >= s/2 (k_gemm_tc base_shift); the kernels work on whole input rows m, so a step
+//                       processes the rows whose successor is final as well     -> [0, (vin - 1) s)
+//                       (k new input rows = k rows of work: whole 128-row tiles, nothing recomputed)
+//   NoiseBlock 1x1: pointwise;  ResidualUnit d: +-3d rows;  fused chain: +-39 rows;  tail conv k7: +-3 samples.
+struct Frontier {
+    int stem, y[4], nz[4], res[4][3], out[4], emit;
+};
+Frontier frontier_calc(int F, const int* strides, int chain_mask) {
+    Frontier f{};
+    auto pos = [](int v) { return v > 0 ? v : 0; };
+    int vin = pos(4 * F - 3);
+    f.stem = vin;
+    for (int bi = 0; bi < 4; ++bi) {
+        const int s = strides[bi];
+        f.y[bi] = vin > 0 ? (vin - 1) * s : 0;
+        if (chain_mask >> bi & 1) {
+            f.nz[bi] = f.res[bi][0] = f.res[bi][1] = 0;
+            f.out[bi] = f.res[bi][2] = pos(f.y[bi] - 39);
+        } else {
+            f.nz[bi] = f.y[bi];
+            f.res[bi][0] = pos(f.nz[bi] - 3);
+            f.res[bi][1] = pos(f.res[bi][0] - 9);
+            f.res[bi][2] = pos(f.res[bi][1] - 27);
+            f.out[bi] = f.res[bi][2];
+        }
+        vin = f.out[bi];
+    }
+    f.emit = pos(f.out[3] - 3);
+    return f;
+}
+Frontier frontier_of(snacb_handle h, int F, int hk) {
+    int strides[4], mask = 0;
+    for (int bi = 0; bi < 4; ++bi) {
+        strides[bi] = h->blk[bi].s;
+        if (h->blk[bi].chain[hk] && !h->no_chain) mask |= 1 << bi;
+    }
+    return frontier_calc(F, strides, mask);
+}
+
+int sess_alloc(snacb_session s, void** p, size_t bytes) {
+    snacb_handle h = s->h;
+    if (cudaMalloc(p, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(h, SNACB_ERR_NOMEM, "snacb_session_create: cudaMalloc of %zu bytes failed", bytes);
+    }
+    s->allocs.push_back(*p);
+    s->bytes += bytes;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int snacb_debug_session_frontier(int frames, int chain_mask, int32_t* out, int cap) {
+    if (frames < 0 || !out || cap < 22) return SNACB_ERR_ARG;
+    static const int strides[4] = {8, 8, 4, 2};
+    const Frontier f = frontier_calc(frames, strides, chain_mask);
+    int k = 0;
+    out[k++] = f.stem;
+    for (int bi = 0; bi < 4; ++bi) {
+        out[k++] = f.y[bi]; out[k++] = f.nz[bi];
+        for (int ri = 0; ri < 3; ++ri) out[k++] = f.res[bi][ri];
+    }
+    out[k++] = f.emit;
+    return k;
+}
+
+int snacb_session_create(snacb_handle h, int n_slots, int max_frames, int flags, snacb_session* out) {
+    if (!h || !out) return SNACB_ERR_ARG;
+    *out = nullptr;
+    if (n_slots < 1 || max_frames < 1 || max_frames > 16384)
+        return fail(h, SNACB_ERR_ARG, "snacb_session_create: bad sizes n_slots=%d max_frames=%d", n_slots, max_frames);
+    if (flags & (SNACB_FP32 | SNACB_STREAM_FP32 | SNACB_KEEP_TAPS | SNACB_EXTRACT_SLICE | SNACB_UNFUSED))
+        return fail(h, SNACB_ERR_ARG, "snacb_session_create: only SNACB_RAW_IDS and SNACB_BF16 apply to a session");
+    CK(h, cudaSetDevice(h->device));
+    snacb_session s = new (std::nothrow) snacb_session_s();
+    if (!s) return SNACB_ERR_NOMEM;
+    s->h = h; s->n_slots = n_slots; s->flags = flags;
+    s->max_frames = (max_frames + 31) / 32 * 32;              // every stage then has >= 128 rows per slot (whole tiles)
+    s->frames.assign(n_slots, 0); s->emitted.assign(n_slots, 0); s->finished.assign(n_slots, 0);
+    const size_t N = static_cast<size_t>(n_slots), Fm = static_cast<size_t>(s->max_frames), T0 = 4 * Fm;
+    const int hk = (flags & SNACB_BF16) ? 0 : 1;
+    int rc = sess_alloc(s, reinterpret_cast<void**>(&s->tok), N * 7 * Fm * sizeof(int32_t));
+    for (int l = 0; l < 3 && !rc; ++l) rc = sess_alloc(s, reinterpret_cast<void**>(&s->codes[l]), N * (Fm << l) * sizeof(int32_t));
+    if (!rc) rc = sess_alloc(s, &s->a0, N * T0 * kLatent * 2);
+    if (!rc) rc = sess_alloc(s, &s->stem, N * T0 * kDecDim * 2);
+    size_t T = T0;
+    for (int bi = 0; bi < 4 && !rc; ++bi) {
+        const BlockW& b = h->blk[bi];
+        T *= b.s;
+        const size_t sz = N * T * b.Cout * 2;
+        rc = sess_alloc(s, &s->ct[bi], sz);
+        if (b.chain[hk] && !h->no_chain) {
+            if (!rc) rc = sess_alloc(s, &s->out[bi], sz);
+        } else {
+            if (!rc) rc = sess_alloc(s, &s->nz[bi], sz);
+            for (int ri = 0; ri < 3 && !rc; ++ri) rc = sess_alloc(s, &s->res[bi][ri], sz);
+            s->out[bi] = s->res[bi][2];
+        }
+    }
+    if (rc) { snacb_session_destroy(s); return rc; }
+    if (!rc) rc = sess_alloc(s, reinterpret_cast<void**>(&s->slot_keys), N * sizeof(int32_t));
+    if (rc) { snacb_session_destroy(s); return rc; }
+    std::vector<int32_t> iota(N);
+    for (size_t i = 0; i < N; ++i) iota[i] = static_cast<int32_t>(i);
+    if (cudaMemset(s->tok, 0, N * 7 * Fm * sizeof(int32_t)) != cudaSuccess ||
+        cudaMemcpy(s->slot_keys, iota.data(), N * sizeof(int32_t), cudaMemcpyHostToDevice) != cudaSuccess) {
+        snacb_session_destroy(s);
+        return fail(h, SNACB_ERR_CUDA, "snacb_session_create: initialising the session buffers failed");
+    }
+    *out = s;
+    return SNACB_OK;
+}
+
+void snacb_session_destroy(snacb_session s) {
+    if (!s) return;
+    cudaSetDevice(s->h->device);
+    cudaDeviceSynchronize();
+    for (void* p : s->allocs) cudaFree(p);
+    s->h->amaps.clear();                                      // maps of the freed buffers
+    delete s;
+}
+
+int64_t snacb_session_bytes(snacb_session s) { return s ? static_cast<int64_t>(s->bytes) : SNACB_ERR_ARG; }
+int snacb_session_max_frames(snacb_session s) { return s ? s->max_frames : SNACB_ERR_ARG; }
+
+int snacb_session_reset(snacb_session s, int slot0, int n) {
+    if (!s) return SNACB_ERR_ARG;
+    if (slot0 < 0 || n < 0 || slot0 + n > s->n_slots) return fail(s->h, SNACB_ERR_ARG, "snacb_session_reset: bad slot range");
+    for (int i = slot0; i < slot0 + n; ++i) { s->frames[i] = 0; s->emitted[i] = 0; s->finished[i] = 0; }
+    return SNACB_OK;
+}
+
+int snacb_session_frames(snacb_session s, int slot) {
+    return (s && slot >= 0 && slot < s->n_slots) ? s->frames[slot] : SNACB_ERR_ARG;
+}
+int snacb_session_emitted(snacb_session s, int slot) {
+    return (s && slot >= 0 && slot < s->n_slots) ? s->emitted[slot] : SNACB_ERR_ARG;
+}
+
+int snacb_session_next_emit(snacb_session s, int slot, int new_frames, int final) {
+    if (!s || slot < 0 || slot >= s->n_slots || new_frames < 0) return SNACB_ERR_ARG;
+    const int F = s->frames[slot] + new_frames;
+    if (F > s->max_frames) return SNACB_ERR_ARG;
+    const int hk = (s->flags & SNACB_BF16) ? 0 : 1;
+    const int end = final ? 2048 * F : frontier_of(s->h, F, hk).emit;
+    return end > s->emitted[slot] ? end - s->emitted[slot] : 0;
+}
+
+int snacb_session_step(snacb_session s, int slot0, int n, const int32_t* new_tok, int tok_stride, int new_frames, int final,
+                       uint64_t seed, const int32_t* stream_keys, int16_t* pcm, int pcm_stride, int* n_emitted,
+                       void* stream) {
+    if (!s) return SNACB_ERR_ARG;
+    snacb_handle h = s->h;
+    if (n_emitted) *n_emitted = 0;
+    if (slot0 < 0 || n < 0 || slot0 + n > s->n_slots || new_frames < 0 || (new_frames > 0 && tok_stride < 7 * new_frames))
+        return fail(h, SNACB_ERR_ARG, "snacb_session_step: bad sizes slot0=%d n=%d new_frames=%d tok_stride=%d", slot0, n, new_frames, tok_stride);
+    if (n == 0) return SNACB_OK;
+    const int Fp = s->frames[slot0], Ep = s->emitted[slot0];
+    for (int i = slot0; i < slot0 + n; ++i) {
+        if (s->finished[i]) return fail(h, SNACB_ERR_STATE, "snacb_session_step: slot %d is finished (snacb_session_reset it)", i);
+        if (s->frames[i] != Fp || s->emitted[i] != Ep)
+            return fail(h, SNACB_ERR_STATE, "snacb_session_step: slots [%d, %d) are not at the same position (slot %d: %d frames, slot %d: %d)",
+                        slot0, slot0 + n, slot0, Fp, i, s->frames[i]);
+    }
+    const int F = Fp + new_frames;
+    if (F > s->max_frames) return fail(h, SNACB_ERR_ARG, "snacb_session_step: %d frames exceed the session's max_frames=%d", F, s->max_frames);
+    if (new_frames > 0 && !new_tok) return fail(h, SNACB_ERR_ARG, "snacb_session_step: null tokens");
+    CK(h, cudaSetDevice(h->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int Fm = s->max_frames;
+    const int hk = (s->flags & SNACB_BF16) ? 0 : 1;
+    const size_t so = static_cast<size_t>(slot0);
+    int32_t* tokp = s->tok + so * 7 * Fm;
+    if (new_frames > 0)
+        CK(h, cudaMemcpy2DAsync(tokp + static_cast<size_t>(7) * Fp, static_cast<size_t>(7) * Fm * sizeof(int32_t), new_tok,
+                                static_cast<size_t>(tok_stride) * sizeof(int32_t), static_cast<size_t>(7) * new_frames * sizeof(int32_t),
+                                n, cudaMemcpyDeviceToDevice, st));
+    const int dflags = s->flags & (SNACB_RAW_IDS | SNACB_BF16);
+    if (!stream_keys) stream_keys = s->slot_keys + slot0;     // a slot draws the same noise whichever slots share its step
+    int n_out = 0;
+    if (final) {
+        // end of stream: the remaining samples see the zero padding at the true end -- one stateless ranged decode of the
+        // stored tokens (exact end semantics, bit-identical to the batch decode; the receptive-field margin is recomputed once)
+        n_out = 2048 * F - Ep;
+        if (n_out > 0) {
+            if (!pcm || pcm_stride < n_out) return fail(h, SNACB_ERR_ARG, "snacb_session_step: pcm_stride %d < %d samples", pcm_stride, n_out);
+            if (pcm_stride == n_out || n == 1) {
+                int rc = snacb_decode_range(h, tokp, n, 7 * Fm, F, dflags, nullptr, seed, stream_keys, Ep, 2048 * F, pcm, nullptr, stream);
+                if (rc) return rc;
+            } else {
+                size_t pb = h->st_pcm_elems * sizeof(int16_t);
+                int rc = grow(h, reinterpret_cast<void**>(&h->st_pcm), &pb, static_cast<size_t>(n) * n_out * sizeof(int16_t));
+                if (rc) return rc;
+                h->st_pcm_elems = pb / sizeof(int16_t);
+                rc = snacb_decode_range(h, tokp, n, 7 * Fm, F, dflags, nullptr, seed, stream_keys, Ep, 2048 * F, h->st_pcm, nullptr, stream);
+                if (rc) return rc;
+                CK(h, cudaMemcpy2DAsync(pcm, static_cast<size_t>(pcm_stride) * 2, h->st_pcm, static_cast<size_t>(n_out) * 2,
+                                        static_cast<size_t>(n_out) * 2, n, cudaMemcpyDeviceToDevice, st));
+            }
+        }
+        for (int i = slot0; i < slot0 + n; ++i) { s->frames[i] = F; s->emitted[i] = 2048 * F; s->finished[i] = 1; }
+        if (n_emitted) *n_emitted = n_out > 0 ? n_out : 0;
+        return SNACB_OK;
+    }
+    if (new_frames == 0) return SNACB_OK;
+    const Frontier a = frontier_of(h, Fp, hk), b = frontier_of(h, F, hk);
+    SessionPlan pl{};
+    pl.c0 = s->codes[0] + so * Fm; pl.c1 = s->codes[1] + so * 2 * Fm; pl.c2 = s->codes[2] + so * 4 * Fm;
+    size_t T = 4 * static_cast<size_t>(Fm);
+    pl.a0 = static_cast<char*>(s->a0) + so * T * kLatent * 2;
+    pl.stem = static_cast<char*>(s->stem) + so * T * kDecDim * 2;
+    pl.stem_r = Rng{a.stem, b.stem};
+    int vin_a = a.stem, vin_b = b.stem;
+    for (int bi = 0; bi < 4; ++bi) {
+        const BlockW& bw = h->blk[bi];
+        T *= bw.s;
+        const size_t off = so * T * bw.Cout * 2;
+        auto at = [&](void* p) -> void* { return p ? static_cast<char*>(p) + off : nullptr; };
+        pl.ct[bi] = at(s->ct[bi]); pl.nz[bi] = at(s->nz[bi]); pl.out[bi] = at(s->out[bi]);
+        for (int ri = 0; ri < 3; ++ri) pl.res[bi][ri] = at(s->res[bi][ri]);
+        // input rows whose successor is final too (the upper output phases of row m read row m + 1)
+        pl.ct_in[bi] = Rng{vin_a > 0 ? vin_a - 1 : 0, vin_b > 0 ? vin_b - 1 : 0};
+        pl.post[bi] = Rng{a.out[bi], b.out[bi]};
+        pl.nz_r[bi] = Rng{a.nz[bi], b.nz[bi]};
+        for (int ri = 0; ri < 3; ++ri) pl.res_r[bi][ri] = Rng{a.res[bi][ri], b.res[bi][ri]};
+        vin_a = a.out[bi]; vin_b = b.out[bi];
+    }
+    n_out = b.emit - Ep;
+    if (n_out < 0) n_out = 0;
+    if (n_out > 0 && (!pcm || pcm_stride < n_out)) return fail(h, SNACB_ERR_ARG, "snacb_session_step: pcm_stride %d < %d samples", pcm_stride, n_out);
+    int16_t* dst = pcm;
+    if (n_out > 0 && pcm_stride != n_out && n > 1) {
+        size_t pb = h->st_pcm_elems * sizeof(int16_t);
+        int rc = grow(h, reinterpret_cast<void**>(&h->st_pcm), &pb, static_cast<size_t>(n) * n_out * sizeof(int16_t));
+        if (rc) return rc;
+        h->st_pcm_elems = pb / sizeof(int16_t);
+        dst = h->st_pcm;
+    }
+    int rc = run_group(h, tokp, n, 7 * Fm, Fm, dflags, nullptr, seed, 0, stream_keys, Ep, Ep + n_out, dst, nullptr, st, &pl);
+    if (rc) return rc;
+    if (dst != pcm)
+        CK(h, cudaMemcpy2DAsync(pcm, static_cast<size_t>(pcm_stride) * 2, dst, static_cast<size_t>(n_out) * 2,
+                                static_cast<size_t>(n_out) * 2, n, cudaMemcpyDeviceToDevice, st));
+    for (int i = slot0; i < slot0 + n; ++i) { s->frames[i] = F; s->emitted[i] = Ep + n_out; }
+    if (n_emitted) *n_emitted = n_out;
     return SNACB_OK;
 }
 

@@ -106,3 +106,84 @@ class LookaheadStreamingDecoder:
         for key in [k for k, st in self._streams.items() if st.done]:
             del self._streams[key]
         return out
+
+
+class StatefulStreamingDecoder:
+    """The same policy interface (push / finish / step) on the stateful session (``snacb_session_*``,
+    SURVEY.md section 8(f) row 1): every stream owns a slot whose per-stage activations stay in HBM, a step appends the
+    new whole frames and gets back exactly the samples that became final -- the prefix is neither re-read nor re-decoded.
+    Emission differs from ``LookaheadStreamingDecoder`` only in WHEN samples appear: here as soon as their receptive field
+    is inside the known tokens (a lag of 2.3 frames = 4757 samples) instead of after a fixed 5-frame lookahead; the bytes are the same
+    (both equal the batch decode of the finished stream, tests/test_io.py).  Streams that are due with the same
+    (frames held, frames to add, finished) and sit in neighbouring slots share one batched step."""
+
+    def __init__(self, decoder, max_streams: int, max_frames: int, frames_per_chunk: int = 4, raw_ids: bool = True,
+                 precision: str = "fp16", seed: int = 0):
+        if frames_per_chunk < 1:
+            raise ValueError("frames_per_chunk >= 1")
+        self._dec = decoder
+        self._sess = decoder.open_session(max_streams, max_frames, raw_ids=raw_ids, precision=precision)
+        self.frames_per_chunk, self.seed = int(frames_per_chunk), int(seed)
+        self._streams: Dict[Hashable, _Stream] = {}
+        self._slot: Dict[Hashable, int] = {}
+        self._free = list(range(max_streams - 1, -1, -1))
+        self._next_key = 0
+
+    @property
+    def session(self):
+        return self._sess
+
+    def push(self, stream: Hashable, ids: Iterable[int]) -> None:
+        st = self._streams.get(stream)
+        if st is None:
+            if not self._free:
+                raise RuntimeError("no free slot: max_streams streams are active")
+            st = self._streams[stream] = _Stream(self._next_key)
+            self._next_key = (self._next_key + 1) & 0x7FFFFFFF
+            self._slot[stream] = self._free.pop()
+        if st.done:
+            raise ValueError(f"stream {stream!r} already finished")
+        st.ids.extend(int(i) for i in ids)
+
+    def finish(self, stream: Hashable) -> None:
+        if stream in self._streams:
+            self._streams[stream].done = True
+
+    def step(self) -> List[Tuple[Hashable, np.ndarray]]:
+        import torch
+        due: Dict[Tuple[int, int, bool], List[Tuple[int, Hashable]]] = {}
+        for key, st in self._streams.items():
+            frames = min(len(st.ids) // FRAME, self._sess.max_frames)
+            new = frames - st.decoded_frames
+            if (st.done and (new > 0 or st.emitted < SAMPLES_PER_FRAME * frames)) or new >= self.frames_per_chunk:
+                due.setdefault((st.decoded_frames, new, st.done), []).append((self._slot[key], key))
+        out: List[Tuple[Hashable, np.ndarray]] = []
+        for (have, new, final), members in sorted(due.items(), key=lambda kv: kv[0]):
+            members.sort()
+            runs, run = [], [members[0]]
+            for m in members[1:]:
+                if m[0] == run[-1][0] + 1:
+                    run.append(m)
+                else:
+                    runs.append(run); run = [m]
+            runs.append(run)
+            for run in runs:
+                keys = [k for _, k in run]
+                tok = np.asarray([self._streams[k].ids[have * FRAME:(have + new) * FRAME] for k in keys], dtype=np.int64)
+                tok = np.clip(tok.reshape(len(keys), new * FRAME), -(2 ** 31), 2 ** 31 - 1).astype(np.int32)
+                nkeys = torch.tensor([self._streams[k].key for k in keys], dtype=torch.int32).cuda(self._dec.device)
+                pcm = self._sess.step(run[0][0], torch.from_numpy(tok).cuda(self._dec.device), final=final, seed=self.seed,
+                                      stream_keys=nkeys)
+                host = pcm.cpu().numpy()
+                for row, k in enumerate(keys):
+                    st = self._streams[k]
+                    st.decoded_frames = have + new
+                    st.emitted += host.shape[1]
+                    if host.shape[1]:
+                        out.append((k, host[row]))
+        for key in [k for k, st in self._streams.items() if st.done and st.decoded_frames >= min(len(st.ids) // FRAME, self._sess.max_frames)]:
+            slot = self._slot.pop(key)
+            self._sess.reset(slot, 1)
+            self._free.append(slot)
+            del self._streams[key]
+        return out
