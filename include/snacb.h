@@ -232,6 +232,51 @@ int snacb_debug_chain_spans(int C, int16_t* out, int cap);
 int snacb_debug_chain_ws_spans(int C, int16_t* out, int cap);
 
 /* ---------------------------------------------------------------------------------------------
+ * SNAC ENCODE path: audio -> codes, the other half of the codec.  The reference never
+ * calls it at inference (it only decodes); upstream it is snac.SNAC.encode = preprocess (right-pad to a multiple of
+ * 2048 samples) -> Encoder (conv k7 1 -> 48; 4 EncoderBlocks: 3 ResidualUnits d = 1/3/9, Snake, strided conv k = 2s,
+ * s = 2/4/8/8, width doubling to 768; depthwise conv k7) -> ResidualVectorQuantize (3 levels, strides 4/2/1: avg-pool,
+ * in_proj 768 -> 8, nearest L2-normalised code of 4096, residual -= out_proj(code)).  fp32 CUDA-core kernels
+ * (csrc/encoder.cu): the codes are an argmax, so the latent has to track the fp32 reference.  Oracle:
+ * oracle/snac_enc_ref.py.  Weight-norm folded, PyTorch layouts, host pointers.
+ * --------------------------------------------------------------------------------------------- */
+typedef struct snacb_encoder_s* snacb_encoder;
+typedef struct {
+    const float* alpha;    /* [C]            EncoderBlock.block.3 Snake alpha (C = block input width)   */
+    const float* conv_w;   /* [2C][C][2s]    EncoderBlock.block.4 strided conv                         */
+    const float* conv_b;   /* [2C]                                                                     */
+    snacb_resunit_weights res[3];   /* EncoderBlock.block.0..2, width C, dilations 1, 3, 9            */
+} snacb_encblock_weights;
+typedef struct {
+    const float* conv0_w;        /* [48][1][7]    encoder.block.0                                      */
+    const float* conv0_b;        /* [48]                                                               */
+    snacb_encblock_weights block[4];   /* encoder.block.1..4: 48 -> 96 s2, -> 192 s4, -> 384 s8, -> 768 s8 */
+    const float* final_w;        /* [768][1][7]   encoder.block.5 (depthwise)                          */
+    const float* final_b;        /* [768]                                                              */
+    const float* in_proj_w[3];   /* [8][768][1]   quantizer.quantizers.i.in_proj                       */
+    const float* in_proj_b[3];   /* [8]                                                                */
+    const float* codebook[3];    /* [4096][8]                                                          */
+    const float* out_proj_w[3];  /* [768][8][1]                                                        */
+    const float* out_proj_b[3];  /* [768]                                                              */
+} snacb_encoder_weights;
+int snacb_encoder_create(snacb_encoder* out, const snacb_encoder_weights* w, int device);
+void snacb_encoder_destroy(snacb_encoder e);
+const char* snacb_encoder_last_error(snacb_encoder e);   /* e may be NULL: error of the last failed create */
+uint64_t snacb_encoder_launches(snacb_encoder e);
+/* Frames (= codes of level 0) that n_samples of audio encode to: ceil(n / 2048). */
+int snacb_encode_frames(int n_samples);
+/* audio float [B][audio_stride] (device), the first n_samples of each row are used, right-padded with zeros to
+ * F = snacb_encode_frames(n_samples) frames.  c0 [B][F], c1 [B][2F], c2 [B][4F] int32.  Optional outputs (tests):
+ * latent [B][4F][768] = the encoder output z (channel-last), best_dist [B][F + 2F + 4F] = winning distance per code,
+ * level by level.  Asynchronous on `stream`. */
+int snacb_encode(snacb_encoder e, const float* audio, int B, int n_samples, int audio_stride, int32_t* c0, int32_t* c1,
+                 int32_t* c2, float* latent, float* best_dist, void* stream);
+/* codes -> the 7 token ids per frame the LLM vocabulary uses (inverse of snacb_unpack; modal_audio_stream.py:156-188):
+ * tok [B][7 * frames] = code + 4096 * position (+ 128266 with SNACB_RAW_IDS). */
+int snacb_pack_tokens(const int32_t* c0, const int32_t* c1, const int32_t* c2, int B, int frames, int flags, int32_t* tok,
+                      void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Batcher: the multi-stream replacement of stream_audio's per-stream buffer policy
  * (modal_audio_stream.py:352-396), which decodes one stream at a time under a global lock.
  * Many producers push token ids; flush() packs every ready window of every stream into ONE decode.

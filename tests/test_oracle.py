@@ -188,3 +188,50 @@ def test_convert_to_audio_restatement(oracle_model):
     assert glue_ref.convert_to_audio(oracle_model, codes[:6]) is None
     l0, l1, l2 = glue_ref.unpack_trt(codes)
     assert glue_ref.decode_snac(oracle_model, l0, l1, l2, nz) == full
+
+
+# ------------------------------------------------------------------ encode half
+def _enc_oracle(seed=0):
+    from oracle.snac_enc_ref import SnacEncodeRef
+    from tts_inference_b200 import synth
+    sd = synth.make_encoder_state_dict(seed)
+    m = SnacEncodeRef().eval()
+    m.load_snac_state_dict({k: torch.from_numpy(np.ascontiguousarray(v).copy()) for k, v in sd.items()})
+    return m, sd
+
+
+def test_encoder_oracle_structure_and_consistency(oracle_model):
+    """The encode restatement: total parameter count of snac_24khz (encoder + quantizer + decoder = 19.8 M),
+    output shapes of SNAC.encode incl. preprocess()'s right padding, and z_q of the quantiser's forward pass equal to
+    from_codes(codes) of the DECODE oracle (the two halves share codebooks and out_proj)."""
+    from oracle.snac_enc_ref import SnacEncodeRef
+    from tts_inference_b200 import synth
+    m, sd = _enc_oracle()
+    n_enc = sum(p.numel() for p in m.encoder.parameters())
+    n_q = sum(p.numel() for p in m.quantizers.parameters())
+    n_dec = sum(p.numel() for p in oracle_model.decoder.parameters())
+    assert (n_enc, n_q, n_dec) == (6690672, 139824, 13012418) and n_enc + n_q + n_dec == 19842914
+    audio = torch.from_numpy(synth.make_audio(2, 2048 * 3 - 700))[:, None, :]
+    taps = {}
+    codes = m.encode(audio, taps)
+    assert [tuple(c.shape) for c in codes] == [(2, 3), (2, 6), (2, 12)]
+    assert all(int(c.min()) >= 0 and int(c.max()) < 4096 for c in codes)
+    assert taps["z"].shape == (2, 768, 12) and 0.3 < float(taps["z"].std()) < 3.0
+    with torch.inference_mode():
+        z_q = oracle_model.quantizer.from_codes(codes)
+    assert torch.allclose(z_q, taps["z_q"], atol=1e-5)
+    # the padded tail is zeros: encoding the explicitly padded signal gives the same codes
+    padded = SnacEncodeRef.preprocess(audio)
+    assert padded.shape[-1] == 2048 * 3 and all(torch.equal(a, b) for a, b in zip(codes, m.encode(padded)))
+
+
+def test_encoder_fold_matches_weight_norm():
+    from tts_inference_b200.weights import fold_encoder_state_dict
+    m, sd = _enc_oracle()
+    f = fold_encoder_state_dict(sd)
+    conv = m.encoder.block[2].block[4]                         # strided conv of the second EncoderBlock: g * v / ||v||
+    w = torch._weight_norm(conv.weight_v, conv.weight_g, 0)
+    assert np.allclose(f["enc.b1.conv_w"], w.detach().numpy(), atol=1e-6)
+    ip = m.quantizers[2].in_proj
+    assert np.allclose(f["in_proj_w2"], torch._weight_norm(ip.weight_v, ip.weight_g, 0).detach().numpy(), atol=1e-6)
+    assert f["enc.final_w"].shape == (768, 1, 7) and f["enc.b3.conv_w"].shape == (768, 384, 16)

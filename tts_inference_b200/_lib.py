@@ -33,6 +33,17 @@ class Weights(C.Structure):
     ]
 
 
+class EncBlockWeights(C.Structure):
+    _fields_ = [("alpha", _FP), ("conv_w", _FP), ("conv_b", _FP), ("res", ResUnitWeights * 3)]
+
+
+class EncoderWeights(C.Structure):
+    _fields_ = [
+        ("conv0_w", _FP), ("conv0_b", _FP), ("block", EncBlockWeights * 4), ("final_w", _FP), ("final_b", _FP),
+        ("in_proj_w", _FP * 3), ("in_proj_b", _FP * 3), ("codebook", _FP * 3), ("out_proj_w", _FP * 3), ("out_proj_b", _FP * 3),
+    ]
+
+
 EXPORTS = [
     "snacb_version", "snacb_create", "snacb_destroy", "snacb_last_error", "snacb_unpack", "snacb_decode", "snacb_decode_keyed", "snacb_decode_range",
     "snacb_decode_host", "snacb_decode_host_submit", "snacb_decode_host_wait", "snacb_samples_out", "snacb_set_group_bytes", "snacb_stats",
@@ -44,6 +55,8 @@ EXPORTS = [
     "snacb_session_create", "snacb_session_destroy", "snacb_session_bytes", "snacb_session_max_frames", "snacb_session_reset",
     "snacb_session_frames", "snacb_session_emitted", "snacb_session_next_emit", "snacb_session_step",
     "snacb_debug_session_frontier",
+    "snacb_encoder_create", "snacb_encoder_destroy", "snacb_encoder_last_error", "snacb_encoder_launches", "snacb_encode_frames",
+    "snacb_encode", "snacb_pack_tokens",
 ]
 
 _lib = None
@@ -119,6 +132,16 @@ def load() -> C.CDLL:
     lib.snacb_session_step.argtypes = [vp, C.c_int, C.c_int, i32p, C.c_int, C.c_int, C.c_int, u64, i32p, i16p, C.c_int,
                                        C.POINTER(C.c_int), vp]
     lib.snacb_debug_session_frontier.argtypes = [C.c_int, C.c_int, i32p, C.c_int]
+    lib.snacb_encoder_create.argtypes = [C.POINTER(vp), C.POINTER(EncoderWeights), C.c_int]
+    lib.snacb_encoder_destroy.argtypes = [vp]
+    lib.snacb_encoder_destroy.restype = None
+    lib.snacb_encoder_last_error.argtypes = [vp]
+    lib.snacb_encoder_last_error.restype = C.c_char_p
+    lib.snacb_encoder_launches.argtypes = [vp]
+    lib.snacb_encoder_launches.restype = C.c_uint64
+    lib.snacb_encode_frames.argtypes = [C.c_int]
+    lib.snacb_encode.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, i32p, i32p, i32p, vp, vp, vp]
+    lib.snacb_pack_tokens.argtypes = [i32p, i32p, i32p, C.c_int, C.c_int, C.c_int, i32p, vp]
     _lib = lib
     return lib
 
@@ -144,4 +167,25 @@ def make_weights(folded: Dict[str, np.ndarray]):
             for n in ("alpha1", "dw_w", "dw_b", "alpha2", "pw_w", "pw_b"):
                 setattr(r, n, p(f"b{bi}.r{ri}.{n}"))
     w.tail_alpha, w.tail_w, w.tail_b = p("tail_alpha"), p("tail_w"), p("tail_b")
+    return w
+
+
+def make_encoder_weights(folded: Dict[str, np.ndarray]):
+    """``snacb_encoder_weights`` struct pointing into ``folded`` (weights.fold_encoder_state_dict)."""
+    def p(k):
+        a = folded[k]
+        assert a.dtype == np.float32 and a.flags["C_CONTIGUOUS"], k
+        return a.ctypes.data_as(_FP)
+    w = EncoderWeights()
+    w.conv0_w, w.conv0_b = p("enc.conv0_w"), p("enc.conv0_b")
+    for bi in range(4):
+        b = w.block[bi]
+        b.alpha, b.conv_w, b.conv_b = p(f"enc.b{bi}.alpha"), p(f"enc.b{bi}.conv_w"), p(f"enc.b{bi}.conv_b")
+        for ri in range(3):
+            for n in ("alpha1", "dw_w", "dw_b", "alpha2", "pw_w", "pw_b"):
+                setattr(b.res[ri], n, p(f"enc.b{bi}.r{ri}.{n}"))
+    w.final_w, w.final_b = p("enc.final_w"), p("enc.final_b")
+    for i in range(3):
+        w.in_proj_w[i], w.in_proj_b[i] = p(f"in_proj_w{i}"), p(f"in_proj_b{i}")
+        w.codebook[i], w.out_proj_w[i], w.out_proj_b[i] = p(f"codebook{i}"), p(f"out_proj_w{i}"), p(f"out_proj_b{i}")
     return w

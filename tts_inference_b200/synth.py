@@ -166,6 +166,64 @@ def make_state_dict(seed: int = 0, gains: Optional[Dict[str, float]] = None, alp
     return sd
 
 
+def _encoder_layer_table():
+    """(prefix, kind, shape_v, gain) of every weight-normed conv of the ENCODE half, forward order."""
+    rows = [("encoder.block.0", "conv0", (48, 1, 7), 3.0)]
+    c = 48
+    for bi, s in enumerate((2, 4, 8, 8)):
+        p = f"encoder.block.{1 + bi}.block"
+        for ri in range(3):
+            rows.append((f"{p}.{ri}.block.1", "dw", (c, 1, 7), 1.0))
+            rows.append((f"{p}.{ri}.block.3", "pw", (c, c, 1), 0.3))
+        rows.append((f"{p}.4", "down", (2 * c, c, 2 * s), 0.8))
+        c *= 2
+    rows.append(("encoder.block.5", "dw", (768, 1, 7), 1.0))
+    for i in range(3):
+        rows.append((f"quantizer.quantizers.{i}.in_proj", "pw", (8, 768, 1), 1.0))
+    return rows
+
+
+def make_encoder_state_dict(seed: int = 0) -> Dict[str, "np.ndarray"]:
+    """Synthetic ENCODE-half state dict (upstream key names: ``encoder.block.*``, ``quantizer.quantizers.i.in_proj``) on top
+    of the decode checkpoint of the same seed, whose codebooks and out_proj the quantizer shares: one dict that
+    ``weights.fold_encoder_state_dict`` and ``weights.fold_state_dict`` both accept.  Fan-in scaled weights with fixed
+    per-kind gains; activations stay O(1) through the stack (oracle/snac_enc_ref.py, tests/test_oracle.py)."""
+    sd = make_state_dict(seed)
+    for prefix, kind, shape, gain in _encoder_layer_table():
+        n = int(np.prod(shape))
+        v = rng_normal(seed, _sid(prefix + ".v"), n).reshape(shape) / np.sqrt(shape[1] * shape[2])
+        norm = np.sqrt((v.reshape(shape[0], -1) ** 2).sum(axis=1))
+        jitter = 0.5 + rng_uniform(seed, _sid(prefix + ".g"), shape[0])
+        sd[prefix + ".weight_v"] = v.astype(np.float32)
+        sd[prefix + ".weight_g"] = (gain * norm * jitter).reshape(shape[0], 1, 1).astype(np.float32)
+        sd[prefix + ".bias"] = (0.1 * rng_normal(seed, _sid(prefix + ".b"), shape[0])).astype(np.float32)
+    c = 48
+    for bi in range(4):
+        p = f"encoder.block.{1 + bi}.block"
+        for ri in range(3):
+            for j in (0, 2):
+                k = f"{p}.{ri}.block.{j}.alpha"
+                sd[k] = _alphas(seed, k, c, "benign").reshape(1, c, 1).astype(np.float32)
+        k = f"{p}.3.alpha"
+        sd[k] = _alphas(seed, k, c, "benign").reshape(1, c, 1).astype(np.float32)
+        c *= 2
+    return sd
+
+
+def make_audio(batch: int, n_samples: int, seed: int = 5) -> np.ndarray:
+    """Synthetic audio float32 [B, n] in [-1, 1]: a few decaying sinusoids plus noise per row."""
+    t = np.arange(n_samples, dtype=np.float64) / 24000.0
+    out = np.empty((batch, n_samples), dtype=np.float32)
+    for b in range(batch):
+        u = rng_uniform(seed, 900 + b, 12)
+        x = 0.05 * rng_normal(seed, 1000 + b, n_samples)
+        for k in range(4):
+            f0 = 80.0 * (1.0 + 40.0 * u[3 * k]) 
+            x = x + (0.1 + 0.3 * u[3 * k + 1]) * np.sin(2 * np.pi * f0 * t + 6.28 * u[3 * k + 2])
+        out[b] = np.clip(x * 0.5, -1.0, 1.0).astype(np.float32)
+    return out
+
+
 # ----------------------------------------------------------------------------------------
 # inputs
 # ----------------------------------------------------------------------------------------

@@ -90,6 +90,47 @@ def fold_state_dict(sd: Mapping[str, object]) -> Dict[str, np.ndarray]:
     return out
 
 
+ENCODER_RATES = (2, 4, 8, 8)
+
+
+def fold_encoder_state_dict(sd: Mapping[str, object]) -> Dict[str, np.ndarray]:
+    """Encode half of the checkpoint (``encoder.block.*`` and the quantizers' in_proj / codebook / out_proj), folded, keyed
+    by the field names of ``snacb_encoder_weights`` (include/snacb.h)."""
+    out: Dict[str, np.ndarray] = {}
+    out["enc.conv0_w"] = _weight(sd, "encoder.block.0")
+    out["enc.conv0_b"] = _vec(sd, "encoder.block.0.bias")
+    assert out["enc.conv0_w"].shape == (48, 1, 7)
+    c = 48
+    for bi, s in enumerate(ENCODER_RATES):
+        p = f"encoder.block.{1 + bi}.block"
+        for ri in range(3):
+            q = f"{p}.{ri}.block"
+            out[f"enc.b{bi}.r{ri}.alpha1"] = _vec(sd, q + ".0.alpha")
+            out[f"enc.b{bi}.r{ri}.dw_w"] = _weight(sd, q + ".1")
+            out[f"enc.b{bi}.r{ri}.dw_b"] = _vec(sd, q + ".1.bias")
+            out[f"enc.b{bi}.r{ri}.alpha2"] = _vec(sd, q + ".2.alpha")
+            out[f"enc.b{bi}.r{ri}.pw_w"] = _weight(sd, q + ".3")
+            out[f"enc.b{bi}.r{ri}.pw_b"] = _vec(sd, q + ".3.bias")
+            assert out[f"enc.b{bi}.r{ri}.dw_w"].shape == (c, 1, 7) and out[f"enc.b{bi}.r{ri}.pw_w"].shape == (c, c, 1)
+        out[f"enc.b{bi}.alpha"] = _vec(sd, p + ".3.alpha")
+        out[f"enc.b{bi}.conv_w"] = _weight(sd, p + ".4")
+        out[f"enc.b{bi}.conv_b"] = _vec(sd, p + ".4.bias")
+        assert out[f"enc.b{bi}.conv_w"].shape == (2 * c, c, 2 * s), out[f"enc.b{bi}.conv_w"].shape
+        c *= 2
+    out["enc.final_w"] = _weight(sd, "encoder.block.5")
+    out["enc.final_b"] = _vec(sd, "encoder.block.5.bias")
+    assert out["enc.final_w"].shape == (768, 1, 7)
+    for i in range(3):
+        q = f"quantizer.quantizers.{i}"
+        out[f"in_proj_w{i}"] = _weight(sd, q + ".in_proj")
+        out[f"in_proj_b{i}"] = _vec(sd, q + ".in_proj.bias")
+        out[f"codebook{i}"] = np.ascontiguousarray(_np(sd[q + ".codebook.weight"]).astype(np.float32))
+        out[f"out_proj_w{i}"] = _weight(sd, q + ".out_proj")
+        out[f"out_proj_b{i}"] = _vec(sd, q + ".out_proj.bias")
+        assert out[f"in_proj_w{i}"].shape == (8, 768, 1) and out[f"codebook{i}"].shape == (4096, 8)
+    return out
+
+
 CKPT_ENV = "SNACB_CKPT"            # path of pytorch_model.bin (or its directory) used when init_snac() gets no argument
 CACHE_ENV = "SNACB_CACHE_DIR"      # where folded weights are cached (default ~/.cache/snacb); "" disables the cache
 _FOLD_VERSION = 1                  # bump when fold_state_dict's output changes
