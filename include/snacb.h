@@ -142,26 +142,29 @@ int snacb_decode_range(snacb_handle h, const int32_t* tok, int B, int tok_stride
  * keyed by (seed, block, stream key, t) -- the concatenated output is BIT-IDENTICAL to one snacb_decode_keyed of the
  * finished stream.  Non-final samples lag the newest token by the decoder's receptive field (2.3 frames = 4757 samples), not by a
  * fixed 5-frame lookahead.
- *   n_slots, max_frames   capacity: every slot can hold a stream of up to max_frames frames (rounded up to a multiple
- *                         of 32); activations are kept for the whole stream, ~1.45 MB per frame per slot
- *                         (snacb_session_bytes).  flags: SNACB_RAW_IDS, SNACB_BF16.
+ *   n_slots, window_frames  every slot keeps a SLIDING WINDOW of its stream's activations: window_frames frames (rounded
+ *                         up to a multiple of 32; ~1.45 MB per frame per slot, snacb_session_bytes).  When a step does
+ *                         not fit, the window keeps its last 8 frames (more than the deepest stage's lag plus every
+ *                         stage's halo), moves them to the front and goes on: streams are UNBOUNDED in length, memory is
+ *                         per window.  A step may add at most window_frames - 16 frames to a non-empty window.
+ *                         flags: SNACB_RAW_IDS, SNACB_BF16.
  *   snacb_session_step    appends new_frames frames (new_tok [n][tok_stride] int32, device) to slots
- *                         [slot0, slot0 + n), which must all hold the same number of frames, and writes each slot's newly
+ *                         [slot0, slot0 + n), which must all be at the same position, and writes each slot's newly
  *                         final samples to pcm [n][pcm_stride] (device int16); *n_emitted = samples per slot (the same
  *                         for all n; snacb_session_next_emit tells it in advance).  final != 0 ends the streams: everything
  *                         up to 2048 * frames is emitted (the last receptive field sees the true end's zero padding and is
- *                         decoded by one stateless ranged decode of the stored tokens) and the slots need
+ *                         decoded by one stateless ranged decode of the window's tokens) and the slots need
  *                         snacb_session_reset before reuse.  stream_keys [n] (device) as in snacb_decode_keyed; NULL =
  *                         the slot index.  Asynchronous on `stream`.
  * --------------------------------------------------------------------------------------------- */
 typedef struct snacb_session_s* snacb_session;
-int snacb_session_create(snacb_handle h, int n_slots, int max_frames, int flags, snacb_session* out);
+int snacb_session_create(snacb_handle h, int n_slots, int window_frames, int flags, snacb_session* out);
 void snacb_session_destroy(snacb_session s);
 int64_t snacb_session_bytes(snacb_session s);
-int snacb_session_max_frames(snacb_session s);
+int snacb_session_max_frames(snacb_session s);               /* the window, in frames (after rounding) */
 int snacb_session_reset(snacb_session s, int slot0, int n);
-int snacb_session_frames(snacb_session s, int slot);
-int snacb_session_emitted(snacb_session s, int slot);
+int64_t snacb_session_frames(snacb_session s, int slot);     /* frames ingested so far (whole stream) */
+int64_t snacb_session_emitted(snacb_session s, int slot);    /* samples emitted so far (whole stream) */
 int snacb_session_next_emit(snacb_session s, int slot, int new_frames, int final);
 int snacb_session_step(snacb_session s, int slot0, int n, const int32_t* new_tok, int tok_stride, int new_frames, int final,
                        uint64_t seed, const int32_t* stream_keys, int16_t* pcm, int pcm_stride, int* n_emitted,

@@ -49,7 +49,7 @@ def main():
             outs.append(o)
         return ms, torch.cat(outs, dim=1)
 
-    sess = dec.open_session(B, F)
+    sess = dec.open_session(B, 32)                                # 32-frame sliding window per stream, whatever F is
 
     def run_stateful():
         """the stateful session: every step appends `chunk` frames and emits what became final; no prefix is re-read"""

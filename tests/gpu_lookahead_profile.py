@@ -29,7 +29,7 @@ def run():
     return a.elapsed_time(b)
 
 
-sess = dec.open_session(B, F)
+sess = dec.open_session(B, 32)
 steps = list(range(chunk, F + 1, chunk)) + ([F] if F % chunk else [])
 stoks = [tok[:, 7 * (f - chunk if f % chunk == 0 else f - f % chunk):7 * f].contiguous() for f in steps]
 

@@ -292,9 +292,36 @@ def test_session_default_keys_are_slot_indices_and_steps_cost_new_rows_only(deco
     for s in range(4):
         outs[s].append(o[s])
         assert np.array_equal(np.concatenate(outs[s]), ref[s]), s
+    big = torch.from_numpy(synth.make_tokens(1, 40, seed=4)).cuda()
+    small = decoder.open_session(1, 8)                                    # window of 32 frames (rounded up)
     with pytest.raises(Exception):
-        small = decoder.open_session(1, 8)                                # holds 32 frames (rounded up)
-        for _ in range(3):
-            small.step(0, tok[:1], seed=1)                                 # 16 + 16 + 16 frames
+        small.step(0, big, seed=1)                                         # 40 frames at once do not fit the window
+    small.step(0, big[:, :7 * 30], seed=1)
+    with pytest.raises(Exception):
+        small.step(0, big[:, :7 * 25], seed=1)                             # nor do 25 more: the window keeps 8 frames, 8 + 25 > 32
     with pytest.raises(ValueError):
         decoder.open_session(1, 8, precision="fp32")
+
+
+@pytest.mark.parametrize("chunk", [4, 16, 7])
+def test_session_window_slides_over_a_long_stream(decoder, chunk):
+    """A stream much longer than the session's window (100 frames through 32): the window keeps its last 8 frames and
+    moves them to the front whenever a step does not fit; the NoiseBlock noise stays keyed by the absolute time step.  The
+    stream is still bit-identical to one batch decode, and the session's memory does not grow."""
+    F, B = 100, 2
+    tokens = synth.make_tokens(B, F, seed=77)
+    tok = torch.from_numpy(tokens).cuda()
+    keys = torch.tensor([3, 9], dtype=torch.int32).cuda()
+    ref = decoder.decode(tok, raw_ids=True, seed=4, stream_keys=keys).cpu().numpy()
+    sess = decoder.open_session(B, 32)
+    nbytes = sess.nbytes
+    got, f0 = [], 0
+    while f0 < F:
+        k = min(chunk, F - f0)
+        got.append(sess.step(0, tok[:, 7 * f0: 7 * (f0 + k)], final=(f0 + k == F), seed=4, stream_keys=keys).cpu().numpy())
+        f0 += k
+        assert sess.frames(0) == f0
+    cat = np.concatenate(got, axis=1)
+    assert cat.shape == ref.shape and np.array_equal(cat, ref)
+    assert sess.emitted(1) == 2048 * F and sess.nbytes == nbytes
+    sess.close()

@@ -281,7 +281,7 @@ def test_stateful_policy_against_batch_decode(decoder):
     lens = [24, 17, 24, 9, 13, 6]
     starts = [0, 0, 0, 0, 12, 20]                   # the last two streams start later and reuse freed slots
     tokens = synth.make_tokens(len(lens), 24, seed=9)
-    sd = policy.StatefulStreamingDecoder(decoder, max_streams=4, max_frames=32, frames_per_chunk=4, seed=3)
+    sd = policy.StatefulStreamingDecoder(decoder, max_streams=4, window_frames=32, frames_per_chunk=4, seed=3)
     got = [[] for _ in lens]
     for f in range(40):
         for s, n in enumerate(lens):

@@ -127,7 +127,9 @@ def load() -> C.CDLL:
     lib.snacb_session_max_frames.argtypes = [vp]
     lib.snacb_session_reset.argtypes = [vp, C.c_int, C.c_int]
     lib.snacb_session_frames.argtypes = [vp, C.c_int]
+    lib.snacb_session_frames.restype = C.c_int64
     lib.snacb_session_emitted.argtypes = [vp, C.c_int]
+    lib.snacb_session_emitted.restype = C.c_int64
     lib.snacb_session_next_emit.argtypes = [vp, C.c_int, C.c_int, C.c_int]
     lib.snacb_session_step.argtypes = [vp, C.c_int, C.c_int, i32p, C.c_int, C.c_int, C.c_int, u64, i32p, i16p, C.c_int,
                                        C.POINTER(C.c_int), vp]

@@ -202,9 +202,10 @@ class SnacDecoder:
         self._check(self._lib.snacb_decode_host_wait(self._h), "snacb_decode_host_wait")
 
     # ------------------------------------------------------------------ stateful streaming
-    def open_session(self, n_slots: int, max_frames: int, *, raw_ids: bool = True, precision: str = "fp16") -> "StreamingSession":
-        """Incremental decode of growing streams with per-slot, per-stage state in HBM (include/snacb.h, snacb_session_*)."""
-        return StreamingSession(self, n_slots, max_frames, raw_ids=raw_ids, precision=precision)
+    def open_session(self, n_slots: int, window_frames: int = 32, *, raw_ids: bool = True, precision: str = "fp16") -> "StreamingSession":
+        """Incremental decode of growing streams with per-slot, per-stage state in HBM (include/snacb.h, snacb_session_*).
+        ``window_frames``: frames of activations every slot keeps (a sliding window; streams are unbounded)."""
+        return StreamingSession(self, n_slots, window_frames, raw_ids=raw_ids, precision=precision)
 
     # ------------------------------------------------------------------ per-stage timing
     def profile(self, enable: bool = True):
@@ -238,7 +239,8 @@ class StreamingSession:
     """``snacb_session``: slots 0..n_slots-1 each hold one growing stream; ``step`` appends frames to a contiguous range of
     slots that are at the same position and returns the samples that became final -- no recompute of the prefix, and the
     concatenation of all steps of a slot equals ``SnacDecoder.decode(..., stream_keys=key)`` of the finished stream bit for
-    bit (tests/test_gpu_api.py)."""
+    bit (tests/test_gpu_api.py).  Each slot keeps a sliding window of ``max_frames`` frames of activations; a stream may be
+    arbitrarily long, a single step may add at most ``max_frames - 16`` frames to a non-empty window."""
 
     def __init__(self, decoder: SnacDecoder, n_slots: int, max_frames: int, *, raw_ids: bool = True, precision: str = "fp16"):
         if precision not in ("fp16", "bf16"):

@@ -45,6 +45,8 @@ struct GemmArgs {
     int noise_stage;        // decoder block index, keys the counter RNG
     int stream_offset;      // global index of stream 0 of this chunk (counter RNG addressing)
     const int* stream_keys; // optional [S]: counter RNG key of each stream instead of stream_offset + s
+    int t0;                 // absolute index of output row 0 in its stream (counter RNG): a streaming session keeps a sliding
+                            // window of each stream in its buffers, the noise stays keyed by the absolute time step
     const void* resid;      // residual / y tensor, [S*Tin*up][Cout] (16-bit operand type on the tensor-core path)
     void* out;              // [S*Tin*up][Cout]
 };
@@ -86,6 +88,7 @@ struct ChainArgs {
     unsigned long long seed;
     int noise_stage, stream_offset;
     const int* stream_keys;       // optional [S]: counter RNG key of each stream instead of stream_offset + s
+    int t0;                       // absolute index of row 0 in its stream (counter RNG; see GemmArgs::t0)
     ChainSpan spans[3][kChainWarps][kChainSpans];
     int* tile_counter;            // zeroed before the launch: tiles beyond the first gridDim.x are claimed dynamically
     unsigned long long* prof;     // debug: 20 per-phase clock64 sums of CTA 0 / thread 0 (SNACB_CHAIN_PROF=1), else null

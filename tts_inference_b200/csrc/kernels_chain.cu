@@ -503,7 +503,7 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
                 float v = 0.f;
                 if (static_cast<unsigned>(t) < static_cast<unsigned>(a.T))
                     v = a.noise ? a.noise[static_cast<size_t>(s) * a.T + t]
-                                : counter_normal(key, noise_counter(a.stream_keys ? a.stream_keys[s] : a.stream_offset + s, t));
+                                : counter_normal(key, noise_counter(a.stream_keys ? a.stream_keys[s] : a.stream_offset + s, t + a.t0));
                 sNz[i] = v;
             }
         }

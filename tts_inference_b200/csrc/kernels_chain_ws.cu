@@ -331,7 +331,7 @@ k_chain_ws(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUte
                     float nz = 0.f;
                     if (MODE == WS_NOISE && valid)
                         nz = a.noise ? a.noise[static_cast<size_t>(s) * a.T + t]
-                                     : counter_normal(key, noise_counter(a.stream_keys ? a.stream_keys[s] : a.stream_offset + s, t));
+                                     : counter_normal(key, noise_counter(a.stream_keys ? a.stream_keys[s] : a.stream_offset + s, t + a.t0));
                     mbar_wait(&mma_bar[blk], mma_par);
                     tc_fence_after();
                     tick(17 + 2 * bnd);                        // waiting for the MMAs

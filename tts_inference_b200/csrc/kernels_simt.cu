@@ -213,7 +213,7 @@ k_gemm_f32(GemmArgs a, const float* __restrict__ A, const float* __restrict__ W)
         float nz = 0.f;
         if (EPI == EPI_NOISE)
             nz = a.noise ? a.noise[static_cast<size_t>(s) * a.Tin + m]
-                         : counter_normal(key, noise_counter(a.stream_keys ? a.stream_keys[s] : a.stream_offset + s, m));
+                         : counter_normal(key, noise_counter(a.stream_keys ? a.stream_keys[s] : a.stream_offset + s, m + a.t0));
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int o = o0 + j;

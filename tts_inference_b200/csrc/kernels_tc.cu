@@ -144,7 +144,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             float nz = 0.f;
             if (EPI == EPI_NOISE && valid)
                 nz = a.noise ? a.noise[static_cast<size_t>(s) * a.Tin + m]
-                             : counter_normal(key, noise_counter(a.stream_keys ? a.stream_keys[s] : a.stream_offset + s, m));
+                             : counter_normal(key, noise_counter(a.stream_keys ? a.stream_keys[s] : a.stream_offset + s, m + a.t0));
             mbar_wait(&tfull[as], aphase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN);

@@ -41,6 +41,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// try_wait with a suspend-time hint (ns): the thread sleeps in hardware until the phase completes or the hint expires,
+// instead of spinning -- a waiting warp then leaves its issue slots to the warps that work.
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t hint_ns) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
+        : "memory");
+    return ok != 0;
+}
 // Non-blocking test (try_wait may suspend the thread for a system-dependent time when the phase is not complete: an event
 // loop that polls several barriers must not sit in one of them while another becomes ready).
 __device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
@@ -62,7 +75,7 @@ __device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
+    while (!mbar_try_wait_hint(bar, parity, 100000u)) {
         if (clock64() - t0 > SNACB_WAIT_LIMIT_CYCLES) {
             printf("snacb: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x,
                    smem_u32(bar), parity);

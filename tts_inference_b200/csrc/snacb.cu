@@ -387,7 +387,7 @@ struct SessionPlan {
 
 int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, int flags, const float* const* noise,
               uint64_t seed, int stream_offset, const int32_t* stream_keys, int out_lo, int out_hi, int16_t* pcm,
-              float* wave, cudaStream_t st, const SessionPlan* plan = nullptr) {
+              float* wave, cudaStream_t st, const SessionPlan* plan = nullptr, int origin_frames = 0) {
     const bool f32 = (flags & SNACB_FP32) != 0;
     const bool xf32 = f32 || (flags & SNACB_STREAM_FP32);      // residual stream dtype
     const int hk = (flags & SNACB_BF16) ? 0 : 1;               // 16-bit operand type: 0 bf16, 1 fp16
@@ -593,6 +593,7 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
             ca.alpha_next = bi < 3 ? h->blk[bi + 1].alpha : h->tail_alpha;
             ca.inv_next = bi < 3 ? h->blk[bi + 1].inv_alpha : h->tail_inv;
             ca.noise = noise ? noise[bi] : nullptr; ca.seed = seed; ca.noise_stage = bi; ca.stream_offset = stream_offset; ca.stream_keys = stream_keys;
+            ca.t0 = origin_frames * 4 * (T / T0);      // the buffers hold the stream from frame origin_frames on
             const bool ws = h->chain_ws && chain_ws_supported(b.Cout, hk);
             memcpy(ca.spans, ws ? b.spans_ws : b.spans, sizeof ca.spans);
             ca.tile_counter = h->tile_counter;
@@ -634,6 +635,7 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
             if (plan) { a.t_lo = plan->nz_r[bi].lo; a.t_n = plan->nz_r[bi].hi - plan->nz_r[bi].lo; }
             else if (trimmed[bi]) { a.t_lo = post[bi].lo; a.t_n = post[bi].hi - post[bi].lo; }
             a.noise = noise ? noise[bi] : nullptr; a.noise_stage = bi;
+            a.t0 = origin_frames * 4 * (T / T0);
             a.resid = oth; a.out = cur;
             snprintf(nm, sizeof nm, "b%d.noise", bi);
             int rc = gemm(nm, EPI_NOISE, xf32, a, oth, b.nz_f32, b.nz_h, b.Cout, b.Cout);
@@ -934,9 +936,14 @@ int snacb_decode_keyed(snacb_handle h, const int32_t* tok, int B, int tok_stride
     return snacb_decode_range(h, tok, B, tok_stride, frames, flags, noise, seed, stream_keys, 0, 0, pcm, wave, stream);
 }
 
-int snacb_decode_range(snacb_handle h, const int32_t* tok, int B, int tok_stride, int frames, int flags,
-                       const float* const* noise, uint64_t seed, const int32_t* stream_keys, int sample_lo, int sample_hi,
-                       int16_t* pcm, float* wave, void* stream) {
+}  // extern "C"
+
+namespace {
+// snacb_decode_range on tokens that hold a stream from frame `origin_frames` on: rows and samples are relative to that
+// frame, the NoiseBlock noise stays keyed by the absolute time step (a streaming session's end-of-stream flush)
+int decode_range_impl(snacb_handle h, const int32_t* tok, int B, int tok_stride, int frames, int flags,
+                      const float* const* noise, uint64_t seed, const int32_t* stream_keys, int sample_lo, int sample_hi,
+                      int16_t* pcm, float* wave, void* stream, int origin_frames) {
     if (!h) return SNACB_ERR_ARG;
     const bool ranged = sample_lo != 0 || sample_hi != 0;
     if (ranged && (sample_lo < 0 || sample_hi <= sample_lo || sample_hi > 2048LL * frames))
@@ -984,10 +991,20 @@ int snacb_decode_range(snacb_handle h, const int32_t* tok, int B, int tok_stride
         int rc = run_group(h, tok + static_cast<size_t>(g0) * tok_stride, S, tok_stride, frames, flags,
                            noise ? nz : nullptr, seed, g0, stream_keys ? stream_keys + g0 : nullptr,
                            ranged ? sample_lo : 0, ranged ? sample_hi : 0, pcm + static_cast<size_t>(g0) * n_out,
-                           wave ? wave + static_cast<size_t>(g0) * n_out : nullptr, st);
+                           wave ? wave + static_cast<size_t>(g0) * n_out : nullptr, st, nullptr, origin_frames);
         if (rc) return rc;
     }
     return SNACB_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int snacb_decode_range(snacb_handle h, const int32_t* tok, int B, int tok_stride, int frames, int flags,
+                       const float* const* noise, uint64_t seed, const int32_t* stream_keys, int sample_lo, int sample_hi,
+                       int16_t* pcm, float* wave, void* stream) {
+    return decode_range_impl(h, tok, B, tok_stride, frames, flags, noise, seed, stream_keys, sample_lo, sample_hi, pcm, wave,
+                             stream, 0);
 }
 
 // =================================================================================================
@@ -998,10 +1015,11 @@ int snacb_decode_range(snacb_handle h, const int32_t* tok, int B, int tok_stride
 
 struct snacb_session_s {
     snacb_handle h = nullptr;
-    int n_slots = 0, max_frames = 0, flags = 0;
-    std::vector<int> frames, emitted;         // per slot: frames ingested, samples emitted
+    int n_slots = 0, max_frames = 0, flags = 0;   // max_frames: frames of every slot's window (buffers)
+    std::vector<long long> frames, emitted;   // per slot: frames ingested, samples emitted (whole stream)
+    std::vector<long long> origin;            // per slot: stream frame held at row 0 of the slot's buffers
     std::vector<char> finished;
-    int32_t* tok = nullptr;                   // [n_slots][7 * max_frames]
+    int32_t* tok = nullptr;                   // [n_slots][7 * max_frames], the window's tokens
     int32_t* codes[3] = {nullptr, nullptr, nullptr};
     int32_t* slot_keys = nullptr;             // [n_slots] = 0, 1, ...: the default NoiseBlock noise key of a slot
     void* a0 = nullptr;
@@ -1097,7 +1115,7 @@ int snacb_session_create(snacb_handle h, int n_slots, int max_frames, int flags,
     if (!s) return SNACB_ERR_NOMEM;
     s->h = h; s->n_slots = n_slots; s->flags = flags;
     s->max_frames = (max_frames + 31) / 32 * 32;              // every stage then has >= 128 rows per slot (whole tiles)
-    s->frames.assign(n_slots, 0); s->emitted.assign(n_slots, 0); s->finished.assign(n_slots, 0);
+    s->frames.assign(n_slots, 0); s->emitted.assign(n_slots, 0); s->origin.assign(n_slots, 0); s->finished.assign(n_slots, 0);
     const size_t N = static_cast<size_t>(n_slots), Fm = static_cast<size_t>(s->max_frames), T0 = 4 * Fm;
     const int hk = (flags & SNACB_BF16) ? 0 : 1;
     int rc = sess_alloc(s, reinterpret_cast<void**>(&s->tok), N * 7 * Fm * sizeof(int32_t));
@@ -1147,24 +1165,26 @@ int snacb_session_max_frames(snacb_session s) { return s ? s->max_frames : SNACB
 int snacb_session_reset(snacb_session s, int slot0, int n) {
     if (!s) return SNACB_ERR_ARG;
     if (slot0 < 0 || n < 0 || slot0 + n > s->n_slots) return fail(s->h, SNACB_ERR_ARG, "snacb_session_reset: bad slot range");
-    for (int i = slot0; i < slot0 + n; ++i) { s->frames[i] = 0; s->emitted[i] = 0; s->finished[i] = 0; }
+    for (int i = slot0; i < slot0 + n; ++i) { s->frames[i] = 0; s->emitted[i] = 0; s->origin[i] = 0; s->finished[i] = 0; }
     return SNACB_OK;
 }
 
-int snacb_session_frames(snacb_session s, int slot) {
+int64_t snacb_session_frames(snacb_session s, int slot) {
     return (s && slot >= 0 && slot < s->n_slots) ? s->frames[slot] : SNACB_ERR_ARG;
 }
-int snacb_session_emitted(snacb_session s, int slot) {
+int64_t snacb_session_emitted(snacb_session s, int slot) {
     return (s && slot >= 0 && slot < s->n_slots) ? s->emitted[slot] : SNACB_ERR_ARG;
 }
 
 int snacb_session_next_emit(snacb_session s, int slot, int new_frames, int final) {
     if (!s || slot < 0 || slot >= s->n_slots || new_frames < 0) return SNACB_ERR_ARG;
-    const int F = s->frames[slot] + new_frames;
-    if (F > s->max_frames) return SNACB_ERR_ARG;
     const int hk = (s->flags & SNACB_BF16) ? 0 : 1;
-    const int end = final ? 2048 * F : frontier_of(s->h, F, hk).emit;
-    return end > s->emitted[slot] ? end - s->emitted[slot] : 0;
+    // relative to the window's origin (the frontier is translation invariant once it is past the stream's first rows)
+    const long long o = s->origin[slot];
+    const long long Fl = s->frames[slot] - o + new_frames, El = s->emitted[slot] - 2048 * o;
+    if (Fl > 2LL * s->max_frames) return SNACB_ERR_ARG;
+    const long long end = final ? 2048 * Fl : frontier_of(s->h, static_cast<int>(Fl), hk).emit;
+    return end > El ? static_cast<int>(end - El) : 0;
 }
 
 int snacb_session_step(snacb_session s, int slot0, int n, const int32_t* new_tok, int tok_stride, int new_frames, int final,
@@ -1176,22 +1196,56 @@ int snacb_session_step(snacb_session s, int slot0, int n, const int32_t* new_tok
     if (slot0 < 0 || n < 0 || slot0 + n > s->n_slots || new_frames < 0 || (new_frames > 0 && tok_stride < 7 * new_frames))
         return fail(h, SNACB_ERR_ARG, "snacb_session_step: bad sizes slot0=%d n=%d new_frames=%d tok_stride=%d", slot0, n, new_frames, tok_stride);
     if (n == 0) return SNACB_OK;
-    const int Fp = s->frames[slot0], Ep = s->emitted[slot0];
+    constexpr int kKeep = 8;                   // frames a window keeps when it slides: covers the deepest stage's lag (2.3
+                                               // frames), every stage's halo and the left context of the end-of-stream flush
     for (int i = slot0; i < slot0 + n; ++i) {
         if (s->finished[i]) return fail(h, SNACB_ERR_STATE, "snacb_session_step: slot %d is finished (snacb_session_reset it)", i);
-        if (s->frames[i] != Fp || s->emitted[i] != Ep)
-            return fail(h, SNACB_ERR_STATE, "snacb_session_step: slots [%d, %d) are not at the same position (slot %d: %d frames, slot %d: %d)",
-                        slot0, slot0 + n, slot0, Fp, i, s->frames[i]);
+        if (s->frames[i] != s->frames[slot0] || s->emitted[i] != s->emitted[slot0] || s->origin[i] != s->origin[slot0])
+            return fail(h, SNACB_ERR_STATE, "snacb_session_step: slots [%d, %d) are not at the same position (slot %d: %lld frames, slot %d: %lld)",
+                        slot0, slot0 + n, slot0, s->frames[slot0], i, s->frames[i]);
     }
-    const int F = Fp + new_frames;
-    if (F > s->max_frames) return fail(h, SNACB_ERR_ARG, "snacb_session_step: %d frames exceed the session's max_frames=%d", F, s->max_frames);
     if (new_frames > 0 && !new_tok) return fail(h, SNACB_ERR_ARG, "snacb_session_step: null tokens");
+    const int Fm = s->max_frames;
+    long long o = s->origin[slot0];
+    int Fp = static_cast<int>(s->frames[slot0] - o);           // frames held, relative to the window
+    int Ep = static_cast<int>(s->emitted[slot0] - 2048 * o);   // samples emitted, relative to the window
+    int slide = 0;
+    if (Fp + new_frames > Fm) {
+        // the window is full: keep its last kKeep frames, move them to the front (after the checks below)
+        slide = Fp - kKeep;
+        if (slide < kKeep || kKeep + new_frames > Fm)
+            return fail(h, SNACB_ERR_ARG, "snacb_session_step: %d new frames do not fit a %d-frame window holding %d (a step may add at most %d)",
+                        new_frames, Fm, Fp, Fm - 2 * kKeep);
+    }
     CK(h, cudaSetDevice(h->device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int Fm = s->max_frames;
     const int hk = (s->flags & SNACB_BF16) ? 0 : 1;
     const size_t so = static_cast<size_t>(slot0);
     int32_t* tokp = s->tok + so * 7 * Fm;
+    if (slide > 0) {
+        // rows [slide, Fp) frames of every stage -> [0, kKeep): source and destination do not overlap (slide >= kKeep)
+        auto move = [&](void* buf, size_t row_bytes_per_frame) -> cudaError_t {
+            if (!buf) return cudaSuccess;
+            const size_t pitch = row_bytes_per_frame * Fm;
+            char* base = static_cast<char*>(buf) + so * pitch;
+            return cudaMemcpy2DAsync(base, pitch, base + row_bytes_per_frame * slide, pitch, row_bytes_per_frame * kKeep, n,
+                                     cudaMemcpyDeviceToDevice, st);
+        };
+        CK(h, move(s->tok, 7 * sizeof(int32_t)));
+        CK(h, move(s->stem, static_cast<size_t>(4) * kDecDim * 2));
+        size_t rows = 4;
+        for (int bi = 0; bi < 4; ++bi) {
+            rows *= h->blk[bi].s;
+            const size_t rb = rows * h->blk[bi].Cout * 2;
+            CK(h, move(s->ct[bi], rb));
+            CK(h, move(s->nz[bi], rb));
+            for (int ri = 0; ri < 3; ++ri) CK(h, move(s->res[bi][ri], rb));
+            if (s->out[bi] != s->res[bi][2]) CK(h, move(s->out[bi], rb));
+        }
+        o += slide; Fp -= slide; Ep -= 2048 * slide;
+        for (int i = slot0; i < slot0 + n; ++i) s->origin[i] = o;
+    }
+    const int F = Fp + new_frames;
     if (new_frames > 0)
         CK(h, cudaMemcpy2DAsync(tokp + static_cast<size_t>(7) * Fp, static_cast<size_t>(7) * Fm * sizeof(int32_t), new_tok,
                                 static_cast<size_t>(tok_stride) * sizeof(int32_t), static_cast<size_t>(7) * new_frames * sizeof(int32_t),
@@ -1201,25 +1255,27 @@ int snacb_session_step(snacb_session s, int slot0, int n, const int32_t* new_tok
     int n_out = 0;
     if (final) {
         // end of stream: the remaining samples see the zero padding at the true end -- one stateless ranged decode of the
-        // stored tokens (exact end semantics, bit-identical to the batch decode; the receptive-field margin is recomputed once)
+        // window's tokens (exact end semantics; its left edge lies more than a receptive field before the first sample
+        // still to emit, so the result equals the batch decode of the whole stream bit for bit)
         n_out = 2048 * F - Ep;
         if (n_out > 0) {
             if (!pcm || pcm_stride < n_out) return fail(h, SNACB_ERR_ARG, "snacb_session_step: pcm_stride %d < %d samples", pcm_stride, n_out);
-            if (pcm_stride == n_out || n == 1) {
-                int rc = snacb_decode_range(h, tokp, n, 7 * Fm, F, dflags, nullptr, seed, stream_keys, Ep, 2048 * F, pcm, nullptr, stream);
-                if (rc) return rc;
-            } else {
+            int16_t* dst = pcm;
+            if (pcm_stride != n_out && n > 1) {
                 size_t pb = h->st_pcm_elems * sizeof(int16_t);
                 int rc = grow(h, reinterpret_cast<void**>(&h->st_pcm), &pb, static_cast<size_t>(n) * n_out * sizeof(int16_t));
                 if (rc) return rc;
                 h->st_pcm_elems = pb / sizeof(int16_t);
-                rc = snacb_decode_range(h, tokp, n, 7 * Fm, F, dflags, nullptr, seed, stream_keys, Ep, 2048 * F, h->st_pcm, nullptr, stream);
-                if (rc) return rc;
-                CK(h, cudaMemcpy2DAsync(pcm, static_cast<size_t>(pcm_stride) * 2, h->st_pcm, static_cast<size_t>(n_out) * 2,
-                                        static_cast<size_t>(n_out) * 2, n, cudaMemcpyDeviceToDevice, st));
+                dst = h->st_pcm;
             }
+            int rc = decode_range_impl(h, tokp, n, 7 * Fm, F, dflags, nullptr, seed, stream_keys, Ep, 2048 * F, dst, nullptr, stream,
+                                       static_cast<int>(o));
+            if (rc) return rc;
+            if (dst != pcm)
+                CK(h, cudaMemcpy2DAsync(pcm, static_cast<size_t>(pcm_stride) * 2, dst, static_cast<size_t>(n_out) * 2,
+                                        static_cast<size_t>(n_out) * 2, n, cudaMemcpyDeviceToDevice, st));
         }
-        for (int i = slot0; i < slot0 + n; ++i) { s->frames[i] = F; s->emitted[i] = 2048 * F; s->finished[i] = 1; }
+        for (int i = slot0; i < slot0 + n; ++i) { s->frames[i] = o + F; s->emitted[i] = 2048 * (o + F); s->finished[i] = 1; }
         if (n_emitted) *n_emitted = n_out > 0 ? n_out : 0;
         return SNACB_OK;
     }
@@ -1257,12 +1313,13 @@ int snacb_session_step(snacb_session s, int slot0, int n, const int32_t* new_tok
         h->st_pcm_elems = pb / sizeof(int16_t);
         dst = h->st_pcm;
     }
-    int rc = run_group(h, tokp, n, 7 * Fm, Fm, dflags, nullptr, seed, 0, stream_keys, Ep, Ep + n_out, dst, nullptr, st, &pl);
+    int rc = run_group(h, tokp, n, 7 * Fm, Fm, dflags, nullptr, seed, 0, stream_keys, Ep, Ep + n_out, dst, nullptr, st, &pl,
+                       static_cast<int>(o));
     if (rc) return rc;
     if (dst != pcm)
         CK(h, cudaMemcpy2DAsync(pcm, static_cast<size_t>(pcm_stride) * 2, dst, static_cast<size_t>(n_out) * 2,
                                 static_cast<size_t>(n_out) * 2, n, cudaMemcpyDeviceToDevice, st));
-    for (int i = slot0; i < slot0 + n; ++i) { s->frames[i] = F; s->emitted[i] = Ep + n_out; }
+    for (int i = slot0; i < slot0 + n; ++i) { s->frames[i] = o + F; s->emitted[i] = 2048 * o + Ep + n_out; }
     if (n_emitted) *n_emitted = n_out;
     return SNACB_OK;
 }

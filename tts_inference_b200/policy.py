@@ -38,7 +38,7 @@ def stable_samples(frames: int, lookahead_frames: int, final: bool) -> int:
 
 
 class _Stream:
-    __slots__ = ("ids", "decoded_frames", "emitted", "done", "key")
+    __slots__ = ("ids", "decoded_frames", "emitted", "done", "key", "flushed")
 
     def __init__(self, key: int):
         self.key = key
@@ -46,6 +46,7 @@ class _Stream:
         self.decoded_frames = 0
         self.emitted = 0
         self.done = False
+        self.flushed = False
 
 
 class LookaheadStreamingDecoder:
@@ -117,12 +118,12 @@ class StatefulStreamingDecoder:
     (both equal the batch decode of the finished stream, tests/test_io.py).  Streams that are due with the same
     (frames held, frames to add, finished) and sit in neighbouring slots share one batched step."""
 
-    def __init__(self, decoder, max_streams: int, max_frames: int, frames_per_chunk: int = 4, raw_ids: bool = True,
+    def __init__(self, decoder, max_streams: int, window_frames: int = 32, frames_per_chunk: int = 4, raw_ids: bool = True,
                  precision: str = "fp16", seed: int = 0):
         if frames_per_chunk < 1:
             raise ValueError("frames_per_chunk >= 1")
         self._dec = decoder
-        self._sess = decoder.open_session(max_streams, max_frames, raw_ids=raw_ids, precision=precision)
+        self._sess = decoder.open_session(max_streams, window_frames, raw_ids=raw_ids, precision=precision)
         self.frames_per_chunk, self.seed = int(frames_per_chunk), int(seed)
         self._streams: Dict[Hashable, _Stream] = {}
         self._slot: Dict[Hashable, int] = {}
@@ -152,11 +153,13 @@ class StatefulStreamingDecoder:
     def step(self) -> List[Tuple[Hashable, np.ndarray]]:
         import torch
         due: Dict[Tuple[int, int, bool], List[Tuple[int, Hashable]]] = {}
+        cap = self._sess.max_frames - 16                       # frames one step may add to a non-empty window
         for key, st in self._streams.items():
-            frames = min(len(st.ids) // FRAME, self._sess.max_frames)
-            new = frames - st.decoded_frames
-            if (st.done and (new > 0 or st.emitted < SAMPLES_PER_FRAME * frames)) or new >= self.frames_per_chunk:
-                due.setdefault((st.decoded_frames, new, st.done), []).append((self._slot[key], key))
+            avail = len(st.ids) // FRAME                       # whole frames not yet handed to the session
+            new = min(avail, cap)
+            final = st.done and new == avail
+            if final or new >= self.frames_per_chunk or (st.done and new > 0):
+                due.setdefault((st.decoded_frames, new, final), []).append((self._slot[key], key))
         out: List[Tuple[Hashable, np.ndarray]] = []
         for (have, new, final), members in sorted(due.items(), key=lambda kv: kv[0]):
             members.sort()
@@ -169,7 +172,7 @@ class StatefulStreamingDecoder:
             runs.append(run)
             for run in runs:
                 keys = [k for _, k in run]
-                tok = np.asarray([self._streams[k].ids[have * FRAME:(have + new) * FRAME] for k in keys], dtype=np.int64)
+                tok = np.asarray([self._streams[k].ids[:new * FRAME] for k in keys], dtype=np.int64)
                 tok = np.clip(tok.reshape(len(keys), new * FRAME), -(2 ** 31), 2 ** 31 - 1).astype(np.int32)
                 nkeys = torch.tensor([self._streams[k].key for k in keys], dtype=torch.int32).cuda(self._dec.device)
                 pcm = self._sess.step(run[0][0], torch.from_numpy(tok).cuda(self._dec.device), final=final, seed=self.seed,
@@ -178,10 +181,12 @@ class StatefulStreamingDecoder:
                 for row, k in enumerate(keys):
                     st = self._streams[k]
                     st.decoded_frames = have + new
+                    del st.ids[:new * FRAME]                   # the session holds what it still needs
                     st.emitted += host.shape[1]
+                    st.flushed = final
                     if host.shape[1]:
                         out.append((k, host[row]))
-        for key in [k for k, st in self._streams.items() if st.done and st.decoded_frames >= min(len(st.ids) // FRAME, self._sess.max_frames)]:
+        for key in [k for k, st in self._streams.items() if st.done and st.flushed]:
             slot = self._slot.pop(key)
             self._sess.reset(slot, 1)
             self._free.append(slot)
