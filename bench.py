@@ -223,6 +223,54 @@ def extra_configs(dec, args, world, max_over_ranks):
     return res
 
 
+def neighbour_rows(dec, args):
+    """The rows SURVEY.md section 8(f) puts either side of the path, measured on rank 0 (CUDA events): the stateful streaming
+    session (row 1) against one batch decode of the same streams, and the SNAC encode path (row 4).  Beside the headline,
+    never inside it."""
+    import torch
+    from tts_inference_b200 import synth
+    from tts_inference_b200.encoder import SnacEncoder
+    out = {}
+    S, F_, k = 64, 64, 4
+    tok = torch.from_numpy(synth.make_tokens(S, F_, seed=3)).cuda()
+    keys = torch.arange(S, dtype=torch.int32).cuda()
+    sess = dec.open_session(S, 32, precision=args.precision)
+
+    def stream_once():
+        sess.reset()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for f in range(0, F_, k):
+            sess.step(0, tok[:, 7 * f:7 * (f + k)], final=(f + k == F_), seed=1, stream_keys=keys)
+        b.record(); torch.cuda.synchronize()
+        return a.elapsed_time(b)
+    stream_once()
+    ms_s = min(stream_once() for _ in range(3))
+    dec.decode(tok, raw_ids=True, seed=1, stream_keys=keys, precision=args.precision)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(); dec.decode(tok, raw_ids=True, seed=1, stream_keys=keys, precision=args.precision); b.record()
+    torch.cuda.synchronize()
+    audio_s = S * F_ * 2048 / SR
+    out["streaming_session"] = {
+        "what": f"{S} streams x {F_} frames fed {k} frames per step through snacb_session_step (32-frame sliding window per "
+                "stream, per-stage state in HBM, only newly final rows computed; bit-identical to the batch decode)",
+        "steps": F_ // k, "ms_all_steps": ms_s, "audio_s_per_s": audio_s / ms_s * 1e3,
+        "one_batch_decode_ms": a.elapsed_time(b), "session_bytes": sess.nbytes}
+    sess.close()
+    enc = SnacEncoder(synth.make_encoder_state_dict(0))
+    audio = torch.from_numpy(synth.make_audio(64, 2048 * 16)).cuda()
+    enc.encode(audio)
+    ts = []
+    for _ in range(3):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); enc.encode(audio); b.record(); torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    out["encode_path"] = {"what": "SNAC encode (audio -> codes), 64 utterances x 16 frames, fp32 CUDA-core kernels",
+                          "ms": min(ts), "audio_s_per_s": 64 * 16 * 2048 / SR / min(ts) * 1e3}
+    enc.close()
+    return out
+
+
 def run_reference(args, rank: int, world: int):
     """--impl reference: the reference's own CPU implementation of the path = oracle port (the pip
     package `snac` cannot be installed offline), all host threads, bounded sample per step."""
@@ -500,6 +548,7 @@ def main():
             "latency_b1_window_ms": latency,
             "baseline_configs": extra,
             "gpu_torch_baseline": gpu_torch_baseline() if (world == 1 and not args.no_extra) else None,
+            "neighbour_rows": neighbour_rows(dec, args) if not args.no_extra else None,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -233,6 +233,9 @@ int snacb_debug_chain_spans(int C, int16_t* out, int cap);
  * SNACB_CHAIN_WS=1): spans live inside ONE 128-row block and count QUADS (4 steps): {first_row (block-relative),
  * quads, chunk} for each of the 8 prologue warps.  Returns (tile height in rows) | (prologue warps << 16). */
 int snacb_debug_chain_ws_spans(int C, int16_t* out, int cap);
+/* 1 when the library was built with SNACB_EXPERIMENTS=1 (python -m tts_inference_b200.build): k_chain_ws is then compiled
+ * and SNACB_CHAIN_WS=1 selects it.  The default build leaves measured-and-dropped kernel variants out of the product. */
+int snacb_experiments_built(void);
 
 /* ---------------------------------------------------------------------------------------------
  * SNAC ENCODE path: audio -> codes, the other half of the codec.  The reference never

@@ -22,7 +22,14 @@ GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 FP32_TOL = 1e-3      # north_star: fp32 waveform within 1e-3 max-abs
 TC_SNR_DB = 40.0     # north_star: 16-bit tensor-core path SNR >= 40 dB (met with fp16 operands)
-BF16_SNR_FLOOR_DB = 32.0   # what bf16 operands reach on the synthetic checkpoint (34-36 dB measured)
+# bf16 operands do NOT meet the 40 dB bar (34-36 dB measured; tools/precision_emul.py reproduces it on the CPU and shows
+# that bf16 storage between kernels, not the MMA operands, dominates).  The bar stays 40 dB: test_tensorcore_snr[bf16] is
+# an expected failure, and BF16_REGRESSION_DB only guards the optional path against getting worse.
+BF16_REGRESSION_DB = 32.0
+
+
+class Bf16Regression(Exception):
+    """not an AssertionError: the xfail of the 40 dB bar must not swallow a regression of the bf16 path"""
 
 
 def _cuda(a):
@@ -90,9 +97,11 @@ def test_fp32_stage_taps(decoder, oracle_model):
 
 
 # ------------------------------------------------------------------------------------ bf16 tensor-core path
-@pytest.mark.parametrize("prec,bar", [("fp16", TC_SNR_DB), ("bf16", BF16_SNR_FLOOR_DB)])
+@pytest.mark.parametrize("prec", ["fp16", pytest.param("bf16", marks=pytest.mark.xfail(
+    strict=True, raises=AssertionError, reason="bf16 operands / storage reach 34-36 dB, below north_star's 40 dB; fp16 is the shipped operand type"))])
 @pytest.mark.parametrize("B,F_", [(1, 4), (5, 4), (2, 1), (2, 5), (1, 9), (40, 4)])
-def test_tensorcore_snr(decoder, oracle_model, B, F_, prec, bar):
+def test_tensorcore_snr(decoder, oracle_model, B, F_, prec):
+    bar = TC_SNR_DB
     tokens = synth.make_tokens(B, F_, seed=21 + F_, bad_frac=0.02)
     noises = synth.make_noises(B, 4 * F_, seed=6)
     ref, _ = oracle_decode(oracle_model, tokens, noises)
@@ -100,8 +109,10 @@ def test_tensorcore_snr(decoder, oracle_model, B, F_, prec, bar):
                                return_wave=True)
     w = wave.cpu().numpy()
     assert np.isfinite(w).all()
-    assert snr_db(ref, w) >= bar, snr_db(ref, w)
     assert np.array_equal(pcm.cpu().numpy(), pcm_of(w))
+    if prec == "bf16" and not snr_db(ref, w) >= BF16_REGRESSION_DB:
+        raise Bf16Regression(snr_db(ref, w))
+    assert snr_db(ref, w) >= bar, snr_db(ref, w)
 
 
 def test_tensorcore_fp32_stream_is_at_least_as_good(decoder, oracle_model):
@@ -149,6 +160,9 @@ def ws_decoder(state_dict):
     """SNACB_CHAIN_WS=1: blocks 2 and 3 (C = 128 / 64) run kernels_chain_ws.cu (prologue / epilogue / IO warps pipelined
     over the 128-row blocks of a tile) instead of the lock-step k_chain."""
     import os
+    from tts_inference_b200 import _lib
+    if not _lib.load().snacb_experiments_built():
+        pytest.skip("k_chain_ws is an experiment (measured slower): built only with SNACB_EXPERIMENTS=1")
     os.environ["SNACB_CHAIN_WS"] = "1"
     try:
         d = SnacDecoder(state_dict, device=0)          # the switch is read when the handle is created
@@ -229,7 +243,7 @@ def test_adversarial_checkpoint_parity(adversarial):
             assert np.isfinite(wh).all()
             assert snr_db(ref, wh) >= TC_SNR_DB, (kw, snr_db(ref, wh))
         _, wb = dec.decode(_cuda(tokens), raw_ids=True, noise=nz, precision="bf16", return_wave=True)
-        assert np.isfinite(wb.cpu().numpy()).all() and snr_db(ref, wb.cpu().numpy()) >= BF16_SNR_FLOOR_DB
+        assert np.isfinite(wb.cpu().numpy()).all() and snr_db(ref, wb.cpu().numpy()) >= BF16_REGRESSION_DB
 
 
 def test_adversarial_checkpoint_bit_identities(adversarial):

@@ -54,7 +54,7 @@ EXPORTS = [
     "snacb_ingest_step", "snacb_ingest_state", "snacb_base64_len", "snacb_pcm_to_base64", "snacb_pcm_to_wav",
     "snacb_session_create", "snacb_session_destroy", "snacb_session_bytes", "snacb_session_max_frames", "snacb_session_reset",
     "snacb_session_frames", "snacb_session_emitted", "snacb_session_next_emit", "snacb_session_step",
-    "snacb_debug_session_frontier",
+    "snacb_debug_session_frontier", "snacb_experiments_built",
     "snacb_encoder_create", "snacb_encoder_destroy", "snacb_encoder_last_error", "snacb_encoder_launches", "snacb_encode_frames",
     "snacb_encode", "snacb_pack_tokens",
 ]

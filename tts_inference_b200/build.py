@@ -39,6 +39,8 @@ def needs_build() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    """SNACB_EXPERIMENTS=1 in the environment also compiles the measured-and-dropped kernel variants (k_chain_ws); the
+    default product build leaves them out."""
     if not force and not needs_build():
         return LIB
     objs = []
@@ -47,6 +49,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     for s in SOURCES:
         o = os.path.join(PKG, "build", os.path.splitext(s)[0] + ".o")
         cmd = [_nvcc(), *NVCC_FLAGS, "-c", os.path.join(CSRC, s), "-o", o]
+        if os.environ.get("SNACB_EXPERIMENTS") == "1":
+            cmd.insert(1, "-DSNACB_EXPERIMENTS")
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd), flush=True)

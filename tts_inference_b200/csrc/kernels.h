@@ -40,8 +40,9 @@ struct VqStemWeights {
 void launch_unpack(const int32_t* tok, int B, int ntok, int F, int raw_ids, int32_t* c0, int32_t* c1, int32_t* c2,
                    cudaStream_t st);
 template <typename OutT>
-void launch_vq_stem(const int32_t* c0, const int32_t* c1, const int32_t* c2, int S, int F, int t_lo, int t_hi,
-                    const VqStemWeights& w, OutT* out, cudaStream_t st);   // latent steps [t_lo, t_hi) of every stream
+void launch_vq_stem(const int32_t* c0, const int32_t* c1, const int32_t* c2, const int32_t* tok, int tok_stride, int raw_ids,
+                    int S, int F, int t_lo, int t_hi, const VqStemWeights& w, OutT* out, cudaStream_t st);
+// latent steps [t_lo, t_hi) of every stream; tok != null: codes are unpacked from the token rows on the fly (c0..c2 unused)
 void launch_gemm_f32(int epi, const GemmArgs& a, const float* A, const float* W, cudaStream_t st);
 void launch_respre_f32(const ResUnitArgs& a, float* P, cudaStream_t st);
 template <typename InT>
@@ -86,6 +87,7 @@ void chain_build_spans(int C, ChainSpan (*spans)[kChainWarps][kChainSpans]);
 cudaError_t launch_chain(int half_fp16, int fold, const ChainArgs& a, const CUtensorMap* tm, int sm_count, cudaStream_t st);
 
 // ---- kernels_chain_ws.cu  (the same chain, warp-specialised and pipelined over the 128-row blocks of a tile; C = 64 / 128)
+bool chain_ws_built();                // false unless the library was built with SNACB_EXPERIMENTS=1 (measured slower: DESIGN.md section 6)
 bool chain_ws_supported(int C, int half_fp16);
 int chain_ws_tile_rows(int C);
 void chain_ws_build_spans(int C, ChainSpan (*spans)[kChainWarps][kChainSpans]);   // ChainSpan::n_oct counts QUADS here

@@ -106,6 +106,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int threads) {
 
 }  // namespace
 
+#ifdef SNACB_EXPERIMENTS
 template <int C, int NB, typename HT, bool FOLD>
 __global__ void __launch_bounds__(kWsThreads, 1)
 k_chain_ws(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmOe,
@@ -534,8 +535,11 @@ k_chain_ws(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUte
     if (warp == kNP + kNE) tmem_dealloc(tmem_base, Cfg::kTmemCols);
 }
 
+#endif  // SNACB_EXPERIMENTS
+
 namespace {
 
+#ifdef SNACB_EXPERIMENTS
 template <int C, int NB, typename HT, bool FOLD>
 cudaError_t launch_ws_t(const ChainArgs& a, const CUtensorMap* tm, int sm_count, cudaStream_t st) {
     using Cfg = WsCfg<C, NB, std::is_same<HT, __half>::value, FOLD>;
@@ -554,6 +558,7 @@ cudaError_t launch_ws_t(const ChainArgs& a, const CUtensorMap* tm, int sm_count,
     k_chain_ws<C, NB, HT, FOLD><<<grid, kWsThreads, Cfg::kSmem, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], tm[6], a, tiles);
     return cudaGetLastError();
 }
+#endif  // SNACB_EXPERIMENTS
 
 constexpr int kWsNB64 = 8, kWsNB128 = 4;
 
@@ -599,6 +604,8 @@ void chain_ws_build_spans(int C, ChainSpan (*spans)[kChainWarps][kChainSpans]) {
     }
 }
 
+#ifdef SNACB_EXPERIMENTS
+bool chain_ws_built() { return true; }
 cudaError_t launch_chain_ws(int half_fp16, int fold, const ChainArgs& a, const CUtensorMap* tm, int sm_count, cudaStream_t st) {
     if (half_fp16) {
         if (fold) {
@@ -614,5 +621,10 @@ cudaError_t launch_chain_ws(int half_fp16, int fold, const ChainArgs& a, const C
     if (a.C == 64) return launch_ws_t<64, kWsNB64, __nv_bfloat16, false>(a, tm, sm_count, st);
     return cudaErrorInvalidValue;
 }
+#else
+// The kernel is an experiment that lost its A/B: compiled only with SNACB_EXPERIMENTS=1 at build time.
+bool chain_ws_built() { return false; }
+cudaError_t launch_chain_ws(int, int, const ChainArgs&, const CUtensorMap*, int, cudaStream_t) { return cudaErrorNotSupported; }
+#endif
 
 }  // namespace snacb

@@ -61,8 +61,9 @@ constexpr int kVqTile = 16;
 
 template <typename OutT>
 __global__ void __launch_bounds__(256)
-k_vq_stem(const int32_t* __restrict__ c0, const int32_t* __restrict__ c1, const int32_t* __restrict__ c2, int F,
-          int tile_lo, VqStemWeights w, OutT* __restrict__ out) {
+k_vq_stem(const int32_t* __restrict__ c0, const int32_t* __restrict__ c1, const int32_t* __restrict__ c2,
+          const int32_t* __restrict__ tok, int tok_stride, int raw_ids, int F, int tile_lo, VqStemWeights w,
+          OutT* __restrict__ out) {
     const int T0 = 4 * F;
     const int s = blockIdx.y, t0 = (tile_lo + blockIdx.x) * kVqTile;
     __shared__ float emb[3][kVqTile + 6][kCodeDim];
@@ -77,7 +78,16 @@ k_vq_stem(const int32_t* __restrict__ c0, const int32_t* __restrict__ c1, const 
         for (int j = 0; j < kCodeDim; ++j) e[j] = 0.f;
         if (valid) {
             int code;
-            if (lv == 0) code = c0[static_cast<size_t>(s) * F + (t >> 2)];
+            if (tok != nullptr) {
+                // the token -> code unpack of k_unpack, fused into the gather: level 0 sits at position 0 of its frame,
+                // level 1 at positions 1 and 4, level 2 at 2, 3, 5, 6 (modal_audio_stream.py:165-188)
+                const int j = lv == 0 ? (t >> 2) : (lv == 1 ? (t >> 1) : t);
+                const int f = lv == 0 ? j : (lv == 1 ? (j >> 1) : (j >> 2));
+                const int p = lv == 0 ? 0 : (lv == 1 ? ((j & 1) ? 4 : 1) : ((j & 3) < 2 ? 2 + (j & 3) : 3 + (j & 3)));
+                const long long v = static_cast<long long>(tok[static_cast<size_t>(s) * tok_stride + f * kFrame + p]) -
+                                    (raw_ids ? kTokenAudioBase : 0) - 4096LL * p;
+                code = static_cast<int>(v < 0 ? 0 : (v > 4095 ? 4095 : v));
+            } else if (lv == 0) code = c0[static_cast<size_t>(s) * F + (t >> 2)];
             else if (lv == 1) code = c1[static_cast<size_t>(s) * 2 * F + (t >> 1)];
             else code = c2[static_cast<size_t>(s) * 4 * F + t];
             const float* cb = w.codebook[lv] + static_cast<size_t>(code) * kCodeDim;
@@ -127,19 +137,19 @@ k_vq_stem(const int32_t* __restrict__ c0, const int32_t* __restrict__ c1, const 
 }
 
 template <typename OutT>
-void launch_vq_stem(const int32_t* c0, const int32_t* c1, const int32_t* c2, int S, int F, int t_lo, int t_hi,
-                    const VqStemWeights& w, OutT* out, cudaStream_t st) {
+void launch_vq_stem(const int32_t* c0, const int32_t* c1, const int32_t* c2, const int32_t* tok, int tok_stride, int raw_ids,
+                    int S, int F, int t_lo, int t_hi, const VqStemWeights& w, OutT* out, cudaStream_t st) {
     // latent steps [t_lo, t_hi) of every stream, in whole 16-step tiles
     const int tile_lo = t_lo / kVqTile, tile_hi = (t_hi + kVqTile - 1) / kVqTile;
     if (tile_hi <= tile_lo) return;
     dim3 grid(tile_hi - tile_lo, S, kLatent / 256);
-    k_vq_stem<OutT><<<grid, 256, 0, st>>>(c0, c1, c2, F, tile_lo, w, out);
+    k_vq_stem<OutT><<<grid, 256, 0, st>>>(c0, c1, c2, tok, tok_stride, raw_ids, F, tile_lo, w, out);
 }
-template void launch_vq_stem<float>(const int32_t*, const int32_t*, const int32_t*, int, int, int, int,
+template void launch_vq_stem<float>(const int32_t*, const int32_t*, const int32_t*, const int32_t*, int, int, int, int, int, int,
                                     const VqStemWeights&, float*, cudaStream_t);
-template void launch_vq_stem<__nv_bfloat16>(const int32_t*, const int32_t*, const int32_t*, int, int, int, int,
+template void launch_vq_stem<__nv_bfloat16>(const int32_t*, const int32_t*, const int32_t*, const int32_t*, int, int, int, int, int, int,
                                             const VqStemWeights&, __nv_bfloat16*, cudaStream_t);
-template void launch_vq_stem<__half>(const int32_t*, const int32_t*, const int32_t*, int, int, int, int,
+template void launch_vq_stem<__half>(const int32_t*, const int32_t*, const int32_t*, const int32_t*, int, int, int, int, int, int,
                                      const VqStemWeights&, __half*, cudaStream_t);
 
 // ----------------------------------------------------------------------------------------------

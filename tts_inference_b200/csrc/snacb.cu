@@ -407,10 +407,15 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
     int32_t* c0 = plan ? plan->c0 : h->ws_codes;
     int32_t* c1 = plan ? plan->c1 : c0 + static_cast<size_t>(S) * F;
     int32_t* c2 = plan ? plan->c2 : c1 + static_cast<size_t>(S) * 2 * F;
-    prof_begin(h, "unpack", st);
-    launch_unpack(tok, S, tok_stride, F, (flags & SNACB_RAW_IDS) ? 1 : 0, c0, c1, c2, st);
-    prof_end(h, st);
-    h->launches++;
+    // the token -> code unpack is fused into the VQ gather (k_vq_stem reads the token rows); the separate k_unpack pass
+    // runs only for SNACB_KEEP_TAPS decodes, whose callers may read the codes (snacb_unpack keeps the stand-alone call)
+    const bool fused_unpack = !taps;
+    if (!fused_unpack) {
+        prof_begin(h, "unpack", st);
+        launch_unpack(tok, S, tok_stride, F, (flags & SNACB_RAW_IDS) ? 1 : 0, c0, c1, c2, st);
+        prof_end(h, st);
+        h->launches++;
+    }
     // ---- dead-sample trimming (sliced output): only the rows of each stage inside the receptive field of samples
     //      [out_lo, out_hi) are computed.  Backward range propagation; the stem is always computed in full, block 0 unless
     //      less than half of it is live.
@@ -462,9 +467,9 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
     void* const a0 = plan ? plan->a0 : h->ws_a0;
     const bool stem_live = stem_hi > stem_lo;
     if (!stem_live) {}
-    else if (f32) launch_vq_stem<float>(c0, c1, c2, S, F, stem_lo, stem_hi, h->vq, static_cast<float*>(a0), st);
-    else if (hk) launch_vq_stem<__half>(c0, c1, c2, S, F, stem_lo, stem_hi, h->vq, static_cast<__half*>(a0), st);
-    else launch_vq_stem<__nv_bfloat16>(c0, c1, c2, S, F, stem_lo, stem_hi, h->vq, static_cast<__nv_bfloat16*>(a0), st);
+    else if (f32) launch_vq_stem<float>(c0, c1, c2, fused_unpack ? tok : nullptr, tok_stride, (flags & SNACB_RAW_IDS) ? 1 : 0, S, F, stem_lo, stem_hi, h->vq, static_cast<float*>(a0), st);
+    else if (hk) launch_vq_stem<__half>(c0, c1, c2, fused_unpack ? tok : nullptr, tok_stride, (flags & SNACB_RAW_IDS) ? 1 : 0, S, F, stem_lo, stem_hi, h->vq, static_cast<__half*>(a0), st);
+    else launch_vq_stem<__nv_bfloat16>(c0, c1, c2, fused_unpack ? tok : nullptr, tok_stride, (flags & SNACB_RAW_IDS) ? 1 : 0, S, F, stem_lo, stem_hi, h->vq, static_cast<__nv_bfloat16*>(a0), st);
     prof_end(h, st);
     if (stem_live) h->launches++;
     CK(h, cudaGetLastError());
@@ -850,7 +855,7 @@ int snacb_create(snacb_handle* out, const snacb_weights* w, int device) {
     if (const char* e = getenv("SNACB_RES_V1")) h->res_v1 = atoi(e) != 0;
     if (const char* e = getenv("SNACB_NO_CHAIN")) h->no_chain = atoi(e) != 0;
     if (const char* e = getenv("SNACB_NO_FOLD")) h->no_fold = atoi(e) != 0;
-    if (const char* e = getenv("SNACB_CHAIN_WS")) h->chain_ws = atoi(e) != 0;
+    if (const char* e = getenv("SNACB_CHAIN_WS")) h->chain_ws = atoi(e) != 0 && chain_ws_built();
     if (const char* e = getenv("SNACB_TMAP_CACHE")) { const long n = atol(e); if (n >= 1) h->max_act_maps = static_cast<size_t>(n); }
     if (const char* e = getenv("SNACB_CHAIN_PROF")) h->chain_prof = atoi(e);
     if (const char* e = getenv("SNACB_NO_TRIM")) h->no_trim = atoi(e) != 0;
@@ -1435,6 +1440,8 @@ int snacb_debug_chain_spans(int C, int16_t* out, int cap) {
             }
     return chain_tile_rows(C) | (chain_warps(C) << 16);
 }
+
+int snacb_experiments_built(void) { return chain_ws_built() ? 1 : 0; }
 
 int snacb_debug_chain_ws_spans(int C, int16_t* out, int cap) {
     if (!out || !chain_ws_supported(C, 1) || cap < 3 * kChainWarps * kChainSpans * 3) return SNACB_ERR_ARG;
