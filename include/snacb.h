@@ -140,7 +140,7 @@ int snacb_decode_range(snacb_handle h, const int32_t* tok, int B, int tok_stride
  * stage, only the rows that became FINAL with them (their whole receptive field lies inside the known tokens) and emits
  * the samples that became final: 4k latent steps of work, no recompute of the prefix, and -- the NoiseBlock noise being
  * keyed by (seed, block, stream key, t) -- the concatenated output is BIT-IDENTICAL to one snacb_decode_keyed of the
- * finished stream.  Non-final samples lag the newest token by the decoder's receptive field (2.3 frames = 4757 samples), not by a
+ * finished stream.  Non-final samples lag the newest token by the decoder's receptive field (2.5 frames = 5050 samples), not by a
  * fixed 5-frame lookahead.
  *   n_slots, window_frames  every slot keeps a SLIDING WINDOW of its stream's activations: window_frames frames (rounded
  *                         up to a multiple of 32; ~1.45 MB per frame per slot, snacb_session_bytes).  When a step does

@@ -269,7 +269,7 @@ def test_session_stream_is_bit_identical_to_batch_decode(decoder, precision, chu
 
 def test_session_default_keys_are_slot_indices_and_steps_cost_new_rows_only(decoder):
     """Without stream keys a slot's noise is keyed by its slot index whichever slots share its step; non-final steps emit
-    what snacb_session_next_emit announces (the receptive-field lag, 2.3 frames); slots at different positions are refused."""
+    what snacb_session_next_emit announces (the receptive-field lag, 2.5 frames); slots at different positions are refused."""
     F = 16
     tokens = synth.make_tokens(4, F, seed=4)
     tok = torch.from_numpy(tokens).cuda()
@@ -324,4 +324,40 @@ def test_session_window_slides_over_a_long_stream(decoder, chunk):
     cat = np.concatenate(got, axis=1)
     assert cat.shape == ref.shape and np.array_equal(cat, ref)
     assert sess.emitted(1) == 2048 * F and sess.nbytes == nbytes
+    sess.close()
+
+
+def test_session_c_abi_edge_cases(decoder):
+    """Raw C-ABI calls: zero slots / zero frames are no-ops, bad ranges and null buffers are refused with a message, a
+    padded pcm row stride is honoured, the first audio appears with the third frame (receptive-field lag of 2.5 frames;
+    the reference's loops wait for four)."""
+    import ctypes as C
+    lib = decoder._lib
+    sess = decoder.open_session(3, 32)
+    s = sess._s
+    got = C.c_int(-1)
+    assert lib.snacb_session_step(s, 0, 0, None, 0, 0, 0, C.c_uint64(0), None, None, 0, C.byref(got), None) == 0 and got.value == 0
+    assert lib.snacb_session_step(s, 2, 2, None, 0, 0, 0, C.c_uint64(0), None, None, 0, None, None) == -1      # slots 2..3 of 3
+    assert lib.snacb_session_step(s, 0, 1, None, 7, 1, 0, C.c_uint64(0), None, None, 0, None, None) == -1      # null tokens
+    assert b"null tokens" in lib.snacb_last_error(decoder._h)
+    assert lib.snacb_session_reset(s, 1, 5) == -1 and lib.snacb_session_frames(s, 7) == -1
+    tok = torch.from_numpy(synth.make_tokens(2, 6, seed=12)).cuda()
+    ref = decoder.decode(tok, raw_ids=True, seed=5, stream_keys=torch.tensor([1, 2], dtype=torch.int32).cuda()).cpu().numpy()
+    assert sess.next_emit(1, 2) == 0 and sess.next_emit(1, 3) == 2048 * 3 - 5050
+    first = sess.step(1, tok[:, :14], seed=5)                           # two frames: nothing is final yet
+    assert first.shape == (2, 0) and sess.frames(1) == 2 and sess.emitted(1) == 0
+    assert lib.snacb_session_step(s, 1, 2, None, 0, 0, 0, C.c_uint64(5), None, None, 0, C.byref(got), None) == 0 and got.value == 0
+    n = sess.next_emit(1, 1)
+    wide = torch.full((2, n + 5), -7, dtype=torch.int16).cuda()          # row stride 5 samples wider than what is emitted
+    rc = lib.snacb_session_step(s, 1, 2, tok[:, 14:21].contiguous().data_ptr(), 7, 1, 0, C.c_uint64(5), None, wide.data_ptr(),
+                                n + 5, C.byref(got), None)
+    assert rc == 0 and got.value == n == 2048 * 3 - 5050
+    torch.cuda.synchronize()
+    w = wide.cpu().numpy()
+    assert np.array_equal(w[:, :n], ref[:, :n]) and (w[:, n:] == -7).all()
+    small = torch.empty((2, 10), dtype=torch.int16).cuda()
+    assert lib.snacb_session_step(s, 1, 2, tok[:, 21:].contiguous().data_ptr(), 21, 3, 1, C.c_uint64(5), None, small.data_ptr(),
+                                  10, None, None) == -1                  # pcm rows too short for the flush
+    rest = sess.step(1, tok[:, 21:], final=True, seed=5).cpu().numpy()
+    assert np.array_equal(np.concatenate([w[:, :n], rest], axis=1), ref)
     sess.close()

@@ -543,7 +543,7 @@ def test_session_frontier_table(chain_mask):
         if prev is not None:
             assert all(a <= b for a, b in zip(prev, got))
         prev = got
-    # the emitted samples lag the newest token by the receptive field only (2.3 frames), not by a 5-frame lookahead
+    # the emitted samples lag the newest token by the receptive field only (2.5 frames), not by a 5-frame lookahead
     out = (C.c_int32 * 22)()
     lib.snacb_debug_session_frontier(20, chain_mask, out, 22)
     assert 2048 * 17.4 < out[21] < 2048 * 18

@@ -1201,7 +1201,7 @@ int snacb_session_step(snacb_session s, int slot0, int n, const int32_t* new_tok
     if (slot0 < 0 || n < 0 || slot0 + n > s->n_slots || new_frames < 0 || (new_frames > 0 && tok_stride < 7 * new_frames))
         return fail(h, SNACB_ERR_ARG, "snacb_session_step: bad sizes slot0=%d n=%d new_frames=%d tok_stride=%d", slot0, n, new_frames, tok_stride);
     if (n == 0) return SNACB_OK;
-    constexpr int kKeep = 8;                   // frames a window keeps when it slides: covers the deepest stage's lag (2.3
+    constexpr int kKeep = 8;                   // frames a window keeps when it slides: covers the deepest stage's lag (2.5
                                                // frames), every stage's halo and the left context of the end-of-stream flush
     for (int i = slot0; i < slot0 + n; ++i) {
         if (s->finished[i]) return fail(h, SNACB_ERR_STATE, "snacb_session_step: slot %d is finished (snacb_session_reset it)", i);

@@ -114,7 +114,7 @@ class StatefulStreamingDecoder:
     SURVEY.md section 8(f) row 1): every stream owns a slot whose per-stage activations stay in HBM, a step appends the
     new whole frames and gets back exactly the samples that became final -- the prefix is neither re-read nor re-decoded.
     Emission differs from ``LookaheadStreamingDecoder`` only in WHEN samples appear: here as soon as their receptive field
-    is inside the known tokens (a lag of 2.3 frames = 4757 samples) instead of after a fixed 5-frame lookahead; the bytes are the same
+    is inside the known tokens (a lag of 2.5 frames = 5050 samples) instead of after a fixed 5-frame lookahead; the bytes are the same
     (both equal the batch decode of the finished stream, tests/test_io.py).  Streams that are due with the same
     (frames held, frames to add, finished) and sit in neighbouring slots share one batched step."""
 
