@@ -90,6 +90,8 @@ struct ChainArgs {
     const int* stream_keys;       // optional [S]: counter RNG key of each stream instead of stream_offset + s
     int t0;                       // absolute index of row 0 in its stream (counter RNG; see GemmArgs::t0)
     ChainSpan spans[3][kChainWarps][kChainSpans];
+    unsigned jitter;              // debug (SNACB_CHAIN_JITTER=seed): every warp spins a pseudo-random 0..4095 cycles after each
+                                  // barrier of the in-place prologue -- the race detector for the schedule (see k_chain)
     int* tile_counter;            // zeroed before the launch: tiles beyond the first gridDim.x are claimed dynamically
     unsigned long long* prof;     // debug: 20 per-phase clock64 sums of CTA 0 / thread 0 (SNACB_CHAIN_PROF=1), else null
 };

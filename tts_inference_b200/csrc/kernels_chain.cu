@@ -528,6 +528,7 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
             // ---- spans of this warp: pre-read the 3 rows before and after each span (owned by other warps)
             uint32_t hd[kChainSpans][3], tl[kChainSpans][3];
             int r_first[kChainSpans], n_oct[kChainSpans], kcs[kChainSpans];
+            auto preread = [&]() {
 #pragma unroll
             for (int sp = 0; sp < kChainSpans; ++sp) {
                 const ChainSpan spn = sSpan[(l * Cfg::kSpanWarps + warp) * kChainSpans + sp];
@@ -546,7 +547,22 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
                     }
                 }
             }
+            };
+            preread();
             __syncthreads();
+            // Race detector in place of compute-sanitizer racecheck (closed on this pool): with a jitter seed every warp
+            // starts its in-place rewrite at a different, pseudo-random time (up to half a prologue apart), so a warp that
+            // read a row another warp owns AFTER the barrier would see it rewritten in some runs and not in others; the
+            // output must stay bit-identical for every seed (tests/test_gpu_parity.py::test_chain_schedule_survives_jitter).
+            if (a.jitter != 0u) {
+                const unsigned hsh = static_cast<unsigned>(splitmix64((static_cast<unsigned long long>(a.jitter) << 32) ^
+                                                                      (static_cast<unsigned long long>(tile) << 8) ^ (warp << 2) ^ l));
+                const long long until = clock64() + (hsh & 4095u);
+                while (clock64() < until) {}
+                // negative control (seed bit 31): fetch the neighbour rows AFTER the barrier and the delay, i.e. commit the
+                // very read-after-overwrite the schedule forbids -- the test checks that this DOES change the output
+                if (a.jitter & 0x80000000u) preread();
+            }
             tick(2 + 4 * l);
 #pragma unroll 1
             for (int sp = 0; sp < kChainSpans; ++sp) {

@@ -106,6 +106,7 @@ struct snacb_handle_s {
     bool chain_ws = false;              // SNACB_CHAIN_WS=1: warp-specialised, block-pipelined chain kernel where it applies
     bool no_fold = false;               // SNACB_NO_FOLD=1: general (fp32 Snake) chain variant even where the folded one is safe (A/B)
     int chain_prof = 0;                 // SNACB_CHAIN_PROF=1|2: in-kernel clock64 phase timing of k_chain, printed per launch (debug)
+    unsigned chain_jitter = 0;          // SNACB_CHAIN_JITTER=seed: pseudo-random per-warp delays inside k_chain's in-place prologue (race detector)
     bool no_chain = false;              // SNACB_NO_CHAIN=1: per-layer kernels instead of the fused chain
     bool no_convt_res = false;          // SNACB_NO_CONVT_RES=1: generic k_gemm_tc for every ConvTranspose
     bool no_trim = false;               // SNACB_NO_TRIM=1: sliced output still decodes every sample of the window
@@ -602,6 +603,7 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
             const bool ws = h->chain_ws && chain_ws_supported(b.Cout, hk);
             memcpy(ca.spans, ws ? b.spans_ws : b.spans, sizeof ca.spans);
             ca.tile_counter = h->tile_counter;
+            ca.jitter = h->chain_jitter;
             CK(h, cudaMemsetAsync(h->tile_counter, 0, sizeof(int), st));
             const bool fold = hk && b.fold && !h->no_fold;
             CUtensorMap my, moe, mom;
@@ -856,6 +858,7 @@ int snacb_create(snacb_handle* out, const snacb_weights* w, int device) {
     if (const char* e = getenv("SNACB_NO_CHAIN")) h->no_chain = atoi(e) != 0;
     if (const char* e = getenv("SNACB_NO_FOLD")) h->no_fold = atoi(e) != 0;
     if (const char* e = getenv("SNACB_CHAIN_WS")) h->chain_ws = atoi(e) != 0 && chain_ws_built();
+    if (const char* e = getenv("SNACB_CHAIN_JITTER")) h->chain_jitter = static_cast<unsigned>(strtoul(e, nullptr, 10));
     if (const char* e = getenv("SNACB_TMAP_CACHE")) { const long n = atol(e); if (n >= 1) h->max_act_maps = static_cast<size_t>(n); }
     if (const char* e = getenv("SNACB_CHAIN_PROF")) h->chain_prof = atoi(e);
     if (const char* e = getenv("SNACB_NO_TRIM")) h->no_trim = atoi(e) != 0;
