@@ -48,8 +48,9 @@ typedef enum {
                                       contractions (tcgen05, kind::f16) with fp16 operands, fp32 accumulate  */
 #define SNACB_KEEP_TAPS      0x8   /* debug: keep every stage's output for snacb_debug_tap     */
 #define SNACB_STREAM_FP32    0x10  /* tensor-core path: keep the residual stream in fp32 between kernels  */
-#define SNACB_BF16           0x20  /* tensor-core path: bf16 operands / activations instead of fp16 (same
-                                      rate; 3 fewer mantissa bits -- see DESIGN.md "precision")              */
+#define SNACB_BF16           0x20  /* tensor-core path: every contraction as a bf16 tcgen05.mma on exactly split operands
+                                      (A = hi + lo, W = hi + lo: three MMAs), activations stored in fp16 -- the bf16x3 path,
+                                      47.7 dB; one kernel per layer, ~3x slower than the default (DESIGN.md "precision")   */
 #define SNACB_UNFUSED        0x40  /* tensor-core path: one kernel per layer instead of the fused
                                       NoiseBlock + ResidualUnit chain (A/B checks, per-stage taps)          */
 

@@ -95,3 +95,38 @@ if __name__ == "__main__":
     print("bf16 ops W2, fp16 st ", snr(ref, decode_emul(m, codes, noises, bf, store_dt=hf, w_parts_full=2, w_parts_res=2)))
     print("bf16 W2+A2, fp16 st  ", snr(ref, decode_emul(m, codes, noises, bf, store_dt=hf, w_parts_full=2, w_parts_res=2, a_parts=2)))
     print("bf16 W2, b1 unfused, fp32 stream", snr(ref, decode_emul(m, codes, noises, bf, chain_blocks=(2, 3), w_parts_full=2, w_parts_res=2, fp32_stream_unfused=True)))
+
+
+@torch.inference_mode()
+def decode_emul_unfused(m, codes, noises, op_dt, st_dt, w_parts, a_parts_gemm, a_parts_res):
+    """Every layer its own kernel: outputs stored in st_dt; GEMM A operands (loaded from storage) and ResidualUnit A operands
+    (built in registers) split into a_parts_* values of op_dt, weights into w_parts."""
+    z = m.quantizer.from_codes(codes)
+    dec = m.decoder.model
+    a0 = rnd(dec[0](z), st_dt)
+    x = F.conv1d(split(a0, op_dt, a_parts_gemm), split(wfold(dec[1]), op_dt, w_parts), dec[1].bias)
+    for bi in range(4):
+        blk = dec[2 + bi].block
+        x = rnd(snake(x, blk[0].alpha), st_dt)
+        ct = blk[1]
+        y = F.conv_transpose1d(split(x, op_dt, a_parts_gemm), split(wfold(ct), op_dt, w_parts), ct.bias, stride=ct.stride,
+                               padding=ct.padding, output_padding=ct.output_padding)
+        y = rnd(y, st_dt)
+        x = rnd(y + noises[bi] * F.conv1d(split(y, op_dt, a_parts_gemm), split(wfold(blk[2].linear), op_dt, w_parts)), st_dt)
+        for ri in range(3):
+            ru = blk[3 + ri].block
+            h = F.conv1d(snake(x, ru[0].alpha), wfold(ru[1]), ru[1].bias, dilation=ru[1].dilation, padding=ru[1].padding,
+                         groups=ru[1].groups)
+            a = split(snake(h, ru[2].alpha), op_dt, a_parts_res)
+            x = x + F.conv1d(a, split(wfold(ru[3]), op_dt, w_parts), ru[3].bias)
+            if ri < 2:
+                x = rnd(x, st_dt)
+    x = rnd(snake(x, dec[6].alpha), st_dt)
+    return torch.tanh(dec[7](x))
+
+
+if __name__ == "__main__":
+    # the bf16x3 path that was built is the (2, 2, 1) row: predicted 47.72 dB, measured 47.74 dB on B200
+    print("--- unfused, fp16 storage, bf16 MMA operands")
+    for wp, ag, ar in ((1, 1, 1), (2, 1, 1), (2, 2, 1), (2, 2, 2), (1, 2, 2), (2, 1, 2)):
+        print(f"W x{wp}, GEMM A x{ag}, res A x{ar}:", snr(ref, decode_emul_unfused(m, codes, noises, bf, hf, wp, ag, ar)))

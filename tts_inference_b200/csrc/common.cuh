@@ -47,6 +47,10 @@ struct GemmArgs {
     const int* stream_keys; // optional [S]: counter RNG key of each stream instead of stream_offset + s
     int t0;                 // absolute index of output row 0 in its stream (counter RNG): a streaming session keeps a sliding
                             // window of each stream in its buffers, the noise stays keyed by the absolute time step
+    int a_wrap;             // > 0: the A tensor holds only a_wrap 64-column chunks; K chunk kc reads chunk kc % a_wrap (bf16x3:
+                            // A'' = [hi | lo | hi] and [a | a] are never materialised beyond [hi | lo] and [a])
+    int mma_bf16;           // 1: the MMA reads its operands as bf16 whatever the storage type of resid / out is (the bf16x3
+                            // path: fp16 storage, A and W pre-split into bf16 hi / lo column blocks, see snacb.cu)
     const void* resid;      // residual / y tensor, [S*Tin*up][Cout] (16-bit operand type on the tensor-core path)
     void* out;              // [S*Tin*up][Cout]
 };

@@ -45,6 +45,10 @@ void launch_vq_stem(const int32_t* c0, const int32_t* c1, const int32_t* c2, con
 // latent steps [t_lo, t_hi) of every stream; tok != null: codes are unpacked from the token rows on the fly (c0..c2 unused)
 void launch_gemm_f32(int epi, const GemmArgs& a, const float* A, const float* W, cudaStream_t st);
 void launch_respre_f32(const ResUnitArgs& a, float* P, cudaStream_t st);
+// bf16x3 path: fp16 rows [r_lo, r_lo + r_n) of every stream -> bf16 [rows][2K] = [hi | lo] (exact split; GemmArgs::a_wrap)
+void launch_split3(const __half* x, int S, int T, int K, int r_lo, int r_n, __nv_bfloat16* out, cudaStream_t st);
+// bf16x3 path: ResidualUnit front half from the fp16 stream, rows [r_lo, r_lo + r_n) -> bf16 [rows][C]
+void launch_respre16(const ResUnitArgs& a, int r_lo, int r_n, __nv_bfloat16* out, cudaStream_t st);
 template <typename InT>
 void launch_tail(const InT* a, int S, int T, int t_begin, int n_out, const float* w, float bias, int16_t* pcm,
                  float* wave, cudaStream_t st);

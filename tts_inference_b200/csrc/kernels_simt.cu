@@ -296,6 +296,123 @@ void launch_respre_f32(const ResUnitArgs& a, float* P, cudaStream_t st) {
 }
 
 // ----------------------------------------------------------------------------------------------
+// bf16x3 path (precision = bf16 at the 40 dB bar): activations are STORED in fp16, the tensor
+// cores multiply bf16.  An fp16 value splits EXACTLY into two bf16 values (11 significand bits = 8 + 3), a weight into
+// hi + lo to 16 bits, so  A W^T = A_hi W_hi^T + A_lo W_hi^T + A_hi W_lo^T  with every product exact in fp32: the GEMM sees
+// A'' = [A_hi | A_lo | A_hi] (this kernel) against W'' = [W_hi | W_hi | W_lo] (packed at load) and K'' = 3K.
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_split3(const __half* __restrict__ x, int S, int T, int K, int r_lo, int r_n, __nv_bfloat16* __restrict__ out) {
+    const int k8n = K / 8;
+    const long long total = static_cast<long long>(S) * r_n * k8n;
+    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int k = static_cast<int>(idx % k8n) * 8;
+        const long long rr = idx / k8n;
+        const int s = static_cast<int>(rr / r_n), t = r_lo + static_cast<int>(rr % r_n);
+        const size_t row = static_cast<size_t>(s) * T + t;
+        const uint4 raw = *reinterpret_cast<const uint4*>(x + row * K + k);
+        const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+        uint4 hi, lo;
+        uint32_t* ph = reinterpret_cast<uint32_t*>(&hi);
+        uint32_t* pl = reinterpret_cast<uint32_t*>(&lo);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 v = __half22float2(h2[j]);
+            const __nv_bfloat162 h = __floats2bfloat162_rn(v.x, v.y);
+            const float2 hf = __bfloat1622float2(h);
+            const __nv_bfloat162 l = __floats2bfloat162_rn(v.x - hf.x, v.y - hf.y);
+            ph[j] = *reinterpret_cast<const uint32_t*>(&h);
+            pl[j] = *reinterpret_cast<const uint32_t*>(&l);
+        }
+        // [hi | lo]; the GEMM reads the third block of A'' = [hi | lo | hi] by wrapping its K chunk index (GemmArgs::a_wrap)
+        __nv_bfloat16* o = out + row * (2 * static_cast<size_t>(K)) + k;
+        *reinterpret_cast<uint4*>(o) = hi;
+        *reinterpret_cast<uint4*>(o + K) = lo;
+    }
+}
+
+void launch_split3(const __half* x, int S, int T, int K, int r_lo, int r_n, __nv_bfloat16* out, cudaStream_t st) {
+    const long long total = static_cast<long long>(S) * r_n * (K / 8);
+    if (total <= 0) return;
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148LL * 32) blocks = 148LL * 32;
+    k_split3<<<static_cast<unsigned>(blocks), 256, 0, st>>>(x, S, T, K, r_lo, r_n, out);
+}
+
+// ResidualUnit front half of the bf16x3 path: a = snake2(dw_b + sum_j dw_w[j] * snake1(x[t + (j - 3) d])) in fp32 from the
+// fp16 residual stream, written as bf16 [rows][C] (the 1x1 conv runs against [W_hi | W_lo], reading a twice through
+// GemmArgs::a_wrap).  A thread owns 4 channels and walks kRespreRun steps of one dilation class (rows r, r + d, ...): the
+// 7-tap window of snake1 values slides in registers, so each Snake is evaluated once per element.
+constexpr int kRespreRun = 64;
+__global__ void __launch_bounds__(256)
+k_respre16(ResUnitArgs a, int r_lo, int r_n, __nv_bfloat16* __restrict__ out) {
+    const int c4n = a.C / 4, d = a.dil;
+    const int per_class = (r_n + d - 1) / d;                       // steps of the longest class inside [r_lo, r_lo + r_n)
+    const int segs = (per_class + kRespreRun - 1) / kRespreRun;
+    const long long total = static_cast<long long>(a.S) * d * segs * c4n;
+    const __half* x = static_cast<const __half*>(a.x);
+    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(idx % c4n) * 4;
+        long long rest = idx / c4n;
+        const int seg = static_cast<int>(rest % segs); rest /= segs;
+        const int cls = static_cast<int>(rest % d);
+        const int s = static_cast<int>(rest / d);
+        const float4 al = *reinterpret_cast<const float4*>(a.alpha1 + c);
+        const float4 ia = *reinterpret_cast<const float4*>(a.inv_alpha1 + c);
+        const float4 a2 = *reinterpret_cast<const float4*>(a.alpha2 + c);
+        const float4 i2 = *reinterpret_cast<const float4*>(a.inv_alpha2 + c);
+        const float4 db = *reinterpret_cast<const float4*>(a.dw_b + c);
+        float4 w[7];
+#pragma unroll
+        for (int j = 0; j < 7; ++j) w[j] = *reinterpret_cast<const float4*>(a.dw_w + j * a.C + c);
+        const __half* xs = x + static_cast<size_t>(s) * a.T * a.C + c;
+        auto s1 = [&](int t) -> float4 {                          // snake1(x[t]), zero outside the stream (conv padding)
+            if (t < 0 || t >= a.T) return make_float4(0.f, 0.f, 0.f, 0.f);
+            const uint2 raw = *reinterpret_cast<const uint2*>(xs + static_cast<size_t>(t) * a.C);
+            const float2 x01 = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
+            const float2 x23 = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+            return make_float4(snake_f<true>(x01.x, al.x, ia.x), snake_f<true>(x01.y, al.y, ia.y),
+                               snake_f<true>(x23.x, al.z, ia.z), snake_f<true>(x23.y, al.w, ia.w));
+        };
+        const int t_first = r_lo + cls + seg * kRespreRun * d;     // first output row of this run
+        float4 win[7];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) win[j + 1] = s1(t_first + (j - 3) * d);
+        __nv_bfloat16* os = out + static_cast<size_t>(s) * a.T * a.C + c;
+        for (int k = 0; k < kRespreRun; ++k) {
+            const int t = t_first + k * d;
+            if (t >= r_lo + r_n || t >= a.T) break;
+#pragma unroll
+            for (int j = 0; j < 6; ++j) win[j] = win[j + 1];
+            win[6] = s1(t + 3 * d);
+            float4 acc = db;
+#pragma unroll
+            for (int j = 0; j < 7; ++j) {
+                acc.x = fmaf(w[j].x, win[j].x, acc.x); acc.y = fmaf(w[j].y, win[j].y, acc.y);
+                acc.z = fmaf(w[j].z, win[j].z, acc.z); acc.w = fmaf(w[j].w, win[j].w, acc.w);
+            }
+            const __nv_bfloat162 o01 = __floats2bfloat162_rn(snake_f<true>(acc.x, a2.x, i2.x), snake_f<true>(acc.y, a2.y, i2.y));
+            const __nv_bfloat162 o23 = __floats2bfloat162_rn(snake_f<true>(acc.z, a2.z, i2.z), snake_f<true>(acc.w, a2.w, i2.w));
+            uint2 o;
+            o.x = *reinterpret_cast<const uint32_t*>(&o01);
+            o.y = *reinterpret_cast<const uint32_t*>(&o23);
+            *reinterpret_cast<uint2*>(os + static_cast<size_t>(t) * a.C) = o;
+        }
+    }
+}
+
+void launch_respre16(const ResUnitArgs& a, int r_lo, int r_n, __nv_bfloat16* out, cudaStream_t st) {
+    if (r_n <= 0) return;
+    const int per_class = (r_n + a.dil - 1) / a.dil;
+    const long long total = static_cast<long long>(a.S) * a.dil * ((per_class + kRespreRun - 1) / kRespreRun) * (a.C / 4);
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148LL * 32) blocks = 148LL * 32;
+    k_respre16<<<static_cast<unsigned>(blocks), 256, 0, st>>>(a, r_lo, r_n, out);
+}
+
+// ----------------------------------------------------------------------------------------------
 // Tail: conv 64->1 k7 pad 3 over the (already Snake'd) block-3 output, tanh, optional slice
 // [2048:4096] (vllm_inference/modal_audio_stream.py:94-95,195-198), int16 quantise (:201).
 // One warp = 32 consecutive samples; lane = channel pair; 7-row sliding window in registers.

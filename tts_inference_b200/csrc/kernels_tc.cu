@@ -92,7 +92,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     mbar_wait(&empty[stage], phase ^ 1u);
                     uint8_t* sa = smem + stage * Cfg::kStageBytes;
                     mbar_expect_tx(&full[stage], Cfg::kStageBytes);
-                    tma_load_3d(sa, &tmA, kc * kChunkK, t0 + base_shift - tap, s0, &full[stage]);
+                    tma_load_3d(sa, &tmA, (a.a_wrap > 0 ? kc % a.a_wrap : kc) * kChunkK, t0 + base_shift - tap, s0, &full[stage]);
                     tma_load_2d_hint(sa + kABytes, &tmW, tap * a.K + kc * kChunkK, n0, &full[stage], kL2EvictLast);
                     if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
                 }
@@ -100,7 +100,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
-        constexpr uint32_t idesc = umma_idesc_f16(kTileM, BN, HalfFmt<HT>::kFmt);
+        const uint32_t idesc = umma_idesc_f16(kTileM, BN, a.mma_bf16 ? 1u : HalfFmt<HT>::kFmt);
         int stage = 0; uint32_t phase = 0;
         int as = 0; uint32_t aphase = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -160,12 +160,18 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     float v[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-                    if (EPI == EPI_BIAS || EPI == EPI_BIAS_SNAKE) {
+                    if (EPI == EPI_BIAS || EPI == EPI_BIAS_SNAKE || EPI == EPI_RES || EPI == EPI_RES_SNAKE) {
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
                             const float4 b = __ldg(reinterpret_cast<const float4*>(a.bias + o + j));
                             v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
                         }
+                    }
+                    if (EPI == EPI_RES || EPI == EPI_RES_SNAKE) {           // ResidualUnit: x + (W a + b)
+                        float y[32];
+                        load32(static_cast<const HT*>(a.resid) + orow * a.Cout + o, y);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] += y[j];
                     }
                     if (EPI == EPI_NOISE) {
                         float y[32];
@@ -173,7 +179,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = fmaf(nz, v[j], y[j]);
                     }
-                    if (EPI == EPI_BIAS_SNAKE) {
+                    if (EPI == EPI_BIAS_SNAKE || EPI == EPI_RES_SNAKE) {
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
                             const float4 al = __ldg(reinterpret_cast<const float4*>(a.alpha + o + j));
@@ -247,6 +253,8 @@ static cudaError_t launch_gemm_tc_h(int epi, int out_f32, const GemmArgs& a, con
         if (out_f32) return launch_gemm_tc_e<EPI_NOISE, HT, float>(a, tmA, tmW, sm_count, st);
         return launch_gemm_tc_e<EPI_NOISE, HT, HT>(a, tmA, tmW, sm_count, st);
     }
+    if (epi == EPI_RES) return launch_gemm_tc_e<EPI_RES, HT, HT>(a, tmA, tmW, sm_count, st);
+    if (epi == EPI_RES_SNAKE) return launch_gemm_tc_e<EPI_RES_SNAKE, HT, HT>(a, tmA, tmW, sm_count, st);
     return cudaErrorInvalidValue;
 }
 cudaError_t launch_gemm_tc(int epi, int half_fp16, int out_f32, const GemmArgs& a, const CUtensorMap& tmA,

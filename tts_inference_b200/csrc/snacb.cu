@@ -34,6 +34,7 @@ struct ResW {
     float *alpha1, *inv1, *dw_w, *dw_b, *alpha2, *inv2, *pw_f32, *pw_b;
     void* pw_h[2];          // 16-bit copies: [0] bf16, [1] fp16
     CUtensorMap tm_pw[2];   // box (64, min(C,256)) for k_resunit_tc
+    void* pw_x3 = nullptr;  // bf16x3 path: [C][2C] = [W_hi | W_lo]
     void* pwc_h = nullptr;  // fp16 1x1 weights with 1/alpha2 folded into the K columns (fp16 chain kernel)
     CUtensorMap tm_pwc;
 };
@@ -44,6 +45,7 @@ struct BlockW {
     void* ct_h[2];
     float* nz_f32;                      // [Cout][Cout]
     void* nz_h[2];
+    void *ct_x3 = nullptr, *nz_x3 = nullptr;   // bf16x3 path: per tap [W_hi | W_hi | W_lo] (K'' = 3K)
     ResW res[3];
     float* bias_cum;                    // [3][Cout] running sums of the ResidualUnit 1x1 biases (fused chain)
     bool chain[2];                      // the fused NoiseBlock + ResidualUnit chain covers this block ([0] bf16, [1] fp16)
@@ -77,6 +79,7 @@ struct snacb_handle_s {
     VqStemWeights vq{};
     float *stem_pw_f32 = nullptr, *stem_pw_b = nullptr;
     void* stem_pw_h[2] = {nullptr, nullptr};
+    void* stem_pw_x3 = nullptr;         // bf16x3 path: [1024][3 * 768]
     BlockW blk[4]{};
     float *tail_alpha = nullptr, *tail_inv = nullptr, *tail_w = nullptr;
     float tail_b = 0.f;
@@ -89,6 +92,7 @@ struct snacb_handle_s {
     void* ws_buf[3] = {nullptr, nullptr, nullptr};
     size_t ws_buf_bytes = 0;
     void* ws_a0 = nullptr; size_t ws_a0_bytes = 0;
+    void* ws_split = nullptr; size_t ws_split_bytes = 0;      // bf16x3 path: the split A operand of the running GEMM
     int32_t* ws_codes = nullptr; size_t ws_codes_elems = 0;
     int* tile_counter = nullptr;                              // dynamic tile scheduler of the chain kernel
     int32_t* st_tok = nullptr; size_t st_tok_elems = 0;       // decode_host staging
@@ -107,6 +111,8 @@ struct snacb_handle_s {
     bool no_fold = false;               // SNACB_NO_FOLD=1: general (fp32 Snake) chain variant even where the folded one is safe (A/B)
     int chain_prof = 0;                 // SNACB_CHAIN_PROF=1|2: in-kernel clock64 phase timing of k_chain, printed per launch (debug)
     unsigned chain_jitter = 0;          // SNACB_CHAIN_JITTER=seed: pseudo-random per-warp delays inside k_chain's in-place prologue (race detector)
+    bool bf16_plain = false;            // SNACB_BF16_PLAIN=1: precision bf16 = bf16 STORAGE and single bf16 operands (34 dB; the
+                                        // pre-bf16x3 behaviour, kept for A/B) instead of the bf16x3 path
     bool no_chain = false;              // SNACB_NO_CHAIN=1: per-layer kernels instead of the fused chain
     bool no_convt_res = false;          // SNACB_NO_CONVT_RES=1: generic k_gemm_tc for every ConvTranspose
     bool no_trim = false;               // SNACB_NO_TRIM=1: sliced output still decodes every sample of the window
@@ -180,6 +186,27 @@ int upload_h16(snacb_handle h, void** out, const std::vector<float>& v) {
     CK(h, cudaMemcpy(db, b.data(), b.size() * 2, cudaMemcpyHostToDevice));
     CK(h, cudaMemcpy(df, f.data(), f.size() * 2, cudaMemcpyHostToDevice));
     out[0] = db; out[1] = df;
+    return 0;
+}
+// bf16x3 weights: w [rows][ntaps * K] -> bf16 [rows][ntaps * parts * K]; per tap [hi | hi | lo] (parts = 3, against an
+// A operand [hi | lo | hi]) or [hi | lo] (parts = 2, against [a | a]); hi = bf16(w), lo = bf16(w - hi)
+int upload_x3(snacb_handle h, void** out, const std::vector<float>& v, size_t rows, int ntaps, int K, int parts) {
+    std::vector<__nv_bfloat16> b(rows * ntaps * parts * K);
+    for (size_t r = 0; r < rows; ++r)
+        for (int t = 0; t < ntaps; ++t)
+            for (int k = 0; k < K; ++k) {
+                const float w = v[(r * ntaps + t) * K + k];
+                const __nv_bfloat16 hi = __float2bfloat16_rn(w);
+                const __nv_bfloat16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
+                __nv_bfloat16* d = b.data() + (r * ntaps + t) * static_cast<size_t>(parts) * K + k;
+                d[0] = hi;
+                if (parts == 3) { d[K] = hi; d[2 * K] = lo; } else d[K] = lo;
+            }
+    __nv_bfloat16* db;
+    int rc = dev_alloc(h, &db, b.size());
+    if (rc) return rc;
+    CK(h, cudaMemcpy(db, b.data(), b.size() * 2, cudaMemcpyHostToDevice));
+    *out = db;
     return 0;
 }
 std::vector<float> vec(const float* p, size_t n) { return std::vector<float>(p, p + n); }
@@ -390,8 +417,14 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
               uint64_t seed, int stream_offset, const int32_t* stream_keys, int out_lo, int out_hi, int16_t* pcm,
               float* wave, cudaStream_t st, const SessionPlan* plan = nullptr, int origin_frames = 0) {
     const bool f32 = (flags & SNACB_FP32) != 0;
-    const bool xf32 = f32 || (flags & SNACB_STREAM_FP32);      // residual stream dtype
-    const int hk = (flags & SNACB_BF16) ? 0 : 1;               // 16-bit operand type: 0 bf16, 1 fp16
+    // precision bf16 = the bf16x3 path: activations STORED in fp16, every contraction a bf16 tcgen05.mma on operands split
+    // so that the products are exact (k_split3 / k_respre16 in kernels_simt.cu): A'' = [A_hi | A_lo | A_hi] against
+    // W'' = [W_hi | W_hi | W_lo] for the GEMMs fed from storage, [a | a] against [W_hi | W_lo] for the ResidualUnit 1x1s
+    // (only [A_hi | A_lo] and [a] are materialised: the GEMM wraps its K chunk index, GemmArgs::a_wrap).
+    // One kernel per layer (the fused chain keeps a single 16-bit tile copy and has no room for a second operand).
+    const bool x3 = !f32 && (flags & SNACB_BF16) && !h->bf16_plain;
+    const bool xf32 = f32 || (!x3 && (flags & SNACB_STREAM_FP32));      // residual stream dtype
+    const int hk = ((flags & SNACB_BF16) && !x3) ? 0 : 1;      // 16-bit storage type: 0 bf16, 1 fp16
     const bool taps = (flags & SNACB_KEEP_TAPS) != 0;
     const int T0 = 4 * F;
     if (taps) clear_taps(h);
@@ -445,7 +478,7 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
             if (!want || skip0) { post[bi] = Rng{0, Tb[bi]}; ct_in[bi] = Rng{0, Tinb}; continue; }
             trimmed[bi] = true;
             Rng y;                                                  // ConvTranspose output rows that must be valid
-            const bool unfused = (flags & SNACB_UNFUSED) != 0 || h->no_chain;
+            const bool unfused = (flags & SNACB_UNFUSED) != 0 || h->no_chain || x3;
             if (b.chain[hk] && !unfused) {
                 const bool ws = h->chain_ws && chain_ws_supported(b.Cout, hk);
                 const int rows = (ws ? chain_ws_tile_rows(b.Cout) : chain_tile_rows(b.Cout)) - 2 * kChainHalo;
@@ -485,8 +518,10 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
     float* P = static_cast<float*>(h->ws_buf[2]);
     auto live = [](Rng r) { return r.hi > r.lo; };
 
+    // Wx3: the bf16x3 pack of the weights; a_split: A is already the split operand (ResidualUnit: k_respre16 wrote [a | a]
+    // into ws_split and a.K is its width), otherwise an fp16 tensor that k_split3 expands to 3K columns first
     auto gemm = [&](const char* pname, int epi, bool out_f32, GemmArgs& a, const void* A, const float* Wf,
-                    void* const* Wh, int Wrows, int Wcols) -> int {
+                    void* const* Wh, int Wrows, int Wcols, const void* Wx3 = nullptr, bool a_split = false) -> int {
         tile_boxes(a.Tin, &a.Tbox, &a.Wbox);
         if (a.Wbox != 1) a.t_n = 0;
         else if (!f32 && a.t_n > 0 && a.t_n <= 64) {
@@ -508,6 +543,29 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
         }
         CUtensorMap ma;
         const CUtensorMap* mw;
+        if (x3) {
+            prof_begin(h, pname, st);
+            if (!a_split) {
+                // rows the taps read: [t_lo - 1, t_lo + t_n + 1) (all rows of an untrimmed launch)
+                const int r_lo = a.t_n > 0 ? (a.t_lo > 0 ? a.t_lo - 1 : 0) : 0;
+                const int r_hi = a.t_n > 0 ? (a.t_lo + a.t_n + 1 < a.Tin ? a.t_lo + a.t_n + 1 : a.Tin) : a.Tin;
+                launch_split3(static_cast<const __half*>(A), a.S, a.Tin, a.K, r_lo, r_hi - r_lo,
+                              static_cast<__nv_bfloat16*>(h->ws_split), st);
+                h->launches++;
+                a.a_wrap = 2 * a.K / 64;              // ws_split holds [hi | lo]; K chunks beyond it wrap around to hi
+                a.K *= 3;
+                Wcols *= 3;
+            }
+            a.mma_bf16 = 1;
+            int rc = act_map(h, &ma, h->ws_split, a.a_wrap * 64, a.Tin, a.S, a.Tbox, a.Wbox, 0);
+            if (rc) return rc;
+            rc = weight_map(h, &mw, Wx3, Wrows, Wcols, gemm_tc_block_n(a), 0);
+            if (rc) return rc;
+            cudaError_t le = launch_gemm_tc(epi, 1, 0, a, ma, *mw, h->sm_count, st);     // fp16 resid / out
+            prof_end(h, st);
+            CK(h, le);
+            return 0;
+        }
         int rc = act_map(h, &ma, A, a.K, a.Tin, a.S, a.Tbox, a.Wbox, hk);
         if (rc) return rc;
         rc = weight_map(h, &mw, Wh[hk], Wrows, Wcols, gemm_tc_block_n(a), hk);
@@ -526,7 +584,7 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
         a.bias = h->stem_pw_b; a.alpha = h->blk[0].alpha; a.inv_alpha = h->blk[0].inv_alpha;
         if (trimmed[0]) { a.t_lo = stem_lo; a.t_n = stem_hi - stem_lo; }
         a.out = cur;
-        int rc = stem_live ? gemm("stem_pw", EPI_BIAS_SNAKE, false, a, a0, h->stem_pw_f32, h->stem_pw_h, kDecDim, kLatent) : 0;
+        int rc = stem_live ? gemm("stem_pw", EPI_BIAS_SNAKE, false, a, a0, h->stem_pw_f32, h->stem_pw_h, kDecDim, kLatent, h->stem_pw_x3) : 0;
         if (rc) return rc;
         rc = tap_any("stem", cur, dt_h, (int64_t)S * T0, kDecDim);
         if (rc) return rc;
@@ -546,7 +604,7 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
             a.bias = b.ct_b; a.out = oth;
             snprintf(nm, sizeof nm, "b%d.convt", bi);
             int rc = 0;
-            if (!f32 && !h->no_convt_res && convt_res_supported(b.Cin, b.Cout, b.s) && Tin >= 128) {
+            if (!f32 && !x3 && !h->no_convt_res && convt_res_supported(b.Cin, b.Cout, b.s) && Tin >= 128) {
                 // weights resident in smem, one activation load per tile, row-shifted descriptors per tap
                 CUtensorMap ma, mo;
                 const CUtensorMap* mw;
@@ -562,7 +620,7 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
                 prof_end(h, st);
                 CK(h, le);
                 h->launches++;
-            } else if (!f32 && !h->no_convt_res && convt_ph_supported(b.Cin, b.Cout, b.s) && Tin >= 128) {
+            } else if (!f32 && !x3 && !h->no_convt_res && convt_ph_supported(b.Cin, b.Cout, b.s) && Tin >= 128) {
                 // one output phase's weights resident per CTA group, one activation load per tile
                 CUtensorMap ma;
                 const CUtensorMap* mw;
@@ -577,14 +635,14 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
                 CK(h, le);
                 h->launches++;
             } else {
-                rc = gemm(nm, EPI_BIAS, false, a, cur, b.ct_f32, b.ct_h, b.s * b.Cout, 2 * b.Cin);
+                rc = gemm(nm, EPI_BIAS, false, a, cur, b.ct_f32, b.ct_h, b.s * b.Cout, 2 * b.Cin, b.ct_x3);
             }
             if (rc) return rc;
             rc = tap_any(nm, oth, dt_h, (int64_t)S * T, b.Cout);
             if (rc) return rc;
         }
         // ---- fused NoiseBlock + 3 ResidualUnits + next Snake: oth -> cur, one kernel
-        const bool unfused = (flags & SNACB_UNFUSED) != 0 || h->no_chain;
+        const bool unfused = (flags & SNACB_UNFUSED) != 0 || h->no_chain || x3;
         if (!f32 && !xf32 && !unfused && b.chain[hk]) {
             void* const ob = plan ? plan->out[bi] : cur;      // ping-pong: back into the ConvTranspose's input buffer
             if (plan && !live(post[bi])) { cur = ob; Tin = T; continue; }
@@ -645,7 +703,7 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
             a.t0 = origin_frames * 4 * (T / T0);
             a.resid = oth; a.out = cur;
             snprintf(nm, sizeof nm, "b%d.noise", bi);
-            int rc = gemm(nm, EPI_NOISE, xf32, a, oth, b.nz_f32, b.nz_h, b.Cout, b.Cout);
+            int rc = gemm(nm, EPI_NOISE, xf32, a, oth, b.nz_f32, b.nz_h, b.Cout, b.Cout, b.nz_x3);
             if (rc) return rc;
             rc = tap_any(nm, cur, dt_x, (int64_t)S * T, b.Cout);
             if (rc) return rc;
@@ -679,6 +737,21 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
                 prof_end(h, st);
                 h->launches += 2;
                 CK(h, cudaGetLastError());
+            } else if (x3) {
+                // front half on the CUDA cores (fp32 math on the fp16 stream) -> [a | a] in bf16, then the 1x1 conv as a
+                // bf16 GEMM against [W_hi | W_lo] with the residual add (+ the next Snake) in its epilogue
+                launch_respre16(ra, ra.t_n > 0 ? ra.t_lo : 0, ra.t_n > 0 ? ra.t_n : T, static_cast<__nv_bfloat16*>(h->ws_split), st);
+                prof_end(h, st);
+                h->launches++;
+                CK(h, cudaGetLastError());
+                GemmArgs a{};
+                a.S = S; a.Tin = T; a.K = 2 * b.Cout; a.N = b.Cout; a.Cout = b.Cout; a.ntaps = 1; a.up = 1;
+                a.a_wrap = b.Cout / 64;               // ws_split holds [a]; the second K half reads it again (against W_lo)
+                a.t_lo = ra.t_lo; a.t_n = ra.t_n;
+                a.bias = r.pw_b; a.alpha = an; a.inv_alpha = ian; a.resid = cur; a.out = ro;
+                snprintf(nm, sizeof nm, "b%d.res%d", bi, ri);
+                int rc2 = gemm(nm, last ? EPI_RES_SNAKE : EPI_RES, false, a, nullptr, nullptr, nullptr, b.Cout, 2 * b.Cout, r.pw_x3, true);
+                if (rc2) return rc2;
             } else if (!xf32 && !h->res_v1) {
                 int tile_m, box_rows;
                 resunit2_geometry(ra.C, ra.dil, &tile_m, &box_rows);
@@ -778,6 +851,7 @@ int snacb_create(snacb_handle* out, const snacb_weights* w, int device) {
         auto pw = vec(w->stem_pw_w, (size_t)kDecDim * kLatent);
         RC(upload_f32(h, &h->stem_pw_f32, pw));
         RC(upload_h16(h, h->stem_pw_h, pw));
+        RC(upload_x3(h, &h->stem_pw_x3, pw, kDecDim, 1, kLatent, 3));
         RC(upload_f32(h, &h->stem_pw_b, vec(w->stem_pw_b, kDecDim)));
     }
     // ---- decoder blocks
@@ -792,10 +866,12 @@ int snacb_create(snacb_handle* out, const snacb_weights* w, int device) {
         auto ct = pack_convt(s.convt_w, b.Cin, b.Cout, b.s);
         RC(upload_f32(h, &b.ct_f32, ct));
         RC(upload_h16(h, b.ct_h, ct));
+        RC(upload_x3(h, &b.ct_x3, ct, static_cast<size_t>(b.s) * b.Cout, 2, b.Cin, 3));
         RC(upload_f32(h, &b.ct_b, vec(s.convt_b, b.Cout)));
         auto nz = vec(s.noise_w, (size_t)b.Cout * b.Cout);
         RC(upload_f32(h, &b.nz_f32, nz));
         RC(upload_h16(h, b.nz_h, nz));
+        RC(upload_x3(h, &b.nz_x3, nz, b.Cout, 1, b.Cout, 3));
         for (int ri = 0; ri < 3; ++ri) {
             const snacb_resunit_weights& rs = s.res[ri];
             ResW& r = b.res[ri];
@@ -809,6 +885,7 @@ int snacb_create(snacb_handle* out, const snacb_weights* w, int device) {
             auto pw = vec(rs.pw_w, (size_t)C * C);
             RC(upload_f32(h, &r.pw_f32, pw));
             RC(upload_h16(h, r.pw_h, pw));
+            RC(upload_x3(h, &r.pw_x3, pw, C, 1, C, 2));
             RC(upload_f32(h, &r.pw_b, vec(rs.pw_b, C)));
             for (int k = 0; k < 2; ++k) RC(make_tmap_2d(h, &r.tm_pw[k], r.pw_h[k], C, C, C > 256 ? 256 : C, k));
         }
@@ -856,6 +933,7 @@ int snacb_create(snacb_handle* out, const snacb_weights* w, int device) {
     }
     if (const char* e = getenv("SNACB_RES_V1")) h->res_v1 = atoi(e) != 0;
     if (const char* e = getenv("SNACB_NO_CHAIN")) h->no_chain = atoi(e) != 0;
+    if (const char* e = getenv("SNACB_BF16_PLAIN")) h->bf16_plain = atoi(e) != 0;
     if (const char* e = getenv("SNACB_NO_FOLD")) h->no_fold = atoi(e) != 0;
     if (const char* e = getenv("SNACB_CHAIN_WS")) h->chain_ws = atoi(e) != 0 && chain_ws_built();
     if (const char* e = getenv("SNACB_CHAIN_JITTER")) h->chain_jitter = static_cast<unsigned>(strtoul(e, nullptr, 10));
@@ -883,6 +961,7 @@ void snacb_destroy(snacb_handle h) {
     for (void* p : h->allocs) cudaFree(p);
     for (int i = 0; i < 3; ++i) if (h->ws_buf[i]) cudaFree(h->ws_buf[i]);
     if (h->ws_a0) cudaFree(h->ws_a0);
+    if (h->ws_split) cudaFree(h->ws_split);
     if (h->ws_codes) cudaFree(h->ws_codes);
     if (h->st_tok) cudaFree(h->st_tok);
     if (h->st_pcm) cudaFree(h->st_pcm);
@@ -984,6 +1063,10 @@ int decode_range_impl(snacb_handle h, const int32_t* tok, int B, int tok_stride,
         }
         int rc = grow(h, &h->ws_a0, &h->ws_a0_bytes, G * 4 * frames * kLatent * (f32 ? 4 : 2));
         if (rc) return rc;
+        if ((flags & SNACB_BF16) && !f32 && !h->bf16_plain) {             // bf16x3: the split operand of the widest GEMM input
+            rc = grow(h, &h->ws_split, &h->ws_split_bytes, G * per_stream_elems * 2 * 2);
+            if (rc) return rc;
+        }
         size_t cbytes = h->ws_codes_elems * sizeof(int32_t);
         rc = grow(h, reinterpret_cast<void**>(&h->ws_codes), &cbytes, G * 7 * frames * sizeof(int32_t));
         if (rc) return rc;
@@ -1073,11 +1156,16 @@ Frontier frontier_calc(int F, const int* strides, int chain_mask) {
     f.emit = pos(f.out[3] - 3);
     return f;
 }
-Frontier frontier_of(snacb_handle h, int F, int hk) {
+// does a session with these flags run block bi through the fused chain kernel (else: one kernel per layer)
+bool block_fused(snacb_handle h, int bi, int flags) {
+    if ((flags & SNACB_BF16) && !h->bf16_plain) return false;           // bf16x3 path
+    return h->blk[bi].chain[(flags & SNACB_BF16) ? 0 : 1] && !h->no_chain;
+}
+Frontier frontier_of(snacb_handle h, int F, int flags) {
     int strides[4], mask = 0;
     for (int bi = 0; bi < 4; ++bi) {
         strides[bi] = h->blk[bi].s;
-        if (h->blk[bi].chain[hk] && !h->no_chain) mask |= 1 << bi;
+        if (block_fused(h, bi, flags)) mask |= 1 << bi;
     }
     return frontier_calc(F, strides, mask);
 }
@@ -1125,7 +1213,6 @@ int snacb_session_create(snacb_handle h, int n_slots, int max_frames, int flags,
     s->max_frames = (max_frames + 31) / 32 * 32;              // every stage then has >= 128 rows per slot (whole tiles)
     s->frames.assign(n_slots, 0); s->emitted.assign(n_slots, 0); s->origin.assign(n_slots, 0); s->finished.assign(n_slots, 0);
     const size_t N = static_cast<size_t>(n_slots), Fm = static_cast<size_t>(s->max_frames), T0 = 4 * Fm;
-    const int hk = (flags & SNACB_BF16) ? 0 : 1;
     int rc = sess_alloc(s, reinterpret_cast<void**>(&s->tok), N * 7 * Fm * sizeof(int32_t));
     for (int l = 0; l < 3 && !rc; ++l) rc = sess_alloc(s, reinterpret_cast<void**>(&s->codes[l]), N * (Fm << l) * sizeof(int32_t));
     if (!rc) rc = sess_alloc(s, &s->a0, N * T0 * kLatent * 2);
@@ -1136,7 +1223,7 @@ int snacb_session_create(snacb_handle h, int n_slots, int max_frames, int flags,
         T *= b.s;
         const size_t sz = N * T * b.Cout * 2;
         rc = sess_alloc(s, &s->ct[bi], sz);
-        if (b.chain[hk] && !h->no_chain) {
+        if (block_fused(h, bi, flags)) {
             if (!rc) rc = sess_alloc(s, &s->out[bi], sz);
         } else {
             if (!rc) rc = sess_alloc(s, &s->nz[bi], sz);
@@ -1186,12 +1273,11 @@ int64_t snacb_session_emitted(snacb_session s, int slot) {
 
 int snacb_session_next_emit(snacb_session s, int slot, int new_frames, int final) {
     if (!s || slot < 0 || slot >= s->n_slots || new_frames < 0) return SNACB_ERR_ARG;
-    const int hk = (s->flags & SNACB_BF16) ? 0 : 1;
     // relative to the window's origin (the frontier is translation invariant once it is past the stream's first rows)
     const long long o = s->origin[slot];
     const long long Fl = s->frames[slot] - o + new_frames, El = s->emitted[slot] - 2048 * o;
     if (Fl > 2LL * s->max_frames) return SNACB_ERR_ARG;
-    const long long end = final ? 2048 * Fl : frontier_of(s->h, static_cast<int>(Fl), hk).emit;
+    const long long end = final ? 2048 * Fl : frontier_of(s->h, static_cast<int>(Fl), s->flags).emit;
     return end > El ? static_cast<int>(end - El) : 0;
 }
 
@@ -1227,7 +1313,6 @@ int snacb_session_step(snacb_session s, int slot0, int n, const int32_t* new_tok
     }
     CK(h, cudaSetDevice(h->device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int hk = (s->flags & SNACB_BF16) ? 0 : 1;
     const size_t so = static_cast<size_t>(slot0);
     int32_t* tokp = s->tok + so * 7 * Fm;
     if (slide > 0) {
@@ -1288,7 +1373,11 @@ int snacb_session_step(snacb_session s, int slot0, int n, const int32_t* new_tok
         return SNACB_OK;
     }
     if (new_frames == 0) return SNACB_OK;
-    const Frontier a = frontier_of(h, Fp, hk), b = frontier_of(h, F, hk);
+    const Frontier a = frontier_of(h, Fp, s->flags), b = frontier_of(h, F, s->flags);
+    if ((s->flags & SNACB_BF16) && !h->bf16_plain) {          // bf16x3: split operand of the widest GEMM input, absolute rows
+        int rc = grow(h, &h->ws_split, &h->ws_split_bytes, static_cast<size_t>(n) * 131072 * Fm * 2 * 2);
+        if (rc) return rc;
+    }
     SessionPlan pl{};
     pl.c0 = s->codes[0] + so * Fm; pl.c1 = s->codes[1] + so * 2 * Fm; pl.c2 = s->codes[2] + so * 4 * Fm;
     size_t T = 4 * static_cast<size_t>(Fm);
