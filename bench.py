@@ -257,25 +257,35 @@ def neighbour_rows(dec, args):
         "steps": F_ // k, "ms_all_steps": ms_s, "audio_s_per_s": audio_s / ms_s * 1e3,
         "one_batch_decode_ms": a.elapsed_time(b), "session_bytes": sess.nbytes}
     sess.close()
-    # the reference's sliding 28/7 cadence (one new frame per stream per step) on the session: 1024 streams, 1 and 2 frames
+    # the reference's sliding 28/7 cadence (one new frame per stream per step) on the session: 1024 streams, 1 / 2 / 4 frames
     # per step, against the sliced window call that the sliding policy costs (sliding_window_mode above: one 4-frame window,
     # trimmed to the receptive field of its middle frame, per new frame)
     S2 = 1024
-    tok2 = torch.from_numpy(synth.make_tokens(S2, 24, seed=5)).cuda()
+    tok2 = torch.from_numpy(synth.make_tokens(S2, 48, seed=5)).cuda()
     sess2 = dec.open_session(S2, 32, precision=args.precision)
+    slots = np.arange(S2, dtype=np.int32)
     cad = {}
     for k2 in (1, 2, 4):
+        # ASYNCHRONOUS streams: four cohorts that started 0 / 3 / 6 / 9 frames ago (so their windows also slide at
+        # different steps); every step serves all 1024 in one launch sequence (snacb_session_step_multi)
         sess2.reset()
-        sess2.step(0, tok2[:, :7 * 8], seed=1)                            # warm start: 8 frames held
+        pos = np.zeros(S2, dtype=np.int64)
+        for c in range(4):
+            sel = slots[c::4]
+            f0 = 8 + 3 * (3 - c)
+            sess2.step_multi(sel, tok2[c::4, :7 * f0].contiguous(), seed=1)
+            pos[c::4] = f0
         evs = []
-        for f in range(8, 24, k2):
+        for _ in range(16 // k2 + 2):
+            new = torch.stack([tok2[i, 7 * int(pos[i]):7 * (int(pos[i]) + k2)] for i in range(4)])   # one row per cohort
+            new = new.repeat(S2 // 4, 1).contiguous()            # cohort c = rows c, c + 4, ... (token VALUES do not matter here)
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(); sess2.step(0, tok2[:, 7 * f:7 * (f + k2)], seed=1); b.record()
-            evs.append((a, b))
+            a.record(); sess2.step_multi(slots, new, seed=1); b.record()
+            evs.append((a, b)); pos += k2
         torch.cuda.synchronize()
         ms = sorted(x.elapsed_time(y) for x, y in evs)[len(evs) // 2]
         cad[f"{k2}_frames_per_step"] = {"ms_per_step": ms, "emitted_audio_s_per_s": S2 * k2 * 2048 / SR / ms * 1e3}
-    out["streaming_session"]["cadence_1024_streams"] = cad
+    out["streaming_session"]["cadence_1024_async_streams"] = cad
     sess2.close()
     enc = SnacEncoder(synth.make_encoder_state_dict(0))
     audio = torch.from_numpy(synth.make_audio(64, 2048 * 16)).cuda()

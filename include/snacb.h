@@ -170,6 +170,16 @@ int snacb_session_next_emit(snacb_session s, int slot, int new_frames, int final
 int snacb_session_step(snacb_session s, int slot0, int n, const int32_t* new_tok, int tok_stride, int new_frames, int final,
                        uint64_t seed, const int32_t* stream_keys, int16_t* pcm, int pcm_stride, int* n_emitted,
                        void* stream);
+/* The same step for an ARBITRARY set of slots (slots_host [n], any order, need not be contiguous) that may be at DIFFERENT
+ * positions of their streams: past a stream's first three frames every stage's frontier is affine in the frame count, so
+ * all streams that advance by the same number of frames share one launch sequence, each with its own row offset, buffer
+ * slot and window origin (per-stream maps read by every kernel).  This is the call for asynchronous streams: one step
+ * serves every stream that has `new_frames` new frames, wherever it is.  Streams holding fewer than 3 frames can only be
+ * grouped with streams at exactly the same position.  Not for end of stream (use snacb_session_step with final != 0).
+ * new_tok [n][tok_stride] (device), stream_keys [n] (device) or NULL = slot indices, pcm [n][pcm_stride]. */
+int snacb_session_step_multi(snacb_session s, int n, const int32_t* slots_host, const int32_t* new_tok, int tok_stride,
+                             int new_frames, uint64_t seed, const int32_t* stream_keys, int16_t* pcm, int pcm_stride,
+                             int* n_emitted, void* stream);
 /* Host-side frontier table of a session (no GPU needed): the number of FINAL rows of every stage once `frames` frames are
  * known, snac_24khz strides 8/8/4/2; bit bi of chain_mask = block bi runs the fused chain kernel.  out (>= 22 ints):
  * stem, then per block {ConvTranspose out, NoiseBlock out, ResidualUnit 0/1/2 out} (the last three 0 for a chain block

@@ -361,3 +361,53 @@ def test_session_c_abi_edge_cases(decoder):
     rest = sess.step(1, tok[:, 21:], final=True, seed=5).cpu().numpy()
     assert np.array_equal(np.concatenate([w[:, :n], rest], axis=1), ref)
     sess.close()
+
+
+@pytest.mark.parametrize("precision,k", [("fp16", 1), ("fp16", 3), ("bf16", 2)])
+def test_session_step_multi_serves_asynchronous_streams(decoder, precision, k):
+    """Streams that start at different times and therefore sit at different positions share ONE launch sequence per step
+    (snacb_session_step_multi: per-stream row offset, buffer slot and window origin in every kernel), in scattered slots,
+    with windows sliding at different times -- and each stream still equals its own batch decode bit for bit."""
+    starts = [0, 0, 3, 7, 8, 20]                     # step at which a stream begins
+    lens = [70, 41, 66, 30, 52, 12]                  # frames (several times the 32-frame window)
+    lens = [n - n % k for n in lens]
+    slots = [5, 0, 7, 2, 6, 3]                       # scattered, not contiguous, not ordered
+    n_str = len(lens)
+    tokens = synth.make_tokens(n_str, max(lens), seed=91)
+    tok = torch.from_numpy(tokens).cuda()
+    keys = torch.tensor([11, 4, 9, 1, 30, 7], dtype=torch.int32).cuda()
+    refs = [decoder.decode(tok[i:i + 1, :7 * lens[i]].contiguous(), raw_ids=True, seed=6, precision=precision,
+                           stream_keys=keys[i:i + 1]).cpu().numpy()[0] for i in range(n_str)]
+    sess = decoder.open_session(8, 32, precision=precision)
+    got = [[] for _ in lens]
+    pos = [0] * n_str
+    launches = []
+    for step in range(200):
+        live = [i for i in range(n_str) if step >= starts[i] and pos[i] < lens[i]]
+        if not live and all(pos[i] >= lens[i] for i in range(n_str)):
+            break
+        # streams past their third frame share one call whatever their position; younger ones are grouped by exact position
+        groups = {}
+        for i in live:
+            groups.setdefault(-1 if pos[i] >= 3 else pos[i], []).append(i)
+        for _, members in sorted(groups.items()):
+            new = torch.stack([tok[i, 7 * pos[i]: 7 * (pos[i] + k)] for i in members]).contiguous()
+            l0 = decoder.stats()[0]
+            out = sess.step_multi([slots[i] for i in members], new, seed=6, stream_keys=keys[members].contiguous()).cpu().numpy()
+            launches.append((len(members), decoder.stats()[0] - l0))
+            for row, i in enumerate(members):
+                got[i].append(out[row])
+                pos[i] += k
+        for i in range(n_str):
+            if pos[i] == lens[i] and sess.frames(slots[i]) == lens[i] and sess.emitted(slots[i]) < 2048 * lens[i]:
+                got[i].append(sess.step(slots[i], tok[i:i + 1, :0], final=True, seed=6, stream_keys=keys[i:i + 1]).cpu().numpy()[0])
+    for i in range(n_str):
+        cat = np.concatenate(got[i])
+        assert cat.shape == refs[i].shape, (i, cat.shape)
+        assert np.array_equal(cat, refs[i]), i
+    # a step costs the same number of launches whether it serves one stream or five
+    assert len({l for _, l in launches if l > 0}) <= 3, sorted(set(launches))
+    assert max(m for m, _ in launches) >= 4
+    with pytest.raises(Exception):
+        sess.step_multi([1, 1], tok[:2, :7].contiguous())                 # repeated slot
+    sess.close()

@@ -53,7 +53,7 @@ EXPORTS = [
     "snacb_ingest_create", "snacb_ingest_destroy", "snacb_ingest_reset", "snacb_ingest_window_capacity",
     "snacb_ingest_step", "snacb_ingest_state", "snacb_base64_len", "snacb_pcm_to_base64", "snacb_pcm_to_wav",
     "snacb_session_create", "snacb_session_destroy", "snacb_session_bytes", "snacb_session_max_frames", "snacb_session_reset",
-    "snacb_session_frames", "snacb_session_emitted", "snacb_session_next_emit", "snacb_session_step",
+    "snacb_session_frames", "snacb_session_emitted", "snacb_session_next_emit", "snacb_session_step", "snacb_session_step_multi",
     "snacb_debug_session_frontier", "snacb_experiments_built",
     "snacb_encoder_create", "snacb_encoder_destroy", "snacb_encoder_last_error", "snacb_encoder_launches", "snacb_encode_frames",
     "snacb_encode", "snacb_pack_tokens",
@@ -133,6 +133,8 @@ def load() -> C.CDLL:
     lib.snacb_session_next_emit.argtypes = [vp, C.c_int, C.c_int, C.c_int]
     lib.snacb_session_step.argtypes = [vp, C.c_int, C.c_int, i32p, C.c_int, C.c_int, C.c_int, u64, i32p, i16p, C.c_int,
                                        C.POINTER(C.c_int), vp]
+    lib.snacb_session_step_multi.argtypes = [vp, C.c_int, i32p, i32p, C.c_int, C.c_int, u64, i32p, i16p, C.c_int,
+                                             C.POINTER(C.c_int), vp]
     lib.snacb_debug_session_frontier.argtypes = [C.c_int, C.c_int, i32p, C.c_int]
     lib.snacb_encoder_create.argtypes = [C.POINTER(vp), C.POINTER(EncoderWeights), C.c_int]
     lib.snacb_encoder_destroy.argtypes = [vp]

@@ -284,6 +284,31 @@ class StreamingSession:
             raise SnacbError(f"snacb_session_next_emit failed ({r})")
         return r
 
+    def step_multi(self, slots, new_tokens, *, seed: int = 0, stream_keys=None):
+        """One step for an arbitrary set of slots that may be at different positions of their streams (asynchronous
+        streams): ``slots`` a sequence of n distinct slot indices, ``new_tokens`` cuda int32 [n, 7k] with k >= 1 new frames
+        for each.  Returns int16 [n, m], the same m for all (2048 k once a stream holds 3 frames).  Not for end of stream."""
+        import torch
+        slots = np.ascontiguousarray(np.asarray(slots, dtype=np.int32))
+        assert new_tokens.is_cuda and new_tokens.dtype == torch.int32 and new_tokens.dim() == 2
+        new_tokens = new_tokens.contiguous()
+        n, w = new_tokens.shape
+        assert slots.shape == (n,) and w >= FRAME
+        k = w // FRAME
+        m = max(self.next_emit(int(s), k) for s in slots[:1]) if n else 0
+        out = torch.empty((n, m), dtype=torch.int16, device=new_tokens.device)
+        keys = None
+        if stream_keys is not None:
+            assert stream_keys.is_cuda and stream_keys.dtype == torch.int32 and stream_keys.numel() == n
+            stream_keys = stream_keys.contiguous()
+            keys = stream_keys.data_ptr()
+        got = C.c_int(0)
+        rc = self._lib.snacb_session_step_multi(self._s, n, slots.ctypes.data, new_tokens.data_ptr(), w, k, C.c_uint64(seed), keys,
+                                                out.data_ptr() if m else None, m, C.byref(got), self._dec._stream_ptr())
+        self._dec._check(rc, "snacb_session_step_multi")
+        assert got.value == m, (got.value, m)
+        return out
+
     def step(self, slot0: int, new_tokens, *, final: bool = False, seed: int = 0, stream_keys=None, out=None):
         """new_tokens: cuda int32 [n, 7k] (k >= 0 new frames for slots slot0 .. slot0+n-1; k = 0 only with ``final``).
         Returns int16 [n, m]: the m samples per slot that became final (m may be 0)."""

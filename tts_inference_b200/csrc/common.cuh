@@ -23,6 +23,16 @@ enum Epi : int {
     EPI_RES_SNAKE = 4,   // out = snake(x + acc + bias; alpha[o])        (last ResidualUnit of a block)
 };
 
+// Per-stream addressing of a streaming-session launch (all null for the stateless decode): stream s of the launch lives in
+// buffer slot slot[s]; its row range starts off[s] FRAMES after the launch's reference range (streams at different
+// positions that advance by the same number of frames share one launch: past a stream's first three frames every
+// stage's frontier is affine in the frame count); its window's row 0 is stream frame org[s] (the NoiseBlock noise is
+// keyed by the absolute time step).  `rpf` (rows per frame of the tensor at hand) travels beside the map.
+struct StreamMap { const int* slot; const int* off; const int* org; };
+__device__ __forceinline__ int sm_slot(const StreamMap& m, int s) { return m.slot ? m.slot[s] : s; }
+__device__ __forceinline__ int sm_off(const StreamMap& m, int s, int rpf) { return m.off ? m.off[s] * rpf : 0; }
+__device__ __forceinline__ int sm_org(const StreamMap& m, int s, int rpf) { return m.org ? m.org[s] * rpf : 0; }
+
 // A "row GEMM with taps":  out[(s, m*up + p), o] = epi( sum_tap sum_k A[(s, m + shift(p,tap)), k] * W[(p,o), tap*K + k] )
 // with A rows outside [0, Tin) of their stream reading as zero.  Plain 1x1 convs are ntaps=1, up=1.
 struct GemmArgs {
@@ -47,6 +57,7 @@ struct GemmArgs {
     const int* stream_keys; // optional [S]: counter RNG key of each stream instead of stream_offset + s
     int t0;                 // absolute index of output row 0 in its stream (counter RNG): a streaming session keeps a sliding
                             // window of each stream in its buffers, the noise stays keyed by the absolute time step
+    StreamMap map; int rpf; // streaming session: per-stream slot / row offset / origin; rpf = A (input) rows per frame
     int a_wrap;             // > 0: the A tensor holds only a_wrap 64-column chunks; K chunk kc reads chunk kc % a_wrap (bf16x3:
                             // A'' = [hi | lo | hi] and [a | a] are never materialised beyond [hi | lo] and [a])
     int mma_bf16;           // 1: the MMA reads its operands as bf16 whatever the storage type of resid / out is (the bf16x3
@@ -67,6 +78,7 @@ struct ResUnitArgs {
     const float* pw_b;       // [C]
     const float* alpha_next; const float* inv_alpha_next;  // [C] (EPI_RES_SNAKE)
     unsigned long long* prof;   // debug: clock64 sums of CTA 0 (SNACB_RES_PROF=1), else null
+    StreamMap map; int rpf;     // streaming session (see StreamMap); rpf = rows per frame of x / out
 };
 
 // Fused NoiseBlock + 3 ResidualUnits of one DecoderBlock (kernels_chain.cu).
@@ -93,6 +105,7 @@ struct ChainArgs {
     int noise_stage, stream_offset;
     const int* stream_keys;       // optional [S]: counter RNG key of each stream instead of stream_offset + s
     int t0;                       // absolute index of row 0 in its stream (counter RNG; see GemmArgs::t0)
+    StreamMap map; int rpf;       // streaming session (see StreamMap); rpf = rows per frame of y / out
     ChainSpan spans[3][kChainWarps][kChainSpans];
     unsigned jitter;              // debug (SNACB_CHAIN_JITTER=seed): every warp spins a pseudo-random 0..4095 cycles after each
                                   // barrier of the in-place prologue -- the race detector for the schedule (see k_chain)

@@ -41,17 +41,24 @@ void launch_unpack(const int32_t* tok, int B, int ntok, int F, int raw_ids, int3
                    cudaStream_t st);
 template <typename OutT>
 void launch_vq_stem(const int32_t* c0, const int32_t* c1, const int32_t* c2, const int32_t* tok, int tok_stride, int raw_ids,
-                    int S, int F, int t_lo, int t_hi, const VqStemWeights& w, OutT* out, cudaStream_t st);
+                    int S, int F, int t_lo, int t_hi, const VqStemWeights& w, OutT* out, cudaStream_t st,
+                    const StreamMap& map = StreamMap{nullptr, nullptr, nullptr});
 // latent steps [t_lo, t_hi) of every stream; tok != null: codes are unpacked from the token rows on the fly (c0..c2 unused)
 void launch_gemm_f32(int epi, const GemmArgs& a, const float* A, const float* W, cudaStream_t st);
 void launch_respre_f32(const ResUnitArgs& a, float* P, cudaStream_t st);
+// streaming session: scatter each stream's new tokens to its own position; slide full windows (kernels_simt.cu)
+void launch_session_scatter(const int32_t* new_tok, int tok_stride, int n_int, const int* slot, const int* pos, int32_t* tok_buf,
+                            int slot_ints, const int32_t* keys_in, int32_t* keys_out, int n, cudaStream_t st);
+void launch_session_slide(void* buf, size_t slot_bytes, size_t frame_bytes, int keep, const int* list, const int* slide, int n,
+                          cudaStream_t st);
 // bf16x3 path: fp16 rows [r_lo, r_lo + r_n) of every stream -> bf16 [rows][2K] = [hi | lo] (exact split; GemmArgs::a_wrap)
-void launch_split3(const __half* x, int S, int T, int K, int r_lo, int r_n, __nv_bfloat16* out, cudaStream_t st);
+void launch_split3(const __half* x, int S, int T, int K, int r_lo, int r_n, __nv_bfloat16* out, cudaStream_t st,
+                   const StreamMap& map = StreamMap{nullptr, nullptr, nullptr}, int rpf = 0);
 // bf16x3 path: ResidualUnit front half from the fp16 stream, rows [r_lo, r_lo + r_n) -> bf16 [rows][C]
 void launch_respre16(const ResUnitArgs& a, int r_lo, int r_n, __nv_bfloat16* out, cudaStream_t st);
 template <typename InT>
 void launch_tail(const InT* a, int S, int T, int t_begin, int n_out, const float* w, float bias, int16_t* pcm,
-                 float* wave, cudaStream_t st);
+                 float* wave, cudaStream_t st, const StreamMap& map = StreamMap{nullptr, nullptr, nullptr});
 template <typename T>
 void launch_to_f32(const T* in, float* out, size_t n, cudaStream_t st);
 

@@ -308,12 +308,13 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
     };
     auto tile_coords = [&](int tile, int& s, int& t_start) {
         s = tile / tiles_t;
-        t_start = (a.t_n > 0 ? a.t_lo : 0) + (tile % tiles_t) * Cfg::kROut - kHalo;
+        t_start = (a.t_n > 0 ? a.t_lo : 0) + sm_off(a.map, s, a.rpf) + (tile % tiles_t) * Cfg::kROut - kHalo;
     };
     auto load_block = [&](int s, int t_start, int b) {      // thread 0; ld_bar's expect_tx covers the whole tile
+        const int sl = sm_slot(a.map, s);
 #pragma unroll
         for (int kc = 0; kc < CH; ++kc)
-            tma_load_3d_hint(sX + kc * Cfg::kPlane + b * 16384, &tmY, kc * 64, t_start + b * 128, s, ld_bar, kL2EvictFirst);
+            tma_load_3d_hint(sX + kc * Cfg::kPlane + b * 16384, &tmY, kc * 64, t_start + b * 128, sl, ld_bar, kL2EvictFirst);
     };
     int tile = blockIdx.x;
     if (tid == 0 && tile < num_tiles) {
@@ -503,7 +504,7 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
                 float v = 0.f;
                 if (static_cast<unsigned>(t) < static_cast<unsigned>(a.T))
                     v = a.noise ? a.noise[static_cast<size_t>(s) * a.T + t]
-                                : counter_normal(key, noise_counter(a.stream_keys ? a.stream_keys[s] : a.stream_offset + s, t + a.t0));
+                                : counter_normal(key, noise_counter(a.stream_keys ? a.stream_keys[s] : a.stream_offset + s, t + a.t0 + sm_org(a.map, s, a.rpf)));
                 sNz[i] = v;
             }
         }
@@ -554,6 +555,7 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
             // starts its in-place rewrite at a different, pseudo-random time (up to half a prologue apart), so a warp that
             // read a row another warp owns AFTER the barrier would see it rewritten in some runs and not in others; the
             // output must stay bit-identical for every seed (tests/test_gpu_parity.py::test_chain_schedule_survives_jitter).
+            // (Measured cost of carrying it in the product kernel: < 0.5 % of the chain.)
             if (a.jitter != 0u) {
                 const unsigned hsh = static_cast<unsigned>(splitmix64((static_cast<unsigned long long>(a.jitter) << 32) ^
                                                                       (static_cast<unsigned long long>(tile) << 8) ^ (warp << 2) ^ l));
@@ -607,14 +609,15 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
         // ---------------------------------------------------------------- stream the tile out, refill behind it
         if (tid == 0) {
             const int t_out = t_start + kHalo;
+            const int sl = sm_slot(a.map, s);
 #pragma unroll
             for (int b = 0; b < NB; ++b) {
 #pragma unroll
                 for (int kc = 0; kc < CH; ++kc) {
                     const uint8_t* src = sX + kc * Cfg::kPlane + b * 16384;
-                    if (b == 0) tma_store_3d(&tmOe, src + kHalo * 128, kc * 64, t_out, s);
-                    else if (b == NB - 1) tma_store_3d(&tmOe, src, kc * 64, t_start + b * 128, s);
-                    else tma_store_3d(&tmOm, src, kc * 64, t_start + b * 128, s);
+                    if (b == 0) tma_store_3d(&tmOe, src + kHalo * 128, kc * 64, t_out, sl);
+                    else if (b == NB - 1) tma_store_3d(&tmOe, src, kc * 64, t_start + b * 128, sl);
+                    else tma_store_3d(&tmOm, src, kc * 64, t_start + b * 128, sl);
                 }
                 bulk_commit_group();
             }

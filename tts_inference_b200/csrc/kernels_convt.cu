@@ -102,11 +102,12 @@ k_convt_res(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 tma_load_2d_hint(sW + j * Cfg::kWChunk, &tmW, j * 64, 0, wbar, kL2EvictLast);
             int stage = 0; uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int s = tile / tiles_t, m0 = t_lo + (tile % tiles_t) * 128;
+                const int s = tile / tiles_t, m0 = t_lo + sm_off(a.map, s, a.rpf) + (tile % tiles_t) * 128;
+                const int sl = sm_slot(a.map, s);
                 mbar_wait(&empty[stage], phase ^ 1u);
                 mbar_expect_tx(&full[stage], Cfg::kAStage);
                 for (int kc = 0; kc < Cfg::kCH; ++kc)
-                    tma_load_3d(sA + stage * Cfg::kAStage + kc * Cfg::kAChunk, &tmA, kc * 64, m0 - 1, s, &full[stage]);
+                    tma_load_3d(sA + stage * Cfg::kAStage + kc * Cfg::kAChunk, &tmA, kc * 64, m0 - 1, sl, &full[stage]);
                 if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
             }
         }
@@ -152,7 +153,8 @@ k_convt_res(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const bool leader = (warp == 2 && lane == 0);
         int as = 0; uint32_t aphase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int s = tile / tiles_t, m0 = t_lo + (tile % tiles_t) * 128;
+            const int s = tile / tiles_t, m0 = t_lo + sm_off(a.map, s, a.rpf) + (tile % tiles_t) * 128;
+                const int sl = sm_slot(a.map, s);
             mbar_wait(&tfull[as], aphase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * Cfg::kN + half * COUT;
@@ -183,7 +185,7 @@ k_convt_res(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             fence_proxy_async_smem();
             asm volatile("bar.sync 1, %0;" ::"n"(Cfg::kEpiWarps * 32) : "memory");
             if (leader) {
-                tma_store_3d(&tmO, sO, 0, m0 * S, s);                      // rows beyond T are clipped by TMA
+                tma_store_3d(&tmO, sO, 0, m0 * S, sl);                      // rows beyond T are clipped by TMA
                 bulk_commit_group();
             }
             if (++as == 2) { as = 0; aphase ^= 1u; }
@@ -272,11 +274,12 @@ k_convt_ph(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
                 tma_load_2d_hint(sW + j * Cfg::kWChunk, &tmW, j * 64, p * COUT, wbar, kL2EvictLast);
             int stage = 0; uint32_t phase = 0;
             for (int tile = gi; tile < num_tiles; tile += gs) {
-                const int s = tile / tiles_t, m0 = t_lo + (tile % tiles_t) * 128;
+                const int s = tile / tiles_t, m0 = t_lo + sm_off(a.map, s, a.rpf) + (tile % tiles_t) * 128;
+                const int sl = sm_slot(a.map, s);
                 for (int kc = 0; kc < Cfg::kCH; ++kc) {
                     mbar_wait(&empty[stage], phase ^ 1u);
                     mbar_expect_tx(&full[stage], Cfg::kAChunk);
-                    tma_load_3d(sA + stage * Cfg::kAChunk, &tmA, kc * 64, m0 - 1, s, &full[stage]);
+                    tma_load_3d(sA + stage * Cfg::kAChunk, &tmA, kc * 64, m0 - 1, sl, &full[stage]);
                     if (++stage == Cfg::kRing) { stage = 0; phase ^= 1u; }
                 }
             }
@@ -318,8 +321,9 @@ k_convt_ph(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
         HT* out = static_cast<HT*>(a.out);
         int as = 0; uint32_t aphase = 0;
         for (int tile = gi; tile < num_tiles; tile += gs) {
-            const int s = tile / tiles_t, m = t_lo + (tile % tiles_t) * 128 + q * 32 + lane;
-            const bool valid = (m < a.Tin) && (m < t_lo + t_n);
+            const int s = tile / tiles_t, so = sm_off(a.map, s, a.rpf), m = t_lo + so + (tile % tiles_t) * 128 + q * 32 + lane;
+            const int sl = sm_slot(a.map, s);
+            const bool valid = (m < a.Tin) && (m < t_lo + so + t_n);
             mbar_wait(&tfull[as], aphase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * COUT + half * 64;
@@ -331,7 +335,7 @@ k_convt_ph(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[as]);
             if (valid) {
-                HT* dst = out + (static_cast<size_t>(s) * a.Tin * S + static_cast<size_t>(m) * S + p) * COUT + half * 64;
+                HT* dst = out + (static_cast<size_t>(sl) * a.Tin * S + static_cast<size_t>(m) * S + p) * COUT + half * 64;
                 float v[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r0[j]) + sBias[half * 64 + j];

@@ -177,7 +177,8 @@ k_resunit2(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
             int g = 0;
             for (int n = 0; n < my_tiles; ++n) {
                 const int tile = blockIdx.x + n * gridDim.x;
-                const int s = tile / tiles_t, t0 = t_lo + (tile % tiles_t) * Cfg::kTileM;
+                const int s_ = tile / tiles_t, s = sm_slot(a.map, s_);             // s: the stream's buffer slot (addressing only)
+                const int t0 = t_lo + sm_off(a.map, s_, a.rpf) + (tile % tiles_t) * Cfg::kTileM;
                 for (int kc = 0; kc < Cfg::kChunks; ++kc, ++g) {
                     const int sx = g % Cfg::kNXS;
                     if (g >= Cfg::kNXS) mbar_wait(&x_empty[sx], ((g / Cfg::kNXS) - 1) & 1);
@@ -252,7 +253,8 @@ k_resunit2(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
         constexpr int kIters = Cfg::kAccs * (C / 32);          // 32-column pieces per tile and quadrant
         for (int n = 0; n < my_tiles; ++n) {
             const int tile = blockIdx.x + n * gridDim.x;
-            const int s = tile / tiles_t, t0 = t_lo + (tile % tiles_t) * Cfg::kTileM;
+            const int s_ = tile / tiles_t, s = sm_slot(a.map, s_);             // s: the stream's buffer slot (addressing only)
+                const int t0 = t_lo + sm_off(a.map, s_, a.rpf) + (tile % tiles_t) * Cfg::kTileM;
             const int as = n % Cfg::kAccStages;
             const size_t srow = static_cast<size_t>(s) * a.T;
             // residual of the first piece is fetched before waiting for the accumulator
@@ -320,7 +322,8 @@ k_resunit2(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
             const HT* x = static_cast<const HT*>(a.x);
             HT* out = static_cast<HT*>(a.out);
             const int tile = blockIdx.x + n * gridDim.x;
-            const int s = tile / tiles_t, t0 = t_lo + (tile % tiles_t) * Cfg::kTileM;
+            const int s_ = tile / tiles_t, s = sm_slot(a.map, s_);             // s: the stream's buffer slot (addressing only)
+                const int t0 = t_lo + sm_off(a.map, s_, a.rpf) + (tile % tiles_t) * Cfg::kTileM;
             const int as = n % Cfg::kAccStages;
             const int q = warp & 3, rest = warp >> 2;
             const int ac = (Cfg::kAccs == 2) ? (rest & 1) : 0;

@@ -62,10 +62,11 @@ constexpr int kVqTile = 16;
 template <typename OutT>
 __global__ void __launch_bounds__(256)
 k_vq_stem(const int32_t* __restrict__ c0, const int32_t* __restrict__ c1, const int32_t* __restrict__ c2,
-          const int32_t* __restrict__ tok, int tok_stride, int raw_ids, int F, int tile_lo, VqStemWeights w,
-          OutT* __restrict__ out) {
+          const int32_t* __restrict__ tok, int tok_stride, int raw_ids, int F, int t_lo, VqStemWeights w,
+          OutT* __restrict__ out, const StreamMap map) {
     const int T0 = 4 * F;
-    const int s = blockIdx.y, t0 = (tile_lo + blockIdx.x) * kVqTile;
+    // streaming session: the stream's tokens / output live in its slot, its rows start off[s] frames further on
+    const int s = sm_slot(map, blockIdx.y), t0 = t_lo + sm_off(map, blockIdx.y, 4) + blockIdx.x * kVqTile;
     __shared__ float emb[3][kVqTile + 6][kCodeDim];
     __shared__ int ok[kVqTile + 6];
     for (int idx = threadIdx.x; idx < 3 * (kVqTile + 6); idx += blockDim.x) {
@@ -138,19 +139,21 @@ k_vq_stem(const int32_t* __restrict__ c0, const int32_t* __restrict__ c1, const 
 
 template <typename OutT>
 void launch_vq_stem(const int32_t* c0, const int32_t* c1, const int32_t* c2, const int32_t* tok, int tok_stride, int raw_ids,
-                    int S, int F, int t_lo, int t_hi, const VqStemWeights& w, OutT* out, cudaStream_t st) {
-    // latent steps [t_lo, t_hi) of every stream, in whole 16-step tiles
-    const int tile_lo = t_lo / kVqTile, tile_hi = (t_hi + kVqTile - 1) / kVqTile;
-    if (tile_hi <= tile_lo) return;
-    dim3 grid(tile_hi - tile_lo, S, kLatent / 256);
-    k_vq_stem<OutT><<<grid, 256, 0, st>>>(c0, c1, c2, tok, tok_stride, raw_ids, F, tile_lo, w, out);
+                    int S, int F, int t_lo, int t_hi, const VqStemWeights& w, OutT* out, cudaStream_t st,
+                    const StreamMap& map) {
+    // latent steps [t_lo, t_hi) of every stream, in 16-step tiles from t_lo rounded down to a tile (the stateless decode) or
+    // from the stream's own first step (session: t_lo + off[s] frames); steps past t_hi in the last tile are computed too
+    if (t_hi <= t_lo) return;
+    const int lo = map.off ? t_lo : (t_lo / kVqTile) * kVqTile;
+    dim3 grid((t_hi - lo + kVqTile - 1) / kVqTile, S, kLatent / 256);
+    k_vq_stem<OutT><<<grid, 256, 0, st>>>(c0, c1, c2, tok, tok_stride, raw_ids, F, lo, w, out, map);
 }
 template void launch_vq_stem<float>(const int32_t*, const int32_t*, const int32_t*, const int32_t*, int, int, int, int, int, int,
-                                    const VqStemWeights&, float*, cudaStream_t);
+                                    const VqStemWeights&, float*, cudaStream_t, const StreamMap&);
 template void launch_vq_stem<__nv_bfloat16>(const int32_t*, const int32_t*, const int32_t*, const int32_t*, int, int, int, int, int, int,
-                                            const VqStemWeights&, __nv_bfloat16*, cudaStream_t);
+                                            const VqStemWeights&, __nv_bfloat16*, cudaStream_t, const StreamMap&);
 template void launch_vq_stem<__half>(const int32_t*, const int32_t*, const int32_t*, const int32_t*, int, int, int, int, int, int,
-                                     const VqStemWeights&, __half*, cudaStream_t);
+                                     const VqStemWeights&, __half*, cudaStream_t, const StreamMap&);
 
 // ----------------------------------------------------------------------------------------------
 // fp32 row-GEMM with taps (CUDA cores).  64x64 tile, 16-deep K steps, 4x4 register micro-tile.
@@ -296,21 +299,66 @@ void launch_respre_f32(const ResUnitArgs& a, float* P, cudaStream_t st) {
 }
 
 // ----------------------------------------------------------------------------------------------
+// Streaming session helpers (snacb_session_step_multi): new tokens of n streams go to each stream's own position of its
+// slot's token row; the launch's noise keys are gathered; a full window slides by moving its last frames to the front.
+// ----------------------------------------------------------------------------------------------
+__global__ void k_session_scatter(const int32_t* __restrict__ new_tok, int tok_stride, int n_int, const int* __restrict__ slot,
+                                  const int* __restrict__ pos, int32_t* __restrict__ tok_buf, int slot_ints,
+                                  const int32_t* __restrict__ keys_in, int32_t* __restrict__ keys_out, int n) {
+    const int s = blockIdx.y;
+    if (s >= n) return;
+    int32_t* dst = tok_buf + static_cast<size_t>(slot[s]) * slot_ints + static_cast<size_t>(7) * pos[s];
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_int; j += gridDim.x * blockDim.x)
+        dst[j] = new_tok[static_cast<size_t>(s) * tok_stride + j];
+    if (blockIdx.x == 0 && threadIdx.x == 0) keys_out[s] = keys_in ? keys_in[s] : slot[s];
+}
+void launch_session_scatter(const int32_t* new_tok, int tok_stride, int n_int, const int* slot, const int* pos, int32_t* tok_buf,
+                            int slot_ints, const int32_t* keys_in, int32_t* keys_out, int n, cudaStream_t st) {
+    if (n <= 0) return;
+    dim3 grid(n_int > 0 ? (n_int + 127) / 128 : 1, n);
+    k_session_scatter<<<grid, 128, 0, st>>>(new_tok, tok_stride, n_int, slot, pos, tok_buf, slot_ints, keys_in, keys_out, n);
+}
+
+// rows [slide[i], slide[i] + keep) frames of slot list[i] -> rows [0, keep); source and destination never overlap (slide >= keep)
+__global__ void k_session_slide(uint8_t* __restrict__ buf, size_t slot_bytes, size_t frame_bytes, int keep, const int* __restrict__ list,
+                                const int* __restrict__ slide, int n) {
+    const int i = blockIdx.y;
+    if (i >= n) return;
+    uint4* dst = reinterpret_cast<uint4*>(buf + static_cast<size_t>(list[i]) * slot_bytes);
+    const uint4* src = reinterpret_cast<const uint4*>(buf + static_cast<size_t>(list[i]) * slot_bytes + static_cast<size_t>(slide[i]) * frame_bytes);
+    const size_t n16 = static_cast<size_t>(keep) * frame_bytes / 16;
+    for (size_t j = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; j < n16; j += static_cast<size_t>(gridDim.x) * blockDim.x)
+        dst[j] = src[j];
+}
+void launch_session_slide(void* buf, size_t slot_bytes, size_t frame_bytes, int keep, const int* list, const int* slide, int n,
+                          cudaStream_t st) {
+    if (n <= 0 || !buf) return;
+    const size_t n16 = static_cast<size_t>(keep) * frame_bytes / 16;
+    unsigned gx = static_cast<unsigned>((n16 + 255) / 256);
+    if (gx > 256) gx = 256;
+    if (gx < 1) gx = 1;
+    dim3 grid(gx, n);
+    k_session_slide<<<grid, 256, 0, st>>>(static_cast<uint8_t*>(buf), slot_bytes, frame_bytes, keep, list, slide, n);
+}
+
+// ----------------------------------------------------------------------------------------------
 // bf16x3 path (precision = bf16 at the 40 dB bar): activations are STORED in fp16, the tensor
 // cores multiply bf16.  An fp16 value splits EXACTLY into two bf16 values (11 significand bits = 8 + 3), a weight into
 // hi + lo to 16 bits, so  A W^T = A_hi W_hi^T + A_lo W_hi^T + A_hi W_lo^T  with every product exact in fp32: the GEMM sees
 // A'' = [A_hi | A_lo | A_hi] (this kernel) against W'' = [W_hi | W_hi | W_lo] (packed at load) and K'' = 3K.
 // ----------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-k_split3(const __half* __restrict__ x, int S, int T, int K, int r_lo, int r_n, __nv_bfloat16* __restrict__ out) {
+k_split3(const __half* __restrict__ x, int S, int T, int K, int r_lo, int r_n, __nv_bfloat16* __restrict__ out,
+         const StreamMap map, int rpf) {
     const int k8n = K / 8;
     const long long total = static_cast<long long>(S) * r_n * k8n;
     for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
          idx += static_cast<long long>(gridDim.x) * blockDim.x) {
         const int k = static_cast<int>(idx % k8n) * 8;
         const long long rr = idx / k8n;
-        const int s = static_cast<int>(rr / r_n), t = r_lo + static_cast<int>(rr % r_n);
-        const size_t row = static_cast<size_t>(s) * T + t;
+        const int s = static_cast<int>(rr / r_n), t = r_lo + sm_off(map, s, rpf) + static_cast<int>(rr % r_n);
+        if (t >= T) continue;
+        const size_t row = static_cast<size_t>(sm_slot(map, s)) * T + t;
         const uint4 raw = *reinterpret_cast<const uint4*>(x + row * K + k);
         const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
         uint4 hi, lo;
@@ -332,12 +380,13 @@ k_split3(const __half* __restrict__ x, int S, int T, int K, int r_lo, int r_n, _
     }
 }
 
-void launch_split3(const __half* x, int S, int T, int K, int r_lo, int r_n, __nv_bfloat16* out, cudaStream_t st) {
+void launch_split3(const __half* x, int S, int T, int K, int r_lo, int r_n, __nv_bfloat16* out, cudaStream_t st,
+                   const StreamMap& map, int rpf) {
     const long long total = static_cast<long long>(S) * r_n * (K / 8);
     if (total <= 0) return;
     long long blocks = (total + 255) / 256;
     if (blocks > 148LL * 32) blocks = 148LL * 32;
-    k_split3<<<static_cast<unsigned>(blocks), 256, 0, st>>>(x, S, T, K, r_lo, r_n, out);
+    k_split3<<<static_cast<unsigned>(blocks), 256, 0, st>>>(x, S, T, K, r_lo, r_n, out, map, rpf);
 }
 
 // ResidualUnit front half of the bf16x3 path: a = snake2(dw_b + sum_j dw_w[j] * snake1(x[t + (j - 3) d])) in fp32 from the
@@ -346,7 +395,7 @@ void launch_split3(const __half* x, int S, int T, int K, int r_lo, int r_n, __nv
 // 7-tap window of snake1 values slides in registers, so each Snake is evaluated once per element.
 constexpr int kRespreRun = 64;
 __global__ void __launch_bounds__(256)
-k_respre16(ResUnitArgs a, int r_lo, int r_n, __nv_bfloat16* __restrict__ out) {
+k_respre16(ResUnitArgs a, int r_lo_, int r_n, __nv_bfloat16* __restrict__ out) {
     const int c4n = a.C / 4, d = a.dil;
     const int per_class = (r_n + d - 1) / d;                       // steps of the longest class inside [r_lo, r_lo + r_n)
     const int segs = (per_class + kRespreRun - 1) / kRespreRun;
@@ -358,7 +407,8 @@ k_respre16(ResUnitArgs a, int r_lo, int r_n, __nv_bfloat16* __restrict__ out) {
         long long rest = idx / c4n;
         const int seg = static_cast<int>(rest % segs); rest /= segs;
         const int cls = static_cast<int>(rest % d);
-        const int s = static_cast<int>(rest / d);
+        const int s_ = static_cast<int>(rest / d), s = sm_slot(a.map, s_);   // s: buffer slot (addressing)
+        const int r_lo = r_lo_ + sm_off(a.map, s_, a.rpf);
         const float4 al = *reinterpret_cast<const float4*>(a.alpha1 + c);
         const float4 ia = *reinterpret_cast<const float4*>(a.inv_alpha1 + c);
         const float4 a2 = *reinterpret_cast<const float4*>(a.alpha2 + c);
@@ -457,18 +507,20 @@ __device__ __forceinline__ float tail_chunk(const float2 (&wj)[7], int lane, Row
     return v[0];
 }
 
-template <typename InT>
+// MAPPED: a streaming-session launch (per-stream slot / first sample); the stateless decode compiles without the map
+template <typename InT, bool MAPPED>
 __global__ void __launch_bounds__(256)
-k_tail(const InT* __restrict__ a, int T, int t_begin, int n_out, const float* __restrict__ w /*[7][64]*/, float bias,
-       int16_t* __restrict__ pcm, float* __restrict__ wave) {
+k_tail(const InT* __restrict__ a, int T, int t_begin_, int n_out, const float* __restrict__ w /*[7][64]*/, float bias,
+       int16_t* __restrict__ pcm, float* __restrict__ wave, const StreamMap map) {
     const int s = blockIdx.y;
+    const int t_begin = MAPPED ? t_begin_ + sm_off(map, s, 2048) : t_begin_;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int base = t_begin + blockIdx.x * 256 + warp * 32;
     if (base >= t_begin + n_out) return;
     float2 wj[7];
 #pragma unroll
     for (int j = 0; j < 7; ++j) wj[j] = make_float2(w[j * 64 + 2 * lane], w[j * 64 + 2 * lane + 1]);
-    const InT* src = a + static_cast<size_t>(s) * T * 64 + 2 * lane;
+    const InT* src = a + static_cast<size_t>(MAPPED ? sm_slot(map, s) : s) * T * 64 + 2 * lane;
     const float v = tail_chunk(wj, lane, [&](int i) -> float2 {     // one 4-byte (16-bit types) or 8-byte load per lane and row
         const int t = base - 3 + i;
         if (t < 0 || t >= T) return make_float2(0.f, 0.f);
@@ -493,10 +545,10 @@ constexpr int kTailStages = 3;
 constexpr int kTailStageBytes = kTailRows * 128;
 constexpr int kTailSmem = kTailStages * kTailStageBytes + 64 + 128;
 
-template <typename InT>
+template <typename InT, bool MAPPED>
 __global__ void __launch_bounds__(256, 2)
-k_tail_bulk(const InT* __restrict__ a, int T, int t_begin, int n_out, const float* __restrict__ w, float bias,
-            int16_t* __restrict__ pcm, float* __restrict__ wave, int tiles_per_stream, int num_tiles) {
+k_tail_bulk(const InT* __restrict__ a, int T, int t_begin_, int n_out, const float* __restrict__ w, float bias,
+            int16_t* __restrict__ pcm, float* __restrict__ wave, int tiles_per_stream, int num_tiles, const StreamMap map) {
     static_assert(sizeof(InT) == 2, "16-bit activations");
     extern __shared__ __align__(128) uint8_t tail_smem[];
     uint8_t* ring = tail_smem + ((128u - (ptx::smem_u32(tail_smem) & 127u)) & 127u);
@@ -512,10 +564,11 @@ k_tail_bulk(const InT* __restrict__ a, int T, int t_begin, int n_out, const floa
     for (int j = 0; j < 7; ++j) wj[j] = make_float2(w[j * 64 + 2 * lane], w[j * 64 + 2 * lane + 1]);
 
     auto issue = [&](int tile, int stage) {               // thread 0: rows [base - 3, base + 259) clipped to the stream
-        const int s = tile / tiles_per_stream, base = t_begin + (tile % tiles_per_stream) * kTailTile;
+        const int s = tile / tiles_per_stream;
+        const int base = t_begin_ + (MAPPED ? sm_off(map, s, 2048) : 0) + (tile % tiles_per_stream) * kTailTile;
         const int lo = max(base - 3, 0), hi = min(base + kTailTile + 3, T);
         const uint32_t bytes = static_cast<uint32_t>(hi - lo) * 128u;
-        const InT* src = a + (static_cast<size_t>(s) * T + lo) * 64;
+        const InT* src = a + (static_cast<size_t>(MAPPED ? sm_slot(map, s) : s) * T + lo) * 64;
         uint8_t* dst = ring + stage * kTailStageBytes + (lo - (base - 3)) * 128;
         ptx::mbar_expect_tx(&full[stage], bytes);
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -529,7 +582,9 @@ k_tail_bulk(const InT* __restrict__ a, int T, int t_begin, int n_out, const floa
     int k = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++k) {
         const int stage = k % kTailStages;
-        const int s = tile / tiles_per_stream, tile_base = t_begin + (tile % tiles_per_stream) * kTailTile;
+        const int s = tile / tiles_per_stream;
+        const int t_begin = t_begin_ + (MAPPED ? sm_off(map, s, 2048) : 0);
+        const int tile_base = t_begin + (tile % tiles_per_stream) * kTailTile;
         ptx::mbar_wait(&full[stage], (k / kTailStages) & 1);
         const int base = tile_base + warp * 32;
         if (base < t_begin + n_out) {
@@ -555,9 +610,9 @@ k_tail_bulk(const InT* __restrict__ a, int T, int t_begin, int n_out, const floa
     }
 }
 
-template <typename InT>
-void launch_tail(const InT* a, int S, int T, int t_begin, int n_out, const float* w, float bias, int16_t* pcm,
-                 float* wave, cudaStream_t st) {
+template <typename InT, bool MAPPED>
+static void launch_tail_m(const InT* a, int S, int T, int t_begin, int n_out, const float* w, float bias, int16_t* pcm,
+                          float* wave, cudaStream_t st, const StreamMap& map) {
     if constexpr (sizeof(InT) == 2) {
         const int tps = (n_out + kTailTile - 1) / kTailTile;
         const long long tiles = static_cast<long long>(S) * tps;
@@ -567,24 +622,32 @@ void launch_tail(const InT* a, int S, int T, int t_begin, int n_out, const float
             int dev;
             bool ok = true;
             if (once.needed(&dev)) {
-                ok = cudaFuncSetAttribute(k_tail_bulk<InT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTailSmem) == cudaSuccess;
+                ok = cudaFuncSetAttribute(k_tail_bulk<InT, MAPPED>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTailSmem) == cudaSuccess;
                 if (ok) once.done(dev);
             }
             if (ok) {
-                k_tail_bulk<InT><<<2 * 148, 256, kTailSmem, st>>>(a, T, t_begin, n_out, w, bias, pcm, wave, tps,
-                                                                   static_cast<int>(tiles));
+                k_tail_bulk<InT, MAPPED><<<2 * 148, 256, kTailSmem, st>>>(a, T, t_begin, n_out, w, bias, pcm, wave, tps,
+                                                                           static_cast<int>(tiles), map);
                 return;
             }
             (void)cudaGetLastError();       // the opt-in failed: fall through to the kernel that needs no dynamic shared memory
         }
     }
     dim3 grid((n_out + 255) / 256, S);
-    k_tail<InT><<<grid, 256, 0, st>>>(a, T, t_begin, n_out, w, bias, pcm, wave);
+    k_tail<InT, MAPPED><<<grid, 256, 0, st>>>(a, T, t_begin, n_out, w, bias, pcm, wave, map);
 }
-template void launch_tail<float>(const float*, int, int, int, int, const float*, float, int16_t*, float*, cudaStream_t);
+template <typename InT>
+void launch_tail(const InT* a, int S, int T, int t_begin, int n_out, const float* w, float bias, int16_t* pcm,
+                 float* wave, cudaStream_t st, const StreamMap& map) {
+    if (map.slot || map.off) launch_tail_m<InT, true>(a, S, T, t_begin, n_out, w, bias, pcm, wave, st, map);
+    else launch_tail_m<InT, false>(a, S, T, t_begin, n_out, w, bias, pcm, wave, st, map);
+}
+template void launch_tail<float>(const float*, int, int, int, int, const float*, float, int16_t*, float*, cudaStream_t,
+                                 const StreamMap&);
 template void launch_tail<__nv_bfloat16>(const __nv_bfloat16*, int, int, int, int, const float*, float, int16_t*,
-                                         float*, cudaStream_t);
-template void launch_tail<__half>(const __half*, int, int, int, int, const float*, float, int16_t*, float*, cudaStream_t);
+                                         float*, cudaStream_t, const StreamMap&);
+template void launch_tail<__half>(const __half*, int, int, int, int, const float*, float, int16_t*, float*, cudaStream_t,
+                                  const StreamMap&);
 
 // ----------------------------------------------------------------------------------------------
 template <typename T>

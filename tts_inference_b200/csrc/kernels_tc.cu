@@ -83,7 +83,10 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             int stage = 0; uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int mt = tile / num_n_tiles, nt = tile % num_n_tiles;
-                const int s0 = (mt / tiles_t) * a.Wbox, t0 = t_lo + (mt % tiles_t) * a.Tbox;
+                const int sg = (mt / tiles_t) * a.Wbox;           // first stream of the tile
+                const bool mapped = a.map.slot != nullptr || a.map.off != nullptr;
+                const int s0 = sm_slot(a.map, sg);
+                const int t0 = t_lo + sm_off(a.map, sg, a.rpf) + (mt % tiles_t) * a.Tbox;
                 const int n0 = nt * BN;
                 const int p = n0 / a.Cout;
                 const int base_shift = (a.up > 1 && p >= a.up / 2) ? 1 : 0;
@@ -91,8 +94,20 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     const int tap = kk / kchunks, kc = kk % kchunks;
                     mbar_wait(&empty[stage], phase ^ 1u);
                     uint8_t* sa = smem + stage * Cfg::kStageBytes;
-                    mbar_expect_tx(&full[stage], Cfg::kStageBytes);
-                    tma_load_3d(sa, &tmA, (a.a_wrap > 0 ? kc % a.a_wrap : kc) * kChunkK, t0 + base_shift - tap, s0, &full[stage]);
+                    const int ka = (a.a_wrap > 0 ? kc % a.a_wrap : kc) * kChunkK;
+                    if (mapped && a.Wbox > 1) {
+                        // session launch with several streams per tile: every stream has its own rows and slot, so its
+                        // Tbox rows arrive by their own load (the A map's box is then (64, Tbox, 1))
+                        const int nv = (a.S - sg) < a.Wbox ? (a.S - sg) : a.Wbox;
+                        mbar_expect_tx(&full[stage], static_cast<uint32_t>(nv * a.Tbox * 128 + BN * 128));
+                        for (int j = 0; j < nv; ++j)
+                            tma_load_3d(sa + j * a.Tbox * 128, &tmA, ka,
+                                        t_lo + sm_off(a.map, sg + j, a.rpf) + (mt % tiles_t) * a.Tbox + base_shift - tap,
+                                        sm_slot(a.map, sg + j), &full[stage]);
+                    } else {
+                        mbar_expect_tx(&full[stage], Cfg::kStageBytes);
+                        tma_load_3d(sa, &tmA, ka, t0 + base_shift - tap, s0, &full[stage]);
+                    }
                     tma_load_2d_hint(sa + kABytes, &tmW, tap * a.K + kc * kChunkK, n0, &full[stage], kL2EvictLast);
                     if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
                 }
@@ -137,14 +152,17 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         OutT* out = static_cast<OutT*>(a.out);
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int mt = tile / num_n_tiles, nt = tile % num_n_tiles;
-            const int s = (mt / tiles_t) * a.Wbox + r / a.Tbox;
-            const int m = t_lo + (mt % tiles_t) * a.Tbox + r % a.Tbox;
-            const bool valid = (s < a.S) && (m < a.Tin) && (m < t_lo + t_n);
+            const int s = (mt / tiles_t) * a.Wbox + r / a.Tbox;        // stream of the launch (noise key, row offset)
+            const int so = (s < a.S) ? sm_off(a.map, s, a.rpf) : 0;
+            const int sl = (s < a.S) ? sm_slot(a.map, s) : 0;          // its buffer slot
+            const int m = t_lo + so + (mt % tiles_t) * a.Tbox + r % a.Tbox;
+            const bool valid = (s < a.S) && (m < a.Tin) && (m < t_lo + so + t_n);
             const int n0 = nt * BN;
             float nz = 0.f;
             if (EPI == EPI_NOISE && valid)
                 nz = a.noise ? a.noise[static_cast<size_t>(s) * a.Tin + m]
-                             : counter_normal(key, noise_counter(a.stream_keys ? a.stream_keys[s] : a.stream_offset + s, m + a.t0));
+                             : counter_normal(key, noise_counter(a.stream_keys ? a.stream_keys[s] : a.stream_offset + s,
+                                                                 m + a.t0 + sm_org(a.map, s, a.rpf)));
             mbar_wait(&tfull[as], aphase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN);
@@ -156,7 +174,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 if (valid) {
                     const int n = n0 + c * 32;
                     const int pc = n / a.Cout, o = n - pc * a.Cout;
-                    const size_t orow = (static_cast<size_t>(s) * a.Tin + m) * a.up + pc;
+                    const size_t orow = (static_cast<size_t>(sl) * a.Tin + m) * a.up + pc;
                     float v[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);

@@ -411,6 +411,9 @@ struct SessionPlan {
     Rng ct_in[4];            // ConvTranspose input rows
     Rng post[4];             // fused chain: output rows
     Rng nz_r[4], res_r[4][3];// per-layer rows of the blocks without the fused chain
+    int n_slots;             // streams the buffers hold (tensor-map extent: a mapped launch addresses slots, not 0..S-1); 0 = S
+    StreamMap map;           // per-stream slot / frame offset / window origin (device arrays; null: stream s = slot s at the
+                             // reference position) -- streams at different positions advancing by the same number of frames
 };
 
 int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, int flags, const float* const* noise,
@@ -480,7 +483,7 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
             Rng y;                                                  // ConvTranspose output rows that must be valid
             const bool unfused = (flags & SNACB_UNFUSED) != 0 || h->no_chain || x3;
             if (b.chain[hk] && !unfused) {
-                const bool ws = h->chain_ws && chain_ws_supported(b.Cout, hk);
+                const bool ws = h->chain_ws && chain_ws_supported(b.Cout, hk) && !plan;
                 const int rows = (ws ? chain_ws_tile_rows(b.Cout) : chain_tile_rows(b.Cout)) - 2 * kChainHalo;
                 const int n = (need.hi - need.lo + rows - 1) / rows;
                 post[bi] = Rng{need.lo, need.lo + n * rows};
@@ -500,10 +503,13 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
     const int stem_hi = plan ? plan->stem_r.hi : (trimmed[0] ? ct_in[0].hi : T0);
     void* const a0 = plan ? plan->a0 : h->ws_a0;
     const bool stem_live = stem_hi > stem_lo;
+    const StreamMap smap = plan ? plan->map : StreamMap{nullptr, nullptr, nullptr};
+    const bool mapped = smap.slot != nullptr || smap.off != nullptr || smap.org != nullptr;
+    const int S_buf = (plan && plan->n_slots > 0) ? plan->n_slots : S;      // stream extent of the buffers (tensor maps)
     if (!stem_live) {}
-    else if (f32) launch_vq_stem<float>(c0, c1, c2, fused_unpack ? tok : nullptr, tok_stride, (flags & SNACB_RAW_IDS) ? 1 : 0, S, F, stem_lo, stem_hi, h->vq, static_cast<float*>(a0), st);
-    else if (hk) launch_vq_stem<__half>(c0, c1, c2, fused_unpack ? tok : nullptr, tok_stride, (flags & SNACB_RAW_IDS) ? 1 : 0, S, F, stem_lo, stem_hi, h->vq, static_cast<__half*>(a0), st);
-    else launch_vq_stem<__nv_bfloat16>(c0, c1, c2, fused_unpack ? tok : nullptr, tok_stride, (flags & SNACB_RAW_IDS) ? 1 : 0, S, F, stem_lo, stem_hi, h->vq, static_cast<__nv_bfloat16*>(a0), st);
+    else if (f32) launch_vq_stem<float>(c0, c1, c2, fused_unpack ? tok : nullptr, tok_stride, (flags & SNACB_RAW_IDS) ? 1 : 0, S, F, stem_lo, stem_hi, h->vq, static_cast<float*>(a0), st, smap);
+    else if (hk) launch_vq_stem<__half>(c0, c1, c2, fused_unpack ? tok : nullptr, tok_stride, (flags & SNACB_RAW_IDS) ? 1 : 0, S, F, stem_lo, stem_hi, h->vq, static_cast<__half*>(a0), st, smap);
+    else launch_vq_stem<__nv_bfloat16>(c0, c1, c2, fused_unpack ? tok : nullptr, tok_stride, (flags & SNACB_RAW_IDS) ? 1 : 0, S, F, stem_lo, stem_hi, h->vq, static_cast<__nv_bfloat16*>(a0), st, smap);
     prof_end(h, st);
     if (stem_live) h->launches++;
     CK(h, cudaGetLastError());
@@ -523,6 +529,7 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
     auto gemm = [&](const char* pname, int epi, bool out_f32, GemmArgs& a, const void* A, const float* Wf,
                     void* const* Wh, int Wrows, int Wcols, const void* Wx3 = nullptr, bool a_split = false) -> int {
         tile_boxes(a.Tin, &a.Tbox, &a.Wbox);
+        a.map = smap; a.rpf = a.Tin / F;                  // session: per-stream slot / offset / origin (A rows per frame)
         if (a.Wbox != 1) a.t_n = 0;
         else if (!f32 && a.t_n > 0 && a.t_n <= 64) {
             // the trimmed rows of a stream fill at most half a 128-row tile (block-1 ConvTranspose of the sliced call:
@@ -550,14 +557,14 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
                 const int r_lo = a.t_n > 0 ? (a.t_lo > 0 ? a.t_lo - 1 : 0) : 0;
                 const int r_hi = a.t_n > 0 ? (a.t_lo + a.t_n + 1 < a.Tin ? a.t_lo + a.t_n + 1 : a.Tin) : a.Tin;
                 launch_split3(static_cast<const __half*>(A), a.S, a.Tin, a.K, r_lo, r_hi - r_lo,
-                              static_cast<__nv_bfloat16*>(h->ws_split), st);
+                              static_cast<__nv_bfloat16*>(h->ws_split), st, smap, a.rpf);
                 h->launches++;
                 a.a_wrap = 2 * a.K / 64;              // ws_split holds [hi | lo]; K chunks beyond it wrap around to hi
                 a.K *= 3;
                 Wcols *= 3;
             }
             a.mma_bf16 = 1;
-            int rc = act_map(h, &ma, h->ws_split, a.a_wrap * 64, a.Tin, a.S, a.Tbox, a.Wbox, 0);
+            int rc = act_map(h, &ma, h->ws_split, a.a_wrap * 64, a.Tin, S_buf, a.Tbox, mapped ? 1 : a.Wbox, 0);
             if (rc) return rc;
             rc = weight_map(h, &mw, Wx3, Wrows, Wcols, gemm_tc_block_n(a), 0);
             if (rc) return rc;
@@ -566,7 +573,7 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
             CK(h, le);
             return 0;
         }
-        int rc = act_map(h, &ma, A, a.K, a.Tin, a.S, a.Tbox, a.Wbox, hk);
+        int rc = act_map(h, &ma, A, a.K, a.Tin, S_buf, a.Tbox, mapped ? 1 : a.Wbox, hk);
         if (rc) return rc;
         rc = weight_map(h, &mw, Wh[hk], Wrows, Wcols, gemm_tc_block_n(a), hk);
         if (rc) return rc;
@@ -608,13 +615,14 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
                 // weights resident in smem, one activation load per tile, row-shifted descriptors per tap
                 CUtensorMap ma, mo;
                 const CUtensorMap* mw;
-                rc = act_map(h, &ma, cur, b.Cin, Tin, S, convt_res_box_rows(), 1, hk);
+                rc = act_map(h, &ma, cur, b.Cin, Tin, S_buf, convt_res_box_rows(), 1, hk);
                 if (rc) return rc;
                 rc = weight_map(h, &mw, b.ct_h[hk], b.s * b.Cout, 2 * b.Cin, b.s * b.Cout, hk);
                 if (rc) return rc;
-                rc = act_map(h, &mo, oth, b.Cout, T, S, 128 * b.s, 1, hk);
+                rc = act_map(h, &mo, oth, b.Cout, T, S_buf, 128 * b.s, 1, hk);
                 if (rc) return rc;
                 a.seed = seed; a.stream_offset = stream_offset; a.stream_keys = stream_keys; a.Tbox = 128; a.Wbox = 1;
+                a.map = smap; a.rpf = Tin / F;
                 prof_begin(h, nm, st);
                 cudaError_t le = launch_convt_res(hk, a, ma, *mw, mo, h->sm_count, st);
                 prof_end(h, st);
@@ -624,11 +632,12 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
                 // one output phase's weights resident per CTA group, one activation load per tile
                 CUtensorMap ma;
                 const CUtensorMap* mw;
-                rc = act_map(h, &ma, cur, b.Cin, Tin, S, convt_res_box_rows(), 1, hk);
+                rc = act_map(h, &ma, cur, b.Cin, Tin, S_buf, convt_res_box_rows(), 1, hk);
                 if (rc) return rc;
                 rc = weight_map(h, &mw, b.ct_h[hk], b.s * b.Cout, 2 * b.Cin, b.Cout, hk);
                 if (rc) return rc;
                 a.seed = seed; a.stream_offset = stream_offset; a.stream_keys = stream_keys; a.Tbox = 128; a.Wbox = 1;
+                a.map = smap; a.rpf = Tin / F;
                 prof_begin(h, nm, st);
                 cudaError_t le = launch_convt_ph(hk, a, ma, *mw, h->sm_count, st);
                 prof_end(h, st);
@@ -658,7 +667,8 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
             ca.inv_next = bi < 3 ? h->blk[bi + 1].inv_alpha : h->tail_inv;
             ca.noise = noise ? noise[bi] : nullptr; ca.seed = seed; ca.noise_stage = bi; ca.stream_offset = stream_offset; ca.stream_keys = stream_keys;
             ca.t0 = origin_frames * 4 * (T / T0);      // the buffers hold the stream from frame origin_frames on
-            const bool ws = h->chain_ws && chain_ws_supported(b.Cout, hk);
+            ca.map = smap; ca.rpf = T / F;
+            const bool ws = h->chain_ws && chain_ws_supported(b.Cout, hk) && !plan;     // the experiment knows no sessions
             memcpy(ca.spans, ws ? b.spans_ws : b.spans, sizeof ca.spans);
             ca.tile_counter = h->tile_counter;
             ca.jitter = h->chain_jitter;
@@ -666,11 +676,11 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
             const bool fold = hk && b.fold && !h->no_fold;
             CUtensorMap my, moe, mom;
             const CUtensorMap* mn;
-            int rc = act_map(h, &my, oth, b.Cout, T, S, 128, 1, hk, 1);
+            int rc = act_map(h, &my, oth, b.Cout, T, S_buf, 128, 1, hk, 1);
             if (rc) return rc;
-            rc = act_map(h, &moe, ob, b.Cout, T, S, 128 - kChainHalo, 1, hk, 1);
+            rc = act_map(h, &moe, ob, b.Cout, T, S_buf, 128 - kChainHalo, 1, hk, 1);
             if (rc) return rc;
-            rc = act_map(h, &mom, ob, b.Cout, T, S, 128, 1, hk, 1);
+            rc = act_map(h, &mom, ob, b.Cout, T, S_buf, 128, 1, hk, 1);
             if (rc) return rc;
             rc = weight_map(h, &mn, b.nz_h[hk], b.Cout, b.Cout, b.Cout, hk);
             if (rc) return rc;
@@ -722,6 +732,7 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
             if (plan) { ra.t_lo = plan->res_r[bi][ri].lo; ra.t_n = plan->res_r[bi][ri].hi - plan->res_r[bi][ri].lo; }
             else if (trimmed[bi]) { ra.t_lo = post[bi].lo; ra.t_n = post[bi].hi - post[bi].lo; }
             ra.x = cur; ra.out = ro;
+            ra.map = smap; ra.rpf = T / F;
             ra.alpha1 = r.alpha1; ra.inv_alpha1 = r.inv1; ra.dw_w = r.dw_w; ra.dw_b = r.dw_b;
             ra.alpha2 = r.alpha2; ra.inv_alpha2 = r.inv2; ra.pw_b = r.pw_b;
             ra.alpha_next = an; ra.inv_alpha_next = ian;
@@ -756,7 +767,7 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
                 int tile_m, box_rows;
                 resunit2_geometry(ra.C, ra.dil, &tile_m, &box_rows);
                 CUtensorMap mx;
-                int rc2 = act_map(h, &mx, cur, ra.C, T, S, box_rows, 1, hk, 0);
+                int rc2 = act_map(h, &mx, cur, ra.C, T, S_buf, box_rows, 1, hk, 0);
                 if (rc2) return rc2;
                 cudaError_t le = launch_resunit2(hk, ra, mx, r.tm_pw[hk], h->sm_count, st);
                 prof_end(h, st);
@@ -780,9 +791,9 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
     const int t_begin = out_lo, n_out = out_hi - out_lo;
     if (plan && n_out <= 0) { h->streams += S; return 0; }
     prof_begin(h, "tail", st);
-    if (f32) launch_tail<float>(static_cast<const float*>(cur), S, T, t_begin, n_out, h->tail_w, h->tail_b, pcm, wave, st);
-    else if (hk) launch_tail<__half>(static_cast<const __half*>(cur), S, T, t_begin, n_out, h->tail_w, h->tail_b, pcm, wave, st);
-    else launch_tail<__nv_bfloat16>(static_cast<const __nv_bfloat16*>(cur), S, T, t_begin, n_out, h->tail_w, h->tail_b, pcm, wave, st);
+    if (f32) launch_tail<float>(static_cast<const float*>(cur), S, T, t_begin, n_out, h->tail_w, h->tail_b, pcm, wave, st, smap);
+    else if (hk) launch_tail<__half>(static_cast<const __half*>(cur), S, T, t_begin, n_out, h->tail_w, h->tail_b, pcm, wave, st, smap);
+    else launch_tail<__nv_bfloat16>(static_cast<const __nv_bfloat16*>(cur), S, T, t_begin, n_out, h->tail_w, h->tail_b, pcm, wave, st, smap);
     prof_end(h, st);
     h->launches++;
     CK(h, cudaGetLastError());
@@ -1113,6 +1124,7 @@ struct snacb_session_s {
     int32_t* tok = nullptr;                   // [n_slots][7 * max_frames], the window's tokens
     int32_t* codes[3] = {nullptr, nullptr, nullptr};
     int32_t* slot_keys = nullptr;             // [n_slots] = 0, 1, ...: the default NoiseBlock noise key of a slot
+    int32_t* map_dev = nullptr;               // [7][n_slots]: slot, off, org, pos, keys, slide list, slide amount of a multi step
     void* a0 = nullptr;
     void* stem = nullptr;
     void* ct[4] = {}; void* nz[4] = {}; void* res[4][3] = {}; void* out[4] = {};
@@ -1233,6 +1245,7 @@ int snacb_session_create(snacb_handle h, int n_slots, int max_frames, int flags,
     }
     if (rc) { snacb_session_destroy(s); return rc; }
     if (!rc) rc = sess_alloc(s, reinterpret_cast<void**>(&s->slot_keys), N * sizeof(int32_t));
+    if (!rc) rc = sess_alloc(s, reinterpret_cast<void**>(&s->map_dev), 7 * N * sizeof(int32_t));
     if (rc) { snacb_session_destroy(s); return rc; }
     std::vector<int32_t> iota(N);
     for (size_t i = 0; i < N; ++i) iota[i] = static_cast<int32_t>(i);
@@ -1418,6 +1431,138 @@ int snacb_session_step(snacb_session s, int slot0, int n, const int32_t* new_tok
                                 static_cast<size_t>(n_out) * 2, n, cudaMemcpyDeviceToDevice, st));
     for (int i = slot0; i < slot0 + n; ++i) { s->frames[i] = o + F; s->emitted[i] = 2048 * o + Ep + n_out; }
     if (n_emitted) *n_emitted = n_out;
+    return SNACB_OK;
+}
+
+int snacb_session_step_multi(snacb_session s, int n, const int32_t* slots_host, const int32_t* new_tok, int tok_stride,
+                             int new_frames, uint64_t seed, const int32_t* stream_keys, int16_t* pcm, int pcm_stride,
+                             int* n_emitted, void* stream) {
+    if (!s) return SNACB_ERR_ARG;
+    snacb_handle h = s->h;
+    if (n_emitted) *n_emitted = 0;
+    if (n < 0 || new_frames <= 0 || tok_stride < 7 * new_frames || (n > 0 && (!slots_host || !new_tok)))
+        return fail(h, SNACB_ERR_ARG, "snacb_session_step_multi: bad arguments n=%d new_frames=%d tok_stride=%d", n, new_frames, tok_stride);
+    if (n == 0) return SNACB_OK;
+    if (n > s->n_slots) return fail(h, SNACB_ERR_ARG, "snacb_session_step_multi: %d streams for %d slots", n, s->n_slots);
+    constexpr int kKeep = 8;
+    const int Fm = s->max_frames;
+    // ---- positions (frames held relative to each window), windows that have to slide first
+    std::vector<int32_t> hs(static_cast<size_t>(7) * n);
+    int32_t *v_slot = hs.data(), *v_off = v_slot + n, *v_org = v_off + n, *v_pos = v_org + n, *v_list = v_pos + 2 * n, *v_slide = v_list + n;
+    std::vector<char> seen(s->n_slots, 0);
+    int n_slide = 0;
+    bool same = true;
+    for (int i = 0; i < n; ++i) {
+        const int sl = slots_host[i];
+        if (sl < 0 || sl >= s->n_slots || seen[sl]) return fail(h, SNACB_ERR_ARG, "snacb_session_step_multi: bad or repeated slot %d", sl);
+        seen[sl] = 1;
+        if (s->finished[sl]) return fail(h, SNACB_ERR_STATE, "snacb_session_step_multi: slot %d is finished (snacb_session_reset it)", sl);
+        int Fp = static_cast<int>(s->frames[sl] - s->origin[sl]);
+        if (Fp + new_frames > Fm) {
+            const int slide = Fp - kKeep;
+            if (slide < kKeep || kKeep + new_frames > Fm)
+                return fail(h, SNACB_ERR_ARG, "snacb_session_step_multi: %d new frames do not fit a %d-frame window holding %d", new_frames, Fm, Fp);
+            v_list[n_slide] = sl; v_slide[n_slide] = slide; ++n_slide;
+            v_org[i] = static_cast<int32_t>(s->origin[sl] + slide);
+            Fp = kKeep;
+        } else {
+            v_org[i] = static_cast<int32_t>(s->origin[sl]);
+        }
+        v_slot[i] = sl; v_pos[i] = Fp;
+        same = same && Fp == v_pos[0];
+    }
+    const int Fref = v_pos[0];
+    for (int i = 0; i < n; ++i) {
+        // past its first frames every stage's frontier is affine in the frame count, so streams at different positions share
+        // the launch: stream i's row ranges are the reference's shifted by (pos_i - pos_ref) frames
+        if (!same && v_pos[i] < 3)
+            return fail(h, SNACB_ERR_STATE, "snacb_session_step_multi: slot %d holds %d frames; streams with fewer than 3 frames can only share a step with streams at the same position", v_slot[i], v_pos[i]);
+        v_off[i] = v_pos[i] - Fref;
+    }
+    const Frontier a = frontier_of(h, Fref, s->flags), b = frontier_of(h, Fref + new_frames, s->flags);
+    const int n_out = b.emit - a.emit;                   // = what every stream of the step emits (its own emitted count lags alike)
+    for (int i = 0; i < n; ++i) {
+        const int sl = v_slot[i];
+        const long long el = s->emitted[sl] - 2048LL * v_org[i];  // samples emitted, relative to the (new) window
+        if (el != frontier_of(h, v_pos[i], s->flags).emit)
+            return fail(h, SNACB_ERR_STATE, "snacb_session_step_multi: slot %d is out of step with its frontier", sl);
+    }
+    if (n_out > 0 && (!pcm || pcm_stride < n_out)) return fail(h, SNACB_ERR_ARG, "snacb_session_step_multi: pcm_stride %d < %d samples", pcm_stride, n_out);
+    CK(h, cudaSetDevice(h->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t N = static_cast<size_t>(s->n_slots);
+    int32_t *d_slot = s->map_dev, *d_off = d_slot + N, *d_org = d_off + N, *d_pos = d_org + N, *d_keys = d_pos + N,
+            *d_list = d_keys + N, *d_slide = d_list + N;
+    CK(h, cudaMemcpyAsync(d_slot, v_slot, n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    CK(h, cudaMemcpyAsync(d_off, v_off, n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    CK(h, cudaMemcpyAsync(d_org, v_org, n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    CK(h, cudaMemcpyAsync(d_pos, v_pos, n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    if (n_slide > 0) {
+        CK(h, cudaMemcpyAsync(d_list, v_list, n_slide * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        CK(h, cudaMemcpyAsync(d_slide, v_slide, n_slide * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        auto move = [&](void* buf, size_t frame_bytes) { launch_session_slide(buf, frame_bytes * Fm, frame_bytes, kKeep, d_list, d_slide, n_slide, st); };
+        // the token rows are 28 bytes per frame (sources not 16-byte aligned): a plain copy per sliding slot
+        for (int i = 0; i < n_slide; ++i) {
+            int32_t* row = s->tok + static_cast<size_t>(v_list[i]) * 7 * Fm;
+            CK(h, cudaMemcpyAsync(row, row + static_cast<size_t>(7) * v_slide[i], static_cast<size_t>(7) * kKeep * sizeof(int32_t),
+                                  cudaMemcpyDeviceToDevice, st));
+        }
+        move(s->stem, static_cast<size_t>(4) * kDecDim * 2);
+        size_t rows = 4;
+        for (int bi = 0; bi < 4; ++bi) {
+            rows *= h->blk[bi].s;
+            const size_t rb = rows * h->blk[bi].Cout * 2;
+            move(s->ct[bi], rb);
+            move(s->nz[bi], rb);
+            for (int ri = 0; ri < 3; ++ri) move(s->res[bi][ri], rb);
+            if (s->out[bi] != s->res[bi][2]) move(s->out[bi], rb);
+        }
+        CK(h, cudaGetLastError());
+    }
+    launch_session_scatter(new_tok, tok_stride, 7 * new_frames, d_slot, d_pos, s->tok, 7 * Fm, stream_keys, d_keys, n, st);
+    CK(h, cudaGetLastError());
+    if ((s->flags & SNACB_BF16) && !h->bf16_plain) {
+        int rc = grow(h, &h->ws_split, &h->ws_split_bytes, N * 131072 * Fm * 2 * 2);     // indexed by slot
+        if (rc) return rc;
+    }
+    SessionPlan pl{};
+    pl.c0 = s->codes[0]; pl.c1 = s->codes[1]; pl.c2 = s->codes[2];
+    pl.a0 = s->a0; pl.stem = s->stem;
+    pl.stem_r = Rng{a.stem, b.stem};
+    int vin_a = a.stem, vin_b = b.stem;
+    for (int bi = 0; bi < 4; ++bi) {
+        pl.ct[bi] = s->ct[bi]; pl.nz[bi] = s->nz[bi]; pl.out[bi] = s->out[bi];
+        for (int ri = 0; ri < 3; ++ri) pl.res[bi][ri] = s->res[bi][ri];
+        pl.ct_in[bi] = Rng{vin_a > 0 ? vin_a - 1 : 0, vin_b > 0 ? vin_b - 1 : 0};
+        pl.post[bi] = Rng{a.out[bi], b.out[bi]};
+        pl.nz_r[bi] = Rng{a.nz[bi], b.nz[bi]};
+        for (int ri = 0; ri < 3; ++ri) pl.res_r[bi][ri] = Rng{a.res[bi][ri], b.res[bi][ri]};
+        vin_a = a.out[bi]; vin_b = b.out[bi];
+    }
+    pl.map = StreamMap{d_slot, d_off, d_org};
+    pl.n_slots = s->n_slots;
+    int16_t* dst = pcm;
+    if (n_out > 0 && pcm_stride != n_out && n > 1) {
+        size_t pb = h->st_pcm_elems * sizeof(int16_t);
+        int rc = grow(h, reinterpret_cast<void**>(&h->st_pcm), &pb, static_cast<size_t>(n) * n_out * sizeof(int16_t));
+        if (rc) return rc;
+        h->st_pcm_elems = pb / sizeof(int16_t);
+        dst = h->st_pcm;
+    }
+    const int dflags = s->flags & (SNACB_RAW_IDS | SNACB_BF16);
+    int rc = run_group(h, s->tok, n, 7 * Fm, Fm, dflags, nullptr, seed, 0, d_keys, a.emit, a.emit + (n_out > 0 ? n_out : 0), dst,
+                       nullptr, st, &pl, 0);
+    if (rc) return rc;
+    if (dst != pcm && n_out > 0)
+        CK(h, cudaMemcpy2DAsync(pcm, static_cast<size_t>(pcm_stride) * 2, dst, static_cast<size_t>(n_out) * 2,
+                                static_cast<size_t>(n_out) * 2, n, cudaMemcpyDeviceToDevice, st));
+    for (int i = 0; i < n; ++i) {
+        const int sl = v_slot[i];
+        s->origin[sl] = v_org[i];
+        s->frames[sl] += new_frames;
+        s->emitted[sl] += n_out > 0 ? n_out : 0;
+    }
+    if (n_emitted) *n_emitted = n_out > 0 ? n_out : 0;
     return SNACB_OK;
 }
 

@@ -115,8 +115,8 @@ class StatefulStreamingDecoder:
     new whole frames and gets back exactly the samples that became final -- the prefix is neither re-read nor re-decoded.
     Emission differs from ``LookaheadStreamingDecoder`` only in WHEN samples appear: here as soon as their receptive field
     is inside the known tokens (a lag of 2.5 frames = 5050 samples) instead of after a fixed 5-frame lookahead; the bytes are the same
-    (both equal the batch decode of the finished stream, tests/test_io.py).  Streams that are due with the same
-    (frames held, frames to add, finished) and sit in neighbouring slots share one batched step."""
+    (both equal the batch decode of the finished stream, tests/test_io.py).  Streams at different positions share one
+    launch sequence per tick (``snacb_session_step_multi``)."""
 
     def __init__(self, decoder, max_streams: int, window_frames: int = 32, frames_per_chunk: int = 4, raw_ids: bool = True,
                  precision: str = "fp16", seed: int = 0):
@@ -151,41 +151,49 @@ class StatefulStreamingDecoder:
             self._streams[stream].done = True
 
     def step(self) -> List[Tuple[Hashable, np.ndarray]]:
+        """One decode tick.  Every stream that has ``frames_per_chunk`` new whole frames (or is finished) is served; streams
+        past their third frame share ONE launch sequence per distinct number of new frames, wherever they are in their
+        utterances and whichever slots they hold (``snacb_session_step_multi``); younger streams are grouped by exact
+        position; a finished stream is flushed (``final``) by one ranged decode of its window."""
         import torch
-        due: Dict[Tuple[int, int, bool], List[Tuple[int, Hashable]]] = {}
         cap = self._sess.max_frames - 16                       # frames one step may add to a non-empty window
+        multi: Dict[Tuple[int, int], List[Hashable]] = {}      # (position class, new frames) -> streams
+        finals: Dict[Tuple[int, int], List[Tuple[int, Hashable]]] = {}
         for key, st in self._streams.items():
             avail = len(st.ids) // FRAME                       # whole frames not yet handed to the session
             new = min(avail, cap)
             final = st.done and new == avail
-            if final or new >= self.frames_per_chunk or (st.done and new > 0):
-                due.setdefault((st.decoded_frames, new, final), []).append((self._slot[key], key))
+            if final:
+                finals.setdefault((st.decoded_frames, new), []).append((self._slot[key], key))
+            elif new >= self.frames_per_chunk or (st.done and new > 0):
+                multi.setdefault((-1 if st.decoded_frames >= 3 else st.decoded_frames, new), []).append(key)
         out: List[Tuple[Hashable, np.ndarray]] = []
-        for (have, new, final), members in sorted(due.items(), key=lambda kv: kv[0]):
-            members.sort()
-            runs, run = [], [members[0]]
-            for m in members[1:]:
-                if m[0] == run[-1][0] + 1:
-                    run.append(m)
-                else:
-                    runs.append(run); run = [m]
-            runs.append(run)
-            for run in runs:
-                keys = [k for _, k in run]
-                tok = np.asarray([self._streams[k].ids[:new * FRAME] for k in keys], dtype=np.int64)
-                tok = np.clip(tok.reshape(len(keys), new * FRAME), -(2 ** 31), 2 ** 31 - 1).astype(np.int32)
-                nkeys = torch.tensor([self._streams[k].key for k in keys], dtype=torch.int32).cuda(self._dec.device)
-                pcm = self._sess.step(run[0][0], torch.from_numpy(tok).cuda(self._dec.device), final=final, seed=self.seed,
-                                      stream_keys=nkeys)
-                host = pcm.cpu().numpy()
-                for row, k in enumerate(keys):
-                    st = self._streams[k]
-                    st.decoded_frames = have + new
-                    del st.ids[:new * FRAME]                   # the session holds what it still needs
-                    st.emitted += host.shape[1]
-                    st.flushed = final
-                    if host.shape[1]:
-                        out.append((k, host[row]))
+
+        def tokens_of(keys, new):
+            tok = np.asarray([self._streams[k].ids[:new * FRAME] for k in keys], dtype=np.int64)
+            tok = np.clip(tok.reshape(len(keys), new * FRAME), -(2 ** 31), 2 ** 31 - 1).astype(np.int32)
+            nkeys = torch.tensor([self._streams[k].key for k in keys], dtype=torch.int32).cuda(self._dec.device)
+            return torch.from_numpy(tok).cuda(self._dec.device), nkeys
+
+        def account(keys, new, host, final):
+            for row, k in enumerate(keys):
+                st = self._streams[k]
+                st.decoded_frames += new
+                del st.ids[:new * FRAME]                       # the session holds what it still needs
+                st.emitted += host.shape[1]
+                st.flushed = final
+                if host.shape[1]:
+                    out.append((k, host[row]))
+
+        for (_, new), keys in sorted(multi.items(), key=lambda kv: kv[0]):
+            tok, nkeys = tokens_of(keys, new)
+            pcm = self._sess.step_multi([self._slot[k] for k in keys], tok, seed=self.seed, stream_keys=nkeys)
+            account(keys, new, pcm.cpu().numpy(), False)
+        for (have, new), members in sorted(finals.items(), key=lambda kv: kv[0]):
+            for slot, k in sorted(members):                    # end of stream: once per stream, one ranged decode each
+                tok, nkeys = tokens_of([k], new)
+                pcm = self._sess.step(slot, tok, final=True, seed=self.seed, stream_keys=nkeys)
+                account([k], new, pcm.cpu().numpy(), True)
         for key in [k for k, st in self._streams.items() if st.done and st.flushed]:
             slot = self._slot.pop(key)
             self._sess.reset(slot, 1)
