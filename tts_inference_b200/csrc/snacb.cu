@@ -1330,14 +1330,18 @@ int snacb_session_step(snacb_session s, int slot0, int n, const int32_t* new_tok
     int32_t* tokp = s->tok + so * 7 * Fm;
     if (slide > 0) {
         // rows [slide, Fp) frames of every stage -> [0, kKeep): source and destination do not overlap (slide >= kKeep)
-        auto move = [&](void* buf, size_t row_bytes_per_frame) -> cudaError_t {
+        // the window keeps kKeep frames of TOKENS (the end-of-stream flush re-decodes from them) but only the last
+        // kKeepAct frames of the activations: no stage reads further back than 3.1 frames (block 0: 2.2 frames of lag + 27 rows of taps)
+        constexpr int kKeepAct = 4;
+        auto move_n = [&](void* buf, size_t row_bytes_per_frame, int keep) -> cudaError_t {
             if (!buf) return cudaSuccess;
             const size_t pitch = row_bytes_per_frame * Fm;
-            char* base = static_cast<char*>(buf) + so * pitch;
-            return cudaMemcpy2DAsync(base, pitch, base + row_bytes_per_frame * slide, pitch, row_bytes_per_frame * kKeep, n,
+            char* base = static_cast<char*>(buf) + so * pitch + row_bytes_per_frame * (kKeep - keep);
+            return cudaMemcpy2DAsync(base, pitch, base + row_bytes_per_frame * slide, pitch, row_bytes_per_frame * keep, n,
                                      cudaMemcpyDeviceToDevice, st);
         };
-        CK(h, move(s->tok, 7 * sizeof(int32_t)));
+        auto move = [&](void* buf, size_t row_bytes_per_frame) { return move_n(buf, row_bytes_per_frame, kKeepAct); };
+        CK(h, move_n(s->tok, 7 * sizeof(int32_t), kKeep));
         CK(h, move(s->stem, static_cast<size_t>(4) * kDecDim * 2));
         size_t rows = 4;
         for (int bi = 0; bi < 4; ++bi) {
@@ -1500,7 +1504,11 @@ int snacb_session_step_multi(snacb_session s, int n, const int32_t* slots_host, 
     if (n_slide > 0) {
         CK(h, cudaMemcpyAsync(d_list, v_list, n_slide * sizeof(int32_t), cudaMemcpyHostToDevice, st));
         CK(h, cudaMemcpyAsync(d_slide, v_slide, n_slide * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-        auto move = [&](void* buf, size_t frame_bytes) { launch_session_slide(buf, frame_bytes * Fm, frame_bytes, kKeep, d_list, d_slide, n_slide, st); };
+        constexpr int kKeepAct = 4;      // activations: only the last 4 frames of the kept window are live (see snacb_session_step)
+        auto move = [&](void* buf, size_t frame_bytes) {
+            if (buf) launch_session_slide(static_cast<char*>(buf) + frame_bytes * (kKeep - kKeepAct), frame_bytes * Fm, frame_bytes, kKeepAct,
+                                          d_list, d_slide, n_slide, st);
+        };
         // the token rows are 28 bytes per frame (sources not 16-byte aligned): a plain copy per sliding slot
         for (int i = 0; i < n_slide; ++i) {
             int32_t* row = s->tok + static_cast<size_t>(v_list[i]) * 7 * Fm;
