@@ -199,7 +199,9 @@ enum { EPI_C_NOISE = 0, EPI_C_MID = 1, EPI_C_FINAL = 2 };
 }  // namespace
 
 // NW symmetric warps (prologue + epilogue); thread 0 also issues TMA / MMA.  16 warps: one CTA per SM; 8 warps: two.
-template <int C, int NB, int NW, typename HT, bool FOLD>
+// JIT: the race-detector build of the same kernel (per-warp delays after the prologue's barrier, see below); the product
+// instantiations carry none of it
+template <int C, int NB, int NW, typename HT, bool FOLD, bool JIT = false>
 __global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 1)
 k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmOe,
         const __grid_constant__ CUtensorMap tmOm, const __grid_constant__ CUtensorMap tmWn,
@@ -555,8 +557,8 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
             // starts its in-place rewrite at a different, pseudo-random time (up to half a prologue apart), so a warp that
             // read a row another warp owns AFTER the barrier would see it rewritten in some runs and not in others; the
             // output must stay bit-identical for every seed (tests/test_gpu_parity.py::test_chain_schedule_survives_jitter).
-            // (Measured cost of carrying it in the product kernel: < 0.5 % of the chain.)
-            if (a.jitter != 0u) {
+            // (Carried in the product kernel it cost 3 % of the C = 64 chain: a separate instantiation, selected by the seed.)
+            if (JIT && a.jitter != 0u) {
                 const unsigned hsh = static_cast<unsigned>(splitmix64((static_cast<unsigned long long>(a.jitter) << 32) ^
                                                                       (static_cast<unsigned long long>(tile) << 8) ^ (warp << 2) ^ l));
                 const long long until = clock64() + (hsh & 4095u);
@@ -653,15 +655,15 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
 
 namespace {
 
-template <int C, int NB, int NW, typename HT, bool FOLD>
+template <int C, int NB, int NW, typename HT, bool FOLD, bool JIT = false>
 cudaError_t launch_chain_t(const ChainArgs& a, const CUtensorMap* tm, int sm_count, cudaStream_t st) {
     using Cfg = ChainCfg<C, NB, std::is_same<HT, __half>::value, FOLD>;
     static PerDeviceOnce once;
     int dev_;
     if (once.needed(&dev_)) {
-        cudaError_t e = cudaFuncSetAttribute(k_chain<C, NB, NW, HT, FOLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
+        cudaError_t e = cudaFuncSetAttribute(k_chain<C, NB, NW, HT, FOLD, JIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(k_chain<C, NB, NW, HT, FOLD>, cudaFuncAttributePreferredSharedMemoryCarveout,
+        e = cudaFuncSetAttribute(k_chain<C, NB, NW, HT, FOLD, JIT>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                  cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return e;
         once.done(dev_);
@@ -670,7 +672,7 @@ cudaError_t launch_chain_t(const ChainArgs& a, const CUtensorMap* tm, int sm_cou
     if (tiles == 0) return cudaSuccess;
     const int slots = sm_count * (NW == 8 ? 2 : 1);
     const int grid = tiles < slots ? tiles : slots;
-    k_chain<C, NB, NW, HT, FOLD><<<grid, NW * 32, Cfg::kSmem, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], tm[6], a, tiles);
+    k_chain<C, NB, NW, HT, FOLD, JIT><<<grid, NW * 32, Cfg::kSmem, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], tm[6], a, tiles);
     return cudaGetLastError();
 }
 
@@ -732,6 +734,12 @@ void chain_build_spans(int C, ChainSpan (*spans)[kChainWarps][kChainSpans]) {
 // fold: the alpha-folded fp16 formulation (the d=1, 3, 9 weight maps then carry 1 / alpha2 in their K columns)
 cudaError_t launch_chain(int half_fp16, int fold, const ChainArgs& a, const CUtensorMap* tm, int sm_count, cudaStream_t st) {
     if (half_fp16) {
+        if (fold && a.jitter != 0u) {                       // race-detector instantiations (SNACB_CHAIN_JITTER)
+            if (a.C == 64) return launch_chain_t<64, kNB64, kNW64, __half, true, true>(a, tm, sm_count, st);
+            if (a.C == 128) return launch_chain_t<128, kNB128, kNW128, __half, true, true>(a, tm, sm_count, st);
+            if (a.C == 256) return launch_chain_t<256, kNB256, kNW256, __half, true, true>(a, tm, sm_count, st);
+            return cudaErrorInvalidValue;
+        }
         if (fold) {
             if (a.C == 64) return launch_chain_t<64, kNB64, kNW64, __half, true>(a, tm, sm_count, st);
             if (a.C == 128) return launch_chain_t<128, kNB128, kNW128, __half, true>(a, tm, sm_count, st);
