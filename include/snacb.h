@@ -249,6 +249,27 @@ int snacb_debug_chain_ws_spans(int C, int16_t* out, int cap);
 int snacb_experiments_built(void);
 
 /* ---------------------------------------------------------------------------------------------
+ * Streamer: the multi-stream front of the stateful session, what snacb_batcher_* is for window decodes.  Producers push
+ * token ids per stream (THREAD-SAFE, also while a tick runs); tick() -- single caller -- hands every stream's new whole
+ * frames to one snacb_session_step_multi per distinct frame count (streams at different positions share the launches),
+ * flushes the streams that ended, and returns the newly final samples: chunk i belongs to stream ids[i], its PCM is at
+ * pcm_host + offsets[i], lengths[i] samples; a stream's chunks over successive ticks concatenate to the batch decode of
+ * its tokens, bit for bit.  A stream holds one of max_streams session slots from its first push until the tick that
+ * flushes it; a push for a new stream when all slots are taken returns SNACB_ERR_STATE.  min_frames: new whole frames a
+ * stream needs before a tick serves it (1 = every frame, the reference's sliding cadence).  Replaces the per-stream
+ * Python buffering of stream_audio (modal_audio_stream.py:340-409) for any number of concurrent streams.
+ * --------------------------------------------------------------------------------------------- */
+typedef struct snacb_streamer_s* snacb_streamer;
+int snacb_streamer_create(snacb_streamer* out, snacb_handle h, int max_streams, int window_frames, int flags, int min_frames);
+void snacb_streamer_destroy(snacb_streamer s);
+int snacb_streamer_push(snacb_streamer s, uint64_t stream_id, const int32_t* tokens_host, int n);
+int snacb_streamer_end(snacb_streamer s, uint64_t stream_id);
+int snacb_streamer_active(snacb_streamer s);            /* streams holding a slot */
+/* Returns the number of chunks written (>= 0) or a negative status. */
+int snacb_streamer_tick(snacb_streamer s, uint64_t seed, int max_chunks, uint64_t* ids, int64_t* offsets, int32_t* lengths,
+                        int16_t* pcm_host, size_t pcm_capacity);
+
+/* ---------------------------------------------------------------------------------------------
  * SNAC ENCODE path: audio -> codes, the other half of the codec.  The reference never
  * calls it at inference (it only decodes); upstream it is snac.SNAC.encode = preprocess (right-pad to a multiple of
  * 2048 samples) -> Encoder (conv k7 1 -> 48; 4 EncoderBlocks: 3 ResidualUnits d = 1/3/9, Snake, strided conv k = 2s,

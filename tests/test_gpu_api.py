@@ -411,3 +411,70 @@ def test_session_step_multi_serves_asynchronous_streams(decoder, precision, k):
     with pytest.raises(Exception):
         sess.step_multi([1, 1], tok[:2, :7].contiguous())                 # repeated slot
     sess.close()
+
+
+def test_native_streamer_from_producer_threads(decoder):
+    """snacb_streamer_*: four producer threads push token ids of 12 streams (different lengths, starting at different
+    times, more streams over time than there are slots) while the main thread ticks; every stream's chunks concatenate to
+    its own batch decode, bit for bit; slots are recycled; a push beyond the slot capacity is refused."""
+    import threading
+    import time
+    from tts_inference_b200.streamer import StreamServer
+    n_str, max_streams = 12, 8
+    lens = [9, 40, 23, 5, 61, 17, 33, 2, 28, 45, 12, 36]
+    tokens = synth.make_tokens(n_str, max(lens), seed=123)
+    srv = StreamServer(decoder, max_streams, 32, min_frames=1)
+    got = {i: [] for i in range(n_str)}
+    order = []                                   # stream ids in the order of their first push = their noise keys
+    lock = threading.Lock()
+    stop = threading.Event()
+    errors = []
+
+    def producer(my):
+        try:
+            for sid in my:
+                while True:                      # wait for a free slot (the first push claims it)
+                    try:
+                        with lock:
+                            srv.push(sid, tokens[sid, :3].tolist())
+                            order.append(sid)
+                        break
+                    except Exception:
+                        time.sleep(0.002)
+                pos = 3
+                n_ids = 7 * lens[sid] + (sid % 4)            # some streams end with a ragged tail (< 7 ids): dropped
+                ids = np.concatenate([tokens[sid, :7 * lens[sid]], tokens[sid, :sid % 4]])
+                while pos < n_ids:
+                    step = 1 + (sid + pos) % 11
+                    srv.push(sid, ids[pos:pos + step].tolist())
+                    pos += step
+                    if pos % 3 == 0:
+                        time.sleep(0.0005)
+                srv.end(sid)
+        except Exception as e:                   # noqa: BLE001
+            errors.append(e)
+
+    threads = [threading.Thread(target=producer, args=(list(range(k, n_str, 4)),)) for k in range(4)]
+    for t in threads:
+        t.start()
+    t0 = time.time()
+    while (any(t.is_alive() for t in threads) or srv.active() > 0) and time.time() - t0 < 120:
+        for sid, pcm in srv.tick(seed=4):
+            got[sid].append(pcm)
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    assert srv.active() == 0
+    for sid in range(n_str):
+        key = torch.tensor([order.index(sid)], dtype=torch.int32).cuda()
+        tok = torch.from_numpy(np.ascontiguousarray(tokens[sid:sid + 1, :7 * lens[sid]])).cuda()
+        ref = decoder.decode(tok, raw_ids=True, seed=4, stream_keys=key).cpu().numpy()[0]
+        cat = np.concatenate(got[sid]) if got[sid] else np.empty(0, dtype=np.int16)
+        assert cat.shape == ref.shape, (sid, cat.shape, ref.shape)
+        assert np.array_equal(cat, ref), sid
+    # capacity: the ninth concurrent stream is refused until a slot frees up
+    for sid in range(100, 100 + max_streams):
+        srv.push(sid, tokens[0, :7].tolist())
+    with pytest.raises(Exception):
+        srv.push(999, tokens[0, :7].tolist())
+    srv.close()

@@ -57,6 +57,8 @@ EXPORTS = [
     "snacb_debug_session_frontier", "snacb_experiments_built",
     "snacb_encoder_create", "snacb_encoder_destroy", "snacb_encoder_last_error", "snacb_encoder_launches", "snacb_encode_frames",
     "snacb_encode", "snacb_pack_tokens",
+    "snacb_streamer_create", "snacb_streamer_destroy", "snacb_streamer_push", "snacb_streamer_end", "snacb_streamer_active",
+    "snacb_streamer_tick",
 ]
 
 _lib = None
@@ -146,6 +148,13 @@ def load() -> C.CDLL:
     lib.snacb_encode_frames.argtypes = [C.c_int]
     lib.snacb_encode.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, i32p, i32p, i32p, vp, vp, vp]
     lib.snacb_pack_tokens.argtypes = [i32p, i32p, i32p, C.c_int, C.c_int, C.c_int, i32p, vp]
+    lib.snacb_streamer_create.argtypes = [C.POINTER(vp), vp, C.c_int, C.c_int, C.c_int, C.c_int]
+    lib.snacb_streamer_destroy.argtypes = [vp]
+    lib.snacb_streamer_destroy.restype = None
+    lib.snacb_streamer_push.argtypes = [vp, u64, vp, C.c_int]
+    lib.snacb_streamer_end.argtypes = [vp, u64]
+    lib.snacb_streamer_active.argtypes = [vp]
+    lib.snacb_streamer_tick.argtypes = [vp, u64, C.c_int, vp, vp, vp, vp, C.c_size_t]
     _lib = lib
     return lib
 

@@ -15,7 +15,7 @@ import sys
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libsnacb.so")
-SOURCES = ["snacb.cu", "kernels_simt.cu", "kernels_tc.cu", "kernels_res2.cu", "kernels_chain.cu", "kernels_chain_ws.cu", "kernels_convt.cu", "kernels_io.cu", "encoder.cu", "batcher.cpp"]
+SOURCES = ["snacb.cu", "kernels_simt.cu", "kernels_tc.cu", "kernels_res2.cu", "kernels_chain.cu", "kernels_chain_ws.cu", "kernels_convt.cu", "kernels_io.cu", "encoder.cu", "batcher.cpp", "streamer.cpp"]
 HEADERS = ["common.cuh", "chain_span.cuh", "kernels.h", "ptx.cuh", os.path.join("..", "..", "include", "snacb.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
