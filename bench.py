@@ -287,6 +287,30 @@ def neighbour_rows(dec, args):
         cad[f"{k2}_frames_per_step"] = {"ms_per_step": ms, "emitted_audio_s_per_s": S2 * k2 * 2048 / SR / ms * 1e3}
     out["streaming_session"]["cadence_1024_async_streams"] = cad
     sess2.close()
+    # the native streamer end to end: host token ids in, host int16 out, 1024 asynchronous streams, one new frame per stream
+    # per tick (pushes outside the timed region: they run on producer threads in a server)
+    from tts_inference_b200.streamer import StreamServer
+    srv = StreamServer(dec, S2, 32, precision=args.precision, min_frames=1, max_samples_per_tick=S2 * 2048 * 12)
+    host_tok = synth.make_tokens(S2, 40, seed=5)
+    for i in range(S2):
+        srv.push(i, host_tok[i, :7 * (8 + 3 * (i % 4))])
+    srv.tick(seed=1)
+    srv.tick(seed=1)                                         # (a first step takes at most window - 16 frames: the 17-frame cohort's rest)
+    ticks = []
+    pos = [8 + 3 * (i % 4) for i in range(S2)]
+    for _ in range(10):
+        for i in range(S2):
+            srv.push(i, host_tok[i, 7 * pos[i]:7 * pos[i] + 7]); pos[i] += 1
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        chunks = srv.tick(seed=1)
+        ticks.append(time.perf_counter() - t0)
+        assert len(chunks) == S2 and all(c.size == 2048 for _, c in chunks)
+    tk = sorted(ticks)[len(ticks) // 2]
+    out["streaming_session"]["native_streamer_tick_1024_async_streams"] = {
+        "what": "snacb_streamer_tick wall time: staging + H2D of the new tokens, one session step for all streams, D2H of the PCM, sync",
+        "ms_per_tick": tk * 1e3, "emitted_audio_s_per_s": S2 * 2048 / SR / tk}
+    srv.close()
     enc = SnacEncoder(synth.make_encoder_state_dict(0))
     audio = torch.from_numpy(synth.make_audio(64, 2048 * 16)).cuda()
     enc.encode(audio)
