@@ -478,3 +478,40 @@ def test_native_streamer_from_producer_threads(decoder):
     with pytest.raises(Exception):
         srv.push(999, tokens[0, :7].tolist())
     srv.close()
+
+
+def test_two_gpus_in_one_process(state_dict):
+    """Two handles on two GPUs in ONE process (the opt-in shared-memory attributes are per device; entry points
+    must select their handle's device): the same tokens decode to the same bytes on both, calls interleaved, a session and
+    the device ingest on the second GPU while the current device is the first."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    from tts_inference_b200 import SnacDecoder
+    from tts_inference_b200.ingest import DeviceIngest
+    d0, d1 = SnacDecoder(state_dict, device=0), SnacDecoder(state_dict, device=1)
+    tokens = synth.make_tokens(33, 4, seed=8)
+    t0, t1 = torch.from_numpy(tokens).cuda(0), torch.from_numpy(tokens).cuda(1)
+    torch.cuda.set_device(0)
+    outs = []
+    for i in range(3):
+        a = d0.decode(t0, raw_ids=True, seed=i, extract_slice=bool(i & 1))
+        b = d1.decode(t1, raw_ids=True, seed=i, extract_slice=bool(i & 1))        # current device is 0: the handle selects 1
+        outs.append((a, b))
+    for a, b in outs:
+        assert a.device.index == 0 and b.device.index == 1
+        assert torch.equal(a.cpu(), b.cpu())
+    h = d1.decode_host(tokens, raw_ids=True, seed=0)
+    assert np.array_equal(h, outs[0][0].cpu().numpy())
+    sess = d1.open_session(4, 32)
+    long_tok = torch.from_numpy(synth.make_tokens(2, 12, seed=3)).cuda(1)
+    ref = d0.decode(long_tok.cuda(0), raw_ids=True, seed=2, stream_keys=torch.tensor([0, 1], dtype=torch.int32).cuda(0)).cpu()
+    got = torch.cat([sess.step(0, long_tok[:, :42], seed=2).cpu(), sess.step(0, long_tok[:, 42:], final=True, seed=2).cpu()], dim=1)
+    assert torch.equal(got, ref)
+    ing = DeviceIngest(8, device=1) if "device" in DeviceIngest.__init__.__code__.co_varnames else None
+    if ing is not None:
+        ids = torch.full((8, 30), 128266 + 5, dtype=torch.int32).cuda(1)
+        ids[:, 0] = 128257
+        wt, ws, *_ = ing.step(ids)
+        assert wt.shape[0] == 8 and wt.device.index == 1
+    d0.close(); d1.close()                                  # closes d1's open session first
+    assert not sess._s.value

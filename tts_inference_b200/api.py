@@ -42,8 +42,16 @@ class SnacDecoder:
     # ------------------------------------------------------------------ plumbing
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
+            for child in list(getattr(self, "_children", ())):      # sessions / streamers hold pointers into the handle
+                child.close()
             self._lib.snacb_destroy(self._h)
             self._h = C.c_void_p()
+
+    def _adopt(self, child):
+        import weakref
+        if not hasattr(self, "_children"):
+            self._children = weakref.WeakSet()
+        self._children.add(child)
 
     def __del__(self):
         try:
@@ -252,6 +260,7 @@ class StreamingSession:
         decoder._check(rc, "snacb_session_create")
         self.n_slots = int(n_slots)
         self.max_frames = int(self._lib.snacb_session_max_frames(self._s))
+        decoder._adopt(self)                                # closed with (before) its decoder
 
     def close(self):
         if getattr(self, "_s", None) is not None and self._s.value:

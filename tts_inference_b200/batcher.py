@@ -31,6 +31,8 @@ class WindowBatcher:
         self.policy = int(policy)
         flags = (_lib.RAW_IDS if raw_ids else 0) | (_lib.FP32 if precision == "fp32" else 0) | \
             (_lib.BF16 if precision == "bf16" else 0)
+        if decoder is not None:
+            decoder._adopt(self)                            # closed with (before) its decoder
         rc = self._lib.snacb_batcher_create(C.byref(self._b), decoder._h if decoder is not None else None,
                                             self.policy, flags, self.max_windows)
         if rc != 0:

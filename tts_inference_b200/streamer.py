@@ -23,6 +23,7 @@ class StreamServer:
         rc = self._lib.snacb_streamer_create(C.byref(self._s), decoder._h, int(max_streams), int(window_frames), flags, int(min_frames))
         decoder._check(rc, "snacb_streamer_create")
         self.max_streams = int(max_streams)
+        decoder._adopt(self)                                # closed with (before) its decoder
         import torch
         cap = max_samples_per_tick or self.max_streams * 2048 * 24
         self._pcm = torch.empty(cap, dtype=torch.int16).pin_memory()        # pinned: the copy-out is a DMA
