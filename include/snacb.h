@@ -239,6 +239,10 @@ int snacb_debug_tap_copy(snacb_handle h, int idx, float* dst_host, size_t dst_el
  * Returns (tile height in rows incl. the 40-row halo either side) | (warps per CTA << 16), or SNACB_ERR_ARG.
  * No GPU needed. */
 int snacb_debug_chain_spans(int C, int16_t* out, int cap);
+/* The schedule of a SHORT last tile: a row range that is not a whole number of tiles ends in a tile that owns only
+ * own_rows (0 < own_rows < tile height - 80) rows; it runs this shorter table and skips everything past its right halo.
+ * Same layout and return value; 0 when such a tile does not fit the table (the kernel then runs it as a full tile). */
+int snacb_debug_chain_spans_last(int C, int own_rows, int16_t* out, int cap);
 
 /* The same for the warp-specialised, block-pipelined chain kernel (kernels_chain_ws.cu; C = 64 or 128, enabled with
  * SNACB_CHAIN_WS=1): spans live inside ONE 128-row block and count QUADS (4 steps): {first_row (block-relative),

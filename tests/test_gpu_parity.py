@@ -403,6 +403,26 @@ def test_bulk_tail_kernel_is_bit_identical(decoder, monkeypatch, prec, B, F_, sl
     assert int((new[0] != 0).sum()) > new[0].numel() // 2
 
 
+@pytest.mark.parametrize("prec", ["fp16", "bf16"])
+@pytest.mark.parametrize("B,F_,rng", [(24, 4, None), (3, 37, None), (7, 4, "slice"), (5, 23, (9000, 30011)), (4, 9, (100, 2300)),
+                                      (2, 64, None), (9, 1, None), (3, 5, (0, 17))])
+def test_short_last_chain_tile_is_bit_identical(decoder, monkeypatch, prec, B, F_, rng):
+    """A row range that is not a whole number of chain tiles ends in a SHORT tile (own schedule, blocks / epilogue pieces
+    past its right halo skipped: kernels_chain.cu) -- against the same decode with every tile run as a full tile."""
+    tokens = _cuda(synth.make_tokens(B, F_, seed=17))
+    kw = dict(raw_ids=True, seed=6, precision=prec, return_wave=True)
+    if rng == "slice":
+        kw["extract_slice"] = True
+    elif rng is not None:
+        kw["sample_range"] = rng
+    new = decoder.decode(tokens, **kw)
+    monkeypatch.setenv("SNACB_NO_SHORT_TILE", "1")
+    old = decoder.decode(tokens, **kw)
+    torch.cuda.synchronize()
+    assert torch.equal(new[0], old[0]) and torch.equal(new[1], old[1])
+    assert int((new[0] != 0).sum()) > new[0].numel() // 2
+
+
 def test_golden_vectors(decoder):
     """Committed fixtures: bytes the REFERENCE's convert_to_audio returned with the oracle as SNAC."""
     z = np.load(os.path.join(GOLD, "decode_golden.npz"))

@@ -176,6 +176,18 @@ def test_two_rank_sharding_gloo():
 
 @pytest.mark.parametrize("C", [64, 128, 256])
 def test_chain_span_schedule(C):
+    _check_chain_span_schedule(C, 0)
+
+
+@pytest.mark.parametrize("C,own", [(64, 8), (64, 416), (64, 200), (128, 208), (128, 160), (128, 24), (256, 144), (256, 80),
+                                   (256, 98), (128, 431), (256, 1), (64, 345)])
+def test_chain_span_schedule_short_last_tile(C, own):
+    """The same emulation for the shorter schedule of a row range's LAST tile, which owns only `own` rows (round 2: it
+    used to run as a full tile): every row up to its right halo is still produced from the layer's original inputs."""
+    _check_chain_span_schedule(C, own)
+
+
+def _check_chain_span_schedule(C, own):
     """Schedule of the fused chain kernel's in-place prologue (host logic, no GPU): emulate the kernel's protocol
     on integers -- every warp first fetches the 3 rows before/after its spans, then all warps rewrite their rows
     in place in arbitrary order -- and check that every row whose result is needed at that layer is produced from
@@ -184,7 +196,8 @@ def test_chain_span_schedule(C):
     from tts_inference_b200 import _lib
     lib = _lib.load()
     buf = (Ct.c_int16 * (3 * 16 * 4 * 3))()
-    rc = lib.snacb_debug_chain_spans(C, buf, len(buf))
+    rc = lib.snacb_debug_chain_spans_last(C, own, buf, len(buf)) if own else lib.snacb_debug_chain_spans(C, buf, len(buf))
+    assert rc > 0
     rows, nw = rc & 0xFFFF, rc >> 16
     assert rows % 128 == 0 and 256 <= rows <= 1024 and nw in (8, 16)
     sp = np.frombuffer(buf, dtype=np.int16).reshape(3, 16, 4, 3)
@@ -221,8 +234,11 @@ def test_chain_span_schedule(C):
                             assert r not in written
                             written.add(r)
                             work[r] = sum((j + 2) * win[j] for j in range(7))
-            for r in range(need_lo[d], rows - need_lo[d]):     # the schedule may skip rows nobody consumes
+            need_hi = rows - need_lo[d] if not own else 40 + own + (36, 27, 0)[l]
+            for r in range(need_lo[d], need_hi):               # the schedule may skip rows nobody consumes
                 assert r in written and work[r] == want[r], (C, d, kc, r)
+            if own:                                            # and a short tile does skip: nothing far past its right halo
+                assert max(written) < min(rows, need_hi + 8 * d)
     per_warp = sp[:, :nw, :, 1].sum(axis=2)
     assert per_warp.max() - per_warp.min() <= 1                             # balanced to one octet
 

@@ -107,6 +107,11 @@ struct ChainArgs {
     int t0;                       // absolute index of row 0 in its stream (counter RNG; see GemmArgs::t0)
     StreamMap map; int rpf;       // streaming session (see StreamMap); rpf = rows per frame of y / out
     ChainSpan spans[3][kChainWarps][kChainSpans];
+    // the LAST tile of every stream owns only last_rows (a multiple of 8 would be nice, any value works) of the tile's
+    // rows when the row range is not a whole number of tiles: it runs the shorter schedule spans_last and skips the
+    // blocks / epilogue pieces past its right halo (kernels_chain.cu).  last_rows = 0: every tile is a full tile.
+    ChainSpan spans_last[3][kChainWarps][kChainSpans];
+    int last_rows;
     unsigned jitter;              // debug (SNACB_CHAIN_JITTER=seed): every warp spins a pseudo-random 0..4095 cycles after each
                                   // barrier of the in-place prologue -- the race detector for the schedule (see k_chain)
     int* tile_counter;            // zeroed before the launch: tiles beyond the first gridDim.x are claimed dynamically

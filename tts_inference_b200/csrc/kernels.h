@@ -91,7 +91,9 @@ cudaError_t launch_convt_ph(int half_fp16, const GemmArgs& a, const CUtensorMap&
 bool chain_supported(int C, int half_fp16);
 int chain_tile_rows(int C);           // rows of a tile incl. the halo (y tensor-map box = (64, 128, 1), 128B swizzle)
 int chain_warps(int C);               // warps per CTA of the launch configuration used for C channels
-void chain_build_spans(int C, ChainSpan (*spans)[kChainWarps][kChainSpans]);
+// own_rows > 0: the schedule of a tile that owns only its first own_rows rows (the last tile of a row range);
+// false (table untouched) when such a tile would not fit the table -- the caller then runs it as a full tile
+bool chain_build_spans(int C, ChainSpan (*spans)[kChainWarps][kChainSpans], int own_rows = 0);
 // tm[7]: y load map box (64,128,1); out store maps box (64,128-kChainHalo,1) and (64,128,1); noise 1x1, res d=1,
 // d=3, d=9 weight maps box (64, C); all 128B-swizzled.  fold = 1: the alpha-folded fp16 formulation (the three res
 // weight maps then point at the copies with 1 / alpha2 folded into their K columns); see chain_fold_safe in snacb.cu

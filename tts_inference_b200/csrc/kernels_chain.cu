@@ -37,6 +37,7 @@
 // two warp groups half a layer apart) are kept, uncompiled, under csrc/experiments/ (DESIGN.md section 6).
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <type_traits>
 #include <vector>
 
@@ -92,7 +93,8 @@ struct ChainCfg {
     static constexpr int kOffEpi = kOffPrm + kPrmBytes;
     static constexpr int kOffNz = kOffEpi + kEpiBytes;
     static constexpr int kSpanWarps = (C == 64) ? 8 : kChainWarps;          // warps of the launch configuration (kNW*)
-    static constexpr int kSpanBytes = 3 * kSpanWarps * kChainSpans * 8;    // the launch's span table (copied from the kernel parameters)
+    static constexpr int kSpanElems = 3 * kSpanWarps * kChainSpans;
+    static constexpr int kSpanBytes = 2 * kSpanElems * 4;   // the launch's two span tables (full tile, short last tile), packed
     static constexpr int kBarBytes = 256;
     static constexpr int kOffSpan = kOffNz + kNzBytes;
     static constexpr int kOffBar = kOffSpan + kSpanBytes;
@@ -218,7 +220,7 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
     uint32_t* sPrm = reinterpret_cast<uint32_t*>(smem + Cfg::kOffPrm);
     float* sEpi = reinterpret_cast<float*>(smem + Cfg::kOffEpi);
     float* sNz = reinterpret_cast<float*>(smem + Cfg::kOffNz);
-    ChainSpan* sSpan = reinterpret_cast<ChainSpan*>(smem + Cfg::kOffSpan);   // [3][kSpanWarps][kChainSpans]
+    uint32_t* sSpan = reinterpret_cast<uint32_t*>(smem + Cfg::kOffSpan);     // [2][3][kSpanWarps][kChainSpans]: r_first | n_oct << 16 | kc << 24
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kOffBar);
     uint64_t* ld_bar = bars;          // tile landed (TMA)
     uint64_t* w_bar = bars + 1;       // [2] weight buffers landed
@@ -226,6 +228,8 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
     uint64_t* wfree_bar = bars + 3 + NB;   // [2] chunked weights: the MMAs reading a buffer have retired
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5 + NB);
     volatile int* s_next = reinterpret_cast<volatile int*>(tmem_slot + 2);   // [2] next tile of this CTA, by tile parity
+    volatile int* s_cfg = s_next + 2;   // [2] rows_e | own_end << 16 of the tile (short last tile, see the tile loop); re-read
+                                        // where it is used instead of living in registers through the whole tile
 
     const long long t_kernel0 = clock64();
     const int tid = threadIdx.x;
@@ -272,8 +276,12 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
     // the span table is indexed by (layer, warp) at run time: from shared memory, not from the constant bank (a dynamically
     // indexed kernel parameter costs a constant-cache miss per layer: ~1 k cycles of the 'pre' phase, measured)
     static_assert(NW <= Cfg::kSpanWarps, "span table");
-    for (int i = tid; i < 3 * Cfg::kSpanWarps * kChainSpans; i += kThreads)
-        sSpan[i] = a.spans[i / (Cfg::kSpanWarps * kChainSpans)][(i / kChainSpans) % Cfg::kSpanWarps][i % kChainSpans];
+    for (int i = tid; i < Cfg::kSpanElems; i += kThreads) {
+        const ChainSpan f = a.spans[i / (Cfg::kSpanWarps * kChainSpans)][(i / kChainSpans) % Cfg::kSpanWarps][i % kChainSpans];
+        const ChainSpan g = a.spans_last[i / (Cfg::kSpanWarps * kChainSpans)][(i / kChainSpans) % Cfg::kSpanWarps][i % kChainSpans];
+        sSpan[i] = (static_cast<uint32_t>(f.r_first) & 0xFFFFu) | (static_cast<uint32_t>(f.n_oct) << 16) | (static_cast<uint32_t>(f.kc) << 24);
+        sSpan[Cfg::kSpanElems + i] = (static_cast<uint32_t>(g.r_first) & 0xFFFFu) | (static_cast<uint32_t>(g.n_oct) << 16) | (static_cast<uint32_t>(g.kc) << 24);
+    }
     // epilogue vectors, three per layer boundary i (0: NoiseBlock -> unit d=1, 1: d=1 -> d=3, 2: d=3 -> d=9, 3: d=9 -> out):
     //   [3i]     bias: sum of the 1x1 biases so far (0 for i = 0); FOLD, i < 3: that bias times alpha1 of the coming unit
     //   [3i + 1] alpha of the Snake the epilogue applies (the coming unit's snake1, the next layer's Snake for i = 3)
@@ -346,7 +354,7 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
     const uint32_t sx_addr = smem_u32(sX);
 
     // issue one layer's 1x1 conv for the whole tile (thread 0): TMEM[blk] (+)= A[blk] * W^T, one commit per block
-    auto issue_layer = [&](int l, int n, bool has_next) {
+    auto issue_layer = [&](int l, int n, bool has_next, int nb_live) {
         if (Cfg::kWChunked) {
             // K chunk by K chunk through two weight buffers; a buffer is refilled (two chunks ahead) as soon as the
             // MMAs reading it have retired.  All blocks complete with the last chunk.
@@ -358,11 +366,13 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
                 tc_fence_after();
                 const uint32_t w_addr = smem_u32(sW + buf * Cfg::kWChunk);
 #pragma unroll
-                for (int b = 0; b < NB; ++b)
+                for (int b = 0; b < NB; ++b) {
+                    if (b >= nb_live) continue;            // short last tile: blocks past its right halo
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
                         mma_f16_ss(tmem_base + b * C, umma_desc_sw128(sx_addr + kc * Cfg::kPlane + b * 16384 + k * 32),
                                    umma_desc_sw128(w_addr + k * 32), idescW, (l > 0 || kc > 0 || k > 0) ? 1u : 0u);
+                }
                 mma_commit(&wfree_bar[buf]);
                 if (kc & 1) {
                     const bool more = (kc + 1 < CH) || (l < 3) || has_next;
@@ -383,14 +393,16 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
         const uint32_t w_addr = smem_u32(sW + (Cfg::kWRes ? l : buf) * Cfg::kWLayer);
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
+            if (b < nb_live) {                             // short last tile: blocks past its right halo carry no MMAs
 #pragma unroll
-            for (int kc = 0; kc < CH; ++kc)
+                for (int kc = 0; kc < CH; ++kc)
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    mma_f16_ss(tmem_base + b * C, umma_desc_sw128(sx_addr + kc * Cfg::kPlane + b * 16384 + k * 32),
-                               umma_desc_sw128(w_addr + kc * (C * 128) + k * 32), idescW,
-                               (l > 0 || kc > 0 || k > 0) ? 1u : 0u);
-            mma_commit(&mma_bar[b]);
+                    for (int k = 0; k < 4; ++k)
+                        mma_f16_ss(tmem_base + b * C, umma_desc_sw128(sx_addr + kc * Cfg::kPlane + b * 16384 + k * 32),
+                                   umma_desc_sw128(w_addr + kc * (C * 128) + k * 32), idescW,
+                                   (l > 0 || kc > 0 || k > 0) ? 1u : 0u);
+            }
+            mma_commit(&mma_bar[b]);                       // every block's barrier completes a phase per layer
         }
     };
     // after ALL of layer l's MMAs completed: its weight buffer is free -> prefetch the layer two ahead (thread 0)
@@ -404,7 +416,8 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
     //   NOISE (bnd 0): x1 = y + n[t] * TMEM -> TMEM (fp32 residual stream); tile copy = snake1_0(x1)
     //   MID (bnd 1, 2): tile copy = snake1_bnd(TMEM + cumulative bias)
     //   FINAL (bnd 3):  tile copy = snake_next(TMEM + cumulative bias)
-    auto epilogue = [&](auto mode_tag, const int bnd, int t_start) {
+    auto epilogue = [&](auto mode_tag, const int bnd, int t_start, const int cfg) {
+        const int rows_e = cfg & 0xFFFF, own_end = cfg >> 16;
         constexpr int MODE = decltype(mode_tag)::value;
         constexpr bool kFoldHere = FOLD && MODE != EPI_C_FINAL;
         const float* vb = sEpi + (3 * bnd) * C;            // bias (FOLD: scaled bias)
@@ -417,7 +430,8 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
         for (int it = g; it < kPieces; it += NW / 4) {
             const int blk = it / (C / 32), cg = it % (C / 32);
             // the last epilogue only feeds the TMA stores: 32-row groups entirely inside the halo are skipped
-            if (MODE == EPI_C_FINAL && (blk * 128 + q * 32 + 32 <= kHalo || blk * 128 + q * 32 >= Cfg::kRows - kHalo)) continue;
+            if (MODE == EPI_C_FINAL && (blk * 128 + q * 32 + 32 <= kHalo || blk * 128 + q * 32 >= own_end)) continue;
+            if (blk * 128 + q * 32 >= rows_e) continue;        // short last tile: rows past its right halo
             mbar_wait(&mma_bar[blk], mma_par);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + blk * C + cg * 32;
@@ -494,7 +508,16 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
         int s, t_start;
         tile_coords(tile, s, t_start);
         // claim the tile after this one (persistent CTAs, dynamic order: tiles cost the same but SMs do not run alike)
-        if (tid == 0) s_next[n & 1] = static_cast<int>(gridDim.x) + atomicAdd(a.tile_counter, 1);
+        if (tid == 0) {
+            s_next[n & 1] = static_cast<int>(gridDim.x) + atomicAdd(a.tile_counter, 1);
+            // The last tile of a row range that is not a whole number of tiles owns only a.last_rows rows: it runs the
+            // shorter span schedule, drains / rewrites rows [0, rows_e) only (rows_e covers its right halo, in whole 32-row
+            // pieces) and issues MMAs for the blocks that hold them.  Every row it computes goes through the same arithmetic.
+            const bool short_t = a.last_rows > 0 && a.last_rows < Cfg::kROut && (tile % tiles_t) == tiles_t - 1;
+            const int own_end = short_t ? kHalo + a.last_rows : Cfg::kRows - kHalo;
+            const int rows_e = short_t ? ((own_end + kHalo + 31) & ~31) : Cfg::kRows;
+            s_cfg[n & 1] = rows_e | (own_end << 16);
+        }
 
         // ---------------------------------------------------------------- noise values (overlaps the tile load)
         {
@@ -516,8 +539,8 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
         const bool has_next = next_tile < num_tiles;
         tick(0);
         // ---------------------------------------------------------------- NoiseBlock: TMEM = Wn y, then x1 = y + n TMEM
-        if (tid == 0) issue_layer(0, n, has_next);
-        epilogue(std::integral_constant<int, EPI_C_NOISE>{}, 0, t_start);
+        if (tid == 0) issue_layer(0, n, has_next, ((s_cfg[n & 1] & 0xFFFF) + 127) >> 7);
+        epilogue(std::integral_constant<int, EPI_C_NOISE>{}, 0, t_start, s_cfg[n & 1]);
         if (tid == 0) { mbar_wait(&mma_bar[NB - 1], mma_par); prefetch_w(0, has_next); }
         mma_par ^= 1u;
         tc_fence_before();
@@ -531,10 +554,12 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
             // ---- spans of this warp: pre-read the 3 rows before and after each span (owned by other warps)
             uint32_t hd[kChainSpans][3], tl[kChainSpans][3];
             int r_first[kChainSpans], n_oct[kChainSpans], kcs[kChainSpans];
+            const uint32_t* spanT = sSpan + ((s_cfg[n & 1] & 0xFFFF) < Cfg::kRows ? Cfg::kSpanElems : 0);
             auto preread = [&]() {
 #pragma unroll
             for (int sp = 0; sp < kChainSpans; ++sp) {
-                const ChainSpan spn = sSpan[(l * Cfg::kSpanWarps + warp) * kChainSpans + sp];
+                const uint32_t spw = spanT[(l * Cfg::kSpanWarps + warp) * kChainSpans + sp];
+                const ChainSpan spn{static_cast<short>(spw & 0xFFFFu), static_cast<short>((spw >> 16) & 0xFFu), static_cast<short>(spw >> 24), 0};
                 r_first[sp] = spn.r_first; n_oct[sp] = spn.n_oct; kcs[sp] = spn.kc;
 #pragma unroll
                 for (int j = 0; j < 3; ++j) { hd[sp][j] = 0u; tl[sp][j] = 0u; }
@@ -597,9 +622,9 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
             fence_proxy_async_smem();
             __syncthreads();
             tick(4 + 4 * l);
-            if (tid == 0) issue_layer(l + 1, n, has_next);
-            if (l < 2) epilogue(std::integral_constant<int, EPI_C_MID>{}, l + 1, t_start);
-            else epilogue(std::integral_constant<int, EPI_C_FINAL>{}, 3, t_start);
+            if (tid == 0) issue_layer(l + 1, n, has_next, ((s_cfg[n & 1] & 0xFFFF) + 127) >> 7);
+            if (l < 2) epilogue(std::integral_constant<int, EPI_C_MID>{}, l + 1, t_start, s_cfg[n & 1]);
+            else epilogue(std::integral_constant<int, EPI_C_FINAL>{}, 3, t_start, s_cfg[n & 1]);
             if (tid == 0) { mbar_wait(&mma_bar[NB - 1], mma_par); prefetch_w(l + 1, has_next); }
             mma_par ^= 1u;
             if (l == 2) fence_proxy_async_smem();          // the tile copy is the source of the TMA stores below
@@ -611,11 +636,13 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
         // ---------------------------------------------------------------- stream the tile out, refill behind it
         if (tid == 0) {
             const int t_out = t_start + kHalo;
+            const int own_end = s_cfg[n & 1] >> 16;
             const int sl = sm_slot(a.map, s);
 #pragma unroll
             for (int b = 0; b < NB; ++b) {
 #pragma unroll
                 for (int kc = 0; kc < CH; ++kc) {
+                    if (b * 128 >= own_end) continue;      // short last tile: nothing owned in this block (empty group)
                     const uint8_t* src = sX + kc * Cfg::kPlane + b * 16384;
                     if (b == 0) tma_store_3d(&tmOe, src + kHalo * 128, kc * 64, t_out, sl);
                     else if (b == NB - 1) tma_store_3d(&tmOe, src, kc * 64, t_start + b * 128, sl);
@@ -691,17 +718,19 @@ int chain_warps(int C) { return C == 64 ? kNW64 : (C == 128 ? kNW128 : kNW256); 
 // Spans of the in-place prologue (see the header comment): for dilation d the rows of a tile split into d classes
 // r = r0 + k d.  Class starts are multiples of 8 (so that the swizzle phase of step k is static) no larger than the
 // first row whose result is needed at that layer; negative starts skip their first few steps.
-void chain_build_spans(int C, ChainSpan (*spans)[kChainWarps][kChainSpans]) {
+bool chain_build_spans(int C, ChainSpan (*spans)[kChainWarps][kChainSpans], int own_rows) {
     const int rows = chain_tile_rows(C), ch = C / 64, nw = chain_warps(C);
+    const int own = (own_rows > 0 && own_rows < rows - 2 * kChainHalo) ? own_rows : rows - 2 * kChainHalo;
     static const int dil[3] = {1, 3, 9};
+    ChainSpan out[3][kChainWarps][kChainSpans];
     for (int l = 0; l < 3; ++l) {
         const int d = dil[l];
         struct Cls { int kc, r0, noct; };
         std::vector<Cls> cls;
         const int top = (d == 1) ? 0 : (d == 3 ? 8 : 40);
-        // rows at or beyond `hi` are not needed downstream: the last unit feeds only the stored rows (< rows - halo),
+        // rows at or beyond `hi` are not needed downstream: the last unit feeds only the stored rows (< halo + own),
         // the unit before it additionally that unit's 27 rows of taps, the first one 9 more
-        const int hi = rows - kChainHalo + (l == 2 ? 0 : (l == 1 ? 27 : 36));
+        const int hi = kChainHalo + own + (l == 2 ? 0 : (l == 1 ? 27 : 36));
         for (int kc = 0; kc < ch; ++kc)
             for (int m = 0; m < d; ++m) {
                 const int r0 = top - 8 * m;
@@ -711,7 +740,7 @@ void chain_build_spans(int C, ChainSpan (*spans)[kChainWarps][kChainSpans]) {
         int total = 0;
         for (auto& c : cls) total += c.noct;
         for (int w = 0; w < kChainWarps; ++w) {
-            for (int k = 0; k < kChainSpans; ++k) spans[l][w][k] = ChainSpan{0, 0, 0, 0};
+            for (int k = 0; k < kChainSpans; ++k) out[l][w][k] = ChainSpan{0, 0, 0, 0};
             if (w >= nw) continue;
             const int lo = static_cast<int>(static_cast<long long>(w) * total / nw);
             const int hi = static_cast<int>(static_cast<long long>(w + 1) * total / nw);
@@ -719,14 +748,19 @@ void chain_build_spans(int C, ChainSpan (*spans)[kChainWarps][kChainSpans]) {
             for (auto& c : cls) {
                 const int a0 = lo > base ? lo : base, a1 = hi < base + c.noct ? hi : base + c.noct;
                 if (a1 > a0) {
-                    if (nsp >= kChainSpans) { fprintf(stderr, "snacb: chain span table overflow\n"); abort(); }
-                    spans[l][w][nsp++] = ChainSpan{static_cast<short>(c.r0 + 8 * d * (a0 - base)),
-                                                   static_cast<short>(a1 - a0), static_cast<short>(c.kc), 0};
+                    if (nsp >= kChainSpans) {
+                        if (own_rows > 0) return false;
+                        fprintf(stderr, "snacb: chain span table overflow\n"); abort();
+                    }
+                    out[l][w][nsp++] = ChainSpan{static_cast<short>(c.r0 + 8 * d * (a0 - base)),
+                                                 static_cast<short>(a1 - a0), static_cast<short>(c.kc), 0};
                 }
                 base += c.noct;
             }
         }
     }
+    memcpy(spans, out, sizeof out);
+    return true;
 }
 
 // tm: [0] y load map, box (64, 128, 1); [1] out store map, box (64, 88, 1); [2] out store map, box (64, 128, 1);

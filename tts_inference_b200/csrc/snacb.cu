@@ -51,6 +51,9 @@ struct BlockW {
     bool chain[2];                      // the fused NoiseBlock + ResidualUnit chain covers this block ([0] bf16, [1] fp16)
     ChainSpan spans[3][kChainWarps][kChainSpans];
     ChainSpan spans_ws[3][kChainWarps][kChainSpans];   // warp-specialised chain kernel (kernels_chain_ws.cu): quads inside a block
+    ChainSpan spans_last[3][kChainWarps][kChainSpans]; // schedule of a short last tile owning spans_last_key rows (cached)
+    int spans_last_key = 0;
+    bool spans_last_ok = false;
     bool fold = false;                  // fp16 chain: the alpha-folded formulation is numerically safe for this block's
                                         // Snake alphas (chain_fold_safe); otherwise the general fp32-Snake variant runs
 };
@@ -670,6 +673,19 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
             ca.map = smap; ca.rpf = T / F;
             const bool ws = h->chain_ws && chain_ws_supported(b.Cout, hk) && !plan;     // the experiment knows no sessions
             memcpy(ca.spans, ws ? b.spans_ws : b.spans, sizeof ca.spans);
+            const char* nst = getenv("SNACB_NO_SHORT_TILE");      // A/B switch (tests): the last tile runs as a full tile
+            if (!ws && !(nst && nst[0] == '1')) {
+                // the row range is rarely a whole number of tiles: its last tile runs a shorter schedule (kernels_chain.cu)
+                const int own = chain_tile_rows(b.Cout) - 2 * kChainHalo;
+                const int last = (ca.t_n > 0 ? ca.t_n : T) % own;
+                if (last > 0) {
+                    if (b.spans_last_key != last) {
+                        b.spans_last_ok = chain_build_spans(b.Cout, b.spans_last, last);
+                        b.spans_last_key = last;
+                    }
+                    if (b.spans_last_ok) { memcpy(ca.spans_last, b.spans_last, sizeof ca.spans_last); ca.last_rows = last; }
+                }
+            }
             ca.tile_counter = h->tile_counter;
             ca.jitter = h->chain_jitter;
             CK(h, cudaMemsetAsync(h->tile_counter, 0, sizeof(int), st));
@@ -1677,6 +1693,20 @@ int snacb_debug_chain_spans(int C, int16_t* out, int cap) {
     if (!out || !chain_supported(C, 1) || cap < 3 * kChainWarps * kChainSpans * 3) return SNACB_ERR_ARG;
     ChainSpan sp[3][kChainWarps][kChainSpans];
     chain_build_spans(C, sp);
+    for (int l = 0; l < 3; ++l)
+        for (int w = 0; w < kChainWarps; ++w)
+            for (int k = 0; k < kChainSpans; ++k) {
+                int16_t* o = out + ((l * kChainWarps + w) * kChainSpans + k) * 3;
+                o[0] = sp[l][w][k].r_first; o[1] = sp[l][w][k].n_oct; o[2] = sp[l][w][k].kc;
+            }
+    return chain_tile_rows(C) | (chain_warps(C) << 16);
+}
+
+int snacb_debug_chain_spans_last(int C, int own_rows, int16_t* out, int cap) {
+    if (!out || !chain_supported(C, 1) || cap < 3 * kChainWarps * kChainSpans * 3) return SNACB_ERR_ARG;
+    if (own_rows <= 0 || own_rows >= chain_tile_rows(C) - 2 * kChainHalo) return SNACB_ERR_ARG;
+    ChainSpan sp[3][kChainWarps][kChainSpans];
+    if (!chain_build_spans(C, sp, own_rows)) return 0;
     for (int l = 0; l < 3; ++l)
         for (int w = 0; w < kChainWarps; ++w)
             for (int k = 0; k < kChainSpans; ++k) {
