@@ -239,10 +239,15 @@ int snacb_debug_tap_copy(snacb_handle h, int idx, float* dst_host, size_t dst_el
  * Returns (tile height in rows incl. the 40-row halo either side) | (warps per CTA << 16), or SNACB_ERR_ARG.
  * No GPU needed. */
 int snacb_debug_chain_spans(int C, int16_t* out, int cap);
-/* The schedule of a SHORT last tile: a row range that is not a whole number of tiles ends in a tile that owns only
- * own_rows (0 < own_rows < tile height - 80) rows; it runs this shorter table and skips everything past its right halo.
- * Same layout and return value; 0 when such a tile does not fit the table (the kernel then runs it as a full tile). */
-int snacb_debug_chain_spans_last(int C, int own_rows, int16_t* out, int cap);
+/* The schedule of any tile type (kernels_chain.cu): own_end = first tile row past the rows the tile owns (0: a full
+ * tile; smaller for the SHORT last tile of a row range, which skips everything past its right halo); carry_top = 1: the
+ * tile is not the first of its strip, owns its rows from row 0 on and takes the three class rows above row 0 from the
+ * previous tile (top spans have field 4 = 1 + steps above row 0).  out: int16[3][16][4][4] {first_row, octets, chunk,
+ * top}.  Returns as above; 0 when such a tile does not fit the table (the decoder then falls back to full / halo tiles). */
+int snacb_debug_chain_spans_ex(int C, int own_end, int carry_top, int16_t* out, int cap);
+/* Strip plan of the chain kernel for t_n rows per stream, S streams, `slots` CTA slots: out4 = {tiles per strip, strips
+ * per stream, tiles of a stream's last strip, rows owned by its last tile (0 = full)}.  No GPU needed. */
+int snacb_debug_chain_plan(int C, int t_n, int S, int slots, int32_t* out4);
 
 /* The same for the warp-specialised, block-pipelined chain kernel (kernels_chain_ws.cu; C = 64 or 128, enabled with
  * SNACB_CHAIN_WS=1): spans live inside ONE 128-row block and count QUADS (4 steps): {first_row (block-relative),

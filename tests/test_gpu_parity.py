@@ -405,10 +405,13 @@ def test_bulk_tail_kernel_is_bit_identical(decoder, monkeypatch, prec, B, F_, sl
 
 @pytest.mark.parametrize("prec", ["fp16", "bf16"])
 @pytest.mark.parametrize("B,F_,rng", [(24, 4, None), (3, 37, None), (7, 4, "slice"), (5, 23, (9000, 30011)), (4, 9, (100, 2300)),
-                                      (2, 64, None), (9, 1, None), (3, 5, (0, 17))])
-def test_short_last_chain_tile_is_bit_identical(decoder, monkeypatch, prec, B, F_, rng):
-    """A row range that is not a whole number of chain tiles ends in a SHORT tile (own schedule, blocks / epilogue pieces
-    past its right halo skipped: kernels_chain.cu) -- against the same decode with every tile run as a full tile."""
+                                      (2, 64, None), (9, 1, None), (3, 5, (0, 17)), (300, 4, None), (1, 200, None)])
+def test_chain_tile_geometries_are_bit_identical(decoder, monkeypatch, prec, B, F_, rng):
+    """The chain kernel cuts a stream's row range into strips that one CTA walks in order: the first tile of a strip
+    recomputes 40 rows of context above its rows (halo-top), every further tile takes the three class rows above each
+    dilation class from its predecessor (carry-top, no halo above), and a range that is not a whole number of tiles ends in
+    a SHORT tile (own schedule, blocks / epilogue pieces past its right halo skipped): kernels_chain.cu.  Against the same
+    decode with one halo-top tile per strip (SNACB_NO_CARRY=1, the round-1 geometry) and with full last tiles."""
     tokens = _cuda(synth.make_tokens(B, F_, seed=17))
     kw = dict(raw_ids=True, seed=6, precision=prec, return_wave=True)
     if rng == "slice":
@@ -416,10 +419,15 @@ def test_short_last_chain_tile_is_bit_identical(decoder, monkeypatch, prec, B, F
     elif rng is not None:
         kw["sample_range"] = rng
     new = decoder.decode(tokens, **kw)
+    monkeypatch.setenv("SNACB_NO_CARRY", "1")
+    mid = decoder.decode(tokens, **kw)
     monkeypatch.setenv("SNACB_NO_SHORT_TILE", "1")
     old = decoder.decode(tokens, **kw)
+    monkeypatch.delenv("SNACB_NO_CARRY")
+    alt = decoder.decode(tokens, **kw)                     # carry-top tiles, full last tile
     torch.cuda.synchronize()
-    assert torch.equal(new[0], old[0]) and torch.equal(new[1], old[1])
+    for other in (mid, old, alt):
+        assert torch.equal(new[0], other[0]) and torch.equal(new[1], other[1])
     assert int((new[0] != 0).sum()) > new[0].numel() // 2
 
 

@@ -176,54 +176,81 @@ def test_two_rank_sharding_gloo():
 
 @pytest.mark.parametrize("C", [64, 128, 256])
 def test_chain_span_schedule(C):
-    _check_chain_span_schedule(C, 0)
+    _check_chain_span_schedule(C, 0, False)
 
 
-@pytest.mark.parametrize("C,own", [(64, 8), (64, 416), (64, 200), (128, 208), (128, 160), (128, 24), (256, 144), (256, 80),
-                                   (256, 98), (128, 431), (256, 1), (64, 345)])
-def test_chain_span_schedule_short_last_tile(C, own):
-    """The same emulation for the shorter schedule of a row range's LAST tile, which owns only `own` rows (round 2: it
-    used to run as a full tile): every row up to its right halo is still produced from the layer's original inputs."""
-    _check_chain_span_schedule(C, own)
+@pytest.mark.parametrize("C", [64, 128, 256])
+def test_chain_span_schedule_carry_top_tile(C):
+    """A tile that is not the first of its strip owns its rows from row 0 on: every dilation class starts at or above
+    row 0 and its first span takes the three class rows above row 0 from the carry the previous tile left."""
+    _check_chain_span_schedule(C, 0, True)
 
 
-def _check_chain_span_schedule(C, own):
+@pytest.mark.parametrize("C,own_end,carry", [(64, 48, False), (64, 456, False), (64, 240, False), (128, 248, False), (128, 200, False),
+                                             (128, 64, False), (256, 184, False), (256, 120, False), (256, 138, False),
+                                             (128, 471, False), (256, 41, False), (64, 385, False), (64, 8, True), (64, 440, True),
+                                             (128, 208, True), (128, 1, True), (256, 200, True), (256, 77, True), (128, 465, True)])
+def test_chain_span_schedule_short_last_tile(C, own_end, carry):
+    """The same emulation for the shorter schedule of a row range's LAST tile, which owns rows up to `own_end` only (round 2:
+    it used to run as a full tile): every row up to its right halo is still produced from the layer's original inputs."""
+    _check_chain_span_schedule(C, own_end, carry)
+
+
+def _check_chain_span_schedule(C, own_end, carry):
     """Schedule of the fused chain kernel's in-place prologue (host logic, no GPU): emulate the kernel's protocol
-    on integers -- every warp first fetches the 3 rows before/after its spans, then all warps rewrite their rows
-    in place in arbitrary order -- and check that every row whose result is needed at that layer is produced from
-    the layer's ORIGINAL inputs (no read-after-overwrite hazard), for dilations 1, 3, 9."""
+    on integers -- every warp first fetches the 3 rows before/after its spans (from the carry for the top span of a class
+    of a carry-top tile), then all warps rewrite their rows in place in arbitrary order -- and check that every row whose
+    result is needed at that layer is produced from the layer's ORIGINAL inputs (no read-after-overwrite hazard), for
+    dilations 1, 3, 9."""
     import ctypes as Ct
     from tts_inference_b200 import _lib
     lib = _lib.load()
-    buf = (Ct.c_int16 * (3 * 16 * 4 * 3))()
-    rc = lib.snacb_debug_chain_spans_last(C, own, buf, len(buf)) if own else lib.snacb_debug_chain_spans(C, buf, len(buf))
+    buf = (Ct.c_int16 * (3 * 16 * 4 * 4))()
+    rc = lib.snacb_debug_chain_spans_ex(C, own_end, 1 if carry else 0, buf, len(buf))
     assert rc > 0
     rows, nw = rc & 0xFFFF, rc >> 16
     assert rows % 128 == 0 and 256 <= rows <= 1024 and nw in (8, 16)
-    sp = np.frombuffer(buf, dtype=np.int16).reshape(3, 16, 4, 3)
+    sp = np.frombuffer(buf, dtype=np.int16).reshape(3, 16, 4, 4)
     assert (sp[:, nw:, :, 1] == 0).all()
-    need_lo = {1: 4, 3: 13, 9: 40}          # first row whose result is consumed downstream, per dilation
+    if not carry:
+        assert (sp[..., 3] == 0).all()
+    need_lo = {1: 4, 3: 13, 9: 40}          # halo-top tile: first row whose result is consumed downstream, per dilation
     rng = np.random.default_rng(0)
     for l, d in enumerate((1, 3, 9)):
         for kc in range(C // 64):
             x = rng.integers(1, 1 << 30, size=rows).astype(np.int64)       # layer input (one value per row)
-            f = lambda r, src: int(sum((j + 2) * (src[r + (j - 3) * d] if 0 <= r + (j - 3) * d < rows else 0)
-                                       for j in range(7)))                 # stands in for the 7-tap op
-            want = {r: f(r, x) for r in range(rows)}
+            above = rng.integers(1, 1 << 30, size=3 * d).astype(np.int64)  # the 3 d rows above the tile (previous tile)
+            src_at = lambda r: (int(x[r]) if 0 <= r < rows else (int(above[r + 3 * d]) if carry and -3 * d <= r < 0 else 0))
+            want = {r: sum((j + 2) * src_at(r + (j - 3) * d) for j in range(7)) for r in range(rows)}   # stands in for the 7-tap op
             work = x.copy()
-            spans = [(w, k, *sp[l, w, k]) for w in range(16) for k in range(4) if sp[l, w, k, 1] > 0 and sp[l, w, k, 2] == kc]
+            spans = [(w, k, *[int(v) for v in sp[l, w, k]]) for w in range(16) for k in range(4)
+                     if sp[l, w, k, 1] > 0 and sp[l, w, k, 2] == kc]
             pre = {}
-            for (w, k, r0, noct, _) in spans:                               # phase 1: pre-reads
+            for (w, k, r0, noct, _, top) in spans:                          # phase 1: pre-reads
                 assert r0 % 8 == 0
-                head = [work[r0 - (3 - j) * d] if r0 - (3 - j) * d >= 0 else 0 for j in range(3)]
+                if top > 0:
+                    r_nn = r0 + (top - 1) * d
+                    assert 0 <= r_nn < d and r_nn - d < 0                   # the class's first row inside the tile
+                    head = [int(above[r_nn - (3 - j) * d + 3 * d]) for j in range(3)]
+                else:
+                    head = [work[r0 - (3 - j) * d] if r0 - (3 - j) * d >= 0 else
+                            (int(above[r0 - (3 - j) * d + 3 * d]) if carry else 0) for j in range(3)]
                 tail = [work[r0 + (8 * noct + j) * d] if r0 + (8 * noct + j) * d < rows else 0 for j in range(3)]
                 pre[(w, k)] = (head, tail)
             written = set()
-            for (w, k, r0, noct, _) in sorted(spans, key=lambda s_: rng.random()):   # phase 2, any warp order
+            for (w, k, r0, noct, _, top) in sorted(spans, key=lambda s_: rng.random()):   # phase 2, any warp order
                 head, tail = pre[(w, k)]
                 n = 8 * noct
-                get = lambda i: (head[i + 3] if i < 0 else tail[i - n] if i >= n else
-                                 (work[r0 + i * d] if 0 <= r0 + i * d < rows else 0))
+                k0 = top - 1
+
+                def get(i):
+                    if top > 0 and k0 - 3 <= i < k0:
+                        return head[i - (k0 - 3)]
+                    if i < 0:
+                        return head[i + 3] if top == 0 else 0
+                    if i >= n:
+                        return tail[i - n]
+                    return work[r0 + i * d] if 0 <= r0 + i * d < rows else 0
                 win = [get(i) for i in range(-3, 3)]
                 for q in range(noct):
                     raw = [get(8 * q + kk + 3) for kk in range(8)]          # the octet's 8 loads come first
@@ -234,13 +261,36 @@ def _check_chain_span_schedule(C, own):
                             assert r not in written
                             written.add(r)
                             work[r] = sum((j + 2) * win[j] for j in range(7))
-            need_hi = rows - need_lo[d] if not own else 40 + own + (36, 27, 0)[l]
-            for r in range(need_lo[d], need_hi):               # the schedule may skip rows nobody consumes
+            lo = 0 if carry else need_lo[d]
+            need_hi = (own_end if own_end else rows - 40) + (36, 27, 0)[l]
+            for r in range(lo, need_hi):                       # the schedule may skip rows nobody consumes
                 assert r in written and work[r] == want[r], (C, d, kc, r)
-            if own:                                            # and a short tile does skip: nothing far past its right halo
+            if own_end:                                        # and a short tile does skip: nothing far past its right halo
                 assert max(written) < min(rows, need_hi + 8 * d)
     per_warp = sp[:, :nw, :, 1].sum(axis=2)
-    assert per_warp.max() - per_warp.min() <= 1                             # balanced to one octet
+    assert (per_warp.max(axis=1) - per_warp.min(axis=1) <= 1).all()         # every layer balanced to one octet
+
+
+def test_chain_strip_plan():
+    """Strips of the chain kernel (host logic): the tiles of a plan own exactly the row range, for many range lengths."""
+    import ctypes as Ct
+    from tts_inference_b200 import _lib
+    lib = _lib.load()
+    out = (Ct.c_int32 * 4)()
+    for C, rows in ((64, 512), (128, 512), (256, 256)):
+        own_h, own_c = rows - 80, rows - 40
+        for t_n in list(range(1, 1200, 7)) + [1024, 2048, 4096, 8192, 2592, 1296, 16384, 131072]:
+            for S, slots in ((1, 148), (64, 148), (1024, 296), (5000, 148)):
+                assert lib.snacb_debug_chain_plan(C, t_n, S, slots, out) == 0
+                K, sps, lst, lrows = out[0], out[1], out[2], out[3]
+                assert 1 <= K <= 24 and sps >= 1 and 1 <= lst <= K
+                SR = own_h + (K - 1) * own_c
+                full_last = own_h if lst == 1 else own_c
+                assert 0 <= lrows < full_last
+                owned = (sps - 1) * SR + (own_h + (lst - 2) * own_c if lst > 1 else 0) + (lrows if lrows else full_last)
+                assert owned == t_n, (C, t_n, S, K, sps, lst, lrows)
+    lib.snacb_debug_chain_plan(256, 1024, 1024, 148, out)
+    assert list(out) == [5, 1, 5, 200]              # BASELINE configs[1] at B = 1024, block 1: 5 tiles per stream instead of 6
 
 
 @pytest.mark.parametrize("policy", [0, 1])

@@ -47,7 +47,7 @@ class EncoderWeights(C.Structure):
 EXPORTS = [
     "snacb_version", "snacb_create", "snacb_destroy", "snacb_last_error", "snacb_unpack", "snacb_decode", "snacb_decode_keyed", "snacb_decode_range",
     "snacb_decode_host", "snacb_decode_host_submit", "snacb_decode_host_wait", "snacb_samples_out", "snacb_set_group_bytes", "snacb_stats",
-    "snacb_profile", "snacb_profile_report", "snacb_debug_tap_count", "snacb_debug_tap_info", "snacb_debug_tap_copy", "snacb_debug_chain_spans", "snacb_debug_chain_spans_last", "snacb_debug_chain_ws_spans", "snacb_chain_modes",
+    "snacb_profile", "snacb_profile_report", "snacb_debug_tap_count", "snacb_debug_tap_info", "snacb_debug_tap_copy", "snacb_debug_chain_spans", "snacb_debug_chain_spans_ex", "snacb_debug_chain_plan", "snacb_debug_chain_ws_spans", "snacb_chain_modes",
     "snacb_batcher_create", "snacb_batcher_destroy", "snacb_batcher_push", "snacb_batcher_end",
     "snacb_batcher_flush", "snacb_batcher_pending", "snacb_batcher_forget", "snacb_batcher_flush_submit", "snacb_batcher_flush_wait", "snacb_batcher_take",
     "snacb_ingest_create", "snacb_ingest_destroy", "snacb_ingest_reset", "snacb_ingest_window_capacity",
@@ -97,7 +97,8 @@ def load() -> C.CDLL:
     lib.snacb_debug_tap_info.argtypes = [vp, C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     lib.snacb_debug_tap_copy.argtypes = [vp, C.c_int, vp, C.c_size_t]
     lib.snacb_debug_chain_spans.argtypes = [C.c_int, i16p, C.c_int]
-    lib.snacb_debug_chain_spans_last.argtypes = [C.c_int, C.c_int, i16p, C.c_int]
+    lib.snacb_debug_chain_spans_ex.argtypes = [C.c_int, C.c_int, C.c_int, i16p, C.c_int]
+    lib.snacb_debug_chain_plan.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, i32p]
     lib.snacb_debug_chain_ws_spans.argtypes = [C.c_int, i16p, C.c_int]
     lib.snacb_chain_modes.argtypes = [vp, i32p]
     lib.snacb_batcher_create.argtypes = [C.POINTER(vp), vp, C.c_int, C.c_int, C.c_int]

@@ -86,7 +86,7 @@ constexpr int kChainWarps = 16;        // at most; a launch configuration may us
 constexpr int kChainSpans = 4;         // spans per warp and layer, at most
 constexpr int kChainWsP = 7;           // prologue warps of the warp-specialised chain kernel (kernels_chain_ws.cu)
 constexpr int kChainHalo = 40;
-struct ChainSpan { short r_first, n_oct, kc, pad; };   // a warp's run of 8-step octets along one dilation class
+struct ChainSpan { short r_first, n_oct, kc, pad; };   // a warp's run of 8-step octets along one dilation class; pad: see ChainArgs
 struct ChainLayer {
     const float *alpha1, *inv1;   // [C]
     const float* dw_w;            // [7][C]
@@ -106,12 +106,19 @@ struct ChainArgs {
     const int* stream_keys;       // optional [S]: counter RNG key of each stream instead of stream_offset + s
     int t0;                       // absolute index of row 0 in its stream (counter RNG; see GemmArgs::t0)
     StreamMap map; int rpf;       // streaming session (see StreamMap); rpf = rows per frame of y / out
+    // Tiles and strips (kernels_chain.cu).  A stream's row range is cut into STRIPS of strip_tiles tiles that one CTA
+    // walks in order.  The first tile of a strip is a HALO-TOP tile (40 rows of recomputed context above its owned rows,
+    // schedule `spans`); every further tile is a CARRY-TOP tile: it owns its rows from row 0 on, the three dilation-class
+    // rows above each class coming from the previous tile through `carry` (schedule `spans_carry`, whose top spans carry
+    // 1 + the number of steps above row 0 in ChainSpan::pad).  strip_tiles = 1: every tile is a halo-top tile.
+    // The last tile of a stream's last strip owns only last_rows rows when the range is not a whole number of tiles
+    // (0: it is a full tile): it runs `spans_last` (of its own type) and skips everything past its right halo.
     ChainSpan spans[3][kChainWarps][kChainSpans];
-    // the LAST tile of every stream owns only last_rows (a multiple of 8 would be nice, any value works) of the tile's
-    // rows when the row range is not a whole number of tiles: it runs the shorter schedule spans_last and skips the
-    // blocks / epilogue pieces past its right halo (kernels_chain.cu).  last_rows = 0: every tile is a full tile.
+    ChainSpan spans_carry[3][kChainWarps][kChainSpans];
     ChainSpan spans_last[3][kChainWarps][kChainSpans];
     int last_rows;
+    int strip_tiles, sps, last_strip_tiles;   // tiles per strip, strips per stream, tiles of a stream's last strip
+    void* carry;                  // [gridDim.x][2 (tile parity)][39][C] 16-bit scratch (strip_tiles > 1)
     unsigned jitter;              // debug (SNACB_CHAIN_JITTER=seed): every warp spins a pseudo-random 0..4095 cycles after each
                                   // barrier of the in-place prologue -- the race detector for the schedule (see k_chain)
     int* tile_counter;            // zeroed before the launch: tiles beyond the first gridDim.x are claimed dynamically

@@ -91,9 +91,15 @@ cudaError_t launch_convt_ph(int half_fp16, const GemmArgs& a, const CUtensorMap&
 bool chain_supported(int C, int half_fp16);
 int chain_tile_rows(int C);           // rows of a tile incl. the halo (y tensor-map box = (64, 128, 1), 128B swizzle)
 int chain_warps(int C);               // warps per CTA of the launch configuration used for C channels
-// own_rows > 0: the schedule of a tile that owns only its first own_rows rows (the last tile of a row range);
-// false (table untouched) when such a tile would not fit the table -- the caller then runs it as a full tile
-bool chain_build_spans(int C, ChainSpan (*spans)[kChainWarps][kChainSpans], int own_rows = 0);
+// Schedule of one tile type: own_end = first tile row past the owned rows (0: a full tile, rows - 40); carry_top: the
+// tile owns its rows from row 0 on (classes start at or above row 0, top spans flagged in ChainSpan::pad) instead of
+// from row 40.  false (table untouched) when the tile does not fit the table -- the caller then falls back.
+bool chain_build_spans(int C, ChainSpan (*spans)[kChainWarps][kChainSpans], int own_end = 0, bool carry_top = false);
+// strips for a row range of t_n rows per stream, S streams on `slots` CTA slots: tiles per strip, strips per stream, tiles
+// of the last strip, rows the last tile owns (0 = full).  no_carry: one halo-top tile per strip (the round-1 geometry)
+void chain_plan_strips(int C, int t_n, int S, int slots, bool no_carry, int* strip_tiles, int* sps, int* last_strip_tiles,
+                       int* last_rows);
+size_t chain_carry_bytes(int C, int sm_count);   // scratch for ChainArgs::carry
 // tm[7]: y load map box (64,128,1); out store maps box (64,128-kChainHalo,1) and (64,128,1); noise 1x1, res d=1,
 // d=3, d=9 weight maps box (64, C); all 128B-swizzled.  fold = 1: the alpha-folded fp16 formulation (the three res
 // weight maps then point at the copies with 1 / alpha2 folded into their K columns); see chain_fold_safe in snacb.cu

@@ -94,7 +94,8 @@ struct ChainCfg {
     static constexpr int kOffNz = kOffEpi + kEpiBytes;
     static constexpr int kSpanWarps = (C == 64) ? 8 : kChainWarps;          // warps of the launch configuration (kNW*)
     static constexpr int kSpanElems = 3 * kSpanWarps * kChainSpans;
-    static constexpr int kSpanBytes = 2 * kSpanElems * 4;   // the launch's two span tables (full tile, short last tile), packed
+    static constexpr int kSpanBytes = 3 * kSpanElems * 4;   // the launch's span tables (halo-top, carry-top, short last tile), packed
+    static constexpr int kROutC = kRows - kHalo;            // rows a carry-top tile owns (no halo above them)
     static constexpr int kBarBytes = 256;
     static constexpr int kOffSpan = kOffNz + kNzBytes;
     static constexpr int kOffBar = kOffSpan + kSpanBytes;
@@ -115,7 +116,7 @@ struct ChainCfg {
 template <int D, int ROWS, bool FOLD>
 __device__ __forceinline__ void span_half(uint8_t* plane, int r_oct, const int nq, const uint32_t h0, const uint32_t h1,
                                           const uint32_t h2, const uint32_t t0, const uint32_t t1, const uint32_t t2,
-                                          const uint32_t (&swz)[8], const uint32_t* prm) {
+                                          const uint32_t (&swz)[8], const uint32_t* prm, const int k0) {
     const uint4 q0 = *reinterpret_cast<const uint4*>(prm), q1 = *reinterpret_cast<const uint4*>(prm + 4);
     const __half2 bd = as_h2(q0.x);
     const __half2 w[7] = {as_h2(q0.y), as_h2(q0.z), as_h2(q0.w), as_h2(q1.x), as_h2(q1.y), as_h2(q1.z), as_h2(q1.w)};
@@ -134,8 +135,37 @@ __device__ __forceinline__ void span_half(uint8_t* plane, int r_oct, const int n
         if (r_oct + j * D >= 0) raw = *reinterpret_cast<const uint32_t*>(ob + j * D * 128 + swz[(j * D) & 7]);
         xs[3 + j] = raw;
     }
+    int qo = 0;
+    if (k0 >= 0) {
+        // Top span of a carry-top tile, first octet (kept out of the loop below, whose code must not change): the class
+        // starts k0 steps above row 0.  Rows above the tile read as 0, except the three class rows right above the first
+        // row inside it, which the previous tile left in the carry (h0..h2)
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            xs[6 + k] = (r_oct + (k + 3) * D >= 0)
+                            ? *reinterpret_cast<const uint32_t*>(ob + (k + 3) * D * 128 + swz[((k + 3) * D) & 7]) : 0u;
+        if (k0 > 0) {
+#pragma unroll
+            for (int i = 0; i < 11; ++i)
+                xs[i] = (i == k0) ? h0 : ((i == k0 + 1) ? h1 : ((i == k0 + 2) ? h2 : (i < 3 ? 0u : xs[i])));
+        }
+        if (nq == 1) { xs[11] = t0; xs[12] = t1; xs[13] = t2; }
+        uint32_t o[8];
+        dw_snake_half<8, FOLD>(xs, w, bd, al2, ia2, o);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int r = r_oct + k * D;
+            if (static_cast<unsigned>(r) < static_cast<unsigned>(ROWS))
+                *reinterpret_cast<uint32_t*>(ob + k * D * 128 + swz[(k * D) & 7]) = o[k];
+        }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) xs[i] = xs[8 + i];
+        r_oct += 8 * D;
+        ob += 8 * D * 128;
+        qo = 1;
+    }
 #pragma unroll 1
-    for (int qo = 0; qo < nq; ++qo) {
+    for (; qo < nq; ++qo) {
 #pragma unroll
         for (int k = 0; k < 8; ++k)
             xs[6 + k] = *reinterpret_cast<const uint32_t*>(ob + (k + 3) * D * 128 + swz[((k + 3) * D) & 7]);
@@ -159,7 +189,7 @@ __device__ __forceinline__ void span_half(uint8_t* plane, int r_oct, const int n
 template <int D, int ROWS>
 __device__ __forceinline__ void span_bf16(uint8_t* plane, int r_oct, const int nq, const uint32_t h0, const uint32_t h1,
                                           const uint32_t h2, const uint32_t t0, const uint32_t t1, const uint32_t t2,
-                                          const uint32_t (&swz)[8], const uint32_t* prm) {
+                                          const uint32_t (&swz)[8], const uint32_t* prm, const int k0) {
     const float4* p4 = reinterpret_cast<const float4*>(prm);
     const float4 q0 = p4[0], q1 = p4[1], q2 = p4[2], q3 = p4[3], q4 = p4[4];
     const float2 w[7] = {make_float2(q0.x, q0.y), make_float2(q0.z, q0.w), make_float2(q1.x, q1.y), make_float2(q1.z, q1.w),
@@ -175,8 +205,34 @@ __device__ __forceinline__ void span_bf16(uint8_t* plane, int r_oct, const int n
         if (r_oct + j * D >= 0) raw = *reinterpret_cast<const uint32_t*>(ob + j * D * 128 + swz[(j * D) & 7]);
         xs[3 + j] = raw;
     }
+    int qo = 0;
+    if (k0 >= 0) {                                 // top span of a carry-top tile: see span_half
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            xs[6 + k] = (r_oct + (k + 3) * D >= 0)
+                            ? *reinterpret_cast<const uint32_t*>(ob + (k + 3) * D * 128 + swz[((k + 3) * D) & 7]) : 0u;
+        if (k0 > 0) {
+#pragma unroll
+            for (int i = 0; i < 11; ++i)
+                xs[i] = (i == k0) ? h0 : ((i == k0 + 1) ? h1 : ((i == k0 + 2) ? h2 : (i < 3 ? 0u : xs[i])));
+        }
+        if (nq == 1) { xs[11] = t0; xs[12] = t1; xs[13] = t2; }
+        uint32_t o[8];
+        dw_snake_bf16<8>(xs, w, bd, al2, ia2, o);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int r = r_oct + k * D;
+            if (static_cast<unsigned>(r) < static_cast<unsigned>(ROWS))
+                *reinterpret_cast<uint32_t*>(ob + k * D * 128 + swz[(k * D) & 7]) = o[k];
+        }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) xs[i] = xs[8 + i];
+        r_oct += 8 * D;
+        ob += 8 * D * 128;
+        qo = 1;
+    }
 #pragma unroll 1
-    for (int qo = 0; qo < nq; ++qo) {
+    for (; qo < nq; ++qo) {
 #pragma unroll
         for (int k = 0; k < 8; ++k)
             xs[6 + k] = *reinterpret_cast<const uint32_t*>(ob + (k + 3) * D * 128 + swz[((k + 3) * D) & 7]);
@@ -208,7 +264,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 1)
 k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmOe,
         const __grid_constant__ CUtensorMap tmOm, const __grid_constant__ CUtensorMap tmWn,
         const __grid_constant__ CUtensorMap tmW0, const __grid_constant__ CUtensorMap tmW1,
-        const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ ChainArgs a, const int num_tiles) {
+        const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ ChainArgs a, const int num_strips) {
     constexpr bool kHalfMath = std::is_same<HT, __half>::value;
     using Cfg = ChainCfg<C, NB, kHalfMath, FOLD>;
     constexpr int CH = Cfg::kCH;
@@ -220,7 +276,7 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
     uint32_t* sPrm = reinterpret_cast<uint32_t*>(smem + Cfg::kOffPrm);
     float* sEpi = reinterpret_cast<float*>(smem + Cfg::kOffEpi);
     float* sNz = reinterpret_cast<float*>(smem + Cfg::kOffNz);
-    uint32_t* sSpan = reinterpret_cast<uint32_t*>(smem + Cfg::kOffSpan);     // [2][3][kSpanWarps][kChainSpans]: r_first | n_oct << 16 | kc << 24
+    uint32_t* sSpan = reinterpret_cast<uint32_t*>(smem + Cfg::kOffSpan);     // [3 tables][3][kSpanWarps][kChainSpans]: r_first | n_oct << 16 | kc << 24 | top << 28
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kOffBar);
     uint64_t* ld_bar = bars;          // tile landed (TMA)
     uint64_t* w_bar = bars + 1;       // [2] weight buffers landed
@@ -228,13 +284,14 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
     uint64_t* wfree_bar = bars + 3 + NB;   // [2] chunked weights: the MMAs reading a buffer have retired
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5 + NB);
     volatile int* s_next = reinterpret_cast<volatile int*>(tmem_slot + 2);   // [2] next tile of this CTA, by tile parity
-    volatile int* s_cfg = s_next + 2;   // [2] rows_e | own_end << 16 of the tile (short last tile, see the tile loop); re-read
-                                        // where it is used instead of living in registers through the whole tile
+    volatile int* s_cfg = s_next + 2;   // [2] the tile's type (see the tile loop): rows_e | own_end << 11 | halo_top << 22 |
+                                        // table << 23 | carry_out << 25; re-read where it is used instead of living in
+                                        // registers through the whole tile
 
     const long long t_kernel0 = clock64();
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
-    const int tiles_t = ((a.t_n > 0 ? a.t_n : a.T) + Cfg::kROut - 1) / Cfg::kROut;
+    const int strip_rows = Cfg::kROut + (a.strip_tiles - 1) * Cfg::kROutC;     // rows a full strip owns
     const CUtensorMap* wmaps[4] = {&tmWn, &tmW0, &tmW1, &tmW2};
 
     // ------------------------------------------------------------------ one-time setup
@@ -277,10 +334,14 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
     // indexed kernel parameter costs a constant-cache miss per layer: ~1 k cycles of the 'pre' phase, measured)
     static_assert(NW <= Cfg::kSpanWarps, "span table");
     for (int i = tid; i < Cfg::kSpanElems; i += kThreads) {
-        const ChainSpan f = a.spans[i / (Cfg::kSpanWarps * kChainSpans)][(i / kChainSpans) % Cfg::kSpanWarps][i % kChainSpans];
-        const ChainSpan g = a.spans_last[i / (Cfg::kSpanWarps * kChainSpans)][(i / kChainSpans) % Cfg::kSpanWarps][i % kChainSpans];
-        sSpan[i] = (static_cast<uint32_t>(f.r_first) & 0xFFFFu) | (static_cast<uint32_t>(f.n_oct) << 16) | (static_cast<uint32_t>(f.kc) << 24);
-        sSpan[Cfg::kSpanElems + i] = (static_cast<uint32_t>(g.r_first) & 0xFFFFu) | (static_cast<uint32_t>(g.n_oct) << 16) | (static_cast<uint32_t>(g.kc) << 24);
+        const int l_ = i / (Cfg::kSpanWarps * kChainSpans), w_ = (i / kChainSpans) % Cfg::kSpanWarps, k_ = i % kChainSpans;
+        auto pk = [](const ChainSpan& f) {
+            return (static_cast<uint32_t>(f.r_first) & 0xFFFFu) | (static_cast<uint32_t>(f.n_oct) << 16) |
+                   (static_cast<uint32_t>(f.kc) << 24) | (static_cast<uint32_t>(f.pad) << 28);
+        };
+        sSpan[i] = pk(a.spans[l_][w_][k_]);
+        sSpan[Cfg::kSpanElems + i] = pk(a.spans_carry[l_][w_][k_]);
+        sSpan[2 * Cfg::kSpanElems + i] = pk(a.spans_last[l_][w_][k_]);
     }
     // epilogue vectors, three per layer boundary i (0: NoiseBlock -> unit d=1, 1: d=1 -> d=3, 2: d=3 -> d=9, 3: d=9 -> out):
     //   [3i]     bias: sum of the 1x1 biases so far (0 for i = 0); FOLD, i < 3: that bias times alpha1 of the coming unit
@@ -316,9 +377,12 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
         mbar_expect_tx(&w_bar[buf], Cfg::kWChunk);
         tma_load_2d_hint(sW + buf * Cfg::kWChunk, wmaps[(G / CH) & 3], (G % CH) * 64, 0, &w_bar[buf], kL2EvictLast);
     };
+    // a tile = (strip << 5) | j: tile j of a strip; strip = stream * sps + the strip's index inside the stream's row range
     auto tile_coords = [&](int tile, int& s, int& t_start) {
-        s = tile / tiles_t;
-        t_start = (a.t_n > 0 ? a.t_lo : 0) + sm_off(a.map, s, a.rpf) + (tile % tiles_t) * Cfg::kROut - kHalo;
+        const int strip = tile >> 5, j = tile & 31;
+        s = strip / a.sps;
+        t_start = (a.t_n > 0 ? a.t_lo : 0) + sm_off(a.map, s, a.rpf) + (strip - s * a.sps) * strip_rows +
+                  (j == 0 ? -kHalo : Cfg::kROut + (j - 1) * Cfg::kROutC);
     };
     auto load_block = [&](int s, int t_start, int b) {      // thread 0; ld_bar's expect_tx covers the whole tile
         const int sl = sm_slot(a.map, s);
@@ -326,8 +390,8 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
         for (int kc = 0; kc < CH; ++kc)
             tma_load_3d_hint(sX + kc * Cfg::kPlane + b * 16384, &tmY, kc * 64, t_start + b * 128, sl, ld_bar, kL2EvictFirst);
     };
-    int tile = blockIdx.x;
-    if (tid == 0 && tile < num_tiles) {
+    int tile = static_cast<int>(blockIdx.x) << 5;
+    if (tid == 0 && (tile >> 5) < num_strips) {
         if (Cfg::kWRes) {
             mbar_expect_tx(&w_bar[0], 4 * Cfg::kWLayer);
             for (int l = 0; l < 4; ++l) load_w(l, 0);
@@ -417,7 +481,7 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
     //   MID (bnd 1, 2): tile copy = snake1_bnd(TMEM + cumulative bias)
     //   FINAL (bnd 3):  tile copy = snake_next(TMEM + cumulative bias)
     auto epilogue = [&](auto mode_tag, const int bnd, int t_start, const int cfg) {
-        const int rows_e = cfg & 0xFFFF, own_end = cfg >> 16;
+        const int rows_e = cfg & 0x7FF, own_end = (cfg >> 11) & 0x7FF, own_begin = ((cfg >> 22) & 1) ? kHalo : 0;
         constexpr int MODE = decltype(mode_tag)::value;
         constexpr bool kFoldHere = FOLD && MODE != EPI_C_FINAL;
         const float* vb = sEpi + (3 * bnd) * C;            // bias (FOLD: scaled bias)
@@ -430,7 +494,7 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
         for (int it = g; it < kPieces; it += NW / 4) {
             const int blk = it / (C / 32), cg = it % (C / 32);
             // the last epilogue only feeds the TMA stores: 32-row groups entirely inside the halo are skipped
-            if (MODE == EPI_C_FINAL && (blk * 128 + q * 32 + 32 <= kHalo || blk * 128 + q * 32 >= own_end)) continue;
+            if (MODE == EPI_C_FINAL && (blk * 128 + q * 32 + 32 <= own_begin || blk * 128 + q * 32 >= own_end)) continue;
             if (blk * 128 + q * 32 >= rows_e) continue;        // short last tile: rows past its right halo
             mbar_wait(&mma_bar[blk], mma_par);
             tc_fence_after();
@@ -504,19 +568,29 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
         }
     };
 
-    for (int n = 0; tile < num_tiles; ++n) {
+    for (int n = 0; (tile >> 5) < num_strips; ++n) {
         int s, t_start;
         tile_coords(tile, s, t_start);
         // claim the tile after this one (persistent CTAs, dynamic order: tiles cost the same but SMs do not run alike)
         if (tid == 0) {
-            s_next[n & 1] = static_cast<int>(gridDim.x) + atomicAdd(a.tile_counter, 1);
-            // The last tile of a row range that is not a whole number of tiles owns only a.last_rows rows: it runs the
-            // shorter span schedule, drains / rewrites rows [0, rows_e) only (rows_e covers its right halo, in whole 32-row
-            // pieces) and issues MMAs for the blocks that hold them.  Every row it computes goes through the same arithmetic.
-            const bool short_t = a.last_rows > 0 && a.last_rows < Cfg::kROut && (tile % tiles_t) == tiles_t - 1;
-            const int own_end = short_t ? kHalo + a.last_rows : Cfg::kRows - kHalo;
-            const int rows_e = short_t ? ((own_end + kHalo + 31) & ~31) : Cfg::kRows;
-            s_cfg[n & 1] = rows_e | (own_end << 16);
+            // Tile types.  The first tile of a strip is a HALO-TOP tile: 40 rows of context above its owned rows are
+            // recomputed (and garbage towards the top, never stored).  Every further tile of the strip is a CARRY-TOP tile:
+            // it owns its rows from row 0 on -- the three class rows above each dilation class come from the previous tile
+            // through the carry -- so only the halo BELOW a tile is computed twice.  The last tile of a stream's last strip
+            // may own fewer rows (a.last_rows): it runs the shorter span schedule, drains / rewrites rows [0, rows_e) only
+            // (rows_e covers its right halo, in whole 32-row pieces) and issues MMAs for the blocks that hold them.
+            // Every row any tile computes goes through the same arithmetic on the same inputs.
+            const int strip = tile >> 5, j = tile & 31;
+            const int si = strip % a.sps;
+            const int ntl = (si == a.sps - 1) ? a.last_strip_tiles : a.strip_tiles;
+            s_next[n & 1] = (j + 1 < ntl) ? tile + 1 : ((static_cast<int>(gridDim.x) + atomicAdd(a.tile_counter, 1)) << 5);
+            const bool short_t = a.last_rows > 0 && si == a.sps - 1 && j == ntl - 1;
+            const int own_begin = j == 0 ? kHalo : 0;
+            const int own_end = short_t ? own_begin + a.last_rows : Cfg::kRows - kHalo;
+            int rows_e = short_t ? ((own_end + kHalo + 31) & ~31) : Cfg::kRows;
+            if (rows_e > Cfg::kRows) rows_e = Cfg::kRows;
+            s_cfg[n & 1] = rows_e | (own_end << 11) | ((j == 0 ? 1 : 0) << 22) | ((short_t ? 2 : (j == 0 ? 0 : 1)) << 23) |
+                           ((j + 1 < ntl ? 1 : 0) << 25);
         }
 
         // ---------------------------------------------------------------- noise values (overlaps the tile load)
@@ -536,10 +610,10 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
         mbar_wait(ld_bar, n & 1);
         __syncthreads();
         const int next_tile = s_next[n & 1];
-        const bool has_next = next_tile < num_tiles;
+        const bool has_next = (next_tile >> 5) < num_strips;
         tick(0);
         // ---------------------------------------------------------------- NoiseBlock: TMEM = Wn y, then x1 = y + n TMEM
-        if (tid == 0) issue_layer(0, n, has_next, ((s_cfg[n & 1] & 0xFFFF) + 127) >> 7);
+        if (tid == 0) issue_layer(0, n, has_next, ((s_cfg[n & 1] & 0x7FF) + 127) >> 7);
         epilogue(std::integral_constant<int, EPI_C_NOISE>{}, 0, t_start, s_cfg[n & 1]);
         if (tid == 0) { mbar_wait(&mma_bar[NB - 1], mma_par); prefetch_w(0, has_next); }
         mma_par ^= 1u;
@@ -554,12 +628,15 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
             // ---- spans of this warp: pre-read the 3 rows before and after each span (owned by other warps)
             uint32_t hd[kChainSpans][3], tl[kChainSpans][3];
             int r_first[kChainSpans], n_oct[kChainSpans], kcs[kChainSpans];
-            const uint32_t* spanT = sSpan + ((s_cfg[n & 1] & 0xFFFF) < Cfg::kRows ? Cfg::kSpanElems : 0);
+            const int cfg_l = s_cfg[n & 1];
+            const uint32_t* spanT = sSpan + ((cfg_l >> 23) & 3) * Cfg::kSpanElems;
+            const bool carry_top = ((cfg_l >> 22) & 1) == 0;
+            const int c_off = (l == 0) ? 0 : (l == 1 ? 3 : 12);                 // this layer's rows inside the 39-row carry
             auto preread = [&]() {
 #pragma unroll
             for (int sp = 0; sp < kChainSpans; ++sp) {
                 const uint32_t spw = spanT[(l * Cfg::kSpanWarps + warp) * kChainSpans + sp];
-                const ChainSpan spn{static_cast<short>(spw & 0xFFFFu), static_cast<short>((spw >> 16) & 0xFFu), static_cast<short>(spw >> 24), 0};
+                const ChainSpan spn{static_cast<short>(spw & 0xFFFFu), static_cast<short>((spw >> 16) & 0xFFu), static_cast<short>((spw >> 24) & 0xFu), 0};
                 r_first[sp] = spn.r_first; n_oct[sp] = spn.n_oct; kcs[sp] = spn.kc;
 #pragma unroll
                 for (int j = 0; j < 3; ++j) { hd[sp][j] = 0u; tl[sp][j] = 0u; }
@@ -573,10 +650,36 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
                         if (rh >= 0) hd[sp][j] = *reinterpret_cast<const uint32_t*>(lane_base + rh * 128 + (((c16 ^ rh) & 7) << 4));
                         tl[sp][j] = *reinterpret_cast<const uint32_t*>(lane_base + rt * 128 + (((c16 ^ rt) & 7) << 4));
                     }
+                    // carry-top tile (rare path, kept apart from the loads above): the head rows of a span that lie above
+                    // row 0 come from the carry the previous tile of the strip left -- for the FIRST span of a class
+                    // (top = 1 + its steps above row 0) the three class rows above its first row inside the tile
+                    if (carry_top && spn.r_first - 3 * d < 0) {
+                        const int topk = static_cast<int>(spw >> 28);
+                        kcs[sp] = spn.kc | (topk << 8);
+                        // carry buffers of this CTA by tile parity: this tile reads what the previous one wrote
+                        const __half* crd = static_cast<const __half*>(a.carry) +
+                                            (static_cast<size_t>(blockIdx.x) * 2 + ((n & 1) ^ 1)) * 39 * C + c_off * C + spn.kc * 64 + 2 * lane;
+                        const int r_nn = spn.r_first + (topk > 0 ? topk - 1 : 0) * d;
+#pragma unroll
+                        for (int j = 0; j < 3; ++j) {
+                            const int rh = r_nn - (3 - j) * d;      // topk = 0: r_nn = r_first, only its rows above row 0
+                            if (rh < 0) hd[sp][j] = *reinterpret_cast<const uint32_t*>(crd + (rh + 3 * d) * C);
+                        }
+                    }
                 }
             }
             };
             preread();
+            if ((cfg_l >> 25) & 1) {
+                // the next tile of the strip starts at this tile's row kRows - 40: leave it the 3 d rows of S1 above that
+                for (int idx = tid; idx < 3 * d * CH * 8; idx += kThreads) {
+                    const int row = idx / (CH * 8), kc = (idx >> 3) % CH, c16 = idx & 7;
+                    const int r = Cfg::kRows - kHalo - 3 * d + row;
+                    const uint4 v = *reinterpret_cast<const uint4*>(sX + kc * Cfg::kPlane + r * 128 + (((c16 ^ r) & 7) << 4));
+                    __half* carry_wr = static_cast<__half*>(a.carry) + (static_cast<size_t>(blockIdx.x) * 2 + (n & 1)) * 39 * C;
+                    *reinterpret_cast<uint4*>(carry_wr + (c_off + row) * C + kc * 64 + c16 * 8) = v;
+                }
+            }
             __syncthreads();
             // Race detector in place of compute-sanitizer racecheck (closed on this pool): with a jitter seed every warp
             // starts its in-place rewrite at a different, pseudo-random time (up to half a prologue apart), so a warp that
@@ -598,7 +701,8 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
                 static_assert(kChainSpans == 4, "span select");
                 const int nq = sp == 0 ? n_oct[0] : (sp == 1 ? n_oct[1] : (sp == 2 ? n_oct[2] : n_oct[3]));
                 if (nq == 0) continue;
-                const int kc = sp == 0 ? kcs[0] : (sp == 1 ? kcs[1] : (sp == 2 ? kcs[2] : kcs[3]));
+                const int kck = sp == 0 ? kcs[0] : (sp == 1 ? kcs[1] : (sp == 2 ? kcs[2] : kcs[3]));
+                const int kc = kck & 0xFF, k0 = (kck >> 8) - 1;           // k0 >= 0: top span of a carry-top tile
                 const int r0 = sp == 0 ? r_first[0] : (sp == 1 ? r_first[1] : (sp == 2 ? r_first[2] : r_first[3]));
                 uint32_t hh[3], tt[3];
 #pragma unroll
@@ -609,20 +713,20 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
                 const uint32_t* prm = sPrm + ((l * (C / 2)) + kc * 32 + lane) * Cfg::kPrmWords;
                 uint8_t* plane = sX + kc * Cfg::kPlane;
                 if (kHalfMath) {
-                    if (d == 1) span_half<1, Cfg::kRows, FOLD>(plane, r0, nq, hh[0], hh[1], hh[2], tt[0], tt[1], tt[2], swz, prm);
-                    else if (d == 3) span_half<3, Cfg::kRows, FOLD>(plane, r0, nq, hh[0], hh[1], hh[2], tt[0], tt[1], tt[2], swz, prm);
-                    else span_half<9, Cfg::kRows, FOLD>(plane, r0, nq, hh[0], hh[1], hh[2], tt[0], tt[1], tt[2], swz, prm);
+                    if (d == 1) span_half<1, Cfg::kRows, FOLD>(plane, r0, nq, hh[0], hh[1], hh[2], tt[0], tt[1], tt[2], swz, prm, k0);
+                    else if (d == 3) span_half<3, Cfg::kRows, FOLD>(plane, r0, nq, hh[0], hh[1], hh[2], tt[0], tt[1], tt[2], swz, prm, k0);
+                    else span_half<9, Cfg::kRows, FOLD>(plane, r0, nq, hh[0], hh[1], hh[2], tt[0], tt[1], tt[2], swz, prm, k0);
                 } else {
-                    if (d == 1) span_bf16<1, Cfg::kRows>(plane, r0, nq, hh[0], hh[1], hh[2], tt[0], tt[1], tt[2], swz, prm);
-                    else if (d == 3) span_bf16<3, Cfg::kRows>(plane, r0, nq, hh[0], hh[1], hh[2], tt[0], tt[1], tt[2], swz, prm);
-                    else span_bf16<9, Cfg::kRows>(plane, r0, nq, hh[0], hh[1], hh[2], tt[0], tt[1], tt[2], swz, prm);
+                    if (d == 1) span_bf16<1, Cfg::kRows>(plane, r0, nq, hh[0], hh[1], hh[2], tt[0], tt[1], tt[2], swz, prm, k0);
+                    else if (d == 3) span_bf16<3, Cfg::kRows>(plane, r0, nq, hh[0], hh[1], hh[2], tt[0], tt[1], tt[2], swz, prm, k0);
+                    else span_bf16<9, Cfg::kRows>(plane, r0, nq, hh[0], hh[1], hh[2], tt[0], tt[1], tt[2], swz, prm, k0);
                 }
             }
             tick(3 + 4 * l);
             fence_proxy_async_smem();
             __syncthreads();
             tick(4 + 4 * l);
-            if (tid == 0) issue_layer(l + 1, n, has_next, ((s_cfg[n & 1] & 0xFFFF) + 127) >> 7);
+            if (tid == 0) issue_layer(l + 1, n, has_next, ((s_cfg[n & 1] & 0x7FF) + 127) >> 7);
             if (l < 2) epilogue(std::integral_constant<int, EPI_C_MID>{}, l + 1, t_start, s_cfg[n & 1]);
             else epilogue(std::integral_constant<int, EPI_C_FINAL>{}, 3, t_start, s_cfg[n & 1]);
             if (tid == 0) { mbar_wait(&mma_bar[NB - 1], mma_par); prefetch_w(l + 1, has_next); }
@@ -636,7 +740,8 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
         // ---------------------------------------------------------------- stream the tile out, refill behind it
         if (tid == 0) {
             const int t_out = t_start + kHalo;
-            const int own_end = s_cfg[n & 1] >> 16;
+            const int own_end = (s_cfg[n & 1] >> 11) & 0x7FF;
+            const bool halo_top = ((s_cfg[n & 1] >> 22) & 1) != 0;
             const int sl = sm_slot(a.map, s);
 #pragma unroll
             for (int b = 0; b < NB; ++b) {
@@ -644,7 +749,7 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
                 for (int kc = 0; kc < CH; ++kc) {
                     if (b * 128 >= own_end) continue;      // short last tile: nothing owned in this block (empty group)
                     const uint8_t* src = sX + kc * Cfg::kPlane + b * 16384;
-                    if (b == 0) tma_store_3d(&tmOe, src + kHalo * 128, kc * 64, t_out, sl);
+                    if (b == 0 && halo_top) tma_store_3d(&tmOe, src + kHalo * 128, kc * 64, t_out, sl);
                     else if (b == NB - 1) tma_store_3d(&tmOe, src, kc * 64, t_start + b * 128, sl);
                     else tma_store_3d(&tmOm, src, kc * 64, t_start + b * 128, sl);
                 }
@@ -695,11 +800,16 @@ cudaError_t launch_chain_t(const ChainArgs& a, const CUtensorMap* tm, int sm_cou
         if (e != cudaSuccess) return e;
         once.done(dev_);
     }
-    const int tiles = a.S * (((a.t_n > 0 ? a.t_n : a.T) + Cfg::kROut - 1) / Cfg::kROut);
-    if (tiles == 0) return cudaSuccess;
+    if (a.strip_tiles < 1 || a.strip_tiles > 31 || a.sps < 1 || a.last_strip_tiles < 1 || a.last_strip_tiles > a.strip_tiles ||
+        (a.strip_tiles > 1 && a.carry == nullptr))
+        return cudaErrorInvalidValue;
+    const long long strips = static_cast<long long>(a.S) * a.sps;
+    if (strips == 0) return cudaSuccess;
+    if (strips >= (1LL << 25)) return cudaErrorInvalidValue;            // a tile id is (strip << 5) | j
     const int slots = sm_count * (NW == 8 ? 2 : 1);
-    const int grid = tiles < slots ? tiles : slots;
-    k_chain<C, NB, NW, HT, FOLD, JIT><<<grid, NW * 32, Cfg::kSmem, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], tm[6], a, tiles);
+    const int grid = strips < slots ? static_cast<int>(strips) : slots;
+    k_chain<C, NB, NW, HT, FOLD, JIT><<<grid, NW * 32, Cfg::kSmem, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], tm[6], a,
+                                                                          static_cast<int>(strips));
     return cudaGetLastError();
 }
 
@@ -718,24 +828,31 @@ int chain_warps(int C) { return C == 64 ? kNW64 : (C == 128 ? kNW128 : kNW256); 
 // Spans of the in-place prologue (see the header comment): for dilation d the rows of a tile split into d classes
 // r = r0 + k d.  Class starts are multiples of 8 (so that the swizzle phase of step k is static) no larger than the
 // first row whose result is needed at that layer; negative starts skip their first few steps.
-bool chain_build_spans(int C, ChainSpan (*spans)[kChainWarps][kChainSpans], int own_rows) {
+bool chain_build_spans(int C, ChainSpan (*spans)[kChainWarps][kChainSpans], int own_end_in, bool carry_top) {
     const int rows = chain_tile_rows(C), ch = C / 64, nw = chain_warps(C);
-    const int own = (own_rows > 0 && own_rows < rows - 2 * kChainHalo) ? own_rows : rows - 2 * kChainHalo;
+    const int own_end = (own_end_in > 0 && own_end_in < rows - kChainHalo) ? own_end_in : rows - kChainHalo;
     static const int dil[3] = {1, 3, 9};
     ChainSpan out[3][kChainWarps][kChainSpans];
     for (int l = 0; l < 3; ++l) {
         const int d = dil[l];
-        struct Cls { int kc, r0, noct; };
+        struct Cls { int kc, r0, noct, k0; };
         std::vector<Cls> cls;
         const int top = (d == 1) ? 0 : (d == 3 ? 8 : 40);
-        // rows at or beyond `hi` are not needed downstream: the last unit feeds only the stored rows (< halo + own),
+        // rows at or beyond `hi` are not needed downstream: the last unit feeds only the stored rows (< own_end),
         // the unit before it additionally that unit's 27 rows of taps, the first one 9 more
-        const int hi = kChainHalo + own + (l == 2 ? 0 : (l == 1 ? 27 : 36));
+        const int hi = own_end + (l == 2 ? 0 : (l == 1 ? 27 : 36));
         for (int kc = 0; kc < ch; ++kc)
             for (int m = 0; m < d; ++m) {
-                const int r0 = top - 8 * m;
+                int r0 = top - 8 * m, k0 = 0;
+                if (carry_top) {
+                    // the class of residue m must produce every row from its first one (m) on: start at the largest
+                    // multiple of 8 that is <= m and = m (mod d); k0 = its steps above row 0 (nothing is stored for them)
+                    r0 = m;
+                    while (r0 & 7) { r0 -= d; ++k0; }
+                }
                 const int steps = (hi - r0 + d - 1) / d;
-                cls.push_back({kc, r0, (steps + 7) / 8});
+                if (steps <= 0) continue;
+                cls.push_back({kc, r0, (steps + 7) / 8, k0});
             }
         int total = 0;
         for (auto& c : cls) total += c.noct;
@@ -749,11 +866,13 @@ bool chain_build_spans(int C, ChainSpan (*spans)[kChainWarps][kChainSpans], int 
                 const int a0 = lo > base ? lo : base, a1 = hi < base + c.noct ? hi : base + c.noct;
                 if (a1 > a0) {
                     if (nsp >= kChainSpans) {
-                        if (own_rows > 0) return false;
+                        if (own_end_in > 0 || carry_top) return false;
                         fprintf(stderr, "snacb: chain span table overflow\n"); abort();
                     }
+                    // a carry-top class's FIRST span reads the three class rows above row 0 from the carry: pad = 1 + k0
+                    const short top_flag = (carry_top && a0 == base) ? static_cast<short>(1 + c.k0) : static_cast<short>(0);
                     out[l][w][nsp++] = ChainSpan{static_cast<short>(c.r0 + 8 * d * (a0 - base)),
-                                                 static_cast<short>(a1 - a0), static_cast<short>(c.kc), 0};
+                                                 static_cast<short>(a1 - a0), static_cast<short>(c.kc), top_flag};
                 }
                 base += c.noct;
             }
@@ -761,6 +880,36 @@ bool chain_build_spans(int C, ChainSpan (*spans)[kChainWarps][kChainSpans], int 
     }
     memcpy(spans, out, sizeof out);
     return true;
+}
+
+// Strips: cost model = tiles every CTA slot walks (a short last tile counts by its rows) + half a strip of tail.
+void chain_plan_strips(int C, int t_n, int S, int slots, bool no_carry, int* strip_tiles, int* sps, int* last_strip_tiles,
+                       int* last_rows) {
+    const int rows = chain_tile_rows(C), own_h = rows - 2 * kChainHalo, own_c = rows - kChainHalo;
+    auto plan = [&](int K, int* sps_o, int* lst_o, int* lrows_o) {
+        const int SR = own_h + (K - 1) * own_c;
+        const int n = (t_n + SR - 1) / SR, rem = t_n - (n - 1) * SR;
+        const int lst = rem <= own_h ? 1 : 1 + (rem - own_h + own_c - 1) / own_c;
+        int lrows = lst == 1 ? rem : rem - own_h - (lst - 2) * own_c;
+        if (lrows == (lst == 1 ? own_h : own_c)) lrows = 0;
+        *sps_o = n; *lst_o = lst; *lrows_o = lrows;
+        const double last_cost = lrows ? (lrows + (lst == 1 ? 2 : 1) * kChainHalo + 32.0) / rows : 1.0;
+        const double per_stream = (n - 1) * static_cast<double>(K) + (lst - 1) + (last_cost < 1.0 ? last_cost : 1.0);
+        return per_stream * S / slots + 0.5 * K;
+    };
+    int bestK = 1, a, b, c;
+    double best = plan(1, &a, &b, &c);
+    if (!no_carry)
+        for (int K = 2; K <= 24; ++K) {
+            const double v = plan(K, &a, &b, &c);
+            if (v < best - 1e-9) { best = v; bestK = K; }
+        }
+    plan(bestK, sps, last_strip_tiles, last_rows);
+    *strip_tiles = bestK;
+}
+
+size_t chain_carry_bytes(int C, int sm_count) {
+    return static_cast<size_t>(sm_count) * (chain_warps(C) == 8 ? 2 : 1) * 2 * 39 * C * 2;
 }
 
 // tm: [0] y load map, box (64, 128, 1); [1] out store map, box (64, 88, 1); [2] out store map, box (64, 128, 1);

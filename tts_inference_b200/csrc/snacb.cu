@@ -51,7 +51,9 @@ struct BlockW {
     bool chain[2];                      // the fused NoiseBlock + ResidualUnit chain covers this block ([0] bf16, [1] fp16)
     ChainSpan spans[3][kChainWarps][kChainSpans];
     ChainSpan spans_ws[3][kChainWarps][kChainSpans];   // warp-specialised chain kernel (kernels_chain_ws.cu): quads inside a block
-    ChainSpan spans_last[3][kChainWarps][kChainSpans]; // schedule of a short last tile owning spans_last_key rows (cached)
+    ChainSpan spans_carry[3][kChainWarps][kChainSpans]; // schedule of a carry-top tile (kernels_chain.cu)
+    bool spans_carry_ok = false;
+    ChainSpan spans_last[3][kChainWarps][kChainSpans]; // schedule of a short last tile of type / size spans_last_key (cached)
     int spans_last_key = 0;
     bool spans_last_ok = false;
     bool fold = false;                  // fp16 chain: the alpha-folded formulation is numerically safe for this block's
@@ -96,6 +98,7 @@ struct snacb_handle_s {
     size_t ws_buf_bytes = 0;
     void* ws_a0 = nullptr; size_t ws_a0_bytes = 0;
     void* ws_split = nullptr; size_t ws_split_bytes = 0;      // bf16x3 path: the split A operand of the running GEMM
+    void* chain_carry = nullptr; size_t chain_carry_bytes = 0; // chain kernel: per-CTA rows handed from tile to tile of a strip
     int32_t* ws_codes = nullptr; size_t ws_codes_elems = 0;
     int* tile_counter = nullptr;                              // dynamic tile scheduler of the chain kernel
     int32_t* st_tok = nullptr; size_t st_tok_elems = 0;       // decode_host staging
@@ -673,17 +676,33 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
             ca.map = smap; ca.rpf = T / F;
             const bool ws = h->chain_ws && chain_ws_supported(b.Cout, hk) && !plan;     // the experiment knows no sessions
             memcpy(ca.spans, ws ? b.spans_ws : b.spans, sizeof ca.spans);
-            const char* nst = getenv("SNACB_NO_SHORT_TILE");      // A/B switch (tests): the last tile runs as a full tile
-            if (!ws && !(nst && nst[0] == '1')) {
-                // the row range is rarely a whole number of tiles: its last tile runs a shorter schedule (kernels_chain.cu)
-                const int own = chain_tile_rows(b.Cout) - 2 * kChainHalo;
-                const int last = (ca.t_n > 0 ? ca.t_n : T) % own;
-                if (last > 0) {
-                    if (b.spans_last_key != last) {
-                        b.spans_last_ok = chain_build_spans(b.Cout, b.spans_last, last);
-                        b.spans_last_key = last;
+            ca.strip_tiles = 1; ca.sps = 1; ca.last_strip_tiles = 1;
+            if (!ws) {
+                // strips of tiles walked in order by one CTA (carry-top tiles, kernels_chain.cu); A/B switches for the tests:
+                // SNACB_NO_CARRY=1: one halo-top tile per strip; SNACB_NO_SHORT_TILE=1: the last tile runs as a full tile
+                const char* nst = getenv("SNACB_NO_SHORT_TILE");
+                const char* ncy = getenv("SNACB_NO_CARRY");
+                const int slots = h->sm_count * (chain_warps(b.Cout) == 8 ? 2 : 1);
+                const int t_n = ca.t_n > 0 ? ca.t_n : T;
+                bool no_carry = (ncy && ncy[0] == '1');
+                if (!no_carry && !b.spans_carry_ok) no_carry = true;
+                if (!no_carry) {
+                    const size_t need = chain_carry_bytes(256, h->sm_count);   // the widest block's, once
+                    if (grow(h, &h->chain_carry, &h->chain_carry_bytes, need)) no_carry = true;
+                }
+                int lrows = 0;
+                chain_plan_strips(b.Cout, t_n, S, slots, no_carry, &ca.strip_tiles, &ca.sps, &ca.last_strip_tiles, &lrows);
+                ca.carry = h->chain_carry;
+                memcpy(ca.spans_carry, b.spans_carry, sizeof ca.spans_carry);
+                if (lrows > 0 && !(nst && nst[0] == '1')) {
+                    const bool last_carry = ca.last_strip_tiles > 1;
+                    const int own_end = (last_carry ? 0 : kChainHalo) + lrows;
+                    const int key = own_end | (last_carry ? 1 << 16 : 0);
+                    if (b.spans_last_key != key) {
+                        b.spans_last_ok = chain_build_spans(b.Cout, b.spans_last, own_end, last_carry);
+                        b.spans_last_key = key;
                     }
-                    if (b.spans_last_ok) { memcpy(ca.spans_last, b.spans_last, sizeof ca.spans_last); ca.last_rows = last; }
+                    if (b.spans_last_ok) { memcpy(ca.spans_last, b.spans_last, sizeof ca.spans_last); ca.last_rows = lrows; }
                 }
             }
             ca.tile_counter = h->tile_counter;
@@ -925,7 +944,10 @@ int snacb_create(snacb_handle* out, const snacb_weights* w, int device) {
             RC(upload_f32(h, &b.bias_cum, bc));
             b.chain[0] = chain_supported(b.Cout, 0);
             b.chain[1] = chain_supported(b.Cout, 1);
-            if (b.chain[0] || b.chain[1]) chain_build_spans(b.Cout, b.spans);
+            if (b.chain[0] || b.chain[1]) {
+                chain_build_spans(b.Cout, b.spans);
+                b.spans_carry_ok = chain_build_spans(b.Cout, b.spans_carry, 0, true);
+            }
             if (chain_ws_supported(b.Cout, 1)) chain_ws_build_spans(b.Cout, b.spans_ws);
             // fp16 chain: the alpha-folded formulation (kernels_chain.cu) divides by the Snake alphas when it packs its
             // parameters; it is used only where that is numerically safe for THIS checkpoint, else the general variant runs
@@ -989,6 +1011,7 @@ void snacb_destroy(snacb_handle h) {
     for (int i = 0; i < 3; ++i) if (h->ws_buf[i]) cudaFree(h->ws_buf[i]);
     if (h->ws_a0) cudaFree(h->ws_a0);
     if (h->ws_split) cudaFree(h->ws_split);
+    if (h->chain_carry) cudaFree(h->chain_carry);
     if (h->ws_codes) cudaFree(h->ws_codes);
     if (h->st_tok) cudaFree(h->st_tok);
     if (h->st_pcm) cudaFree(h->st_pcm);
@@ -1702,18 +1725,26 @@ int snacb_debug_chain_spans(int C, int16_t* out, int cap) {
     return chain_tile_rows(C) | (chain_warps(C) << 16);
 }
 
-int snacb_debug_chain_spans_last(int C, int own_rows, int16_t* out, int cap) {
-    if (!out || !chain_supported(C, 1) || cap < 3 * kChainWarps * kChainSpans * 3) return SNACB_ERR_ARG;
-    if (own_rows <= 0 || own_rows >= chain_tile_rows(C) - 2 * kChainHalo) return SNACB_ERR_ARG;
+int snacb_debug_chain_spans_ex(int C, int own_end, int carry_top, int16_t* out, int cap) {
+    if (!out || !chain_supported(C, 1) || cap < 3 * kChainWarps * kChainSpans * 4) return SNACB_ERR_ARG;
+    if (own_end < 0 || own_end > chain_tile_rows(C) - kChainHalo) return SNACB_ERR_ARG;
     ChainSpan sp[3][kChainWarps][kChainSpans];
-    if (!chain_build_spans(C, sp, own_rows)) return 0;
+    if (!chain_build_spans(C, sp, own_end, carry_top != 0)) return 0;
     for (int l = 0; l < 3; ++l)
         for (int w = 0; w < kChainWarps; ++w)
             for (int k = 0; k < kChainSpans; ++k) {
-                int16_t* o = out + ((l * kChainWarps + w) * kChainSpans + k) * 3;
-                o[0] = sp[l][w][k].r_first; o[1] = sp[l][w][k].n_oct; o[2] = sp[l][w][k].kc;
+                int16_t* o = out + ((l * kChainWarps + w) * kChainSpans + k) * 4;
+                o[0] = sp[l][w][k].r_first; o[1] = sp[l][w][k].n_oct; o[2] = sp[l][w][k].kc; o[3] = sp[l][w][k].pad;
             }
     return chain_tile_rows(C) | (chain_warps(C) << 16);
+}
+
+int snacb_debug_chain_plan(int C, int t_n, int S, int slots, int32_t* out4) {
+    if (!out4 || !chain_supported(C, 1) || t_n <= 0 || S <= 0 || slots <= 0) return SNACB_ERR_ARG;
+    int k, sps, lst, lrows;
+    chain_plan_strips(C, t_n, S, slots, false, &k, &sps, &lst, &lrows);
+    out4[0] = k; out4[1] = sps; out4[2] = lst; out4[3] = lrows;
+    return SNACB_OK;
 }
 
 int snacb_experiments_built(void) { return chain_ws_built() ? 1 : 0; }
