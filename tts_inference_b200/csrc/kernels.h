@@ -100,6 +100,7 @@ bool chain_build_spans(int C, ChainSpan (*spans)[kChainWarps][kChainSpans], int 
 void chain_plan_strips(int C, int t_n, int S, int slots, bool no_carry, int* strip_tiles, int* sps, int* last_strip_tiles,
                        int* last_rows);
 size_t chain_carry_bytes(int C, int sm_count);   // scratch for ChainArgs::carry
+size_t chain_carry_bytes_max(int sm_count);      // the largest over the supported widths
 // tm[7]: y load map box (64,128,1); out store maps box (64,128-kChainHalo,1) and (64,128,1); noise 1x1, res d=1,
 // d=3, d=9 weight maps box (64, C); all 128B-swizzled.  fold = 1: the alpha-folded fp16 formulation (the three res
 // weight maps then point at the copies with 1 / alpha2 folded into their K columns); see chain_fold_safe in snacb.cu

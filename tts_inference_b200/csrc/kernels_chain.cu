@@ -75,10 +75,14 @@ struct ChainCfg {
     static constexpr int kPlane = NB * 16384;               // one chunk plane of the tile [NB][128 rows][128 B]
     static constexpr int kXBytes = kCH * kPlane;
     static constexpr bool kWRes = (C == 64);                // all four 1x1 weights resident
+    static constexpr bool kWSingle = (C == 128);            // ONE layer resident: the next layer's weights are fetched into
+                                                            // the same buffer as soon as this layer's MMAs have retired and
+                                                            // land during the epilogue + prologue that follow (two CTAs per SM:
+                                                            // 32 KB instead of 64 KB of weights per CTA)
     static constexpr bool kWChunked = (C == 256);           // weights streamed one 64-channel K chunk at a time
     static constexpr int kWLayer = C * C * 2;               // one layer's weights [kCH][C rows][128 B]
     static constexpr int kWChunk = C * 128;                 // one K chunk of them
-    static constexpr int kWBytes = kWRes ? 4 * kWLayer : (kWChunked ? 2 * kWChunk : 2 * kWLayer);
+    static constexpr int kWBytes = kWRes ? 4 * kWLayer : (kWChunked ? 2 * kWChunk : (kWSingle ? kWLayer : 2 * kWLayer));
     // prologue parameters per layer and channel pair:
     //   FOLD        8 words : half2 alpha2 * dw bias, 7 x half2 dw tap * alpha2 / alpha1
     //   fp16        12 words: half2 dw bias, 7 x half2 dw tap, float2 alpha2, float2 1 / (alpha2 + 1e-9)
@@ -92,7 +96,7 @@ struct ChainCfg {
     static constexpr int kOffPrm = kOffW + kWBytes;
     static constexpr int kOffEpi = kOffPrm + kPrmBytes;
     static constexpr int kOffNz = kOffEpi + kEpiBytes;
-    static constexpr int kSpanWarps = (C == 64) ? 8 : kChainWarps;          // warps of the launch configuration (kNW*)
+    static constexpr int kSpanWarps = (C == 256) ? kChainWarps : 8;         // warps of the launch configuration (kNW*)
     static constexpr int kSpanElems = 3 * kSpanWarps * kChainSpans;
     static constexpr int kSpanBytes = 3 * kSpanElems * 4;   // the launch's span tables (halo-top, carry-top, short last tile), packed
     static constexpr int kROutC = kRows - kHalo;            // rows a carry-top tile owns (no halo above them)
@@ -365,8 +369,8 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
 
     // weight staging: resident (C = 64) or two rotating buffers, layer l of a tile uses buffer l & 1
     auto load_w = [&](int l, int buf) {       // thread 0
-        uint8_t* dst = sW + (Cfg::kWRes ? l : buf) * Cfg::kWLayer;
-        uint64_t* bar = &w_bar[Cfg::kWRes ? 0 : buf];
+        uint8_t* dst = sW + (Cfg::kWRes ? l : (Cfg::kWSingle ? 0 : buf)) * Cfg::kWLayer;
+        uint64_t* bar = &w_bar[(Cfg::kWRes || Cfg::kWSingle) ? 0 : buf];
         if (!Cfg::kWRes) mbar_expect_tx(bar, Cfg::kWLayer);
 #pragma unroll
         for (int kc = 0; kc < CH; ++kc) tma_load_2d_hint(dst + kc * (C * 128), wmaps[l], kc * 64, 0, bar, kL2EvictLast);
@@ -398,6 +402,8 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
         } else if (Cfg::kWChunked) {
             load_wc(0);
             load_wc(1);
+        } else if (Cfg::kWSingle) {
+            load_w(0, 0);
         } else {
             load_w(0, 0);
             load_w(1, 1);
@@ -452,9 +458,10 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
         }
         const int buf = l & 1;
         if (Cfg::kWRes) { if (n == 0 && l == 0) mbar_wait(&w_bar[0], 0); }
+        else if (Cfg::kWSingle) mbar_wait(&w_bar[0], (4 * n + l) & 1);       // one load per layer into the one buffer
         else mbar_wait(&w_bar[buf], (2 * n + (l >> 1)) & 1);
         tc_fence_after();
-        const uint32_t w_addr = smem_u32(sW + (Cfg::kWRes ? l : buf) * Cfg::kWLayer);
+        const uint32_t w_addr = smem_u32(sW + (Cfg::kWRes ? l : (Cfg::kWSingle ? 0 : buf)) * Cfg::kWLayer);
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
             if (b < nb_live) {                             // short last tile: blocks past its right halo carry no MMAs
@@ -469,9 +476,14 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
             mma_commit(&mma_bar[b]);                       // every block's barrier completes a phase per layer
         }
     };
-    // after ALL of layer l's MMAs completed: its weight buffer is free -> prefetch the layer two ahead (thread 0)
+    // after ALL of layer l's MMAs completed: its weight buffer is free -> prefetch the layer two ahead (thread 0);
+    // single buffer: the NEXT layer, which lands while the epilogue and the next prologue run
     auto prefetch_w = [&](int l, bool has_next) {
         if (Cfg::kWRes || Cfg::kWChunked) return;
+        if (Cfg::kWSingle) {
+            if (l + 1 < 4 || has_next) load_w((l + 1) & 3, 0);
+            return;
+        }
         const int l2 = (l + 2) & 3;
         if (l + 2 < 4 || has_next) load_w(l2, l & 1);
     };
@@ -814,10 +826,11 @@ cudaError_t launch_chain_t(const ChainArgs& a, const CUtensorMap* tm, int sm_cou
 }
 
 // launch configurations: C = 64: 512-row tiles, 8 warps, two CTAs per SM (one CTA's barrier / MMA / TMA waits are
-// the other's issue slots); C = 128: 512-row tiles, 16 warps, one CTA per SM (shared memory bound)
+// the other's issue slots); C = 128: 256-row tiles, 8 warps, two CTAs per SM as well (64 KB tile copy + ONE layer of
+// weights per CTA; with carry-top tiles a 256-row tile owns 216 rows = 84 %, what a 512-row tile with two halos owned);
 // C = 256 (fp16 only: the fp32-math parameters of the bf16 variant do not fit): 256-row tiles (TMEM: 2 x 256 columns),
 // 16 warps, weights streamed per K chunk
-constexpr int kNB64 = 4, kNW64 = 8, kNB128 = 4, kNW128 = 16, kNB256 = 2, kNW256 = 16;
+constexpr int kNB64 = 4, kNW64 = 8, kNB128 = 2, kNW128 = 8, kNB256 = 2, kNW256 = 16;
 
 }  // namespace
 
@@ -910,6 +923,11 @@ void chain_plan_strips(int C, int t_n, int S, int slots, bool no_carry, int* str
 
 size_t chain_carry_bytes(int C, int sm_count) {
     return static_cast<size_t>(sm_count) * (chain_warps(C) == 8 ? 2 : 1) * 2 * 39 * C * 2;
+}
+size_t chain_carry_bytes_max(int sm_count) {
+    size_t m = 0;
+    for (int C : {64, 128, 256}) { const size_t b = chain_carry_bytes(C, sm_count); if (b > m) m = b; }
+    return m;
 }
 
 // tm: [0] y load map, box (64, 128, 1); [1] out store map, box (64, 88, 1); [2] out store map, box (64, 128, 1);

@@ -687,7 +687,7 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
                 bool no_carry = (ncy && ncy[0] == '1');
                 if (!no_carry && !b.spans_carry_ok) no_carry = true;
                 if (!no_carry) {
-                    const size_t need = chain_carry_bytes(256, h->sm_count);   // the widest block's, once
+                    const size_t need = chain_carry_bytes_max(h->sm_count);     // the largest over the blocks, once
                     if (grow(h, &h->chain_carry, &h->chain_carry_bytes, need)) no_carry = true;
                 }
                 int lrows = 0;
