@@ -1,7 +1,8 @@
 #!/usr/bin/env python
-"""Round-2 profile summaries from the raw ncu files of the final build (gpurun_out/*r02f*) -> profiles/r02_*.
-    python tools/make_profiles_r02.py          (needs `ncu` on PATH to read the .ncu-rep; no GPU)"""
-import collections, csv, gzip, json, os, re, shutil, subprocess
+"""Round-2 profile summaries from the raw ncu files of the final build (gpurun_out/*<tag>*) -> profiles/r02_*.
+    python tools/make_profiles_r02.py [tag]    (default r3b; needs `ncu` on PATH to read the .ncu-rep; no GPU)"""
+import collections, csv, gzip, json, os, re, shutil, subprocess, sys
+TAG = sys.argv[1] if len(sys.argv) > 1 else "r3b"
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
 MULT = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}
@@ -43,7 +44,7 @@ def summarise(rep, title, traffic=None):
 
 def main():
     # ---- launch list
-    src = os.path.join(G, "launches_r02f.csv")
+    src = os.path.join(G, f"launches_{TAG}.csv")
     rows = list(csv.reader(l for l in open(src) if l.startswith('"')))
     hdr = rows[0]
     ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
@@ -64,7 +65,7 @@ def main():
         shutil.copyfileobj(f, g)
     # ---- full captures
     traffic = {}
-    txt = summarise(os.path.join(G, "prof_chain_r02f.ncu-rep"),
+    txt = summarise(os.path.join(G, f"prof_chain_{TAG}.ncu-rep"),
                     "ncu --set full --clock-control none --import-source on, the three k_chain launches of one decode of 1024 four-frame windows\n"
                     "(full windows, SNACB_NO_TRIM=1, fp16 operands, round-2 final build): python tests/gpu_one.py 1024 fp16 1\n"
                     "(per-launch times under ncu are cold-cache and serialised; shares, not absolutes)", traffic)
@@ -72,7 +73,7 @@ def main():
     json.dump({"chain": {"1024": sum(traffic.values()) / len(traffic)}, "_per_kernel_bytes": traffic,
                "_what": "dram__bytes_read.sum + dram__bytes_write.sum per launch (mean over the three k_chain launches of a step), "
                         "ncu --set full, B = 1024 full windows, round-2 final build"}, open(os.path.join(P, "ncu_traffic.json"), "w"), indent=1)
-    txt = summarise(os.path.join(G, "prof_mem_r02f.ncu-rep"),
+    txt = summarise(os.path.join(G, f"prof_mem_{TAG}.ncu-rep"),
                     "ncu --set full --clock-control none, the kernels outside the chain in one decode of 1024 four-frame windows (full windows, fp16,\n"
                     "round-2 final build): k_vq_stem (token unpack fused), stem / ConvTranspose / NoiseBlock GEMMs (k_gemm_tc), block-0 ResidualUnits\n"
                     "(k_resunit2), k_convt_ph (block 2), k_convt_res (block 3), k_tail_bulk.  Achieved HBM bandwidth per kernel against the measured 6.55 TB/s.")
