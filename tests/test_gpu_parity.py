@@ -129,6 +129,31 @@ def test_tensorcore_stage_taps(decoder, oracle_model):
         assert snr_db(r, taps[k]) >= 45.0, (k, snr_db(r, taps[k]))
 
 
+@pytest.mark.parametrize("prec", ["fp16", "bf16"])
+@pytest.mark.parametrize("B,F_", [(3, 4), (2, 5), (1, 13)])
+def test_resident_weight_convtranspose_against_generic_gemm(monkeypatch, B, F_, prec):
+    """Blocks 2 / 3 run their ConvTranspose1d through k_convt_ph (TMA-store epilogue; ragged last row group by per-row
+    stores) / k_convt_res; SNACB_NO_CONVT_RES=1 sends them through the generic 2-tap GEMM kernel.  Same operands, fp32
+    accumulation in a different order: the ConvTranspose outputs agree to rounding, every row of every phase."""
+    sd = synth.make_state_dict(0)
+    tokens = _cuda(synth.make_tokens(B, F_, seed=77 + F_))
+    nz = [_cuda(n) for n in synth.make_noises(B, 4 * F_, seed=5)]
+    dec_a = SnacDecoder(sd, device=0)
+    monkeypatch.setenv("SNACB_NO_CONVT_RES", "1")
+    dec_b = SnacDecoder(sd, device=0)
+    monkeypatch.delenv("SNACB_NO_CONVT_RES")
+    dec_a.decode(tokens, raw_ids=True, noise=nz, precision=prec, keep_taps=True)
+    ta = dec_a.taps()
+    dec_b.decode(tokens, raw_ids=True, noise=nz, precision=prec, keep_taps=True)
+    tb = dec_b.taps()
+    for k in ("b2.convt", "b3.convt"):
+        a, b = ta[k].astype(np.float64), tb[k].astype(np.float64)
+        assert a.shape == b.shape and np.isfinite(a).all(), k
+        assert snr_db(b, a) >= (60.0 if prec == "fp16" else 45.0), (k, snr_db(b, a))
+        if k == "b2.convt":        # same input to both kernels here (block 3's differs by block 2's rounding noise)
+            assert np.abs(a - b).max() <= 2.0 ** (-9 if prec == "fp16" else -6) * max(1.0, np.abs(b).max()), k
+
+
 @pytest.mark.parametrize("B,F_", [(2, 4), (3, 1), (1, 7)])
 def test_fused_chain_block_outputs(decoder, oracle_model, B, F_):
     """The fused NoiseBlock + ResidualUnit chain (blocks 2 and 3): block outputs against the oracle's, and the

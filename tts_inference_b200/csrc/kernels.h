@@ -84,8 +84,9 @@ cudaError_t launch_convt_res(int half_fp16, const GemmArgs& a, const CUtensorMap
                              const CUtensorMap& tmO, int sm_count, cudaStream_t st);   // tmO: output box (64, 128*s, 1)
 
 bool convt_ph_supported(int Cin, int Cout, int s);   // block 2: one output phase's weights resident per CTA group
-cudaError_t launch_convt_ph(int half_fp16, const GemmArgs& a, const CUtensorMap& tmA, const CUtensorMap& tmW, int sm_count,
-                            cudaStream_t st);        // tmA box (64, 136, 1); tmW box (64, Cout)
+cudaError_t launch_convt_ph(int half_fp16, const GemmArgs& a, const CUtensorMap& tmA, const CUtensorMap& tmW,
+                            const CUtensorMap& tmO, int sm_count, cudaStream_t st);
+                            // tmA box (64, 136, 1); tmW box (64, Cout); tmO: output as [slot][Tin][s*Cout], box (64, 32, 1)
 
 // ---- kernels_chain.cu  (NoiseBlock + 3 ResidualUnits fused, residual stream in TMEM)
 bool chain_supported(int C, int half_fp16);

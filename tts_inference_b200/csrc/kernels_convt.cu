@@ -211,30 +211,33 @@ struct ConvtPhCfg {
     static constexpr int kCH = CIN / 64;
     static constexpr int kBoxRows = 136;
     static constexpr int kAChunk = kBoxRows * 128;
-    static constexpr int kRing = 5;                      // A chunk stages (more than one tile deep)
+    static constexpr int kRing = 4;                      // A chunk stages: one tile deep (5 measured the same)
     static constexpr int kWChunk = COUT * 128;           // [COUT rows][64 k]
     static constexpr int kWBytes = 2 * kCH * kWChunk;    // taps x chunks of this phase
     static constexpr int kOffA = 0;
     static constexpr int kOffW = kRing * kAChunk;
-    static constexpr int kOffBias = kOffW + kWBytes;
+    static constexpr int kEpiWarps = 4;                  // one per TMEM lane quadrant
+    static constexpr int kStage = 32 * 128;              // a warp's staging tile: 32 rows x 64 channels, 128B-swizzled
+    static constexpr int kOffStage = kOffW + kWBytes;
+    static constexpr int kOffBias = kOffStage + kEpiWarps * kStage;
     static constexpr int kOffBar = kOffBias + COUT * 4;
     static constexpr int kSmem = kOffBar + 128 + 1024;
     static constexpr int kTmemCols = 2 * COUT;
-    static constexpr int kEpiWarps = 8;
     static constexpr int kThreads = 64 + kEpiWarps * 32;
-    static_assert(COUT == 128 && (kOffW % 1024) == 0 && kSmem <= 232448, "configuration");
+    static_assert(COUT == 128 && (kOffW % 1024) == 0 && (kOffStage % 1024) == 0 && kSmem <= 232448, "configuration");
 };
 }  // namespace
 
 template <int CIN, int COUT, int S, typename HT>
 __global__ void __launch_bounds__((ConvtPhCfg<CIN, COUT, S>::kThreads), 1)
-k_convt_ph(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const GemmArgs a,
-           const int num_tiles) {
+k_convt_ph(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+           const __grid_constant__ CUtensorMap tmO, const GemmArgs a, const int num_tiles) {
     using Cfg = ConvtPhCfg<CIN, COUT, S>;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* sA = smem + Cfg::kOffA;
     uint8_t* sW = smem + Cfg::kOffW;
+    uint8_t* sStage = smem + Cfg::kOffStage;
     float* sBias = reinterpret_cast<float*>(smem + Cfg::kOffBias);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kOffBar);
     uint64_t* full = bars;                    // [kRing]
@@ -254,6 +257,7 @@ k_convt_ph(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
     if (threadIdx.x == 0) {
         prefetch_tmap(&tmA);
         prefetch_tmap(&tmW);
+        prefetch_tmap(&tmO);
         for (int i = 0; i < Cfg::kRing; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], Cfg::kEpiWarps); }
         mbar_init(wbar, 1);
@@ -316,36 +320,71 @@ k_convt_ph(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
             if (++as == 2) { as = 0; aphase ^= 1u; }
         }
     } else {
-        // ------------------------------------------------------------------ epilogue: 2 warps per TMEM lane quadrant
-        const int q = warp & 3, half = (warp - 2) >> 2;      // half: which 64 of the phase's 128 channels
+        // ------------------------------------------------------------------ epilogue: one warp per TMEM lane quadrant.
+        // A warp drains its 32 rows x 128 channels in two 64-channel halves; each half is packed into the warp's own
+        // 4 KB staging tile (128B-swizzled: conflict-free 16-byte stores, lane = row) and leaves with ONE TMA store
+        // (box 64 channels x 32 input rows of phase p; the output seen as [slot][Tin][s * Cout]).  Before: every lane
+        // stored its row's 128 bytes itself -- 32 cache lines per store instruction, the L1-wavefront-bound epilogue that
+        // held the tensor pipe at 54 %.  A 32-row group cut by the end of the row range keeps the per-row stores.
+        const int q = warp & 3;
+        uint8_t* stg = sStage + (warp - 2) * Cfg::kStage;
         HT* out = static_cast<HT*>(a.out);
         int as = 0; uint32_t aphase = 0;
         for (int tile = gi; tile < num_tiles; tile += gs) {
-            const int s = tile / tiles_t, so = sm_off(a.map, s, a.rpf), m = t_lo + so + (tile % tiles_t) * 128 + q * 32 + lane;
+            const int s = tile / tiles_t, so = sm_off(a.map, s, a.rpf), mw = t_lo + so + (tile % tiles_t) * 128 + q * 32;
             const int sl = sm_slot(a.map, s);
-            const bool valid = (m < a.Tin) && (m < t_lo + so + t_n);
+            const int m = mw + lane;
+            const int m_end = min(a.Tin, t_lo + so + t_n);
+            const bool whole = mw + 32 <= m_end;                 // warp-uniform
             mbar_wait(&tfull[as], aphase);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * COUT + half * 64;
-            uint32_t r0[32], r1[32];
-            tmem_ld32(taddr, r0);
-            tmem_ld32(taddr + 32, r1);
-            tmem_ld_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[as]);
-            if (valid) {
-                HT* dst = out + (static_cast<size_t>(sl) * a.Tin * S + static_cast<size_t>(m) * S + p) * COUT + half * 64;
-                float v[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r0[j]) + sBias[half * 64 + j];
-                store32(dst, v);
+            for (int half = 0; half < 2; ++half) {
+                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * COUT + half * 64;
+                uint32_t r0[32], r1[32];
+                tmem_ld32(taddr, r0);
+                tmem_ld32(taddr + 32, r1);
+                tmem_ld_wait();
+                if (half == 1) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty[as]);
+                }
+                if (whole) {
+                    if (lane == 0) bulk_wait_group_read<0>();    // the previous store has read the staging tile
+                    __syncwarp();
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r1[j]) + sBias[half * 64 + 32 + j];
-                store32(dst + 32, v);
+                    for (int c = 0; c < 8; ++c) {
+                        const uint32_t* r = (c < 4) ? r0 : r1;
+                        uint32_t o[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int col = (c & 3) * 8 + 2 * e, ch = half * 64 + c * 8 + 2 * e;
+                            o[e] = pack2(__uint_as_float(r[col]) + sBias[ch], __uint_as_float(r[col + 1]) + sBias[ch + 1],
+                                         static_cast<const HT*>(nullptr));
+                        }
+                        *reinterpret_cast<uint4*>(stg + lane * 128 + ((c ^ (lane & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_3d(&tmO, stg, p * COUT + half * 64, mw, sl);
+                        bulk_commit_group();
+                    }
+                } else if (m < m_end) {
+                    HT* dst = out + (static_cast<size_t>(sl) * a.Tin * S + static_cast<size_t>(m) * S + p) * COUT + half * 64;
+                    float v[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r0[j]) + sBias[half * 64 + j];
+                    store32(dst, v);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r1[j]) + sBias[half * 64 + 32 + j];
+                    store32(dst + 32, v);
+                }
             }
             if (++as == 2) { as = 0; aphase ^= 1u; }
         }
+        if (lane == 0) bulk_wait_group<0>();
     }
     tc_fence_before();
     __syncthreads();
@@ -375,7 +414,8 @@ cudaError_t launch_t(const GemmArgs& a, const CUtensorMap& tmA, const CUtensorMa
 
 namespace {
 template <int CIN, int COUT, int S, typename HT>
-cudaError_t launch_ph_t(const GemmArgs& a, const CUtensorMap& tmA, const CUtensorMap& tmW, int sm_count, cudaStream_t st) {
+cudaError_t launch_ph_t(const GemmArgs& a, const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmO, int sm_count,
+                        cudaStream_t st) {
     using Cfg = ConvtPhCfg<CIN, COUT, S>;
     static PerDeviceOnce once;
     int dev_;
@@ -390,18 +430,19 @@ cudaError_t launch_ph_t(const GemmArgs& a, const CUtensorMap& tmA, const CUtenso
     int per = sm_count / S;                           // CTAs per phase group
     if (per > tiles) per = tiles;
     if (per < 1) per = 1;
-    k_convt_ph<CIN, COUT, S, HT><<<per * S, Cfg::kThreads, Cfg::kSmem, st>>>(tmA, tmW, a, tiles);
+    k_convt_ph<CIN, COUT, S, HT><<<per * S, Cfg::kThreads, Cfg::kSmem, st>>>(tmA, tmW, tmO, a, tiles);
     return cudaGetLastError();
 }
 }  // namespace
 
 bool convt_ph_supported(int Cin, int Cout, int s) { return Cin == 256 && Cout == 128 && s == 4; }
-// tmA: activation map box (64, 136, 1); tmW: packed weights [s*Cout][2*Cin], box (64, Cout)
-cudaError_t launch_convt_ph(int half_fp16, const GemmArgs& a, const CUtensorMap& tmA, const CUtensorMap& tmW, int sm_count,
-                            cudaStream_t st) {
+// tmA: activation map box (64, 136, 1); tmW: packed weights [s*Cout][2*Cin], box (64, Cout); tmO: the output seen as
+// [slot][Tin][s*Cout] (one row = the s phases of an input row), box (64, 32, 1); all 128B-swizzled
+cudaError_t launch_convt_ph(int half_fp16, const GemmArgs& a, const CUtensorMap& tmA, const CUtensorMap& tmW,
+                            const CUtensorMap& tmO, int sm_count, cudaStream_t st) {
     if (!convt_ph_supported(a.K, a.Cout, a.up)) return cudaErrorInvalidValue;
-    return half_fp16 ? launch_ph_t<256, 128, 4, __half>(a, tmA, tmW, sm_count, st)
-                     : launch_ph_t<256, 128, 4, __nv_bfloat16>(a, tmA, tmW, sm_count, st);
+    return half_fp16 ? launch_ph_t<256, 128, 4, __half>(a, tmA, tmW, tmO, sm_count, st)
+                     : launch_ph_t<256, 128, 4, __nv_bfloat16>(a, tmA, tmW, tmO, sm_count, st);
 }
 
 bool convt_res_supported(int Cin, int Cout, int s) { return Cin == 128 && Cout == 64 && s == 2; }

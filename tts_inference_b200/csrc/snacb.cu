@@ -636,16 +636,18 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
                 h->launches++;
             } else if (!f32 && !x3 && !h->no_convt_res && convt_ph_supported(b.Cin, b.Cout, b.s) && Tin >= 128) {
                 // one output phase's weights resident per CTA group, one activation load per tile
-                CUtensorMap ma;
+                CUtensorMap ma, mo;
                 const CUtensorMap* mw;
                 rc = act_map(h, &ma, cur, b.Cin, Tin, S_buf, convt_res_box_rows(), 1, hk);
                 if (rc) return rc;
                 rc = weight_map(h, &mw, b.ct_h[hk], b.s * b.Cout, 2 * b.Cin, b.Cout, hk);
                 if (rc) return rc;
+                rc = act_map(h, &mo, oth, b.s * b.Cout, Tin, S_buf, 32, 1, hk);     // a row = the s phases of an input row
+                if (rc) return rc;
                 a.seed = seed; a.stream_offset = stream_offset; a.stream_keys = stream_keys; a.Tbox = 128; a.Wbox = 1;
                 a.map = smap; a.rpf = Tin / F;
                 prof_begin(h, nm, st);
-                cudaError_t le = launch_convt_ph(hk, a, ma, *mw, h->sm_count, st);
+                cudaError_t le = launch_convt_ph(hk, a, ma, *mw, mo, h->sm_count, st);
                 prof_end(h, st);
                 CK(h, le);
                 h->launches++;
