@@ -67,6 +67,27 @@ __device__ __forceinline__ uint32_t as_u32(__half2 v) { return *reinterpret_cast
 
 constexpr int kHalo = kChainHalo;            // 40 >= 39, multiple of 8
 
+// Packed fp32 pairs (sm_100 FFMA2 / FMUL2: one issue slot and one FMA-pipe slot for two IEEE fp32 operations, the same
+// results as two FFMA): the TMEM-drain epilogues run their scale / bias and sin^2 accumulate on column pairs
+__device__ __forceinline__ unsigned long long f2_pack(float x, float y) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y));
+    return r;
+}
+__device__ __forceinline__ void f2_unpack(unsigned long long v, float& x, float& y) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ unsigned long long fmul2(unsigned long long a, unsigned long long b) {
+    unsigned long long d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
 template <int C, int NB, bool HALF, bool FOLD>
 struct ChainCfg {
     static constexpr int kCH = C / 64;                      // 64-channel K chunks
@@ -257,6 +278,24 @@ __device__ __forceinline__ void span_bf16(uint8_t* plane, int r_oct, const int n
 }
 
 enum { EPI_C_NOISE = 0, EPI_C_MID = 1, EPI_C_FINAL = 2 };
+
+// x + sin^2 x on a half2 without the XU pipe: r = x / pi - rint(x / pi) by the magic-number trick, sin^2(pi r) as a
+// degree-4 odd-free minimax polynomial in r^2 (|r| <= 1/2); 9 FMA-pipe instructions with immediate operands
+__device__ __forceinline__ __half2 snake_h2_poly(__half2 xh) {
+    const __half2 kInvPi = __float2half2_rn(0.318309886f), kMagic = __float2half2_rn(1536.f);
+    const __half2 m = __hfma2(xh, kInvPi, kMagic);
+    const __half2 n = __hsub2(m, kMagic);
+    const __half2 r = __hfma2(xh, kInvPi, __hneg2(n));
+    const __half2 u = __hmin2(__hmul2(r, r), __float2half2_rn(0.25f));      // |x| >= 1608 (no phase left in fp16): stay finite
+    __half2 p = __hfma2(__float2half2_rn(-22.99092533f), u, __float2half2_rn(41.29496355f));
+    p = __hfma2(p, u, __float2half2_rn(-32.35387252f));
+    p = __hfma2(p, u, __float2half2_rn(9.86667475f));
+    return __hfma2(p, u, xh);
+}
+#ifndef SNACB_EPI_POLY_MASK
+#define SNACB_EPI_POLY_MASK 0x8888u
+#endif
+constexpr unsigned kEpiPolyMask = SNACB_EPI_POLY_MASK;   // bit i: column pair i of a 32-column piece takes the polynomial
 
 }  // namespace
 
@@ -533,20 +572,43 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
                 if (MODE == EPI_C_NOISE) {
                     const uint32_t* yw = reinterpret_cast<const uint32_t*>(yv);
                     const float2 y0 = unpack2c(yw[j / 2], tag), y1 = unpack2c(yw[j / 2 + 1], tag);
-                    v0 = fmaf(nz, v0, y0.x); v1 = fmaf(nz, v1, y0.y); v2 = fmaf(nz, v2, y1.x); v3 = fmaf(nz, v3, y1.y);
+                    const unsigned long long nz2 = f2_pack(nz, nz);
+                    f2_unpack(ffma2(nz2, f2_pack(v0, v1), f2_pack(y0.x, y0.y)), v0, v1);
+                    f2_unpack(ffma2(nz2, f2_pack(v2, v3), f2_pack(y1.x, y1.y)), v2, v3);
                     raw[j] = __float_as_uint(v0); raw[j + 1] = __float_as_uint(v1);
                     raw[j + 2] = __float_as_uint(v2); raw[j + 3] = __float_as_uint(v3);
                 }
                 const float4 al = *reinterpret_cast<const float4*>(va + cg * 32 + j);
                 if (kFoldHere) {
-                    // x'' = alpha1 * (x + b);  S1'' = x'' + sin^2 x''
-                    if (MODE == EPI_C_NOISE) { v0 *= al.x; v1 *= al.y; v2 *= al.z; v3 *= al.w; }
+                    // x'' = alpha1 * (x + b);  S1'' = x'' + sin^2 x''   (column pairs: FFMA2, bit-identical to two FFMA)
+                    unsigned long long p01 = f2_pack(v0, v1), p23 = f2_pack(v2, v3);
+                    if (MODE == EPI_C_NOISE) { p01 = fmul2(p01, f2_pack(al.x, al.y)); p23 = fmul2(p23, f2_pack(al.z, al.w)); }
                     else {
                         const float4 b = *reinterpret_cast<const float4*>(vb + cg * 32 + j);
-                        v0 = fmaf(v0, al.x, b.x); v1 = fmaf(v1, al.y, b.y); v2 = fmaf(v2, al.z, b.z); v3 = fmaf(v3, al.w, b.w);
+                        p01 = ffma2(p01, f2_pack(al.x, al.y), f2_pack(b.x, b.y));
+                        p23 = ffma2(p23, f2_pack(al.z, al.w), f2_pack(b.z, b.w));
                     }
-                    const float s0 = __sinf(v0), s1 = __sinf(v1), s2 = __sinf(v2), s3 = __sinf(v3);
-                    v0 = fmaf(s0, s0, v0); v1 = fmaf(s1, s1, v1); v2 = fmaf(s2, s2, v2); v3 = fmaf(s3, s3, v3);
+                    // The epilogue is bound by the XU pipe (32 MUFU.SIN per 32 x 32 piece = 256 cycles per sub-partition
+                    // against ~160 issue slots): kEpiPolyMask moves some column pairs' sin^2 to the FMA pipe as a packed
+                    // half2 polynomial, until the two pipes balance
+                    f2_unpack(p01, v0, v1); f2_unpack(p23, v2, v3);
+                    if ((kEpiPolyMask >> (j / 2)) & 1u) {
+                        o[j / 2] = as_u32(snake_h2_poly(__floats2half2_rn(v0, v1)));
+                    } else {
+                        const float s0 = __sinf(v0), s1 = __sinf(v1);
+                        const unsigned long long s01 = f2_pack(s0, s1);
+                        f2_unpack(ffma2(s01, s01, p01), v0, v1);
+                        o[j / 2] = pack2(v0, v1, tag);
+                    }
+                    if ((kEpiPolyMask >> (j / 2 + 1)) & 1u) {
+                        o[j / 2 + 1] = as_u32(snake_h2_poly(__floats2half2_rn(v2, v3)));
+                    } else {
+                        const float s2 = __sinf(v2), s3 = __sinf(v3);
+                        const unsigned long long s23 = f2_pack(s2, s3);
+                        f2_unpack(ffma2(s23, s23, p23), v2, v3);
+                        o[j / 2 + 1] = pack2(v2, v3, tag);
+                    }
+                    continue;
                 } else {
                     if (MODE != EPI_C_NOISE) {
                         const float4 b = *reinterpret_cast<const float4*>(vb + cg * 32 + j);
@@ -560,12 +622,21 @@ k_chain(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtenso
                 o[j / 2 + 1] = pack2(v2, v3, tag);
             }
             if (MODE == EPI_C_NOISE) tmem_st32(taddr, raw);
+            // rows outside [0, T) are the convs' zero padding: only the tiles at a stream's two ends have any, so the
+            // selects are kept out of the common path (warp-uniform branch)
+            if (MODE == EPI_C_FINAL || __all_sync(0xFFFFFFFFu, valid)) {
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const int chunk = ((cg & 1) * 4 + c) ^ (i & 7);
-                *reinterpret_cast<uint4*>(row + chunk * 16) =
-                    (valid || MODE == EPI_C_FINAL) ? make_uint4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3])
-                                                   : make_uint4(0u, 0u, 0u, 0u);
+                for (int c = 0; c < 4; ++c) {
+                    const int chunk = ((cg & 1) * 4 + c) ^ (i & 7);
+                    *reinterpret_cast<uint4*>(row + chunk * 16) = make_uint4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int chunk = ((cg & 1) * 4 + c) ^ (i & 7);
+                    *reinterpret_cast<uint4*>(row + chunk * 16) =
+                        valid ? make_uint4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]) : make_uint4(0u, 0u, 0u, 0u);
+                }
             }
         }
         if (MODE == EPI_C_NOISE) tmem_st_wait();

@@ -806,10 +806,24 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
                 CUtensorMap mx;
                 int rc2 = act_map(h, &mx, cur, ra.C, T, S_buf, box_rows, 1, hk, 0);
                 if (rc2) return rc2;
+                const bool rprof = getenv("SNACB_RES_PROF") != nullptr;     // debug: in-kernel wait / phase cycles of CTA 0
+                if (rprof) {
+                    CK(h, cudaMalloc(reinterpret_cast<void**>(&ra.prof), 8 * sizeof(long long)));
+                    CK(h, cudaMemsetAsync(ra.prof, 0, 8 * sizeof(long long), st));
+                }
                 cudaError_t le = launch_resunit2(hk, ra, mx, r.tm_pw[hk], h->sm_count, st);
                 prof_end(h, st);
                 CK(h, le);
                 h->launches++;
+                if (rprof) {
+                    long long pv[8];
+                    CK(h, cudaStreamSynchronize(st));
+                    CK(h, cudaMemcpy(pv, ra.prof, sizeof pv, cudaMemcpyDeviceToHost));
+                    CK(h, cudaFree(ra.prof));
+                    fprintf(stderr, "%s C=%d: CTA0 cycles: mma-warp waits a_full %lld w_full %lld acc_empty %lld | warp0 waits x_full %lld "
+                            "a_empty %lld, prologue %lld, epilogue %lld over %lld tiles\n", nm, ra.C, pv[0], pv[1], pv[2], pv[3], pv[4],
+                            pv[5], pv[6], pv[7]);
+                }
             } else {
                 cudaError_t le = launch_resunit_tc(last ? EPI_RES_SNAKE : EPI_RES, hk, xf32 ? 1 : 0, ra, r.tm_pw[hk], st);
                 prof_end(h, st);
