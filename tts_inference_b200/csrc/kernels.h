@@ -73,9 +73,10 @@ cudaError_t launch_resunit_tc(int epi, int half_fp16, int x_f32, const ResUnitAr
 cudaError_t init_tc_kernels();            // opt-in shared memory sizes
 
 // ---- kernels_res2.cu  (persistent pipelined ResidualUnit, 16-bit activations)
-void resunit2_geometry(int C, int dil, int* tile_m, int* box_rows);   // x tensor-map box = (64, box_rows, 1), no swizzle
+void resunit2_geometry(int C, int dil, int* tile_m, int* box_rows);   // x tensor-map box = (64, box_rows, 1)
+bool resunit2_swizzled_x(int C);          // C = 512: the x map is 128B-swizzled (the x chunk doubles as the residual MMA's A operand)
 cudaError_t launch_resunit2(int half_fp16, const ResUnitArgs& a, const CUtensorMap& tmX, const CUtensorMap& tmW,
-                            int sm_count, cudaStream_t st);
+                            const CUtensorMap& tmO, int sm_count, cudaStream_t st);   // tmO (C = 512): output, box (32, 32, 1), 64B-swizzled
 
 // ---- kernels_convt.cu  (ConvTranspose1d with resident weights and row-shifted UMMA descriptors; block 3)
 bool convt_res_supported(int Cin, int Cout, int s);

@@ -64,25 +64,33 @@ struct Res2Cfg {
     static constexpr int kThreads = (kComputeWarps + 2 + (kSplitEpi ? kEpiWarps : 0)) * 32;
     static constexpr bool kParamsSmem = (C <= 256);
     static constexpr int kPrmBytes = kParamsSmem ? (C / 2) * 96 : 0; // 24 floats per channel pair
+    // C = 512 (block 0): the RESIDUAL is added by the tensor core.  The x chunk that the prologue reads sits in shared
+    // memory anyway; loaded 128B-swizzled it is a valid UMMA A operand, and an MMA against a 64 x 64 identity adds it --
+    // exactly: 16-bit x times 1.0 into the fp32 accumulator -- onto the chunk's 64 output columns.  The epilogue then has no
+    // global loads left (they were the long pole: row-per-lane 32-byte loads, 32 cache lines per instruction).
+    static constexpr bool kResMma = (C == 512);
+    static constexpr int kIdentBytes = kResMma ? 64 * 128 : 0;
     static constexpr int kEpiBytes = 3 * C * 4;                      // bias, alpha_next, inv_alpha_next
     static constexpr int kMapBytes = 128;                            // segment table (int per compute warp)
     static constexpr int kBarBytes = 256;
     static constexpr int kOffA = 0;
     static constexpr int kOffW = kOffA + kNSA * kABytes;
     static constexpr int kOffXs = kOffW + kNSW * kWStageBytes;
-    static constexpr int kOffPrm = kOffXs + kNXS * kXsBytes;
+    static constexpr int kOffIdent = kOffXs + kNXS * kXsBytes;
+    static constexpr int kOffPrm = kOffIdent + kIdentBytes;
     static constexpr int kOffEpi = kOffPrm + kPrmBytes;
     static constexpr int kOffMap = kOffEpi + kEpiBytes;
     static constexpr int kOffBar = ((kOffMap + kMapBytes + 15) / 16) * 16;
     static constexpr int kSmem = kOffBar + kBarBytes + 1024;
     static_assert(kRows % 2 == 0 && kHalfRows <= 256, "TMA box");
+    static_assert(!kResMma || (kRows <= 256 && kAccs == 1 && (kOffIdent % 1024) == 0 && (kXsBytes % 1024) == 0), "residual MMA");
     static_assert(kSmem <= 232448, "shared memory budget");
 };
 
 template <int C, int DIL, int EPI, typename HT>
 __global__ void __launch_bounds__((Res2Cfg<C, DIL>::kThreads), 1)
-k_resunit2(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const ResUnitArgs a,
-           const int num_tiles) {
+k_resunit2(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
+           const __grid_constant__ CUtensorMap tmO, const ResUnitArgs a, const int num_tiles) {
     using Cfg = Res2Cfg<C, DIL>;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // keep pointer provenance (no integer round trip) so that the compiler emits LDS/STS
@@ -112,7 +120,8 @@ k_resunit2(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
     if (tid == 0) {
         prefetch_tmap(&tmX);
         prefetch_tmap(&tmW);
-        for (int i = 0; i < 3; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], kComputeWarps); }
+        if (Cfg::kResMma) prefetch_tmap(&tmO);
+        for (int i = 0; i < 3; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], kComputeWarps + (Cfg::kResMma ? 1 : 0)); }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&a_full[i], kComputeWarps); mbar_init(&a_empty[i], 1);
             mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1);
@@ -159,6 +168,15 @@ k_resunit2(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
             for (; nseg < kComputeWarps; ++nseg) sSeg[nseg] = -1;
         }
     }
+    if (Cfg::kResMma) {
+        // identity [64 n][64 k], K-major, 128B-swizzled (the B operand of the residual MMA)
+        uint8_t* sI = smem + Cfg::kOffIdent;
+        for (int i = tid; i < 64 * 64; i += Cfg::kThreads) {
+            const int n = i >> 6, k = i & 63;
+            *reinterpret_cast<HT*>(sI + sw128_offset(n, k)) = static_cast<HT>(n == k ? 1.0f : 0.0f);
+        }
+        fence_proxy_async_smem();
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -184,8 +202,12 @@ k_resunit2(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
                     if (g >= Cfg::kNXS) mbar_wait(&x_empty[sx], ((g / Cfg::kNXS) - 1) & 1);
                     mbar_expect_tx(&x_full[sx], Cfg::kRows * 128);
                     uint8_t* dst = sX + sx * Cfg::kXsBytes;
-                    tma_load_3d(dst, &tmX, kc * 64, t0 - 3 * DIL, s, &x_full[sx]);
-                    tma_load_3d(dst + Cfg::kHalfRows * 128, &tmX, kc * 64, t0 - 3 * DIL + Cfg::kHalfRows, s, &x_full[sx]);
+                    if (Cfg::kResMma) {                    // one box of kRows rows, 128B-swizzled (tmX: box (64, kRows, 1))
+                        tma_load_3d(dst, &tmX, kc * 64, t0 - 3 * DIL, s, &x_full[sx]);
+                    } else {
+                        tma_load_3d(dst, &tmX, kc * 64, t0 - 3 * DIL, s, &x_full[sx]);
+                        tma_load_3d(dst + Cfg::kHalfRows * 128, &tmX, kc * 64, t0 - 3 * DIL + Cfg::kHalfRows, s, &x_full[sx]);
+                    }
                     if (!Cfg::kWRes) {
 #pragma unroll
                         for (int nh = 0; nh < Cfg::kNHalfW; ++nh) {
@@ -212,6 +234,26 @@ k_resunit2(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
             const uint32_t d_base = tmem_base + as * Cfg::kAccCols;
             for (int kc = 0; kc < Cfg::kChunks; ++kc, ++g) {
                 const int sa = g % 2;
+                // residual (kResMma): acc[:, kc*64 .. +64) += x[rows 3 DIL .. 3 DIL + 128 of the stage] * I.  It needs the x
+                // stage only, not the prologue's A operand: chunks >= 1 issue it as soon as the stage has landed (the
+                // accumulator was initialised by chunk 0's first 1x1 MMA), chunk 0 after its 1x1 MMAs.  The stage is
+                // released to the producer when these MMAs retire (x_empty counts them beside the 18 prologue warps).
+                auto residual_mma = [&]() {
+                    const int sx = g % Cfg::kNXS;
+                    mbar_wait(&x_full[sx], (g / Cfg::kNXS) & 1);
+                    tc_fence_after();
+                    if (lane == 0) {
+                        constexpr uint32_t idescI = umma_idesc_f16(128, 64, HalfFmt2<HT>::kFmt);
+                        const uint32_t x_addr = smem_u32(sX + sx * Cfg::kXsBytes) + 3 * DIL * 128;
+                        const uint32_t i_addr = smem_u32(smem + Cfg::kOffIdent);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            mma_f16_ss(d_base + kc * 64, umma_desc_sw128(x_addr + k * 32), umma_desc_sw128(i_addr + k * 32), idescI, 1u);
+                        mma_commit(&x_empty[sx]);
+                    }
+                    __syncwarp();
+                };
+                if (Cfg::kResMma && kc > 0) residual_mma();
                 long long tp0 = clock64();
                 mbar_wait(&a_full[sa], (g / 2) & 1);
                 if (a.prof && blockIdx.x == 0 && lane == 0) a.prof[0] += clock64() - tp0;
@@ -237,6 +279,7 @@ k_resunit2(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
                     }
                     __syncwarp();
                 }
+                if (Cfg::kResMma && kc == 0) residual_mma();
                 if (lane == 0) {
                     mma_commit(&a_empty[sa]);
                     if (kc == Cfg::kChunks - 1) mma_commit(&acc_full[as]);
@@ -337,6 +380,7 @@ k_resunit2(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
             // ready): its L2 latency is the long pole of this epilogue, not the arithmetic
             U32x8 xa[2], xb[2];
             auto fetch = [&](int cc, U32x8 (&dst)[2]) {
+                if (Cfg::kResMma) return;                  // the residual is in the accumulator already
                 if (valid) {
                     const HT* p = x + grow * C + cg * kColsPerWarp + cc * 32;
                     dst[0] = ld_global_v8(p);
@@ -354,15 +398,18 @@ k_resunit2(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
                 tmem_ld32(taddr + col, raw);
                 if (cc + 1 < kColsPerWarp / 32) fetch(cc + 1, xb);
                 tmem_ld_wait();
-                if (valid) {
+                if (valid || Cfg::kResMma) {
                     const uint32_t* xw = reinterpret_cast<const uint32_t*>(xa);
                     U32x8 o[2];
                     uint32_t* ow = reinterpret_cast<uint32_t*>(o);
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
                         const float4 b = *reinterpret_cast<const float4*>(sEpi + col + j);
-                        const float2 x0 = unpack2(xw[j / 2], static_cast<const HT*>(nullptr));
-                        const float2 x1 = unpack2(xw[j / 2 + 1], static_cast<const HT*>(nullptr));
+                        float2 x0 = make_float2(0.f, 0.f), x1 = make_float2(0.f, 0.f);
+                        if (!Cfg::kResMma) {
+                            x0 = unpack2(xw[j / 2], static_cast<const HT*>(nullptr));
+                            x1 = unpack2(xw[j / 2 + 1], static_cast<const HT*>(nullptr));
+                        }
                         float v0 = x0.x + (__uint_as_float(raw[j]) + b.x);
                         float v1 = x0.y + (__uint_as_float(raw[j + 1]) + b.y);
                         float v2 = x1.x + (__uint_as_float(raw[j + 2]) + b.z);
@@ -378,18 +425,47 @@ k_resunit2(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
                         ow[j / 2] = pack2(v0, v1, static_cast<const HT*>(nullptr));
                         ow[j / 2 + 1] = pack2(v2, v3, static_cast<const HT*>(nullptr));
                     }
-                    st_global_v8(out + grow * C + col, o[0]);
-                    st_global_v8(out + grow * C + col + 16, o[1]);
+                    if (!Cfg::kResMma) {
+                        st_global_v8(out + grow * C + col, o[0]);
+                        st_global_v8(out + grow * C + col + 16, o[1]);
+                    } else {
+                        // kResMma: the 32 rows x 32 columns leave through the warp's 2 KB slot of the A stages (idle until the
+                        // next tile's prologue; 64-byte rows, 64B-swizzled: conflict-free 16-byte stores) and ONE TMA store
+                        // (box 32 x 32; rows past T are clipped) instead of 32 cache lines per store instruction
+                        uint8_t* stg = sA + warp * 2048;
+                        if (lane == 0) bulk_wait_group_read<0>();      // the previous piece's store has read the slot
+                        __syncwarp();
+#pragma unroll
+                        for (int c = 0; c < 4; ++c)
+                            *reinterpret_cast<uint4*>(stg + lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4)) =
+                                make_uint4(ow[4 * c], ow[4 * c + 1], ow[4 * c + 2], ow[4 * c + 3]);
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_store_3d(&tmO, stg, col, t0 + ac * 128 + q * 32, s);
+                            bulk_commit_group();
+                        }
+                    }
                 }
                 xa[0] = xb[0]; xa[1] = xb[1];
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[as]);
+            if (Cfg::kResMma) {                                // the A stages go back to the prologue (barrier below)
+                if (lane == 0) bulk_wait_group_read<0>();
+                __syncwarp();
+            }
         };
 
         int g = 0;
         const int seg_base = sSeg[warp];
+        // swizzled x stage (kResMma): the 16-byte chunk of this lane's channel pair is XORed with (row & 7); input row j of
+        // the segment is stage row seg_base + j DIL, whose (row & 7) repeats with period 8 in j (DIL is odd)
+        uint32_t xswz[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            xswz[j] = static_cast<uint32_t>(seg_base) * 128u + ((((lane >> 2) ^ (seg_base + j * DIL)) & 7) << 4) + ((lane & 3) << 2);
         for (int n = 0; n < my_tiles; ++n) {
             for (int kc = 0; kc < Cfg::kChunks; ++kc, ++g) {
                 // ---- per-lane parameters of channels (kc*64 + 2*lane, +1)
@@ -430,9 +506,16 @@ k_resunit2(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
                     // all kSegLen+6 input rows of the segment are fetched up front (packed 16-bit pairs, one
                     // register each) so that their shared-memory latency is paid once, not per row
                     uint32_t xr[Cfg::kSegLen + 6];
+                    if (Cfg::kResMma) {
+                        const uint32_t xb0 = smem_u32(xs);
 #pragma unroll
-                    for (int j = 0; j < Cfg::kSegLen + 6; ++j)
-                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(xr[j]) : "r"(xaddr + j * DIL * 128));
+                        for (int j = 0; j < Cfg::kSegLen + 6; ++j)
+                            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(xr[j]) : "r"(xb0 + xswz[j & 7] + j * DIL * 128));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < Cfg::kSegLen + 6; ++j)
+                            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(xr[j]) : "r"(xaddr + j * DIL * 128));
+                    }
                     float2 win[7];
 #pragma unroll
                     for (int j = 0; j < 6; ++j)
@@ -464,8 +547,12 @@ k_resunit2(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
                 else if (n > 0) epilogue(n - 1);
                 if (a.prof && blockIdx.x == 0 && tid == 0) { a.prof[6] += clock64() - te; a.prof[7] += 1; }
             }
+            // kResMma: the epilogue staged its output in the A stages -- no prologue warp (16 and 17 run no epilogue) may
+            // write the next tile's operand before every store has read its slot
+            if (Cfg::kResMma) asm volatile("bar.sync 2, %0;" ::"n"(kComputeWarps * 32) : "memory");
         }
         if (!Cfg::kSplitEpi && Cfg::kAccStages == 2 && my_tiles > 0 && warp < kLockstepEpiWarps) epilogue(my_tiles - 1);
+        if (Cfg::kResMma && warp < kLockstepEpiWarps && lane == 0) bulk_wait_group<0>();
     }
     tc_fence_before();
     __syncthreads();
@@ -473,7 +560,8 @@ k_resunit2(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
 }
 
 template <int C, int DIL, int EPI, typename HT>
-cudaError_t launch_t(const ResUnitArgs& a, const CUtensorMap& tmX, const CUtensorMap& tmW, int sm_count, cudaStream_t st) {
+cudaError_t launch_t(const ResUnitArgs& a, const CUtensorMap& tmX, const CUtensorMap& tmW, const CUtensorMap& tmO, int sm_count,
+                     cudaStream_t st) {
     using Cfg = Res2Cfg<C, DIL>;
     static PerDeviceOnce once;
     int dev_;
@@ -485,25 +573,27 @@ cudaError_t launch_t(const ResUnitArgs& a, const CUtensorMap& tmX, const CUtenso
     const int tiles = a.S * (((a.t_n > 0 ? a.t_n : a.T) + Cfg::kTileM - 1) / Cfg::kTileM);
     if (tiles == 0) return cudaSuccess;
     const int grid = tiles < sm_count ? tiles : sm_count;
-    k_resunit2<C, DIL, EPI, HT><<<grid, Cfg::kThreads, Cfg::kSmem, st>>>(tmX, tmW, a, tiles);
+    k_resunit2<C, DIL, EPI, HT><<<grid, Cfg::kThreads, Cfg::kSmem, st>>>(tmX, tmW, tmO, a, tiles);
     return cudaGetLastError();
 }
 
 template <int C, typename HT>
-cudaError_t launch_c(const ResUnitArgs& a, const CUtensorMap& tmX, const CUtensorMap& tmW, int sm_count, cudaStream_t st) {
-    if (a.dil == 1) return launch_t<C, 1, EPI_RES, HT>(a, tmX, tmW, sm_count, st);
-    if (a.dil == 3) return launch_t<C, 3, EPI_RES, HT>(a, tmX, tmW, sm_count, st);
-    if (a.dil == 9) return launch_t<C, 9, EPI_RES_SNAKE, HT>(a, tmX, tmW, sm_count, st);
+cudaError_t launch_c(const ResUnitArgs& a, const CUtensorMap& tmX, const CUtensorMap& tmW, const CUtensorMap& tmO, int sm_count,
+                     cudaStream_t st) {
+    if (a.dil == 1) return launch_t<C, 1, EPI_RES, HT>(a, tmX, tmW, tmO, sm_count, st);
+    if (a.dil == 3) return launch_t<C, 3, EPI_RES, HT>(a, tmX, tmW, tmO, sm_count, st);
+    if (a.dil == 9) return launch_t<C, 9, EPI_RES_SNAKE, HT>(a, tmX, tmW, tmO, sm_count, st);
     return cudaErrorInvalidValue;
 }
 
 template <typename HT>
-cudaError_t launch_h(const ResUnitArgs& a, const CUtensorMap& tmX, const CUtensorMap& tmW, int sm_count, cudaStream_t st) {
+cudaError_t launch_h(const ResUnitArgs& a, const CUtensorMap& tmX, const CUtensorMap& tmW, const CUtensorMap& tmO, int sm_count,
+                     cudaStream_t st) {
     switch (a.C) {
-        case 512: return launch_c<512, HT>(a, tmX, tmW, sm_count, st);
-        case 256: return launch_c<256, HT>(a, tmX, tmW, sm_count, st);
-        case 128: return launch_c<128, HT>(a, tmX, tmW, sm_count, st);
-        case 64: return launch_c<64, HT>(a, tmX, tmW, sm_count, st);
+        case 512: return launch_c<512, HT>(a, tmX, tmW, tmO, sm_count, st);
+        case 256: return launch_c<256, HT>(a, tmX, tmW, tmO, sm_count, st);
+        case 128: return launch_c<128, HT>(a, tmX, tmW, tmO, sm_count, st);
+        case 64: return launch_c<64, HT>(a, tmX, tmW, tmO, sm_count, st);
         default: return cudaErrorInvalidValue;
     }
 }
@@ -513,13 +603,16 @@ cudaError_t launch_h(const ResUnitArgs& a, const CUtensorMap& tmX, const CUtenso
 void resunit2_geometry(int C, int dil, int* tile_m, int* box_rows) {
     const int tm = (C == 512) ? 128 : 256;
     *tile_m = tm;
-    *box_rows = (tm + 6 * dil) / 2;
+    *box_rows = (C == 512) ? tm + 6 * dil : (tm + 6 * dil) / 2;     // C = 512: one 128B-swizzled box (resunit2_swizzled_x)
 }
 
+bool resunit2_swizzled_x(int C) { return C == 512; }
+
 // dil 1 and 3 use the plain residual epilogue, dil 9 (last unit of a block) applies the next Snake.
+// tmO (C = 512 only, else unused): the output, box (32, 32, 1), 64B-swizzled
 cudaError_t launch_resunit2(int half_fp16, const ResUnitArgs& a, const CUtensorMap& tmX, const CUtensorMap& tmW,
-                            int sm_count, cudaStream_t st) {
-    return half_fp16 ? launch_h<__half>(a, tmX, tmW, sm_count, st) : launch_h<__nv_bfloat16>(a, tmX, tmW, sm_count, st);
+                            const CUtensorMap& tmO, int sm_count, cudaStream_t st) {
+    return half_fp16 ? launch_h<__half>(a, tmX, tmW, tmO, sm_count, st) : launch_h<__nv_bfloat16>(a, tmX, tmW, tmO, sm_count, st);
 }
 
 }  // namespace snacb

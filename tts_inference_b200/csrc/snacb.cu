@@ -260,10 +260,11 @@ int make_tmap_3d(snacb_handle h, CUtensorMap* m, const void* base, uint64_t C, u
                  uint32_t wbox, int fp16, int swizzle = 1) {
     cuuint64_t gdim[3] = {C, T, S};
     cuuint64_t gstr[2] = {C * 2, T * C * 2};
-    cuuint32_t box[3] = {64, tbox, wbox};
+    cuuint32_t box[3] = {swizzle == 2 ? 32u : 64u, tbox, wbox};         // swizzle: 0 none, 1 128B (64-column box), 2 64B (32-column box)
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = h->encode(m, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstr, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           swizzle == 2 ? CU_TENSOR_MAP_SWIZZLE_64B : (swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE),
                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(h, SNACB_ERR_CUDA, "cuTensorMapEncodeTiled(3d C=%llu T=%llu S=%llu) failed: %d",
@@ -804,14 +805,19 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
                 int tile_m, box_rows;
                 resunit2_geometry(ra.C, ra.dil, &tile_m, &box_rows);
                 CUtensorMap mx;
-                int rc2 = act_map(h, &mx, cur, ra.C, T, S_buf, box_rows, 1, hk, 0);
+                int rc2 = act_map(h, &mx, cur, ra.C, T, S_buf, box_rows, 1, hk, resunit2_swizzled_x(ra.C) ? 1 : 0);
                 if (rc2) return rc2;
                 const bool rprof = getenv("SNACB_RES_PROF") != nullptr;     // debug: in-kernel wait / phase cycles of CTA 0
                 if (rprof) {
                     CK(h, cudaMalloc(reinterpret_cast<void**>(&ra.prof), 8 * sizeof(long long)));
                     CK(h, cudaMemsetAsync(ra.prof, 0, 8 * sizeof(long long), st));
                 }
-                cudaError_t le = launch_resunit2(hk, ra, mx, r.tm_pw[hk], h->sm_count, st);
+                CUtensorMap mo = mx;                                          // C = 512: staged TMA-store epilogue
+                if (resunit2_swizzled_x(ra.C)) {
+                    rc2 = act_map(h, &mo, ro, ra.C, T, S_buf, 32, 1, hk, 2);
+                    if (rc2) return rc2;
+                }
+                cudaError_t le = launch_resunit2(hk, ra, mx, r.tm_pw[hk], mo, h->sm_count, st);
                 prof_end(h, st);
                 CK(h, le);
                 h->launches++;
