@@ -129,6 +129,30 @@ def test_tensorcore_stage_taps(decoder, oracle_model):
         assert snr_db(r, taps[k]) >= 45.0, (k, snr_db(r, taps[k]))
 
 
+@pytest.mark.parametrize("B,F_", [(3, 4), (2, 5), (1, 13), (150, 4)])
+def test_block0_residual_by_identity_mma_against_v1_kernel(monkeypatch, B, F_):
+    """Block 0's ResidualUnits (k_resunit2<512>) add the residual with an identity MMA on the 128B-swizzled x chunk and
+    store through a swizzled staging tile by TMA; SNACB_RES_V1=1 selects the first-generation kernel (residual loaded and
+    added in the epilogue, per-row stores).  Same operands, a different accumulation order: the three unit outputs agree
+    to rounding in every row and channel (a wrong swizzle phase or row shift would show up as whole rows / chunks off)."""
+    sd = synth.make_state_dict(0)
+    tokens = _cuda(synth.make_tokens(B, F_, seed=91 + F_))
+    nz = [_cuda(n) for n in synth.make_noises(B, 4 * F_, seed=4)]
+    dec_a = SnacDecoder(sd, device=0)
+    monkeypatch.setenv("SNACB_RES_V1", "1")
+    dec_b = SnacDecoder(sd, device=0)
+    monkeypatch.delenv("SNACB_RES_V1")
+    dec_a.decode(tokens, raw_ids=True, noise=nz, precision="fp16", keep_taps=True)
+    ta = dec_a.taps()
+    dec_b.decode(tokens, raw_ids=True, noise=nz, precision="fp16", keep_taps=True)
+    tb = dec_b.taps()
+    for k in ("b0.res0", "b0.res1", "b0.res2"):
+        a, b = ta[k].astype(np.float64), tb[k].astype(np.float64)
+        assert a.shape == b.shape and np.isfinite(a).all(), k
+        assert snr_db(b, a) >= 55.0, (k, snr_db(b, a))
+        assert np.abs(a - b).max() <= 2.0 ** -6 * max(1.0, np.abs(b).max()), (k, np.abs(a - b).max())
+
+
 @pytest.mark.parametrize("prec", ["fp16", "bf16"])
 @pytest.mark.parametrize("B,F_", [(3, 4), (2, 5), (1, 13)])
 def test_resident_weight_convtranspose_against_generic_gemm(monkeypatch, B, F_, prec):
