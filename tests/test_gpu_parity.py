@@ -440,16 +440,25 @@ def test_grouping_and_batch_independence(decoder, prec):
 
 
 @pytest.mark.parametrize("prec", ["fp16", "bf16"])
-@pytest.mark.parametrize("B,F_,sliced", [(40, 4, False), (301, 4, True), (3, 64, False), (5, 37, False)])
-def test_bulk_tail_kernel_is_bit_identical(decoder, monkeypatch, prec, B, F_, sliced):
-    """k_tail_bulk (persistent, cp.async.bulk ring; large batches) against k_tail (one load per lane and row)."""
+@pytest.mark.parametrize("B,F_,sliced", [(40, 4, False), (301, 4, True), (3, 64, False), (5, 37, False), (1, 1, False)])
+def test_tail_kernels_agree(decoder, monkeypatch, prec, B, F_, sliced):
+    """The three tail kernels on the same block-3 output.  k_tail_tc (default for 16-bit activations: channel contraction
+    as a tcgen05 GEMM against the hi / lo split of the fp32 weights, diagonal sum over the taps) against the FFMA kernels:
+    the same sum in another order -> the waveform agrees to fp32 rounding, the PCM to 1 LSB.  The two FFMA kernels
+    (SNACB_TAIL_V1=1: one load per lane and row; =2: persistent, cp.async.bulk ring) share their arithmetic: bit-identical."""
     tokens = _cuda(synth.make_tokens(B, F_, seed=11))
-    new = decoder.decode(tokens, raw_ids=True, seed=4, precision=prec, extract_slice=sliced, return_wave=True)
+    kw = dict(raw_ids=True, seed=4, precision=prec, extract_slice=sliced, return_wave=True)
+    new = decoder.decode(tokens, **kw)
     monkeypatch.setenv("SNACB_TAIL_V1", "1")
-    old = decoder.decode(tokens, raw_ids=True, seed=4, precision=prec, extract_slice=sliced, return_wave=True)
+    old = decoder.decode(tokens, **kw)
+    monkeypatch.setenv("SNACB_TAIL_V1", "2")
+    bulk = decoder.decode(tokens, **kw)
     torch.cuda.synchronize()
-    assert torch.equal(new[0], old[0]) and torch.equal(new[1], old[1])
+    assert torch.equal(bulk[0], old[0]) and torch.equal(bulk[1], old[1])
     assert int((new[0] != 0).sum()) > new[0].numel() // 2
+    assert float((new[1] - old[1]).abs().max()) <= 4e-6
+    assert int((new[0].int() - old[0].int()).abs().max()) <= 1
+    assert np.array_equal(new[0].cpu().numpy(), pcm_of(new[1].cpu().numpy()))
 
 
 @pytest.mark.parametrize("prec", ["fp16", "bf16"])

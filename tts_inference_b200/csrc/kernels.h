@@ -58,7 +58,8 @@ void launch_split3(const __half* x, int S, int T, int K, int r_lo, int r_n, __nv
 void launch_respre16(const ResUnitArgs& a, int r_lo, int r_n, __nv_bfloat16* out, cudaStream_t st);
 template <typename InT>
 void launch_tail(const InT* a, int S, int T, int t_begin, int n_out, const float* w, float bias, int16_t* pcm,
-                 float* wave, cudaStream_t st, const StreamMap& map = StreamMap{nullptr, nullptr, nullptr});
+                 float* wave, cudaStream_t st, const StreamMap& map = StreamMap{nullptr, nullptr, nullptr},
+                 const CUtensorMap* tm128 = nullptr, const CUtensorMap* tm8 = nullptr);   // maps: the tensor-core tail (16-bit input)
 template <typename T>
 void launch_to_f32(const T* in, float* out, size_t n, cudaStream_t st);
 

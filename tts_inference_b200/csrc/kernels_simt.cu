@@ -7,6 +7,7 @@
 //   * k_to_f32        debug taps
 // Activations are channel-last: [stream][time][channel].
 #include <cstdlib>
+#include <type_traits>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -610,13 +611,175 @@ k_tail_bulk(const InT* __restrict__ a, int T, int t_begin_, int n_out, const flo
     }
 }
 
+// ----------------------------------------------------------------------------------------------
+// k_tail_tc: the same conv 64 -> 1 k7 + tanh + int16 for 16-bit activations, shaped so that nothing but HBM is left:
+// the channel contraction runs on the tensor core.  P[t][k] = sum_c a[t][c] * w[k][c] is a GEMM with M = time rows,
+// N = the 7 taps, K = 64 channels (tcgen05.mma M = 128, N = 16: columns 0..6 carry the 16-bit "hi" part of the fp32
+// weights, columns 8..14 the "lo" part -- w = hi + lo to 2^-22 -- accumulated in fp32 in TMEM), and the output is the
+// diagonal sum  y[t] = b + sum_k P[t + k - 3][k].  Per 256-sample tile: the 264 input rows [base - 3, base + 261) arrive
+// 128B-swizzled by three TMA loads (boxes of 128, 128 and 8 rows; rows outside the stream are the zero fill = the conv's
+// padding) into a 3-stage ring, one thread issues 12 MMAs (three 128-row blocks at stage rows 0, 128 and 136), the eight
+// warps drain the 16 accumulator columns of their rows (tcgen05.ld), fold hi + lo and park P tap-major in shared memory,
+// and every thread sums one output's diagonal.  Each P[t][k] depends on row t alone and the diagonal is summed in a fixed
+// order, so the result does not depend on where a tile starts: a session step, a ranged decode and the batch decode give
+// the same bits (the property the FFMA kernels above had by sharing tail_chunk).  Before: 38 LDS + 224 FFMA2 + a
+// 31-step transposing lane reduction per 32 samples and warp -- issue-bound at 3.4 TB/s of input.
+// ----------------------------------------------------------------------------------------------
+constexpr int kTtTile = 256;
+constexpr int kTtRows = 264;                       // 3 + 256 + 3, rounded up to the 8-row box of the last load
+constexpr int kTtStageBytes = kTtRows * 128;       // 33 KB, a multiple of 1024
+constexpr int kTtStages = 3;
+constexpr int kTtOffW = kTtStages * kTtStageBytes; // [16 n][64 k] weights, 128B-swizzled K-major
+constexpr int kTtOffP = kTtOffW + 2048;            // P tap-major: [7][kTtRows] fp32
+constexpr int kTtOffBar = kTtOffP + 7 * kTtRows * 4;
+constexpr int kTtSmem = kTtOffBar + 64 + 1024;
+constexpr int kTtTmemCols = 64;                    // three blocks x 16 columns (power of two >= 48)
+
+template <typename InT, bool MAPPED>
+__global__ void __launch_bounds__(256, 2)
+k_tail_tc(const __grid_constant__ CUtensorMap tm128, const __grid_constant__ CUtensorMap tm8, int T, int t_begin_, int n_out,
+          const float* __restrict__ w, float bias, int16_t* __restrict__ pcm, float* __restrict__ wave, int tiles_per_stream,
+          int num_tiles, const StreamMap map) {
+    using namespace ptx;
+    static_assert(sizeof(InT) == 2, "16-bit activations");
+    extern __shared__ __align__(1024) uint8_t tt_smem[];
+    uint8_t* smem = tt_smem + ((1024u - (smem_u32(tt_smem) & 1023u)) & 1023u);
+    uint8_t* sWt = smem + kTtOffW;
+    float* sP = reinterpret_cast<float*>(smem + kTtOffP);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + kTtOffBar);      // [kTtStages]
+    uint64_t* mma_bar = full + kTtStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_bar + 1);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    if (tid == 0) {
+        prefetch_tmap(&tm128); prefetch_tmap(&tm8);
+        for (int i = 0; i < kTtStages; ++i) mbar_init(&full[i], 1);
+        mbar_init(mma_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) { tmem_alloc(tmem_slot, kTtTmemCols); tmem_relinquish(); }
+    for (int i = tid; i < 16 * 64; i += 256) {       // weights: row n = tap (hi) / 8 + tap (lo), column k = channel
+        const int n = i >> 6, k = i & 63, tap = n & 7;
+        float v = 0.f;
+        if (tap < 7) {
+            const float wf = w[tap * 64 + k];
+            const InT hi = static_cast<InT>(wf);
+            v = (n < 8) ? static_cast<float>(hi) : wf - static_cast<float>(hi);
+        }
+        *reinterpret_cast<InT*>(sWt + sw128_offset(n, k)) = static_cast<InT>(v);
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    auto issue = [&](int tile, int stage) {          // thread 0
+        const int s = tile / tiles_per_stream;
+        const int base = t_begin_ + (MAPPED ? sm_off(map, s, 2048) : 0) + (tile % tiles_per_stream) * kTtTile;
+        const int sl = MAPPED ? sm_slot(map, s) : s;
+        uint8_t* dst = smem + stage * kTtStageBytes;
+        mbar_expect_tx(&full[stage], kTtStageBytes);
+        tma_load_3d(dst, &tm128, 0, base - 3, sl, &full[stage]);
+        tma_load_3d(dst + 128 * 128, &tm128, 0, base + 125, sl, &full[stage]);
+        tma_load_3d(dst + 256 * 128, &tm8, 0, base + 253, sl, &full[stage]);
+    };
+    if (tid == 0)
+        for (int k = 0; k < kTtStages; ++k) {
+            const int tile = blockIdx.x + k * gridDim.x;
+            if (tile < num_tiles) issue(tile, k);
+        }
+    constexpr uint32_t idesc = umma_idesc_f16(128, 16, std::is_same<InT, __half>::value ? 0u : 1u);
+    int k = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++k) {
+        const int stage = k % kTtStages;
+        const int s = tile / tiles_per_stream;
+        const int t_begin = t_begin_ + (MAPPED ? sm_off(map, s, 2048) : 0);
+        const int tile_base = t_begin + (tile % tiles_per_stream) * kTtTile;
+        if (tid == 0) {
+            mbar_wait(&full[stage], (k / kTtStages) & 1);
+            tc_fence_after();
+            const uint32_t a0 = smem_u32(smem + stage * kTtStageBytes), w0 = smem_u32(sWt);
+#pragma unroll
+            for (int b = 0; b < 3; ++b) {
+                const uint32_t ab = a0 + (b == 0 ? 0 : (b == 1 ? 128 * 128 : 136 * 128));     // block 2 = stage rows 136..263
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                    mma_f16_ss(tmem_base + b * 16, umma_desc_sw128(ab + kk * 32), umma_desc_sw128(w0 + kk * 32), idesc, kk > 0 ? 1u : 0u);
+            }
+            mma_commit(mma_bar);
+        }
+        mbar_wait(mma_bar, k & 1);
+        tc_fence_after();
+        if (tid == 0) {                                // the MMAs have read the stage: refill it
+            const int nxt = tile + kTtStages * gridDim.x;
+            if (nxt < num_tiles) issue(nxt, stage);
+        }
+        {
+            // warps 0..3: block 0 (stage rows 0..127); warps 4..7: block 1 (128..255); warp 3 also the last 8 rows
+            // (256..263 = TMEM lanes 120..127 of block 2)
+            const int q = warp & 3, blk = warp >> 2;
+            uint32_t r[16];
+            tmem_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + blk * 16, r);
+            tmem_ld_wait();
+            const int row = blk * 128 + q * 32 + lane;
+#pragma unroll
+            for (int j = 0; j < 7; ++j) sP[j * kTtRows + row] = __uint_as_float(r[j]) + __uint_as_float(r[8 + j]);
+            if (warp == 3) {
+                tmem_ld16(tmem_base + (static_cast<uint32_t>(96) << 16) + 32, r);
+                tmem_ld_wait();
+                if (lane >= 24) {
+#pragma unroll
+                    for (int j = 0; j < 7; ++j) sP[j * kTtRows + 232 + lane] = __uint_as_float(r[j]) + __uint_as_float(r[8 + j]);
+                }
+            }
+        }
+        tc_fence_before();
+        __syncthreads();
+        {
+            const int t = tile_base + tid;             // stage row tid + j holds input row t - 3 + j
+            if (t < t_begin + n_out && t < T) {
+                float v = sP[tid];
+#pragma unroll
+                for (int j = 1; j < 7; ++j) v += sP[j * kTtRows + tid + j];
+                const float r = tanhf(v + bias);
+                const size_t o = static_cast<size_t>(s) * n_out + (t - t_begin);
+                pcm[o] = pcm16(r);
+                if (wave) wave[o] = r;
+            }
+        }
+        __syncthreads();                               // P and the accumulators are free for the next tile
+        tc_fence_after();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, kTtTmemCols);
+}
+
 template <typename InT, bool MAPPED>
 static void launch_tail_m(const InT* a, int S, int T, int t_begin, int n_out, const float* w, float bias, int16_t* pcm,
-                          float* wave, cudaStream_t st, const StreamMap& map) {
+                          float* wave, cudaStream_t st, const StreamMap& map, const CUtensorMap* tm128, const CUtensorMap* tm8) {
     if constexpr (sizeof(InT) == 2) {
         const int tps = (n_out + kTailTile - 1) / kTailTile;
         const long long tiles = static_cast<long long>(S) * tps;
-        const char* v1 = getenv("SNACB_TAIL_V1");          // A/B switch (tests): the per-warp-load kernel for every size
+        const char* v1 = getenv("SNACB_TAIL_V1");          // A/B switch (tests): 1 = the per-warp-load FFMA kernel for every
+                                                           // size, 2 = the FFMA kernels (bulk ring for large batches)
+        if (tm128 != nullptr && tm8 != nullptr && tiles > 0 && tiles < (1LL << 31) && !(v1 && (v1[0] == '1' || v1[0] == '2'))) {
+            static PerDeviceOnce once_tc;
+            int dev;
+            bool ok = true;
+            if (once_tc.needed(&dev)) {
+                ok = cudaFuncSetAttribute(k_tail_tc<InT, MAPPED>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTtSmem) == cudaSuccess;
+                if (ok) once_tc.done(dev);
+            }
+            if (ok) {
+                const int grid = tiles < 2 * 148 ? static_cast<int>(tiles) : 2 * 148;
+                k_tail_tc<InT, MAPPED><<<grid, 256, kTtSmem, st>>>(*tm128, *tm8, T, t_begin, n_out, w, bias, pcm, wave, tps,
+                                                                    static_cast<int>(tiles), map);
+                return;
+            }
+            (void)cudaGetLastError();
+        }
         if (tiles >= 2 * 148 && tiles < (1LL << 31) && !(v1 && v1[0] == '1')) {
             static PerDeviceOnce once;
             int dev;
@@ -636,18 +799,19 @@ static void launch_tail_m(const InT* a, int S, int T, int t_begin, int n_out, co
     dim3 grid((n_out + 255) / 256, S);
     k_tail<InT, MAPPED><<<grid, 256, 0, st>>>(a, T, t_begin, n_out, w, bias, pcm, wave, map);
 }
+// tm128 / tm8 (16-bit activations; null = the FFMA kernels): the input as [slot][T][64], 128B-swizzled, boxes (64, 128, 1) / (64, 8, 1)
 template <typename InT>
 void launch_tail(const InT* a, int S, int T, int t_begin, int n_out, const float* w, float bias, int16_t* pcm,
-                 float* wave, cudaStream_t st, const StreamMap& map) {
-    if (map.slot || map.off) launch_tail_m<InT, true>(a, S, T, t_begin, n_out, w, bias, pcm, wave, st, map);
-    else launch_tail_m<InT, false>(a, S, T, t_begin, n_out, w, bias, pcm, wave, st, map);
+                 float* wave, cudaStream_t st, const StreamMap& map, const CUtensorMap* tm128, const CUtensorMap* tm8) {
+    if (map.slot || map.off) launch_tail_m<InT, true>(a, S, T, t_begin, n_out, w, bias, pcm, wave, st, map, tm128, tm8);
+    else launch_tail_m<InT, false>(a, S, T, t_begin, n_out, w, bias, pcm, wave, st, map, tm128, tm8);
 }
 template void launch_tail<float>(const float*, int, int, int, int, const float*, float, int16_t*, float*, cudaStream_t,
-                                 const StreamMap&);
+                                 const StreamMap&, const CUtensorMap*, const CUtensorMap*);
 template void launch_tail<__nv_bfloat16>(const __nv_bfloat16*, int, int, int, int, const float*, float, int16_t*,
-                                         float*, cudaStream_t, const StreamMap&);
+                                         float*, cudaStream_t, const StreamMap&, const CUtensorMap*, const CUtensorMap*);
 template void launch_tail<__half>(const __half*, int, int, int, int, const float*, float, int16_t*, float*, cudaStream_t,
-                                  const StreamMap&);
+                                  const StreamMap&, const CUtensorMap*, const CUtensorMap*);
 
 // ----------------------------------------------------------------------------------------------
 template <typename T>

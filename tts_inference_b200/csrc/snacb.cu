@@ -847,10 +847,17 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
     const int T = Tin;                                   // 2048 * F samples
     const int t_begin = out_lo, n_out = out_hi - out_lo;
     if (plan && n_out <= 0) { h->streams += S; return 0; }
+    CUtensorMap mt128, mt8;                              // 16-bit activations: the tensor-core tail reads its rows by TMA
+    if (!f32) {
+        int rc = act_map(h, &mt128, cur, 64, T, S_buf, 128, 1, hk, 1);
+        if (rc) return rc;
+        rc = act_map(h, &mt8, cur, 64, T, S_buf, 8, 1, hk, 1);
+        if (rc) return rc;
+    }
     prof_begin(h, "tail", st);
     if (f32) launch_tail<float>(static_cast<const float*>(cur), S, T, t_begin, n_out, h->tail_w, h->tail_b, pcm, wave, st, smap);
-    else if (hk) launch_tail<__half>(static_cast<const __half*>(cur), S, T, t_begin, n_out, h->tail_w, h->tail_b, pcm, wave, st, smap);
-    else launch_tail<__nv_bfloat16>(static_cast<const __nv_bfloat16*>(cur), S, T, t_begin, n_out, h->tail_w, h->tail_b, pcm, wave, st, smap);
+    else if (hk) launch_tail<__half>(static_cast<const __half*>(cur), S, T, t_begin, n_out, h->tail_w, h->tail_b, pcm, wave, st, smap, &mt128, &mt8);
+    else launch_tail<__nv_bfloat16>(static_cast<const __nv_bfloat16*>(cur), S, T, t_begin, n_out, h->tail_w, h->tail_b, pcm, wave, st, smap, &mt128, &mt8);
     prof_end(h, st);
     h->launches++;
     CK(h, cudaGetLastError());
