@@ -129,6 +129,25 @@ def test_tensorcore_stage_taps(decoder, oracle_model):
         assert snr_db(r, taps[k]) >= 45.0, (k, snr_db(r, taps[k]))
 
 
+@pytest.mark.parametrize("prec", ["fp16", "bf16"])
+@pytest.mark.parametrize("B,F_", [(3, 4), (2, 5), (1, 13), (300, 4)])
+def test_noiseblock_tma_epilogue_is_bit_identical(monkeypatch, B, F_, prec):
+    """Block 0's NoiseBlock GEMM takes y in and puts x out by TMA through per-warp staging tiles (k_gemm_tc, whole 32-row
+    groups; F_ = 5 / 13 leave ragged groups on the per-row path); SNACB_NO_TMA_EPI=1 keeps every row on the per-row path.
+    The arithmetic is the same: identical bits in the NoiseBlock output and in the waveform."""
+    sd = synth.make_state_dict(0)
+    tokens = _cuda(synth.make_tokens(B, F_, seed=51 + F_))
+    kw = dict(raw_ids=True, seed=3, precision=prec, keep_taps=True, return_wave=True)
+    dec = SnacDecoder(sd, device=0)
+    _, wa = dec.decode(tokens, **kw)
+    ta = dec.taps()["b0.noise"].copy()
+    monkeypatch.setenv("SNACB_NO_TMA_EPI", "1")
+    _, wb = dec.decode(tokens, **kw)
+    tb = dec.taps()["b0.noise"]
+    assert np.isfinite(ta).all() and np.array_equal(ta, tb)
+    assert torch.equal(wa, wb)
+
+
 @pytest.mark.parametrize("B,F_", [(3, 4), (2, 5), (1, 13), (150, 4)])
 def test_block0_residual_by_identity_mma_against_v1_kernel(monkeypatch, B, F_):
     """Block 0's ResidualUnits (k_resunit2<512>) add the residual with an identity MMA on the 128B-swizzled x chunk and

@@ -60,6 +60,8 @@ struct GemmArgs {
     StreamMap map; int rpf; // streaming session: per-stream slot / row offset / origin; rpf = A (input) rows per frame
     int a_wrap;             // > 0: the A tensor holds only a_wrap 64-column chunks; K chunk kc reads chunk kc % a_wrap (bf16x3:
                             // A'' = [hi | lo | hi] and [a | a] are never materialised beyond [hi | lo] and [a])
+    int tma_epi;            // k_gemm_tc, NoiseBlock epilogue: 1 = y arrives and x leaves by TMA through per-warp staging tiles
+                            // (needs Tbox = 128, Wbox = 1, up = 1, BN = 256, 16-bit out; whole 32-row groups only)
     int mma_bf16;           // 1: the MMA reads its operands as bf16 whatever the storage type of resid / out is (the bf16x3
                             // path: fp16 storage, A and W pre-split into bf16 hi / lo column blocks, see snacb.cu)
     const void* resid;      // residual / y tensor, [S*Tin*up][Cout] (16-bit operand type on the tensor-core path)

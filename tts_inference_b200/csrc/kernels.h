@@ -68,7 +68,8 @@ void launch_to_f32(const T* in, float* out, size_t n, cudaStream_t st);
 int gemm_tc_block_n(const GemmArgs& a);   // column-tile width the tensor-core GEMM will use for this problem
 // half_fp16: 16-bit operand / storage type, 0 = bf16, 1 = fp16 (same tensor-core rate, fp32 accumulate)
 cudaError_t launch_gemm_tc(int epi, int half_fp16, int out_f32, const GemmArgs& a, const CUtensorMap& tmA,
-                           const CUtensorMap& tmW, int sm_count, cudaStream_t st);
+                           const CUtensorMap& tmW, const CUtensorMap& tmY, const CUtensorMap& tmO, int sm_count, cudaStream_t st);
+                           // tmY / tmO: GemmArgs::tma_epi (NoiseBlock epilogue by TMA), else any valid map
 cudaError_t launch_resunit_tc(int epi, int half_fp16, int x_f32, const ResUnitArgs& a, const CUtensorMap& tmW,
                               cudaStream_t st);
 cudaError_t init_tc_kernels();            // opt-in shared memory sizes

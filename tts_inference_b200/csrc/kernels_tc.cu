@@ -24,6 +24,13 @@ __device__ __forceinline__ uint8_t* align1024(uint8_t* p) {
     return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~static_cast<uintptr_t>(1023));
 }
 
+__device__ __forceinline__ float2 unpack2t(uint32_t v, const __half*) {
+    return __half22float2(*reinterpret_cast<const __half2*>(&v));
+}
+__device__ __forceinline__ float2 unpack2t(uint32_t v, const __nv_bfloat16*) {
+    return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v));
+}
+
 template <typename HT> struct HalfFmt;
 template <> struct HalfFmt<__half> { static constexpr uint32_t kFmt = 0; };
 template <> struct HalfFmt<__nv_bfloat16> { static constexpr uint32_t kFmt = 1; };
@@ -37,13 +44,21 @@ struct GemmTcCfg {
     static constexpr int kWBytes = BN * 128;
     static constexpr int kStageBytes = kABytes + kWBytes;
     static constexpr int kBarBytes = 256;
-    static constexpr int kSmem = kStages * kStageBytes + kBarBytes + 1024;
+    // NoiseBlock epilogue by TMA (BN = 256 only: one CTA per SM, 33 KB of shared memory to spare): per epilogue warp two
+    // 2 KB tiles for y (32 rows x 32 columns, 64B-swizzled, loaded two pieces ahead) and two for the output (a piece is
+    // written while the previous piece's store is still reading its tile)
+    static constexpr int kEpiYBufs = 2;
+    static constexpr int kEpiWarpBytes = (kEpiYBufs + 2) * 2048;
+    static constexpr int kEpiBytes = (BN == 256) ? 4 * kEpiWarpBytes : 0;
+    static constexpr int kOffEpi = kStages * kStageBytes + 1024;
+    static constexpr int kSmem = kStages * kStageBytes + (kEpiBytes ? 1024 + kEpiBytes : kBarBytes) + 1024;
     static constexpr int kTmemCols = 2 * BN;   // two accumulator stages
 };
 
 template <int BN, int EPI, typename HT, typename OutT>
 __global__ void __launch_bounds__(192, 1)
-k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const GemmArgs a,
+k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+          const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmO, const GemmArgs a,
           const int num_m_tiles, const int num_n_tiles) {
     using Cfg = GemmTcCfg<BN>;
     extern __shared__ uint8_t smem_raw[];
@@ -54,6 +69,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     uint64_t* tfull = bars + 2 * Cfg::kStages;
     uint64_t* tempty = tfull + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    uint64_t* ybar = bars + 16;                     // [4 epilogue warps][kEpiYBufs]: a y staging tile has landed (TMA epilogue)
+    constexpr bool kTmaEpi = (BN == 256 && EPI == EPI_NOISE && sizeof(OutT) == 2);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -61,8 +78,10 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmA);
         prefetch_tmap(&tmW);
+        if (kTmaEpi && a.tma_epi) { prefetch_tmap(&tmY); prefetch_tmap(&tmO); }
         for (int i = 0; i < Cfg::kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+        for (int i = 0; i < 4 * Cfg::kEpiYBufs; ++i) mbar_init(&ybar[i], 1);
         fence_barrier_init();
     }
     if (warp == 1) { tmem_alloc(tmem_slot, Cfg::kTmemCols); tmem_relinquish(); }
@@ -150,6 +169,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         if (EPI == EPI_NOISE && a.noise == nullptr)
             key = splitmix64(a.seed * 0x100000001B3ull + static_cast<unsigned long long>(100 + a.noise_stage));
         OutT* out = static_cast<OutT*>(a.out);
+        uint32_t yph = 0;                             // phase bits of this warp's two y barriers
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int mt = tile / num_n_tiles, nt = tile % num_n_tiles;
             const int s = (mt / tiles_t) * a.Wbox + r / a.Tbox;        // stream of the launch (noise key, row offset)
@@ -163,9 +183,76 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 nz = a.noise ? a.noise[static_cast<size_t>(s) * a.Tin + m]
                              : counter_normal(key, noise_counter(a.stream_keys ? a.stream_keys[s] : a.stream_offset + s,
                                                                  m + a.t0 + sm_org(a.map, s, a.rpf)));
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN);
+            if constexpr (kTmaEpi) {
+                // NoiseBlock epilogue by TMA (a.tma_epi: Tbox = 128, one stream per tile, up = 1).  Row-per-lane global
+                // accesses touch 32 cache lines per instruction and held this epilogue at ~1.9 k cycles per 32-column
+                // piece against a 4.3 k-cycle MMA per tile; here y arrives 64B-swizzled in the warp's own 2 KB tiles (two
+                // pieces ahead) and x leaves through a third by one TMA store per piece.  A 32-row group cut by the end
+                // of the row range keeps the per-row path below.
+                const int mw = t_lo + so + (mt % tiles_t) * a.Tbox + q * 32;
+                const int m_end = (a.Tin < t_lo + so + t_n) ? a.Tin : t_lo + so + t_n;
+                if (a.tma_epi && s < a.S && mw + 32 <= m_end) {
+                    const int wq = warp - 2;
+                    uint8_t* ystg = smem + Cfg::kOffEpi + wq * Cfg::kEpiWarpBytes;
+                    constexpr int NY = Cfg::kEpiYBufs;
+                    uint8_t* ostg = ystg + NY * 2048;
+                    auto yload = [&](int c) {
+                        if (lane == 0) {
+                            uint64_t* bar = &ybar[wq * NY + (c % NY)];
+                            mbar_expect_tx(bar, 2048);
+                            tma_load_3d(ystg + (c % NY) * 2048, &tmY, n0 + c * 32, mw, sl, bar);
+                        }
+                    };
+#pragma unroll
+                    for (int c = 0; c < NY; ++c) yload(c);
+                    mbar_wait(&tfull[as], aphase);
+                    tc_fence_after();
+                    const uint32_t sw = static_cast<uint32_t>((lane >> 1) & 3);
+#pragma unroll 1
+                    for (int c = 0; c < BN / 32; ++c) {
+                        const int buf = c % NY;
+                        uint32_t raw[32];
+                        tmem_ld32(taddr + c * 32, raw);
+                        mbar_wait(&ybar[wq * NY + buf], (yph >> buf) & 1u);
+                        yph ^= 1u << buf;
+                        uint4 yv[4];
+#pragma unroll
+                        for (int cc = 0; cc < 4; ++cc)
+                            yv[cc] = *reinterpret_cast<const uint4*>(ystg + buf * 2048 + lane * 64 + ((cc ^ sw) << 4));
+                        tmem_ld_wait();
+                        const uint32_t* yw = reinterpret_cast<const uint32_t*>(yv);
+                        uint32_t ow[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const float2 y = unpack2t(yw[j], static_cast<const HT*>(nullptr));
+                            ow[j] = pack2(fmaf(nz, __uint_as_float(raw[2 * j]), y.x), fmaf(nz, __uint_as_float(raw[2 * j + 1]), y.y),
+                                          static_cast<const OutT*>(nullptr));
+                        }
+                        if (lane == 0) bulk_wait_group_read<1>();        // the store before the previous one has read this tile
+                        __syncwarp();
+                        uint8_t* ob = ostg + (c & 1) * 2048;
+#pragma unroll
+                        for (int cc = 0; cc < 4; ++cc)
+                            *reinterpret_cast<uint4*>(ob + lane * 64 + ((cc ^ sw) << 4)) =
+                                make_uint4(ow[4 * cc], ow[4 * cc + 1], ow[4 * cc + 2], ow[4 * cc + 3]);
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_store_3d(&tmO, ob, n0 + c * 32, mw, sl);
+                            bulk_commit_group();
+                        }
+                        if (c + NY < BN / 32) yload(c + NY);             // every lane has read y tile `buf` (fence above)
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty[as]);
+                    if (++as == 2) { as = 0; aphase ^= 1u; }
+                    continue;
+                }
+            }
             mbar_wait(&tfull[as], aphase);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN);
 #pragma unroll 1
             for (int c = 0; c < BN / 32; ++c) {
                 uint32_t raw[32];
@@ -216,6 +303,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             if (lane == 0) mbar_arrive(&tempty[as]);
             if (++as == 2) { as = 0; aphase ^= 1u; }
         }
+        if (kTmaEpi && lane == 0) bulk_wait_group<0>();
     }
     tc_fence_before();
     __syncthreads();
@@ -230,8 +318,8 @@ int gemm_tc_block_n(const GemmArgs& a) {
 }
 
 template <int BN, int EPI, typename HT, typename OutT>
-static cudaError_t launch_gemm_tc_t(const GemmArgs& a, const CUtensorMap& tmA, const CUtensorMap& tmW, int sm_count,
-                                    cudaStream_t st) {
+static cudaError_t launch_gemm_tc_t(const GemmArgs& a, const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmY,
+                                    const CUtensorMap& tmO, int sm_count, cudaStream_t st) {
     using Cfg = GemmTcCfg<BN>;
     static PerDeviceOnce once;
     int dev_;
@@ -248,37 +336,39 @@ static cudaError_t launch_gemm_tc_t(const GemmArgs& a, const CUtensorMap& tmA, c
     const int ctas_per_sm = (BN == 256) ? 1 : 2;
     int grid = total < sm_count * ctas_per_sm ? total : sm_count * ctas_per_sm;
     if (grid < 1) grid = 1;
-    k_gemm_tc<BN, EPI, HT, OutT><<<grid, 192, Cfg::kSmem, st>>>(tmA, tmW, a, num_m, num_n);
+    k_gemm_tc<BN, EPI, HT, OutT><<<grid, 192, Cfg::kSmem, st>>>(tmA, tmW, tmY, tmO, a, num_m, num_n);
     return cudaGetLastError();
 }
 
 template <int EPI, typename HT, typename OutT>
-static cudaError_t launch_gemm_tc_e(const GemmArgs& a, const CUtensorMap& tmA, const CUtensorMap& tmW, int sm_count,
-                                    cudaStream_t st) {
+static cudaError_t launch_gemm_tc_e(const GemmArgs& a, const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmY,
+                                    const CUtensorMap& tmO, int sm_count, cudaStream_t st) {
     switch (gemm_tc_block_n(a)) {
-        case 256: return launch_gemm_tc_t<256, EPI, HT, OutT>(a, tmA, tmW, sm_count, st);
-        case 128: return launch_gemm_tc_t<128, EPI, HT, OutT>(a, tmA, tmW, sm_count, st);
-        default: return launch_gemm_tc_t<64, EPI, HT, OutT>(a, tmA, tmW, sm_count, st);
+        case 256: return launch_gemm_tc_t<256, EPI, HT, OutT>(a, tmA, tmW, tmY, tmO, sm_count, st);
+        case 128: return launch_gemm_tc_t<128, EPI, HT, OutT>(a, tmA, tmW, tmY, tmO, sm_count, st);
+        default: return launch_gemm_tc_t<64, EPI, HT, OutT>(a, tmA, tmW, tmY, tmO, sm_count, st);
     }
 }
 
 template <typename HT>
 static cudaError_t launch_gemm_tc_h(int epi, int out_f32, const GemmArgs& a, const CUtensorMap& tmA,
-                                    const CUtensorMap& tmW, int sm_count, cudaStream_t st) {
-    if (epi == EPI_BIAS) return launch_gemm_tc_e<EPI_BIAS, HT, HT>(a, tmA, tmW, sm_count, st);
-    if (epi == EPI_BIAS_SNAKE) return launch_gemm_tc_e<EPI_BIAS_SNAKE, HT, HT>(a, tmA, tmW, sm_count, st);
+                                    const CUtensorMap& tmW, const CUtensorMap& tmY, const CUtensorMap& tmO, int sm_count,
+                                    cudaStream_t st) {
+    if (epi == EPI_BIAS) return launch_gemm_tc_e<EPI_BIAS, HT, HT>(a, tmA, tmW, tmY, tmO, sm_count, st);
+    if (epi == EPI_BIAS_SNAKE) return launch_gemm_tc_e<EPI_BIAS_SNAKE, HT, HT>(a, tmA, tmW, tmY, tmO, sm_count, st);
     if (epi == EPI_NOISE) {
-        if (out_f32) return launch_gemm_tc_e<EPI_NOISE, HT, float>(a, tmA, tmW, sm_count, st);
-        return launch_gemm_tc_e<EPI_NOISE, HT, HT>(a, tmA, tmW, sm_count, st);
+        if (out_f32) return launch_gemm_tc_e<EPI_NOISE, HT, float>(a, tmA, tmW, tmY, tmO, sm_count, st);
+        return launch_gemm_tc_e<EPI_NOISE, HT, HT>(a, tmA, tmW, tmY, tmO, sm_count, st);
     }
-    if (epi == EPI_RES) return launch_gemm_tc_e<EPI_RES, HT, HT>(a, tmA, tmW, sm_count, st);
-    if (epi == EPI_RES_SNAKE) return launch_gemm_tc_e<EPI_RES_SNAKE, HT, HT>(a, tmA, tmW, sm_count, st);
+    if (epi == EPI_RES) return launch_gemm_tc_e<EPI_RES, HT, HT>(a, tmA, tmW, tmY, tmO, sm_count, st);
+    if (epi == EPI_RES_SNAKE) return launch_gemm_tc_e<EPI_RES_SNAKE, HT, HT>(a, tmA, tmW, tmY, tmO, sm_count, st);
     return cudaErrorInvalidValue;
 }
+// tmY / tmO (GemmArgs::tma_epi, NoiseBlock only; else any valid map): resid and out as [slot][Tin][Cout], box (32, 32, 1), 64B-swizzled
 cudaError_t launch_gemm_tc(int epi, int half_fp16, int out_f32, const GemmArgs& a, const CUtensorMap& tmA,
-                           const CUtensorMap& tmW, int sm_count, cudaStream_t st) {
-    return half_fp16 ? launch_gemm_tc_h<__half>(epi, out_f32, a, tmA, tmW, sm_count, st)
-                     : launch_gemm_tc_h<__nv_bfloat16>(epi, out_f32, a, tmA, tmW, sm_count, st);
+                           const CUtensorMap& tmW, const CUtensorMap& tmY, const CUtensorMap& tmO, int sm_count, cudaStream_t st) {
+    return half_fp16 ? launch_gemm_tc_h<__half>(epi, out_f32, a, tmA, tmW, tmY, tmO, sm_count, st)
+                     : launch_gemm_tc_h<__nv_bfloat16>(epi, out_f32, a, tmA, tmW, tmY, tmO, sm_count, st);
 }
 
 // =================================================================================================

@@ -575,7 +575,7 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
             if (rc) return rc;
             rc = weight_map(h, &mw, Wx3, Wrows, Wcols, gemm_tc_block_n(a), 0);
             if (rc) return rc;
-            cudaError_t le = launch_gemm_tc(epi, 1, 0, a, ma, *mw, h->sm_count, st);     // fp16 resid / out
+            cudaError_t le = launch_gemm_tc(epi, 1, 0, a, ma, *mw, ma, ma, h->sm_count, st);     // fp16 resid / out
             prof_end(h, st);
             CK(h, le);
             return 0;
@@ -584,8 +584,18 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
         if (rc) return rc;
         rc = weight_map(h, &mw, Wh[hk], Wrows, Wcols, gemm_tc_block_n(a), hk);
         if (rc) return rc;
+        // NoiseBlock of block 0 (the blocks without the fused chain): y in and x out by TMA through per-warp staging tiles
+        CUtensorMap my = ma, mo = ma;
+        if (epi == EPI_NOISE && !out_f32 && a.Tbox == 128 && a.Wbox == 1 && a.up == 1 && gemm_tc_block_n(a) == 256 &&
+            !getenv("SNACB_NO_TMA_EPI")) {
+            rc = act_map(h, &my, a.resid, a.Cout, a.Tin, S_buf, 32, 1, hk, 2);
+            if (rc) return rc;
+            rc = act_map(h, &mo, a.out, a.Cout, a.Tin, S_buf, 32, 1, hk, 2);
+            if (rc) return rc;
+            a.tma_epi = 1;
+        }
         prof_begin(h, pname, st);
-        cudaError_t le = launch_gemm_tc(epi, hk, out_f32 ? 1 : 0, a, ma, *mw, h->sm_count, st);
+        cudaError_t le = launch_gemm_tc(epi, hk, out_f32 ? 1 : 0, a, ma, *mw, my, mo, h->sm_count, st);
         prof_end(h, st);
         CK(h, le);
         return 0;
