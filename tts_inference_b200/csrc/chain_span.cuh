@@ -18,6 +18,26 @@ namespace snacb {
 __device__ __forceinline__ __half2 cs_h2(uint32_t v) { return *reinterpret_cast<const __half2*>(&v); }
 __device__ __forceinline__ uint32_t cs_u32(__half2 v) { return *reinterpret_cast<const uint32_t*>(&v); }
 
+// The TMEM-drain epilogues of the chain kernels are bound by the XU pipe (32 MUFU.SIN per 32 x 32 piece): the column pairs
+// selected by kEpiPolyMask take their sin^2 from the FMA pipe instead.
+// x + sin^2 x on a half2 without the XU pipe: r = x / pi - rint(x / pi) by the magic-number trick, sin^2(pi r) as a
+// degree-4 odd-free minimax polynomial in r^2 (|r| <= 1/2); 9 FMA-pipe instructions with immediate operands
+__device__ __forceinline__ __half2 snake_h2_poly(__half2 xh) {
+    const __half2 kInvPi = __float2half2_rn(0.318309886f), kMagic = __float2half2_rn(1536.f);
+    const __half2 m = __hfma2(xh, kInvPi, kMagic);
+    const __half2 n = __hsub2(m, kMagic);
+    const __half2 r = __hfma2(xh, kInvPi, __hneg2(n));
+    const __half2 u = __hmin2(__hmul2(r, r), __float2half2_rn(0.25f));      // |x| >= 1608 (no phase left in fp16): stay finite
+    __half2 p = __hfma2(__float2half2_rn(-22.99092533f), u, __float2half2_rn(41.29496355f));
+    p = __hfma2(p, u, __float2half2_rn(-32.35387252f));
+    p = __hfma2(p, u, __float2half2_rn(9.86667475f));
+    return __hfma2(p, u, xh);
+}
+#ifndef SNACB_EPI_POLY_MASK
+#define SNACB_EPI_POLY_MASK 0x8888u
+#endif
+constexpr unsigned kEpiPolyMask = SNACB_EPI_POLY_MASK;   // bit i: column pair i of a 32-column piece takes the polynomial
+
 // fp16 math.  FOLD: xs / w / bd carry the alpha scalings (kernels_chain.cu), snake2 = a + sin^2 a on a = alpha2 * conv.
 // !FOLD: al2 / ia2 = alpha2, 1 / (alpha2 + 1e-9) of the channel pair; Snake in fp32.
 template <int NOUT, bool FOLD>

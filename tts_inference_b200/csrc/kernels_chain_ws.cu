@@ -368,8 +368,20 @@ k_chain_ws(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUte
                                     const float4 bb = *reinterpret_cast<const float4*>(vb + cg * 32 + j);
                                     v0 = fmaf(v0, al.x, bb.x); v1 = fmaf(v1, al.y, bb.y); v2 = fmaf(v2, al.z, bb.z); v3 = fmaf(v3, al.w, bb.w);
                                 }
-                                const float s0 = __sinf(v0), s1 = __sinf(v1), s2 = __sinf(v2), s3 = __sinf(v3);
-                                v0 = fmaf(s0, s0, v0); v1 = fmaf(s1, s1, v1); v2 = fmaf(s2, s2, v2); v3 = fmaf(s3, s3, v3);
+                                // the same pipe split as k_chain's epilogue (kEpiPolyMask), so that the two kernels stay bit-identical
+                                if ((kEpiPolyMask >> (j / 2)) & 1u) {
+                                    o[j / 2] = cs_u32(snake_h2_poly(__floats2half2_rn(v0, v1)));
+                                } else {
+                                    const float s0 = __sinf(v0), s1 = __sinf(v1);
+                                    o[j / 2] = pack2(fmaf(s0, s0, v0), fmaf(s1, s1, v1), tag);
+                                }
+                                if ((kEpiPolyMask >> (j / 2 + 1)) & 1u) {
+                                    o[j / 2 + 1] = cs_u32(snake_h2_poly(__floats2half2_rn(v2, v3)));
+                                } else {
+                                    const float s2 = __sinf(v2), s3 = __sinf(v3);
+                                    o[j / 2 + 1] = pack2(fmaf(s2, s2, v2), fmaf(s3, s3, v3), tag);
+                                }
+                                continue;
                             } else {
                                 if (MODE != WS_NOISE) {
                                     const float4 bb = *reinterpret_cast<const float4*>(vb + cg * 32 + j);
