@@ -172,6 +172,23 @@ def test_block0_residual_by_identity_mma_against_v1_kernel(monkeypatch, B, F_):
         assert np.abs(a - b).max() <= 2.0 ** -6 * max(1.0, np.abs(b).max()), (k, np.abs(a - b).max())
 
 
+def test_cta_pair_convtranspose_experiment(monkeypatch):
+    """k_convt_ph2 (cta_group::2 CTA pairs; SNACB_EXPERIMENTS build only, measured slower than k_convt_ph): block 2's
+    ConvTranspose output against k_convt_ph's on the same input -- the same MMAs' worth of fp32 sums in the same order."""
+    from tts_inference_b200 import _lib
+    if not hasattr(_lib.load(), "snacb_debug_chain_ws_spans") or os.environ.get("SNACB_EXPERIMENTS") != "1":
+        pytest.skip("k_convt_ph2 is an experiment: built only with SNACB_EXPERIMENTS=1")
+    sd = synth.make_state_dict(0)
+    tokens = _cuda(synth.make_tokens(37, 5, seed=13))
+    dec = SnacDecoder(sd, device=0)
+    dec.decode(tokens, raw_ids=True, seed=2, keep_taps=True)
+    a = dec.taps()["b2.convt"].copy()
+    monkeypatch.setenv("SNACB_CONVT_2CTA", "1")
+    dec.decode(tokens, raw_ids=True, seed=2, keep_taps=True)
+    b = dec.taps()["b2.convt"]
+    assert np.isfinite(a).all() and np.array_equal(a, b)
+
+
 @pytest.mark.parametrize("prec", ["fp16", "bf16"])
 @pytest.mark.parametrize("B,F_", [(3, 4), (2, 5), (1, 13)])
 def test_resident_weight_convtranspose_against_generic_gemm(monkeypatch, B, F_, prec):

@@ -86,6 +86,8 @@ int convt_res_box_rows();             // activation tensor-map box = (64, box_ro
 cudaError_t launch_convt_res(int half_fp16, const GemmArgs& a, const CUtensorMap& tmA, const CUtensorMap& tmW,
                              const CUtensorMap& tmO, int sm_count, cudaStream_t st);   // tmO: output box (64, 128*s, 1)
 
+cudaError_t launch_convt_ph2(int half_fp16, const GemmArgs& a, const CUtensorMap& tmA, const CUtensorMap& tmW,
+                             const CUtensorMap& tmO, int sm_count, cudaStream_t st);   // CTA pairs (cta_group::2); tmW box (64, Cout / 2)
 bool convt_ph_supported(int Cin, int Cout, int s);   // block 2: one output phase's weights resident per CTA group
 cudaError_t launch_convt_ph(int half_fp16, const GemmArgs& a, const CUtensorMap& tmA, const CUtensorMap& tmW,
                             const CUtensorMap& tmO, int sm_count, cudaStream_t st);

@@ -658,7 +658,16 @@ int run_group(snacb_handle h, const int32_t* tok, int S, int tok_stride, int F, 
                 a.seed = seed; a.stream_offset = stream_offset; a.stream_keys = stream_keys; a.Tbox = 128; a.Wbox = 1;
                 a.map = smap; a.rpf = Tin / F;
                 prof_begin(h, nm, st);
-                cudaError_t le = launch_convt_ph(hk, a, ma, *mw, mo, h->sm_count, st);
+                cudaError_t le;
+#ifdef SNACB_EXPERIMENTS
+                if (getenv("SNACB_CONVT_2CTA")) {                 // experiment (measured slower): CTA pairs, half of the weights per CTA
+                    const CUtensorMap* mw2;
+                    rc = weight_map(h, &mw2, b.ct_h[hk], b.s * b.Cout, 2 * b.Cin, b.Cout / 2, hk);
+                    if (rc) return rc;
+                    le = launch_convt_ph2(hk, a, ma, *mw2, mo, h->sm_count, st);
+                } else
+#endif
+                    le = launch_convt_ph(hk, a, ma, *mw, mo, h->sm_count, st);
                 prof_end(h, st);
                 CK(h, le);
                 h->launches++;
