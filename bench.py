@@ -565,7 +565,7 @@ def main():
                 "share_of_step": topc["share"], "avg_launch_ms": topc["avg_launch_ms"], "peak_source": peaks["source"],
                 "note": "algorithmic FLOPs of the fused NoiseBlock + 3 ResidualUnits over the CUDA-event time of the k_chain launches; "
                         "the kernel is bound by the MUFU (XU) pipe and issue slots of its Snake / depthwise prologue, not by the "
-                        "tensor pipe (ncu: XU 35-51 %, issue 49-67 %, tensor 7-18 %, DRAM 6-12 %; DESIGN.md section 6)",
+                        "tensor pipe (ncu: XU 28-43 %, FMA 35-50 %, issue 46-64 %, tensor 7-18 %, DRAM 6-12 %; DESIGN.md sections 6.1, 6.2)",
                 "whole_step": {"achieved": FLOP_PER_WINDOW * B * world * args.steps / (dev_ms * 1e-3) / 1e12 / world,
                                "frac": FLOP_PER_WINDOW * B * args.steps / (dev_ms * 1e-3) / 1e12 / peaks["bf16_tflops_sustained"]}}
         cpu = None
