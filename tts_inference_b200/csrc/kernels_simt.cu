@@ -633,7 +633,7 @@ constexpr int kTtOffW = kTtStages * kTtStageBytes; // [16 n][64 k] weights, 128B
 constexpr int kTtOffP = kTtOffW + 2048;            // P tap-major: [7][kTtRows] fp32
 constexpr int kTtOffBar = kTtOffP + 7 * kTtRows * 4;
 constexpr int kTtSmem = kTtOffBar + 64 + 1024;
-constexpr int kTtTmemCols = 64;                    // three blocks x 16 columns (power of two >= 48)
+constexpr int kTtTmemCols = 128;                   // two accumulator stages of three blocks x 16 columns (64 columns each)
 
 template <typename InT, bool MAPPED>
 __global__ void __launch_bounds__(256, 2)
@@ -647,14 +647,14 @@ k_tail_tc(const __grid_constant__ CUtensorMap tm128, const __grid_constant__ CUt
     uint8_t* sWt = smem + kTtOffW;
     float* sP = reinterpret_cast<float*>(smem + kTtOffP);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + kTtOffBar);      // [kTtStages]
-    uint64_t* mma_bar = full + kTtStages;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_bar + 1);
+    uint64_t* mma_bar = full + kTtStages;                                // [2] by tile parity
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_bar + 2);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     if (tid == 0) {
         prefetch_tmap(&tm128); prefetch_tmap(&tm8);
         for (int i = 0; i < kTtStages; ++i) mbar_init(&full[i], 1);
-        mbar_init(mma_bar, 1);
+        mbar_init(&mma_bar[0], 1); mbar_init(&mma_bar[1], 1);
         fence_barrier_init();
     }
     if (warp == 1) { tmem_alloc(tmem_slot, kTtTmemCols); tmem_relinquish(); }
@@ -690,43 +690,50 @@ k_tail_tc(const __grid_constant__ CUtensorMap tm128, const __grid_constant__ CUt
             if (tile < num_tiles) issue(tile, k);
         }
     constexpr uint32_t idesc = umma_idesc_f16(128, 16, std::is_same<InT, __half>::value ? 0u : 1u);
+    // the MMAs of tile k (thread 0): into accumulator stage k & 1, completion on mma_bar[k & 1].  They are issued one tile
+    // ahead -- tile k + 1's while tile k is drained and summed -- so that their latency is off the critical path
+    auto issue_mma = [&](int kq) {
+        const int stage = kq % kTtStages;
+        mbar_wait(&full[stage], (kq / kTtStages) & 1);
+        tc_fence_after();
+        const uint32_t a0 = smem_u32(smem + stage * kTtStageBytes), w0 = smem_u32(sWt);
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+            const uint32_t ab = a0 + (b == 0 ? 0 : (b == 1 ? 128 * 128 : 136 * 128));     // block 2 = stage rows 136..263
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+                mma_f16_ss(tmem_base + (kq & 1) * 64 + b * 16, umma_desc_sw128(ab + kk * 32), umma_desc_sw128(w0 + kk * 32), idesc,
+                           kk > 0 ? 1u : 0u);
+        }
+        mma_commit(&mma_bar[kq & 1]);
+    };
+    if (tid == 0 && static_cast<int>(blockIdx.x) < num_tiles) issue_mma(0);
     int k = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++k) {
         const int stage = k % kTtStages;
         const int s = tile / tiles_per_stream;
         const int t_begin = t_begin_ + (MAPPED ? sm_off(map, s, 2048) : 0);
         const int tile_base = t_begin + (tile % tiles_per_stream) * kTtTile;
-        if (tid == 0) {
-            mbar_wait(&full[stage], (k / kTtStages) & 1);
-            tc_fence_after();
-            const uint32_t a0 = smem_u32(smem + stage * kTtStageBytes), w0 = smem_u32(sWt);
-#pragma unroll
-            for (int b = 0; b < 3; ++b) {
-                const uint32_t ab = a0 + (b == 0 ? 0 : (b == 1 ? 128 * 128 : 136 * 128));     // block 2 = stage rows 136..263
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk)
-                    mma_f16_ss(tmem_base + b * 16, umma_desc_sw128(ab + kk * 32), umma_desc_sw128(w0 + kk * 32), idesc, kk > 0 ? 1u : 0u);
-            }
-            mma_commit(mma_bar);
-        }
-        mbar_wait(mma_bar, k & 1);
+        mbar_wait(&mma_bar[k & 1], (k >> 1) & 1);
         tc_fence_after();
-        if (tid == 0) {                                // the MMAs have read the stage: refill it
-            const int nxt = tile + kTtStages * gridDim.x;
+        if (tid == 0) {
+            const int nxt = tile + kTtStages * gridDim.x;     // the MMAs have read the stage: refill it
             if (nxt < num_tiles) issue(nxt, stage);
+            if (tile + static_cast<int>(gridDim.x) < num_tiles) issue_mma(k + 1);   // stage (k + 1) & 1 was drained in iteration k - 1
         }
+        const uint32_t tacc = tmem_base + (k & 1) * 64;
         {
             // warps 0..3: block 0 (stage rows 0..127); warps 4..7: block 1 (128..255); warp 3 also the last 8 rows
             // (256..263 = TMEM lanes 120..127 of block 2)
             const int q = warp & 3, blk = warp >> 2;
             uint32_t r[16];
-            tmem_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + blk * 16, r);
+            tmem_ld16(tacc + (static_cast<uint32_t>(q * 32) << 16) + blk * 16, r);
             tmem_ld_wait();
             const int row = blk * 128 + q * 32 + lane;
 #pragma unroll
             for (int j = 0; j < 7; ++j) sP[j * kTtRows + row] = __uint_as_float(r[j]) + __uint_as_float(r[8 + j]);
             if (warp == 3) {
-                tmem_ld16(tmem_base + (static_cast<uint32_t>(96) << 16) + 32, r);
+                tmem_ld16(tacc + (static_cast<uint32_t>(96) << 16) + 32, r);
                 tmem_ld_wait();
                 if (lane >= 24) {
 #pragma unroll
